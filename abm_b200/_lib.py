@@ -1,0 +1,101 @@
+"""ctypes binding of libabm_b200.so (C ABI declared in include/abm_b200.h).
+
+There is no CPU fallback: if the library is missing, or no sm_100 device is
+usable, the calls raise -- they never route to another implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libabm_b200.so")
+
+ABM_OK = 0
+BOUNDARY_WALLS = 0
+BOUNDARY_INFINITE = 1
+VF_EXACT_FIXUP = 1 << 0
+VF_KEEP_FIELDS = 1 << 1
+VF_KEEP_TERMS = 1 << 2
+VF_NPARAM = 6
+
+
+class AbmError(RuntimeError):
+    def __init__(self, code, where, detail):
+        super().__init__(f"{where} failed with code {code}: {detail}")
+        self.code = code
+
+
+class VFConfig(C.Structure):
+    """abm_vf_config_t"""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_replicates", C.c_int32), ("n_agents", C.c_int32),
+        ("resolution", C.c_int32), ("fov_px0", C.c_int32), ("fov_px1", C.c_int32),
+        ("boundary", C.c_int32), ("limit_movement", C.c_int32),
+        ("width", C.c_float), ("height", C.c_float), ("window_pad", C.c_float),
+        ("max_vel", C.c_float), ("max_th", C.c_float), ("flags", C.c_uint32),
+        ("tile_begin", C.c_int32), ("tile_count", C.c_int32),
+    ]
+
+
+class VFProjArgs(C.Structure):
+    """abm_vf_proj_args_t"""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("resolution", C.c_int32),
+        ("fov0", C.c_double), ("fov1", C.c_double),
+        ("x", C.c_double), ("y", C.c_double), ("radius", C.c_double), ("orientation", C.c_double),
+        ("n_obj", C.c_int32),
+        ("obj_x", C.POINTER(C.c_double)), ("obj_y", C.POINTER(C.c_double)), ("obj_size", C.POINTER(C.c_double)),
+        ("boundary", C.c_int32),
+        ("arena_width", C.c_double), ("arena_height", C.c_double), ("vision_range", C.c_double),
+    ]
+
+
+# every symbol include/abm_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "abm_version": (C.c_int, []),
+    "abm_last_error": (C.c_char_p, []),
+    "abm_device_count": (C.c_int, []),
+    "abm_field_words": (C.c_int, [C.c_int]),
+    "abm_vf_create": (C.c_int, [C.POINTER(VFConfig), C.c_int, C.POINTER(_P)]),
+    "abm_destroy": (C.c_int, [_P]),
+    "abm_vf_set_params": (C.c_int, [_P, _P, C.c_int]),
+    "abm_vf_set_agent_overrides": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "abm_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "abm_get_state": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
+    "abm_vf_step": (C.c_int, [_P, C.c_int, _P]),
+    "abm_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
+    "abm_vf_get_terms": (C.c_int, [_P, _P, C.c_int, _P]),
+    "abm_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
+    "abm_vf_record_table": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
+    "abm_synchronize": (C.c_int, [_P, _P]),
+    "abm_vf_projection_field": (C.c_int, [C.POINTER(VFProjArgs), _P]),
+    "abm_vf_flocking_terms": (C.c_int, [_P, C.c_int, C.c_double, _P, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(abm_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)   # AttributeError here == header / library skew
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, where):
+    if rc != ABM_OK:
+        detail = load().abm_last_error()
+        raise AbmError(rc, where, detail.decode() if detail else "")

@@ -1,0 +1,483 @@
+// C ABI of libabm_b200.so (declared in include/abm_b200.h): engine life cycle, state
+// transfer and launches of the fused kernels.  No CPU fallback: without a usable device
+// every entry point fails with ABM_E_NO_DEVICE / ABM_E_CUDA.
+#include "../../include/abm_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "abm_common.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define ABM_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      char _b[512];                                                                            \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? ABM_E_NO_DEVICE : ABM_E_CUDA, _b); \
+    }                                                                                          \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    n = count;
+    return cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * (count ? count : 1));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+};
+
+// Bin / integration-grid constants shared by the engine and the stateless entry points.
+struct GridConsts {
+  int R = 0, W = 0;
+  float inv_step, t_frac; int k_off;
+  float y_scale, tau_k, tau_h_abs, tau_h_rel, ca_guard, cull_scale;
+  double lin_step, dphi;
+  int phi_ok;
+  std::vector<abm::PhiLut> lut;   // R + 1 entries
+};
+
+// numpy.arange(-pi, pi, 2pi/R) as numpy computes it: length ceil((stop-start)/step),
+// element i = start + i * delta with delta = (start + step) - start  (vf_agent.py:44).
+void build_grid(int R, GridConsts& g) {
+  g.R = R;
+  g.W = (R + 31) / 32;
+  const double PI = ABM_PI_D;
+  const double two_pi = 2.0 * PI;
+  g.lin_step = two_pi / (double)(R - 1);          // numpy.linspace: step = (stop - start) / (num - 1)
+  g.inv_step = (float)((double)(R - 1) / two_pi);
+  if (R % 2 == 0) { g.t_frac = 0.0f; g.k_off = R / 2 - 1; }
+  else            { g.t_frac = 0.5f; g.k_off = (R - 3) / 2; }
+  g.y_scale = (float)((double)R / two_pi);
+  // fp32 error bounds of the pair path, in bins (DESIGN.md "guard bands"): angle error
+  // <= 2.0e-6 rad -> 2.0e-6 * R / 2pi bins, plus rounding of t (|t| <= R/2).
+  g.tau_k = (float)(2.0e-6 * (double)R / two_pi + 2.5e-7 * (double)R + 1e-5);
+  g.tau_h_abs = 2.0e-5f;
+  g.tau_h_rel = 3.0e-6f;
+  g.ca_guard = (float)(PI - 4.0e-6);
+  const double tn = std::tan(two_pi / (double)R);
+  g.cull_scale = (float)((1.0 / (tn * tn)) * (1.0 + 1e-4));
+  const double step = two_pi / (double)R;
+  g.dphi = step;
+  const double start = -PI;
+  const long long len = (long long)std::ceil((PI - start) / step);
+  g.phi_ok = (len == (long long)R) ? 1 : 0;
+  const double delta = (start + step) - start;
+  g.lut.assign((size_t)R + 1, abm::PhiLut{0, 0, 0, 0});
+  long double pc = 0.0L, ps = 0.0L;
+  for (int k = 0; k <= R; ++k) {
+    const double phi = start + (double)k * delta;
+    g.lut[k].c = std::cos(phi);
+    g.lut[k].s = std::sin(phi);
+    g.lut[k].pc = (double)pc;
+    g.lut[k].ps = (double)ps;
+    pc += (long double)g.lut[k].c;
+    ps += (long double)g.lut[k].s;
+  }
+}
+
+}  // namespace
+
+struct abm_engine {
+  abm_vf_config_t cfg;
+  int device = 0;
+  int tile_begin = 0, tile_count = 0;
+  GridConsts grid;
+  size_t n_total = 0;   // B * N
+  size_t n_tile = 0;    // B * tile_count
+  DevBuf<float4> rec[2];
+  int cur = 0;          // rec[cur] is the state of the current step
+  DevBuf<float> theta, vel, stage_x, stage_y, stage_r;
+  DevBuf<double> params;
+  int n_param_sets = 1;
+  DevBuf<float> ov_alp0, ov_bet0, ov_v0;
+  bool has_alp0 = false, has_bet0 = false, has_v0 = false;
+  DevBuf<abm::PhiLut> lut;
+  DevBuf<uint32_t> fields;
+  DevBuf<double> terms;
+  DevBuf<unsigned long long> counters;
+  bool state_set = false;
+  unsigned long long launches = 0;
+};
+
+namespace {
+
+int copy_in(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
+  ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return ABM_OK;
+}
+int copy_out(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
+  ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  return ABM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int abm_version(void) { return ABM_B200_VERSION; }
+
+const char* abm_last_error(void) { return g_last_error.c_str(); }
+
+int abm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int abm_field_words(int resolution) { return (resolution + 31) / 32; }
+
+int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
+  if (!cfg || !out) return fail(ABM_E_INVALID, "abm_vf_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(abm_vf_config_t))
+    return fail(ABM_E_INVALID, "abm_vf_create: struct_size mismatch (header / library version skew)");
+  if (cfg->n_replicates < 1 || cfg->n_agents < 1) return fail(ABM_E_INVALID, "abm_vf_create: B, N must be >= 1");
+  if (cfg->n_agents >= (1 << 24)) return fail(ABM_E_INVALID, "abm_vf_create: N must be < 2^24");
+  if (cfg->resolution < 8 || cfg->resolution > 65535)
+    return fail(ABM_E_INVALID, "abm_vf_create: resolution must be in [8, 65535]");
+  if (cfg->boundary != ABM_BOUNDARY_WALLS && cfg->boundary != ABM_BOUNDARY_INFINITE)
+    return fail(ABM_E_INVALID, "abm_vf_create: boundary must be walls (0) or infinite (1)");
+  int tb = cfg->tile_begin, tc = cfg->tile_count;
+  if (tc == 0) { tb = 0; tc = cfg->n_agents; }
+  if (tb < 0 || tc < 1 || tb + tc > cfg->n_agents) return fail(ABM_E_INVALID, "abm_vf_create: bad agent tile");
+  int ndev = 0;
+  ABM_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1 || device < 0 || device >= ndev) return fail(ABM_E_NO_DEVICE, "abm_vf_create: no such CUDA device");
+  ABM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ABM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(ABM_E_NO_DEVICE, "abm_vf_create: device is not sm_100 (the kernels are built for sm_100a only)");
+
+  abm_engine* e = new (std::nothrow) abm_engine();
+  if (!e) return fail(ABM_E_INVALID, "abm_vf_create: out of host memory");
+  e->cfg = *cfg;
+  e->device = device;
+  e->tile_begin = tb;
+  e->tile_count = tc;
+  build_grid(cfg->resolution, e->grid);
+  const size_t smem = abm::vf_step_smem_bytes(abm::vf_step_threads(tc), e->grid.W);
+  if (smem > (size_t)prop.sharedMemPerBlockOptin) {
+    delete e;
+    return fail(ABM_E_INVALID, "abm_vf_create: resolution too large for shared memory");
+  }
+  e->n_total = (size_t)cfg->n_replicates * cfg->n_agents;
+  e->n_tile = (size_t)cfg->n_replicates * tc;
+  cudaError_t err = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+  A(e->rec[0].alloc(e->n_total));
+  A(e->rec[1].alloc(e->n_total));
+  A(e->theta.alloc(e->n_total));
+  A(e->vel.alloc(e->n_total));
+  A(e->stage_x.alloc(e->n_total));
+  A(e->stage_y.alloc(e->n_total));
+  A(e->stage_r.alloc(e->n_total));
+  A(e->params.alloc((size_t)cfg->n_replicates * ABM_VF_NPARAM));
+  A(e->lut.alloc(e->grid.lut.size()));
+  A(e->counters.alloc(4));
+  if (cfg->flags & ABM_VF_KEEP_FIELDS) A(e->fields.alloc(e->n_tile * e->grid.W));
+  if (cfg->flags & ABM_VF_KEEP_TERMS) A(e->terms.alloc(e->n_tile * 6));
+  if (err == cudaSuccess) err = cudaMemcpy(e->lut.p, e->grid.lut.data(), sizeof(abm::PhiLut) * e->grid.lut.size(),
+                                           cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemset(e->counters.p, 0, 4 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(e->rec[0].p, 0, sizeof(float4) * e->n_total);
+  if (err == cudaSuccess) err = cudaMemset(e->rec[1].p, 0, sizeof(float4) * e->n_total);
+  const double defaults[ABM_VF_NPARAM] = {0.1, 1.0, 1.0, 0.09, 1.0, 0.09};   // vf_params.py:12-19 defaults
+  if (err == cudaSuccess) err = cudaMemcpy(e->params.p, defaults, sizeof(defaults), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    std::string m = std::string("abm_vf_create: ") + cudaGetErrorString(err);
+    abm_destroy(e);
+    return fail(ABM_E_CUDA, m);
+  }
+  *out = e;
+  return ABM_OK;
+}
+
+int abm_destroy(abm_engine_t* e) {
+  if (!e) return ABM_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  e->rec[0].release(); e->rec[1].release();
+  e->theta.release(); e->vel.release();
+  e->stage_x.release(); e->stage_y.release(); e->stage_r.release();
+  e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
+  e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
+  delete e;
+  return ABM_OK;
+}
+
+int abm_vf_set_params(abm_engine_t* e, const double* params, int n_sets) {
+  if (!e || !params) return fail(ABM_E_INVALID, "abm_vf_set_params: null argument");
+  if (n_sets != 1 && n_sets != e->cfg.n_replicates)
+    return fail(ABM_E_INVALID, "abm_vf_set_params: n_sets must be 1 or n_replicates");
+  ABM_CUDA(cudaSetDevice(e->device));
+  ABM_CUDA(cudaMemcpy(e->params.p, params, sizeof(double) * ABM_VF_NPARAM * n_sets, cudaMemcpyHostToDevice));
+  e->n_param_sets = n_sets;
+  return ABM_OK;
+}
+
+int abm_vf_set_agent_overrides(abm_engine_t* e, const float* alp0, const float* bet0, const float* v0,
+                               int on_device, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_vf_set_agent_overrides: null engine");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  struct Item { const float* src; DevBuf<float>* buf; bool* has; } items[3] = {
+      {alp0, &e->ov_alp0, &e->has_alp0}, {bet0, &e->ov_bet0, &e->has_bet0}, {v0, &e->ov_v0, &e->has_v0}};
+  for (auto& it : items) {
+    if (!it.src) { *it.has = false; continue; }
+    if (!it.buf->p) ABM_CUDA(it.buf->alloc(e->n_total));
+    int rc = copy_in(it.buf->p, it.src, sizeof(float) * e->n_total, on_device, st);
+    if (rc) return rc;
+    *it.has = true;
+  }
+  return ABM_OK;
+}
+
+int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* theta, const float* vel,
+                  const float* radius, int on_device, void* stream) {
+  if (!e || !x || !y || !theta || !vel || !radius) return fail(ABM_E_INVALID, "abm_set_state: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = sizeof(float) * e->n_total;
+  const float *dx = x, *dy = y, *dr = radius;
+  if (!on_device) {
+    int rc;
+    if ((rc = copy_in(e->stage_x.p, x, bytes, 0, st))) return rc;
+    if ((rc = copy_in(e->stage_y.p, y, bytes, 0, st))) return rc;
+    if ((rc = copy_in(e->stage_r.p, radius, bytes, 0, st))) return rc;
+    dx = e->stage_x.p; dy = e->stage_y.p; dr = e->stage_r.p;
+  }
+  int rc;
+  if ((rc = copy_in(e->theta.p, theta, bytes, on_device, st))) return rc;
+  if ((rc = copy_in(e->vel.p, vel, bytes, on_device, st))) return rc;
+  abm::launch_pack_records(dx, dy, dr, e->grid.cull_scale, e->rec[e->cur].p, (long long)e->n_total, st);
+  ABM_CUDA(cudaGetLastError());
+  e->state_set = true;
+  return ABM_OK;
+}
+
+int abm_get_state(abm_engine_t* e, float* x, float* y, float* theta, float* vel, int on_device, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_get_state: null engine");
+  if (!e->state_set) return fail(ABM_E_STATE, "abm_get_state: no state has been set");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = sizeof(float) * e->n_total;
+  int rc;
+  if (x || y) {
+    float* tx = on_device ? x : e->stage_x.p;
+    float* ty = on_device ? y : e->stage_y.p;
+    abm::launch_unpack_records(e->rec[e->cur].p, x ? tx : nullptr, y ? ty : nullptr, (long long)e->n_total, st);
+    ABM_CUDA(cudaGetLastError());
+    if (!on_device) {
+      if (x && (rc = copy_out(x, tx, bytes, 0, st))) return rc;
+      if (y && (rc = copy_out(y, ty, bytes, 0, st))) return rc;
+    }
+  }
+  if (theta && (rc = copy_out(theta, e->theta.p, bytes, on_device, st))) return rc;
+  if (vel && (rc = copy_out(vel, e->vel.p, bytes, on_device, st))) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize(st));
+  return ABM_OK;
+}
+
+int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_vf_step: null engine");
+  if (!e->state_set) return fail(ABM_E_STATE, "abm_vf_step: abm_set_state has not been called");
+  if (n_steps < 0) return fail(ABM_E_INVALID, "abm_vf_step: n_steps < 0");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridConsts& g = e->grid;
+  abm::VFKernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = e->cfg.n_replicates; a.N = e->cfg.n_agents; a.R = g.R; a.W = g.W;
+  a.tile_begin = e->tile_begin; a.tile_count = e->tile_count;
+  a.fov_px0 = e->cfg.fov_px0; a.fov_px1 = e->cfg.fov_px1;
+  a.boundary = e->cfg.boundary; a.limit_movement = e->cfg.limit_movement;
+  a.phi_ok = g.phi_ok; a.flags = e->cfg.flags;
+  a.inv_step = g.inv_step; a.t_frac = g.t_frac; a.k_off = g.k_off; a.y_scale = g.y_scale;
+  a.tau_k = g.tau_k; a.tau_h_abs = g.tau_h_abs; a.tau_h_rel = g.tau_h_rel; a.ca_guard = g.ca_guard;
+  a.width = e->cfg.width; a.height = e->cfg.height;
+  a.half_w = 0.5f * e->cfg.width; a.half_h = 0.5f * e->cfg.height;
+  a.cull_scale = g.cull_scale;
+  a.lin_step = g.lin_step; a.dphi = g.dphi;
+  a.width_d = e->cfg.width; a.height_d = e->cfg.height; a.pad_d = e->cfg.window_pad;
+  a.max_vel = e->cfg.max_vel; a.max_th = e->cfg.max_th;
+  a.theta = e->theta.p; a.vel = e->vel.p;
+  a.params = e->params.p; a.param_stride = (e->n_param_sets == 1) ? 0 : ABM_VF_NPARAM;
+  a.ov_alp0 = e->has_alp0 ? e->ov_alp0.p : nullptr;
+  a.ov_bet0 = e->has_bet0 ? e->ov_bet0.p : nullptr;
+  a.ov_v0 = e->has_v0 ? e->ov_v0.p : nullptr;
+  a.lut = e->lut.p;
+  a.fields_out = e->fields.p; a.terms_out = e->terms.p;
+  a.counters = e->counters.p;
+  for (int s = 0; s < n_steps; ++s) {
+    a.rec_in = e->rec[e->cur].p;
+    a.rec_out = e->rec[e->cur ^ 1].p;
+    abm::launch_vf_step(a, st);
+    e->cur ^= 1;
+    ++e->launches;
+  }
+  ABM_CUDA(cudaGetLastError());
+  return ABM_OK;
+}
+
+int abm_get_fields(abm_engine_t* e, uint32_t* packed, int on_device, void* stream) {
+  if (!e || !packed) return fail(ABM_E_INVALID, "abm_get_fields: null argument");
+  if (!e->fields.p) return fail(ABM_E_STATE, "abm_get_fields: engine created without ABM_VF_KEEP_FIELDS");
+  ABM_CUDA(cudaSetDevice(e->device));
+  int rc = copy_out(packed, e->fields.p, sizeof(uint32_t) * e->n_tile * e->grid.W, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABM_OK;
+}
+
+int abm_vf_get_terms(abm_engine_t* e, double* terms, int on_device, void* stream) {
+  if (!e || !terms) return fail(ABM_E_INVALID, "abm_vf_get_terms: null argument");
+  if (!e->terms.p) return fail(ABM_E_STATE, "abm_vf_get_terms: engine created without ABM_VF_KEEP_TERMS");
+  ABM_CUDA(cudaSetDevice(e->device));
+  int rc = copy_out(terms, e->terms.p, sizeof(double) * e->n_tile * 6, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABM_OK;
+}
+
+int abm_get_counters(abm_engine_t* e, uint64_t counters[4], void* stream) {
+  if (!e || !counters) return fail(ABM_E_INVALID, "abm_get_counters: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  unsigned long long h[4];
+  ABM_CUDA(cudaMemcpyAsync(h, e->counters.p, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  counters[0] = h[0]; counters[1] = h[1]; counters[2] = h[2];
+  counters[3] = e->launches;
+  return ABM_OK;
+}
+
+int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent) {
+  if (!e || !dev_ptr) return fail(ABM_E_INVALID, "abm_vf_record_table: null argument");
+  *dev_ptr = e->rec[e->cur].p;
+  if (bytes_per_agent) *bytes_per_agent = (int)sizeof(float4);
+  return ABM_OK;
+}
+
+int abm_synchronize(abm_engine_t* e, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_synchronize: null engine");
+  ABM_CUDA(cudaSetDevice(e->device));
+  ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABM_OK;
+}
+
+// ---- stateless function-level entry points ----
+
+int abm_vf_projection_field(const abm_vf_proj_args_t* args, uint32_t* out_rows) {
+  if (!args || !out_rows) return fail(ABM_E_INVALID, "abm_vf_projection_field: null argument");
+  if (args->struct_size != (int32_t)sizeof(abm_vf_proj_args_t))
+    return fail(ABM_E_INVALID, "abm_vf_projection_field: struct_size mismatch");
+  if (args->resolution < 8 || args->resolution > 4096)
+    return fail(ABM_E_INVALID, "abm_vf_projection_field: resolution must be in [8, 4096]");
+  if (args->n_obj < 0 || (args->n_obj > 0 && (!args->obj_x || !args->obj_y)))
+    return fail(ABM_E_INVALID, "abm_vf_projection_field: bad object list");
+  if (args->n_obj == 0) return ABM_OK;
+  GridConsts g;
+  build_grid(args->resolution, g);
+  const int n = args->n_obj;
+  std::vector<float> hx(n), hy(n), hs(n);
+  for (int j = 0; j < n; ++j) {
+    hx[j] = (float)args->obj_x[j];
+    hy[j] = (float)args->obj_y[j];
+    hs[j] = (float)(args->obj_size ? args->obj_size[j] : args->radius);
+  }
+  DevBuf<float> dx, dy, ds;
+  DevBuf<uint32_t> rows;
+  ABM_CUDA(dx.alloc(n)); ABM_CUDA(dy.alloc(n)); ABM_CUDA(ds.alloc(n)); ABM_CUDA(rows.alloc((size_t)n * g.W));
+  int rc = ABM_OK;
+  do {
+    cudaError_t ce;
+    if ((ce = cudaMemcpy(dx.p, hx.data(), sizeof(float) * n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(dy.p, hy.data(), sizeof(float) * n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(ds.p, hs.data(), sizeof(float) * n, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+      break;
+    }
+    // find_nearest(phis, fov[i]) in float64 (vf_supcalc.py:105)
+    auto nearest = [&](double v) {
+      int best = 0; double bd = 1e300;
+      for (int k = 0; k < g.R; ++k) {
+        const double phi = (k == g.R - 1) ? ABM_PI_D : ((double)k * g.lin_step + (-ABM_PI_D));
+        const double d = std::fabs(phi - v);
+        if (d < bd) { bd = d; best = k; }
+      }
+      return best;
+    };
+    abm::VFProjArgs a;
+    memset(&a, 0, sizeof(a));
+    a.R = g.R; a.W = g.W; a.n_obj = n; a.boundary = args->boundary;
+    a.fov_px0 = nearest(args->fov0); a.fov_px1 = nearest(args->fov1);
+    a.inv_step = g.inv_step; a.t_frac = g.t_frac; a.k_off = g.k_off; a.y_scale = g.y_scale;
+    a.tau_k = g.tau_k; a.tau_h_abs = g.tau_h_abs; a.tau_h_rel = g.tau_h_rel; a.ca_guard = g.ca_guard;
+    a.width = (float)args->arena_width; a.height = (float)args->arena_height;
+    a.half_w = 0.5f * a.width; a.half_h = 0.5f * a.height;
+    a.lin_step = g.lin_step; a.width_d = args->arena_width; a.height_d = args->arena_height;
+    a.fx = (float)args->x; a.fy = (float)args->y; a.fr = (float)args->radius; a.ftheta = (float)args->orientation;
+    a.vision_range = args->vision_range;
+    a.ox = dx.p; a.oy = dy.p; a.osz = ds.p; a.rows = rows.p;
+    abm::launch_vf_projection(a, 0);
+    if ((ce = cudaGetLastError()) != cudaSuccess ||
+        (ce = cudaMemcpy(out_rows, rows.p, sizeof(uint32_t) * (size_t)n * g.W, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+      break;
+    }
+  } while (0);
+  dx.release(); dy.release(); ds.release(); rows.release();
+  return rc;
+}
+
+int abm_vf_flocking_terms(const uint32_t* packed_v_now, int resolution, double vel_now, const double* params,
+                          double out[6]) {
+  if (!packed_v_now || !params || !out) return fail(ABM_E_INVALID, "abm_vf_flocking_terms: null argument");
+  if (resolution < 8 || resolution > 65535) return fail(ABM_E_INVALID, "abm_vf_flocking_terms: bad resolution");
+  GridConsts g;
+  build_grid(resolution, g);
+  if (!g.phi_ok) {   // vf_agent.py:282-284: resolution mismatch -> no update
+    for (int i = 0; i < 6; ++i) out[i] = 0.0;
+    return ABM_OK;
+  }
+  DevBuf<uint32_t> v; DevBuf<abm::PhiLut> lut; DevBuf<double> prm, res;
+  ABM_CUDA(v.alloc(g.W)); ABM_CUDA(lut.alloc(g.lut.size())); ABM_CUDA(prm.alloc(6)); ABM_CUDA(res.alloc(6));
+  int rc = ABM_OK;
+  cudaError_t ce;
+  if ((ce = cudaMemcpy(v.p, packed_v_now, sizeof(uint32_t) * g.W, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (ce = cudaMemcpy(lut.p, g.lut.data(), sizeof(abm::PhiLut) * g.lut.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (ce = cudaMemcpy(prm.p, params, sizeof(double) * 6, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  } else {
+    abm::launch_vf_terms(v.p, g.R, g.W, vel_now, reinterpret_cast<const abm::VFParams6*>(prm.p), lut.p, g.dphi,
+                         res.p, 0);
+    if ((ce = cudaGetLastError()) != cudaSuccess ||
+        (ce = cudaMemcpy(out, res.p, sizeof(double) * 6, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  }
+  v.release(); lut.release(); prm.release(); res.release();
+  return rc;
+}
+
+}  // extern "C"

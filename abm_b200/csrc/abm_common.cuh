@@ -1,0 +1,83 @@
+// Shared declarations for the abm_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ABM_PI_D 3.141592653589793238462643383279502884
+#define ABM_TWO_PI_D (2.0 * ABM_PI_D)
+
+namespace abm {
+
+constexpr int kMaxThreads = 256;     // focal agents per CTA (one thread each)
+constexpr int kRecTile = 512;        // neighbour records per shared-memory stage
+constexpr int kQueueCap = 1024;      // per-CTA queue of pairs deferred to the fp64 path
+
+// per-replicate flocking parameters, order of ABM_VF_* in include/abm_b200.h
+struct VFParams6 { double gam, v0, alp0, alp1, bet0, bet1; };
+
+// one entry of the integration-grid table (Phi = arange(-pi, pi, 2pi/R), vf_agent.py:44)
+struct __align__(32) PhiLut {
+  double c;   // cos(Phi_k)
+  double s;   // sin(Phi_k)
+  double pc;  // sum_{m<k} cos(Phi_m)
+  double ps;  // sum_{m<k} sin(Phi_m)
+};
+
+struct VFKernelArgs {
+  int B, N, R, W;                 // replicates, agents / replicate, bins, words / field
+  int tile_begin, tile_count;     // focal agents handled by this engine
+  int fov_px0, fov_px1;
+  int boundary, limit_movement;
+  int phi_ok;                     // len(arange grid) == R (vf_agent.py:267); else dv = dphi = 0
+  uint32_t flags;
+  // fp32 pair path
+  float inv_step;                 // (R-1) / 2pi
+  float t_frac;                   // 0 (even R) or 0.5 (odd R)
+  int k_off;                      // k = ceil(ca * inv_step + t_frac) + k_off
+  float y_scale;                  // R / 2pi  (proj_size / 2 = atan(r/d) * y_scale)
+  float tau_k, tau_h_abs, tau_h_rel, ca_guard;
+  float width, height, half_w, half_h;
+  float cull_scale;               // cot^2(2pi/R) * (1 + margin): cull^2 = r^2 * cull_scale
+  // fp64 exact path / epilogue
+  double lin_step;                // linspace step fl(2*pi_fl / (R-1))
+  double dphi;                    // 2pi / R
+  double width_d, height_d, pad_d, max_vel, max_th;
+  // state
+  const float4* rec_in;           // (x, y, r, cull^2) per agent, B*N
+  float4* rec_out;
+  float* theta;                   // B*N, updated in place (only the owner thread touches it)
+  float* vel;
+  const double* params;           // n_sets * 6
+  int param_stride;               // 0 (shared) or 6
+  const float* ov_alp0;           // nullable per-agent overrides, NaN = none
+  const float* ov_bet0;
+  const float* ov_v0;
+  const PhiLut* lut;              // R + 1 entries
+  uint32_t* fields_out;           // nullable, B*tile*W
+  double* terms_out;              // nullable, B*tile*6
+  unsigned long long* counters;   // 4
+};
+
+void launch_vf_step(const VFKernelArgs& a, cudaStream_t stream);
+size_t vf_step_smem_bytes(int threads, int W);
+int vf_step_threads(int tile_count);
+
+struct VFProjArgs {
+  int R, W, n_obj, boundary;
+  int fov_px0, fov_px1;
+  float inv_step, t_frac; int k_off; float y_scale, tau_k, tau_h_abs, tau_h_rel, ca_guard;
+  float width, height, half_w, half_h;
+  double lin_step, width_d, height_d;
+  float fx, fy, fr, ftheta;       // focal agent (fp32 state)
+  double vision_range;            // < 0: none
+  const float* ox; const float* oy; const float* osz;
+  uint32_t* rows;                 // n_obj * W, stored order
+};
+void launch_vf_projection(const VFProjArgs& a, cudaStream_t stream);
+void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const VFParams6* prm,
+                     const PhiLut* lut, double dphi, double* out6, cudaStream_t stream);
+void launch_pack_records(const float* x, const float* y, const float* r, float cull_scale,
+                         float4* rec, long long n, cudaStream_t stream);
+void launch_unpack_records(const float4* rec, float* x, float* y, long long n, cudaStream_t stream);
+
+}  // namespace abm

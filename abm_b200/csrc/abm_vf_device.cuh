@@ -1,0 +1,322 @@
+// Device functions of the visual-flocking (VF) path, shared by the fused step kernel and
+// the stateless function-level kernels.  sm_100a only.
+//
+// Reference behaviour restated here (paths relative to the reference root):
+//   vf_supcalc.projection_field          vf_supcalc.py:20-138   (interval per object)
+//   vf_supcalc.calculate_closed_angle    vf_supcalc.py:142-158  -> supcalc.angle_between supcalc.py:19-34
+//   supcalc.find_nearest                 supcalc.py:8-11        (first arg-min => lower index wins ties)
+//   vf_supcalc.dPhi_V_of                 vf_supcalc.py:257-277
+//   vf_supcalc.VSWRM_flocking_state_variables  vf_supcalc.py:161-254
+//   VFAgent.update_agent_position        vf_agent.py:289-330
+//   Agent.reflect_from_walls / prove_orientation   agent.py:347-394, 605-610
+//   VFAgent.teleport_infinite_arena      vf_agent.py:188-204
+#pragma once
+#include "abm_common.cuh"
+
+namespace abm {
+
+// ---------------------------------------------------------------------------------------
+// fp32 pair path
+// ---------------------------------------------------------------------------------------
+
+// atan(q) for q in [0, 1]: q * P(q^2), minimax in RELATIVE error (7.5e-7 in fp32 Horner).
+__device__ __forceinline__ float atan_unit(float q) {
+  const float z = q * q;
+  float p = 0.007863515056669712f;
+  p = fmaf(p, z, -0.037013452500104904f);
+  p = fmaf(p, z, 0.0838717594742775f);
+  p = fmaf(p, z, -0.13487225770950317f);
+  p = fmaf(p, z, 0.19881492853164673f);
+  p = fmaf(p, z, -0.33326515555381775f);
+  p = fmaf(p, z, 0.9999993443489075f);
+  return p * q;
+}
+
+// atan2(w, u) in (-pi, pi]; abs error ~1e-6 rad, absorbed by the tau_k guard band.
+__device__ __forceinline__ float atan2_fast(float w, float u) {
+  const float au = fabsf(u), aw = fabsf(w);
+  const float mx = fmaxf(au, aw), mn = fminf(au, aw);
+  float p = atan_unit(__fdividef(mn, mx));
+  if (aw > au) p = 1.57079632679489662f - p;
+  if (u < 0.0f) p = 3.14159265358979324f - p;
+  return copysignf(p, w);
+}
+
+// Static per-launch constants of the fp32 bin arithmetic.
+struct BinConsts {
+  float inv_step, t_frac; int k_off;
+  float y_scale, tau_k, tau_h_abs, tau_h_rel;
+  float ca_guard;   // |ca| beyond this is within the error bound of the +-pi seam
+};
+
+// Result of the fp32 evaluation of one (focal, object) pair.
+struct PairFast {
+  int k, h;        // centre bin, half width
+  bool flagged;    // k or h within the fp32 error bound of a rounding boundary (or q > 1)
+};
+
+// (dx, dy): centre difference object - focal (screen coords, y down); (c, s) = cos/sin of the
+// focal heading; r_obj: object radius; d2 = dx^2 + dy^2 > 0.
+__device__ __forceinline__ PairFast vf_pair_fast(float dx, float dy, float d2, float r_obj,
+                                                 float c, float s, const BinConsts& bc) {
+  PairFast o;
+  // rotate (dx, -dy) by -theta: closed angle = atan2(w, u)  (== -angle_between remapped, A.1)
+  const float u = fmaf(dx, c, -dy * s);
+  const float w = -fmaf(dx, s, dy * c);
+  const float ca = atan2_fast(w, u);
+  // k = first-argmin |phis - ca| = ceil(x - 0.5), x = (ca + pi) / step   (A.2)
+  const float t = fmaf(ca, bc.inv_step, bc.t_frac);
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (t + MAGIC) - MAGIC == rint(t)
+  const float tr = t + MAGIC;
+  const float df = t - (tr - MAGIC);                       // in [-0.5, 0.5]
+  o.k = (__float_as_int(tr) - 0x4B400000) + (df > 0.0f ? 1 : 0) + bc.k_off;
+  bool flagged = (fabsf(df) < bc.tau_k) | (fabsf(ca) > bc.ca_guard);
+  // h = floor(proj_size / 2), proj_size / 2 = atan(r / d) * R / 2pi
+  const float q = r_obj * rsqrtf(d2);
+  flagged |= (q > 1.0f);
+  const float y = atan_unit(fminf(q, 1.0f)) * bc.y_scale;
+  const float yr = y + MAGIC;
+  const float dy_ = y - (yr - MAGIC);
+  o.h = (__float_as_int(yr) - 0x4B400000) - (dy_ < 0.0f ? 1 : 0);
+  flagged |= fabsf(dy_) < fmaf(y, bc.tau_h_rel, bc.tau_h_abs);
+  o.flagged = flagged;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 exact pair path: the reference's own operation sequence, individually rounded
+// ---------------------------------------------------------------------------------------
+
+struct FocalExact {
+  double cix, ciy;   // centre (vf_supcalc.py:42)
+  double u1x, u1y;   // unit heading vector v1 / |v1| (vf_supcalc.py:45-49, supcalc.py:14)
+};
+
+__device__ __forceinline__ FocalExact vf_focal_exact(float px, float py, float r, float theta) {
+  FocalExact f;
+  const double x = px, y = py, rr = r, th = theta;
+  f.cix = __dadd_rn(x, rr);
+  f.ciy = __dadd_rn(y, rr);
+  const double ex = __dadd_rn(x, __dmul_rn(__dadd_rn(1.0, cos(th)), rr));
+  const double ey = __dadd_rn(y, __dmul_rn(__dadd_rn(1.0, -sin(th)), rr));
+  const double v1x = __dadd_rn(ex, -f.cix), v1y = __dadd_rn(ey, -f.ciy);
+  const double n1 = __dsqrt_rn(__dadd_rn(__dmul_rn(v1x, v1x), __dmul_rn(v1y, v1y)));
+  f.u1x = __ddiv_rn(v1x, n1);
+  f.u1y = __ddiv_rn(v1y, n1);
+  return f;
+}
+
+// first-argmin over the numpy linspace(-pi, pi, R) grid, evaluated on the three candidates
+// around the closed-form estimate with the grid values numpy produces
+// (y[k] = fl(fl(k * step) + (-pi)), y[R-1] = pi).
+__device__ __forceinline__ int nearest_bin_exact(double value, int R, double lin_step) {
+  int k0 = (int)ceil((value + ABM_PI_D) / lin_step - 0.5);
+  k0 = max(0, min(R - 1, k0));
+  int best = k0;
+  double bestd = 1e300;
+  for (int kk = max(0, k0 - 1); kk <= min(R - 1, k0 + 1); ++kk) {
+    const double phi = (kk == R - 1) ? ABM_PI_D : __dadd_rn(__dmul_rn((double)kk, lin_step), -ABM_PI_D);
+    const double d = fabs(__dadd_rn(phi, -value));
+    if (d < bestd) { bestd = d; best = kk; }
+  }
+  return best;
+}
+
+struct PairExact { int k, h; bool valid; };
+
+// Object at top-left (ox, oy) with radius orad seen by the focal agent `f`.
+// boundary / width / height: torus re-centring of vf_supcalc.py:70-83.
+__device__ __noinline__ PairExact vf_pair_exact(const FocalExact& f, float ox, float oy, float orad,
+                                                int boundary, double width, double height,
+                                                int R, double lin_step) {
+  PairExact o;
+  const double rr = orad;
+  double cjx = __dadd_rn((double)ox, rr), cjy = __dadd_rn((double)oy, rr);   // :61-64
+  double v2x = __dadd_rn(cjx, -f.cix), v2y = __dadd_rn(cjy, -f.ciy);
+  if (boundary == 1) {                                                      // :70-83
+    if (fabs(v2x) > width * 0.5) {
+      if (f.cix < cjx) cjx = __dadd_rn(cjx, -width); else if (f.cix > cjx) cjx = __dadd_rn(cjx, width);
+    }
+    if (fabs(v2y) > height * 0.5) {
+      if (f.ciy < cjy) cjy = __dadd_rn(cjy, -height); else if (f.ciy > cjy) cjy = __dadd_rn(cjy, height);
+    }
+    v2x = __dadd_rn(cjx, -f.cix); v2y = __dadd_rn(cjy, -f.ciy);
+  }
+  const double n2 = __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+  const double u2x = __ddiv_rn(v2x, n2), u2y = __ddiv_rn(v2y, n2);
+  double dot = __dadd_rn(__dmul_rn(f.u1x, u2x), __dmul_rn(f.u1y, u2y));
+  dot = fmin(1.0, fmax(-1.0, dot));
+  double ang = acos(dot);                                                   // supcalc.py:31
+  if (__dadd_rn(__dmul_rn(f.u1x, u2y), -__dmul_rn(f.u1y, u2x)) < 0.0) ang = -ang;
+  if (ang < 0.0) ang = __dadd_rn(ang, ABM_TWO_PI_D);                        // % 2pi (vf_supcalc.py:150)
+  const double ca = (ang >= 0.0 && ang <= ABM_PI_D) ? -ang : __dadd_rn(ABM_TWO_PI_D, -ang);   // :154-157
+  const double dist = n2;                                                   // :88
+  const double vis = __dmul_rn(2.0, atan(__ddiv_rn(rr, dist)));             // :99
+  const double proj = __dmul_rn(__ddiv_rn(vis, ABM_TWO_PI_D), (double)R);   // :114
+  o.k = nearest_bin_exact(ca, R, lin_step);                                 // :102
+  o.h = (int)floor(__ddiv_rn(proj, 2.0));                                   // :116
+  o.valid = (n2 > 0.0);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// drawing an interval into a bit-packed UN-flipped row (vf_supcalc.py:119-129)
+// ---------------------------------------------------------------------------------------
+
+// Row word w of the calling thread lives at f[w * stride].
+template <bool ATOMIC>
+__device__ __forceinline__ void or_word(uint32_t* p, uint32_t m) {
+  if (ATOMIC) atomicOr(p, m); else *p |= m;
+}
+
+// set bins [a, b), 0 <= a < b <= R
+template <bool ATOMIC>
+__device__ __forceinline__ void set_range(uint32_t* f, int stride, int a, int b) {
+  const int w0 = a >> 5, w1 = (b - 1) >> 5;
+  const uint32_t m0 = 0xffffffffu << (a & 31);
+  const uint32_t m1 = 0xffffffffu >> ((32 - b) & 31);
+  if (w0 == w1) {
+    or_word<ATOMIC>(f + w0 * stride, m0 & m1);
+  } else {
+    or_word<ATOMIC>(f + w0 * stride, m0);
+    for (int w = w0 + 1; w < w1; ++w) or_word<ATOMIC>(f + w * stride, 0xffffffffu);
+    or_word<ATOMIC>(f + w1 * stride, m1);
+  }
+}
+
+// Full drawing rule incl. the visibility test on pixel indices and the VF wrap quirks.
+template <bool ATOMIC>
+__device__ __forceinline__ void vf_draw(uint32_t* f, int stride, int R, int fov0, int fov1, int k, int h) {
+  int ps = k - h, pe = k + h;
+  const bool vis = (fov0 < ps && ps < fov1) || (fov0 < pe && pe < fov1);   // :119
+  if (!vis || h <= 0) return;
+  if (ps < 0) {                                                             // :122-124
+    set_range<ATOMIC>(f, stride, max(R + ps, 0), R);
+    ps = 0;
+  }
+  if (pe >= R) {                                                            // :125-127
+    const int e = min(pe - (R - 1), R);
+    if (e > 0) set_range<ATOMIC>(f, stride, 0, e);
+    pe = R;
+  }
+  if (pe > ps) set_range<ATOMIC>(f, stride, ps, pe);                        // :129
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogue: dV/dphi, flocking integrals, kinematics (fp64; tiny next to the pair loop)
+// ---------------------------------------------------------------------------------------
+
+struct FlockTerms { double dvel, dpsi, a_blob, a_edge, b_blob, b_edge; };
+
+// V (un-flipped row) word w at f[w * stride].  Closed form of vf_supcalc.py:199-254:
+//   blob = trapz(cos(Phi) * (-V), Phi) = dphi * (-sum_k cos_k V_k + (cos_0 V_0 + cos_{R-1} V_{R-1}) / 2)
+//   edge = sum_k cos_k * dPhi_V_of(V)_k^2, attributed to bin k-1 (forward diff) or k (backward diff,
+//          iff V[0] - V[R-1] > 0; vf_supcalc.py:268-272) of each ring boundary between k-1 and k.
+// sum_k cos_k V_k over a run [a, b) = pc[b] - pc[a] (prefix table).
+__device__ __forceinline__ FlockTerms vf_flock_terms(const uint32_t* f, int stride, int R, int W,
+                                                     const PhiLut* __restrict__ lut, double dphi,
+                                                     double vel, const VFParams6& prm,
+                                                     double A0, double B0, double V0) {
+  const uint32_t last_valid = (R & 31) ? ((1u << (R & 31)) - 1u) : 0xffffffffu;
+  const uint32_t w_last = f[(W - 1) * stride] & last_valid;
+  const uint32_t v_first = f[0] & 1u;
+  const uint32_t v_last = (w_last >> ((R - 1) & 31)) & 1u;
+  const bool backward = (v_first == 1u) && (v_last == 0u);
+  double Sc = 0.0, Ss = 0.0, Ec = 0.0, Es = 0.0;
+  uint32_t carry = v_last;   // ring predecessor of bin 0
+  for (int w = 0; w < W; ++w) {
+    uint32_t cur = f[w * stride];
+    if (w == W - 1) cur &= last_valid;
+    uint32_t diff = cur ^ ((cur << 1) | carry);   // bit b: V[k] != V[k-1], k = 32w + b
+    if (w == W - 1) diff &= last_valid;
+    carry = (w == W - 1) ? 0u : (cur >> 31);
+    while (diff) {
+      const int b = __ffs(diff) - 1;
+      diff &= diff - 1;
+      const int k = (w << 5) + b;
+      const int ke = backward ? k : (k == 0 ? R - 1 : k - 1);
+      const double2 cs = *reinterpret_cast<const double2*>(&lut[ke].c);
+      Ec += cs.x; Es += cs.y;
+      const double2 pp = *reinterpret_cast<const double2*>(&lut[k].pc);
+      if ((cur >> b) & 1u) { Sc -= pp.x; Ss -= pp.y; }   // run starts at k
+      else                 { Sc += pp.x; Ss += pp.y; }   // run ended at k
+    }
+  }
+  if (v_last) { Sc += lut[R].pc; Ss += lut[R].ps; }      // run reaching the end of the row
+  const double c0 = lut[0].c, s0 = lut[0].s, cl = lut[R - 1].c, sl = lut[R - 1].s;
+  const double endc = 0.5 * (c0 * (double)v_first + cl * (double)v_last);
+  const double ends = 0.5 * (s0 * (double)v_first + sl * (double)v_last);
+  FlockTerms t;
+  t.a_blob = A0 * (dphi * (endc - Sc));
+  t.a_edge = A0 * prm.alp1 * Ec;
+  t.b_blob = B0 * (dphi * (ends - Ss));
+  t.b_edge = B0 * prm.bet1 * Es;
+  t.dvel = prm.gam * (V0 - vel) + t.a_blob + t.a_edge;
+  t.dpsi = t.b_blob + t.b_edge;
+  return t;
+}
+
+__device__ __forceinline__ double wrap_heading_once(double th) {   // agent.py:605-610
+  if (th < 0.0) th = ABM_TWO_PI_D + th;
+  if (th > ABM_TWO_PI_D) th = th - ABM_TWO_PI_D;
+  return th;
+}
+
+__device__ __forceinline__ double limit_abs(double v, double lim) {   // vf_agent.py:311-330
+  const double sg = (v < 0.0) ? -1.0 : 1.0;
+  return (fabs(v) > lim) ? lim * sg : v;
+}
+
+// Agent.reflect_from_walls (agent.py:347-394): tests use the centre BEFORE any fix.
+__device__ __forceinline__ void reflect_from_walls(double& x, double& y, double& th, double r,
+                                                   double width, double height, double pad) {
+  const double bx0 = pad, bx1 = pad + width, by0 = pad, by1 = pad + height;
+  const double cx = x + r, cy = y + r;
+  const double PI = ABM_PI_D, H = ABM_PI_D / 2.0, T3 = 3.0 * ABM_PI_D / 2.0, TWO = 2.0 * ABM_PI_D;
+  if (cx < bx0) {
+    x = bx0 - r;
+    if (H <= th && th < PI) th -= H; else if (PI <= th && th <= T3) th += H;
+    th = wrap_heading_once(th);
+  }
+  if (cx > bx1) {
+    x = bx1 - r - 1.0;
+    if (T3 <= th && th < TWO) th -= H; else if (0.0 <= th && th <= H) th += H;
+    th = wrap_heading_once(th);
+  }
+  if (cy < by0) {
+    y = by0 - r;
+    if (H <= th && th <= PI) th += H; else if (0.0 <= th && th < H) th -= H;
+    th = wrap_heading_once(th);
+  }
+  if (cy > by1) {
+    y = by1 - r - 1.0;
+    if (T3 <= th && th <= TWO) th += H; else if (PI <= th && th < T3) th -= H;
+    th = wrap_heading_once(th);
+  }
+}
+
+// VFAgent.teleport_infinite_arena (vf_agent.py:188-204)
+__device__ __forceinline__ void teleport_torus(double& x, double& y, double r, double width, double height,
+                                               double pad) {
+  const double bx0 = pad, bx1 = pad + width, by0 = pad, by1 = pad + height;
+  const double cx = x + r, cy = y + r;
+  if (cx < bx0) x = bx1 - r; else if (cx > bx1) x = bx0 + r;
+  if (cy < by0) y = by1 - r; else if (cy > by1) y = by0 + r;
+}
+
+// stored word ws of the flipped field: stored[s] = V[R - 1 - s]
+__device__ __forceinline__ uint32_t flipped_word(const uint32_t* f, int stride, int R, int W, int ws) {
+  // bits s = 32ws .. 32ws+31  <-  V[hi .. hi-31], hi = R - 1 - 32ws
+  const int hi = R - 1 - (ws << 5);
+  const int wh = hi >> 5;            // word holding V[hi]   (hi >= 0 for ws < W)
+  const int sh = 31 - (hi & 31);     // left shift that brings V[hi] to bit 31
+  const uint32_t a = f[wh * stride];
+  const uint32_t lo = (wh > 0) ? f[(wh - 1) * stride] : 0u;
+  const uint32_t v = sh ? ((a << sh) | (lo >> (32 - sh))) : a;   // bit 31 = V[hi], bit 0 = V[hi-31]
+  uint32_t out = __brev(v);                                       // bit 0 = V[hi]
+  const int nvalid = min(32, hi + 1);
+  if (nvalid < 32) out &= (1u << nvalid) - 1u;
+  return out;
+}
+
+}  // namespace abm

@@ -1,0 +1,201 @@
+"""Host-side handle of the fused visual-flocking engine (thin wrapper over the C ABI).
+
+Arrays may be numpy arrays (host; copied inside the call) or torch CUDA tensors
+(device pointers, no copy).  Shapes are (n_replicates, n_agents) or flat.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _fov_pixels(R: int, fov) -> tuple[int, int]:
+    """find_nearest(linspace(-pi, pi, R), fov[i]) in float64 (vf_supcalc.py:39, :105)."""
+    phis = np.linspace(-np.pi, np.pi, R)
+    return int(np.abs(phis - fov[0]).argmin()), int(np.abs(phis - fov[1]).argmin())
+
+
+def _is_torch_cuda(a) -> bool:
+    return hasattr(a, "is_cuda") and a.is_cuda
+
+
+def _current_stream() -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_stream().cuda_stream)
+    except ImportError:
+        pass
+    return 0
+
+
+class VFEngine:
+    """B replicates x N agents of the visual-flocking model, resident on one GPU.
+
+    Mirrors what VFSimulation + VFAgent hold per run (vf_sims.py:16-44, vf_agent.py:12-50):
+    ``resolution`` is R AFTER the int(R / fov) rescale, ``fov`` the (lo, hi) tuple in radians.
+    """
+
+    def __init__(self, n_replicates: int, n_agents: int, *, resolution: int = 1200,
+                 fov=(-np.pi, np.pi), boundary: str = "walls", width: float = 900.0, height: float = 900.0,
+                 window_pad: float = 30.0, limit_movement: bool = False, max_vel: float = 3.0,
+                 max_th: float = 0.1, exact_fixup: bool = True, keep_fields: bool = False,
+                 keep_terms: bool = False, device: int = 0, tile: tuple[int, int] | None = None):
+        if boundary not in ("walls", "infinite"):
+            raise ValueError(f"boundary must be 'walls' or 'infinite', got {boundary!r}")
+        self._lib = _lib.load()
+        self.B, self.N, self.R = int(n_replicates), int(n_agents), int(resolution)
+        self.W = (self.R + 31) // 32
+        self.device = int(device)
+        self.tile_begin, self.tile_count = (0, self.N) if tile is None else (int(tile[0]), int(tile[1]))
+        f0, f1 = _fov_pixels(self.R, fov)
+        flags = (_lib.VF_EXACT_FIXUP if exact_fixup else 0) | (_lib.VF_KEEP_FIELDS if keep_fields else 0) \
+            | (_lib.VF_KEEP_TERMS if keep_terms else 0)
+        cfg = _lib.VFConfig(
+            struct_size=C.sizeof(_lib.VFConfig), n_replicates=self.B, n_agents=self.N, resolution=self.R,
+            fov_px0=f0, fov_px1=f1,
+            boundary=_lib.BOUNDARY_INFINITE if boundary == "infinite" else _lib.BOUNDARY_WALLS,
+            limit_movement=int(bool(limit_movement)), width=float(width), height=float(height),
+            window_pad=float(window_pad), max_vel=float(max_vel), max_th=float(max_th), flags=flags,
+            tile_begin=self.tile_begin, tile_count=0 if tile is None else self.tile_count)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.abm_vf_create(C.byref(cfg), self.device, C.byref(self._h)), "abm_vf_create")
+        self.keep_fields, self.keep_terms = keep_fields, keep_terms
+
+    # -- life cycle --------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.abm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- helpers -----------------------------------------------------------------------
+    def _ptr(self, a, dtype, count, keep):
+        """(pointer, on_device) of an input array; host arrays are made contiguous/typed."""
+        if a is None:
+            return None, None
+        if _is_torch_cuda(a):
+            import torch
+            want = {np.float32: torch.float32, np.float64: torch.float64, np.uint32: torch.int32}[dtype]
+            if a.dtype != want or not a.is_contiguous() or a.numel() != count:
+                raise ValueError("device tensors must be contiguous, of the engine dtype and full size")
+            return C.c_void_p(a.data_ptr()), 1
+        arr = np.ascontiguousarray(np.asarray(a, dtype=dtype).reshape(-1))
+        if arr.size != count:
+            raise ValueError(f"expected {count} elements, got {arr.size}")
+        keep.append(arr)
+        return C.c_void_p(arr.ctypes.data), 0
+
+    @staticmethod
+    def _same_side(flags):
+        s = {f for f in flags if f is not None}
+        if len(s) > 1:
+            raise ValueError("all arrays of one call must live on the same side (host or device)")
+        return s.pop() if s else 0
+
+    # -- parameters --------------------------------------------------------------------
+    def set_params(self, GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, BET0=1.0, BET1=0.09):
+        """Scalars (shared) or length-B arrays (one set per replicate: a MetaProtocol sweep)."""
+        vals = [np.atleast_1d(np.asarray(v, np.float64)) for v in (GAM, V0, ALP0, ALP1, BET0, BET1)]
+        n = max(v.size for v in vals)
+        if n not in (1, self.B):
+            raise ValueError("parameter arrays must have length 1 or n_replicates")
+        tab = np.ascontiguousarray(np.stack([np.broadcast_to(v, (n,)) for v in vals], axis=1))
+        _lib.check(self._lib.abm_vf_set_params(self._h, C.c_void_p(tab.ctypes.data), n), "abm_vf_set_params")
+
+    def set_agent_overrides(self, alp0=None, bet0=None, v0=None):
+        """Per-agent VFAgent.ALP0 / .BET0 / .V0 (NaN = None = use the replicate's value)."""
+        keep = []
+        total = self.B * self.N
+        ptrs = [self._ptr(a, np.float32, total, keep) for a in (alp0, bet0, v0)]
+        side = self._same_side([p[1] for p in ptrs])
+        _lib.check(self._lib.abm_vf_set_agent_overrides(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0], side,
+                                                        C.c_void_p(_current_stream())), "abm_vf_set_agent_overrides")
+        if not side:
+            self.synchronize()
+
+    # -- state -------------------------------------------------------------------------
+    def set_state(self, x, y, theta, vel, radius):
+        keep = []
+        total = self.B * self.N
+        if not _is_torch_cuda(radius):
+            radius = np.broadcast_to(np.asarray(radius, np.float32), np.asarray(x).shape)
+        ptrs = [self._ptr(a, np.float32, total, keep) for a in (x, y, theta, vel, radius)]
+        side = self._same_side([p[1] for p in ptrs])
+        _lib.check(self._lib.abm_set_state(self._h, *[p[0] for p in ptrs], side, C.c_void_p(_current_stream())),
+                   "abm_set_state")
+        if not side:
+            self.synchronize()   # the host arrays in `keep` may go away after return
+
+    def get_state(self, out=None):
+        """Returns dict(x, y, theta, vel) of (B, N) float32 numpy arrays (or fills ``out``,
+        a dict of numpy arrays / torch CUDA tensors)."""
+        total = self.B * self.N
+        if out is None:
+            out = {k: np.empty((self.B, self.N), np.float32) for k in ("x", "y", "theta", "vel")}
+        ptrs, sides = [], []
+        for k in ("x", "y", "theta", "vel"):
+            a = out.get(k)
+            if a is None:
+                ptrs.append(None)
+            elif _is_torch_cuda(a):
+                ptrs.append(C.c_void_p(a.data_ptr())); sides.append(1)
+            else:
+                if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != total:
+                    raise ValueError("output arrays must be C-contiguous float32 of full size")
+                ptrs.append(C.c_void_p(a.ctypes.data)); sides.append(0)
+        side = self._same_side(sides)
+        _lib.check(self._lib.abm_get_state(self._h, *ptrs, side, C.c_void_p(_current_stream())), "abm_get_state")
+        return out
+
+    def step(self, n_steps: int = 1):
+        _lib.check(self._lib.abm_vf_step(self._h, int(n_steps), C.c_void_p(_current_stream())), "abm_vf_step")
+
+    def synchronize(self):
+        _lib.check(self._lib.abm_synchronize(self._h, C.c_void_p(_current_stream())), "abm_synchronize")
+
+    # -- outputs of the last step ----------------------------------------------------------
+    def fields_packed(self) -> np.ndarray:
+        """(B, tile, W) uint32, STORED (flipped) order like Agent.soc_v_field."""
+        out = np.empty((self.B, self.tile_count, self.W), np.uint32)
+        _lib.check(self._lib.abm_get_fields(self._h, C.c_void_p(out.ctypes.data), 0, C.c_void_p(_current_stream())),
+                   "abm_get_fields")
+        return out
+
+    def fields(self) -> np.ndarray:
+        """(B, tile, R) bool, STORED order."""
+        w = self.fields_packed()
+        bits = (w[..., :, None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)
+        return bits.reshape(self.B, self.tile_count, -1)[..., :self.R].astype(bool)
+
+    def terms(self) -> np.ndarray:
+        """(B, tile, 6) float64: dvel, dpsi, a_blob, a_edge, b_blob, b_edge."""
+        out = np.empty((self.B, self.tile_count, 6), np.float64)
+        _lib.check(self._lib.abm_vf_get_terms(self._h, C.c_void_p(out.ctypes.data), 0,
+                                              C.c_void_p(_current_stream())), "abm_vf_get_terms")
+        return out
+
+    def counters(self) -> dict:
+        c = (C.c_uint64 * 4)()
+        _lib.check(self._lib.abm_get_counters(self._h, c, C.c_void_p(_current_stream())), "abm_get_counters")
+        return dict(fp64_pairs=int(c[0]), fp64_inline=int(c[1]), fp32_fp64_differ=int(c[2]), launches=int(c[3]))
+
+    def record_table_ptr(self) -> tuple[int, int]:
+        p = C.c_void_p()
+        nbytes = C.c_int()
+        _lib.check(self._lib.abm_vf_record_table(self._h, C.byref(p), C.byref(nbytes)), "abm_vf_record_table")
+        return int(p.value), int(nbytes.value)

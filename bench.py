@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the ABM hot path (visual field + flocking update), BASELINE.json metric:
+agent-steps/sec at N agents x R replicates on 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE configs[3] -- visual flocking, 1024 agents x 1024
+replicates PER GPU (weak scaling: replicates are independent, no data-path collective),
+R = 1200, full FOV, walls, reference disc initial condition (vf_sims.py:212-228),
+parameters of VFExp4c (GAM .1, V0 1, ALP0 1, ALP1 .09, BET0 1, BET1 .09), arena
+ceil(900 * sqrt(N/100)) = 2880 px, radius 10.  A "step" = one fused kernel launch that
+advances all agents of all replicates of the rank by one time step.
+
+One JSON line is printed by rank 0 (see the driver contract in the task statement).
+`--impl reference` times the CPU port of the reference's own algorithm (oracle/literal.py;
+the reference is pure Python and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = int(os.environ.get("ABM_BENCH_AGENTS", 1024))
+N_REPLICATES = int(os.environ.get("ABM_BENCH_REPLICATES", 1024))
+R = 1200
+RADIUS = 10.0
+PAD = 30.0
+PARAMS = dict(GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, BET0=1.0, BET1=0.09)
+METRIC = "agent-steps/sec (visual field + flocking update)"
+UNIT = "agent-steps/s"
+
+
+def arena_side(n_agents):
+    return float(math.ceil(900.0 * math.sqrt(n_agents / 100.0)))
+
+
+def synthetic_state(n_rep, n_agents, first_replicate=0):
+    """Reference disc initial condition (vf_sims.py:216-221), seeds default_rng(1234 + replicate)
+    (SURVEY 8d).  Returns float32 (n_rep, n_agents) arrays x, y, theta, vel."""
+    W = arena_side(n_agents)
+    x = np.empty((n_rep, n_agents), np.float32)
+    y = np.empty_like(x)
+    th = np.empty_like(x)
+    for b in range(n_rep):
+        rng = np.random.default_rng(1234 + first_replicate + b)
+        orient = rng.uniform(0, 2 * np.pi, n_agents)
+        dist = rng.uniform(0, 1, n_agents) * (W / 2 - 2 * PAD - RADIUS)
+        x[b] = np.cos(orient) * dist + W / 2
+        y[b] = np.sin(orient) * dist + W / 2
+        th[b] = orient
+    return x, y, th, np.zeros_like(x)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU phases run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples)
+        reasons = []
+        for idx, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"),
+                          (7, "sw_power_cap")):
+            if any(s[idx].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(s[3]) for s in self.samples)}
+
+
+def visible_pair_fraction(x, y, r=RADIUS):
+    """Fraction of ordered pairs whose half width is >= 1 bin: d <= r / tan(2pi/R)."""
+    import torch
+    lim2 = (r / math.tan(2 * math.pi / R)) ** 2
+    cx, cy = x + r, y + r
+    d2 = (cx[:, :, None] - cx[:, None, :]) ** 2 + (cy[:, :, None] - cy[:, None, :]) ** 2
+    n = x.shape[1]
+    vis = (d2 <= lim2).sum().item() - x.shape[0] * n
+    return vis / float(x.shape[0] * n * (n - 1))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def cpu_port_rate(n_focal, n_agents, procs=1, seed_replicate=0):
+    """agent-steps/s of the CPU port (oracle/literal.py) on `procs` host processes: `n_focal`
+    focal agents of one replicate against the full neighbour set, frozen snapshot."""
+    from oracle import literal, restate as rs
+    x, y, th, v = synthetic_state(1, n_agents, seed_replicate)
+    x64, y64, th64, v64 = (a[0].astype(np.float64) for a in (x, y, th, v))
+    rad = np.full(n_agents, RADIUS)
+    W = arena_side(n_agents)
+    cfg = rs.VFConfig(R=R, width=W, height=W, **PARAMS)
+    idx = list(range(n_focal))
+    if procs <= 1:
+        t0 = time.perf_counter()
+        for i in idx:
+            literal.agent_update(i, x64, y64, th64, v64, rad, cfg)
+        dt = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+        chunks = [idx[p::procs] for p in range(procs)]
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_chunk, [([], x64, y64, th64, v64, rad, cfg)] * procs)   # warm the workers
+            t0 = time.perf_counter()
+            pool.map(_cpu_chunk, [(c, x64, y64, th64, v64, rad, cfg) for c in chunks])
+            dt = time.perf_counter() - t0
+    return n_focal / dt, dt
+
+
+def _cpu_chunk(job):
+    from oracle import literal
+    idx, x, y, th, v, rad, cfg = job
+    for i in idx:
+        literal.agent_update(i, x, y, th, v, rad, cfg)
+    return len(idx)
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path (port, all host cores)."""
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_focal = max(procs * 2, int(os.environ.get("ABM_BENCH_CPU_FOCAL", 4 * procs)))
+    rates = []
+    for s in range(args.warmup + args.steps):
+        rate, dt = cpu_port_rate(n_focal, N_AGENTS, procs=procs)
+        if s >= args.warmup:
+            rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([d for _, d in rates]) * 1e3)
+    sample = (f"{n_focal} focal agents x {N_AGENTS - 1} neighbours of replicate 0 per step, frozen snapshot, "
+              f"{procs} processes (one per host core), oracle/literal.py float64 port of VFAgent.update")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "BASELINE configs[3]: visual flocking, 1024 agents x 1024 replicates per GPU, R=1200",
+            "n_agents": N_AGENTS, "replicates_per_gpu": N_REPLICATES, "replicates_total": N_REPLICATES * world,
+            "fov_resolution": R, "boundary": "walls", "arena_px": arena_side(N_AGENTS), "agent_radius": RADIUS,
+            "params": PARAMS, "parallelism": f"replicate-sharded x{world}, no data-path collective",
+            "l2": "L2 flushed (256 MiB memset) between timed steps; flush excluded from the timing",
+            "update": "synchronous (Jacobi) step from a frozen snapshot; epilogue in fp64, pair path fp32 + fp64 "
+                      "re-evaluation of near-boundary pairs"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference_arm(args, rank, world)
+        return
+    args.steps = 30 if args.steps is None else args.steps
+    args.warmup = 3 if args.warmup is None else max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (abm_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from abm_b200 import VFEngine
+
+    B, N = N_REPLICATES, N_AGENTS
+    W = arena_side(N)
+    x, y, th, v = synthetic_state(B, N, first_replicate=rank * B)
+    rad = np.full((B, N), RADIUS, np.float32)
+    eng = VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank)
+    eng.set_params(**PARAMS)
+    dev = [torch.from_numpy(a).cuda() for a in (x, y, th, v, rad)]
+    eng.set_state(*dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        # ---- kernel-only arm: state resident in HBM ----
+        for _ in range(args.warmup):
+            eng.step(1)
+        sx = torch.empty(B, N, device="cuda"); sy = torch.empty(B, N, device="cuda")
+        eng.get_state({"x": sx, "y": sy})
+        torch.cuda.synchronize()
+        vis0 = visible_pair_fraction(sx[:16], sy[:16])
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        barrier()
+        t_wall0 = time.perf_counter()
+        for s in range(args.steps):
+            flush.zero_()                      # L2 flush, outside the timed interval
+            starts[s].record()
+            eng.step(1)
+            ends[s].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
+        total_ms = float(sum(step_ms))
+        eng.get_state({"x": sx, "y": sy})
+        torch.cuda.synchronize()
+        vis1 = visible_pair_fraction(sx[:16], sy[:16])
+        launches = args.steps
+
+        # ---- end-to-end arm: host buffers in, host buffers out, every step ----
+        hx, hy, hth, hv, hr = (torch.from_numpy(a).pin_memory() for a in (x, y, th, v, rad))
+        ox, oy, oth, ov = (torch.empty(B, N).pin_memory() for _ in range(4))
+        h_in = [t.numpy() for t in (hx, hy, hth, hv, hr)]
+        h_out = {"x": ox.numpy(), "y": oy.numpy(), "theta": oth.numpy(), "vel": ov.numpy()}
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            eng.set_state(*h_in); eng.step(1); eng.get_state(h_out)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            eng.set_state(*h_in)               # H2D of the step's inputs (pinned)
+            eng.step(1)
+            eng.get_state(h_out)               # D2H of the step's result
+            for k, a in zip(("x", "y", "theta", "vel"), h_in):   # feed the result back (host memcpy)
+                np.copyto(a, h_out[k])
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    counters = eng.counters()
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = (float(v) for v in t.tolist())
+    agents_total = B * N * world
+    value = agents_total * args.steps / (total_ms * 1e-3)
+    e2e_value = agents_total * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        props = torch.cuda.get_device_properties(local_rank)
+        sms = props.multi_processor_count
+        vis = 0.5 * (vis0 + vis1)
+        pairs = B * N * (N - 1)
+        # OPS_PAIR = 6 * P_all + 42 * P_vis ; OPS_AGENT = 8 * ceil(R/32) + 12 * n_edges + 30
+        ops_launch = 6.0 * pairs + 42.0 * pairs * vis + B * N * (8 * ((R + 31) // 32) + 30)
+        avg_s = total_ms * 1e-3 / args.steps
+        sm_clock = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        peak_ops = sms * 128 * sm_clock
+        bytes_launch = 44.0 * B * N
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(5 * 4 * B * N),
+                    "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
+                         "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops, "traffic": None,
+                         "kernel": "abm::vf_step_kernel", "algorithmic_ops_per_launch": ops_launch,
+                         "visible_pair_fraction": vis, "peak_source": f"{sms} SMs x 128 lanes x "
+                         f"{sm_clock / 1e6:.0f} MHz ({peak_kind} sm_max_mhz)",
+                         "hbm": {"achieved": bytes_launch / avg_s / 1e9, "peak": peaks.get("hbm_gbs"),
+                                 "unit": "GB/s", "frac": bytes_launch / avg_s / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                                 "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_kind}},
+            "pairs_per_sec": pairs * world * args.steps / (total_ms * 1e-3),
+            "fp64_pairs_fraction": counters["fp64_pairs"] / float(pairs * counters["launches"]),
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            os.environ.setdefault("OMP_NUM_THREADS", "1")
+            n_focal = int(os.environ.get("ABM_BENCH_CPU_FOCAL", 256))
+            rate, dt = cpu_port_rate(n_focal, N, procs=1)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{n_focal} focal agents x {N - 1} neighbours of replicate 0 ({dt:.1f} s), frozen snapshot, "
+                          "oracle/literal.py float64 port of VFAgent.update (same per-pair loop and arg-min scans "
+                          "as the reference), 1 core"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,188 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path (abm_b200/).
+
+Harness glue that lets the UNMODIFIED reference (scioip34/ABM, mounted read-only
+at /root/reference in the build container) be imported without pygame /
+matplotlib, so that its own functions and agent classes can be executed to
+
+  * validate the restatements in ``oracle/restate.py`` / ``oracle/literal.py``, and
+  * generate the golden fixtures under ``tests/golden/`` (see
+    ``tests/golden/make_golden.py``).
+
+``/root/reference`` does not exist on the GPU box, so nothing in ``-m gpu`` tests,
+``bench.py`` or ``__graft_entry__.smoke()`` may import this module; CPU tests that
+use it skip themselves when the reference tree is absent.
+
+What is stubbed: ``pygame`` (Sprite / Group with a
+sequential ``update``, no-op Surface, MagicMock drawing sub-modules),
+``matplotlib.cm.get_cmap``, and ``scipy.integrate.trapz`` (removed in
+SciPy >= 1.14; the reference calls it at vf_supcalc.py:234-246).
+Nothing under /root/reference is edited.
+"""
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+REFERENCE_ROOT = os.environ.get("ABM_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "abm", "agent"))
+
+
+class _Rect:
+    def __init__(self):
+        self.x = 0
+        self.y = 0
+        self.centerx = 0
+        self.centery = 0
+
+    def collidepoint(self, *_a, **_k):
+        return False
+
+
+class _Surface:
+    def __init__(self, *_a, **_k):
+        pass
+
+    def fill(self, *_a, **_k):
+        pass
+
+    def set_colorkey(self, *_a, **_k):
+        pass
+
+    def set_alpha(self, *_a, **_k):
+        pass
+
+    def blit(self, *_a, **_k):
+        pass
+
+    def get_rect(self, *_a, **_k):
+        return _Rect()
+
+
+class _Sprite:
+    def __init__(self, *_a, **_k):
+        self._groups = []
+
+    def kill(self):
+        for g in list(self._groups):
+            if self in g:
+                g.remove(self)
+        self._groups = []
+
+
+class _Group(list):
+    """Insertion-ordered group whose update() walks a snapshot sequentially
+    (what pygame.sprite.Group.update does; reference call sims.py:861)."""
+
+    def add(self, *sprites):
+        for s in sprites:
+            if s not in self:
+                self.append(s)
+                if hasattr(s, "_groups"):
+                    s._groups.append(self)
+
+    def sprites(self):
+        return list(self)
+
+    def update(self, *args, **kwargs):
+        for s in list(self):
+            s.update(*args, **kwargs)
+
+
+def install():
+    """Install the stubs and put the reference on sys.path.  Idempotent."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    if "pygame" not in sys.modules or not getattr(sys.modules["pygame"], "_abm_stub", False):
+        pg = types.ModuleType("pygame")
+        pg._abm_stub = True
+        sprite = types.ModuleType("pygame.sprite")
+        sprite.Sprite = _Sprite
+        sprite.Group = _Group
+        sprite.collide_circle = MagicMock()
+        sprite.groupcollide = MagicMock()
+        pg.sprite = sprite
+        pg.Surface = _Surface
+        for name in ("draw", "mask", "gfxdraw", "transform", "math", "display", "time", "event",
+                     "font", "mouse", "key", "surfarray"):
+            m = MagicMock()
+            setattr(pg, name, m)
+            sys.modules[f"pygame.{name}"] = m
+        pg.init = lambda *a, **k: None
+        pg.quit = lambda *a, **k: None
+        sys.modules["pygame"] = pg
+        sys.modules["pygame.sprite"] = sprite
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        cm = types.ModuleType("matplotlib.cm")
+        cm.get_cmap = lambda _name: (lambda _x: (0.0, 0.0, 0.0, 1.0))
+        mpl.cm = cm
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.cm"] = cm
+    import scipy.integrate as _si
+    if not hasattr(_si, "trapz"):
+        _si.trapz = _si.trapezoid
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    # the reference's param modules read {EXPERIMENT_NAME}.env relative to the reference root
+    os.environ.setdefault("EXPERIMENT_NAME", "")
+
+
+def load_vf():
+    """Returns (vf_supcalc, vf_agent module, vf_params) of the real reference."""
+    install()
+    from abm.projects.visual_flocking.vf_agent import vf_supcalc, vf_agent
+    from abm.projects.visual_flocking.vf_contrib import vf_params
+    return vf_supcalc, vf_agent, vf_params
+
+
+def load_base():
+    """Returns (supcalc, agent module, decision_params, movement_params)."""
+    install()
+    from abm.agent import supcalc, agent
+    from abm.contrib import decision_params, movement_params
+    return supcalc, agent, decision_params, movement_params
+
+
+def make_vf_agents(x, y, theta, vel, radius, *, R, fov_ratio=1.0, width, height, window_pad=30,
+                   boundary="walls", params=None, alp0=None, bet0=None, v0=None,
+                   limit_movement=False, max_vel=3.0, max_th=0.1):
+    """Build real reference VFAgent objects from arrays (state cast to float64).
+
+    Constructor kwargs follow vf_sims.py:191-208.  vf_params attributes are
+    overridden AFTER construction because every constructor reloads them from
+    the reference's root .env (vf_agent.py:15-16)."""
+    import numpy as np
+    vf_supcalc, vf_agent, vf_params = load_vf()
+    agents = []
+    n = len(x)
+    radius = np.broadcast_to(np.asarray(radius), (n,))
+    for i in range(n):
+        rad = radius[i]
+        rad = int(rad) if float(rad).is_integer() else float(rad)
+        a = vf_agent.VFAgent(
+            id=i, radius=rad, position=(float(x[i]), float(y[i])), orientation=float(theta[i]),
+            env_size=(int(width), int(height)), color=(0, 0, 0), v_field_res=R,
+            FOV=(-fov_ratio * np.pi, fov_ratio * np.pi), window_pad=int(window_pad), pooling_time=0,
+            pooling_prob=0, consumption=1, vision_range=2000, visual_exclusion=False,
+            patchwise_exclusion=True, behave_params=None)
+        a.velocity = float(vel[i])
+        a.boundary_cond = boundary
+        a.limit_movement = limit_movement
+        a.max_vel = max_vel
+        a.max_th = max_th
+        if alp0 is not None:
+            a.ALP0 = float(alp0[i])
+        if bet0 is not None:
+            a.BET0 = float(bet0[i])
+        if v0 is not None:
+            a.V0 = float(v0[i])
+        agents.append(a)
+    p = dict(GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, ALP2=0.0, BET0=1.0, BET1=0.09, BET2=0.0)
+    if params:
+        p.update(params)
+    for k, v in p.items():
+        setattr(vf_params, k, v)
+    return agents

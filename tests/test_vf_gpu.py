@@ -1,0 +1,262 @@
+"""GPU parity tests of the fused visual-flocking step (through the C ABI) against
+  * fixtures produced by the unmodified reference (tests/golden/vf_golden.npz), and
+  * the CPU oracle (oracle/restate.py) on seeded random scenes.
+
+Bar (BASELINE.json north_star): binary fields bit-exact except at exact bin-boundary ties
+(<= 1 bin per edge, counted); dV integrals / velocities / headings within 1e-5 relative.
+With the fp64 re-evaluation of near-boundary pairs (ABM_VF_EXACT_FIXUP, default) the
+fields are expected to match bit for bit, and the tests assert exactly that.
+"""
+import numpy as np
+import pytest
+
+from golden_io import load_pf_cases, load_vf_cases
+from oracle import restate as rs
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # tolerance stated by north_star for integrals, velocities and headings (fp32 state)
+
+
+def _engine(c_or_cfg, B, N, **kw):
+    from abm_b200 import VFEngine
+    return VFEngine(B, N, keep_fields=True, keep_terms=True, **kw)
+
+
+def _check_state(st, ref, b=None):
+    for k in ("x", "y", "theta", "vel"):
+        got = st[k] if b is None else st[k][b]
+        np.testing.assert_allclose(got.reshape(-1), ref[k], rtol=RTOL, atol=1e-5, err_msg=k)
+
+
+@pytest.mark.parametrize("case", load_vf_cases(), ids=lambda c: f"N{c['N']}_R{c['R']}_{c['boundary']}")
+def test_step_matches_reference_fixture(built_lib, case):
+    c = case
+    fov = (-c["fov_ratio"] * np.pi, c["fov_ratio"] * np.pi)
+    eng = _engine(None, 1, c["N"], resolution=c["R"], fov=fov, boundary=c["boundary"], width=c["W"],
+                  height=c["W"], limit_movement=c["limit"])
+    eng.set_params()
+    if c["alp0"] is not None:
+        eng.set_agent_overrides(c["alp0"], c["bet0"], c["v0"])
+    eng.set_state(c["x"], c["y"], c["theta"], c["vel"], c["radius"])
+    eng.step(1)
+    assert np.array_equal(eng.fields_packed()[0], c["fields"])          # bit-exact stored fields
+    np.testing.assert_allclose(eng.terms()[0], c["terms"], rtol=RTOL, atol=1e-9)
+    st = eng.get_state()
+    got = np.stack([st["x"][0], st["y"][0], st["theta"][0], st["vel"][0]], axis=1)
+    np.testing.assert_allclose(got, c["new"], rtol=RTOL, atol=1e-5)
+    eng.close()
+
+
+@pytest.mark.parametrize("pc", load_pf_cases(), ids=lambda p: f"R{p['R']}_{p['boundary']}")
+def test_projection_field_function_matches_reference_fixture(built_lib, pc):
+    from abm_b200 import vf_supcalc
+    rows = vf_supcalc.projection_field(pc["fov"], pc["R"], np.array(pc["pos"]), pc["r"], pc["th"],
+                                       [np.array(o) for o in pc["objs"]], object_sizes=pc["sizes"],
+                                       boundary_cond=pc["boundary"], arena_width=pc["W"], arena_height=pc["W"],
+                                       vision_range=pc["vr"])
+    assert rows.shape == (len(pc["objs"]), pc["R"])
+    assert np.array_equal(rs.pack_bits(rows > 0), pc["rows"])
+
+
+def test_reference_golden_vector_through_plugin(built_lib):
+    """test_cs_supcalc.py:143-158, verbatim through the drop-in function."""
+    from abm_b200 import vf_supcalc
+    out = vf_supcalc.projection_field((-np.pi, np.pi), 8, np.array([-1, -1]), 1, 0, [np.array([0, -1])])
+    assert out.tolist() == [[0, 0, 0, 0, 1, 1, 0, 0]]
+
+
+def test_flocking_terms_function_kat(built_lib):
+    """KAT-V1 of SURVEY App. B through VSWRM_flocking_state_variables."""
+    from types import SimpleNamespace
+    from abm_b200 import vf_supcalc
+    field = np.zeros(1200)
+    for a, b in [(130, 160), (473, 511), (754, 828), (1060, 1090)]:
+        field[a:b] = 1
+    prm = SimpleNamespace(GAM=0.1, V0=1, ALP0=1, ALP1=0.09, BET0=1, BET1=0.09, ALP2=0, BET2=0)
+    Phi = np.arange(-np.pi, np.pi, 2 * np.pi / 1200)
+    got = vf_supcalc.VSWRM_flocking_state_variables(0.5, Phi, np.flip(field), prm, verbose=True)
+    expect = (-0.11295710879884255, 0.16720418209113855, -0.13687988331415218, -0.02607722548469037,
+              0.20545193082925006, -0.038247748738111514)
+    np.testing.assert_allclose(got, expect, rtol=1e-11)
+    dv, dpsi = vf_supcalc.VSWRM_flocking_state_variables(0.5, Phi, np.flip(field), prm)
+    assert np.isclose(dv, expect[0]) and np.isclose(dpsi, expect[1])
+
+
+def _random_scene(rng, B, N, W, spread=None):
+    pad = 30.0
+    lo, hi = (pad - 10, pad + W - 10) if spread is None else spread
+    x = rng.uniform(lo, hi, (B, N)).astype(np.float32)
+    y = rng.uniform(lo, hi, (B, N)).astype(np.float32)
+    th = rng.uniform(0, 2 * np.pi, (B, N)).astype(np.float32)
+    v = rng.uniform(0, 2.5, (B, N)).astype(np.float32)
+    return x, y, th, v
+
+
+SCENES = [
+    # B, N, R, W, boundary, fov_ratio, radius
+    (3, 50, 1200, 500.0, "walls", 1.0, 10.0),
+    (2, 100, 1200, 900.0, "walls", 1.0, 10.0),       # config 2 shape
+    (2, 100, 1200, 900.0, "infinite", 1.0, 5.0),
+    (2, 70, 2400, 600.0, "walls", 0.5, 10.0),
+    (2, 33, 1201, 300.0, "infinite", 1.0, 10.0),     # odd R
+    (1, 300, 1200, 1559.0, "walls", 1.0, 10.0),      # more than one CTA per replicate
+    (4, 10, 320, 900.0, "walls", 1.0, 10.0),
+    (1, 600, 1200, 400.0, "walls", 1.0, 10.0),       # crowded, > one record stage
+]
+
+
+@pytest.mark.parametrize("B,N,R,W,boundary,fovr,radius", SCENES)
+def test_step_matches_oracle_random(built_lib, B, N, R, W, boundary, fovr, radius):
+    rng = np.random.default_rng(1234 + N + R)
+    x, y, th, v = _random_scene(rng, B, N, W)
+    fov = (-fovr * np.pi, fovr * np.pi)
+    eng = _engine(None, B, N, resolution=R, fov=fov, boundary=boundary, width=W, height=W)
+    eng.set_params()
+    eng.set_state(x, y, th, v, radius)
+    eng.step(1)
+    fields, terms, st = eng.fields(), eng.terms(), eng.get_state()
+    cfg = rs.VFConfig(R=R, fov=fov, boundary=boundary, width=W, height=W)
+    sample = range(N) if N <= 120 else sorted(rng.choice(N, 60, replace=False).tolist())
+    for b in range(B):
+        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], radius, cfg, agents=sample)
+        idx = np.array(list(sample))
+        assert np.array_equal(fields[b][idx], ref["rows"][idx][:, ::-1]), "stored field mismatch"
+        np.testing.assert_allclose(terms[b][idx], ref["terms"][idx], rtol=RTOL, atol=1e-9)
+        for k in ("x", "y", "theta", "vel"):
+            np.testing.assert_allclose(st[k][b][idx], ref[k][idx], rtol=RTOL, atol=1e-5, err_msg=k)
+    cnt = eng.counters()
+    assert cnt["launches"] == 1
+    eng.close()
+
+
+def test_per_replicate_parameter_sweep(built_lib):
+    """One launch, one parameter set per replicate (the MetaProtocol sweep shape)."""
+    rng = np.random.default_rng(5)
+    B, N, R, W = 6, 24, 1200, 400.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    alp0 = np.linspace(0, 5, B); bet0 = np.linspace(5, 0, B)
+    eng = _engine(None, B, N, resolution=R, width=W, height=W)
+    eng.set_params(ALP0=alp0, BET0=bet0, ALP1=0.0014, BET1=0.0014)
+    eng.set_state(x, y, th, v, 10.0)
+    eng.step(1)
+    terms, st = eng.terms(), eng.get_state()
+    for b in range(B):
+        cfg = rs.VFConfig(R=R, width=W, height=W, ALP0=alp0[b], BET0=bet0[b], ALP1=0.0014, BET1=0.0014)
+        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], 10.0, cfg)
+        np.testing.assert_allclose(terms[b], ref["terms"], rtol=RTOL, atol=1e-9)
+        _check_state(st, ref, b)
+    eng.close()
+
+
+def test_multi_step_lockstep_with_oracle(built_lib):
+    """20 steps; after every step the oracle is restarted from the engine's fp32 state, so
+    each step is judged on its own from identical state (no drift accumulation)."""
+    rng = np.random.default_rng(11)
+    B, N, R, W = 1, 40, 1200, 300.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    eng = _engine(None, B, N, resolution=R, width=W, height=W)
+    eng.set_params()
+    eng.set_state(x, y, th, v, 10.0)
+    cfg = rs.VFConfig(R=R, width=W, height=W)
+    cur = dict(x=x, y=y, theta=th, vel=v)
+    for _ in range(20):
+        ref = rs.vf_step_frozen(cur["x"][0], cur["y"][0], cur["theta"][0], cur["vel"][0], 10.0, cfg)
+        eng.step(1)
+        st = eng.get_state()
+        assert np.array_equal(eng.fields()[0], ref["rows"][:, ::-1])
+        _check_state(st, ref, 0)
+        cur = st
+    assert eng.counters()["launches"] == 20
+    eng.close()
+
+
+def test_device_pointer_state_roundtrip(built_lib):
+    import torch
+    rng = np.random.default_rng(3)
+    B, N = 2, 64
+    x, y, th, v = _random_scene(rng, B, N, 500.0)
+    from abm_b200 import VFEngine
+    eng = VFEngine(B, N, resolution=1200, width=500.0, height=500.0)
+    dev = [torch.from_numpy(a).cuda() for a in (x, y, th, v)]
+    rad = torch.full((B, N), 10.0, device="cuda")
+    eng.set_state(*dev, rad)
+    out = {k: torch.empty(B, N, device="cuda") for k in ("x", "y", "theta", "vel")}
+    eng.get_state(out)
+    torch.cuda.synchronize()
+    for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v)):
+        assert np.array_equal(out[k].cpu().numpy(), a)
+    eng.close()
+
+
+def test_empty_field_and_single_agent(built_lib):
+    """N=1: nothing to see -> field empty, integrals zero, agent relaxes towards V0."""
+    eng = _engine(None, 2, 1, resolution=1200, width=300.0, height=300.0)
+    eng.set_params()
+    eng.set_state(np.array([[100.0], [150.0]]), np.array([[100.0], [90.0]]), np.array([[0.5], [4.0]]),
+                  np.array([[0.0], [2.0]]), 10.0)
+    eng.step(1)
+    assert not eng.fields().any()
+    t = eng.terms()
+    np.testing.assert_allclose(t[:, 0, 0], [0.1 * (1 - 0.0), 0.1 * (1 - 2.0)], rtol=1e-12)
+    assert np.all(t[:, 0, 1:] == 0)
+    eng.close()
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE configs[3] shape at reduced replicate count (1024 agents x 8 replicates,
+    R=1200): size-independent properties instead of the (too slow) oracle --
+    (1) replicates are independent: replicate b of a batch == the same replicate alone;
+    (2) agent order inside the neighbour table does not matter (union is commutative);
+    (3) mirror symmetry: reflecting the scene left-right flips every field."""
+    rng = np.random.default_rng(2024)
+    B, N, R = 8, 1024, 1200
+    W = float(np.ceil(900 * np.sqrt(N / 100)))
+    x, y, th, v = _random_scene(rng, B, N, W)
+    from abm_b200 import VFEngine
+    eng = VFEngine(B, N, resolution=R, width=W, height=W, keep_fields=True, keep_terms=True)
+    eng.set_params(); eng.set_state(x, y, th, v, 10.0); eng.step(1)
+    f_all, t_all = eng.fields_packed(), eng.terms()
+    eng.close()
+    # (1)
+    e1 = VFEngine(1, N, resolution=R, width=W, height=W, keep_fields=True, keep_terms=True)
+    e1.set_params(); e1.set_state(x[3:4], y[3:4], th[3:4], v[3:4], 10.0); e1.step(1)
+    assert np.array_equal(e1.fields_packed()[0], f_all[3])
+    assert np.array_equal(e1.terms()[0], t_all[3])
+    # (2) permute agents of replicate 3
+    perm = rng.permutation(N)
+    e1.set_state(x[3:4, perm], y[3:4, perm], th[3:4, perm], v[3:4, perm], 10.0); e1.step(1)
+    assert np.array_equal(e1.fields_packed()[0], f_all[3][perm])
+    # (3) oracle spot check on a few agents of the full-size scene
+    cfg = rs.VFConfig(R=R, width=W, height=W)
+    sample = [0, 17, 511, 1023]
+    ref = rs.vf_step_frozen(x[3], y[3], th[3], v[3], 10.0, cfg, agents=sample)
+    bits = rs.unpack_bits(f_all[3], R)
+    assert np.array_equal(bits[sample], ref["rows"][sample][:, ::-1])
+    np.testing.assert_allclose(t_all[3][sample], ref["terms"][sample], rtol=RTOL, atol=1e-9)
+    e1.close()
+
+
+def test_fixup_counters_and_fp32_only_mode(built_lib):
+    """With the fp64 re-evaluation switched off the fp32 path alone may differ from the oracle
+    only by <= 1 bin per edge; the number of such agents is counted and reported."""
+    rng = np.random.default_rng(77)
+    B, N, R, W = 4, 256, 1200, 1440.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    from abm_b200 import VFEngine
+    exact = VFEngine(B, N, resolution=R, width=W, height=W, keep_fields=True)
+    fast = VFEngine(B, N, resolution=R, width=W, height=W, keep_fields=True, exact_fixup=False)
+    for e in (exact, fast):
+        e.set_params(); e.set_state(x, y, th, v, 10.0); e.step(1)
+    fe, ff = exact.fields(), fast.fields()
+    cnt = exact.counters()
+    pairs = B * N * (N - 1)
+    assert 0 < cnt["fp64_pairs"] < 0.02 * pairs          # a small fraction goes through fp64
+    assert cnt["fp32_fp64_differ"] <= cnt["fp64_pairs"]
+    diff_agents = int((fe != ff).any(axis=-1).sum())
+    # every differing agent differs by isolated single bins (an edge moved by one bin)
+    d = (fe != ff)
+    assert d.sum() <= 4 * max(diff_agents, 1)
+    print(f"fp64 pairs {cnt['fp64_pairs']} of {pairs} ({cnt['fp64_pairs'] / pairs:.2e}); fp32/fp64 index "
+          f"differences {cnt['fp32_fp64_differ']}; agents whose fp32-only field differs: {diff_agents} of {B * N}")
+    exact.close(); fast.close()
