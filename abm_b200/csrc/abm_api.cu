@@ -50,6 +50,12 @@ struct GridConsts {
   int R = 0, W = 0;
   float inv_step, t_frac; int k_off;
   float y_scale, tau_k, tau_h_abs, tau_h_rel, ca_guard, cull_scale;
+  // derived constants of the fp32 pair path (BinConsts); exact == false: fp32-only mode
+  float t_half() const { return t_frac + 0.5f; }
+  int k_bias() const { return k_off - 0x4B400000 + 32; }
+  float thr_k(bool exact) const { return exact ? 0.5f - tau_k : 3.0e38f; }
+  float thr_h0(bool exact) const { return exact ? 0.5f - tau_h_abs - 0.5f * tau_h_rel : 3.0e38f; }
+  float thr_h1(bool exact) const { return exact ? -tau_h_rel : 0.0f; }
   double lin_step, dphi;
   int phi_ok;
   std::vector<abm::PhiLut> lut;   // R + 1 entries
@@ -114,6 +120,9 @@ struct abm_engine {
   DevBuf<uint32_t> fields;
   DevBuf<double> terms;
   DevBuf<unsigned long long> counters;
+  DevBuf<unsigned> radius_minmax;
+  bool radius_known = false;   // host copy of radius_minmax is current
+  float r_min = 0.f, r_max = 0.f;
   bool state_set = false;
   unsigned long long launches = 0;
 };
@@ -196,6 +205,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   A(e->params.alloc((size_t)cfg->n_replicates * ABM_VF_NPARAM));
   A(e->lut.alloc(e->grid.lut.size()));
   A(e->counters.alloc(4));
+  A(e->radius_minmax.alloc(2));
   if (cfg->flags & ABM_VF_KEEP_FIELDS) A(e->fields.alloc(e->n_tile * e->grid.W));
   if (cfg->flags & ABM_VF_KEEP_TERMS) A(e->terms.alloc(e->n_tile * 6));
   if (err == cudaSuccess) err = cudaMemcpy(e->lut.p, e->grid.lut.data(), sizeof(abm::PhiLut) * e->grid.lut.size(),
@@ -223,6 +233,7 @@ int abm_destroy(abm_engine_t* e) {
   e->stage_x.release(); e->stage_y.release(); e->stage_r.release();
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
+  e->radius_minmax.release();
   delete e;
   return ABM_OK;
 }
@@ -271,8 +282,12 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
   int rc;
   if ((rc = copy_in(e->theta.p, theta, bytes, on_device, st))) return rc;
   if ((rc = copy_in(e->vel.p, vel, bytes, on_device, st))) return rc;
-  abm::launch_pack_records(dx, dy, dr, e->grid.cull_scale, e->rec[e->cur].p, (long long)e->n_total, st);
+  const unsigned init_mm[2] = {0x7f800000u, 0u};
+  ABM_CUDA(cudaMemcpyAsync(e->radius_minmax.p, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
+  abm::launch_pack_records(dx, dy, dr, e->grid.cull_scale, e->rec[e->cur].p, e->radius_minmax.p,
+                           (long long)e->n_total, st);
   ABM_CUDA(cudaGetLastError());
+  e->radius_known = false;
   e->state_set = true;
   return ABM_OK;
 }
@@ -314,8 +329,10 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.fov_px0 = e->cfg.fov_px0; a.fov_px1 = e->cfg.fov_px1;
   a.boundary = e->cfg.boundary; a.limit_movement = e->cfg.limit_movement;
   a.phi_ok = g.phi_ok; a.flags = e->cfg.flags;
-  a.inv_step = g.inv_step; a.t_frac = g.t_frac; a.k_off = g.k_off; a.y_scale = g.y_scale;
-  a.tau_k = g.tau_k; a.tau_h_abs = g.tau_h_abs; a.tau_h_rel = g.tau_h_rel; a.ca_guard = g.ca_guard;
+  const bool exact = (e->cfg.flags & ABM_VF_EXACT_FIXUP) != 0;   // false: no guard bands (hard cases still go to fp64)
+  a.inv_step = g.inv_step; a.t_half = g.t_half(); a.k_bias = g.k_bias(); a.y_scale = g.y_scale;
+  a.thr_k = g.thr_k(exact); a.thr_h0 = g.thr_h0(exact); a.thr_h1 = g.thr_h1(exact); a.ca_guard = g.ca_guard;
+  a.fov0p = e->cfg.fov_px0 + 33; a.span = (unsigned)(e->cfg.fov_px1 - e->cfg.fov_px0 - 1);
   a.width = e->cfg.width; a.height = e->cfg.height;
   a.half_w = 0.5f * e->cfg.width; a.half_h = 0.5f * e->cfg.height;
   a.cull_scale = g.cull_scale;
@@ -330,10 +347,23 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.lut = e->lut.p;
   a.fields_out = e->fields.p; a.terms_out = e->terms.p;
   a.counters = e->counters.p;
+  if (!e->radius_known) {   // kernel variant selection needs min / max radius of the batch (once per set_state)
+    unsigned mm[2];
+    ABM_CUDA(cudaMemcpyAsync(mm, e->radius_minmax.p, sizeof(mm), cudaMemcpyDeviceToHost, st));
+    ABM_CUDA(cudaStreamSynchronize(st));
+    memcpy(&e->r_min, &mm[0], 4);
+    memcpy(&e->r_max, &mm[1], 4);
+    e->radius_known = true;
+  }
+  const bool uniform_r = (e->r_min == e->r_max);
+  // Distance culling pays only when most pairs are farther apart than the distance at which the
+  // half width drops to 0 (r / tan(2pi/R)); expected visible fraction ~ pi * d_cull^2 / arena area.
+  const double d_cull = (double)e->r_max * std::sqrt((double)g.cull_scale);
+  const bool cull = ABM_PI_D * d_cull * d_cull < 0.5 * (double)e->cfg.width * (double)e->cfg.height;
   for (int s = 0; s < n_steps; ++s) {
     a.rec_in = e->rec[e->cur].p;
     a.rec_out = e->rec[e->cur ^ 1].p;
-    abm::launch_vf_step(a, st);
+    abm::launch_vf_step(a, uniform_r, cull, st);
     e->cur ^= 1;
     ++e->launches;
   }
@@ -432,8 +462,8 @@ int abm_vf_projection_field(const abm_vf_proj_args_t* args, uint32_t* out_rows) 
     memset(&a, 0, sizeof(a));
     a.R = g.R; a.W = g.W; a.n_obj = n; a.boundary = args->boundary;
     a.fov_px0 = nearest(args->fov0); a.fov_px1 = nearest(args->fov1);
-    a.inv_step = g.inv_step; a.t_frac = g.t_frac; a.k_off = g.k_off; a.y_scale = g.y_scale;
-    a.tau_k = g.tau_k; a.tau_h_abs = g.tau_h_abs; a.tau_h_rel = g.tau_h_rel; a.ca_guard = g.ca_guard;
+    a.inv_step = g.inv_step; a.t_half = g.t_half(); a.k_bias = g.k_bias(); a.y_scale = g.y_scale;
+    a.thr_k = g.thr_k(true); a.thr_h0 = g.thr_h0(true); a.thr_h1 = g.thr_h1(true); a.ca_guard = g.ca_guard;
     a.width = (float)args->arena_width; a.height = (float)args->arena_height;
     a.half_w = 0.5f * a.width; a.half_h = 0.5f * a.height;
     a.lin_step = g.lin_step; a.width_d = args->arena_width; a.height_d = args->arena_height;

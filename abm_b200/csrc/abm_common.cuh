@@ -30,12 +30,15 @@ struct VFKernelArgs {
   int boundary, limit_movement;
   int phi_ok;                     // len(arange grid) == R (vf_agent.py:267); else dv = dphi = 0
   uint32_t flags;
-  // fp32 pair path
+  // fp32 pair path (see BinConsts in abm_vf_device.cuh); kept as plain kernel arguments so that
+  // the hot loop reads them straight from the constant bank
   float inv_step;                 // (R-1) / 2pi
-  float t_frac;                   // 0 (even R) or 0.5 (odd R)
-  int k_off;                      // k = ceil(ca * inv_step + t_frac) + k_off
+  float t_half;                   // 0.5 (even R) or 1.0 (odd R)
+  int k_bias;                     // k_off - 0x4B400000 + 32
   float y_scale;                  // R / 2pi  (proj_size / 2 = atan(r/d) * y_scale)
-  float tau_k, tau_h_abs, tau_h_rel, ca_guard;
+  float thr_k, thr_h0, thr_h1, ca_guard;
+  int fov0p;                      // fov_px0 + 33: first visible padded position
+  unsigned span;                  // fov_px1 - fov_px0 - 1: number of visible positions
   float width, height, half_w, half_h;
   float cull_scale;               // cot^2(2pi/R) * (1 + margin): cull^2 = r^2 * cull_scale
   // fp64 exact path / epilogue
@@ -58,14 +61,14 @@ struct VFKernelArgs {
   unsigned long long* counters;   // 4
 };
 
-void launch_vf_step(const VFKernelArgs& a, cudaStream_t stream);
+void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream);
 size_t vf_step_smem_bytes(int threads, int W);
 int vf_step_threads(int tile_count);
 
 struct VFProjArgs {
   int R, W, n_obj, boundary;
   int fov_px0, fov_px1;
-  float inv_step, t_frac; int k_off; float y_scale, tau_k, tau_h_abs, tau_h_rel, ca_guard;
+  float inv_step, t_half; int k_bias; float y_scale, thr_k, thr_h0, thr_h1, ca_guard;
   float width, height, half_w, half_h;
   double lin_step, width_d, height_d;
   float fx, fy, fr, ftheta;       // focal agent (fp32 state)
@@ -76,8 +79,9 @@ struct VFProjArgs {
 void launch_vf_projection(const VFProjArgs& a, cudaStream_t stream);
 void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const VFParams6* prm,
                      const PhiLut* lut, double dphi, double* out6, cudaStream_t stream);
+// radius_minmax: 2 uints (bit patterns of min / max radius; init 0x7f800000 / 0)
 void launch_pack_records(const float* x, const float* y, const float* r, float cull_scale,
-                         float4* rec, long long n, cudaStream_t stream);
+                         float4* rec, unsigned* radius_minmax, long long n, cudaStream_t stream);
 void launch_unpack_records(const float4* rec, float* x, float* y, long long n, cudaStream_t stream);
 
 }  // namespace abm

@@ -49,7 +49,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 size_t vf_step_smem_bytes(int threads, int W) {
   return 2 * sizeof(float4) * kRecTile            // record stages
-         + sizeof(uint32_t) * (size_t)W * threads   // rows
+         + sizeof(uint32_t) * (size_t)(W + 2) * threads   // padded rows
          + 2 * sizeof(uint32_t) * kQueueCap         // deferred-pair queue
          + 64;                                      // mbarriers + queue counter
 }
@@ -59,13 +59,39 @@ int vf_step_threads(int tile_count) {
   return t > kMaxThreads ? kMaxThreads : t;
 }
 
-__global__ void __launch_bounds__(kMaxThreads)
+// Out-of-line fp64 evaluation + atomic draw of one pair (queue overflow / deferred pairs).
+// Returns 1 if the fp64 indices differ from the fp32 ones (k32, h32).
+__device__ __noinline__ unsigned vf_exact_and_draw(const VFKernelArgs& a, uint32_t* row, int stride,
+                                                   float4 f4, float fth, float4 o, int k32, int h32) {
+  const FocalExact fe = vf_focal_exact(f4.x, f4.y, f4.z, fth);
+  const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, a.R, a.lin_step);
+  if (pe.valid) vf_draw<true>(row, stride, a.R, a.fov_px0, a.fov_px1, pe.k, pe.h);
+  return (pe.valid && ((pe.k != k32) | (pe.h != h32))) ? 1u : 0u;
+}
+
+// Queue overflow: evaluate a flagged pair on the spot (out of line: rare).
+__device__ __noinline__ void vf_exact_inline(const VFKernelArgs& a, uint32_t* myrow, int stride, float4 me, size_t gi,
+                                             float4 o, int k, int h) {
+  const unsigned diff = vf_exact_and_draw(a, myrow, stride, me, a.theta[gi], o, k, h);
+  atomicAdd(&a.counters[1], 1ull);
+  if (diff) atomicAdd(&a.counters[2], 1ull);
+}
+
+// Interval that would leave the row padding (h > 16 right at the seam): general rule, out of line.
+__device__ __noinline__ void vf_draw_general(const VFKernelArgs& a, uint32_t* myrow, int stride, int k, int h) {
+  vf_draw<false>(myrow, stride, a.R, a.fov_px0, a.fov_px1, k, h);
+}
+
+// TORUS: BOUNDARY == infinite.  UNIFORM_R: all radii equal (centre difference == position
+// difference).  CULL: skip pairs beyond the distance at which the half width becomes 0.
+template <bool TORUS, bool UNIFORM_R, bool CULL>
+__global__ void __launch_bounds__(kMaxThreads, 3)
 vf_step_kernel(const VFKernelArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* recs = reinterpret_cast<float4*>(smem_raw);                       // [2][kRecTile]
-  uint32_t* rows = reinterpret_cast<uint32_t*>(recs + 2 * kRecTile);        // [W][T]
+  uint32_t* rows = reinterpret_cast<uint32_t*>(recs + 2 * kRecTile);        // [W + 2][T], padded (vf_draw_fast)
   const int T = blockDim.x;
-  uint32_t* queue = rows + (size_t)a.W * T;                                 // [kQueueCap][2]
+  uint32_t* queue = rows + (size_t)(a.W + 2) * T;                           // [kQueueCap][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(queue + 2 * kQueueCap);      // [2]
   int* qcount = reinterpret_cast<int*>(bars + 2);
 
@@ -84,7 +110,7 @@ vf_step_kernel(const VFKernelArgs a) {
     *qcount = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int w = 0; w < a.W; ++w) rows[w * T + tid] = 0u;
+  for (int w = 0; w < a.W + 2; ++w) rows[w * T + tid] = 0u;
   __syncthreads();
 
   const int n_stage = (a.N + kRecTile - 1) / kRecTile;
@@ -100,17 +126,22 @@ vf_step_kernel(const VFKernelArgs a) {
     me = rep_in[i];
     th = a.theta[(size_t)b * a.N + i];
   }
-  float c, s;
+  float c, ns;
   {
     double sd, cd;
     sincos((double)th, &sd, &cd);
-    c = (float)cd; s = (float)sd;
+    c = (float)cd; ns = (float)(-sd);
   }
-  BinConsts bc{a.inv_step, a.t_frac, a.k_off, a.y_scale, a.tau_k, a.tau_h_abs, a.tau_h_rel, a.ca_guard};
-  uint32_t* myrow = rows + tid;
-  const bool torus = a.boundary == 1;
-  const bool fixup = (a.flags & 1u) != 0;
-  unsigned n_flag = 0, n_inline = 0, n_mismatch = 0;
+  const BinConsts bc{a.inv_step, a.t_half, a.k_bias, a.y_scale, a.thr_k, a.thr_h0, a.thr_h1, a.ca_guard};
+  uint32_t* padrow = rows + tid;        // padded word 0 (virtual bins [-32, 0))
+  uint32_t* myrow = rows + T + tid;     // real word 0
+  const int R = a.R;
+  unsigned char* padrow_b = reinterpret_cast<unsigned char*>(padrow);
+  const int stride_b = 4 * T;
+  const int fov0p = a.fov0p;           // first visible padded position
+  const unsigned span = a.span;        // number of visible positions (vf_supcalc.py:119)
+  const float width = a.width, height = a.height, half_w = a.half_w, half_h = a.half_h;
+  unsigned n_mismatch = 0;
 
   for (int st = 0; st < n_stage; ++st) {
     if (tid == 0 && st + 1 < n_stage) {
@@ -124,39 +155,44 @@ vf_step_kernel(const VFKernelArgs a) {
     const float4* tile_recs = recs + (st & 1) * kRecTile;
     const int nj = min(kRecTile, a.N - st * kRecTile);
     if (active) {
+      const float4* rend = tile_recs + nj;
 #pragma unroll 2
-      for (int jj = 0; jj < nj; ++jj) {
-        const float4 o = tile_recs[jj];                      // broadcast LDS.128
-        // centre difference: positions first (exact for close neighbours), then radii
-        const float dr = o.z - me.z;
-        float dx = (o.x - me.x) + dr;
-        float dy = (o.y - me.y) + dr;
-        if (torus) {                                         // vf_supcalc.py:70-83
-          if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
-          if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+      for (const float4* rp = tile_recs; rp < rend; ++rp) {
+        const float4 o = *rp;                                // broadcast LDS.128
+        float dx, dy;
+        if (UNIFORM_R) {
+          dx = o.x - me.x; dy = o.y - me.y;
+        } else {   // positions first (exact for close neighbours), then radii
+          const float dr = o.z - me.z;
+          dx = (o.x - me.x) + dr; dy = (o.y - me.y) + dr;
+        }
+        if (TORUS) {                                         // vf_supcalc.py:70-83
+          if (fabsf(dx) > half_w) dx -= copysignf(width, dx);
+          if (fabsf(dy) > half_h) dy -= copysignf(height, dy);
         }
         const float d2 = fmaf(dx, dx, dy * dy);
-        const bool same = (o.x == me.x) & (o.y == me.y);     // vf_supcalc.py:57 (covers j == i)
-        if (same | (d2 > o.w) | !(d2 > 0.0f)) continue;      // o.w: beyond it the half width is 0
-        const PairFast pf = vf_pair_fast(dx, dy, d2, o.z, c, s, bc);
-        if (fixup && pf.flagged) {
-          const int slot = atomicAdd(qcount, 1);
-          const int j = st * kRecTile + jj;
-          if (slot < kQueueCap) {
-            queue[2 * slot] = ((uint32_t)tid << 24) | (uint32_t)j;
-            queue[2 * slot + 1] = ((uint32_t)pf.k << 16) | ((uint32_t)pf.h & 0xffffu);
-          } else {   // queue full: evaluate here and now
-            const FocalExact fe = vf_focal_exact(me.x, me.y, me.z, th);
-            const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, a.R,
-                                               a.lin_step);
-            if (pe.valid) vf_draw<true>(myrow, T, a.R, a.fov_px0, a.fov_px1, pe.k, pe.h);
-            n_mismatch += (pe.k != pf.k) | (pe.h != pf.h);
-            ++n_inline;
+        if (CULL) { if (d2 > o.w) continue; }                // o.w: beyond it the half width is 0
+        if (!UNIFORM_R) { if ((o.x == me.x) & (o.y == me.y)) continue; }   // vf_supcalc.py:57
+        const PairFast pf = vf_pair_fast(dx, dy, d2, o.z, c, ns, bc);
+        const int ps = pf.k - pf.h, pe = pf.k + pf.h;        // padded positions
+        const bool vis = ((unsigned)(ps - fov0p) < span) | ((unsigned)(pe - fov0p) < span);   // vf_supcalc.py:119
+        if (!pf.flagged & vis & ((unsigned)(pf.h - 1) < 16u)) {
+          vf_draw_short(padrow_b, stride_b, ps, pf.h);
+        } else if (pf.flagged) {
+          // deferred to fp64 (self / exactly coincident positions are skipped: vf_supcalc.py:57)
+          if (!((o.x == me.x) & (o.y == me.y))) {
+            const int slot = atomicAdd(qcount, 1);           // keeps counting past the capacity
+            if (slot < kQueueCap) {
+              queue[2 * slot] = ((uint32_t)tid << 24) | (uint32_t)(st * kRecTile + (int)(rp - tile_recs));
+              queue[2 * slot + 1] = ((uint32_t)(pf.k - 32) << 16) | ((uint32_t)pf.h & 0xffffu);
+            } else {
+              vf_exact_inline(a, myrow, T, me, (size_t)b * a.N + i, o, pf.k - 32, pf.h);
+            }
           }
-          ++n_flag;
-          continue;
+        } else if (vis & (pf.h > 16)) {
+          if ((ps >= 0) & (pe <= R + 62)) vf_draw_wide(padrow_b, stride_b, ps, pe);
+          else vf_draw_general(a, myrow, T, pf.k - 32, pf.h);
         }
-        vf_draw<false>(myrow, T, a.R, a.fov_px0, a.fov_px1, pf.k, pf.h);
       }
     }
     __syncthreads();   // everyone is done with this stage before it is refilled
@@ -170,32 +206,21 @@ vf_step_kernel(const VFKernelArgs a) {
       const int ft = (int)(q0 >> 24);
       const int j = (int)(q0 & 0xffffffu);
       const int fi = a.tile_begin + tile * T + ft;
-      const float4 f4 = rep_in[fi];
-      const float fth = a.theta[(size_t)b * a.N + fi];
-      const float4 o = rep_in[j];
-      const FocalExact fe = vf_focal_exact(f4.x, f4.y, f4.z, fth);
-      const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, a.R, a.lin_step);
-      if (pe.valid) vf_draw<true>(rows + ft, T, a.R, a.fov_px0, a.fov_px1, pe.k, pe.h);
-      n_mismatch += (pe.k != (int)(q1 >> 16)) | (pe.h != (int)(q1 & 0xffffu));
+      n_mismatch += vf_exact_and_draw(a, rows + T + ft, T, rep_in[fi], a.theta[(size_t)b * a.N + fi], rep_in[j],
+                                      (int)(q1 >> 16), (int)(short)(q1 & 0xffffu));
     }
   }
   __syncthreads();
 
   // ---- counters (one atomic per warp) ----
   {
-    for (int off = 16; off > 0; off >>= 1) {
-      n_flag += __shfl_down_sync(0xffffffffu, n_flag, off);
-      n_inline += __shfl_down_sync(0xffffffffu, n_inline, off);
-      n_mismatch += __shfl_down_sync(0xffffffffu, n_mismatch, off);
-    }
-    if ((tid & 31) == 0) {
-      if (n_flag) atomicAdd(&a.counters[0], (unsigned long long)n_flag);
-      if (n_inline) atomicAdd(&a.counters[1], (unsigned long long)n_inline);
-      if (n_mismatch) atomicAdd(&a.counters[2], (unsigned long long)n_mismatch);
-    }
+    const unsigned nm = __reduce_add_sync(0xffffffffu, n_mismatch);
+    if ((tid & 31) == 0 && nm) atomicAdd(&a.counters[2], (unsigned long long)nm);
+    if (tid == 0 && *qcount) atomicAdd(&a.counters[0], (unsigned long long)*qcount);   // all flagged pairs
   }
 
   if (!active) return;
+  vf_fold_padding(padrow, T, a.R, a.W);
 
   // ---- epilogue: edges, integrals, kinematics (fp64) ----
   const size_t gi = (size_t)b * a.N + i;
@@ -220,7 +245,7 @@ vf_step_kernel(const VFKernelArgs a) {
   sincos(nth, &sn, &cn);
   double nx = (double)me.x + nv * cn;                           // :303-306
   double ny = (double)me.y - nv * sn;
-  if (a.boundary == 0) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
+  if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
   else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
 
   a.rec_out[gi] = make_float4((float)nx, (float)ny, me.z, me.w);
@@ -238,17 +263,33 @@ vf_step_kernel(const VFKernelArgs a) {
   }
 }
 
-void launch_vf_step(const VFKernelArgs& a, cudaStream_t stream) {
+template <bool TORUS, bool UNIFORM_R, bool CULL>
+static void launch_variant(const VFKernelArgs& a, unsigned grid, int T, size_t smem, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(vf_step_kernel<TORUS, UNIFORM_R, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    configured = smem;
+  }
+  vf_step_kernel<TORUS, UNIFORM_R, CULL><<<grid, T, smem, stream>>>(a);
+}
+
+void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream) {
   const int T = vf_step_threads(a.tile_count);
   const int tiles_per_rep = (a.tile_count + T - 1) / T;
   const size_t smem = vf_step_smem_bytes(T, a.W);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(vf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   const unsigned grid = (unsigned)((size_t)a.B * tiles_per_rep);
-  vf_step_kernel<<<grid, T, smem, stream>>>(a);
+  const int v = (a.boundary == 1 ? 4 : 0) | (uniform_r ? 2 : 0) | (cull ? 1 : 0);
+  switch (v) {
+    case 0: launch_variant<false, false, false>(a, grid, T, smem, stream); break;
+    case 1: launch_variant<false, false, true>(a, grid, T, smem, stream); break;
+    case 2: launch_variant<false, true, false>(a, grid, T, smem, stream); break;
+    case 3: launch_variant<false, true, true>(a, grid, T, smem, stream); break;
+    case 4: launch_variant<true, false, false>(a, grid, T, smem, stream); break;
+    case 5: launch_variant<true, false, true>(a, grid, T, smem, stream); break;
+    case 6: launch_variant<true, true, false>(a, grid, T, smem, stream); break;
+    default: launch_variant<true, true, true>(a, grid, T, smem, stream); break;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -273,7 +314,7 @@ __global__ void vf_projection_kernel(const VFProjArgs a) {
       if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
     }
     const float d2 = fmaf(dx, dx, dy * dy);
-    bool in_range = d2 > 0.0f;
+    bool in_range = true;
     if (a.vision_range >= 0.0) {                              // :91-93 (decided in fp64)
       const double ddx = dx, ddy = dy;
       in_range &= !(sqrt(ddx * ddx + ddy * ddy) > a.vision_range);
@@ -281,13 +322,13 @@ __global__ void vf_projection_kernel(const VFProjArgs a) {
     if (in_range) {
       double sd, cd;
       sincos((double)a.ftheta, &sd, &cd);
-      BinConsts bc{a.inv_step, a.t_frac, a.k_off, a.y_scale, a.tau_k, a.tau_h_abs, a.tau_h_rel, a.ca_guard};
-      const PairFast pf = vf_pair_fast(dx, dy, d2, orad, (float)cd, (float)sd, bc);
-      int k = pf.k, h = pf.h;
+      const BinConsts bc{a.inv_step, a.t_half, a.k_bias, a.y_scale, a.thr_k, a.thr_h0, a.thr_h1, a.ca_guard};
+      const PairFast pf = vf_pair_fast(dx, dy, d2, orad, (float)cd, (float)(-sd), bc);
+      int k = pf.k - 32, h = pf.h;
       if (pf.flagged) {
         const FocalExact fe = vf_focal_exact(a.fx, a.fy, a.fr, a.ftheta);
         const PairExact pe = vf_pair_exact(fe, ox, oy, orad, a.boundary, a.width_d, a.height_d, a.R, a.lin_step);
-        k = pe.k; h = pe.h;
+        k = pe.k; h = pe.valid ? pe.h : 0;
       }
       vf_draw<false>(tmp, 1, a.R, a.fov_px0, a.fov_px1, k, h);
     }
@@ -314,11 +355,21 @@ void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const V
 
 // SoA host-facing state <-> packed neighbour records
 __global__ void pack_records_kernel(const float* x, const float* y, const float* r, float cull_scale,
-                                    float4* rec, long long n) {
+                                    float4* rec, unsigned* radius_minmax, long long n) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float rr = 0.f;
   if (g < n) {
-    const float rr = r[g];
+    rr = r[g];
     rec[g] = make_float4(x[g], y[g], rr, rr * rr * cull_scale);
+  }
+  // min / max radius of the batch (non-negative floats order like their bit patterns)
+  unsigned lo = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0x7f800000u;
+  unsigned hi = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0u;
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&radius_minmax[0], lo);
+    atomicMax(&radius_minmax[1], hi);
   }
 }
 __global__ void unpack_records_kernel(const float4* rec, float* x, float* y, long long n) {
@@ -330,9 +381,10 @@ __global__ void unpack_records_kernel(const float4* rec, float* x, float* y, lon
   }
 }
 void launch_pack_records(const float* x, const float* y, const float* r, float cull_scale, float4* rec,
-                         long long n, cudaStream_t stream) {
+                         unsigned* radius_minmax, long long n, cudaStream_t stream) {
   const int threads = 256;
-  pack_records_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(x, y, r, cull_scale, rec, n);
+  pack_records_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(x, y, r, cull_scale, rec,
+                                                                                      radius_minmax, n);
 }
 void launch_unpack_records(const float4* rec, float* x, float* y, long long n, cudaStream_t stream) {
   const int threads = 256;

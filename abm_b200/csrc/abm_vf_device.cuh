@@ -32,53 +32,69 @@ __device__ __forceinline__ float atan_unit(float q) {
   return p * q;
 }
 
+// single-instruction MUFU reciprocal / reciprocal square root (no denormal fix-up code)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // atan2(w, u) in (-pi, pi]; abs error ~1e-6 rad, absorbed by the tau_k guard band.
 __device__ __forceinline__ float atan2_fast(float w, float u) {
   const float au = fabsf(u), aw = fabsf(w);
   const float mx = fmaxf(au, aw), mn = fminf(au, aw);
-  float p = atan_unit(__fdividef(mn, mx));
+  float p = atan_unit(mn * rcp_approx(mx));
   if (aw > au) p = 1.57079632679489662f - p;
   if (u < 0.0f) p = 3.14159265358979324f - p;
   return copysignf(p, w);
 }
 
 // Static per-launch constants of the fp32 bin arithmetic.
+//   k = ceil(ca * inv_step + t_frac) + k_off = rint(ca * inv_step + t_half) + k_off   (t_half = t_frac + 0.5)
+//   h = floor(y) = rint(y - 0.5),  y = atan(r / d) * y_scale
+// Both identities fail only where the argument is within the fp32 error bound of an integer
+// -- exactly the pairs that are flagged for fp64 re-evaluation anyway.
 struct BinConsts {
-  float inv_step, t_frac; int k_off;
-  float y_scale, tau_k, tau_h_abs, tau_h_rel;
-  float ca_guard;   // |ca| beyond this is within the error bound of the +-pi seam
+  float inv_step, t_half;
+  int k_bias;               // k_off - 0x4B400000 (bit pattern of the rounding constant) + 32 (row padding)
+  float y_scale;
+  float thr_k;              // 0.5 - tau_k           (+inf: guard band off = fp32-only mode)
+  float thr_h0, thr_h1;     // 0.5 - tau_h(y') = thr_h0 + thr_h1 * y'
+  float ca_guard;           // |ca| beyond this is within the error bound of the +-pi seam
 };
 
 // Result of the fp32 evaluation of one (focal, object) pair.
 struct PairFast {
-  int k, h;        // centre bin, half width
-  bool flagged;    // k or h within the fp32 error bound of a rounding boundary (or q > 1)
+  int k, h;        // centre bin IN PADDED POSITIONS (real bin + 32), half width
+  bool flagged;    // must be re-evaluated in fp64: k or h within the fp32 error bound of a rounding
+                   // boundary, angle on the +-pi seam, overlapping / coincident centres (q > 1, NaN)
 };
 
-// (dx, dy): centre difference object - focal (screen coords, y down); (c, s) = cos/sin of the
-// focal heading; r_obj: object radius; d2 = dx^2 + dy^2 > 0.
+// (dx, dy): centre difference object - focal (screen coords, y down); (c, ns) = (cos, -sin) of
+// the focal heading; r_obj: object radius; d2 = dx^2 + dy^2 (0 -> flagged).
 __device__ __forceinline__ PairFast vf_pair_fast(float dx, float dy, float d2, float r_obj,
-                                                 float c, float s, const BinConsts& bc) {
+                                                 float c, float ns, const BinConsts& bc) {
   PairFast o;
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (x + MAGIC) - MAGIC == rint(x), low bits of x + MAGIC = rint(x)
   // rotate (dx, -dy) by -theta: closed angle = atan2(w, u)  (== -angle_between remapped, A.1)
-  const float u = fmaf(dx, c, -dy * s);
-  const float w = -fmaf(dx, s, dy * c);
+  const float u = fmaf(dx, c, dy * ns);          //  dx cos - dy sin
+  const float w = fmaf(dx, ns, -(dy * c));       // -dx sin - dy cos
   const float ca = atan2_fast(w, u);
-  // k = first-argmin |phis - ca| = ceil(x - 0.5), x = (ca + pi) / step   (A.2)
-  const float t = fmaf(ca, bc.inv_step, bc.t_frac);
-  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: (t + MAGIC) - MAGIC == rint(t)
+  const float t = fmaf(ca, bc.inv_step, bc.t_half);
   const float tr = t + MAGIC;
-  const float df = t - (tr - MAGIC);                       // in [-0.5, 0.5]
-  o.k = (__float_as_int(tr) - 0x4B400000) + (df > 0.0f ? 1 : 0) + bc.k_off;
-  bool flagged = (fabsf(df) < bc.tau_k) | (fabsf(ca) > bc.ca_guard);
-  // h = floor(proj_size / 2), proj_size / 2 = atan(r / d) * R / 2pi
-  const float q = r_obj * rsqrtf(d2);
-  flagged |= (q > 1.0f);
-  const float y = atan_unit(fminf(q, 1.0f)) * bc.y_scale;
+  o.k = __float_as_int(tr) + bc.k_bias;
+  bool flagged = (fabsf(t - (tr - MAGIC)) > bc.thr_k) | (fabsf(ca) > bc.ca_guard);
+  const float q = r_obj * rsqrt_approx(d2);
+  flagged |= !(q <= 1.0f);                                 // also catches d2 == 0 (inf / NaN)
+  const float y = fmaf(atan_unit(q), bc.y_scale, -0.5f);
   const float yr = y + MAGIC;
-  const float dy_ = y - (yr - MAGIC);
-  o.h = (__float_as_int(yr) - 0x4B400000) - (dy_ < 0.0f ? 1 : 0);
-  flagged |= fabsf(dy_) < fmaf(y, bc.tau_h_rel, bc.tau_h_abs);
+  o.h = __float_as_int(yr) - 0x4B400000;
+  flagged |= fabsf(y - (yr - MAGIC)) > fmaf(y, bc.thr_h1, bc.thr_h0);
   o.flagged = flagged;
   return o;
 }
@@ -88,12 +104,14 @@ __device__ __forceinline__ PairFast vf_pair_fast(float dx, float dy, float d2, f
 // ---------------------------------------------------------------------------------------
 
 struct FocalExact {
+  float px, py;      // top-left position (exact-coincidence test, vf_supcalc.py:57)
   double cix, ciy;   // centre (vf_supcalc.py:42)
   double u1x, u1y;   // unit heading vector v1 / |v1| (vf_supcalc.py:45-49, supcalc.py:14)
 };
 
 __device__ __forceinline__ FocalExact vf_focal_exact(float px, float py, float r, float theta) {
   FocalExact f;
+  f.px = px; f.py = py;
   const double x = px, y = py, rr = r, th = theta;
   f.cix = __dadd_rn(x, rr);
   f.ciy = __dadd_rn(y, rr);
@@ -130,6 +148,7 @@ __device__ __noinline__ PairExact vf_pair_exact(const FocalExact& f, float ox, f
                                                 int boundary, double width, double height,
                                                 int R, double lin_step) {
   PairExact o;
+  const bool same_pos = (ox == f.px) && (oy == f.py);                       // :57
   const double rr = orad;
   double cjx = __dadd_rn((double)ox, rr), cjy = __dadd_rn((double)oy, rr);   // :61-64
   double v2x = __dadd_rn(cjx, -f.cix), v2y = __dadd_rn(cjy, -f.ciy);
@@ -155,7 +174,7 @@ __device__ __noinline__ PairExact vf_pair_exact(const FocalExact& f, float ox, f
   const double proj = __dmul_rn(__ddiv_rn(vis, ABM_TWO_PI_D), (double)R);   // :114
   o.k = nearest_bin_exact(ca, R, lin_step);                                 // :102
   o.h = (int)floor(__ddiv_rn(proj, 2.0));                                   // :116
-  o.valid = (n2 > 0.0);
+  o.valid = (n2 > 0.0) && !same_pos;
   return o;
 }
 
@@ -200,6 +219,74 @@ __device__ __forceinline__ void vf_draw(uint32_t* f, int stride, int R, int fov0
     pe = R;
   }
   if (pe > ps) set_range<ATOMIC>(f, stride, ps, pe);                        // :129
+}
+
+// The slow, fully general rule kept out of line so the pair loop stays small (f: real word 0).
+__device__ __noinline__ void vf_draw_general(uint32_t* f, int stride, int R, int fov0, int fov1, int k, int h) {
+  vf_draw<false>(f, stride, R, fov0, fov1, k, h);
+}
+
+// Hot-path drawing into a PADDED private row: word 0 of the padded row holds the virtual bins
+// [-32, 0), words 1.. the real bins, and one more word follows the last real word, so an
+// interval that leaves [0, R) by at most 32 bins is drawn without any wrap logic; the padding
+// is folded back onto the ring once per step (vf_fold_padding).  `f` points at padded word 0.
+//   VF wrap rule (vf_supcalc.py:122-127): bins below 0 wrap to R + bin; an interval reaching
+//   pe >= R additionally sets bin pe - R (the slice end is pe - (R - 1)), i.e. it is drawn as
+//   [ps, pe + 1) on the ring.
+// An interval of at most 32 bins touches at most two words: one funnel shift each.
+// Interval [ps, ps + 2h) in PADDED bit positions (real bin + 32), 1 <= h <= 16.  The extra
+// wrap bin of the reference is added once per step in vf_fold_padding, not per interval.
+__device__ __forceinline__ void vf_draw_short(unsigned char* row_bytes, int stride_bytes, int ps_padded, int h) {
+  const uint32_t t = 0xffffffffu >> (32 - 2 * h);
+  uint32_t* p = reinterpret_cast<uint32_t*>(row_bytes + (ps_padded >> 5) * stride_bytes);
+  const uint32_t lo = __funnelshift_l(0u, t, ps_padded);   // t << (ps & 31)
+  const uint32_t hi = __funnelshift_l(t, 0u, ps_padded);   // bits shifted out into the next word
+  *p |= lo;
+  if (hi) *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(p) + stride_bytes) |= hi;
+}
+
+// Wide interval (h > 16) that still fits in the padded row: first / middle / last word.
+// [ps, pe) in padded positions, 0 <= ps, pe <= R + 62.
+__device__ __forceinline__ void vf_draw_wide(unsigned char* row_bytes, int stride_bytes, int ps_padded, int pe_padded) {
+  const int w0 = ps_padded >> 5, w1 = (pe_padded - 1) >> 5;   // w1 > w0 because the interval has > 32 bins
+  unsigned char* p = row_bytes + w0 * stride_bytes;
+  *reinterpret_cast<uint32_t*>(p) |= __funnelshift_l(0u, 0xffffffffu, ps_padded);
+#pragma unroll 1
+  for (int w = w0 + 1; w < w1; ++w) {
+    p += stride_bytes;
+    *reinterpret_cast<uint32_t*>(p) = 0xffffffffu;
+  }
+  p += stride_bytes;
+  *reinterpret_cast<uint32_t*>(p) |= 0xffffffffu >> ((32 - pe_padded) & 31);
+}
+
+// Fold the padding words back onto the ring and clear them.  `f` points at padded word 0.
+// Intervals drawn by vf_draw_short that reach pe >= R cover bin R-1 and spill into [R, R+32);
+// the reference gives each of them the slice [0, pe - R + 1), so their union is the spilled
+// bits shifted up by one bin with bin 0 added (vf_supcalc.py:125-127).  (An interval drawn by
+// the general rule with ps < 0 also covers bin R-1, but it always covers bin 0 as well, so
+// taking it for a reaching interval is harmless.)
+__device__ __forceinline__ void vf_fold_padding(uint32_t* f, int stride, int R, int W) {
+  const bool reach = (f[(((R - 1) >> 5) + 1) * stride] >> ((R - 1) & 31)) & 1u;
+  // overflow: ring bins [R, R + 32) (padded positions [R + 32, R + 64)) -> bins [0, 32) = padded word 1
+  {
+    const int pos = R + 32, w = pos >> 5, sh = pos & 31;
+    const uint32_t lo = f[w * stride];
+    const uint32_t hi = (w + 1 < W + 2) ? f[(w + 1) * stride] : 0u;
+    const uint32_t ov = sh ? __funnelshift_r(lo, hi, sh) : lo;
+    if (reach) f[stride] |= (ov << 1) | 1u;
+    // clear everything at or beyond ring bin R
+    f[w * stride] = sh ? (lo & ((1u << sh) - 1u)) : 0u;
+    if (w + 1 < W + 2) f[(w + 1) * stride] = 0u;
+  }
+  // underflow: virtual bins [-32, 0) -> ring bins [R - 32, R) = padded positions [R, R + 32)
+  const uint32_t un = f[0];
+  if (un) {
+    const int sh = R & 31, w = R >> 5;
+    f[w * stride] |= un << sh;
+    if (sh) f[(w + 1) * stride] |= un >> (32 - sh);
+    f[0] = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------

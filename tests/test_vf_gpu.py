@@ -254,9 +254,14 @@ def test_fixup_counters_and_fp32_only_mode(built_lib):
     assert 0 < cnt["fp64_pairs"] < 0.02 * pairs          # a small fraction goes through fp64
     assert cnt["fp32_fp64_differ"] <= cnt["fp64_pairs"]
     diff_agents = int((fe != ff).any(axis=-1).sum())
-    # every differing agent differs by isolated single bins (an edge moved by one bin)
+    # an fp32-only field may differ from the exact one only by edges moved by ONE bin: every
+    # differing bin is isolated (its ring neighbours agree) and sits on an edge of the exact field
     d = (fe != ff)
-    assert d.sum() <= 4 * max(diff_agents, 1)
+    assert not (d & np.roll(d, 1, axis=-1)).any(), "differences wider than one bin"
+    edges = fe != np.roll(fe, 1, axis=-1)
+    near_edge = edges | np.roll(edges, -1, axis=-1)
+    assert not (d & ~near_edge).any(), "difference away from an edge"
+    assert diff_agents <= 0.2 * B * N
     print(f"fp64 pairs {cnt['fp64_pairs']} of {pairs} ({cnt['fp64_pairs'] / pairs:.2e}); fp32/fp64 index "
           f"differences {cnt['fp32_fp64_differ']}; agents whose fp32-only field differs: {diff_agents} of {B * N}")
     exact.close(); fast.close()
