@@ -6,5 +6,6 @@ ctypes); this package is the host-side mirror of the reference's Python interfac
 There is no CPU fallback."""
 from ._lib import AbmError, LIB_PATH  # noqa: F401
 from .engine import VFEngine  # noqa: F401
+from .base_engine import BaseEngine  # noqa: F401
 
 __version__ = "0.1.0"

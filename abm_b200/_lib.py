@@ -51,6 +51,41 @@ class VFProjArgs(C.Structure):
     ]
 
 
+class BaseConfig(C.Structure):
+    """abm_base_config_t"""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_replicates", C.c_int32), ("n_agents", C.c_int32), ("n_patches", C.c_int32),
+        ("resolution", C.c_int32), ("tau", C.c_int32), ("visual_exclusion", C.c_int32),
+        ("patchwise_exclusion", C.c_int32), ("teleport_exploit", C.c_int32), ("regenerate_patches", C.c_int32),
+        ("patch_border_overlap", C.c_int32), ("keep_fields", C.c_int32),
+        ("fov0", C.c_double), ("fov1", C.c_double),
+        ("width", C.c_double), ("height", C.c_double), ("window_pad", C.c_double),
+        ("vision_range", C.c_double), ("agent_radius", C.c_double), ("patch_radius", C.c_double),
+        ("min_quality", C.c_double), ("max_quality", C.c_double),
+        ("min_units", C.c_int32), ("max_units", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
+BASE_AGENT_FIELDS = [("x", "f"), ("y", "f"), ("theta", "f"), ("vel", "f"), ("w", "f"), ("u", "f"),
+                     ("collected", "f"), ("collected_before", "f"), ("i_priv", "f"),
+                     ("env_status", "i"), ("override_mode", "i"), ("mode", "i"), ("patch_id", "i"), ("novelty", "u")]
+BASE_PATCH_FIELDS = [("x", "f"), ("y", "f"), ("radius", "f"), ("left", "f"), ("quality", "f"), ("id", "i")]
+BASE_NPARAM = 20
+BASE_PARAM_NAMES = ["T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u", "u_max", "S_wu", "S_uw",
+                    "F_N", "F_R", "exp_vel_max", "exp_theta_min", "exp_theta_max", "reloc_theta_max",
+                    "exp_stop_ratio", "agent_consumption"]
+
+
+class BaseAgents(C.Structure):
+    """abm_base_agents_t"""
+    _fields_ = [(n, C.c_void_p) for n, _ in BASE_AGENT_FIELDS]
+
+
+class BasePatches(C.Structure):
+    """abm_base_patches_t"""
+    _fields_ = [(n, C.c_void_p) for n, _ in BASE_PATCH_FIELDS]
+
+
 # every symbol include/abm_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -72,6 +107,16 @@ SYMBOLS = {
     "abm_synchronize": (C.c_int, [_P, _P]),
     "abm_vf_projection_field": (C.c_int, [C.POINTER(VFProjArgs), _P]),
     "abm_vf_flocking_terms": (C.c_int, [_P, C.c_int, C.c_double, _P, C.POINTER(C.c_double)]),
+    "abm_base_create": (C.c_int, [C.POINTER(BaseConfig), C.c_int, C.POINTER(_P)]),
+    "abm_base_destroy": (C.c_int, [_P]),
+    "abm_base_set_params": (C.c_int, [_P, _P, C.c_int]),
+    "abm_base_set_agents": (C.c_int, [_P, C.POINTER(BaseAgents), C.c_int, _P]),
+    "abm_base_get_agents": (C.c_int, [_P, C.POINTER(BaseAgents), C.c_int, _P]),
+    "abm_base_set_patches": (C.c_int, [_P, C.POINTER(BasePatches), C.c_int, _P]),
+    "abm_base_get_patches": (C.c_int, [_P, C.POINTER(BasePatches), C.c_int, _P]),
+    "abm_base_step": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_uint32, _P]),
+    "abm_base_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
+    "abm_base_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
 }
 
 _lib = None

@@ -12,38 +12,21 @@
 
 #include "abm_common.cuh"
 
-namespace {
+#include "abm_api_util.cuh"
 
-thread_local std::string g_last_error;
-
-int fail(int code, const std::string& msg) {
+namespace abm {
+static thread_local std::string g_last_error;
+int api_fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+const char* api_last_error() { return g_last_error.c_str(); }
+}  // namespace abm
 
-#define ABM_CUDA(expr)                                                                         \
-  do {                                                                                         \
-    cudaError_t _e = (expr);                                                                   \
-    if (_e != cudaSuccess) {                                                                   \
-      char _b[512];                                                                            \
-      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-      return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? ABM_E_NO_DEVICE : ABM_E_CUDA, _b); \
-    }                                                                                          \
-  } while (0)
+namespace {
 
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  cudaError_t alloc(size_t count) {
-    n = count;
-    return cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * (count ? count : 1));
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-  }
-};
+using abm::DevBuf;
+inline int fail(int code, const std::string& msg) { return abm::api_fail(code, msg); }
 
 // Bin / integration-grid constants shared by the engine and the stateless entry points.
 struct GridConsts {
@@ -144,7 +127,7 @@ extern "C" {
 
 int abm_version(void) { return ABM_B200_VERSION; }
 
-const char* abm_last_error(void) { return g_last_error.c_str(); }
+const char* abm_last_error(void) { return abm::api_last_error(); }
 
 int abm_device_count(void) {
   int n = 0;

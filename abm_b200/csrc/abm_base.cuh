@@ -1,0 +1,63 @@
+// Declarations of the BASE (collective foraging) path.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "abm_common.cuh"
+
+namespace abm {
+
+// override codes (Agent.overriding_mode, agent.py:671-693) and logged mode codes (ifdb.py:197-206)
+enum { OV_NONE = 0, OV_EXPLOIT = 1, OV_COLLIDE = 3 };
+enum { MODE_EXPLORE = 0, MODE_EXPLOIT = 1, MODE_RELOCATE = 2, MODE_COLLIDE = 3 };
+
+// per-replicate decision / movement parameters, order of ABM_BASE_* in include/abm_b200.h
+struct BaseParams {
+  double T_w, Eps_w, g_w, B_w, w_max;
+  double T_u, Eps_u, g_u, B_u, u_max;
+  double S_wu, S_uw, F_N, F_R;
+  double exp_vel_max, exp_theta_min, exp_theta_max, reloc_theta_max, exp_stop_ratio;
+  double consumption;
+};
+constexpr int kBaseNParam = 20;
+
+struct BaseAgentPtrs {
+  float *x, *y, *theta, *vel, *w, *u, *collected, *collected_before, *i_priv;
+  int32_t *env_status, *override_mode, *mode, *patch_id;
+  uint32_t* novelty;   // Tau-bit shift register: bit t = novelty[t] (sims.py:33-37)
+  // frozen snapshot read by the agent phase (Jacobi update): written at the end of the environment phase
+  float *snap_x, *snap_y;
+  int32_t* snap_override;
+};
+struct BasePatchPtrs {
+  float *x, *y, *radius, *left, *quality;
+  int32_t* id;
+};
+
+struct BaseKernelArgs {
+  int B, N, P, R, W, Tau;
+  int visual_exclusion, patchwise_exclusion, teleport_exploit, regenerate, border_overlap;
+  double fov0, fov1;           // agent FOV in radians (strict test on the closed angle, agent.py:535)
+  int mask_lo, mask_hi;        // stored bins kept by the FOV mask: phis[b] >= fov0 && phis[b] <= fov1 (agent.py:594-595)
+  double lin_step;             // numpy linspace step (see nearest_bin_exact)
+  double width, height, pad, vision_range, radius;
+  // patch regeneration (sims.py:332-374)
+  double patch_radius, min_quality, max_quality;
+  int min_units, max_units;
+  unsigned long long seed;
+  unsigned step;               // time step index, part of the RNG counter
+  BaseAgentPtrs ag;            // B*N, updated in place
+  BasePatchPtrs pa;            // B*P, updated in place
+  const double* params;        // n_sets * kBaseNParam
+  int param_stride;            // 0 or kBaseNParam
+  const float* inject_dtheta;  // nullable, B*N: replaces the random-walk draw (parity tests)
+  uint32_t* fields_out;        // nullable, B*N*W, stored order
+  unsigned long long* counters;   // [0] patches regenerated, [1] regeneration retries exhausted
+};
+
+void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream);
+void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream);
+size_t base_agents_smem_bytes(int N, int W, int warps);
+int base_agents_warps(int N, int W, size_t smem_limit);
+
+}  // namespace abm

@@ -1,0 +1,278 @@
+// C ABI of the BASE / collective-foraging engine (declared in include/abm_b200.h).
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "abm_api_util.cuh"
+#include "abm_base.cuh"
+
+using abm::DevBuf;
+
+struct abm_base_engine {
+  abm_base_config_t cfg;
+  int device = 0;
+  int W = 0, mask_lo = 0, mask_hi = -1;
+  double lin_step = 0.0;
+  size_t n_agents_total = 0, n_patches_total = 0;
+  DevBuf<float> x, y, theta, vel, w, u, collected, collected_before, i_priv, snap_x, snap_y;
+  DevBuf<int32_t> env_status, override_mode, mode, patch_id, snap_override;
+  DevBuf<uint32_t> novelty, fields;
+  DevBuf<float> px, py, pradius, pleft, pquality;
+  DevBuf<int32_t> pid;
+  DevBuf<double> params;
+  DevBuf<float> inject;
+  DevBuf<unsigned long long> counters;
+  int n_param_sets = 1;
+  bool agents_set = false, patches_set = false;
+  unsigned step = 0;
+  unsigned long long launches = 0, steps = 0;
+};
+
+namespace {
+
+inline int fail(int code, const std::string& msg) { return abm::api_fail(code, msg); }
+
+template <typename T>
+int xfer(T* dev, const T* host_or_dev, T* out, size_t n, bool to_device, int on_device, cudaStream_t st) {
+  // to_device: copy src(host_or_dev) -> dev ; else dev -> out
+  if (to_device) {
+    if (!host_or_dev) return ABM_OK;
+    ABM_CUDA(cudaMemcpyAsync(dev, host_or_dev, sizeof(T) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  } else {
+    if (!out) return ABM_OK;
+    ABM_CUDA(cudaMemcpyAsync(out, dev, sizeof(T) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  }
+  return ABM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t** out) {
+  if (!cfg || !out) return fail(ABM_E_INVALID, "abm_base_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(abm_base_config_t))
+    return fail(ABM_E_INVALID, "abm_base_create: struct_size mismatch (header / library version skew)");
+  if (cfg->n_replicates < 1 || cfg->n_agents < 1 || cfg->n_patches < 0)
+    return fail(ABM_E_INVALID, "abm_base_create: bad batch shape");
+  if (cfg->resolution < 8 || cfg->resolution > 65535) return fail(ABM_E_INVALID, "abm_base_create: bad resolution");
+  if (cfg->tau < 1 || cfg->tau > 32) return fail(ABM_E_INVALID, "abm_base_create: tau must be in [1, 32]");
+  if (!(cfg->agent_radius > 0.0)) return fail(ABM_E_INVALID, "abm_base_create: agent_radius must be > 0");
+  int ndev = 0;
+  ABM_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1 || device < 0 || device >= ndev) return fail(ABM_E_NO_DEVICE, "abm_base_create: no such CUDA device");
+  ABM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ABM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(ABM_E_NO_DEVICE, "abm_base_create: device is not sm_100");
+  abm_base_engine* e = new (std::nothrow) abm_base_engine();
+  if (!e) return fail(ABM_E_INVALID, "abm_base_create: out of host memory");
+  e->cfg = *cfg;
+  e->device = device;
+  const int R = cfg->resolution;
+  e->W = (R + 31) / 32;
+  e->lin_step = ABM_TWO_PI_D / (double)(R - 1);
+  // FOV mask in stored coordinates (agent.py:594-595) on the numpy linspace grid
+  e->mask_lo = R; e->mask_hi = -1;
+  for (int k = 0; k < R; ++k) {
+    const double phi = (k == R - 1) ? ABM_PI_D : ((double)k * e->lin_step + (-ABM_PI_D));
+    if (!(phi < cfg->fov0) && !(phi > cfg->fov1)) {
+      if (k < e->mask_lo) e->mask_lo = k;
+      if (k > e->mask_hi) e->mask_hi = k;
+    }
+  }
+  if (abm::base_agents_smem_bytes(cfg->n_agents, e->W, 1) > (size_t)prop.sharedMemPerBlockOptin) {
+    delete e;
+    return fail(ABM_E_INVALID, "abm_base_create: n_agents too large for the per-warp occlusion buffers");
+  }
+  const size_t na = e->n_agents_total = (size_t)cfg->n_replicates * cfg->n_agents;
+  const size_t np = e->n_patches_total = (size_t)cfg->n_replicates * cfg->n_patches;
+  cudaError_t err = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
+  for (DevBuf<float>* b : {&e->x, &e->y, &e->theta, &e->vel, &e->w, &e->u, &e->collected, &e->collected_before,
+                           &e->i_priv, &e->snap_x, &e->snap_y, &e->inject}) A(b->alloc(na));
+  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override}) A(b->alloc(na));
+  A(e->novelty.alloc(na));
+  if (cfg->keep_fields) A(e->fields.alloc(na * e->W));
+  for (DevBuf<float>* b : {&e->px, &e->py, &e->pradius, &e->pleft, &e->pquality}) A(b->alloc(np));
+  A(e->pid.alloc(np));
+  A(e->params.alloc((size_t)cfg->n_replicates * abm::kBaseNParam));
+  A(e->counters.alloc(4));
+  if (err == cudaSuccess) err = cudaMemset(e->counters.p, 0, 4 * sizeof(unsigned long long));
+  // defaults of decision_params.py / movement_params.py
+  const double defaults[abm::kBaseNParam] = {0.5, 3, 0.085, 0, 1, 0.5, 3, 0.085, 0, 1, 0.25, 0.01, 2, 1,
+                                             1, -0.3, 0.3, 0.5, 0.08, 1};
+  if (err == cudaSuccess) err = cudaMemcpy(e->params.p, defaults, sizeof(defaults), cudaMemcpyHostToDevice);
+  for (DevBuf<float>* b : {&e->w, &e->u, &e->collected, &e->collected_before, &e->i_priv, &e->vel})
+    if (err == cudaSuccess) err = cudaMemset(b->p, 0, sizeof(float) * na);
+  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode})
+    if (err == cudaSuccess) err = cudaMemset(b->p, 0, sizeof(int32_t) * na);
+  if (err == cudaSuccess) err = cudaMemset(e->patch_id.p, 0xff, sizeof(int32_t) * na);
+  if (err == cudaSuccess) err = cudaMemset(e->novelty.p, 0, sizeof(uint32_t) * na);
+  if (err != cudaSuccess) {
+    std::string m = std::string("abm_base_create: ") + cudaGetErrorString(err);
+    abm_base_destroy(e);
+    return fail(ABM_E_CUDA, m);
+  }
+  *out = e;
+  return ABM_OK;
+}
+
+int abm_base_destroy(abm_base_engine_t* e) {
+  if (!e) return ABM_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (DevBuf<float>* b : {&e->x, &e->y, &e->theta, &e->vel, &e->w, &e->u, &e->collected, &e->collected_before,
+                           &e->i_priv, &e->snap_x, &e->snap_y, &e->inject, &e->px, &e->py, &e->pradius, &e->pleft,
+                           &e->pquality}) b->release();
+  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid})
+    b->release();
+  e->novelty.release(); e->fields.release(); e->params.release(); e->counters.release();
+  delete e;
+  return ABM_OK;
+}
+
+int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets) {
+  if (!e || !params) return fail(ABM_E_INVALID, "abm_base_set_params: null argument");
+  if (n_sets != 1 && n_sets != e->cfg.n_replicates)
+    return fail(ABM_E_INVALID, "abm_base_set_params: n_sets must be 1 or n_replicates");
+  ABM_CUDA(cudaSetDevice(e->device));
+  ABM_CUDA(cudaMemcpy(e->params.p, params, sizeof(double) * abm::kBaseNParam * n_sets, cudaMemcpyHostToDevice));
+  e->n_param_sets = n_sets;
+  return ABM_OK;
+}
+
+static int agents_xfer(abm_base_engine_t* e, const abm_base_agents_t* s, bool to_dev, int on_device, cudaStream_t st) {
+  const size_t n = e->n_agents_total;
+  int rc;
+#define F(member, buf) if ((rc = xfer(e->buf.p, s->member, s->member, n, to_dev, on_device, st))) return rc;
+  F(x, x) F(y, y) F(theta, theta) F(vel, vel) F(w, w) F(u, u) F(collected, collected)
+  F(collected_before, collected_before) F(i_priv, i_priv) F(env_status, env_status)
+  F(override_mode, override_mode) F(mode, mode) F(patch_id, patch_id) F(novelty, novelty)
+#undef F
+  return ABM_OK;
+}
+
+int abm_base_set_agents(abm_base_engine_t* e, const abm_base_agents_t* src, int on_device, void* stream) {
+  if (!e || !src) return fail(ABM_E_INVALID, "abm_base_set_agents: null argument");
+  if (!e->agents_set && (!src->x || !src->y || !src->theta))
+    return fail(ABM_E_INVALID, "abm_base_set_agents: x, y, theta are required on the first call");
+  ABM_CUDA(cudaSetDevice(e->device));
+  int rc = agents_xfer(e, src, true, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->agents_set = true;
+  return ABM_OK;
+}
+
+int abm_base_get_agents(abm_base_engine_t* e, const abm_base_agents_t* dst, int on_device, void* stream) {
+  if (!e || !dst) return fail(ABM_E_INVALID, "abm_base_get_agents: null argument");
+  if (!e->agents_set) return fail(ABM_E_STATE, "abm_base_get_agents: no agent state has been set");
+  ABM_CUDA(cudaSetDevice(e->device));
+  int rc = agents_xfer(e, dst, false, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABM_OK;
+}
+
+static int patches_xfer(abm_base_engine_t* e, const abm_base_patches_t* s, bool to_dev, int on_device, cudaStream_t st) {
+  const size_t n = e->n_patches_total;
+  int rc;
+#define F(member, buf) if ((rc = xfer(e->buf.p, s->member, s->member, n, to_dev, on_device, st))) return rc;
+  F(x, px) F(y, py) F(radius, pradius) F(left, pleft) F(quality, pquality) F(id, pid)
+#undef F
+  return ABM_OK;
+}
+
+int abm_base_set_patches(abm_base_engine_t* e, const abm_base_patches_t* src, int on_device, void* stream) {
+  if (!e || !src) return fail(ABM_E_INVALID, "abm_base_set_patches: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  int rc = patches_xfer(e, src, true, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->patches_set = true;
+  return ABM_OK;
+}
+
+int abm_base_get_patches(abm_base_engine_t* e, const abm_base_patches_t* dst, int on_device, void* stream) {
+  if (!e || !dst) return fail(ABM_E_INVALID, "abm_base_get_patches: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  int rc = patches_xfer(e, dst, false, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABM_OK;
+}
+
+int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta, int inject_on_device,
+                  uint32_t phases, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_step: null engine");
+  if (!e->agents_set) return fail(ABM_E_STATE, "abm_base_step: abm_base_set_agents has not been called");
+  if (e->cfg.n_patches > 0 && !e->patches_set)
+    return fail(ABM_E_STATE, "abm_base_step: abm_base_set_patches has not been called");
+  if (n_steps < 0) return fail(ABM_E_INVALID, "abm_base_step: n_steps < 0");
+  if (inject_dtheta && n_steps > 1) return fail(ABM_E_INVALID, "abm_base_step: inject_dtheta needs n_steps == 1");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const abm_base_config_t& c = e->cfg;
+  abm::BaseKernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = c.n_replicates; a.N = c.n_agents; a.P = c.n_patches; a.R = c.resolution; a.W = e->W; a.Tau = c.tau;
+  a.visual_exclusion = c.visual_exclusion; a.patchwise_exclusion = c.patchwise_exclusion;
+  a.teleport_exploit = c.teleport_exploit; a.regenerate = c.regenerate_patches; a.border_overlap = c.patch_border_overlap;
+  a.fov0 = c.fov0; a.fov1 = c.fov1; a.mask_lo = e->mask_lo; a.mask_hi = e->mask_hi; a.lin_step = e->lin_step;
+  a.width = c.width; a.height = c.height; a.pad = c.window_pad; a.vision_range = c.vision_range; a.radius = c.agent_radius;
+  a.patch_radius = c.patch_radius; a.min_quality = c.min_quality; a.max_quality = c.max_quality;
+  a.min_units = c.min_units; a.max_units = c.max_units; a.seed = c.seed;
+  a.ag = abm::BaseAgentPtrs{e->x.p, e->y.p, e->theta.p, e->vel.p, e->w.p, e->u.p, e->collected.p,
+                            e->collected_before.p, e->i_priv.p, e->env_status.p, e->override_mode.p, e->mode.p,
+                            e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p};
+  a.pa = abm::BasePatchPtrs{e->px.p, e->py.p, e->pradius.p, e->pleft.p, e->pquality.p, e->pid.p};
+  a.params = e->params.p; a.param_stride = (e->n_param_sets == 1) ? 0 : abm::kBaseNParam;
+  a.fields_out = e->fields.p; a.counters = e->counters.p;
+  if (inject_dtheta) {
+    const float* src = inject_dtheta;
+    if (!inject_on_device) {
+      ABM_CUDA(cudaMemcpyAsync(e->inject.p, inject_dtheta, sizeof(float) * e->n_agents_total, cudaMemcpyHostToDevice, st));
+      src = e->inject.p;
+    }
+    a.inject_dtheta = src;
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    a.step = e->step;
+    if (phases & ABM_BASE_PHASE_ENV) { abm::launch_base_env(a, st); ++e->launches; }
+    else {   // agent phase alone: the snapshot is the current state
+      ABM_CUDA(cudaMemcpyAsync(e->snap_x.p, e->x.p, sizeof(float) * e->n_agents_total, cudaMemcpyDeviceToDevice, st));
+      ABM_CUDA(cudaMemcpyAsync(e->snap_y.p, e->y.p, sizeof(float) * e->n_agents_total, cudaMemcpyDeviceToDevice, st));
+      ABM_CUDA(cudaMemcpyAsync(e->snap_override.p, e->override_mode.p, sizeof(int32_t) * e->n_agents_total,
+                               cudaMemcpyDeviceToDevice, st));
+    }
+    if (phases & ABM_BASE_PHASE_AGENTS) { abm::launch_base_agents(a, st); ++e->launches; }
+    ++e->step; ++e->steps;
+  }
+  ABM_CUDA(cudaGetLastError());
+  if (inject_dtheta && !inject_on_device) ABM_CUDA(cudaStreamSynchronize(st));
+  return ABM_OK;
+}
+
+int abm_base_get_fields(abm_base_engine_t* e, uint32_t* packed, int on_device, void* stream) {
+  if (!e || !packed) return fail(ABM_E_INVALID, "abm_base_get_fields: null argument");
+  if (!e->fields.p) return fail(ABM_E_STATE, "abm_base_get_fields: engine created without keep_fields");
+  ABM_CUDA(cudaSetDevice(e->device));
+  ABM_CUDA(cudaMemcpyAsync(packed, e->fields.p, sizeof(uint32_t) * e->n_agents_total * e->W,
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (!on_device) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABM_OK;
+}
+
+int abm_base_get_counters(abm_base_engine_t* e, uint64_t counters[4], void* stream) {
+  if (!e || !counters) return fail(ABM_E_INVALID, "abm_base_get_counters: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  unsigned long long h[4];
+  ABM_CUDA(cudaMemcpyAsync(h, e->counters.p, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  counters[0] = h[0]; counters[1] = h[1]; counters[2] = e->launches; counters[3] = e->steps;
+  return ABM_OK;
+}
+
+}  // extern "C"

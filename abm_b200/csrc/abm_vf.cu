@@ -61,7 +61,7 @@ int vf_step_threads(int tile_count) {
 
 // Out-of-line fp64 evaluation + atomic draw of one pair (queue overflow / deferred pairs).
 // Returns 1 if the fp64 indices differ from the fp32 ones (k32, h32).
-__device__ __noinline__ unsigned vf_exact_and_draw(const VFKernelArgs& a, uint32_t* row, int stride,
+static __device__ __noinline__ unsigned vf_exact_and_draw(const VFKernelArgs& a, uint32_t* row, int stride,
                                                    float4 f4, float fth, float4 o, int k32, int h32) {
   const FocalExact fe = vf_focal_exact(f4.x, f4.y, f4.z, fth);
   const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, a.R, a.lin_step);
@@ -70,7 +70,7 @@ __device__ __noinline__ unsigned vf_exact_and_draw(const VFKernelArgs& a, uint32
 }
 
 // Queue overflow: evaluate a flagged pair on the spot (out of line: rare).
-__device__ __noinline__ void vf_exact_inline(const VFKernelArgs& a, uint32_t* myrow, int stride, float4 me, size_t gi,
+static __device__ __noinline__ void vf_exact_inline(const VFKernelArgs& a, uint32_t* myrow, int stride, float4 me, size_t gi,
                                              float4 o, int k, int h) {
   const unsigned diff = vf_exact_and_draw(a, myrow, stride, me, a.theta[gi], o, k, h);
   atomicAdd(&a.counters[1], 1ull);
@@ -78,7 +78,7 @@ __device__ __noinline__ void vf_exact_inline(const VFKernelArgs& a, uint32_t* my
 }
 
 // Interval that would leave the row padding (h > 16 right at the seam): general rule, out of line.
-__device__ __noinline__ void vf_draw_general(const VFKernelArgs& a, uint32_t* myrow, int stride, int k, int h) {
+static __device__ __noinline__ void vf_draw_general(const VFKernelArgs& a, uint32_t* myrow, int stride, int k, int h) {
   vf_draw<false>(myrow, stride, a.R, a.fov_px0, a.fov_px1, k, h);
 }
 

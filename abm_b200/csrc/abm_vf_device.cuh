@@ -144,7 +144,7 @@ struct PairExact { int k, h; bool valid; };
 
 // Object at top-left (ox, oy) with radius orad seen by the focal agent `f`.
 // boundary / width / height: torus re-centring of vf_supcalc.py:70-83.
-__device__ __noinline__ PairExact vf_pair_exact(const FocalExact& f, float ox, float oy, float orad,
+static __device__ __noinline__ PairExact vf_pair_exact(const FocalExact& f, float ox, float oy, float orad,
                                                 int boundary, double width, double height,
                                                 int R, double lin_step) {
   PairExact o;
@@ -219,11 +219,6 @@ __device__ __forceinline__ void vf_draw(uint32_t* f, int stride, int R, int fov0
     pe = R;
   }
   if (pe > ps) set_range<ATOMIC>(f, stride, ps, pe);                        // :129
-}
-
-// The slow, fully general rule kept out of line so the pair loop stays small (f: real word 0).
-__device__ __noinline__ void vf_draw_general(uint32_t* f, int stride, int R, int fov0, int fov1, int k, int h) {
-  vf_draw<false>(f, stride, R, fov0, fov1, k, h);
 }
 
 // Hot-path drawing into a PADDED private row: word 0 of the padded row holds the virtual bins

@@ -165,6 +165,93 @@ int abm_vf_projection_field(const abm_vf_proj_args_t* args, uint32_t* out_rows);
 int abm_vf_flocking_terms(const uint32_t* packed_v_now, int resolution, double vel_now,
                           const double* params, double out[6]);
 
+
+/* =====================================================================================
+ * BASE / collective-foraging variant (Simulation + Agent of abm/simulation/sims.py and
+ * abm/agent/agent.py): social visual field with distance-ordered occlusion, decision
+ * process (w, u), mode machine, kinematics, walls, and agent-patch exploitation.
+ * ===================================================================================== */
+
+typedef struct abm_base_engine abm_base_engine_t;
+
+/* Replaces: Simulation.__init__ kwargs (sims.py:60-68) that the hot path reads. */
+typedef struct {
+  int32_t struct_size;          /* = sizeof(abm_base_config_t) */
+  int32_t n_replicates;         /* B independent simulations */
+  int32_t n_agents;             /* N (sims.py N) */
+  int32_t n_patches;            /* N_resc; 0 = no environment */
+  int32_t resolution;           /* v_field_res */
+  int32_t tau;                  /* DEC_TAU: length of the novelty memory, <= 32 (decision_params.py:39) */
+  int32_t visual_exclusion;     /* VISUAL_EXCLUSION (agent.py:415, :559) */
+  int32_t patchwise_exclusion;  /* PATCHWISE_SOCIAL_EXCLUSION (agent.py:406-410) */
+  int32_t teleport_exploit;     /* TELEPORT_TO_MIDDLE (sims.py:820-821) */
+  int32_t regenerate_patches;   /* REGENERATE_PATCHES (sims.py:321-330) */
+  int32_t patch_border_overlap; /* PATCH_BORDER_OVERLAP (sims.py:351-358) */
+  int32_t keep_fields;          /* keep packed stored fields of the last step (abm_base_get_fields) */
+  double fov0, fov1;            /* agent_fov in radians: (-fov*pi, fov*pi) (sims.py:160-161) */
+  double width, height, window_pad;
+  double vision_range;          /* VISION_RANGE (agent.py:400) */
+  double agent_radius;          /* RADIUS_AGENT (one radius per batch, as in the reference's homogeneous runs) */
+  double patch_radius;          /* RADIUS_RESOURCE, used when a depleted patch is re-created */
+  double min_quality, max_quality;   /* MIN/MAX_RESOURCE_QUALITY (negatives resolved by the host, sims.py:176-179) */
+  int32_t min_units, max_units;      /* MIN/MAX_RESOURCE_PER_PATCH */
+  uint64_t seed;                /* counter-based RNG key (random walk, patch regeneration) */
+} abm_base_config_t;
+
+/* Per-replicate parameters, in this order (decision_params.py:13-42, movement_params.py:13-23,
+ * sims.py agent_consumption). */
+enum {
+  ABM_BASE_T_W = 0, ABM_BASE_EPS_W, ABM_BASE_G_W, ABM_BASE_B_W, ABM_BASE_W_MAX,
+  ABM_BASE_T_U, ABM_BASE_EPS_U, ABM_BASE_G_U, ABM_BASE_B_U, ABM_BASE_U_MAX,
+  ABM_BASE_S_WU, ABM_BASE_S_UW, ABM_BASE_F_N, ABM_BASE_F_R,
+  ABM_BASE_EXP_VEL_MAX, ABM_BASE_EXP_TH_MIN, ABM_BASE_EXP_TH_MAX, ABM_BASE_REL_TH_MAX, ABM_BASE_STOP_RATIO,
+  ABM_BASE_CONSUMPTION, ABM_BASE_NPARAM
+};
+
+/* override_mode: Agent.overriding_mode (agent.py:671-693): 0 None, 1 "exploit", 3 "collide".
+ * mode: last Agent.mode, logged code of ifdb.py:197-206: 0 explore, 1 exploit, 2 relocate, 3 collide.
+ * novelty: bit t = Agent.novelty[t] (sims.py:33-37).  SoA, n_replicates * n_agents each;
+ * any member may be NULL (skipped). */
+typedef struct {
+  float *x, *y, *theta, *vel, *w, *u, *collected, *collected_before, *i_priv;
+  int32_t *env_status, *override_mode, *mode, *patch_id;
+  uint32_t* novelty;
+} abm_base_agents_t;
+
+/* Rescource fields (rescource.py:15-47): top-left position, radius, resc_left, unit_per_timestep, id.
+ * n_replicates * n_patches each. */
+typedef struct {
+  float *x, *y, *radius, *left, *quality;
+  int32_t* id;
+} abm_base_patches_t;
+
+enum { ABM_BASE_PHASE_ENV = 1, ABM_BASE_PHASE_AGENTS = 2, ABM_BASE_PHASE_ALL = 3 };
+
+/* Replaces: Simulation(**kwargs) + create_agents / create_resources (sims.py:526-541). */
+int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t** out);
+int abm_base_destroy(abm_base_engine_t* e);
+int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets);
+int abm_base_set_agents(abm_base_engine_t* e, const abm_base_agents_t* src, int on_device, void* stream);
+int abm_base_get_agents(abm_base_engine_t* e, const abm_base_agents_t* dst, int on_device, void* stream);
+int abm_base_set_patches(abm_base_engine_t* e, const abm_base_patches_t* src, int on_device, void* stream);
+int abm_base_get_patches(abm_base_engine_t* e, const abm_base_patches_t* dst, int on_device, void* stream);
+
+/* n_steps time steps of the main loop body (sims.py:733-864): environment phase
+ * (agent-patch interaction, notify; sims.py:790-858) then agent phase (Agent.update for all
+ * agents from one frozen snapshot; sims.py:861 -> agent.py:212-283).
+ * inject_dtheta: NULL, or n_replicates*n_agents floats that replace the random-walk draw
+ * np.random.uniform(exp_theta_min, exp_theta_max) (supcalc.py:45) -- used with n_steps == 1
+ * by the parity tests.  phases: ABM_BASE_PHASE_*. */
+int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta, int inject_on_device,
+                  uint32_t phases, void* stream);
+
+/* Packed STORED fields (flipped + FOV-masked: Agent.soc_v_field, agent.py:593-597) of the last step. */
+int abm_base_get_fields(abm_base_engine_t* e, uint32_t* packed, int on_device, void* stream);
+
+/* counters[0] = patches regenerated, [1] = regenerations that exhausted their retries,
+ * [2] = kernel launches, [3] = steps. */
+int abm_base_get_counters(abm_base_engine_t* e, uint64_t counters[4], void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,12 @@ def install():
         mpl.cm = cm
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.cm"] = cm
+    # logging / plotting back ends the hot path never reaches (abm/monitoring/ifdb.py imports them)
+    for name in ("influxdb", "zarr", "fastcluster", "xvfbwrapper", "pygame_widgets"):
+        try:
+            __import__(name)
+        except ImportError:
+            sys.modules[name] = MagicMock()
     import scipy.integrate as _si
     if not hasattr(_si, "trapz"):
         _si.trapz = _si.trapezoid
@@ -185,4 +191,50 @@ def make_vf_agents(x, y, theta, vel, radius, *, R, fov_ratio=1.0, width, height,
         p.update(params)
     for k, v in p.items():
         setattr(vf_params, k, v)
+    return agents
+
+
+DECISION_KEYS = ("T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u", "u_max", "S_wu", "S_uw",
+                 "F_N", "F_R")
+
+
+def make_base_agents(st, cfg):
+    """Build real reference Agent objects (abm/agent/agent.py) from an oracle state dict
+    (see oracle/restate_base.base_step_frozen) and a BaseConfig.  Constructor kwargs follow
+    sims.py:481-498; decision / movement parameters are set on the instances and on the
+    modules after construction (constructors reload them from the reference's .env)."""
+    import numpy as np
+    supcalc, agent_mod, decision_params, movement_params = load_base()
+    mode_names = {0: "explore", 1: "exploit", 2: "relocate", 3: "collide"}
+    agents = []
+    N = len(st["x"])
+    rad = st["radius"]
+    rad = int(rad) if float(rad).is_integer() else float(rad)
+    for i in range(N):
+        a = agent_mod.Agent(
+            id=i, radius=rad, position=(float(st["x"][i]), float(st["y"][i])), orientation=float(st["theta"][i]),
+            env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0), v_field_res=cfg.R, FOV=tuple(cfg.fov),
+            window_pad=int(cfg.window_pad), pooling_time=0, pooling_prob=0, consumption=cfg.agent_consumption,
+            vision_range=cfg.vision_range, visual_exclusion=cfg.visual_exclusion,
+            patchwise_exclusion=cfg.patchwise_exclusion, behave_params=None)
+        a.velocity = float(st["vel"][i])
+        a.w, a.u = float(st["w"][i]), float(st["u"][i])
+        a.novelty = np.array(st["novelty"][i], dtype=np.float64)
+        a.env_status = int(st["env_status"][i])
+        a.exploited_patch_id = int(st["patch_id"][i])
+        a.collected_r = float(st["collected"][i])
+        a.collected_r_before = float(st["collected_before"][i])
+        ov = int(st["override"][i])
+        a.overriding_mode = {0: None, 1: "exploit", 3: "collide"}[ov]
+        a.mode = mode_names[int(st["mode"][i])]
+        for k in DECISION_KEYS:
+            setattr(a, k, getattr(cfg, k))
+        a.max_exp_vel = cfg.exp_vel_max
+        a.exp_stop_ratio = cfg.exp_stop_ratio
+        agents.append(a)
+    movement_params.exp_vel_max = cfg.exp_vel_max
+    movement_params.exp_theta_min = cfg.exp_theta_min
+    movement_params.exp_theta_max = cfg.exp_theta_max
+    movement_params.reloc_theta_max = cfg.reloc_theta_max
+    movement_params.exp_stop_ratio = cfg.exp_stop_ratio
     return agents

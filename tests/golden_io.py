@@ -35,3 +35,31 @@ def load_pf_cases():
                           vr=None if s[9] < 0 else s[9], objs=z[p + "objs"],
                           sizes=None if sizes.size == 0 else sizes, rows=z[p + "rows"]))
     return cases
+
+
+BASE_CFG_KEYS = ["R", "width", "height", "vision_range", "visual_exclusion", "patchwise_exclusion", "T_w", "Eps_w",
+                 "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u", "u_max", "S_wu", "S_uw", "Tau", "F_N", "F_R",
+                 "exp_vel_max", "exp_theta_min", "exp_theta_max", "reloc_theta_max", "exp_stop_ratio"]
+BASE_STATE_KEYS = ["x", "y", "theta", "vel", "w", "u", "novelty", "env_status", "override", "mode", "patch_id",
+                   "collected", "collected_before"]
+BASE_OUT_KEYS = ["x", "y", "theta", "vel", "w", "u", "I_priv", "override", "mode", "collected_before"]
+
+
+def load_base_cases():
+    """tests/golden/base_golden.npz (written by make_golden_base.py from real reference output)."""
+    from oracle import restate_base as rb
+    z = np.load(os.path.join(GOLDEN, "base_golden.npz"))
+    cases = []
+    for c in range(int(z["n_cases"])):
+        p = f"c{c}_"
+        vals = dict(zip(BASE_CFG_KEYS, z[p + "cfg"]))
+        for k in ("R", "Tau"):
+            vals[k] = int(vals[k])
+        for k in ("visual_exclusion", "patchwise_exclusion"):
+            vals[k] = bool(vals[k])
+        cfg = rb.BaseConfig(fov=tuple(z[p + "fov"]), **vals)
+        st = {k: z[p + "st_" + k] for k in BASE_STATE_KEYS}
+        st["radius"] = 10.0
+        cases.append(dict(cfg=cfg, st=st, dth=z[p + "dth"], fields=z[p + "fields"],
+                          out={k: z[p + "out_" + k] for k in BASE_OUT_KEYS}))
+    return cases

@@ -1,0 +1,179 @@
+"""GPU parity tests of the BASE / foraging path (through the C ABI) against fixtures produced
+by the unmodified reference's Agent.update and against the CPU oracle (oracle/restate_base.py).
+Fields: bit-exact.  Scalars (w, u, velocity, heading, position): 1e-5 relative (fp32 state)."""
+import numpy as np
+import pytest
+
+from golden_io import BASE_OUT_KEYS, load_base_cases
+from oracle import restate as rs
+from oracle import restate_base as rb
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+PHASE_ENV, PHASE_AGENTS = 1, 2
+
+
+def _engine_for(cfg, B, N, P=0, **kw):
+    from abm_b200 import BaseEngine
+    fovr = cfg.fov[1] / np.pi
+    eng = BaseEngine(B, N, P, resolution=cfg.R, agent_fov=fovr, width=cfg.width, height=cfg.height,
+                     vision_range=cfg.vision_range, agent_radius=10.0, visual_exclusion=cfg.visual_exclusion,
+                     patchwise_exclusion=cfg.patchwise_exclusion, teleport_exploit=cfg.teleport_exploit,
+                     tau=cfg.Tau, keep_fields=True, **kw)
+    eng.set_params(T_w=cfg.T_w, Eps_w=cfg.Eps_w, g_w=cfg.g_w, B_w=cfg.B_w, w_max=cfg.w_max, T_u=cfg.T_u,
+                   Eps_u=cfg.Eps_u, g_u=cfg.g_u, B_u=cfg.B_u, u_max=cfg.u_max, S_wu=cfg.S_wu, S_uw=cfg.S_uw,
+                   F_N=cfg.F_N, F_R=cfg.F_R, exp_vel_max=cfg.exp_vel_max, exp_theta_min=cfg.exp_theta_min,
+                   exp_theta_max=cfg.exp_theta_max, reloc_theta_max=cfg.reloc_theta_max,
+                   exp_stop_ratio=cfg.exp_stop_ratio, agent_consumption=cfg.agent_consumption)
+    return eng
+
+
+def _upload(eng, st, B=1):
+    def r(a):
+        return np.asarray(a).reshape((B, -1) + np.asarray(a).shape[2:] if B > 1 else (1,) + np.asarray(a).shape)
+    eng.set_agents(x=r(st["x"]), y=r(st["y"]), theta=r(st["theta"]), vel=r(st["vel"]), w=r(st["w"]), u=r(st["u"]),
+                   collected=r(st["collected"]), collected_before=r(st["collected_before"]),
+                   env_status=r(st["env_status"]), override_mode=r(st["override"]), mode=r(st["mode"]),
+                   patch_id=r(st["patch_id"]), novelty=r(st["novelty"]))
+
+
+def _compare_agents(got, ref, b=0, idx=None):
+    names = dict(x="x", y="y", theta="theta", vel="vel", w="w", u="u", I_priv="i_priv",
+                 collected_before="collected_before")
+    sel = slice(None) if idx is None else idx
+    for k, g in names.items():
+        np.testing.assert_allclose(got[g][b][sel], np.asarray(ref[k])[sel], rtol=RTOL, atol=1e-5, err_msg=k)
+    assert np.array_equal(got["override_mode"][b][sel], np.asarray(ref["override"])[sel].astype(int))
+    assert np.array_equal(got["mode"][b][sel], np.asarray(ref["mode"])[sel].astype(int))
+
+
+@pytest.mark.parametrize("case", load_base_cases(), ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_agent_phase_matches_reference_fixture(built_lib, case):
+    cfg, st = case["cfg"], case["st"]
+    N = len(case["dth"])
+    eng = _engine_for(cfg, 1, N)
+    _upload(eng, st)
+    eng.step(1, inject_dtheta=case["dth"], phases=PHASE_AGENTS)
+    assert np.array_equal(rs.pack_bits(eng.fields()[0]), case["fields"])          # bit-exact stored fields
+    _compare_agents(eng.get_agents(), case["out"])
+    eng.close()
+
+
+def _random_state(rng, N, W, cfg):
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    override = rng.choice([0, 0, 1, 1, 3], N)
+    st = dict(x=rng.integers(20, 30 + int(W), N).astype(float), y=rng.integers(20, 30 + int(W), N).astype(float),
+              theta=f32(rng.uniform(0, 2 * np.pi, N)), vel=f32(rng.uniform(0, 3, N)), radius=10.0,
+              w=f32(rng.uniform(-0.2, 1, N)), u=f32(rng.uniform(-0.2, 1, N)),
+              novelty=(rng.uniform(0, 1, (N, cfg.Tau)) < 0.15).astype(float),
+              env_status=rng.choice([-1, 1], N), override=override,
+              mode=np.where(override == 1, 1, np.where(override == 3, 3, 0)),
+              patch_id=rng.choice([-1, 0, 1, 2], N), collected=f32(rng.uniform(0, 5, N)))
+    st["collected_before"] = f32(st["collected"] - rng.choice([0.0, 0.25, 1.0], N))
+    return st
+
+
+@pytest.mark.parametrize("B,N,R,W,vis_excl,fovr", [
+    (4, 50, 1200, 500.0, True, 1.0),        # config 3 shape
+    (3, 10, 1200, 900.0, False, 0.5),       # config 1 shape
+    (2, 100, 1200, 500.0, True, 1.0),
+    (2, 37, 601, 300.0, True, 0.75),
+    (1, 200, 1200, 400.0, True, 1.0),       # crowded: heavy occlusion
+])
+def test_agent_phase_matches_oracle_random(built_lib, B, N, R, W, vis_excl, fovr):
+    rng = np.random.default_rng(100 + N + R)
+    cfg = rb.BaseConfig(R=R, fov=(-fovr * np.pi, fovr * np.pi), width=W, height=W, visual_exclusion=vis_excl,
+                        Eps_w=2.0, Eps_u=1.0, exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5,
+                        reloc_theta_max=1.8, exp_stop_ratio=0.175, F_N=0.5, F_R=0.5)
+    states = [_random_state(rng, N, W, cfg) for _ in range(B)]
+    dth = np.asarray(rng.uniform(-0.5, 0.5, (B, N)), np.float32)
+    eng = _engine_for(cfg, B, N)
+    stacked = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    eng.set_agents(x=stacked["x"], y=stacked["y"], theta=stacked["theta"], vel=stacked["vel"], w=stacked["w"],
+                   u=stacked["u"], collected=stacked["collected"], collected_before=stacked["collected_before"],
+                   env_status=stacked["env_status"], override_mode=stacked["override"], mode=stacked["mode"],
+                   patch_id=stacked["patch_id"], novelty=stacked["novelty"])
+    eng.step(1, inject_dtheta=dth, phases=PHASE_AGENTS)
+    got, fields = eng.get_agents(), eng.fields()
+    sample = None if N <= 100 else np.sort(rng.choice(N, 40, replace=False))
+    for b in range(B):
+        ref = rb.base_step_frozen(states[b], cfg, dth[b].astype(np.float64),
+                                  agents=None if sample is None else sample.tolist())
+        sel = slice(None) if sample is None else sample
+        assert np.array_equal(fields[b][sel], ref["fields"][sel])
+        _compare_agents(got, ref, b, sample)
+    eng.close()
+
+
+def test_env_phase_matches_oracle(built_lib):
+    """Agent-patch interaction (sims.py:790-858): membership, heading bias, notify / novelty,
+    depletion order, depletion of a patch within the step (regeneration switched off)."""
+    rng = np.random.default_rng(8)
+    B, N, P, W = 5, 40, 3, 300.0
+    cfg = rb.BaseConfig(R=320, width=W, height=W, agent_consumption=1.0)
+    from abm_b200 import BaseEngine
+    eng = BaseEngine(B, N, P, resolution=320, width=W, height=W, regenerate_patches=False, tau=cfg.Tau)
+    eng.set_params(agent_consumption=1.0)
+    states, patches = [], []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 1], N); st["mode"] = st["override"].copy()
+        states.append(st)
+        patches.append(dict(x=np.array([40.0, 150.0, 230.0]), y=np.array([50.0, 160.0, 60.0]),
+                            radius=np.array([45.0, 40.0, 35.0]), left=np.array([2.5, 400.0, 0.5]),
+                            quality=np.array([0.75, 0.25, 1.0]), id=np.array([0, 1, 2])))
+    S = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    Pm = {k: np.stack([p[k] for p in patches]) for k in patches[0]}
+    eng.set_agents(x=S["x"], y=S["y"], theta=S["theta"], vel=S["vel"], w=S["w"], u=S["u"], collected=S["collected"],
+                   collected_before=S["collected_before"], env_status=S["env_status"], override_mode=S["override"],
+                   mode=S["mode"], patch_id=S["patch_id"], novelty=S["novelty"])
+    eng.set_patches(**Pm)
+    eng.step(1, phases=PHASE_ENV)
+    got, gp = eng.get_agents(), eng.get_patches()
+    any_depleted = False
+    for b in range(B):
+        st, pa = states[b], patches[b]
+        st = {k: (np.array(v, dtype=float) if k in ("theta", "collected", "collected_before") else np.array(v))
+              for k, v in st.items()}
+        depleted = rb.base_patch_phase(st, pa, cfg)
+        any_depleted |= bool(depleted)
+        np.testing.assert_allclose(got["theta"][b], st["theta"], rtol=RTOL)
+        np.testing.assert_allclose(got["collected"][b], st["collected"], rtol=RTOL)
+        np.testing.assert_allclose(got["collected_before"][b], st["collected_before"], rtol=RTOL)
+        assert np.array_equal(got["env_status"][b], st["env_status"])
+        assert np.array_equal(got["patch_id"][b], st["patch_id"])
+        nov = ((got["novelty"][b][:, None] >> np.arange(cfg.Tau)) & 1).astype(float)
+        assert np.array_equal(nov, st["novelty"])
+        np.testing.assert_allclose(gp["left"][b], pa["left"], rtol=RTOL, atol=1e-6)
+        for p in depleted:
+            assert gp["radius"][b][p] == 0.0        # killed patch (no regeneration)
+    assert any_depleted
+    eng.close()
+
+
+def test_full_loop_runs_and_forages(built_lib):
+    """configs[0] shape (N=10, 3 patches, R=1200) for 300 steps with the engine's own RNG:
+    sanity properties -- agents stay inside the arena, some resource gets collected, patches
+    are regenerated, state stays finite, replicates with different seeds differ."""
+    from abm_b200 import BaseEngine
+    B, N, P, W = 8, 10, 3, 500.0
+    rng = np.random.default_rng(0)
+    eng = BaseEngine(B, N, P, resolution=1200, width=W, height=W, visual_exclusion=True, patch_radius=30.0,
+                     min_resc_perpatch=20, max_resc_perpatch=30, min_resc_quality=0.25, seed=42)
+    eng.set_params(Eps_w=2.0, Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5,
+                   reloc_theta_max=1.8, exp_stop_ratio=0.175)
+    eng.set_agents(x=rng.integers(20, 520, (B, N)), y=rng.integers(20, 520, (B, N)),
+                   theta=rng.uniform(0, 2 * np.pi, (B, N)))
+    eng.set_patches(x=rng.integers(40, 440, (B, P)), y=rng.integers(40, 440, (B, P)), radius=np.full((B, P), 30.0),
+                    left=np.full((B, P), 25.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
+    eng.step(300)
+    a = eng.get_agents()
+    for k in ("x", "y", "theta", "vel", "w", "u", "collected"):
+        assert np.isfinite(a[k]).all(), k
+    assert (a["x"] + 10 >= 30 - 1e-3).all() and (a["x"] + 10 <= 30 + W + 1e-3).all()
+    assert (a["y"] + 10 >= 30 - 1e-3).all() and (a["y"] + 10 <= 30 + W + 1e-3).all()
+    assert a["collected"].sum() > 0
+    assert not np.array_equal(a["x"][0], a["x"][1])
+    c = eng.counters()
+    assert c["steps"] == 300 and c["launches"] == 600 and c["regeneration_failed"] == 0
+    eng.close()

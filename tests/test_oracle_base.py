@@ -1,0 +1,101 @@
+"""CPU tests: the BASE oracle (oracle/restate_base.py) against SURVEY KAT-B1, against fixtures
+produced by executing the unmodified reference's Agent.update (tests/golden/base_golden.npz)
+and, when /root/reference is mounted, the reference's own notify / deplete / bias functions."""
+import numpy as np
+import pytest
+
+from golden_io import BASE_OUT_KEYS, load_base_cases
+from oracle import ref_shim
+from oracle import restate as rs
+from oracle import restate_base as rb
+
+
+@pytest.mark.parametrize("vis_excl,runs,mean,reloc", [
+    (False, [(1, 18), (348, 369), (584, 609), (1199, 1200)], 0.053333, (2.0, 0.132)),
+    (True, [(1, 18), (584, 588), (1199, 1200)], 0.018333, (2.0, 0.06)),
+])
+def test_kat_b1(vis_excl, runs, mean, reloc):
+    x = np.array([250., 400, 330, 250, 250, 60]); y = np.array([250., 200, 230, 60, 150, 301])
+    th = np.array([0.3, 0, 0, 0, 0, 0])
+    ex = np.array([0, 1, 0, 1, 0, 1], bool); pid = np.array([-1, 1, -1, 1, -1, 1])
+    cfg = rb.BaseConfig(R=1200, vision_range=2000, visual_exclusion=vis_excl, patchwise_exclusion=True,
+                        reloc_theta_max=1.8)
+    f, src = rb.base_field(0, x, y, 10.0, th, ex, pid, cfg)
+    assert rs.runs_of(f) == runs
+    assert round(float(f.mean()), 6) == mean
+    np.testing.assert_allclose(rb.relocation_force(1.0, f, 3.0, cfg), reloc, rtol=1e-12)
+    if vis_excl:   # source data (k, s, e, s_ex, e_ex, d) of SURVEY App. B
+        by_j = {o["j"]: o for o in src}
+        assert (by_j[1]["k"], by_j[1]["s"], by_j[1]["e"], by_j[1]["sx"], by_j[1]["ex"]) == (604, 591, 616, 612, 616)
+        assert (by_j[3]["sx"], by_j[3]["ex"]) == (0, 0)
+        assert (by_j[5]["s"], by_j[5]["e"], by_j[5]["sx"], by_j[5]["ex"]) == (1182, 1201, 1182, 1201)
+        assert round(by_j[5]["d"], 3) == 196.726
+
+
+def test_dead_ahead_object_is_invisible():
+    """agent.py:520-523: closed angle 0 maps to 2pi."""
+    x = np.array([100.0, 200.0]); y = np.array([100.0, 100.0])
+    cfg = rb.BaseConfig(R=1200, visual_exclusion=False)
+    f, _ = rb.base_field(0, x, y, 10.0, np.zeros(2), np.array([False, True]), np.array([-1, 2]), cfg)
+    assert not f.any()
+    f, _ = rb.base_field(0, x, np.array([100.0, 100.0001]), 10.0, np.zeros(2), np.array([False, True]),
+                         np.array([-1, 2]), cfg)
+    assert f.sum() > 30
+
+
+@pytest.mark.parametrize("case", load_base_cases(), ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_restatement_matches_reference_fixture(case):
+    out = rb.base_step_frozen(case["st"], case["cfg"], case["dth"])
+    assert np.array_equal(rs.pack_bits(out["fields"]), case["fields"])
+    for k in BASE_OUT_KEYS:
+        np.testing.assert_allclose(out[k], case["out"][k], rtol=1e-12, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_patch_phase_pieces_match_live_reference():
+    """notify_agent (sims.py:29-42), Rescource.deplete (rescource.py:118-133) and
+    bias_agent_towards_res_center (sims.py:544-552) of the real reference against the oracle's
+    patch phase on a one-patch scene."""
+    ref_shim.install()
+    import types
+    from abm.simulation import sims
+    from abm.environment.rescource import Rescource
+    rng = np.random.default_rng(4)
+    N = 12
+    cfg = rb.BaseConfig(R=320, width=300, height=300, agent_consumption=1.0)
+    st = dict(x=rng.integers(100, 160, N).astype(float), y=rng.integers(100, 160, N).astype(float),
+              theta=rng.uniform(0, 2 * np.pi, N), vel=np.zeros(N), radius=10.0, w=np.zeros(N), u=np.zeros(N),
+              novelty=np.zeros((N, 10)), env_status=rng.choice([-1, 1], N), override=rng.choice([0, 1], N),
+              mode=np.zeros(N, int), patch_id=np.full(N, -1), collected=np.zeros(N), collected_before=np.zeros(N))
+    patches = dict(x=np.array([100.0]), y=np.array([100.0]), radius=np.array([30.0]), left=np.array([3.0]),
+                   quality=np.array([0.75]), id=np.array([7]))
+    agents = ref_shim.make_base_agents(st, cfg)
+    res = Rescource(7, 30, (100.0, 100.0), (300, 300), (0, 0, 0), 30, 3.0, 0.75)
+    # the loop body of sims.py:805-844 driven with the reference's own functions
+    members = [a for a in agents if sims.supcalc.distance(res, a) < res.radius]
+    destroy = 0
+    dummy = types.SimpleNamespace()
+    for a in members:
+        sims.Simulation.bias_agent_towards_res_center(dummy, a, res)
+        if destroy:
+            sims.notify_agent(a, -1)
+        else:
+            sims.notify_agent(a, 1, res.id)
+            if a.get_mode() == "exploit":
+                depl, destroy = res.deplete(a.consumption)
+                a.collected_r_before = a.collected_r
+                a.collected_r += depl
+                if destroy:
+                    for a2 in members:
+                        sims.notify_agent(a2, -1)
+    for a in agents:
+        if a not in members:
+            sims.notify_agent(a, -1)
+    depleted = rb.base_patch_phase(st, patches, cfg)
+    assert depleted == ([0] if destroy else [])
+    assert np.isclose(patches["left"][0], res.resc_left)
+    for i, a in enumerate(agents):
+        assert np.isclose(st["theta"][i], a.orientation, rtol=1e-14)
+        assert st["env_status"][i] == a.env_status and st["patch_id"][i] == a.exploited_patch_id
+        assert np.array_equal(st["novelty"][i], a.novelty)
+        assert np.isclose(st["collected"][i], a.collected_r)
