@@ -1,0 +1,87 @@
+"""GPU tests of the class-level drop-in interface (Simulation / VFSimulation / MetaProtocol)."""
+import numpy as np
+import pytest
+
+from oracle import restate as rs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vfsimulation_programmatic_stepping(built_lib):
+    """The stepping API used by vf_utils/attraction_repulsion_map.py:27-66: prepare_start,
+    mutate agents, step_sim, read dv / dphi / ablob ... -- checked against the oracle."""
+    from abm_b200.simulation import VFSimulation
+    from abm_b200.params import VFParams
+    sim = VFSimulation(N=2, T=10, v_field_res=1200, width=500, height=500, agent_radius=10, agent_fov=1.0,
+                       vf_params=VFParams(ALP0=1.0, BET0=1.0, ALP1=0.09, BET1=0.09), seed=3)
+    sim.prepare_start()
+    a0, a1 = sim.agents
+    a0.position = [250.0, 250.0]; a0.orientation = 0.0; a0.velocity = 1.0
+    a1.position = [330.0, 210.0]; a1.orientation = 2.0; a1.velocity = 1.0
+    a0.verbose_supcalc = True
+    sim.step_sim()
+    cfg = rs.VFConfig(R=1200, width=500, height=500)
+    ref = rs.vf_step_frozen([250.0, 330.0], [250.0, 210.0], [0.0, 2.0], [1.0, 1.0], 10.0, cfg)
+    np.testing.assert_allclose([a0.dv, a0.dphi, a0.ablob, a0.aedge, a0.bblob, a0.bedge], ref["terms"][0], rtol=1e-9)
+    np.testing.assert_allclose(a0.position, [ref["x"][0], ref["y"][0]], rtol=1e-5)
+    assert np.isclose(a1.orientation, ref["theta"][1], rtol=1e-5)
+    assert np.array_equal(a0.soc_v_field > 0, ref["rows"][0][::-1])
+    assert sim.t == 1
+
+
+def test_vfsimulation_rescales_resolution_with_fov(built_lib):
+    from abm_b200.simulation import VFSimulation
+    sim = VFSimulation(N=4, T=3, v_field_res=1200, width=400, height=400, agent_fov=0.5, seed=1)
+    assert sim.v_field_res == 2400                # vf_sims.py:41-44
+    sim.start()
+    assert sim.t == 3 and len(sim.agents[0].soc_v_field) == 2400
+
+
+def test_simulation_facade_runs(built_lib):
+    from abm_b200.simulation import Simulation
+    from abm_b200.params import DecisionParams
+    sim = Simulation(N=10, T=50, v_field_res=1200, width=500, height=500, N_resc=3, patch_radius=30,
+                     min_resc_perpatch=100, max_resc_perpatch=-1, min_resc_quality=0.25, max_resc_quality=-1,
+                     vision_range=2000, agent_fov=1.0, visual_exclusion=True, teleport_exploit=False,
+                     allow_border_patch_overlap=True, collide_agents=False, n_replicates=4, seed=5,
+                     decision_params=DecisionParams(Eps_w=2.0, Eps_u=1.0, exp_vel_max=3.0))
+    sim.start()
+    assert sim.t == 50 and len(sim.agents) == 10 and len(sim.rescources) == 3
+    a = sim.agents[0]
+    assert a.mode in ("explore", "exploit", "relocate", "collide") and a.get_mode() in ("explore", "exploit", "relocate")
+    assert np.isfinite(a.position).all() and len(a.soc_v_field) == 1200
+    assert sim.rescources[0].radius == 30.0 and sim.rescources[0].resc_left <= 101
+
+
+def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
+    from abm_b200 import metarunner as mr
+    env = dict(N="12", T="20", VISUAL_FIELD_RESOLUTION="1200", ENV_WIDTH="400", ENV_HEIGHT="400", RADIUS_AGENT="10",
+               AGENT_FOV="1", APP_VERSION="VisualFlocking", BOUNDARY="walls", VF_ALP1="0.09", VF_BET1="0.09")
+    mp = mr.MetaProtocol("sweep", num_batches=2, default_envconf=env, root_dir=str(tmp_path))
+    mp.add_criterion(mr.Tunable("VF_ALP0", values_override=[0, 1, 3]))
+    mp.add_criterion(mr.Tunable("VF_BET0", values_override=[0, 2]))
+    assert mp.generate_temp_env_files() == 12
+    res = mp.run_protocols(project="VisualFlocking", seed=7)
+    assert len(res) == 1                              # one replicate batch for the whole sweep
+    paths, sim = res[0]
+    assert len(paths) == 12 and sim.B == 12 and sim.t == 20
+    assert sim.engine.counters()["launches"] == 20
+    st = sim.engine.get_state()
+    assert np.isfinite(st["x"]).all()
+    # replicates with ALP0 = BET0 = 0 only relax their speed towards V0: headings never change
+    assert mp.run_protocols(project="VisualFlocking") == []      # env files are consumed
+
+
+def test_tiled_swarm_matches_single_gpu_if_two_gpus(built_lib):
+    """Large-swarm mode (agent tiles + one all-gather per step) over NCCL; needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29544",
+                        os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTIGPU_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

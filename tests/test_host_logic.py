@@ -1,0 +1,83 @@
+"""CPU tests of the host-side mirror of the reference interface: .env parsing rules
+(app.py:27-63), parameter modules, sweep generation (metarunner.py:168-199)."""
+import os
+
+import numpy as np
+import pytest
+
+from abm_b200 import metarunner as mr
+from abm_b200 import params
+
+ENV_TEXT = """
+N=10
+T=5000
+VISUAL_FIELD_RESOLUTION=320
+ENV_WIDTH=900
+ENV_HEIGHT=900
+RADIUS_AGENT=5.5
+AGENT_FOV=0.5
+N_RESOURCES=3
+VISION_RANGE=2000
+VISUAL_EXCLUSION=1
+AGENT_AGENT_COLLISION=0
+DEC_EPSW=2
+DEC_TAU=10
+MOV_EXP_VEL_MAX=3
+APP_VERSION=VisualFlocking
+VF_GAM=0.5
+VF_ALP0=2
+BOUNDARY=infinite
+"""
+
+
+def _write_env(tmp_path):
+    p = tmp_path / ".env"
+    p.write_text(ENV_TEXT)
+    return str(p)
+
+
+def test_env_parsing_rules(tmp_path):
+    e = params.read_env(_write_env(tmp_path))
+    kw = params.simulation_kwargs(e)
+    assert kw["N"] == 10 and kw["T"] == 5000 and kw["v_field_res"] == 320
+    assert kw["agent_radius"] == 5          # int(float("5.5")) (app.py:39)
+    assert kw["agent_fov"] == 0.5 and kw["visual_exclusion"] is True and kw["collide_agents"] is False
+    assert kw["window_pad"] == 30
+
+
+def test_vf_gamma_key_quirk(tmp_path):
+    """vf_params.py:12 reads VF_GAMMA; experiments set VF_GAM -> GAM stays 0.1."""
+    e = params.read_env(_write_env(tmp_path))
+    p = params.VFParams.from_env(e)
+    assert p.GAM == 0.1 and p.ALP0 == 2.0 and p.BOUNDARY == "infinite"
+    d = params.DecisionParams.from_env(e)
+    assert d.Eps_w == 2.0 and d.exp_vel_max == 3.0 and d.Tau == 10 and d.S_wu == 0.25
+
+
+def test_metaprotocol_env_generation(tmp_path):
+    e = params.read_env(_write_env(tmp_path))
+    mp = mr.MetaProtocol("exp", num_batches=2, default_envconf=e, root_dir=str(tmp_path))
+    mp.add_criterion(mr.Tunable("VF_ALP0", 0, 5, 3))
+    mp.add_criterion(mr.Tunable("VF_BET0", values_override=[0.5, 1.0]))
+    mp.add_criterion(mr.Constant("N", 12))
+    assert mp.generate_temp_env_files() == 12
+    files = sorted(os.listdir(tmp_path / "abm/data/metaprotocol/temp/exp"))
+    assert len(files) == 12 and files[0] == "0_b0.env"
+    env0 = params.read_env(str(tmp_path / "abm/data/metaprotocol/temp/exp/5_b1.env"))
+    assert env0["N"] == "12" and float(env0["VF_ALP0"]) == 5.0 and float(env0["VF_BET0"]) == 1.0
+    assert env0["SAVE_ROOT_DIR"].endswith("exp/batch_1")
+
+
+def test_tuned_pair_restraint(tmp_path):
+    mp = mr.MetaProtocol("e2", default_envconf={}, root_dir=str(tmp_path))
+    mp.add_criterion(mr.Tunable("A", values_override=[1, 2, 4]))
+    mp.add_criterion(mr.Tunable("B", values_override=[1, 2, 4]))
+    mp.add_tuned_pair(mr.TunedPairRestrain("A", "B", 4))
+    names, combos = mp.combinations()
+    assert sorted(combos) == [(1, 4), (2, 2), (4, 1)]
+
+
+def test_tunable_requires_values():
+    with pytest.raises(Exception):
+        mr.Tunable("X")
+    assert np.allclose(mr.Tunable("X", 0, 1, 5).get_values(), [0, .25, .5, .75, 1])
