@@ -36,6 +36,9 @@ R = 1200
 RADIUS = 10.0
 PAD = 30.0
 PARAMS = dict(GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, BET0=1.0, BET1=0.09)
+# dram__bytes_read.sum + dram__bytes_write.sum of one vf_step_kernel launch at the default workload, from the
+# committed `ncu --set full` capture (profiles/r1_vf_step_ncu_summary.md); None for any other workload size
+NCU_DRAM_BYTES_PER_LAUNCH = 55.2e6 if (N_AGENTS, N_REPLICATES) == (1024, 1024) else None
 METRIC = "agent-steps/sec (visual field + flocking update)"
 UNIT = "agent-steps/s"
 
@@ -167,7 +170,7 @@ def run_reference_arm(args, rank, world):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    n_focal = max(procs * 2, int(os.environ.get("ABM_BENCH_CPU_FOCAL", 4 * procs)))
+    n_focal = max(procs * 2, int(os.environ.get("ABM_BENCH_CPU_FOCAL", 16 * procs)))
     rates = []
     for s in range(args.warmup + args.steps):
         rate, dt = cpu_port_rate(n_focal, N_AGENTS, procs=procs)
@@ -329,7 +332,7 @@ def main():
                     "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
-                         "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops, "traffic": None,
+                         "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "kernel": "abm::vf_step_kernel", "algorithmic_ops_per_launch": ops_launch,
                          "visible_pair_fraction": vis, "peak_source": f"{sms} SMs x 128 lanes x "
                          f"{sm_clock / 1e6:.0f} MHz ({peak_kind} sm_max_mhz)",
