@@ -58,6 +58,7 @@ class BaseConfig(C.Structure):
         ("resolution", C.c_int32), ("tau", C.c_int32), ("visual_exclusion", C.c_int32),
         ("patchwise_exclusion", C.c_int32), ("teleport_exploit", C.c_int32), ("regenerate_patches", C.c_int32),
         ("patch_border_overlap", C.c_int32), ("keep_fields", C.c_int32),
+        ("collide_agents", C.c_int32), ("ghost_mode", C.c_int32),
         ("fov0", C.c_double), ("fov1", C.c_double),
         ("width", C.c_double), ("height", C.c_double), ("window_pad", C.c_double),
         ("vision_range", C.c_double), ("agent_radius", C.c_double), ("patch_radius", C.c_double),
@@ -74,6 +75,17 @@ BASE_NPARAM = 20
 BASE_PARAM_NAMES = ["T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u", "u_max", "S_wu", "S_uw",
                     "F_N", "F_R", "exp_vel_max", "exp_theta_min", "exp_theta_max", "reloc_theta_max",
                     "exp_stop_ratio", "agent_consumption"]
+
+
+class BaseProjArgs(C.Structure):
+    """abm_base_proj_args_t"""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("resolution", C.c_int32), ("fov0", C.c_double), ("fov1", C.c_double),
+        ("x", C.c_double), ("y", C.c_double), ("radius", C.c_double), ("orientation", C.c_double),
+        ("n_social", C.c_int32), ("n_occluders", C.c_int32),
+        ("social_x", C.c_void_p), ("social_y", C.c_void_p), ("occluder_x", C.c_void_p), ("occluder_y", C.c_void_p),
+        ("visual_exclusion", C.c_int32), ("keep_distance_info", C.c_int32), ("vision_range", C.c_double),
+    ]
 
 
 class BaseAgents(C.Structure):
@@ -117,6 +129,10 @@ SYMBOLS = {
     "abm_base_step": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_uint32, _P]),
     "abm_base_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_base_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
+    "abm_base_projection_field": (C.c_int, [C.POINTER(BaseProjArgs), _P, C.POINTER(C.c_double)]),
+    "abm_base_reloc_lr": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.POINTER(C.c_double)]),
+    "abm_vf_dphi": (C.c_int, [_P, C.c_int, _P]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ from . import _lib
 from .engine import _current_stream
 
 _DT = {"f": np.float32, "i": np.int32, "u": np.uint32}
-PHASE_ENV, PHASE_AGENTS, PHASE_ALL = 1, 2, 3
+PHASE_ENV, PHASE_AGENTS, PHASE_COLLISIONS, PHASE_ALL = 1, 2, 4, 7
 
 
 class BaseEngine:
@@ -27,7 +27,8 @@ class BaseEngine:
                  patchwise_exclusion: bool = True, teleport_exploit: bool = False, regenerate_patches: bool = True,
                  patch_border_overlap: bool = True, patch_radius: float = 30.0, min_resc_quality: float = 0.25,
                  max_resc_quality: float = -1.0, min_resc_perpatch: int = 100, max_resc_perpatch: int = -1,
-                 tau: int = 10, keep_fields: bool = False, seed: int = 0, device: int = 0):
+                 tau: int = 10, keep_fields: bool = False, collide_agents: bool = False, ghost_mode: bool = True,
+                 seed: int = 0, device: int = 0):
         self._lib = _lib.load()
         self.B, self.N, self.P, self.R = int(n_replicates), int(n_agents), int(n_patches), int(resolution)
         self.W = (self.R + 31) // 32
@@ -42,7 +43,8 @@ class BaseEngine:
             resolution=self.R, tau=self.tau, visual_exclusion=int(bool(visual_exclusion)),
             patchwise_exclusion=int(bool(patchwise_exclusion)), teleport_exploit=int(bool(teleport_exploit)),
             regenerate_patches=int(bool(regenerate_patches)), patch_border_overlap=int(bool(patch_border_overlap)),
-            keep_fields=int(bool(keep_fields)),
+            keep_fields=int(bool(keep_fields)), collide_agents=int(bool(collide_agents)),
+            ghost_mode=int(bool(ghost_mode)),
             fov0=-float(agent_fov) * np.pi, fov1=float(agent_fov) * np.pi,      # sims.py:160-161
             width=float(width), height=float(height), window_pad=float(window_pad),
             vision_range=float(vision_range), agent_radius=float(agent_radius), patch_radius=float(patch_radius),

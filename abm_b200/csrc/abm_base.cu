@@ -17,7 +17,7 @@
 // interval ends agree with the float64 reference without guard bands; with N <= a few hundred
 // agents per replicate the all-pairs work is small next to the occlusion pass.
 #include "abm_base.cuh"
-#include "abm_vf_device.cuh"
+#include "abm_base_device.cuh"
 
 namespace abm {
 
@@ -140,7 +140,7 @@ __global__ void base_env_kernel(const BaseKernelArgs a) {
     const size_t g = a0 + i;
     const int m = a.ag.mode[g];
     if (m & 0x100) a.ag.mode[g] = m & 0xff;
-    else if (a.ag.override_mode[g] != OV_COLLIDE) notify(a.ag, g, -1, -1, tau_mask);
+    else if (!a.ag.collided[g]) notify(a.ag, g, -1, -1, tau_mask);
     // frozen snapshot for the agent phase: every agent sees the same positions / modes
     a.ag.snap_x[g] = a.ag.x[g];
     a.ag.snap_y[g] = a.ag.y[g];
@@ -156,59 +156,18 @@ void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------
 // agent phase: one warp per focal agent
 // ---------------------------------------------------------------------------------------
-struct __align__(16) ObjRec {
-  int s, e;      // raw interval ends, int() truncated (agent.py:545-546)
-  double d;      // centre distance (agent.py:526-528)
-};
-
-size_t base_agents_smem_bytes(int N, int W, int warps) {
-  const size_t per_warp = 2 * sizeof(ObjRec) * (size_t)N + 2 * sizeof(int) * (size_t)N + sizeof(uint32_t) * (size_t)(W + 1);
-  return ((per_warp + 15) / 16 * 16) * warps;
-}
+size_t base_agents_smem_bytes(int N, int W, int warps) { return warp_field_bytes(N, W) * warps; }
 int base_agents_warps(int N, int W, size_t smem_limit) {
   int w = 8;
   while (w > 1 && base_agents_smem_bytes(N, W, w) > smem_limit) w >>= 1;
   return w;
 }
 
-// numpy basic-slice bounds of v[a:b] on a length-R array (negative indices count from the end)
-__device__ __forceinline__ void np_slice(int a, int b, int R, int& lo, int& hi) {
-  if (a < 0) a = max(a + R, 0);
-  if (b < 0) b = max(b + R, 0);
-  lo = min(a, R);
-  hi = min(b, R);
-}
-__device__ __forceinline__ void base_draw(uint32_t* row, int R, int s, int e) {   // agent.py:577-588
-  int lo, hi;
-  if (s < 0) { np_slice(R + s, R, R, lo, hi); if (hi > lo) set_range<true>(row, 1, lo, hi); s = 0; }
-  if (e >= R) { np_slice(0, e - R, R, lo, hi); if (hi > lo) set_range<true>(row, 1, lo, hi); e = R - 1; }
-  np_slice(s, e, R, lo, hi);
-  if (hi > lo) set_range<true>(row, 1, lo, hi);
-}
-// number of set bits of row in bins [a, b)
-__device__ __forceinline__ int popc_range(const uint32_t* row, int W, int a, int b, int lane) {
-  int n = 0;
-  for (int w = lane; w < W; w += 32) {
-    const int lo = max(a - (w << 5), 0), hi = min(b - (w << 5), 32);
-    if (hi > lo) {
-      uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-      n += __popc(row[w] & m);
-    }
-  }
-  return __reduce_add_sync(0xffffffffu, n);
-}
-
 __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const size_t per_warp = (2 * sizeof(ObjRec) * (size_t)a.N + 2 * sizeof(int) * (size_t)a.N +
-                           sizeof(uint32_t) * (size_t)(a.W + 1) + 15) / 16 * 16;
-  unsigned char* base = smem_raw + per_warp * wib;
-  ObjRec* raw = reinterpret_cast<ObjRec*>(base);
-  ObjRec* sorted = raw + a.N;
-  int* key = reinterpret_cast<int*>(sorted + a.N);      // tie-break key of raw[m]; bit 30 = social cue
-  int* skey = key + a.N;                                // same for sorted[rank]
-  uint32_t* row = reinterpret_cast<uint32_t*>(skey + a.N);   // un-flipped field v (agent.py:480)
+  WarpField wf = warp_field_at(smem_raw + warp_field_bytes(a.N, a.W) * wib, a.N);
+  uint32_t* row = wf.row;
 
   const long long gw = (long long)blockIdx.x * wpb + wib;   // global warp = (replicate, focal agent)
   if (gw >= (long long)a.B * a.N) return;
@@ -226,15 +185,13 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
   int M = 0;
   for (int j0 = 0; j0 < N; j0 += 32) {
     const int j = j0 + lane;
-    bool rec = false, social = false;
+    bool rec = false;
     ObjRec o; o.s = 0; o.e = 0; o.d = 0.0;
     int k2 = 0;
     if (j < N) {
       const size_t gj = a0 + j;
       const float xj_f = a.ag.snap_x[gj], yj_f = a.ag.snap_y[gj];
-      const double cjx = __dadd_rn((double)xj_f, r), cjy = __dadd_rn((double)yj_f, r);
-      const double v2x = __dadd_rn(cjx, -fe.cix), v2y = __dadd_rn(cjy, -fe.ciy);
-      const double n2 = __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+      const double n2 = base_centre_distance(fe, r, xj_f, yj_f);
       const bool in_range = n2 <= a.vision_range;                                   // agent.py:400
       const bool is_expl = (j != i) && (a.ag.snap_override[gj] == OV_EXPLOIT);      // :402-403
       int cls = 0;   // 0 none, 1 social, 2 occluder (other), 3 occluder (same-patch exploiter)
@@ -248,73 +205,18 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
         }
       }
       if (!a.visual_exclusion && cls != 1) cls = 0;                                 // :415-419
-      const bool same = (xj_f == xi_f) && (yj_f == yi_f);                           // :502
-      if (cls != 0 && !same && n2 > 0.0) {
-        const double u2x = __ddiv_rn(v2x, n2), u2y = __ddiv_rn(v2y, n2);
-        double dot = __dadd_rn(__dmul_rn(fe.u1x, u2x), __dmul_rn(fe.u1y, u2y));
-        dot = fmin(1.0, fmax(-1.0, dot));
-        double ang = acos(dot);                                                     // supcalc.py:31
-        if (__dadd_rn(__dmul_rn(fe.u1x, u2y), -__dmul_rn(fe.u1y, u2x)) < 0.0) ang = -ang;
-        if (ang < 0.0) ang = __dadd_rn(ang, ABM_TWO_PI_D);                          // % 2pi (agent.py:516)
-        const double ca = (ang > 0.0 && ang < ABM_PI_D) ? -ang : __dadd_rn(ABM_TWO_PI_D, -ang);   // :520-523
-        if (a.fov0 < ca && ca < a.fov1) {                                           // :535
-          const int k = nearest_bin_exact(ca, R, a.lin_step);                       // :532
-          const double vis = __dmul_rn(2.0, atan(__ddiv_rn(r, n2)));                // :529
-          const double size = __dmul_rn(__ddiv_rn(vis, ABM_TWO_PI_D), (double)R);   // :543
-          const double half = __ddiv_rn(size, 2.0);
-          o.s = (int)__dadd_rn((double)k, -half);                                   // :545-546 int(): toward zero
-          o.e = (int)__dadd_rn((double)k, half);
-          o.d = n2;
-          social = (cls == 1);
-          // list order of the reference: social cues, then other occluders, then same-patch
-          // exploiters, each in agent order (agent.py:402-410, 472-477)
-          k2 = ((cls == 1) ? 0 : (cls == 2 ? 1 : 2)) * N + j;
-          rec = true;
-        }
+      if (cls != 0) {
+        double dist;
+        rec = base_interval(fe, r, xi_f, yi_f, xj_f, yj_f, a.fov0, a.fov1, R, a.lin_step, o, dist);
+        // list order of the reference: social cues, then other occluders, then same-patch
+        // exploiters, each in agent order (agent.py:402-410, 472-477)
+        k2 = (((cls == 1) ? 0 : (cls == 2 ? 1 : 2)) * N + j) | ((cls == 1) ? (1 << 30) : 0);
       }
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, rec);
-    if (rec) {
-      const int idx = M + __popc(mask & ((1u << lane) - 1u));
-      raw[idx] = o;
-      key[idx] = k2 | (social ? (1 << 30) : 0);
-    }
-    M += __popc(mask);
+    M = base_record(wf, M, rec, o, k2, lane);
   }
   __syncwarp();
-
-  // ---- occlusion (agent.py:421-445) and fill (agent.py:569-590) ----
-  if (a.visual_exclusion) {
-    for (int m = lane; m < M; m += 32) {   // rank by (distance, list order): stable sort of :424
-      const ObjRec f = raw[m];
-      const int kf = key[m] & 0x3fffffff;
-      int rank = 0;
-      for (int q = 0; q < M; ++q) {
-        const double dq = raw[q].d;
-        const int kq = key[q] & 0x3fffffff;
-        rank += (dq < f.d) || (dq == f.d && kq < kf);
-      }
-      sorted[rank] = f;
-      skey[rank] = key[m];
-    }
-    __syncwarp();
-    for (int p = lane; p < M; p += 32) {
-      if (!(skey[p] & (1 << 30))) continue;                                         // :447-455 only social cues are drawn
-      const ObjRec f = sorted[p];
-      int sx = f.s, ex = f.e;
-      for (int q = 0; q < p; ++q) {
-        const ObjRec o = sorted[q];
-        if (o.d < f.d) {                                                            // :430 strict
-          if (sx <= o.s && o.s <= ex) ex = o.s;                                     // :432-433
-          if (sx <= o.e && o.e <= ex) sx = o.e;                                     // :435-436
-          if (o.s <= sx && o.e >= ex) { sx = 0; ex = 0; }                           // :438-440
-        }
-      }
-      base_draw(row, R, sx, ex);
-    }
-  } else {
-    for (int m = lane; m < M; m += 32) base_draw(row, R, raw[m].s, raw[m].e);
-  }
+  base_occlude_fill(wf, M, a.visual_exclusion != 0, R, lane);   // agent.py:421-445, 569-590
   __syncwarp();
 
   // ---- flip + FOV mask (agent.py:593-595): stored[b] = v[R-1-b], kept for b in [mask_lo, mask_hi] ----
@@ -389,6 +291,207 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
   a.ag.w[gi] = (float)w; a.ag.u[gi] = (float)u; a.ag.i_priv[gi] = (float)I_priv;
   a.ag.override_mode[gi] = override; a.ag.mode[gi] = mode;
   a.ag.collected_before[gi] = (float)collected;              // :283
+}
+
+// ---------------------------------------------------------------------------------------
+// collision phase (sims.py:736-783, 421-468): one warp per replicate, sequential over the
+// colliding (a1, a2) pairs in group order -- an agent that collides with several others is
+// turned once per partner, each time from its already-turned heading.  PARITY UNPINNED for the
+// pair detection (pygame.sprite.collide_circle on int-truncated rect centres, not in the
+// reference tree); the proximity field itself is Agent.projection_field (agent.py:457-597).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const size_t per_warp = warp_field_bytes(a.N, a.W) + 4 * sizeof(int) * (size_t)a.N;
+  unsigned char* base = smem_raw + per_warp * wib;
+  WarpField wf = warp_field_at(base, a.N);
+  int* ov = reinterpret_cast<int*>(base + warp_field_bytes(a.N, a.W));   // override_mode, mutable
+  int* md = ov + a.N;                                                    // mode
+  float* th = reinterpret_cast<float*>(md + a.N);                        // heading
+  int* col = reinterpret_cast<int*>(th + a.N);                           // member of collided_agents
+  const int b = blockIdx.x * wpb + wib;
+  if (b >= a.B) return;
+  const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
+  const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
+  const size_t a0 = (size_t)b * a.N;
+  const int N = a.N, R = a.R, W = a.W, h = R / 2;
+  const double r = a.radius;
+  for (int i = lane; i < N; i += 32) {
+    ov[i] = a.ag.override_mode[a0 + i]; md[i] = a.ag.mode[a0 + i]; th[i] = a.ag.theta[a0 + i]; col[i] = 0;
+  }
+  __syncwarp();
+  const float lim2 = (float)((2.0 * (r + 2.0)) * (2.0 * (r + 2.0)));     // (r1 + 2 + r2 + 2)^2, sims.py:739-752
+
+  for (int a1 = 0; a1 < N; ++a1) {
+    const float x1 = truncf(a.ag.x[a0 + a1]), y1 = truncf(a.ag.y[a0 + a1]);   // rect.x = int(position) (agent.py:303-304)
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int jj = j0 + lane;
+      bool hit = false;
+      if (jj < N && jj != a1) {
+        const float dx = truncf(a.ag.x[a0 + jj]) - x1, dy = truncf(a.ag.y[a0 + jj]) - y1;
+        hit = dx * dx + dy * dy <= lim2;
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, hit);
+      while (hits) {
+        const int a2 = j0 + __ffs(hits) - 1;
+        hits &= hits - 1;
+        // ---- agent_agent_collision_proximity(a1, a2) (sims.py:421-468) ----
+        bool do_coll = true;
+        if (a.ghost_mode) do_coll = (ov[a2] != OV_EXPLOIT) && (ov[a1] != OV_EXPLOIT);
+        if (do_coll) {
+          __syncwarp();
+          if (lane == 0 && ov[a2] != OV_EXPLOIT) { ov[a2] = OV_COLLIDE; md[a2] = MODE_COLLIDE; }   // :442-443
+          for (int w = lane; w < W + 1; w += 32) wf.row[w] = 0u;
+          const float x2 = a.ag.x[a0 + a2], y2 = a.ag.y[a0 + a2];
+          const FocalExact fe = vf_focal_exact(x2, y2, (float)r, th[a2]);
+          int M = 0, last_j = -1;
+          double last_d = 0.0;
+          for (int v0 = 0; v0 < N; v0 += 32) {
+            const int j = v0 + lane;
+            bool rec = false, counted = false;
+            ObjRec o; o.s = 0; o.e = 0; o.d = 0.0;
+            double dist = 0.0;
+            if (j < N && j != a2) {
+              const float xj = a.ag.x[a0 + j], yj = a.ag.y[a0 + j];
+              if (base_centre_distance(fe, r, xj, yj) < 2.0 * r + 20.0) {           // :446-447
+                counted = !((xj == x2) && (yj == y2));
+                rec = base_interval(fe, r, x2, y2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o, dist);
+              }
+            }
+            // the loop variable `distance` that keep_distance_info leaks (agent.py:590): last obstacle in list order
+            const unsigned cm = __ballot_sync(0xffffffffu, counted);
+            if (cm) {
+              const int src = 31 - __clz(cm);
+              last_j = v0 + src;
+              last_d = __shfl_sync(0xffffffffu, dist, src);
+            }
+            M = base_record(wf, M, rec, o, j | (1 << 30), lane);
+          }
+          __syncwarp();
+          base_occlude_fill(wf, M, a.visual_exclusion != 0, R, lane);
+          const int n_left = popc_range(wf.row, W, R - h, R, lane);                 // stored[0:h]
+          const int n_right = popc_range(wf.row, W, 0, R - h, lane);                // stored[h:]
+          int flo = h - 100, fhi = h + 100;                                         // :462 with numpy slice semantics
+          if (flo < 0) flo = max(flo + R, 0);
+          flo = min(flo, R); fhi = min(fhi, R);
+          const int n_front = (fhi > flo) ? popc_range(wf.row, W, R - fhi, R - flo, lane) : 0;
+          if (lane == 0) {
+            const double amp = (last_j >= 0) ? 1.0 - last_d / a.vision_range : 1.0;
+            const double left = amp * (double)n_left / (double)h, right = amp * (double)n_right / (double)(R - h);
+            double D = (left > right) ? 1.0 : ((left < right) ? -1.0 : 0.0);
+            if (D == 0.0) D = -1.0;                                                  // :456
+            if (ov[a2] != OV_EXPLOIT) th[a2] = (float)((double)th[a2] - D * 0.2);   // :458-459 (not wrapped)
+            if (amp * (double)n_front > 0.0) a.ag.vel[a0 + a2] = 0.0f;              // :462-463
+            else if (ov[a2] != OV_EXPLOIT) a.ag.vel[a0 + a2] = (float)prm.exp_vel_max;
+          }
+          __syncwarp();
+        }
+        // ---- collided_agents bookkeeping (sims.py:759-776) ----
+        if (lane == 0) {
+          const bool e1 = ov[a1] == OV_EXPLOIT, e2 = ov[a2] == OV_EXPLOIT;
+          if (a.teleport_exploit) { if (!e1) col[a1] = 1; if (!e2) col[a2] = 1; }
+          else if (!a.ghost_mode) { col[a1] = 1; col[a2] = 1; }
+          else if (!e1 && !e2) { col[a1] = 1; col[a2] = 1; }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < N; i += 32) {                                              // sims.py:778-783
+    const size_t g = a0 + i;
+    if (!col[i] && ov[i] == OV_COLLIDE) { ov[i] = OV_NONE; md[i] = MODE_EXPLORE; }
+    if (col[i] && ov[i] == OV_COLLIDE) notify(a.ag, g, -1, -1, tau_mask);
+    a.ag.override_mode[g] = ov[i]; a.ag.mode[g] = md[i]; a.ag.theta[g] = th[i]; a.ag.collided[g] = col[i];
+  }
+}
+
+void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int smem_max = 48 * 1024;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t per_warp = warp_field_bytes(a.N, a.W) + 4 * sizeof(int) * (size_t)a.N;
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > (size_t)smem_max) warps >>= 1;
+  const size_t smem = per_warp * warps;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(base_collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  base_collision_kernel<<<(a.B + warps - 1) / warps, warps * 32, smem, stream>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------
+// stateless function-level kernels
+// ---------------------------------------------------------------------------------------
+__global__ void base_projection_kernel(const BaseProjArgs a) {   // one warp
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int n = a.n_social + a.n_occ;
+  WarpField wf = warp_field_at(smem_raw, n > 0 ? n : 1);
+  for (int w = lane; w < a.W + 1; w += 32) wf.row[w] = 0u;
+  const FocalExact fe = vf_focal_exact(a.fx, a.fy, (float)a.radius, a.ftheta);
+  int M = 0, last_j = -1;
+  double last_d = 0.0;
+  const int n_used = a.visual_exclusion ? n : a.n_social;            // agent.py:475-477, :415-419
+  for (int j0 = 0; j0 < n_used; j0 += 32) {
+    const int j = j0 + lane;
+    bool rec = false, counted = false;
+    ObjRec o; o.s = 0; o.e = 0; o.d = 0.0;
+    double dist = 0.0;
+    if (j < n_used) {
+      counted = !((a.ox[j] == a.fx) && (a.oy[j] == a.fy));
+      rec = base_interval(fe, a.radius, a.fx, a.fy, a.ox[j], a.oy[j], a.fov0, a.fov1, a.R, a.lin_step, o, dist);
+    }
+    const unsigned cm = __ballot_sync(0xffffffffu, counted);
+    if (cm) { const int src = 31 - __clz(cm); last_j = j0 + src; last_d = __shfl_sync(0xffffffffu, dist, src); }
+    M = base_record(wf, M, rec, o, j | ((j < a.n_social) ? (1 << 30) : 0), lane);
+  }
+  __syncwarp();
+  base_occlude_fill(wf, M, a.visual_exclusion != 0, a.R, lane);
+  for (int ws = lane; ws < a.W; ws += 32) {
+    uint32_t word = flipped_word(wf.row, 1, a.R, a.W, ws);
+    const int lo = max(a.mask_lo - (ws << 5), 0), hi = min(a.mask_hi + 1 - (ws << 5), 32);
+    uint32_t m = 0u;
+    if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+    a.field[ws] = word & m;
+  }
+  if (lane == 0) *a.amplitude = (a.keep_distance && last_j >= 0) ? 1.0 - last_d / a.vision_range : 1.0;
+}
+void launch_base_projection(const BaseProjArgs& a, cudaStream_t stream) {
+  const int n = a.n_social + a.n_occ;
+  const size_t smem = warp_field_bytes(n > 0 ? n : 1, a.W);
+  cudaFuncSetAttribute(base_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  base_projection_kernel<<<1, 32, smem, stream>>>(a);
+}
+
+__global__ void base_reloc_lr_kernel(const uint32_t* field, int R, int W, double amp, double vel, double vdes,
+                                     double thmax, double* out2) {   // one warp; field in STORED order
+  const int lane = threadIdx.x, h = R / 2;
+  const int n_left = popc_range(field, W, 0, h, lane), n_right = popc_range(field, W, h, R, lane);
+  if (lane == 0) {
+    out2[0] = vdes - vel;                                                           // supcalc.py:92
+    out2[1] = (amp * (double)n_left / (double)h - amp * (double)n_right / (double)(R - h)) * thmax;   // :86-91
+  }
+}
+void launch_base_reloc_lr(const uint32_t* field, int R, int W, double amp, double vel, double vdes, double thmax,
+                          double* out2, cudaStream_t stream) {
+  base_reloc_lr_kernel<<<1, 32, 0, stream>>>(field, R, W, amp, vel, vdes, thmax, out2);
+}
+
+__global__ void vf_dphi_kernel(const uint32_t* v, int R, int W, signed char* out) {   // vf_supcalc.py:257-277
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= R) return;
+  auto bit = [&](int i) { return (int)((v[i >> 5] >> (i & 31)) & 1u); };
+  const bool backward = bit(0) - bit(R - 1) > 0;
+  out[k] = backward ? (signed char)(bit(k) - bit(k == 0 ? R - 1 : k - 1))
+                    : (signed char)(bit(k == R - 1 ? 0 : k + 1) - bit(k));
+}
+void launch_vf_dphi(const uint32_t* v, int R, int W, signed char* out, cudaStream_t stream) {
+  vf_dphi_kernel<<<(R + 127) / 128, 128, 0, stream>>>(v, R, W, out);
 }
 
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream) {

@@ -28,6 +28,7 @@ struct BaseAgentPtrs {
   // frozen snapshot read by the agent phase (Jacobi update): written at the end of the environment phase
   float *snap_x, *snap_y;
   int32_t* snap_override;
+  int32_t* collided;   // 1 = member of `collided_agents` of this step (sims.py:754-783); all 0 without collisions
 };
 struct BasePatchPtrs {
   float *x, *y, *radius, *left, *quality;
@@ -36,7 +37,7 @@ struct BasePatchPtrs {
 
 struct BaseKernelArgs {
   int B, N, P, R, W, Tau;
-  int visual_exclusion, patchwise_exclusion, teleport_exploit, regenerate, border_overlap;
+  int visual_exclusion, patchwise_exclusion, teleport_exploit, regenerate, border_overlap, ghost_mode;
   double fov0, fov1;           // agent FOV in radians (strict test on the closed angle, agent.py:535)
   int mask_lo, mask_hi;        // stored bins kept by the FOV mask: phis[b] >= fov0 && phis[b] <= fov1 (agent.py:594-595)
   double lin_step;             // numpy linspace step (see nearest_bin_exact)
@@ -57,6 +58,20 @@ struct BaseKernelArgs {
 
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream);
+void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream);
+
+struct BaseProjArgs {
+  int R, W, n_social, n_occ, visual_exclusion, keep_distance;
+  int mask_lo, mask_hi;
+  double fov0, fov1, lin_step, radius, vision_range;
+  float fx, fy, ftheta;
+  const float* ox; const float* oy;   // n_social + n_occ positions
+  uint32_t* field; double* amplitude;
+};
+void launch_base_projection(const BaseProjArgs& a, cudaStream_t stream);
+void launch_base_reloc_lr(const uint32_t* field, int R, int W, double amp, double vel, double vdes, double thmax,
+                          double* out2, cudaStream_t stream);
+void launch_vf_dphi(const uint32_t* v, int R, int W, signed char* out, cudaStream_t stream);
 size_t base_agents_smem_bytes(int N, int W, int warps);
 int base_agents_warps(int N, int W, size_t smem_limit);
 

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "abm_api_util.cuh"
 #include "abm_base.cuh"
@@ -16,7 +17,7 @@ struct abm_base_engine {
   double lin_step = 0.0;
   size_t n_agents_total = 0, n_patches_total = 0;
   DevBuf<float> x, y, theta, vel, w, u, collected, collected_before, i_priv, snap_x, snap_y;
-  DevBuf<int32_t> env_status, override_mode, mode, patch_id, snap_override;
+  DevBuf<int32_t> env_status, override_mode, mode, patch_id, snap_override, collided;
   DevBuf<uint32_t> novelty, fields;
   DevBuf<float> px, py, pradius, pleft, pquality;
   DevBuf<int32_t> pid;
@@ -92,7 +93,8 @@ int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t*
   auto A = [&](cudaError_t r) { if (err == cudaSuccess) err = r; };
   for (DevBuf<float>* b : {&e->x, &e->y, &e->theta, &e->vel, &e->w, &e->u, &e->collected, &e->collected_before,
                            &e->i_priv, &e->snap_x, &e->snap_y, &e->inject}) A(b->alloc(na));
-  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override}) A(b->alloc(na));
+  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->collided})
+    A(b->alloc(na));
   A(e->novelty.alloc(na));
   if (cfg->keep_fields) A(e->fields.alloc(na * e->W));
   for (DevBuf<float>* b : {&e->px, &e->py, &e->pradius, &e->pleft, &e->pquality}) A(b->alloc(np));
@@ -106,7 +108,7 @@ int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t*
   if (err == cudaSuccess) err = cudaMemcpy(e->params.p, defaults, sizeof(defaults), cudaMemcpyHostToDevice);
   for (DevBuf<float>* b : {&e->w, &e->u, &e->collected, &e->collected_before, &e->i_priv, &e->vel})
     if (err == cudaSuccess) err = cudaMemset(b->p, 0, sizeof(float) * na);
-  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode})
+  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->collided})
     if (err == cudaSuccess) err = cudaMemset(b->p, 0, sizeof(int32_t) * na);
   if (err == cudaSuccess) err = cudaMemset(e->patch_id.p, 0xff, sizeof(int32_t) * na);
   if (err == cudaSuccess) err = cudaMemset(e->novelty.p, 0, sizeof(uint32_t) * na);
@@ -126,8 +128,8 @@ int abm_base_destroy(abm_base_engine_t* e) {
   for (DevBuf<float>* b : {&e->x, &e->y, &e->theta, &e->vel, &e->w, &e->u, &e->collected, &e->collected_before,
                            &e->i_priv, &e->snap_x, &e->snap_y, &e->inject, &e->px, &e->py, &e->pradius, &e->pleft,
                            &e->pquality}) b->release();
-  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid})
-    b->release();
+  for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid,
+                             &e->collided}) b->release();
   e->novelty.release(); e->fields.release(); e->params.release(); e->counters.release();
   delete e;
   return ABM_OK;
@@ -220,13 +222,14 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   a.B = c.n_replicates; a.N = c.n_agents; a.P = c.n_patches; a.R = c.resolution; a.W = e->W; a.Tau = c.tau;
   a.visual_exclusion = c.visual_exclusion; a.patchwise_exclusion = c.patchwise_exclusion;
   a.teleport_exploit = c.teleport_exploit; a.regenerate = c.regenerate_patches; a.border_overlap = c.patch_border_overlap;
+  a.ghost_mode = c.ghost_mode;
   a.fov0 = c.fov0; a.fov1 = c.fov1; a.mask_lo = e->mask_lo; a.mask_hi = e->mask_hi; a.lin_step = e->lin_step;
   a.width = c.width; a.height = c.height; a.pad = c.window_pad; a.vision_range = c.vision_range; a.radius = c.agent_radius;
   a.patch_radius = c.patch_radius; a.min_quality = c.min_quality; a.max_quality = c.max_quality;
   a.min_units = c.min_units; a.max_units = c.max_units; a.seed = c.seed;
   a.ag = abm::BaseAgentPtrs{e->x.p, e->y.p, e->theta.p, e->vel.p, e->w.p, e->u.p, e->collected.p,
                             e->collected_before.p, e->i_priv.p, e->env_status.p, e->override_mode.p, e->mode.p,
-                            e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p};
+                            e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p};
   a.pa = abm::BasePatchPtrs{e->px.p, e->py.p, e->pradius.p, e->pleft.p, e->pquality.p, e->pid.p};
   a.params = e->params.p; a.param_stride = (e->n_param_sets == 1) ? 0 : abm::kBaseNParam;
   a.fields_out = e->fields.p; a.counters = e->counters.p;
@@ -240,6 +243,7 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   }
   for (int s = 0; s < n_steps; ++s) {
     a.step = e->step;
+    if ((phases & ABM_BASE_PHASE_COLLISIONS) && c.collide_agents) { abm::launch_base_collisions(a, st); ++e->launches; }
     if (phases & ABM_BASE_PHASE_ENV) { abm::launch_base_env(a, st); ++e->launches; }
     else {   // agent phase alone: the snapshot is the current state
       ABM_CUDA(cudaMemcpyAsync(e->snap_x.p, e->x.p, sizeof(float) * e->n_agents_total, cudaMemcpyDeviceToDevice, st));
@@ -273,6 +277,96 @@ int abm_base_get_counters(abm_base_engine_t* e, uint64_t counters[4], void* stre
   ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   counters[0] = h[0]; counters[1] = h[1]; counters[2] = e->launches; counters[3] = e->steps;
   return ABM_OK;
+}
+
+
+// ---- stateless function-level entry points ----
+
+int abm_base_projection_field(const abm_base_proj_args_t* args, uint32_t* out_field, double* out_amplitude) {
+  if (!args || !out_field) return fail(ABM_E_INVALID, "abm_base_projection_field: null argument");
+  if (args->struct_size != (int32_t)sizeof(abm_base_proj_args_t))
+    return fail(ABM_E_INVALID, "abm_base_projection_field: struct_size mismatch");
+  const int R = args->resolution;
+  if (R < 8 || R > 65535) return fail(ABM_E_INVALID, "abm_base_projection_field: bad resolution");
+  const int ns = args->n_social, no = args->n_occluders, n = ns + no;
+  if (ns < 0 || no < 0 || (ns > 0 && (!args->social_x || !args->social_y)) || (no > 0 && (!args->occluder_x || !args->occluder_y)))
+    return fail(ABM_E_INVALID, "abm_base_projection_field: bad object lists");
+  const int W = (R + 31) / 32;
+  std::vector<float> hx(n > 0 ? n : 1), hy(n > 0 ? n : 1);
+  for (int j = 0; j < ns; ++j) { hx[j] = (float)args->social_x[j]; hy[j] = (float)args->social_y[j]; }
+  for (int j = 0; j < no; ++j) { hx[ns + j] = (float)args->occluder_x[j]; hy[ns + j] = (float)args->occluder_y[j]; }
+  abm::BaseProjArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R; a.W = W; a.n_social = ns; a.n_occ = no;
+  a.visual_exclusion = args->visual_exclusion; a.keep_distance = args->keep_distance_info;
+  a.fov0 = args->fov0; a.fov1 = args->fov1; a.lin_step = ABM_TWO_PI_D / (double)(R - 1);
+  a.radius = args->radius; a.vision_range = args->vision_range;
+  a.fx = (float)args->x; a.fy = (float)args->y; a.ftheta = (float)args->orientation;
+  a.mask_lo = R; a.mask_hi = -1;
+  for (int k = 0; k < R; ++k) {
+    const double phi = (k == R - 1) ? ABM_PI_D : ((double)k * a.lin_step + (-ABM_PI_D));
+    if (!(phi < a.fov0) && !(phi > a.fov1)) { if (k < a.mask_lo) a.mask_lo = k; if (k > a.mask_hi) a.mask_hi = k; }
+  }
+  DevBuf<float> dx, dy; DevBuf<uint32_t> df; DevBuf<double> da;
+  ABM_CUDA(dx.alloc(hx.size())); ABM_CUDA(dy.alloc(hy.size())); ABM_CUDA(df.alloc(W)); ABM_CUDA(da.alloc(1));
+  int rc = ABM_OK;
+  cudaError_t ce;
+  double amp = 1.0;
+  if ((ce = cudaMemcpy(dx.p, hx.data(), sizeof(float) * hx.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (ce = cudaMemcpy(dy.p, hy.data(), sizeof(float) * hy.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  } else {
+    a.ox = dx.p; a.oy = dy.p; a.field = df.p; a.amplitude = da.p;
+    abm::launch_base_projection(a, 0);
+    if ((ce = cudaGetLastError()) != cudaSuccess ||
+        (ce = cudaMemcpy(out_field, df.p, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (ce = cudaMemcpy(&amp, da.p, sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  }
+  if (out_amplitude) *out_amplitude = amp;
+  dx.release(); dy.release(); df.release(); da.release();
+  return rc;
+}
+
+int abm_base_reloc_lr(const uint32_t* packed_field, int resolution, double amplitude, double vel_now, double v_desired,
+                      double reloc_theta_max, double out[2]) {
+  if (!packed_field || !out) return fail(ABM_E_INVALID, "abm_base_reloc_lr: null argument");
+  if (resolution < 8 || resolution > 65535) return fail(ABM_E_INVALID, "abm_base_reloc_lr: bad resolution");
+  const int W = (resolution + 31) / 32;
+  DevBuf<uint32_t> df; DevBuf<double> dout;
+  ABM_CUDA(df.alloc(W)); ABM_CUDA(dout.alloc(2));
+  int rc = ABM_OK;
+  cudaError_t ce;
+  if ((ce = cudaMemcpy(df.p, packed_field, sizeof(uint32_t) * W, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  } else {
+    abm::launch_base_reloc_lr(df.p, resolution, W, amplitude, vel_now, v_desired, reloc_theta_max, dout.p, 0);
+    if ((ce = cudaGetLastError()) != cudaSuccess ||
+        (ce = cudaMemcpy(out, dout.p, sizeof(double) * 2, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  }
+  df.release(); dout.release();
+  return rc;
+}
+
+int abm_vf_dphi(const uint32_t* packed_v, int resolution, int8_t* out) {
+  if (!packed_v || !out) return fail(ABM_E_INVALID, "abm_vf_dphi: null argument");
+  if (resolution < 2 || resolution > 65535) return fail(ABM_E_INVALID, "abm_vf_dphi: bad resolution");
+  const int W = (resolution + 31) / 32;
+  DevBuf<uint32_t> dv; DevBuf<signed char> dout;
+  ABM_CUDA(dv.alloc(W)); ABM_CUDA(dout.alloc(resolution));
+  int rc = ABM_OK;
+  cudaError_t ce;
+  if ((ce = cudaMemcpy(dv.p, packed_v, sizeof(uint32_t) * W, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  } else {
+    abm::launch_vf_dphi(dv.p, resolution, W, dout.p, 0);
+    if ((ce = cudaGetLastError()) != cudaSuccess ||
+        (ce = cudaMemcpy(out, dout.p, resolution, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+  }
+  dv.release(); dout.release();
+  return rc;
 }
 
 }  // extern "C"

@@ -1,0 +1,157 @@
+// Warp-level building blocks of the BASE visual field (Agent.projection_field, agent.py:457-597),
+// shared by the agent phase, the collision phase and the stateless function-level kernel.
+#pragma once
+#include "abm_base.cuh"
+#include "abm_vf_device.cuh"
+
+namespace abm {
+
+struct __align__(16) ObjRec {
+  int s, e;      // raw interval ends, int() truncated (agent.py:545-546)
+  double d;      // centre distance (agent.py:526-528)
+};
+
+// per-warp shared-memory work area for up to N objects and a row of W words
+struct WarpField {
+  ObjRec* raw;      // recorded objects in list order
+  ObjRec* sorted;   // ranked by (distance, list order)
+  int* key;         // list-order key of raw[m]; bit 30 = social cue (drawn), else occluder only
+  int* skey;        // same for sorted[rank]
+  uint32_t* row;    // un-flipped field v (agent.py:480), W + 1 words
+};
+__host__ __device__ inline size_t warp_field_bytes(int N, int W) {
+  return (2 * sizeof(ObjRec) * (size_t)N + 2 * sizeof(int) * (size_t)N + sizeof(uint32_t) * (size_t)(W + 1) + 15) / 16 * 16;
+}
+__device__ __forceinline__ WarpField warp_field_at(unsigned char* base, int N) {
+  WarpField wf;
+  wf.raw = reinterpret_cast<ObjRec*>(base);
+  wf.sorted = wf.raw + N;
+  wf.key = reinterpret_cast<int*>(wf.sorted + N);
+  wf.skey = wf.key + N;
+  wf.row = reinterpret_cast<uint32_t*>(wf.skey + N);
+  return wf;
+}
+
+// supcalc.distance between agent centres, both with the focal radius (supcalc.py:73-78, agent.py:504-509)
+__device__ __forceinline__ double base_centre_distance(const FocalExact& fe, double r, float xj, float yj) {
+  const double v2x = __dadd_rn(__dadd_rn((double)xj, r), -fe.cix), v2y = __dadd_rn(__dadd_rn((double)yj, r), -fe.ciy);
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+}
+
+// One obstacle of Agent.projection_field (agent.py:501-556), fp64, the reference's operation
+// order.  Returns true if the obstacle is recorded (not at the focal position, strictly inside
+// the FOV); `dist` is set whenever the position test passes (the loop variable that
+// keep_distance_info leaks, agent.py:528 / :590), else left untouched.
+__device__ __forceinline__ bool base_interval(const FocalExact& fe, double r, float xi, float yi, float xj, float yj,
+                                              double fov0, double fov1, int R, double lin_step, ObjRec& o,
+                                              double& dist) {
+  if ((xj == xi) && (yj == yi)) return false;                                       // :502
+  const double v2x = __dadd_rn(__dadd_rn((double)xj, r), -fe.cix), v2y = __dadd_rn(__dadd_rn((double)yj, r), -fe.ciy);
+  const double n2 = __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+  dist = n2;
+  if (!(n2 > 0.0)) return false;
+  const double u2x = __ddiv_rn(v2x, n2), u2y = __ddiv_rn(v2y, n2);
+  double dot = __dadd_rn(__dmul_rn(fe.u1x, u2x), __dmul_rn(fe.u1y, u2y));
+  dot = fmin(1.0, fmax(-1.0, dot));
+  double ang = acos(dot);                                                           // supcalc.py:31
+  if (__dadd_rn(__dmul_rn(fe.u1x, u2y), -__dmul_rn(fe.u1y, u2x)) < 0.0) ang = -ang;
+  if (ang < 0.0) ang = __dadd_rn(ang, ABM_TWO_PI_D);                                // % 2pi (agent.py:516)
+  const double ca = (ang > 0.0 && ang < ABM_PI_D) ? -ang : __dadd_rn(ABM_TWO_PI_D, -ang);   // :520-523
+  if (!(fov0 < ca && ca < fov1)) return false;                                      // :535
+  const int k = nearest_bin_exact(ca, R, lin_step);                                 // :532
+  const double vis = __dmul_rn(2.0, atan(__ddiv_rn(r, n2)));                        // :529
+  const double size = __dmul_rn(__ddiv_rn(vis, ABM_TWO_PI_D), (double)R);           // :543
+  const double half = __ddiv_rn(size, 2.0);
+  o.s = (int)__dadd_rn((double)k, -half);                                           // :545-546 int(): toward zero
+  o.e = (int)__dadd_rn((double)k, half);
+  o.d = n2;
+  return true;
+}
+
+// append this lane's object (if `rec`) in lane order; returns the new object count
+__device__ __forceinline__ int base_record(WarpField& wf, int M, bool rec, const ObjRec& o, int key, int lane) {
+  const unsigned mask = __ballot_sync(0xffffffffu, rec);
+  if (rec) {
+    const int idx = M + __popc(mask & ((1u << lane) - 1u));
+    wf.raw[idx] = o;
+    wf.key[idx] = key;
+  }
+  return M + __popc(mask);
+}
+
+// numpy basic-slice bounds of v[a:b] on a length-R array (negative indices count from the end)
+__device__ __forceinline__ void np_slice(int a, int b, int R, int& lo, int& hi) {
+  if (a < 0) a = max(a + R, 0);
+  if (b < 0) b = max(b + R, 0);
+  lo = min(a, R);
+  hi = min(b, R);
+}
+__device__ __forceinline__ void base_draw(uint32_t* row, int R, int s, int e) {   // agent.py:577-588
+  int lo, hi;
+  if (s < 0) { np_slice(R + s, R, R, lo, hi); if (hi > lo) set_range<true>(row, 1, lo, hi); s = 0; }
+  if (e >= R) { np_slice(0, e - R, R, lo, hi); if (hi > lo) set_range<true>(row, 1, lo, hi); e = R - 1; }
+  np_slice(s, e, R, lo, hi);
+  if (hi > lo) set_range<true>(row, 1, lo, hi);
+}
+
+// Occlusion (Agent.exlude_V_source_data, agent.py:421-445) and fill (agent.py:569-590) of the M
+// recorded objects into wf.row (which must be zeroed).  Ends with a __syncwarp.
+__device__ __forceinline__ void base_occlude_fill(WarpField& wf, int M, bool visual_exclusion, int R, int lane) {
+  if (visual_exclusion) {
+    for (int m = lane; m < M; m += 32) {   // rank by (distance, list order): the stable sort of :424
+      const ObjRec f = wf.raw[m];
+      const int kf = wf.key[m] & 0x3fffffff;
+      int rank = 0;
+      for (int q = 0; q < M; ++q) {
+        const double dq = wf.raw[q].d;
+        const int kq = wf.key[q] & 0x3fffffff;
+        rank += (dq < f.d) || (dq == f.d && kq < kf);
+      }
+      wf.sorted[rank] = f;
+      wf.skey[rank] = wf.key[m];
+    }
+    __syncwarp();
+    for (int p = lane; p < M; p += 32) {
+      if (!(wf.skey[p] & (1 << 30))) continue;                                      // :447-455 only social cues are drawn
+      const ObjRec f = wf.sorted[p];
+      int sx = f.s, ex = f.e;
+      for (int q = 0; q < p; ++q) {
+        const ObjRec o = wf.sorted[q];
+        if (o.d < f.d) {                                                            // :430 strict
+          if (sx <= o.s && o.s <= ex) ex = o.s;                                     // :432-433
+          if (sx <= o.e && o.e <= ex) sx = o.e;                                     // :435-436
+          if (o.s <= sx && o.e >= ex) { sx = 0; ex = 0; }                           // :438-440
+        }
+      }
+      base_draw(wf.row, R, sx, ex);
+    }
+  } else {
+    for (int m = lane; m < M; m += 32)
+      if (wf.key[m] & (1 << 30)) base_draw(wf.row, R, wf.raw[m].s, wf.raw[m].e);
+  }
+  __syncwarp();
+}
+
+// number of set bits of row in bins [a, b)
+__device__ __forceinline__ int popc_range(const uint32_t* row, int W, int a, int b, int lane) {
+  int n = 0;
+  for (int w = lane; w < W; w += 32) {
+    const int lo = max(a - (w << 5), 0), hi = min(b - (w << 5), 32);
+    if (hi > lo) {
+      uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+      n += __popc(row[w] & m);
+    }
+  }
+  return __reduce_add_sync(0xffffffffu, n);
+}
+
+// set bits of the STORED field (stored[b] = v[R-1-b], kept for b in [mask_lo, mask_hi]) in stored bins [sa, sb)
+__device__ __forceinline__ int popc_stored(const uint32_t* row, int R, int W, int mask_lo, int mask_hi, int sa, int sb,
+                                           int lane) {
+  sa = max(sa, mask_lo);
+  sb = min(sb, mask_hi + 1);
+  if (sb <= sa) return 0;
+  return popc_range(row, W, R - sb, R - sa, lane);
+}
+
+}  // namespace abm

@@ -249,9 +249,6 @@ class Simulation:
             raise NotImplementedError("rendering is out of scope of abm_b200 (headless only)")
         if pooling_time != 0:
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
-        if collide_agents:
-            raise NotImplementedError("agent-agent collision avoidance (sims.py:736-783) is not implemented yet; "
-                                      "run with AGENT_AGENT_COLLISION=0")
         if agent_behave_param_list is not None:
             raise NotImplementedError("heterogeneous agent_behave_param_list is not supported yet (SURVEY f4)")
         self.N, self.T, self.t = int(N), int(T), 0
@@ -275,7 +272,8 @@ class Simulation:
                                  patch_radius=patch_radius, min_resc_quality=min_resc_quality,
                                  max_resc_quality=max_resc_quality, min_resc_perpatch=min_resc_perpatch,
                                  max_resc_perpatch=max_resc_perpatch, tau=self.decision_params.Tau,
-                                 keep_fields=keep_fields, seed=0 if seed is None else int(seed), device=device)
+                                 keep_fields=keep_fields, collide_agents=collide_agents, ghost_mode=ghost_mode,
+                                 seed=0 if seed is None else int(seed), device=device)
         self.engine.set_params(agent_consumption=agent_consumption, **self.decision_params.engine_kwargs())
         self.agents, self.rescources = [], []
         self._a = self._p = self._f = None

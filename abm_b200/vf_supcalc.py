@@ -83,3 +83,15 @@ def VSWRM_flocking_state_variables(vel_now, Phi, V_now, vf_params, t_now=None, V
     if not verbose:
         return out[0], out[1]
     return tuple(out)
+
+
+def dPhi_V_of(Phi, V):
+    """Derivative of the visual projection field w.r.t. the visual angle: circular first
+    difference with the reference's forward / backward rule (vf_supcalc.py:257-277)."""
+    lib = _lib.load()
+    Vb = np.asarray(V)
+    R = Vb.shape[0]
+    packed = _pack(Vb)
+    out = np.zeros(R, np.int8)
+    _lib.check(lib.abm_vf_dphi(C.c_void_p(packed.ctypes.data), R, C.c_void_p(out.ctypes.data)), "abm_vf_dphi")
+    return out.astype(np.float64)

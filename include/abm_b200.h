@@ -188,6 +188,9 @@ typedef struct {
   int32_t regenerate_patches;   /* REGENERATE_PATCHES (sims.py:321-330) */
   int32_t patch_border_overlap; /* PATCH_BORDER_OVERLAP (sims.py:351-358) */
   int32_t keep_fields;          /* keep packed stored fields of the last step (abm_base_get_fields) */
+  int32_t collide_agents;       /* AGENT_AGENT_COLLISION (sims.py:736-783); pair detection restates pygame's
+                                   documented collide_circle -- parity unpinned, see DESIGN.md */
+  int32_t ghost_mode;           /* GHOST_WHILE_EXPLOIT (sims.py:431-436, 771-776) */
   double fov0, fov1;            /* agent_fov in radians: (-fov*pi, fov*pi) (sims.py:160-161) */
   double width, height, window_pad;
   double vision_range;          /* VISION_RANGE (agent.py:400) */
@@ -225,7 +228,7 @@ typedef struct {
   int32_t* id;
 } abm_base_patches_t;
 
-enum { ABM_BASE_PHASE_ENV = 1, ABM_BASE_PHASE_AGENTS = 2, ABM_BASE_PHASE_ALL = 3 };
+enum { ABM_BASE_PHASE_ENV = 1, ABM_BASE_PHASE_AGENTS = 2, ABM_BASE_PHASE_COLLISIONS = 4, ABM_BASE_PHASE_ALL = 7 };
 
 /* Replaces: Simulation(**kwargs) + create_agents / create_resources (sims.py:526-541). */
 int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t** out);
@@ -251,6 +254,38 @@ int abm_base_get_fields(abm_base_engine_t* e, uint32_t* packed, int on_device, v
 /* counters[0] = patches regenerated, [1] = regenerations that exhausted their retries,
  * [2] = kernel launches, [3] = steps. */
 int abm_base_get_counters(abm_base_engine_t* e, uint64_t counters[4], void* stream);
+
+/* ---- stateless function-level entry points of the BASE variant (host pointers, synchronous) ---- */
+
+/* Agent.projection_field(obstacles, keep_distance_info, non_expl_agents, fov) (agent.py:457-597)
+ * of one focal agent.  Objects are [social..., occluders...] in list order; occluders are only
+ * used when visual_exclusion != 0 (they clip, they are never drawn).  out_field: packed STORED
+ * field (flipped + FOV-masked), abm_field_words(R) words.  out_amplitude: the value the set bins
+ * carry: 1, or 1 - distance_last / vision_range with keep_distance_info (agent.py:590). */
+typedef struct {
+  int32_t struct_size;
+  int32_t resolution;
+  double fov0, fov1;
+  double x, y, radius, orientation;
+  int32_t n_social;
+  int32_t n_occluders;
+  const double* social_x;
+  const double* social_y;
+  const double* occluder_x;
+  const double* occluder_y;
+  int32_t visual_exclusion;
+  int32_t keep_distance_info;
+  double vision_range;
+} abm_base_proj_args_t;
+int abm_base_projection_field(const abm_base_proj_args_t* args, uint32_t* out_field, double* out_amplitude);
+
+/* supcalc.F_reloc_LR(vel_now, V_now, v_desired) (supcalc.py:81-92) on a packed STORED field:
+ * out[0] = v_desired - vel_now, out[1] = (mean(V[:R/2]) - mean(V[R/2:])) * amplitude * reloc_theta_max. */
+int abm_base_reloc_lr(const uint32_t* packed_field, int resolution, double amplitude, double vel_now,
+                      double v_desired, double reloc_theta_max, double out[2]);
+
+/* vf_supcalc.dPhi_V_of(Phi, V) (vf_supcalc.py:257-277) on a packed field: out[k] in {-1, 0, 1}. */
+int abm_vf_dphi(const uint32_t* packed_v, int resolution, int8_t* out);
 
 #ifdef __cplusplus
 }

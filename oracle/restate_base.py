@@ -290,3 +290,80 @@ def base_patch_phase(st, patches, cfg: BaseConfig, collided=()):
         if not on_patch[i] and i not in collided:
             notify(st, i, -1)
     return depleted
+
+
+# --------------------------------------------------------------------------------------
+# collision phase (sims.py:736-783, 421-468; interactions.py:5-10)  -- PARITY UNPINNED
+# --------------------------------------------------------------------------------------
+
+def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool):
+    """Agent-agent collision avoidance of one time step, in place.  Restated from the
+    reference's control flow plus pygame's DOCUMENTED semantics (pygame itself is not in the
+    reference tree, so this part cannot be pinned against reference output -- SURVEY 8c):
+    groupcollide(agents, agents, within_group_collision) -> for every agent a1 in group order
+    the list of a2 != a1 with (rect centre distance)^2 <= (r1 + r2)^2, radii temporarily +2,
+    rect.x / rect.y = int-truncated position (agent.py:303-304).  Returns the list
+    `collided_agents` (with repetitions, as the reference builds it)."""
+    N = len(st["x"])
+    r = st["radius"]
+    ix, iy = np.trunc(st["x"]), np.trunc(st["y"])
+    lim2 = (2 * (r + 2)) ** 2                                                     # sims.py:739-752
+    collided = []
+    R = cfg.R
+    h = int(R / 2)
+    for a1 in range(N):
+        partners = [a2 for a2 in range(N)
+                    if a2 != a1 and (ix[a1] - ix[a2]) ** 2 + (iy[a1] - iy[a2]) ** 2 <= lim2]
+        if not partners:
+            continue
+        for a2 in partners:                                                       # agent_agent_collision_proximity :421-468
+            do = True
+            if ghost_mode:
+                do = st["override"][a2] != OV_EXPLOIT and st["override"][a1] != OV_EXPLOIT
+            if not do:
+                continue
+            if st["override"][a2] != OV_EXPLOIT:
+                st["override"][a2] = OV_COLLIDE
+                st["mode"][a2] = MODE_COLLIDE
+            d = np.sqrt(((st["x"] + r) - (st["x"][a2] + r)) ** 2 + ((st["y"] + r) - (st["y"][a2] + r)) ** 2)
+            vicinity = [j for j in range(N) if d[j] < 2 * r + 20 and j != a2]     # :446-447
+            full = (-np.pi, np.pi)
+            src = base_source_data(a2, st["x"], st["y"], r, st["theta"], vicinity, [], cfg, fov=full)
+            if cfg.visual_exclusion:
+                src = base_occlude(src)
+            field = base_fill(src, cfg, fov=full)                                 # :449 (binary part)
+            last = [j for j in vicinity if not (st["x"][j] == st["x"][a2] and st["y"][j] == st["y"][a2])]
+            amp = 1.0
+            if last:
+                amp = 1 - d[last[-1]] / cfg.vision_range                          # leaked loop variable, agent.py:590
+            left = amp * field[0:h].sum() / h
+            right = amp * field[h:].sum() / (R - h)
+            D = np.sign(left - right)
+            if D == 0:
+                D = -1
+            if st["override"][a2] != OV_EXPLOIT:
+                st["theta"][a2] -= D * 0.2                                        # :458-459, not wrapped
+            lo, hi = _np_slice(h - 100, h + 100, R)
+            if amp * field[lo:hi].sum() > 0:                                      # :462-463
+                st["vel"][a2] = 0
+            elif st["override"][a2] != OV_EXPLOIT:
+                st["vel"][a2] = cfg.exp_vel_max
+        for a2 in partners:                                                       # sims.py:759-776
+            e1, e2 = st["override"][a1] == OV_EXPLOIT, st["override"][a2] == OV_EXPLOIT
+            if cfg.teleport_exploit:
+                if not e1:
+                    collided.append(a1)
+                if not e2:
+                    collided.append(a2)
+            elif not ghost_mode:
+                collided += [a1, a2]
+            elif not e1 and not e2:
+                collided += [a1, a2]
+    cset = set(collided)
+    for i in range(N):                                                            # :778-783
+        if i not in cset and st["override"][i] == OV_COLLIDE:
+            st["override"][i] = OV_NONE
+            st["mode"][i] = MODE_EXPLORE
+        if i in cset and st["override"][i] == OV_COLLIDE:
+            notify(st, i, -1)
+    return collided

@@ -177,3 +177,95 @@ def test_full_loop_runs_and_forages(built_lib):
     c = eng.counters()
     assert c["steps"] == 300 and c["launches"] == 600 and c["regeneration_failed"] == 0
     eng.close()
+
+
+@pytest.mark.parametrize("ghost,teleport,vis_excl", [(True, False, False), (False, False, True), (True, True, True)])
+def test_collision_phase_matches_oracle(built_lib, ghost, teleport, vis_excl):
+    """Agent-agent collision avoidance (sims.py:736-783, 421-468) against the oracle restatement
+    (pair detection restates pygame's documented collide_circle: parity unpinned vs the reference;
+    the proximity field is pinned by test_collision_proximity_matches_live_reference)."""
+    from abm_b200 import BaseEngine
+    rng = np.random.default_rng(31 + ghost + 2 * teleport)
+    B, N, W = 4, 40, 200.0
+    cfg = rb.BaseConfig(R=1200, width=W, height=W, visual_exclusion=vis_excl, teleport_exploit=teleport,
+                        exp_vel_max=3.0)
+    eng = BaseEngine(B, N, 0, resolution=1200, width=W, height=W, visual_exclusion=vis_excl,
+                     teleport_exploit=teleport, collide_agents=True, ghost_mode=ghost, tau=cfg.Tau)
+    eng.set_params(exp_vel_max=3.0)
+    states = []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 0, 1, 3], N)
+        st["mode"] = st["override"].copy()
+        states.append(st)
+    S = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    eng.set_agents(x=S["x"], y=S["y"], theta=S["theta"], vel=S["vel"], w=S["w"], u=S["u"], collected=S["collected"],
+                   collected_before=S["collected_before"], env_status=S["env_status"], override_mode=S["override"],
+                   mode=S["mode"], patch_id=S["patch_id"], novelty=S["novelty"])
+    eng.step(1, phases=4)     # collision phase only
+    got = eng.get_agents()
+    n_coll = 0
+    for b in range(B):
+        st = {k: (np.array(v, dtype=float) if k in ("theta", "vel") else np.array(v)) for k, v in states[b].items()}
+        collided = rb.base_collision_phase(st, cfg, ghost_mode=ghost)
+        n_coll += len(set(collided))
+        np.testing.assert_allclose(got["theta"][b], st["theta"], rtol=RTOL, err_msg="theta")
+        np.testing.assert_allclose(got["vel"][b], st["vel"], rtol=RTOL, atol=1e-6, err_msg="vel")
+        assert np.array_equal(got["override_mode"][b], st["override"])
+        assert np.array_equal(got["mode"][b], st["mode"])
+        assert np.array_equal(got["env_status"][b], st["env_status"])
+        assert np.array_equal(got["patch_id"][b], st["patch_id"])
+    assert n_coll > 10
+    eng.close()
+
+
+def test_full_loop_with_collisions(built_lib):
+    """configs[2]-like shape (N=50, 3 patches, occlusion + collisions on) for 200 steps: stays finite,
+    inside the arena, and agents end up less overlapped than without collision avoidance."""
+    from abm_b200 import BaseEngine
+    B, N, P, W = 16, 50, 3, 500.0
+    rng = np.random.default_rng(3)
+    x0, y0 = rng.integers(20, 520, (B, N)), rng.integers(20, 520, (B, N))
+    th0 = rng.uniform(0, 2 * np.pi, (B, N))
+    pa = dict(x=rng.integers(60, 400, (B, P)), y=rng.integers(60, 400, (B, P)), radius=np.full((B, P), 30.0),
+              left=np.full((B, P), 200.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
+    overlaps = {}
+    for collide in (False, True):
+        eng = BaseEngine(B, N, P, resolution=1200, width=W, height=W, visual_exclusion=True, collide_agents=collide,
+                         ghost_mode=False, seed=9)
+        eng.set_params(Eps_w=2.0, Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5,
+                       exp_theta_max=0.5, reloc_theta_max=1.8, exp_stop_ratio=0.175)
+        eng.set_agents(x=x0, y=y0, theta=th0)
+        eng.set_patches(**pa)
+        eng.step(200)
+        a = eng.get_agents()
+        assert np.isfinite(a["x"]).all() and np.isfinite(a["theta"]).all()
+        d = np.sqrt((a["x"][:, :, None] - a["x"][:, None, :]) ** 2 + (a["y"][:, :, None] - a["y"][:, None, :]) ** 2)
+        overlaps[collide] = int(((d < 12.0).sum() - B * N) // 2)
+        assert eng.counters()["launches"] == (600 if collide else 400)
+        eng.close()
+    print("deeply overlapping pairs without / with collision avoidance:", overlaps[False], overlaps[True])
+    assert overlaps[True] <= overlaps[False]
+
+
+def test_function_level_kat_b1(built_lib):
+    """SURVEY App. B KAT-B1 through the function-level drop-ins: Agent.projection_field as
+    abm_b200.supcalc.projection_field, supcalc.F_reloc_LR, vf_supcalc.dPhi_V_of."""
+    from abm_b200 import supcalc, vf_supcalc
+    pos = {0: (250, 250), 1: (400, 200), 2: (330, 230), 3: (250, 60), 4: (250, 150), 5: (60, 301)}
+    social = [pos[1], pos[3], pos[5]]                  # exploiting on another patch
+    occl = [pos[0], pos[2], pos[4]]                    # everyone else in range (self included: skipped)
+    FOV = (-np.pi, np.pi)
+    f = supcalc.projection_field(pos[0], 10, 0.3, 1200, FOV, social)
+    assert rs.runs_of(f > 0) == [(1, 18), (348, 369), (584, 609), (1199, 1200)]
+    np.testing.assert_allclose(supcalc.F_reloc_LR(1.0, f, v_desired=3.0, reloc_theta_max=1.8), (2.0, 0.132), rtol=1e-12)
+    f = supcalc.projection_field(pos[0], 10, 0.3, 1200, FOV, social, non_expl_agents=occl, visual_exclusion=True)
+    assert rs.runs_of(f > 0) == [(1, 18), (584, 588), (1199, 1200)]
+    np.testing.assert_allclose(supcalc.F_reloc_LR(1.0, f, v_desired=3.0, reloc_theta_max=1.8), (2.0, 0.06), rtol=1e-12)
+    # keep_distance_info: amplitude 1 - d_last / vision_range with the LAST obstacle of the list (agent.py:590)
+    f = supcalc.projection_field(pos[0], 10, 0.3, 1200, FOV, social, keep_distance_info=True, vision_range=2000)
+    d_last = np.hypot(60 - 250, 301 - 250)
+    assert np.isclose(f.max(), 1 - d_last / 2000)
+    for v, e in [([1, 1, 1, 0, 0, 0, 0, 0], [1, 0, 0, -1, 0, 0, 0, 0]), ([0, 0, 1, 1, 1, 0, 0, 0], [0, 1, 0, 0, -1, 0, 0, 0]),
+                 ([0, 0, 0, 0, 0, 0, 1, 1], [0, 0, 0, 0, 0, 1, 0, -1])]:
+        assert vf_supcalc.dPhi_V_of(np.zeros(8), np.array(v, float)).tolist() == e

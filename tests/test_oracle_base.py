@@ -99,3 +99,39 @@ def test_patch_phase_pieces_match_live_reference():
         assert st["env_status"][i] == a.env_status and st["patch_id"][i] == a.exploited_patch_id
         assert np.array_equal(st["novelty"][i], a.novelty)
         assert np.isclose(st["collected"][i], a.collected_r)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("ghost,vis_excl", [(True, False), (False, True)])
+def test_collision_proximity_matches_live_reference(ghost, vis_excl):
+    """The part of the collision phase that IS reference code -- agent_agent_collision_proximity
+    (sims.py:421-468), which builds the LIDAR field with Agent.projection_field -- driven with the
+    partner lists of the restatement.  (The pair detection itself is pygame's: unpinned.)"""
+    ref_shim.install()
+    import types
+    from abm.simulation import sims
+    rng = np.random.default_rng(21 + ghost)
+    N = 26
+    cfg = rb.BaseConfig(R=1200, width=160, height=160, visual_exclusion=vis_excl, exp_vel_max=3.0, vision_range=2000)
+    ov = rng.choice([0, 0, 1], N)
+    st = dict(x=rng.integers(30, 160, N).astype(float), y=rng.integers(30, 160, N).astype(float),
+              theta=rng.uniform(0, 2 * np.pi, N), vel=rng.uniform(0, 3, N), radius=10.0, w=np.zeros(N), u=np.zeros(N),
+              novelty=np.zeros((N, 10)), env_status=np.zeros(N, int), override=ov, mode=ov.copy(),
+              patch_id=np.full(N, -1), collected=np.zeros(N), collected_before=np.zeros(N))
+    agents = ref_shim.make_base_agents(st, cfg)
+    dummy = types.SimpleNamespace(ghost_mode=ghost, agents=agents)
+    ix, iy = np.trunc(st["x"]), np.trunc(st["y"])
+    n_pairs = 0
+    for a1 in range(N):
+        partners = [a2 for a2 in range(N) if a2 != a1 and (ix[a1] - ix[a2]) ** 2 + (iy[a1] - iy[a2]) ** 2 <= 24 ** 2]
+        if partners:
+            sims.Simulation.agent_agent_collision_proximity(dummy, agents[a1], [agents[j] for j in partners])
+            n_pairs += len(partners)
+    assert n_pairs > 10
+    rb.base_collision_phase(st, cfg, ghost_mode=ghost)
+    for i, a in enumerate(agents):
+        assert np.isclose(st["theta"][i], a.orientation, rtol=1e-13), i
+        assert np.isclose(st["vel"][i], a.velocity, rtol=1e-13), i
+        # the restatement also ran the post-loop bookkeeping of sims.py:778-783: compare before it
+        if a.overriding_mode == "exploit":
+            assert st["override"][i] == rb.OV_EXPLOIT
