@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -108,6 +109,7 @@ struct abm_engine {
   float r_min = 0.f, r_max = 0.f;
   bool state_set = false;
   unsigned long long launches = 0;
+  size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
 };
 
 namespace {
@@ -168,6 +170,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   e->device = device;
   e->tile_begin = tb;
   e->tile_count = tc;
+  e->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   build_grid(cfg->resolution, e->grid);
   const size_t smem = abm::vf_step_smem_bytes(abm::vf_step_threads(tc), e->grid.W);
   if (smem > (size_t)prop.sharedMemPerBlockOptin) {
@@ -316,6 +319,17 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.inv_step = g.inv_step; a.t_half = g.t_half(); a.k_bias = g.k_bias(); a.y_scale = g.y_scale;
   a.thr_k = g.thr_k(exact); a.thr_h0 = g.thr_h0(exact); a.thr_h1 = g.thr_h1(exact); a.ca_guard = g.ca_guard;
   a.fov0p = e->cfg.fov_px0 + 33; a.span = (unsigned)(e->cfg.fov_px1 - e->cfg.fov_px0 - 1);
+  {
+    static const double kAtan[7] = {0.9999993443489075, -0.33326515555381775, 0.19881492853164673,
+                                    -0.13487225770950317, 0.0838717594742775, -0.037013452500104904,
+                                    0.007863515056669712};   // same polynomial as atan_unit()
+    const double inv = (double)g.inv_step;
+    for (int c = 0; c < 7; ++c) a.ac[c] = (float)(kAtan[c] * inv);
+    a.half_pi_b = (float)(0.5 * ABM_PI_D * inv); a.pi_b = (float)(ABM_PI_D * inv);
+    a.seam_b = (float)((double)g.ca_guard * inv);
+    a.nthr_h1 = -a.thr_h1;
+    a.full_fov = (e->cfg.fov_px0 == 0 && e->cfg.fov_px1 == g.R - 1) ? 1 : 0;
+  }
   a.width = e->cfg.width; a.height = e->cfg.height;
   a.half_w = 0.5f * e->cfg.width; a.half_h = 0.5f * e->cfg.height;
   a.cull_scale = g.cull_scale;
@@ -343,10 +357,16 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   // half width drops to 0 (r / tan(2pi/R)); expected visible fraction ~ pi * d_cull^2 / arena area.
   const double d_cull = (double)e->r_max * std::sqrt((double)g.cull_scale);
   const bool cull = ABM_PI_D * d_cull * d_cull < 0.5 * (double)e->cfg.width * (double)e->cfg.height;
+  // kernel choice: the one-thread-per-focal-agent kernel; ABM_VF_KERNEL=symmetric selects the experimental kernel
+  // that evaluates every unordered pair once (abm_vf_sym.cu; measured slower in round 1)
+  const char* force = getenv("ABM_VF_KERNEL");
+  const bool use_sym = (force && strcmp(force, "symmetric") == 0) &&
+                       abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
   for (int s = 0; s < n_steps; ++s) {
     a.rec_in = e->rec[e->cur].p;
     a.rec_out = e->rec[e->cur ^ 1].p;
-    abm::launch_vf_step(a, uniform_r, cull, st);
+    if (use_sym) abm::launch_vf_step_sym(a, st);
+    else abm::launch_vf_step(a, uniform_r, cull, st);
     e->cur ^= 1;
     ++e->launches;
   }

@@ -37,6 +37,13 @@ struct VFKernelArgs {
   int k_bias;                     // k_off - 0x4B400000 + 32
   float y_scale;                  // R / 2pi  (proj_size / 2 = atan(r/d) * y_scale)
   float thr_k, thr_h0, thr_h1, ca_guard;
+  // the same constants pre-scaled to bins so that every hot-loop instruction needs at most ONE
+  // run-time constant (read straight from the constant bank, no registers, no LDC)
+  float ac[7];                    // atan polynomial coefficients * inv_step (ascending powers of z)
+  float half_pi_b, pi_b;          // pi/2 * inv_step, pi * inv_step
+  float seam_b;                   // ca_guard * inv_step
+  float nthr_h1;                  // -thr_h1
+  int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible
   int fov0p;                      // fov_px0 + 33: first visible padded position
   unsigned span;                  // fov_px1 - fov_px0 - 1: number of visible positions
   float width, height, half_w, half_h;
@@ -63,6 +70,9 @@ struct VFKernelArgs {
 
 void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream);
 size_t vf_step_smem_bytes(int threads, int W);
+// symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
+bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
+void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
 int vf_step_threads(int tile_count);
 
 struct VFProjArgs {

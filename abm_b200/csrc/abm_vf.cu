@@ -47,6 +47,22 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                : "memory");
 }
 
+// explicit shared-space accesses with 32-bit addresses: keeps the generic->shared window arithmetic
+// (S2UR SR_CgaCtaId / ULEA per access) out of the pair loop
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+
 size_t vf_step_smem_bytes(int threads, int W) {
   return 2 * sizeof(float4) * kRecTile            // record stages
          + sizeof(uint32_t) * (size_t)(W + 2) * threads   // padded rows
@@ -82,11 +98,32 @@ static __device__ __noinline__ void vf_draw_general(const VFKernelArgs& a, uint3
   vf_draw<false>(myrow, stride, a.R, a.fov_px0, a.fov_px1, k, h);
 }
 
+// Pair-loop constants that depend only on the resolution R.  RC > 0: compile-time resolution (they become
+// instruction immediates); RC == 0: read from the kernel arguments (constant bank).
+template <int RC>
+struct PairK {
+  static constexpr double kInv = RC > 1 ? (double)(RC - 1) / ABM_TWO_PI_D : 0.0;   // (R - 1) / 2pi
+  static constexpr float kTHalf = (RC % 2 == 0) ? 0.5f : 1.0f;
+  __device__ __forceinline__ static float ac(const VFKernelArgs& a, int c) {
+    constexpr double kA[7] = {0.9999993443489075, -0.33326515555381775, 0.19881492853164673, -0.13487225770950317,
+                              0.0838717594742775, -0.037013452500104904, 0.007863515056669712};
+    return RC ? (float)(kA[c] * kInv) : a.ac[c];
+  }
+  __device__ __forceinline__ static float half_pi_b(const VFKernelArgs& a) { return RC ? (float)(0.5 * ABM_PI_D * kInv) : a.half_pi_b; }
+  __device__ __forceinline__ static float pi_b(const VFKernelArgs& a) { return RC ? (float)(ABM_PI_D * kInv) : a.pi_b; }
+  __device__ __forceinline__ static float t_half(const VFKernelArgs& a) { return RC ? kTHalf : a.t_half; }
+  __device__ __forceinline__ static int k_bias(const VFKernelArgs& a) {
+    return RC ? ((RC % 2 == 0 ? RC / 2 - 1 : (RC - 3) / 2) - 0x4B400000 + 32) : a.k_bias;
+  }
+  __device__ __forceinline__ static float y_scale(const VFKernelArgs& a) { return RC ? (float)((double)RC / ABM_TWO_PI_D) : a.y_scale; }
+};
+
 // TORUS: BOUNDARY == infinite.  UNIFORM_R: all radii equal (centre difference == position
 // difference).  CULL: skip pairs beyond the distance at which the half width becomes 0.
-template <bool TORUS, bool UNIFORM_R, bool CULL>
+template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>
 __global__ void __launch_bounds__(kMaxThreads, 3)
 vf_step_kernel(const VFKernelArgs a) {
+  using K = PairK<RC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* recs = reinterpret_cast<float4*>(smem_raw);                       // [2][kRecTile]
   uint32_t* rows = reinterpret_cast<uint32_t*>(recs + 2 * kRecTile);        // [W + 2][T], padded (vf_draw_fast)
@@ -132,12 +169,12 @@ vf_step_kernel(const VFKernelArgs a) {
     sincos((double)th, &sd, &cd);
     c = (float)cd; ns = (float)(-sd);
   }
-  const BinConsts bc{a.inv_step, a.t_half, a.k_bias, a.y_scale, a.thr_k, a.thr_h0, a.thr_h1, a.ca_guard};
   uint32_t* padrow = rows + tid;        // padded word 0 (virtual bins [-32, 0))
   uint32_t* myrow = rows + T + tid;     // real word 0
-  const int R = a.R;
+  const int R = RC ? RC : a.R;
   unsigned char* padrow_b = reinterpret_cast<unsigned char*>(padrow);
   const int stride_b = 4 * T;
+  const uint32_t row_a = smem_u32(padrow);   // shared-space address of padded word 0
   const int fov0p = a.fov0p;           // first visible padded position
   const unsigned span = a.span;        // number of visible positions (vf_supcalc.py:119)
   const float width = a.width, height = a.height, half_w = a.half_w, half_h = a.half_h;
@@ -155,10 +192,10 @@ vf_step_kernel(const VFKernelArgs a) {
     const float4* tile_recs = recs + (st & 1) * kRecTile;
     const int nj = min(kRecTile, a.N - st * kRecTile);
     if (active) {
-      const float4* rend = tile_recs + nj;
+      const uint32_t rec0 = smem_u32(tile_recs), rec_end = rec0 + 16u * (uint32_t)nj;
 #pragma unroll 2
-      for (const float4* rp = tile_recs; rp < rend; ++rp) {
-        const float4 o = *rp;                                // broadcast LDS.128
+      for (uint32_t ra = rec0; ra < rec_end; ra += 16u) {
+        const float4 o = lds_f4(ra);                         // broadcast LDS.128
         float dx, dy;
         if (UNIFORM_R) {
           dx = o.x - me.x; dy = o.y - me.y;
@@ -173,25 +210,60 @@ vf_step_kernel(const VFKernelArgs a) {
         const float d2 = fmaf(dx, dx, dy * dy);
         if (CULL) { if (d2 > o.w) continue; }                // o.w: beyond it the half width is 0
         if (!UNIFORM_R) { if ((o.x == me.x) & (o.y == me.y)) continue; }   // vf_supcalc.py:57
-        const PairFast pf = vf_pair_fast(dx, dy, d2, o.z, c, ns, bc);
-        const int ps = pf.k - pf.h, pe = pf.k + pf.h;        // padded positions
-        const bool vis = ((unsigned)(ps - fov0p) < span) | ((unsigned)(pe - fov0p) < span);   // vf_supcalc.py:119
-        if (!pf.flagged & vis & ((unsigned)(pf.h - 1) < 16u)) {
-          vf_draw_short(padrow_b, stride_b, ps, pf.h);
-        } else if (pf.flagged) {
+        // ---- closed angle in BINS: rotate (dx, -dy) by -theta, octant-reduced polynomial atan2 whose
+        //      coefficients carry the 1/step factor (vf_supcalc.py:86, :102) ----
+        const float u = fmaf(dx, c, dy * ns);
+        const float w = fmaf(dx, ns, -(dy * c));
+        const float au = fabsf(u), aw = fabsf(w);
+        const float tq = fminf(au, aw) * rcp_approx(fmaxf(au, aw));
+        const float z = tq * tq;
+        float p = fmaf(K::ac(a, 6), z, K::ac(a, 5));
+        p = fmaf(p, z, K::ac(a, 4));
+        p = fmaf(p, z, K::ac(a, 3));
+        p = fmaf(p, z, K::ac(a, 2));
+        p = fmaf(p, z, K::ac(a, 1));
+        p = fmaf(p, z, K::ac(a, 0));
+        p *= tq;
+        if (aw > au) p = K::half_pi_b(a) - p;
+        if (u < 0.0f) p = K::pi_b(a) - p;
+        const float cab = copysignf(p, w);
+        const float MAGIC = 12582912.0f;                     // 1.5 * 2^23
+        const float tk = cab + K::t_half(a);
+        const float tr = tk + MAGIC;                         // rint(tk) in the low mantissa bits
+        const int k = __float_as_int(tr) + K::k_bias(a);     // centre bin, padded position
+        const float dfk = tk - (tr - MAGIC);
+        bool flagged = (fabsf(dfk) > a.thr_k) | (fabsf(cab) > a.seam_b);
+        // ---- half width h = floor(atan(r / d) * R / 2pi) (vf_supcalc.py:96-99, :114-117) ----
+        const float q = o.z * rsqrt_approx(d2);
+        flagged |= !(q <= 1.0f);                             // also d2 == 0 (inf / NaN)
+        const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
+        const float yr = y + MAGIC;
+        const int h = __float_as_int(yr) - 0x4B400000;
+        flagged |= fmaf(y, a.nthr_h1, fabsf(y - (yr - MAGIC))) > a.thr_h0;
+        const int ps = k - h, pe = k + h;
+        const bool vis = FULL_FOV ? true : (((unsigned)(ps - fov0p) < span) | ((unsigned)(pe - fov0p) < span));
+        if (!flagged & vis & ((unsigned)(h - 1) < 16u)) {
+          // interval of <= 32 bins: at most two words of the private row (bank == lane)
+          const uint32_t t = 0xffffffffu >> (32 - 2 * h);
+          const uint32_t wa = row_a + (uint32_t)(ps >> 5) * (uint32_t)stride_b;
+          const uint32_t lo = __funnelshift_l(0u, t, ps);
+          const uint32_t hi = __funnelshift_l(t, 0u, ps);
+          sts_u32(wa, lds_u32(wa) | lo);
+          if (hi) sts_u32(wa + stride_b, lds_u32(wa + stride_b) | hi);
+        } else if (flagged) {
           // deferred to fp64 (self / exactly coincident positions are skipped: vf_supcalc.py:57)
           if (!((o.x == me.x) & (o.y == me.y))) {
             const int slot = atomicAdd(qcount, 1);           // keeps counting past the capacity
             if (slot < kQueueCap) {
-              queue[2 * slot] = ((uint32_t)tid << 24) | (uint32_t)(st * kRecTile + (int)(rp - tile_recs));
-              queue[2 * slot + 1] = ((uint32_t)(pf.k - 32) << 16) | ((uint32_t)pf.h & 0xffffu);
+              queue[2 * slot] = ((uint32_t)tid << 24) | (uint32_t)(st * kRecTile + (int)((ra - rec0) >> 4));
+              queue[2 * slot + 1] = ((uint32_t)(k - 32) << 16) | ((uint32_t)h & 0xffffu);
             } else {
-              vf_exact_inline(a, myrow, T, me, (size_t)b * a.N + i, o, pf.k - 32, pf.h);
+              vf_exact_inline(a, myrow, T, me, (size_t)b * a.N + i, o, k - 32, h);
             }
           }
-        } else if (vis & (pf.h > 16)) {
+        } else if (vis & (h > 16)) {
           if ((ps >= 0) & (pe <= R + 62)) vf_draw_wide(padrow_b, stride_b, ps, pe);
-          else vf_draw_general(a, myrow, T, pf.k - 32, pf.h);
+          else vf_draw_general(a, myrow, T, k - 32, h);
         }
       }
     }
@@ -220,58 +292,27 @@ vf_step_kernel(const VFKernelArgs a) {
   }
 
   if (!active) return;
-  vf_fold_padding(padrow, T, a.R, a.W);
-
-  // ---- epilogue: edges, integrals, kinematics (fp64) ----
-  const size_t gi = (size_t)b * a.N + i;
-  const VFParams6 prm = *reinterpret_cast<const VFParams6*>(a.params + (size_t)b * a.param_stride);
-  double A0 = prm.alp0, B0 = prm.bet0, V0 = prm.v0;            // vf_supcalc.py:191-196
-  if (a.ov_alp0) { const float v = a.ov_alp0[gi]; if (v == v) A0 = v; }
-  if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
-  if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
-  const double vel0 = a.vel[gi];
-  FlockTerms ft;
-  if (a.phi_ok) {
-    ft = vf_flock_terms(myrow, T, a.R, a.W, a.lut, a.dphi, vel0, prm, A0, B0, V0);
-  } else {   // len(PHI) != len(soc_v_field): the reference skips the calculation (vf_agent.py:282-284)
-    ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
-  }
-  double dpsi = ft.dpsi, dvel = ft.dvel;
-  if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
-  double nth = wrap_heading_once((double)th + dpsi);            // :295-296
-  double nv = vel0 + dvel;                                      // :298
-  if (a.limit_movement) nv = limit_abs(nv, a.max_vel);          // :299-300
-  double sn, cn;
-  sincos(nth, &sn, &cn);
-  double nx = (double)me.x + nv * cn;                           // :303-306
-  double ny = (double)me.y - nv * sn;
-  if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
-  else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
-
-  a.rec_out[gi] = make_float4((float)nx, (float)ny, me.z, me.w);
-  a.theta[gi] = (float)nth;
-  a.vel[gi] = (float)nv;
-
-  const size_t oi = (size_t)b * a.tile_count + li;
-  if (a.terms_out) {
-    double* t = a.terms_out + oi * 6;
-    t[0] = ft.dvel; t[1] = ft.dpsi; t[2] = ft.a_blob; t[3] = ft.a_edge; t[4] = ft.b_blob; t[5] = ft.b_edge;
-  }
-  if (a.fields_out) {
-    uint32_t* out = a.fields_out + oi * a.W;
-    for (int ws = 0; ws < a.W; ++ws) out[ws] = flipped_word(myrow, T, a.R, a.W, ws);
-  }
+  vf_agent_epilogue<TORUS>(a, b, i, li, padrow, T, me, th);
 }
 
-template <bool TORUS, bool UNIFORM_R, bool CULL>
+template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>
 static void launch_variant(const VFKernelArgs& a, unsigned grid, int T, size_t smem, cudaStream_t stream) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(vf_step_kernel<TORUS, UNIFORM_R, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
+    cudaFuncSetAttribute(vf_step_kernel<TORUS, UNIFORM_R, CULL, FULL_FOV, RC>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  vf_step_kernel<TORUS, UNIFORM_R, CULL><<<grid, T, smem, stream>>>(a);
+  vf_step_kernel<TORUS, UNIFORM_R, CULL, FULL_FOV, RC><<<grid, T, smem, stream>>>(a);
+}
+
+// R = 1200 (the resolution of 99 of the reference's 108 experiment files) with full FOV gets a
+// kernel with compile-time bin constants; everything else runs the run-time-R variants.
+template <bool TORUS, bool UNIFORM_R, bool CULL>
+static void launch_fov(const VFKernelArgs& a, unsigned grid, int T, size_t smem, cudaStream_t stream) {
+  if (a.full_fov && a.R == 1200) launch_variant<TORUS, UNIFORM_R, CULL, true, 1200>(a, grid, T, smem, stream);
+  else if (a.full_fov) launch_variant<TORUS, UNIFORM_R, CULL, true, 0>(a, grid, T, smem, stream);
+  else launch_variant<TORUS, UNIFORM_R, CULL, false, 0>(a, grid, T, smem, stream);
 }
 
 void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream) {
@@ -281,14 +322,14 @@ void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream
   const unsigned grid = (unsigned)((size_t)a.B * tiles_per_rep);
   const int v = (a.boundary == 1 ? 4 : 0) | (uniform_r ? 2 : 0) | (cull ? 1 : 0);
   switch (v) {
-    case 0: launch_variant<false, false, false>(a, grid, T, smem, stream); break;
-    case 1: launch_variant<false, false, true>(a, grid, T, smem, stream); break;
-    case 2: launch_variant<false, true, false>(a, grid, T, smem, stream); break;
-    case 3: launch_variant<false, true, true>(a, grid, T, smem, stream); break;
-    case 4: launch_variant<true, false, false>(a, grid, T, smem, stream); break;
-    case 5: launch_variant<true, false, true>(a, grid, T, smem, stream); break;
-    case 6: launch_variant<true, true, false>(a, grid, T, smem, stream); break;
-    default: launch_variant<true, true, true>(a, grid, T, smem, stream); break;
+    case 0: launch_fov<false, false, false>(a, grid, T, smem, stream); break;
+    case 1: launch_fov<false, false, true>(a, grid, T, smem, stream); break;
+    case 2: launch_fov<false, true, false>(a, grid, T, smem, stream); break;
+    case 3: launch_fov<false, true, true>(a, grid, T, smem, stream); break;
+    case 4: launch_fov<true, false, false>(a, grid, T, smem, stream); break;
+    case 5: launch_fov<true, false, true>(a, grid, T, smem, stream); break;
+    case 6: launch_fov<true, true, false>(a, grid, T, smem, stream); break;
+    default: launch_fov<true, true, true>(a, grid, T, smem, stream); break;
   }
 }
 

@@ -401,4 +401,53 @@ __device__ __forceinline__ uint32_t flipped_word(const uint32_t* f, int stride, 
   return out;
 }
 
+// Per-agent epilogue shared by the step kernels: fold the row padding, edges + flocking
+// integrals, heading / speed / position update, walls or torus, outputs.
+// b: replicate, i: agent index in the replicate, li: index in this engine's tile,
+// padrow: padded word 0 of the agent's row (stride in words), me: (x, y, radius, cull^2).
+template <bool TORUS>
+__device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, int i, int li, uint32_t* padrow,
+                                                  int stride, float4 me, float th) {
+  vf_fold_padding(padrow, stride, a.R, a.W);
+  uint32_t* myrow = padrow + stride;   // real word 0
+  const size_t gi = (size_t)b * a.N + i;
+  const VFParams6 prm = *reinterpret_cast<const VFParams6*>(a.params + (size_t)b * a.param_stride);
+  double A0 = prm.alp0, B0 = prm.bet0, V0 = prm.v0;            // vf_supcalc.py:191-196
+  if (a.ov_alp0) { const float v = a.ov_alp0[gi]; if (v == v) A0 = v; }
+  if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
+  if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
+  const double vel0 = a.vel[gi];
+  FlockTerms ft;
+  if (a.phi_ok) {
+    ft = vf_flock_terms(myrow, stride, a.R, a.W, a.lut, a.dphi, vel0, prm, A0, B0, V0);
+  } else {   // len(PHI) != len(soc_v_field): the reference skips the calculation (vf_agent.py:282-284)
+    ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
+  }
+  double dpsi = ft.dpsi, dvel = ft.dvel;
+  if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
+  double nth = wrap_heading_once((double)th + dpsi);            // :295-296
+  double nv = vel0 + dvel;                                      // :298
+  if (a.limit_movement) nv = limit_abs(nv, a.max_vel);          // :299-300
+  double sn, cn;
+  sincos(nth, &sn, &cn);
+  double nx = (double)me.x + nv * cn;                           // :303-306
+  double ny = (double)me.y - nv * sn;
+  if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
+  else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
+
+  a.rec_out[gi] = make_float4((float)nx, (float)ny, me.z, me.w);
+  a.theta[gi] = (float)nth;
+  a.vel[gi] = (float)nv;
+
+  const size_t oi = (size_t)b * a.tile_count + li;
+  if (a.terms_out) {
+    double* t = a.terms_out + oi * 6;
+    t[0] = ft.dvel; t[1] = ft.dpsi; t[2] = ft.a_blob; t[3] = ft.a_edge; t[4] = ft.b_blob; t[5] = ft.b_edge;
+  }
+  if (a.fields_out) {
+    uint32_t* out = a.fields_out + oi * a.W;
+    for (int ws = 0; ws < a.W; ++ws) out[ws] = flipped_word(myrow, stride, a.R, a.W, ws);
+  }
+}
+
 }  // namespace abm
