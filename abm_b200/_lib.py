@@ -17,6 +17,7 @@ BOUNDARY_INFINITE = 1
 VF_EXACT_FIXUP = 1 << 0
 VF_KEEP_FIELDS = 1 << 1
 VF_KEEP_TERMS = 1 << 2
+VF_SPATIAL_SORT = 1 << 3
 VF_NPARAM = 6
 
 
@@ -34,7 +35,7 @@ class VFConfig(C.Structure):
         ("boundary", C.c_int32), ("limit_movement", C.c_int32),
         ("width", C.c_float), ("height", C.c_float), ("window_pad", C.c_float),
         ("max_vel", C.c_float), ("max_th", C.c_float), ("flags", C.c_uint32),
-        ("tile_begin", C.c_int32), ("tile_count", C.c_int32),
+        ("tile_begin", C.c_int32), ("tile_count", C.c_int32), ("resort_every", C.c_int32),
     ]
 
 
@@ -116,6 +117,9 @@ SYMBOLS = {
     "abm_vf_get_terms": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "abm_vf_record_table": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
+    "abm_vf_get_permutation": (C.c_int, [_P, _P, C.c_int, _P]),
+    "abm_vf_resort": (C.c_int, [_P, _P]),
+    "abm_vf_internal_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "abm_synchronize": (C.c_int, [_P, _P]),
     "abm_vf_projection_field": (C.c_int, [C.POINTER(VFProjArgs), _P]),
     "abm_vf_flocking_terms": (C.c_int, [_P, C.c_int, C.c_double, _P, C.POINTER(C.c_double)]),

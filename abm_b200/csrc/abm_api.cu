@@ -3,6 +3,7 @@
 // every entry point fails with ABM_E_NO_DEVICE / ABM_E_CUDA.
 #include "../../include/abm_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -110,6 +111,15 @@ struct abm_engine {
   bool state_set = false;
   unsigned long long launches = 0;
   size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  // spatial ordering (ABM_VF_SPATIAL_SORT)
+  bool sort_enabled = false, needs_sort = false, perm_identity = true;
+  int steps_since_sort = 0;
+  DevBuf<int> perm, perm_tmp, order, vals_in, offsets;
+  DevBuf<uint32_t> keys_in, keys_out;
+  DevBuf<unsigned char> sort_temp;
+  size_t sort_temp_bytes = 0;
+  DevBuf<float4> tile_bbox;   // culling by record tiles (CULL variants on sorted state)
+  DevBuf<float> tile_cull2;
 };
 
 namespace {
@@ -120,6 +130,30 @@ int copy_in(void* dst, const void* src, size_t bytes, int on_device, cudaStream_
 }
 int copy_out(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
   ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  return ABM_OK;
+}
+
+// Re-sort the internal order of every replicate by the Morton code of the current positions.
+int resort_engine(abm_engine* e, cudaStream_t st) {
+  const int B = e->cfg.n_replicates, N = e->cfg.n_agents;
+  const long long n = (long long)e->n_total;
+  const float extent = std::max(e->cfg.width, e->cfg.height) + 2.0f * e->cfg.window_pad;
+  ABM_CUDA(abm::vf_sort_order(e->rec[e->cur].p, B, N, 0.0f, 0.0f, extent, e->sort_temp.p, e->sort_temp_bytes, e->keys_in.p,
+                              e->keys_out.p, e->vals_in.p, e->order.p, e->offsets.p, st));
+  abm::launch_gather_f4(e->rec[e->cur].p, e->order.p, e->rec[e->cur ^ 1].p, N, n, st);
+  e->cur ^= 1;
+  abm::launch_gather_f32(e->theta.p, e->order.p, e->stage_x.p, N, n, st); std::swap(e->theta.p, e->stage_x.p);
+  abm::launch_gather_f32(e->vel.p, e->order.p, e->stage_x.p, N, n, st);   std::swap(e->vel.p, e->stage_x.p);
+  abm::launch_gather_i32(e->perm.p, e->order.p, e->perm_tmp.p, N, n, st); std::swap(e->perm.p, e->perm_tmp.p);
+  for (DevBuf<float>* ov : {&e->ov_alp0, &e->ov_bet0, &e->ov_v0}) {
+    if (!ov->p) continue;
+    abm::launch_gather_f32(ov->p, e->order.p, e->stage_x.p, N, n, st);
+    std::swap(ov->p, e->stage_x.p);
+  }
+  ABM_CUDA(cudaGetLastError());
+  e->needs_sort = false;
+  e->perm_identity = false;
+  e->steps_since_sort = 0;
   return ABM_OK;
 }
 
@@ -192,6 +226,16 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   A(e->lut.alloc(e->grid.lut.size()));
   A(e->counters.alloc(4));
   A(e->radius_minmax.alloc(2));
+  e->sort_enabled = (cfg->flags & ABM_VF_SPATIAL_SORT) != 0 && cfg->n_agents >= 64;
+  if (e->sort_enabled) {
+    A(e->perm.alloc(e->n_total)); A(e->perm_tmp.alloc(e->n_total)); A(e->order.alloc(e->n_total));
+    A(e->vals_in.alloc(e->n_total)); A(e->offsets.alloc((size_t)cfg->n_replicates + 1));
+    A(e->keys_in.alloc(e->n_total)); A(e->keys_out.alloc(e->n_total));
+    e->sort_temp_bytes = abm::vf_sort_temp_bytes(cfg->n_replicates, cfg->n_agents);
+    A(e->sort_temp.alloc(e->sort_temp_bytes + 16));
+    const size_t nt = (size_t)cfg->n_replicates * ((cfg->n_agents + abm::kRecTile - 1) / abm::kRecTile);
+    A(e->tile_bbox.alloc(nt)); A(e->tile_cull2.alloc(nt));
+  }
   if (cfg->flags & ABM_VF_KEEP_FIELDS) A(e->fields.alloc(e->n_tile * e->grid.W));
   if (cfg->flags & ABM_VF_KEEP_TERMS) A(e->terms.alloc(e->n_tile * 6));
   if (err == cudaSuccess) err = cudaMemcpy(e->lut.p, e->grid.lut.data(), sizeof(abm::PhiLut) * e->grid.lut.size(),
@@ -219,6 +263,8 @@ int abm_destroy(abm_engine_t* e) {
   e->stage_x.release(); e->stage_y.release(); e->stage_r.release();
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
+  e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
+  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release();
   e->radius_minmax.release();
   delete e;
   return ABM_OK;
@@ -246,6 +292,10 @@ int abm_vf_set_agent_overrides(abm_engine_t* e, const float* alp0, const float* 
     if (!it.buf->p) ABM_CUDA(it.buf->alloc(e->n_total));
     int rc = copy_in(it.buf->p, it.src, sizeof(float) * e->n_total, on_device, st);
     if (rc) return rc;
+    if (e->sort_enabled && !e->perm_identity) {   // caller's order -> internal order
+      abm::launch_gather_f32(it.buf->p, e->perm.p, e->stage_x.p, e->cfg.n_agents, (long long)e->n_total, st);
+      std::swap(it.buf->p, e->stage_x.p);
+    }
     *it.has = true;
   }
   return ABM_OK;
@@ -257,23 +307,42 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
   ABM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = sizeof(float) * e->n_total;
-  const float *dx = x, *dy = y, *dr = radius;
+  const long long n = (long long)e->n_total;
+  const int N = e->cfg.n_agents;
+  // An existing spatial order is kept (positions of consecutive calls are usually close): the new state is
+  // gathered into the current internal order and re-sorted on the usual schedule.
+  const bool permuted = e->sort_enabled && !e->perm_identity;
+  const float *dx = x, *dy = y, *dr = radius, *dth = theta, *dv = vel;
+  int rc;
   if (!on_device) {
-    int rc;
     if ((rc = copy_in(e->stage_x.p, x, bytes, 0, st))) return rc;
     if ((rc = copy_in(e->stage_y.p, y, bytes, 0, st))) return rc;
     if ((rc = copy_in(e->stage_r.p, radius, bytes, 0, st))) return rc;
     dx = e->stage_x.p; dy = e->stage_y.p; dr = e->stage_r.p;
   }
-  int rc;
-  if ((rc = copy_in(e->theta.p, theta, bytes, on_device, st))) return rc;
-  if ((rc = copy_in(e->vel.p, vel, bytes, on_device, st))) return rc;
   const unsigned init_mm[2] = {0x7f800000u, 0u};
   ABM_CUDA(cudaMemcpyAsync(e->radius_minmax.p, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
-  abm::launch_pack_records(dx, dy, dr, e->grid.cull_scale, e->rec[e->cur].p, e->radius_minmax.p,
-                           (long long)e->n_total, st);
+  abm::launch_pack_records(dx, dy, dr, permuted ? e->perm.p : nullptr, N, e->grid.cull_scale, e->rec[e->cur].p,
+                           e->radius_minmax.p, n, st);
+  if (!permuted) {
+    if ((rc = copy_in(e->theta.p, theta, bytes, on_device, st))) return rc;
+    if ((rc = copy_in(e->vel.p, vel, bytes, on_device, st))) return rc;
+  } else {
+    if (!on_device) {   // the x / y stages are free again once the pack kernel has run (stream order)
+      if ((rc = copy_in(e->stage_x.p, theta, bytes, 0, st))) return rc;
+      if ((rc = copy_in(e->stage_y.p, vel, bytes, 0, st))) return rc;
+      dth = e->stage_x.p; dv = e->stage_y.p;
+    }
+    abm::launch_gather_f32(dth, e->perm.p, e->theta.p, N, n, st);
+    abm::launch_gather_f32(dv, e->perm.p, e->vel.p, N, n, st);
+  }
   ABM_CUDA(cudaGetLastError());
   e->radius_known = false;
+  if (e->sort_enabled && !e->state_set) {
+    abm::launch_iota(e->perm.p, N, n, st);
+    e->perm_identity = true;
+    e->needs_sort = true;
+  }
   e->state_set = true;
   return ABM_OK;
 }
@@ -288,15 +357,28 @@ int abm_get_state(abm_engine_t* e, float* x, float* y, float* theta, float* vel,
   if (x || y) {
     float* tx = on_device ? x : e->stage_x.p;
     float* ty = on_device ? y : e->stage_y.p;
-    abm::launch_unpack_records(e->rec[e->cur].p, x ? tx : nullptr, y ? ty : nullptr, (long long)e->n_total, st);
+    abm::launch_unpack_records(e->rec[e->cur].p, (e->sort_enabled && !e->perm_identity) ? e->perm.p : nullptr,
+                               e->cfg.n_agents, x ? tx : nullptr, y ? ty : nullptr, (long long)e->n_total, st);
     ABM_CUDA(cudaGetLastError());
     if (!on_device) {
       if (x && (rc = copy_out(x, tx, bytes, 0, st))) return rc;
       if (y && (rc = copy_out(y, ty, bytes, 0, st))) return rc;
     }
   }
-  if (theta && (rc = copy_out(theta, e->theta.p, bytes, on_device, st))) return rc;
-  if (vel && (rc = copy_out(vel, e->vel.p, bytes, on_device, st))) return rc;
+  const bool permuted = e->sort_enabled && !e->perm_identity;
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which ? vel : theta;
+    const float* src = which ? e->vel.p : e->theta.p;
+    if (!dst) continue;
+    if (permuted) {   // internal order -> caller's order
+      float* tmp = on_device ? dst : e->stage_r.p;
+      abm::launch_scatter_f32(src, e->perm.p, tmp, e->cfg.n_agents, (long long)e->n_total, st);
+      if (!on_device && (rc = copy_out(dst, tmp, bytes, 0, st))) return rc;
+      if (!on_device) ABM_CUDA(cudaStreamSynchronize(st));   // stage_r is reused for the next array
+    } else if ((rc = copy_out(dst, src, bytes, on_device, st))) {
+      return rc;
+    }
+  }
   if (!on_device) ABM_CUDA(cudaStreamSynchronize(st));
   return ABM_OK;
 }
@@ -362,9 +444,27 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   const char* force = getenv("ABM_VF_KERNEL");
   const bool use_sym = (force && strcmp(force, "symmetric") == 0) &&
                        abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
+  const bool tiled = e->tile_count != e->cfg.n_agents;
   for (int s = 0; s < n_steps; ++s) {
+    if (e->sort_enabled && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
+                                               e->steps_since_sort >= e->cfg.resort_every))) {
+      int rc = resort_engine(e, st);
+      if (rc) return rc;
+    }
+    ++e->steps_since_sort;
+    a.theta = e->theta.p; a.vel = e->vel.p;
+    a.ov_alp0 = e->has_alp0 ? e->ov_alp0.p : nullptr;
+    a.ov_bet0 = e->has_bet0 ? e->ov_bet0.p : nullptr;
+    a.ov_v0 = e->has_v0 ? e->ov_v0.p : nullptr;
+    a.perm = (e->sort_enabled && !e->perm_identity && !tiled) ? e->perm.p : nullptr;
     a.rec_in = e->rec[e->cur].p;
     a.rec_out = e->rec[e->cur ^ 1].p;
+    if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
+      abm::launch_tile_bbox(a.rec_in, a.B, a.N, e->tile_bbox.p, e->tile_cull2.p, st);
+      a.tile_bbox = e->tile_bbox.p; a.tile_cull2 = e->tile_cull2.p;
+      a.bbox_slack = 2.0f * (e->r_max - e->r_min);
+      ++e->launches;
+    }
     if (use_sym) abm::launch_vf_step_sym(a, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
     e->cur ^= 1;
@@ -409,6 +509,39 @@ int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent) {
   if (!e || !dev_ptr) return fail(ABM_E_INVALID, "abm_vf_record_table: null argument");
   *dev_ptr = e->rec[e->cur].p;
   if (bytes_per_agent) *bytes_per_agent = (int)sizeof(float4);
+  return ABM_OK;
+}
+
+int abm_vf_get_permutation(abm_engine_t* e, int32_t* perm, int on_device, void* stream) {
+  if (!e || !perm) return fail(ABM_E_INVALID, "abm_vf_get_permutation: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e->sort_enabled) {
+    int rc = copy_out(perm, e->perm.p, sizeof(int32_t) * e->n_total, on_device, st);
+    if (rc) return rc;
+    if (!on_device) ABM_CUDA(cudaStreamSynchronize(st));
+  } else {
+    std::vector<int32_t> h(e->n_total);
+    for (size_t g = 0; g < e->n_total; ++g) h[g] = (int32_t)(g % (size_t)e->cfg.n_agents);
+    ABM_CUDA(cudaMemcpyAsync(perm, h.data(), sizeof(int32_t) * e->n_total,
+                             on_device ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost, st));
+    ABM_CUDA(cudaStreamSynchronize(st));
+  }
+  return ABM_OK;
+}
+
+int abm_vf_resort(abm_engine_t* e, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_vf_resort: null engine");
+  if (!e->state_set) return fail(ABM_E_STATE, "abm_vf_resort: no state has been set");
+  if (!e->sort_enabled) return ABM_OK;
+  ABM_CUDA(cudaSetDevice(e->device));
+  return resort_engine(e, (cudaStream_t)stream);
+}
+
+int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev) {
+  if (!e) return fail(ABM_E_INVALID, "abm_vf_internal_arrays: null engine");
+  if (theta_dev) *theta_dev = e->theta.p;
+  if (vel_dev) *vel_dev = e->vel.p;
   return ABM_OK;
 }
 

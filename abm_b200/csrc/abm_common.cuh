@@ -62,6 +62,12 @@ struct VFKernelArgs {
   const float* ov_alp0;           // nullable per-agent overrides, NaN = none
   const float* ov_bet0;
   const float* ov_v0;
+  const int* perm;                // nullable: internal slot -> API index (outputs are written in API order)
+  // distance culling by whole record tiles (CULL variants, spatially sorted state): bounding box (xmin, ymin,
+  // xmax, ymax) and largest cull^2 of every tile of kRecTile records; nullptr: every tile is visited
+  const float4* tile_bbox;
+  const float* tile_cull2;
+  float bbox_slack;               // 2 * (r_max - r_min): positions are top-left corners, distances are between centres
   const PhiLut* lut;              // R + 1 entries
   uint32_t* fields_out;           // nullable, B*tile*W
   double* terms_out;              // nullable, B*tile*6
@@ -69,6 +75,8 @@ struct VFKernelArgs {
 };
 
 void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream);
+void launch_tile_bbox(const float4* rec, int B, int N, float4* bbox, float* cull2, cudaStream_t stream);
+constexpr int kMaxTileList = 1024;   // tiles per replicate the culling list can hold (N <= 262144)
 size_t vf_step_smem_bytes(int threads, int W);
 // symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
@@ -90,8 +98,22 @@ void launch_vf_projection(const VFProjArgs& a, cudaStream_t stream);
 void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const VFParams6* prm,
                      const PhiLut* lut, double dphi, double* out6, cudaStream_t stream);
 // radius_minmax: 2 uints (bit patterns of min / max radius; init 0x7f800000 / 0)
-void launch_pack_records(const float* x, const float* y, const float* r, float cull_scale,
+// perm (nullable): internal slot -> caller's index; the records are written in internal order
+void launch_pack_records(const float* x, const float* y, const float* r, const int* perm, int N, float cull_scale,
                          float4* rec, unsigned* radius_minmax, long long n, cudaStream_t stream);
-void launch_unpack_records(const float4* rec, float* x, float* y, long long n, cudaStream_t stream);
+// perm (nullable): internal slot -> API index inside the replicate; x / y are written in API order
+void launch_unpack_records(const float4* rec, const int* perm, int N, float* x, float* y, long long n,
+                           cudaStream_t stream);
+
+// spatial re-ordering (abm_vf_sort.cu)
+size_t vf_sort_temp_bytes(int B, int N);
+cudaError_t vf_sort_order(const float4* rec, int B, int N, float x0, float y0, float extent, void* temp, size_t temp_bytes,
+                          uint32_t* keys_in, uint32_t* keys_out, int* vals_in, int* order, int* offsets,
+                          cudaStream_t stream);
+void launch_gather_f4(const float4* in, const int* order, float4* out, int N, long long n, cudaStream_t s);
+void launch_gather_f32(const float* in, const int* order, float* out, int N, long long n, cudaStream_t s);
+void launch_gather_i32(const int* in, const int* order, int* out, int N, long long n, cudaStream_t s);
+void launch_scatter_f32(const float* in, const int* perm, float* out, int N, long long n, cudaStream_t s);
+void launch_iota(int* p, int N, long long n, cudaStream_t s);
 
 }  // namespace abm

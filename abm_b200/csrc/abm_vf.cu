@@ -67,7 +67,8 @@ size_t vf_step_smem_bytes(int threads, int W) {
   return 2 * sizeof(float4) * kRecTile            // record stages
          + sizeof(uint32_t) * (size_t)(W + 2) * threads   // padded rows
          + 2 * sizeof(uint32_t) * kQueueCap         // deferred-pair queue
-         + 64;                                      // mbarriers + queue counter
+         + 64                                       // mbarriers + queue counter
+         + sizeof(int) * (kMaxTileList + 4) + 64;   // tile list of the culling variants, focal bounding box
 }
 
 int vf_step_threads(int tile_count) {
@@ -131,6 +132,8 @@ vf_step_kernel(const VFKernelArgs a) {
   uint32_t* queue = rows + (size_t)(a.W + 2) * T;                           // [kQueueCap][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(queue + 2 * kQueueCap);      // [2]
   int* qcount = reinterpret_cast<int*>(bars + 2);
+  int* tile_list = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(bars) + 64);   // [kMaxTileList] + count
+  float* fbox = reinterpret_cast<float*>(tile_list + kMaxTileList + 4);                     // focal bbox [4]
 
   const int tid = threadIdx.x;
   const int tiles_per_rep = (a.tile_count + T - 1) / T;
@@ -150,12 +153,16 @@ vf_step_kernel(const VFKernelArgs a) {
   for (int w = 0; w < a.W + 2; ++w) rows[w * T + tid] = 0u;
   __syncthreads();
 
-  const int n_stage = (a.N + kRecTile - 1) / kRecTile;
-  if (tid == 0) {
-    const int n0 = min(kRecTile, a.N);
-    mbar_expect_tx(&bars[0], n0 * (uint32_t)sizeof(float4));
-    tma_load_1d(recs, rep_in, n0 * (uint32_t)sizeof(float4), &bars[0]);
-  }
+  uint32_t* padrow = rows + tid;        // padded word 0 (virtual bins [-32, 0))
+  uint32_t* myrow = rows + T + tid;     // real word 0
+  const int R = RC ? RC : a.R;
+  unsigned char* padrow_b = reinterpret_cast<unsigned char*>(padrow);
+  const int stride_b = 4 * T;
+  const uint32_t row_a = smem_u32(padrow);   // shared-space address of padded word 0
+  const int fov0p = a.fov0p;           // first visible padded position
+  const unsigned span = a.span;        // number of visible positions (vf_supcalc.py:119)
+  const float width = a.width, height = a.height, half_w = a.half_w, half_h = a.half_h;
+  unsigned n_mismatch = 0;
 
   float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
   float th = 0.f;
@@ -169,28 +176,67 @@ vf_step_kernel(const VFKernelArgs a) {
     sincos((double)th, &sd, &cd);
     c = (float)cd; ns = (float)(-sd);
   }
-  uint32_t* padrow = rows + tid;        // padded word 0 (virtual bins [-32, 0))
-  uint32_t* myrow = rows + T + tid;     // real word 0
-  const int R = RC ? RC : a.R;
-  unsigned char* padrow_b = reinterpret_cast<unsigned char*>(padrow);
-  const int stride_b = 4 * T;
-  const uint32_t row_a = smem_u32(padrow);   // shared-space address of padded word 0
-  const int fov0p = a.fov0p;           // first visible padded position
-  const unsigned span = a.span;        // number of visible positions (vf_supcalc.py:119)
-  const float width = a.width, height = a.height, half_w = a.half_w, half_h = a.half_h;
-  unsigned n_mismatch = 0;
+  // ---- which record tiles to visit: all of them, or (culling variants on spatially sorted state) only those
+  //      whose bounding box comes within the cull distance of the bounding box of this CTA's focal agents ----
+  const int n_tiles = (a.N + kRecTile - 1) / kRecTile;
+  int n_stage = n_tiles;
+  const bool use_list = CULL && a.tile_bbox != nullptr && n_tiles <= kMaxTileList;
+  if (use_list) {
+    if (tid < 4) fbox[tid] = (tid < 2) ? 3.0e38f : -3.0e38f;
+    if (tid == 0) tile_list[kMaxTileList] = 0;
+    __syncthreads();
+    float x0 = active ? me.x : 3.0e38f, y0 = active ? me.y : 3.0e38f;
+    float x1 = active ? me.x : -3.0e38f, y1 = active ? me.y : -3.0e38f;
+    for (int off = 16; off > 0; off >>= 1) {
+      x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, off)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, off));
+      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, off)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, off));
+    }
+    if ((tid & 31) == 0) {   // positive floats order like their bit patterns; negatives are clamped by the atomics' int view
+      atomicMin(reinterpret_cast<int*>(&fbox[0]), __float_as_int(fmaxf(x0, 0.0f)));
+      atomicMin(reinterpret_cast<int*>(&fbox[1]), __float_as_int(fmaxf(y0, 0.0f)));
+      atomicMax(reinterpret_cast<int*>(&fbox[2]), __float_as_int(fmaxf(x1, 0.0f)));
+      atomicMax(reinterpret_cast<int*>(&fbox[3]), __float_as_int(fmaxf(y1, 0.0f)));
+    }
+    __syncthreads();
+    const float fx0 = fbox[0], fy0 = fbox[1], fx1 = fbox[2], fy1 = fbox[3];
+    const float4* bb = a.tile_bbox + (size_t)b * n_tiles;
+    const float* c2 = a.tile_cull2 + (size_t)b * n_tiles;
+    for (int t = tid; t < n_tiles; t += T) {
+      const float4 q = bb[t];
+      float gx = fmaxf(0.0f, fmaxf(q.x - fx1, fx0 - q.z));
+      float gy = fmaxf(0.0f, fmaxf(q.y - fy1, fy0 - q.w));
+      if (TORUS) {   // minimal image: the tile shifted by one period either way
+        gx = fminf(gx, fmaxf(0.0f, fmaxf(q.x + width - fx1, fx0 - (q.z + width))));
+        gx = fminf(gx, fmaxf(0.0f, fmaxf(q.x - width - fx1, fx0 - (q.z - width))));
+        gy = fminf(gy, fmaxf(0.0f, fmaxf(q.y + height - fy1, fy0 - (q.w + height))));
+        gy = fminf(gy, fmaxf(0.0f, fmaxf(q.y - height - fy1, fy0 - (q.w - height))));
+      }
+      const float reach = sqrtf(c2[t]) + a.bbox_slack + 1.0f;
+      if (gx * gx + gy * gy <= reach * reach) tile_list[atomicAdd(&tile_list[kMaxTileList], 1)] = t;
+    }
+    __syncthreads();
+    n_stage = tile_list[kMaxTileList];
+  }
+  auto tile_of = [&](int st) { return use_list ? tile_list[st] : st; };
+  if (tid == 0 && n_stage > 0) {
+    const int t0 = tile_of(0);
+    const int n0 = min(kRecTile, a.N - t0 * kRecTile);
+    mbar_expect_tx(&bars[0], n0 * (uint32_t)sizeof(float4));
+    tma_load_1d(recs, rep_in + (size_t)t0 * kRecTile, n0 * (uint32_t)sizeof(float4), &bars[0]);
+  }
 
   for (int st = 0; st < n_stage; ++st) {
     if (tid == 0 && st + 1 < n_stage) {
-      const int n1 = min(kRecTile, a.N - (st + 1) * kRecTile);
+      const int t1 = tile_of(st + 1);
+      const int n1 = min(kRecTile, a.N - t1 * kRecTile);
       uint64_t* bar = &bars[(st + 1) & 1];
       mbar_expect_tx(bar, n1 * (uint32_t)sizeof(float4));
-      tma_load_1d(recs + ((st + 1) & 1) * kRecTile, rep_in + (size_t)(st + 1) * kRecTile,
-                  n1 * (uint32_t)sizeof(float4), bar);
+      tma_load_1d(recs + ((st + 1) & 1) * kRecTile, rep_in + (size_t)t1 * kRecTile, n1 * (uint32_t)sizeof(float4), bar);
     }
     mbar_wait(&bars[st & 1], (st >> 1) & 1);
+    const int tile_j0 = tile_of(st) * kRecTile;            // first record index of this stage
     const float4* tile_recs = recs + (st & 1) * kRecTile;
-    const int nj = min(kRecTile, a.N - st * kRecTile);
+    const int nj = min(kRecTile, a.N - tile_j0);
     if (active) {
       const uint32_t rec0 = smem_u32(tile_recs), rec_end = rec0 + 16u * (uint32_t)nj;
 #pragma unroll 2
@@ -255,7 +301,7 @@ vf_step_kernel(const VFKernelArgs a) {
           if (!((o.x == me.x) & (o.y == me.y))) {
             const int slot = atomicAdd(qcount, 1);           // keeps counting past the capacity
             if (slot < kQueueCap) {
-              queue[2 * slot] = ((uint32_t)tid << 24) | (uint32_t)(st * kRecTile + (int)((ra - rec0) >> 4));
+              queue[2 * slot] = ((uint32_t)tid << 24) | (uint32_t)(tile_j0 + (int)((ra - rec0) >> 4));
               queue[2 * slot + 1] = ((uint32_t)(k - 32) << 16) | ((uint32_t)h & 0xffffu);
             } else {
               vf_exact_inline(a, myrow, T, me, (size_t)b * a.N + i, o, k - 32, h);
@@ -394,14 +440,48 @@ void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const V
   vf_terms_kernel<<<1, 1, 0, stream>>>(packed_v, R, W, vel, prm, lut, dphi, out6);
 }
 
+// Bounding box and largest cull^2 of every tile of kRecTile records (culling variants, every step).
+__global__ void __launch_bounds__(kRecTile) vf_tile_bbox_kernel(const float4* rec, int N, int n_tiles, float4* bbox,
+                                                                 float* cull2) {
+  __shared__ float red[5][kRecTile / 32];
+  const int bt = blockIdx.x, b = bt / n_tiles, t = bt - b * n_tiles;
+  const int j = t * kRecTile + threadIdx.x;
+  float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f, c = 0.0f;
+  if (j < N) {
+    const float4 v = rec[(size_t)b * N + j];
+    x0 = x1 = v.x; y0 = y1 = v.y; c = v.w;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, off)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, off));
+    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, off)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, off));
+    c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, off));
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = x0; red[1][w] = y0; red[2][w] = x1; red[3][w] = y1; red[4][w] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < kRecTile / 32; ++k) {
+      x0 = fminf(x0, red[0][k]); y0 = fminf(y0, red[1][k]); x1 = fmaxf(x1, red[2][k]); y1 = fmaxf(y1, red[3][k]);
+      c = fmaxf(c, red[4][k]);
+    }
+    bbox[bt] = make_float4(x0, y0, x1, y1);
+    cull2[bt] = c;
+  }
+}
+void launch_tile_bbox(const float4* rec, int B, int N, float4* bbox, float* cull2, cudaStream_t stream) {
+  const int n_tiles = (N + kRecTile - 1) / kRecTile;
+  vf_tile_bbox_kernel<<<(unsigned)((size_t)B * n_tiles), kRecTile, 0, stream>>>(rec, N, n_tiles, bbox, cull2);
+}
+
 // SoA host-facing state <-> packed neighbour records
-__global__ void pack_records_kernel(const float* x, const float* y, const float* r, float cull_scale,
-                                    float4* rec, unsigned* radius_minmax, long long n) {
+__global__ void pack_records_kernel(const float* x, const float* y, const float* r, const int* perm, int N,
+                                    float cull_scale, float4* rec, unsigned* radius_minmax, long long n) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float rr = 0.f;
   if (g < n) {
-    rr = r[g];
-    rec[g] = make_float4(x[g], y[g], rr, rr * rr * cull_scale);
+    const long long o = perm ? (g - (g % N)) + perm[g] : g;   // caller's order -> internal slot g
+    rr = r[o];
+    rec[g] = make_float4(x[o], y[o], rr, rr * rr * cull_scale);
   }
   // min / max radius of the batch (non-negative floats order like their bit patterns)
   unsigned lo = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0x7f800000u;
@@ -413,23 +493,25 @@ __global__ void pack_records_kernel(const float* x, const float* y, const float*
     atomicMax(&radius_minmax[1], hi);
   }
 }
-__global__ void unpack_records_kernel(const float4* rec, float* x, float* y, long long n) {
+__global__ void unpack_records_kernel(const float4* rec, const int* perm, int N, float* x, float* y, long long n) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g < n) {
     const float4 v = rec[g];
-    if (x) x[g] = v.x;
-    if (y) y[g] = v.y;
+    const long long o = perm ? (g - (g % N)) + perm[g] : g;
+    if (x) x[o] = v.x;
+    if (y) y[o] = v.y;
   }
 }
-void launch_pack_records(const float* x, const float* y, const float* r, float cull_scale, float4* rec,
-                         unsigned* radius_minmax, long long n, cudaStream_t stream) {
+void launch_pack_records(const float* x, const float* y, const float* r, const int* perm, int N, float cull_scale,
+                         float4* rec, unsigned* radius_minmax, long long n, cudaStream_t stream) {
   const int threads = 256;
-  pack_records_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(x, y, r, cull_scale, rec,
+  pack_records_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(x, y, r, perm, N, cull_scale, rec,
                                                                                       radius_minmax, n);
 }
-void launch_unpack_records(const float4* rec, float* x, float* y, long long n, cudaStream_t stream) {
+void launch_unpack_records(const float4* rec, const int* perm, int N, float* x, float* y, long long n,
+                           cudaStream_t stream) {
   const int threads = 256;
-  unpack_records_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(rec, x, y, n);
+  unpack_records_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(rec, perm, N, x, y, n);
 }
 
 }  // namespace abm

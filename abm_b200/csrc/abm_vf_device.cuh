@@ -439,7 +439,8 @@ __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, 
   a.theta[gi] = (float)nth;
   a.vel[gi] = (float)nv;
 
-  const size_t oi = (size_t)b * a.tile_count + li;
+  // outputs in API order when the engine keeps an internal (spatially sorted) order
+  const size_t oi = a.perm ? (size_t)b * a.N + a.perm[gi] : (size_t)b * a.tile_count + li;
   if (a.terms_out) {
     double* t = a.terms_out + oi * 6;
     t[0] = ft.dvel; t[1] = ft.dpsi; t[2] = ft.a_blob; t[3] = ft.a_edge; t[4] = ft.b_blob; t[5] = ft.b_edge;

@@ -43,7 +43,8 @@ class VFEngine:
                  fov=(-np.pi, np.pi), boundary: str = "walls", width: float = 900.0, height: float = 900.0,
                  window_pad: float = 30.0, limit_movement: bool = False, max_vel: float = 3.0,
                  max_th: float = 0.1, exact_fixup: bool = True, keep_fields: bool = False,
-                 keep_terms: bool = False, device: int = 0, tile: tuple[int, int] | None = None):
+                 keep_terms: bool = False, device: int = 0, tile: tuple[int, int] | None = None,
+                 spatial_sort: bool = True, resort_every: int = 32):
         if boundary not in ("walls", "infinite"):
             raise ValueError(f"boundary must be 'walls' or 'infinite', got {boundary!r}")
         self._lib = _lib.load()
@@ -53,14 +54,15 @@ class VFEngine:
         self.tile_begin, self.tile_count = (0, self.N) if tile is None else (int(tile[0]), int(tile[1]))
         f0, f1 = _fov_pixels(self.R, fov)
         flags = (_lib.VF_EXACT_FIXUP if exact_fixup else 0) | (_lib.VF_KEEP_FIELDS if keep_fields else 0) \
-            | (_lib.VF_KEEP_TERMS if keep_terms else 0)
+            | (_lib.VF_KEEP_TERMS if keep_terms else 0) | (_lib.VF_SPATIAL_SORT if spatial_sort else 0)
         cfg = _lib.VFConfig(
             struct_size=C.sizeof(_lib.VFConfig), n_replicates=self.B, n_agents=self.N, resolution=self.R,
             fov_px0=f0, fov_px1=f1,
             boundary=_lib.BOUNDARY_INFINITE if boundary == "infinite" else _lib.BOUNDARY_WALLS,
             limit_movement=int(bool(limit_movement)), width=float(width), height=float(height),
             window_pad=float(window_pad), max_vel=float(max_vel), max_th=float(max_th), flags=flags,
-            tile_begin=self.tile_begin, tile_count=0 if tile is None else self.tile_count)
+            tile_begin=self.tile_begin, tile_count=0 if tile is None else self.tile_count,
+            resort_every=int(resort_every))
         self._h = C.c_void_p()
         _lib.check(self._lib.abm_vf_create(C.byref(cfg), self.device, C.byref(self._h)), "abm_vf_create")
         self.keep_fields, self.keep_terms = keep_fields, keep_terms
@@ -193,6 +195,22 @@ class VFEngine:
         c = (C.c_uint64 * 4)()
         _lib.check(self._lib.abm_get_counters(self._h, c, C.c_void_p(_current_stream())), "abm_get_counters")
         return dict(fp64_pairs=int(c[0]), fp64_inline=int(c[1]), fp32_fp64_differ=int(c[2]), launches=int(c[3]))
+
+    def permutation(self) -> np.ndarray:
+        """(B, N) int32: perm[b, slot] = caller's index of the agent in internal slot `slot`."""
+        out = np.empty((self.B, self.N), np.int32)
+        _lib.check(self._lib.abm_vf_get_permutation(self._h, C.c_void_p(out.ctypes.data), 0,
+                                                    C.c_void_p(_current_stream())), "abm_vf_get_permutation")
+        return out
+
+    def resort(self):
+        _lib.check(self._lib.abm_vf_resort(self._h, C.c_void_p(_current_stream())), "abm_vf_resort")
+
+    def internal_array_ptrs(self) -> tuple[int, int]:
+        """Device pointers of the internal heading / speed arrays (B*N float32, internal order)."""
+        t, v = C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.abm_vf_internal_arrays(self._h, C.byref(t), C.byref(v)), "abm_vf_internal_arrays")
+        return int(t.value), int(v.value)
 
     def record_table_ptr(self) -> tuple[int, int]:
         p = C.c_void_p()

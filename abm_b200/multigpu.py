@@ -79,12 +79,29 @@ class TiledSwarm:
             tile = table[self.begin:self.begin + self.count]
             self.dist.all_gather_into_tensor(table, tile, group=self.group)   # in place, 16 B / agent
 
+    def _internal(self):
+        """torch views of the engine's internal heading / speed arrays (internal order, full size)."""
+        tp, vp = self.engine.internal_array_ptrs()
+        mk = lambda p: self.torch.as_tensor(_DeviceMemory(p, self.N), device="cuda")
+        return mk(tp), mk(vp)
+
+    def resync(self):
+        """Make headings / speeds current on every rank (one all-gather each) and re-sort the
+        internal order spatially -- call every few hundred steps of a long run."""
+        for t in self._internal():
+            self.dist.all_gather_into_tensor(t, t[self.begin:self.begin + self.count].clone(), group=self.group)
+        self.engine.resort()
+        self._tables = {}
+
     def get_state(self):
-        """Full (x, y) from the gathered table; theta / vel of the local tile only (the rest is
-        gathered here, off the step path)."""
+        """Full state in the caller's agent order: (x, y) from the gathered record table, headings /
+        speeds gathered here (off the step path) from the tiles and un-permuted."""
         st = self.engine.get_state()
         out = {"x": st["x"][0], "y": st["y"][0]}
-        for k in ("theta", "vel"):
-            local = self.torch.from_numpy(np.ascontiguousarray(st[k][0, self.begin:self.begin + self.count])).cuda()
-            out[k] = gather_tiles(local, self.world, self.group).cpu().numpy()
+        perm = self.engine.permutation()[0]
+        for k, t in zip(("theta", "vel"), self._internal()):
+            full = gather_tiles(t[self.begin:self.begin + self.count].clone(), self.world, self.group).cpu().numpy()
+            api = np.empty_like(full)
+            api[perm] = full
+            out[k] = api
         return out

@@ -52,7 +52,10 @@ enum {
   ABM_VF_EXACT_FIXUP = 1u << 0, /* re-evaluate pairs whose fp32 bin index is within the error
                                    bound of a rounding boundary in fp64 (default on) */
   ABM_VF_KEEP_FIELDS = 1u << 1, /* keep the packed stored fields of the last step (abm_get_fields) */
-  ABM_VF_KEEP_TERMS = 1u << 2   /* keep the six flocking terms of the last step (abm_vf_get_terms) */
+  ABM_VF_KEEP_TERMS = 1u << 2,  /* keep the six flocking terms of the last step (abm_vf_get_terms) */
+  ABM_VF_SPATIAL_SORT = 1u << 3 /* keep the agents of every replicate in Morton order internally (refreshed every
+                                   `resort_every` steps); invisible through this ABI, which always speaks the
+                                   caller's agent order -- except abm_vf_record_table, see there */
 };
 
 typedef struct abm_engine abm_engine_t;
@@ -80,6 +83,8 @@ typedef struct {
    * neighbour records; tile_count == 0 means the whole replicate. */
   int32_t tile_begin;
   int32_t tile_count;
+  int32_t resort_every;   /* with ABM_VF_SPATIAL_SORT: re-sort after this many steps (0: only when the state is set
+                             or abm_vf_resort is called) */
 } abm_vf_config_t;
 
 /* The six per-replicate flocking parameters, in this order (vf_params.py:12-19;
@@ -136,6 +141,14 @@ int abm_get_counters(abm_engine_t* e, uint64_t counters[4], void* stream);
  * completes the table with an all-gather (torch.distributed / NCCL) before the next
  * abm_vf_step.  *bytes_per_agent = 16. */
 int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent);
+
+/* With ABM_VF_SPATIAL_SORT the record table, and the tile of a tiled engine, are in INTERNAL order.
+ * abm_vf_get_permutation: perm[b * n_agents + slot] = caller's index of the agent in that slot.
+ * abm_vf_resort: re-sort now (a tiled engine needs the full heading / speed arrays to be current on
+ * every rank first: abm_vf_internal_arrays exposes them for the all-gather). */
+int abm_vf_get_permutation(abm_engine_t* e, int32_t* perm, int on_device, void* stream);
+int abm_vf_resort(abm_engine_t* e, void* stream);
+int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev);
 
 int abm_synchronize(abm_engine_t* e, void* stream);
 

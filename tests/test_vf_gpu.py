@@ -265,3 +265,32 @@ def test_fixup_counters_and_fp32_only_mode(built_lib):
     print(f"fp64 pairs {cnt['fp64_pairs']} of {pairs} ({cnt['fp64_pairs'] / pairs:.2e}); fp32/fp64 index "
           f"differences {cnt['fp32_fp64_differ']}; agents whose fp32-only field differs: {diff_agents} of {B * N}")
     exact.close(); fast.close()
+
+
+def test_spatial_sort_is_invisible(built_lib):
+    """The internal Morton ordering (refreshed every few steps) must not change any result:
+    sorted and unsorted engines agree bit for bit after many steps, in the caller's agent order,
+    including fields, terms and per-agent overrides set before and after the first sort."""
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(41)
+    B, N, R, W = 3, 300, 1200, 900.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    alp0 = rng.uniform(0.5, 2.0, (B, N)).astype(np.float32); alp0[:, ::3] = np.nan
+    res = {}
+    for sort in (False, True):
+        eng = VFEngine(B, N, resolution=R, width=W, height=W, keep_fields=True, keep_terms=True,
+                       spatial_sort=sort, resort_every=4)
+        eng.set_params(); eng.set_state(x, y, th, v, 10.0)
+        eng.set_agent_overrides(alp0=alp0)
+        eng.step(7)
+        eng.set_agent_overrides(alp0=alp0, v0=alp0)          # now in a permuted internal order
+        eng.step(6)
+        res[sort] = (eng.get_state(), eng.fields_packed(), eng.terms(), eng.permutation())
+        eng.close()
+    for k in ("x", "y", "theta", "vel"):
+        assert np.array_equal(res[False][0][k], res[True][0][k]), k
+    assert np.array_equal(res[False][1], res[True][1])
+    assert np.array_equal(res[False][2], res[True][2])
+    assert np.array_equal(res[False][3], np.tile(np.arange(N, dtype=np.int32), (B, 1)))
+    assert not np.array_equal(res[True][3], res[False][3])
+    assert np.array_equal(np.sort(res[True][3], axis=1), res[False][3])
