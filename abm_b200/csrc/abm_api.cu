@@ -410,6 +410,11 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.half_pi_b = (float)(0.5 * ABM_PI_D * inv); a.pi_b = (float)(ABM_PI_D * inv);
     a.seam_b = (float)((double)g.ca_guard * inv);
     a.nthr_h1 = -a.thr_h1;
+    // symmetric kernel: closed angle = bearing - heading, both rounded to fp32 bins (|.| <= 1.5 R: ulp 1.2e-4 R/1200)
+    const float tau_k_sym = g.tau_k + (float)(3.0e-7 * (double)g.R);
+    a.sym_thr_k = exact ? 0.5f - tau_k_sym : 3.0e38f;
+    a.sym_seam_b = (float)((ABM_PI_D - 6.0e-6) * inv);
+    a.sym_thr_h = exact ? 0.5f - g.tau_h_abs - 17.5f * g.tau_h_rel : 3.0e38f;
     a.full_fov = (e->cfg.fov_px0 == 0 && e->cfg.fov_px1 == g.R - 1) ? 1 : 0;
   }
   a.width = e->cfg.width; a.height = e->cfg.height;
@@ -439,15 +444,17 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   // half width drops to 0 (r / tan(2pi/R)); expected visible fraction ~ pi * d_cull^2 / arena area.
   const double d_cull = (double)e->r_max * std::sqrt((double)g.cull_scale);
   const bool cull = ABM_PI_D * d_cull * d_cull < 0.5 * (double)e->cfg.width * (double)e->cfg.height;
-  // kernel choice: the one-thread-per-focal-agent kernel; ABM_VF_KERNEL=symmetric selects the experimental kernel
-  // that evaluates every unordered pair once (abm_vf_sym.cu; measured slower in round 1)
+  // kernel choice: the symmetric kernel (abm_vf_sym.cu: every unordered pair once) whenever it applies; ABM_VF_KERNEL=onesided
+  // forces the one-thread-per-focal-agent kernel (abm_vf.cu)
   const char* force = getenv("ABM_VF_KERNEL");
-  const bool use_sym = (force && strcmp(force, "symmetric") == 0) &&
+  a.sym_radius = e->r_max;
+  const bool use_sym = !(force && strcmp(force, "onesided") == 0) &&
                        abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
   const bool tiled = e->tile_count != e->cfg.n_agents;
   for (int s = 0; s < n_steps; ++s) {
-    if (e->sort_enabled && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
-                                               e->steps_since_sort >= e->cfg.resort_every))) {
+    // (the symmetric kernel wants NO spatial order: its blocks should all hold the same mix of near and far pairs)
+    if (e->sort_enabled && !use_sym && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
+                                                           e->steps_since_sort >= e->cfg.resort_every))) {
       int rc = resort_engine(e, st);
       if (rc) return rc;
     }

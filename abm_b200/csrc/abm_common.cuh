@@ -43,6 +43,9 @@ struct VFKernelArgs {
   float half_pi_b, pi_b;          // pi/2 * inv_step, pi * inv_step
   float seam_b;                   // ca_guard * inv_step
   float nthr_h1;                  // -thr_h1
+  // symmetric kernel (abm_vf_sym.cu): wider k guard band (the closed angle is a difference of two rounded bin
+  // angles), absolute h guard band of the fast path (h <= 16), the common radius
+  float sym_thr_k, sym_seam_b, sym_thr_h, sym_radius;
   int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible
   int fov0p;                      // fov_px0 + 33: first visible padded position
   unsigned span;                  // fov_px1 - fov_px0 - 1: number of visible positions

@@ -16,53 +16,6 @@
 
 namespace abm {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 1-D bulk TMA global -> shared, completion on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// explicit shared-space accesses with 32-bit addresses: keeps the generic->shared window arithmetic
-// (S2UR SR_CgaCtaId / ULEA per access) out of the pair loop
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
-}
-
 size_t vf_step_smem_bytes(int threads, int W) {
   return 2 * sizeof(float4) * kRecTile            // record stages
          + sizeof(uint32_t) * (size_t)(W + 2) * threads   // padded rows
@@ -98,26 +51,6 @@ static __device__ __noinline__ void vf_exact_inline(const VFKernelArgs& a, uint3
 static __device__ __noinline__ void vf_draw_general(const VFKernelArgs& a, uint32_t* myrow, int stride, int k, int h) {
   vf_draw<false>(myrow, stride, a.R, a.fov_px0, a.fov_px1, k, h);
 }
-
-// Pair-loop constants that depend only on the resolution R.  RC > 0: compile-time resolution (they become
-// instruction immediates); RC == 0: read from the kernel arguments (constant bank).
-template <int RC>
-struct PairK {
-  static constexpr double kInv = RC > 1 ? (double)(RC - 1) / ABM_TWO_PI_D : 0.0;   // (R - 1) / 2pi
-  static constexpr float kTHalf = (RC % 2 == 0) ? 0.5f : 1.0f;
-  __device__ __forceinline__ static float ac(const VFKernelArgs& a, int c) {
-    constexpr double kA[7] = {0.9999993443489075, -0.33326515555381775, 0.19881492853164673, -0.13487225770950317,
-                              0.0838717594742775, -0.037013452500104904, 0.007863515056669712};
-    return RC ? (float)(kA[c] * kInv) : a.ac[c];
-  }
-  __device__ __forceinline__ static float half_pi_b(const VFKernelArgs& a) { return RC ? (float)(0.5 * ABM_PI_D * kInv) : a.half_pi_b; }
-  __device__ __forceinline__ static float pi_b(const VFKernelArgs& a) { return RC ? (float)(ABM_PI_D * kInv) : a.pi_b; }
-  __device__ __forceinline__ static float t_half(const VFKernelArgs& a) { return RC ? kTHalf : a.t_half; }
-  __device__ __forceinline__ static int k_bias(const VFKernelArgs& a) {
-    return RC ? ((RC % 2 == 0 ? RC / 2 - 1 : (RC - 3) / 2) - 0x4B400000 + 32) : a.k_bias;
-  }
-  __device__ __forceinline__ static float y_scale(const VFKernelArgs& a) { return RC ? (float)((double)RC / ABM_TWO_PI_D) : a.y_scale; }
-};
 
 // TORUS: BOUNDARY == infinite.  UNIFORM_R: all radii equal (centre difference == position
 // difference).  CULL: skip pairs beyond the distance at which the half width becomes 0.

@@ -1,28 +1,59 @@
 // Symmetric visual-flocking step kernel for sm_100a: every UNORDERED pair {i, j} of a replicate
 // is evaluated once and drawn into BOTH agents' rows.
 //
-// What the two directions share: the centre distance, hence rsqrt, atan(r/d) and the half width
-// h (equal radii), and the absolute bearing phi = atan2(-dy, dx); the closed angles are then
-//   ca_i = wrap(phi - theta_i)          and          ca_j = wrap(phi + pi - theta_j),
-// i.e. the expensive part of the pair arithmetic (two polynomial arctangents, two MUFU ops) is
-// paid once per unordered pair instead of once per ordered pair.
+// What the two directions share (equal radii): the centre distance, hence rsqrt, atan(r/d) and
+// the half width h, and the absolute bearing phi = atan2(-dy, dx); the closed angles are then
+//   ca_i = wrap(phi - theta_i)          and          ca_j = wrap(phi + pi - theta_j)
+// (vf_supcalc.py:86-117 evaluated from both ends), so both polynomial arctangents and both MUFU
+// operations are paid once per unordered pair; what is left per direction is one subtraction, the
+// rounding to a bin with its guard band, and the read-modify-write of one or two row words.
 //
-// To draw into both rows without atomics, ALL rows of a replicate live in one CTA's shared
-// memory ([word][agent], 160 B per agent at R = 1200 -> 1024 agents in 160 KB) and the 32-agent
-// blocks are paired by a round-robin tournament: in every round each block belongs to exactly
-// one block pair, each block pair to exactly one warp, so a warp owns the rows it writes; lane l
-// of the warp owns agent l of block I and visits the agents of block J in rotated order
-// (l + s) mod 32, so own-row and partner-row accesses are both bank-conflict free.  One
-// __syncthreads per round; the diagonal blocks (pairs inside a block) take one extra round.
+// Mapping.  CTA = one replicate.  ALL rows of the replicate live in the CTA's shared memory
+// ([word][agent]: bank == agent mod 32; 160 B per agent at R = 1200 -> 1024 agents in 160 KB).
+// The 32-agent blocks are paired by a round-robin tournament: in every round each block belongs
+// to exactly one block pair and each block pair to exactly one warp, so a warp OWNS the rows it
+// writes -- no atomics.  Lane l owns agent l of block I and visits agent (l XOR s) of block J in
+// step s: own-row and partner-row accesses are both bank-conflict free, and the partner's
+// addresses are one LOP3 away from a per-round base.  One __syncthreads per round; the diagonal
+// blocks (pairs inside a block) take one extra round in which every lane draws its own side.
+//
+// Fast path: intervals of 1..32 bins (1 <= h <= 16) whose bin arithmetic is clear of every fp32
+// guard band are drawn with straight-line code (no divergence inside a step).  Everything else is
+// "slow" (about 1 % of the pairs of the benchmark scene): guard-band hits go to the per-CTA fp64
+// queue (the reference's own operation sequence, abm_vf_device.cuh), wide intervals are drawn by
+// the general rule.  The slow path sits behind one warp-uniform branch per step.
 //
 // Used when all radii are equal, no distance culling is wanted, the engine owns whole
 // replicates, and the rows fit in shared memory; otherwise vf_step_kernel (abm_vf.cu) runs.
-// Same fp32 pair arithmetic, guard bands, fp64 queue and epilogue as that kernel.
 #include "abm_vf_device.cuh"
 
 namespace abm {
 
-constexpr int kSymQueueCap = 3072;   // ~0.16 % of the 1M ordered pairs of a 1024-agent replicate are deferred
+constexpr int kSymQueueCap = 3072;   // fp64 queue: ~0.2 % of the 1M ordered pairs of a 1024-agent replicate
+constexpr int kSymWarpQ = 64;        // per-warp queue of lane entries with directions off the fast path
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: low mantissa bits of x + kMagic = rint(x)
+constexpr int kMagicBits = 0x4B400000;
+
+// Loop-invariant values of the pair loop that must live in registers (the compiler would otherwise
+// re-materialise them with a MOV in every step).
+struct SymConsts {
+  float rS;            // radius * R/2pi
+  float c3s, c5s;      // -1/(3 S^2), 1/(5 S^4), S = R/2pi: atan(q) S = qs (1 + c3s qs^2 + c5s qs^4)
+  float a6;            // leading coefficient of the bearing polynomial
+  int scratch_pos;     // padded position of the scratch word
+};
+__device__ __forceinline__ float pin_f(float v) { asm volatile("" : "+f"(v)); return v; }
+__device__ __forceinline__ uint32_t pin_u(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+
+struct SymShared {
+  float4* ag;          // [Np] (x, y, heading in bins, radius); padding agents beyond N are far away
+  uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
+  uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
+  uint32_t* warpq;     // [warps][kSymWarpQ]  per-warp entries: own agent | partner of the even step << 10 | 4 flags << 20
+  int* qcount;         // [0]: fp64 queue
+  int* ready;          // [P] number of tournament rounds (+1 for the diagonal phase) completed on each block
+  int Np, N;
+};
 
 // Out-of-line fp64 evaluation + atomic draw of one ordered pair.  Returns 1 if the fp64 indices
 // differ from the fp32 ones.
@@ -33,102 +64,237 @@ static __device__ __noinline__ unsigned sym_exact_and_draw(const VFKernelArgs& a
   if (pe.valid) vf_draw<true>(row, stride, a.R, a.fov_px0, a.fov_px1, pe.k, pe.h);
   return (pe.valid && ((pe.k != k32) | (pe.h != h32))) ? 1u : 0u;
 }
-static __device__ __noinline__ void sym_draw_general(const VFKernelArgs& a, uint32_t* row, int stride, int k, int h) {
-  vf_draw<false>(row, stride, a.R, a.fov_px0, a.fov_px1, k, h);
+
+// Bearing of the partner in bins of the linspace grid, |.| parts for both directions:
+// pi_abs = |atan2(-dy, dx)|, pj_abs = |atan2(dy, -dx)| (each * (R-1)/2pi).
+template <int RC>
+__device__ __forceinline__ void sym_bearing(const VFKernelArgs& a, float dx, float dy, float a6, float& pi_abs,
+                                            float& pj_abs) {
+  using K = PairK<RC>;
+  const float au = fabsf(dx), aw = fabsf(dy);
+  const float tq = fminf(au, aw) * rcp_approx(fmaxf(au, aw));
+  const float z = tq * tq;
+  float p = fmaf(a6, z, K::ac(a, 5));
+  p = fmaf(p, z, K::ac(a, 4));
+  p = fmaf(p, z, K::ac(a, 3));
+  p = fmaf(p, z, K::ac(a, 2));
+  p = fmaf(p, z, K::ac(a, 1));
+  p = fmaf(p, z, K::ac(a, 0));
+  p *= tq;
+  if (aw > au) p = K::half_pi_b(a) - p;
+  const float pr = K::pi_b(a) - p;
+  const bool neg = dx < 0.0f;
+  pi_abs = neg ? pr : p;
+  pj_abs = neg ? p : pr;
 }
 
-// wrap an angle difference (|x| < 4 pi) into [-pi, pi] (Cody-Waite two-constant reduction)
-__device__ __forceinline__ float wrap_pi(float x) {
-  const float MAGIC = 12582912.0f;
-  const float n = fmaf(x, 0.15915494309189535f, MAGIC) - MAGIC;       // rint(x / 2pi)
-  x = fmaf(n, -6.28318548202514648f, x);                              // 2pi rounded to fp32
-  return fmaf(n, 1.74845553e-07f, x);                                 // - (2pi - fp32(2pi)) * n
+// One direction of a pair on the fast path: closed angle -> padded start position of the interval
+// (h already folded into `bh`), `slow` is set when the bin index is within the fp32 error bound of
+// a rounding boundary or the angle is on the +-pi seam.
+template <int RC>
+__device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, float phi, float thb, int bh, bool& slow) {
+  using K = PairK<RC>;
+  float cab = phi - thb;                                    // thb in [0, R-1] -> cab in [-1.5 (R-1), (R-1)/2]
+  if (cab < -K::pi_b(a)) cab += 2.0f * K::pi_b(a);
+  slow |= fabsf(cab) > a.sym_seam_b;
+  const float t = cab + K::t_half(a);
+  const float tr = t + kMagic;
+  slow |= fabsf(t - (tr - kMagic)) > a.sym_thr_k;
+  return __float_as_int(tr) + bh;
 }
 
-struct SymShared {
-  float4* ag;          // [Np] (x, y, theta, radius); padding agents beyond N are never drawn
-  uint32_t* rows;      // [W + 2][Np] padded rows
-  uint32_t* queue;     // [kSymQueueCap][2]
-  int* qcount;
-};
-
-// One side of a pair: centre bin from the closed angle, guard bands, draw into `row_b`.
-// focal / other: agent indices inside the replicate (for the fp64 queue).
-__device__ __forceinline__ void sym_side(const VFKernelArgs& a, const SymShared& sh, float ca, int h, bool flag_h,
-                                         bool valid, unsigned char* row_b, int stride_b, int focal, int other) {
-  const float MAGIC = 12582912.0f;
-  const float t = fmaf(ca, a.inv_step, a.t_half);
-  const float tr = t + MAGIC;
-  const int k = __float_as_int(tr) + a.k_bias;                 // padded position of the centre bin
-  const bool flagged = flag_h | (fabsf(t - (tr - MAGIC)) > a.thr_k) | (fabsf(ca) > a.ca_guard);
-  const int ps = k - h, pe = k + h;
-  const bool vis = ((unsigned)(ps - a.fov0p) < a.span) | ((unsigned)(pe - a.fov0p) < a.span);   // vf_supcalc.py:119
-  if (valid & !flagged & vis & ((unsigned)(h - 1) < 16u)) {
-    vf_draw_short(row_b, stride_b, ps, h);
-  } else if (valid & flagged) {
-    const int slot = atomicAdd(sh.qcount, 1);
+// Slow path of one direction (focal f sees object o), run from the round queue by any thread: the
+// complete fp32 evaluation (full-range arctangent for the half width, relative guard band);
+// guard-band hits are queued for fp64, anything else visible is drawn by the general rule (wide
+// intervals, wrap quirks) with atomics.
+template <bool TORUS, int RC>
+static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, const SymShared& sh, int f, int o) {
+  using K = PairK<RC>;
+  if ((f >= sh.N) | (o >= sh.N)) return;                              // padding agents
+  const float4 fa = sh.ag[f], oa = sh.ag[o];
+  if ((fa.x == oa.x) & (fa.y == oa.y)) return;                        // vf_supcalc.py:57
+  float dx = oa.x - fa.x, dy = oa.y - fa.y;
+  if (TORUS) {
+    if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
+    if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+  }
+  const float d2 = fmaf(dx, dx, dy * dy);
+  const float q = oa.w * rsqrt_approx(d2);
+  const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
+  const float yr = y + kMagic;
+  const int h = __float_as_int(yr) - kMagicBits;
+  bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
+  float pi_abs, pj_abs;
+  sym_bearing<RC>(a, dx, dy, K::ac(a, 6), pi_abs, pj_abs);
+  const int R = RC ? RC : a.R;
+  const int k = sym_side_k<RC>(a, copysignf(pi_abs, -dy), fa.z, K::k_bias(a), flagged) - 32;   // real bin index
+  uint32_t* row = sh.rows + sh.Np + f;                                // real word 0
+  if (flagged) {
+    const int slot = atomicAdd(&sh.qcount[0], 1);                     // keeps counting past the capacity
     if (slot < kSymQueueCap) {
-      sh.queue[2 * slot] = ((uint32_t)focal << 16) | (uint32_t)other;
-      sh.queue[2 * slot + 1] = ((uint32_t)(k - 32) << 16) | ((uint32_t)h & 0xffffu);
-    } else {   // queue full: evaluate here and now (atomic draw: another warp may own this row right now? no -- rows
-               // touched in a round belong to this warp, and atomics are harmless)
-      const float4 f4 = sh.ag[focal], o4 = sh.ag[other];
-      const unsigned diff = sym_exact_and_draw(a, reinterpret_cast<uint32_t*>(row_b) + stride_b / 4, stride_b / 4,
-                                               make_float4(f4.x, f4.y, f4.w, 0.f), f4.z,
-                                               make_float4(o4.x, o4.y, o4.w, 0.f), k - 32, h);
+      sh.queue[2 * slot] = ((uint32_t)f << 16) | (uint32_t)o;
+      sh.queue[2 * slot + 1] = ((uint32_t)k << 16) | ((uint32_t)h & 0xffffu);
+    } else {
+      const size_t g = (size_t)blockIdx.x * a.N;
+      const unsigned diff = sym_exact_and_draw(a, row, sh.Np, a.rec_in[g + f], a.theta[g + f], a.rec_in[g + o], k, h);
       atomicAdd(&a.counters[1], 1ull);
       if (diff) atomicAdd(&a.counters[2], 1ull);
     }
-  } else if (valid & vis & (h > 16)) {
-    if ((ps >= 0) & (pe <= a.R + 62)) vf_draw_wide(row_b, stride_b, ps, pe);
-    else sym_draw_general(a, reinterpret_cast<uint32_t*>(row_b) + stride_b / 4, stride_b / 4, k - 32, h);
+  } else {
+    vf_draw<true>(row, sh.Np, R, a.fov_px0, a.fov_px1, k, h);
   }
 }
 
-// BOTH: draw both directions; SYNC: own and partner rows may alias (diagonal block) -> separate
-// the two draws with __syncwarp so that no two lanes read-modify-write the same word at once.
-template <bool TORUS, bool BOTH, bool SYNC>
-__device__ __forceinline__ void sym_pair(const VFKernelArgs& a, const SymShared& sh, int Np, int N, int i, int j,
-                                         float xi, float yi, float thi, float radius, unsigned char* rows_b) {
-  const float4 o = sh.ag[j];
+// Work the warp's queue off: every lane takes one entry and walks through its flagged directions
+// (flag bit 0 / 1: own agent sees the partner of the even step / is seen by it, bits 2 / 3: the same
+// for the odd step, whose partner index differs in bit 0).  Draws are atomic: two lanes may hold
+// entries of the same row.  n is warp-uniform.
+template <bool TORUS, int RC>
+static __device__ __noinline__ void sym_flush(const VFKernelArgs& a, const SymShared& sh, const uint32_t* wq, int n,
+                                              int lane) {
+  __syncwarp();
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    const uint32_t ent = (e < n) ? wq[e] : 0u;
+    uint32_t flags = ent >> 20;
+    const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
+    while (flags) {
+      const int bit = __ffs(flags) - 1;
+      flags &= flags - 1;
+      const int j = jA ^ (bit >> 1);
+      sym_slow_side<TORUS, RC>(a, sh, (bit & 1) ? j : i, (bit & 1) ? i : j);
+    }
+  }
+  __syncwarp();
+}
+
+// Append this lane's entry (if it has flagged directions) to the warp's queue; the queue is worked
+// off as soon as it could overflow with the next append.  Called by the converged warp.
+template <bool TORUS, int RC>
+__device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared& sh, uint32_t* wq, int& wcount, int lane,
+                                         bool any, uint32_t entry) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, any);
+  if (bal) {                                                   // warp-uniform
+    if (any) wq[wcount + __popc(bal & ((1u << lane) - 1u))] = entry;
+    wcount += __popc(bal);
+    if (wcount > kSymWarpQ - 32) {
+      sym_flush<TORUS, RC>(a, sh, wq, wcount, lane);
+      wcount = 0;
+    }
+  }
+}
+
+// Tournament dataflow: a block may be worked on in round r only after its round r - 1 user is done
+// with it.  Instead of a CTA-wide barrier per round, every block carries a counter of completed
+// rounds; warps wait only for their own two blocks.
+__device__ __forceinline__ void sym_wait_block(const int* ready, int blk, int need) {
+  const uint32_t addr = smem_u32(ready + blk);
+  uint32_t v;
+  do {
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  } while ((int)v < need);
+}
+__device__ __forceinline__ void sym_release_block(int* ready, int blk, int value) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(ready + blk)), "r"(value) : "memory");
+}
+
+// Result of the fp32 evaluation of one unordered pair: padded start positions of the two intervals
+// (already redirected to the scratch word when the direction is off the fast path), the 2h-ones mask.
+struct SymStep {
+  int ps_i, ps_j;
+  uint32_t mask;
+  bool slow_i, slow_j;
+};
+
+// Pure arithmetic (no shared-memory access): the compiler interleaves two of these.
+// BOTH: evaluate both directions; otherwise only the lane's own.
+template <bool TORUS, bool FULL_FOV, int RC, bool BOTH>
+__device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, float xi, float yi, float thb_i,
+                                            const SymConsts& c) {
+  using K = PairK<RC>;
+  SymStep r;
   float dx = o.x - xi, dy = o.y - yi;
   if (TORUS) {                                               // vf_supcalc.py:70-83
     if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
     if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
-  const bool valid = (i < N) & (j < N) & (d2 > 0.0f);       // padding agents, coincident positions (vf_supcalc.py:57)
-  // shared by both directions: half width h = floor(atan(r / d) * R / 2pi) and its guard band
-  const float MAGIC = 12582912.0f;
-  const float q = radius * rsqrt_approx(d2);
-  const float y = fmaf(atan_unit(q), a.y_scale, -0.5f);
-  const float yr = y + MAGIC;
-  const int h = __float_as_int(yr) - 0x4B400000;
-  const bool flag_h = !(q <= 1.0f) | (fabsf(y - (yr - MAGIC)) > fmaf(y, a.thr_h1, a.thr_h0));
-  // absolute bearing of j seen from i (screen coordinates, y down)
-  const float phi = atan2_fast(-dy, dx);
-  const int stride_b = 4 * Np;
-  sym_side(a, sh, wrap_pi(phi - thi), h, flag_h, valid, rows_b + 4 * i, stride_b, i, j);
-  if (BOTH) {
-    if (SYNC) __syncwarp();
-    sym_side(a, sh, wrap_pi((phi - o.z) + 3.14159265358979324f), h, flag_h, valid, rows_b + 4 * j, stride_b, j, i);
-    if (SYNC) __syncwarp();
+  // ---- half width h = floor(atan(r/d) * R/2pi) (vf_supcalc.py:96-99, :114-117), shared by both directions.
+  //      Three-term series in q = r/d (exact to fp32 for h <= 16, i.e. q < 0.09); larger q -> slow path. ----
+  const float rs = rsqrt_approx(d2);
+  const float qs = rs * c.rS;                                // q * R/2pi
+  const float zs = qs * qs;
+  float p = fmaf(zs, c.c5s, c.c3s);
+  p = fmaf(p, zs, 1.0f);
+  const float y = fmaf(qs, p, -0.5f);
+  const float yr = y + kMagic;
+  const uint32_t hraw = __float_as_uint(yr);                 // h + kMagicBits
+  const bool slow_h = !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);   // also d2 == 0 (NaN)
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask) : "r"(2u * hraw - 2u * (uint32_t)kMagicBits));   // 2h ones
+  const int bh = K::k_bias(a) + kMagicBits - (int)hraw;      // ps = rint(t) + k_off + 32 - h
+  // ---- absolute bearing, both directions ----
+  float pi_abs, pj_abs;
+  sym_bearing<RC>(a, dx, dy, c.a6, pi_abs, pj_abs);
+  const float phi_i = __uint_as_float(__float_as_uint(pi_abs) | (~__float_as_uint(dy) & 0x80000000u));   // copysign(., -dy)
+  r.slow_i = slow_h;
+  const int ps_i = sym_side_k<RC>(a, phi_i, thb_i, bh, r.slow_i);
+  bool draw_i = !r.slow_i;
+  if (!FULL_FOV) {
+    const int pe = ps_i + 2 * ((int)hraw - kMagicBits);
+    draw_i &= ((unsigned)(ps_i - a.fov0p) < a.span) | ((unsigned)(pe - a.fov0p) < a.span);   // vf_supcalc.py:119
   }
+  r.ps_i = draw_i ? ps_i : c.scratch_pos;
+  r.slow_j = false;
+  r.ps_j = c.scratch_pos;
+  if (BOTH) {
+    const float phi_j = __uint_as_float(__float_as_uint(pj_abs) | (__float_as_uint(dy) & 0x80000000u));
+    r.slow_j = slow_h;
+    const int ps_j = sym_side_k<RC>(a, phi_j, o.z, bh, r.slow_j);
+    bool draw_j = !r.slow_j;
+    if (!FULL_FOV) {
+      const int pe = ps_j + 2 * ((int)hraw - kMagicBits);
+      draw_j &= ((unsigned)(ps_j - a.fov0p) < a.span) | ((unsigned)(pe - a.fov0p) < a.span);
+    }
+    r.ps_j = draw_j ? ps_j : c.scratch_pos;
+  }
+  return r;
+}
+
+// The one or two row words an interval of <= 32 bins touches, as an explicit load / store pair so
+// that independent rows can be in flight together.
+struct SymRmw {
+  uint32_t wa, wa1, lo, hi, v0, v1;
+};
+__device__ __forceinline__ void rmw_load(SymRmw& w, uint32_t row, uint32_t stride_b, int ps, uint32_t m) {
+  w.wa = row + (uint32_t)(ps >> 5) * stride_b;
+  w.wa1 = w.wa + stride_b;
+  w.lo = __funnelshift_l(0u, m, ps);
+  w.hi = __funnelshift_l(m, 0u, ps);
+  w.v0 = lds_u32(w.wa);
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.shared.u32 %0, [%1];\n}" : "=r"(w.v1) : "r"(w.wa1), "r"(w.hi));
+}
+__device__ __forceinline__ void rmw_store(const SymRmw& w) {
+  sts_u32(w.wa, w.v0 | w.lo);
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(w.wa1), "r"(w.v1 | w.hi), "r"(w.hi));
 }
 
 size_t vf_sym_smem_bytes(int Np, int W) {
-  return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + 2) * Np + 2 * sizeof(uint32_t) * kSymQueueCap + 16;
+  return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + 3) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
+         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + sizeof(int) * (size_t)(Np / 32) + 16;
 }
 
-template <bool TORUS>
+template <bool TORUS, bool FULL_FOV, int RC>
 __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs a, int Np) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using K = PairK<RC>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   SymShared sh;
   sh.ag = reinterpret_cast<float4*>(smem_raw);
   sh.rows = reinterpret_cast<uint32_t*>(sh.ag + Np);
-  sh.queue = sh.rows + (size_t)(a.W + 2) * Np;
-  sh.qcount = reinterpret_cast<int*>(sh.queue + 2 * kSymQueueCap);
-  unsigned char* rows_b = reinterpret_cast<unsigned char*>(sh.rows);
+  sh.queue = sh.rows + (size_t)(a.W + 3) * Np;
+  sh.warpq = sh.queue + 2 * kSymQueueCap;
+  sh.ready = reinterpret_cast<int*>(sh.warpq + kSymWarpQ * (Np / 64));
+  sh.qcount = sh.ready + (Np / 32);
+  sh.Np = Np; sh.N = a.N;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x;
@@ -138,15 +304,59 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
   const float4* rep_in = a.rec_in + (size_t)b * N;
   const float* th_in = a.theta + (size_t)b * N;
 
+  // ---- stage the replicate: (x, y, heading in bins of the linspace grid, radius) ----
   for (int j = tid; j < Np; j += T) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (j < N) { const float4 r4 = rep_in[j]; v = make_float4(r4.x, r4.y, th_in[j], r4.z); }
+    float4 v;
+    if (j < N) {
+      const float4 r4 = rep_in[j];
+      double th = fmod((double)th_in[j], ABM_TWO_PI_D);
+      if (th < 0.0) th += ABM_TWO_PI_D;
+      const double inv = RC ? PairK<RC>::kInv : (double)a.inv_step;
+      v = make_float4(r4.x, r4.y, (float)(th * inv), r4.z);
+    } else {   // padding: far away (half width 0), all distinct
+      v = make_float4(-1.0e6f - 4096.0f * (float)(j - N), -1.0e6f, 0.f, a.sym_radius);
+    }
     sh.ag[j] = v;
   }
-  for (int w = tid; w < (a.W + 2) * Np; w += T) sh.rows[w] = 0u;
-  if (tid == 0) *sh.qcount = 0;
+  for (int w = tid; w < (a.W + 3) * Np; w += T) sh.rows[w] = 0u;
+  if (tid == 0) sh.qcount[0] = 0;
+  if (tid < P) sh.ready[tid] = 0;
   __syncthreads();
-  const float radius = sh.ag[0].w;            // all radii are equal (kernel precondition)
+
+  const float S = K::y_scale(a);
+  SymConsts c;
+  c.rS = a.sym_radius * S;
+  c.c3s = -1.0f / (3.0f * S * S);
+  c.c5s = pin_f(1.0f / (5.0f * S * S * S * S));
+  c.a6 = pin_f(K::ac(a, 6));
+  c.scratch_pos = 32 * (a.W + 2);
+  const uint32_t ag_s = smem_u32(sh.ag), rows_s = smem_u32(sh.rows);
+  const uint32_t stride_b = 4u * (uint32_t)Np;
+
+  uint32_t* wq = sh.warpq + kSymWarpQ * warp;
+  int wcount = 0;                              // entries in the warp's queue (warp-uniform)
+
+  // ---- diagonal blocks first (nobody else touches them yet): two per warp, every lane draws its own side of
+  //      {l, l ^ s} ----
+  for (int d = 0; d < 2; ++d) {
+    const int I = 2 * warp + d;
+    const int i = (I << 5) + lane;
+    const float4 me = sh.ag[i];
+    const uint32_t rec_i0 = ag_s + 16u * (uint32_t)i, row_i = rows_s + 4u * (uint32_t)i;
+#pragma unroll 1
+    for (int s = 1; s < 32; ++s) {
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, false>(a, lds_f4(rec_i0 ^ (16u * s)), me.x, me.y, me.z, c);
+      SymRmw ai;
+      rmw_load(ai, row_i, stride_b, A.ps_i, A.mask);
+      rmw_store(ai);
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, A.slow_i,
+                          (uint32_t)i | ((uint32_t)(i ^ s) << 10) | (1u << 20));
+    }
+  }
+  if (wcount) { sym_flush<TORUS, RC>(a, sh, wq, wcount, lane); wcount = 0; }
+  __syncwarp();
+  __threadfence_block();
+  if (lane < 2) sym_release_block(sh.ready, 2 * warp + lane, 1);
 
   // ---- off-diagonal block pairs: round-robin tournament (circle method) over P blocks ----
   const int m = P - 1;
@@ -154,39 +364,53 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
     int I, J;
     if (warp == 0) { I = m; J = round; }
     else { I = (round + warp) % m; J = (round - warp + m) % m; }
-    const int i = (I << 5) + lane;
+    sym_wait_block(sh.ready, lane & 1 ? J : I, round + 1);   // odd lanes watch J, even lanes I
+    __syncwarp();
+    const int i = (I << 5) + lane, j0 = (J << 5) + lane;
     const float4 me = sh.ag[i];
-#pragma unroll 2
-    for (int s = 0; s < 32; ++s) {
-      const int j = (J << 5) + ((lane + s) & 31);
-      sym_pair<TORUS, true, false>(a, sh, Np, N, i, j, me.x, me.y, me.z, radius, rows_b);
+    const uint32_t rec_j0 = ag_s + 16u * (uint32_t)j0, row_j0 = rows_s + 4u * (uint32_t)j0;
+    const uint32_t row_i = rows_s + 4u * (uint32_t)i;
+    // two steps per iteration: both evaluations are independent arithmetic (instruction-level parallelism for the
+    // 4 warps per scheduler this kernel runs with)
+    float4 oA = lds_f4(rec_j0), oB = lds_f4(rec_j0 ^ 16u);
+#pragma unroll 1
+    for (int s = 0; s < 32; s += 2) {
+      const uint32_t sn = (uint32_t)(s + 2) & 31u;          // prefetch the next two partner records (wraps harmlessly)
+      const float4 nA = lds_f4(rec_j0 ^ (16u * sn)), nB = lds_f4(rec_j0 ^ (16u * sn + 16u));
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, oA, me.x, me.y, me.z, c);
+      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true>(a, oB, me.x, me.y, me.z, c);
+      // draws of step s, then of step s + 1 (lane l's partner row of step s + 1 is lane l ^ 1's of step s); inside a
+      // step the own row and the partner row are different rows for every lane of the warp: both in flight together
+      SymRmw wi, wj;
+      rmw_load(wi, row_i, stride_b, A.ps_i, A.mask);
+      rmw_load(wj, row_j0 ^ (4u * s), stride_b, A.ps_j, A.mask);
+      rmw_store(wi);
+      rmw_store(wj);
+      rmw_load(wi, row_i, stride_b, B.ps_i, B.mask);
+      rmw_load(wj, row_j0 ^ (4u * s + 4u), stride_b, B.ps_j, B.mask);
+      rmw_store(wi);
+      rmw_store(wj);
+      // ---- off the fast path (~1 % of the directions): into the warp's queue ----
+      const bool any = A.slow_i | A.slow_j | B.slow_i | B.slow_j;
+      const uint32_t flags = (A.slow_i ? 1u : 0u) | (A.slow_j ? 2u : 0u) | (B.slow_i ? 4u : 0u) | (B.slow_j ? 8u : 0u);
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, any, (uint32_t)i | ((uint32_t)(j0 ^ s) << 10) | (flags << 20));
+      oA = nA; oB = nB;
     }
-    __syncthreads();
-  }
-  // ---- diagonal blocks: two per warp ----
-  for (int d = 0; d < 2; ++d) {
-    const int I = 2 * warp + d;
-    const int i = (I << 5) + lane;
-    const float4 me = sh.ag[i];
-    for (int s = 1; s < 16; ++s) {
-      const int j = (I << 5) + ((lane + s) & 31);
-      sym_pair<TORUS, true, true>(a, sh, Np, N, i, j, me.x, me.y, me.z, radius, rows_b);
-    }
-    {   // s = 16: {l, l + 16} would be visited from both ends -> each lane draws its own side only
-      const int j = (I << 5) + ((lane + 16) & 31);
-      sym_pair<TORUS, false, false>(a, sh, Np, N, i, j, me.x, me.y, me.z, radius, rows_b);
-    }
+    if (wcount) { sym_flush<TORUS, RC>(a, sh, wq, wcount, lane); wcount = 0; }
+    __syncwarp();
+    __threadfence_block();
+    if (lane < 2) sym_release_block(sh.ready, lane ? J : I, round + 2);
   }
   __syncthreads();
 
   // ---- deferred pairs: fp64, the reference's own operation sequence ----
   unsigned n_mismatch = 0;
   {
-    const int nq = min(*sh.qcount, kSymQueueCap);
+    const int nq = min(sh.qcount[0], kSymQueueCap);
     for (int e = tid; e < nq; e += T) {
       const uint32_t q0 = sh.queue[2 * e], q1 = sh.queue[2 * e + 1];
       const int f = (int)(q0 >> 16), o = (int)(q0 & 0xffffu);
-      n_mismatch += sym_exact_and_draw(a, sh.rows + Np + f, Np, rep_in[f], th_in[f], rep_in[o], (int)(q1 >> 16),
+      n_mismatch += sym_exact_and_draw(a, sh.rows + Np + f, Np, rep_in[f], th_in[f], rep_in[o], (int)(short)(q1 >> 16),
                                        (int)(short)(q1 & 0xffffu));
     }
   }
@@ -194,34 +418,44 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
   {
     const unsigned nm = __reduce_add_sync(0xffffffffu, n_mismatch);
     if (lane == 0 && nm) atomicAdd(&a.counters[2], (unsigned long long)nm);
-    if (tid == 0 && *sh.qcount) atomicAdd(&a.counters[0], (unsigned long long)*sh.qcount);
+    if (tid == 0 && sh.qcount[0]) atomicAdd(&a.counters[0], (unsigned long long)sh.qcount[0]);
   }
 
   // ---- epilogue: one agent per thread and pass (bank == lane) ----
-  for (int i = tid; i < N; i += T) vf_agent_epilogue<TORUS>(a, b, i, i, sh.rows + i, Np, rep_in[i], sh.ag[i].z);
+  for (int i = tid; i < N; i += T) vf_agent_epilogue<TORUS>(a, b, i, i, sh.rows + i, Np, rep_in[i], th_in[i]);
 }
 
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit) {
   if (!uniform_r || cull) return false;
   if (a.tile_begin != 0 || a.tile_count != a.N) return false;
   const int Np = (a.N + 63) / 64 * 64;
-  if (Np > 1024 || Np > 65535) return false;   // 16 warps at most; queue entries hold 16-bit agent indices
+  if (Np > 1024) return false;   // 16 warps at most; queue entries hold 16-bit agent indices
   return vf_sym_smem_bytes(Np, a.W) <= smem_limit;
+}
+
+template <bool TORUS, bool FULL_FOV, int RC>
+static void launch_sym_variant(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(vf_step_sym_kernel<TORUS, FULL_FOV, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  vf_step_sym_kernel<TORUS, FULL_FOV, RC><<<a.B, threads, smem, stream>>>(a, Np);
+}
+
+template <bool TORUS>
+static void launch_sym_fov(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
+  if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200>(a, Np, threads, smem, stream);
+  else if (a.full_fov) launch_sym_variant<TORUS, true, 0>(a, Np, threads, smem, stream);
+  else launch_sym_variant<TORUS, false, 0>(a, Np, threads, smem, stream);
 }
 
 void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream) {
   const int Np = (a.N + 63) / 64 * 64;
   const int threads = 32 * (Np / 64);
   const size_t smem = vf_sym_smem_bytes(Np, a.W);
-  static size_t configured[2] = {0, 0};
-  const int t = a.boundary == 1 ? 1 : 0;
-  if (smem > configured[t]) {
-    if (t) cudaFuncSetAttribute(vf_step_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else cudaFuncSetAttribute(vf_step_sym_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured[t] = smem;
-  }
-  if (t) vf_step_sym_kernel<true><<<a.B, threads, smem, stream>>>(a, Np);
-  else vf_step_sym_kernel<false><<<a.B, threads, smem, stream>>>(a, Np);
+  if (a.boundary == 1) launch_sym_fov<true>(a, Np, threads, smem, stream);
+  else launch_sym_fov<false>(a, Np, threads, smem, stream);
 }
 
 }  // namespace abm

@@ -254,24 +254,32 @@ def test_fixup_counters_and_fp32_only_mode(built_lib):
     assert 0 < cnt["fp64_pairs"] < 0.02 * pairs          # a small fraction goes through fp64
     assert cnt["fp32_fp64_differ"] <= cnt["fp64_pairs"]
     diff_agents = int((fe != ff).any(axis=-1).sum())
-    # an fp32-only field may differ from the exact one only by edges moved by ONE bin: every
-    # differing bin is isolated (its ring neighbours agree) and sits on an edge of the exact field
+    # an fp32-only field may differ from the exact one only by interval ends moved by ONE bin: every
+    # differing bin is isolated (its ring neighbours agree) and sits on an end of one of the focal
+    # agent's per-object intervals (oracle), whether or not that end is an edge of the union field
     d = (fe != ff)
     assert not (d & np.roll(d, 1, axis=-1)).any(), "differences wider than one bin"
-    edges = fe != np.roll(fe, 1, axis=-1)
-    near_edge = edges | np.roll(edges, -1, axis=-1)
-    assert not (d & ~near_edge).any(), "difference away from an edge"
+    cfg = rs.VFConfig(R=R, width=W, height=W)
+    for b, i in zip(*np.nonzero(d.any(axis=-1))):
+        iv = rs.vf_intervals(x[b].astype(np.float64), y[b].astype(np.float64), 10.0, th[b].astype(np.float64), int(i), cfg)
+        ps, pe = iv["ps"][iv["valid"]], iv["pe"][iv["valid"]]
+        ends = np.concatenate([ps - 1, ps, pe - 1, pe, (pe + 1)[pe >= R - 1]]) % R
+        allowed = np.zeros(R, bool); allowed[ends] = True
+        bad = d[b, i][::-1] & ~allowed                      # stored fields are flipped (vf_supcalc.py:134)
+        assert not bad.any(), f"replicate {b} agent {i}: difference away from an interval end at bins {np.nonzero(bad)[0]}"
     assert diff_agents <= 0.2 * B * N
     print(f"fp64 pairs {cnt['fp64_pairs']} of {pairs} ({cnt['fp64_pairs'] / pairs:.2e}); fp32/fp64 index "
           f"differences {cnt['fp32_fp64_differ']}; agents whose fp32-only field differs: {diff_agents} of {B * N}")
     exact.close(); fast.close()
 
 
-def test_spatial_sort_is_invisible(built_lib):
-    """The internal Morton ordering (refreshed every few steps) must not change any result:
-    sorted and unsorted engines agree bit for bit after many steps, in the caller's agent order,
-    including fields, terms and per-agent overrides set before and after the first sort."""
+def test_spatial_sort_is_invisible(built_lib, monkeypatch):
+    """The internal Morton ordering (refreshed every few steps; used by the one-thread-per-focal-agent
+    kernel) must not change any result: sorted and unsorted engines agree bit for bit after many
+    steps, in the caller's agent order, including fields, terms and per-agent overrides set before
+    and after the first sort."""
     from abm_b200 import VFEngine
+    monkeypatch.setenv("ABM_VF_KERNEL", "onesided")
     rng = np.random.default_rng(41)
     B, N, R, W = 3, 300, 1200, 900.0
     x, y, th, v = _random_scene(rng, B, N, W)
@@ -294,3 +302,42 @@ def test_spatial_sort_is_invisible(built_lib):
     assert np.array_equal(res[False][3], np.tile(np.arange(N, dtype=np.int32), (B, 1)))
     assert not np.array_equal(res[True][3], res[False][3])
     assert np.array_equal(np.sort(res[True][3], axis=1), res[False][3])
+
+
+@pytest.mark.parametrize("B,N,R,boundary,fov_ratio", [
+    (3, 1024, 1200, "walls", 1.0),      # the benchmark shape: no padding, compile-time R
+    (2, 300, 1200, "infinite", 1.0),    # padded blocks, torus
+    (2, 200, 1201, "walls", 1.0),       # odd R (run-time constants)
+    (2, 130, 640, "walls", 0.5),        # limited FOV, small R
+    (5, 40, 1200, "walls", 1.0),        # a single block pair
+    (1, 700, 2400, "infinite", 0.75),   # large R
+])
+def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, boundary, fov_ratio):
+    """The two step kernels (every unordered pair once / one thread per focal agent) are independent
+    implementations of the same step; with the fp64 re-evaluation on, both must produce the exact
+    fields, so they agree bit for bit -- fields, terms and new state -- also over several steps,
+    crowded scenes (wide intervals, overlapping agents) included."""
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(1000 + N)
+    W = 60.0 * np.sqrt(N)                     # crowded: neighbours at a few radii
+    x, y, th, v = _random_scene(rng, B, N, W)
+    x[0, 1], y[0, 1] = x[0, 0], y[0, 0]       # coincident pair (vf_supcalc.py:57)
+    x[0, 3], y[0, 3] = x[0, 2] + 3.0, y[0, 2] # overlapping pair (d < r)
+    fov = (-fov_ratio * np.pi, fov_ratio * np.pi)
+    res = {}
+    for kern in ("onesided", "symmetric"):
+        monkeypatch.setenv("ABM_VF_KERNEL", kern)
+        eng = VFEngine(B, N, resolution=R, width=W, height=W, boundary=boundary, fov=fov, keep_fields=True,
+                       keep_terms=True, spatial_sort=False)
+        eng.set_params(); eng.set_state(x, y, th, v, 10.0)
+        eng.step(1)
+        f1, t1 = eng.fields_packed().copy(), eng.terms().copy()
+        eng.step(3)
+        res[kern] = (f1, t1, eng.fields_packed(), eng.terms(), eng.get_state(), eng.counters())
+        eng.close()
+    a, b = res["onesided"], res["symmetric"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    for k in ("x", "y", "theta", "vel"):
+        assert np.array_equal(a[4][k], b[4][k]), k
+    print("fp64 pairs onesided / symmetric:", a[5]["fp64_pairs"], b[5]["fp64_pairs"])
