@@ -56,7 +56,7 @@ static __device__ __noinline__ void vf_draw_general(const VFKernelArgs& a, uint3
 // difference).  CULL: skip pairs beyond the distance at which the half width becomes 0.
 template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>
 __global__ void __launch_bounds__(kMaxThreads, 3)
-vf_step_kernel(const VFKernelArgs a) {
+vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
   using K = PairK<RC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* recs = reinterpret_cast<float4*>(smem_raw);                       // [2][kRecTile]

@@ -292,6 +292,45 @@ __device__ __forceinline__ void vf_draw(uint32_t* f, int stride, int R, int fov0
   if (pe > ps) set_range<ATOMIC>(f, stride, ps, pe);                        // :129
 }
 
+// The same drawing rule on a row addressed in the SHARED state space (32-bit address of real word 0,
+// byte stride between the words of a row), with fire-and-forget reductions: for code that is not
+// inlined into the kernel (a generic pointer would turn every atomic into a generic-space ATOM).
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t m) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(m) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void set_range_shared(uint32_t row, uint32_t stride_b, int a, int b) {
+  const int w0 = a >> 5, w1 = (b - 1) >> 5;
+  const uint32_t m0 = 0xffffffffu << (a & 31);
+  const uint32_t m1 = 0xffffffffu >> ((32 - b) & 31);
+  if (w0 == w1) {
+    red_or_shared(row + (uint32_t)w0 * stride_b, m0 & m1);
+  } else {
+    red_or_shared(row + (uint32_t)w0 * stride_b, m0);
+    for (int w = w0 + 1; w < w1; ++w) red_or_shared(row + (uint32_t)w * stride_b, 0xffffffffu);
+    red_or_shared(row + (uint32_t)w1 * stride_b, m1);
+  }
+}
+__device__ __forceinline__ void vf_draw_shared(uint32_t row, uint32_t stride_b, int R, int fov0, int fov1, int k, int h) {
+  int ps = k - h, pe = k + h;
+  const bool vis = (fov0 < ps && ps < fov1) || (fov0 < pe && pe < fov1);   // :119
+  if (!vis || h <= 0) return;
+  if (ps < 0) {                                                             // :122-124
+    set_range_shared(row, stride_b, max(R + ps, 0), R);
+    ps = 0;
+  }
+  if (pe >= R) {                                                            // :125-127
+    const int e = min(pe - (R - 1), R);
+    if (e > 0) set_range_shared(row, stride_b, 0, e);
+    pe = R;
+  }
+  if (pe > ps) set_range_shared(row, stride_b, ps, pe);                     // :129
+}
+
 // Hot-path drawing into a PADDED private row: word 0 of the padded row holds the virtual bins
 // [-32, 0), words 1.. the real bins, and one more word follows the last real word, so an
 // interval that leaves [0, R) by at most 32 bins is drawn without any wrap logic; the padding

@@ -30,7 +30,6 @@
 namespace abm {
 
 constexpr int kSymQueueCap = 3072;   // fp64 queue: ~0.2 % of the 1M ordered pairs of a 1024-agent replicate
-constexpr int kSymWarpQ = 64;        // per-warp queue of lane entries with directions off the fast path
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: low mantissa bits of x + kMagic = rint(x)
 constexpr int kMagicBits = 0x4B400000;
 
@@ -49,19 +48,19 @@ struct SymShared {
   float4* ag;          // [Np] (x, y, heading in bins, radius); padding agents beyond N are far away
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
-  uint32_t* warpq;     // [warps][kSymWarpQ]  per-warp entries: own agent | partner of the even step << 10 | 4 flags << 20
+  int* wcounts;        // [warps] entries in every warp's region of the slow queue (global memory)
   int* qcount;         // [0]: fp64 queue
-  int* ready;          // [P] number of tournament rounds (+1 for the diagonal phase) completed on each block
+  uint32_t ag_s, rows_s, queue_s, qcount_s;   // shared-space addresses of the above (code that is not inlined)
   int Np, N;
 };
 
 // Out-of-line fp64 evaluation + atomic draw of one ordered pair.  Returns 1 if the fp64 indices
 // differ from the fp32 ones.
-static __device__ __noinline__ unsigned sym_exact_and_draw(const VFKernelArgs& a, uint32_t* row, int stride, float4 f4,
-                                                           float fth, float4 o, int k32, int h32) {
+static __device__ __noinline__ unsigned sym_exact_and_draw(const VFKernelArgs& a, uint32_t row_s, uint32_t stride_b,
+                                                           float4 f4, float fth, float4 o, int k32, int h32) {
   const FocalExact fe = vf_focal_exact(f4.x, f4.y, f4.z, fth);
   const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, a.R, a.lin_step);
-  if (pe.valid) vf_draw<true>(row, stride, a.R, a.fov_px0, a.fov_px1, pe.k, pe.h);
+  if (pe.valid) vf_draw_shared(row_s, stride_b, a.R, a.fov_px0, a.fov_px1, pe.k, pe.h);
   return (pe.valid && ((pe.k != k32) | (pe.h != h32))) ? 1u : 0u;
 }
 
@@ -108,10 +107,11 @@ __device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, float phi, floa
 // guard-band hits are queued for fp64, anything else visible is drawn by the general rule (wide
 // intervals, wrap quirks) with atomics.
 template <bool TORUS, int RC>
-static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, const SymShared& sh, int f, int o) {
+static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, uint32_t ag_s, uint32_t rows_s, uint32_t queue_s,
+                                                  uint32_t qcount_s, int Np, int f, int o) {
   using K = PairK<RC>;
-  if ((f >= sh.N) | (o >= sh.N)) return;                              // padding agents
-  const float4 fa = sh.ag[f], oa = sh.ag[o];
+  if ((f >= a.N) | (o >= a.N)) return;                                // padding agents
+  const float4 fa = lds_f4(ag_s + 16u * (uint32_t)f), oa = lds_f4(ag_s + 16u * (uint32_t)o);
   if ((fa.x == oa.x) & (fa.y == oa.y)) return;                        // vf_supcalc.py:57
   float dx = oa.x - fa.x, dy = oa.y - fa.y;
   if (TORUS) {
@@ -128,74 +128,62 @@ static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, const S
   sym_bearing<RC>(a, dx, dy, K::ac(a, 6), pi_abs, pj_abs);
   const int R = RC ? RC : a.R;
   const int k = sym_side_k<RC>(a, copysignf(pi_abs, -dy), fa.z, K::k_bias(a), flagged) - 32;   // real bin index
-  uint32_t* row = sh.rows + sh.Np + f;                                // real word 0
+  const uint32_t stride_b = 4u * (uint32_t)Np;
+  const uint32_t row_s = rows_s + stride_b + 4u * (uint32_t)f;        // real word 0
   if (flagged) {
-    const int slot = atomicAdd(&sh.qcount[0], 1);                     // keeps counting past the capacity
+    const int slot = (int)atom_add_shared(qcount_s, 1u);              // keeps counting past the capacity
     if (slot < kSymQueueCap) {
-      sh.queue[2 * slot] = ((uint32_t)f << 16) | (uint32_t)o;
-      sh.queue[2 * slot + 1] = ((uint32_t)k << 16) | ((uint32_t)h & 0xffffu);
+      sts_u32(queue_s + 8u * (uint32_t)slot, ((uint32_t)f << 16) | (uint32_t)o);
+      sts_u32(queue_s + 8u * (uint32_t)slot + 4u, ((uint32_t)k << 16) | ((uint32_t)h & 0xffffu));
     } else {
       const size_t g = (size_t)blockIdx.x * a.N;
-      const unsigned diff = sym_exact_and_draw(a, row, sh.Np, a.rec_in[g + f], a.theta[g + f], a.rec_in[g + o], k, h);
+      const unsigned diff = sym_exact_and_draw(a, row_s, stride_b, a.rec_in[g + f], a.theta[g + f], a.rec_in[g + o], k, h);
       atomicAdd(&a.counters[1], 1ull);
       if (diff) atomicAdd(&a.counters[2], 1ull);
     }
   } else {
-    vf_draw<true>(row, sh.Np, R, a.fov_px0, a.fov_px1, k, h);
+    vf_draw_shared(row_s, stride_b, R, a.fov_px0, a.fov_px1, k, h);
   }
 }
 
-// Work the warp's queue off: every lane takes one entry and walks through its flagged directions
-// (flag bit 0 / 1: own agent sees the partner of the even step / is seen by it, bits 2 / 3: the same
-// for the odd step, whose partner index differs in bit 0).  Draws are atomic: two lanes may hold
-// entries of the same row.  n is warp-uniform.
+// One entry of the slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own agent
+// sees the partner of the even step / is seen by it, bits 2 / 3: the same for the odd step, whose partner index
+// differs in bit 0.  Walk through the flagged directions (draws are atomic).
 template <bool TORUS, int RC>
-static __device__ __noinline__ void sym_flush(const VFKernelArgs& a, const SymShared& sh, const uint32_t* wq, int n,
-                                              int lane) {
-  __syncwarp();
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    const int e = e0 + lane;
-    const uint32_t ent = (e < n) ? wq[e] : 0u;
-    uint32_t flags = ent >> 20;
-    const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
-    while (flags) {
-      const int bit = __ffs(flags) - 1;
-      flags &= flags - 1;
-      const int j = jA ^ (bit >> 1);
-      sym_slow_side<TORUS, RC>(a, sh, (bit & 1) ? j : i, (bit & 1) ? i : j);
-    }
+__device__ __forceinline__ void sym_slow_entry(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
+  uint32_t flags = ent >> 20;
+  const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
+  while (flags) {
+    const int bit = __ffs(flags) - 1;
+    flags &= flags - 1;
+    const int j = jA ^ (bit >> 1);
+    sym_slow_side<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (bit & 1) ? j : i, (bit & 1) ? i : j);
   }
-  __syncwarp();
+}
+template <bool TORUS, int RC>
+static __device__ __noinline__ void sym_slow_now(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
+  sym_slow_entry<TORUS, RC>(a, sh, ent);
 }
 
-// Append this lane's entry (if it has flagged directions) to the warp's queue; the queue is worked
-// off as soon as it could overflow with the next append.  Called by the converged warp.
+// Append this lane's entry (if it has flagged directions) to the warp's region of the slow queue in global memory
+// (fire-and-forget stores; the queue is worked off by the whole CTA after the last round, when every row is quiescent
+// and all lanes are busy).  Region full (crowded scene): on the spot.  Called by the converged warp.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared& sh, uint32_t* wq, int& wcount, int lane,
-                                         bool any, uint32_t entry) {
+                                         int i, int jA, bool f0, bool f1, bool f2, bool f3) {
+  const bool any = f0 | f1 | f2 | f3;
   const uint32_t bal = __ballot_sync(0xffffffffu, any);
   if (bal) {                                                   // warp-uniform
-    if (any) wq[wcount + __popc(bal & ((1u << lane) - 1u))] = entry;
-    wcount += __popc(bal);
-    if (wcount > kSymWarpQ - 32) {
-      sym_flush<TORUS, RC>(a, sh, wq, wcount, lane);
-      wcount = 0;
+    const uint32_t flags = (f0 ? 1u : 0u) | (f1 ? 2u : 0u) | (f2 ? 4u : 0u) | (f3 ? 8u : 0u);
+    const uint32_t entry = (uint32_t)i | ((uint32_t)jA << 10) | (flags << 20);
+    if (wcount + 32 <= a.slowq_cap_w) {
+      if (any) wq[wcount + __popc(bal & ((1u << lane) - 1u))] = entry;
+      wcount += __popc(bal);
+    } else {
+      if (any) sym_slow_now<TORUS, RC>(a, sh, entry);
+      __syncwarp();
     }
   }
-}
-
-// Tournament dataflow: a block may be worked on in round r only after its round r - 1 user is done
-// with it.  Instead of a CTA-wide barrier per round, every block carries a counter of completed
-// rounds; warps wait only for their own two blocks.
-__device__ __forceinline__ void sym_wait_block(const int* ready, int blk, int need) {
-  const uint32_t addr = smem_u32(ready + blk);
-  uint32_t v;
-  do {
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  } while ((int)v < need);
-}
-__device__ __forceinline__ void sym_release_block(int* ready, int blk, int value) {
-  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(ready + blk)), "r"(value) : "memory");
 }
 
 // Result of the fp32 evaluation of one unordered pair: padded start positions of the two intervals
@@ -260,41 +248,34 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   return r;
 }
 
-// The one or two row words an interval of <= 32 bins touches, as an explicit load / store pair so
-// that independent rows can be in flight together.
-struct SymRmw {
-  uint32_t wa, wa1, lo, hi, v0, v1;
-};
-__device__ __forceinline__ void rmw_load(SymRmw& w, uint32_t row, uint32_t stride_b, int ps, uint32_t m) {
-  w.wa = row + (uint32_t)(ps >> 5) * stride_b;
-  w.wa1 = w.wa + stride_b;
-  w.lo = __funnelshift_l(0u, m, ps);
-  w.hi = __funnelshift_l(m, 0u, ps);
-  w.v0 = lds_u32(w.wa);
-  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.shared.u32 %0, [%1];\n}" : "=r"(w.v1) : "r"(w.wa1), "r"(w.hi));
-}
-__device__ __forceinline__ void rmw_store(const SymRmw& w) {
-  sts_u32(w.wa, w.v0 | w.lo);
-  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(w.wa1), "r"(w.v1 | w.hi), "r"(w.hi));
+// OR an interval of <= 32 bins into the one or two row words it touches with shared-memory reductions (RED.OR runs
+// at the rate of a plain shared store: one wavefront per conflict-free warp instruction, measured on B200 --
+// scratch/red_bench.cu).  Nobody has to own a row, draws need no ordering, and the second word is written
+// unconditionally (its mask is usually 0): that is cheaper than a predicate.
+__device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps, uint32_t m) {
+  const uint32_t wa = row + (uint32_t)(ps >> 5) * stride_b;
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(__funnelshift_l(0u, m, ps)));
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + stride_b), "r"(__funnelshift_l(m, 0u, ps)));
 }
 
 size_t vf_sym_smem_bytes(int Np, int W) {
   return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + 3) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
-         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + sizeof(int) * (size_t)(Np / 32) + 16;
+         sizeof(int) * (size_t)(Np / 64) + 16;
 }
 
 template <bool TORUS, bool FULL_FOV, int RC>
-__global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs a, int Np) {
+__global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_constant__ VFKernelArgs a, int Np) {
   using K = PairK<RC>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SymShared sh;
   sh.ag = reinterpret_cast<float4*>(smem_raw);
   sh.rows = reinterpret_cast<uint32_t*>(sh.ag + Np);
   sh.queue = sh.rows + (size_t)(a.W + 3) * Np;
-  sh.warpq = sh.queue + 2 * kSymQueueCap;
-  sh.ready = reinterpret_cast<int*>(sh.warpq + kSymWarpQ * (Np / 64));
-  sh.qcount = sh.ready + (Np / 32);
+  sh.wcounts = reinterpret_cast<int*>(sh.queue + 2 * kSymQueueCap);
+  sh.qcount = sh.wcounts + (Np / 64);
   sh.Np = Np; sh.N = a.N;
+  sh.ag_s = smem_u32(sh.ag); sh.rows_s = smem_u32(sh.rows); sh.queue_s = smem_u32(sh.queue);
+  sh.qcount_s = smem_u32(sh.qcount);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x;
@@ -320,7 +301,6 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
   }
   for (int w = tid; w < (a.W + 3) * Np; w += T) sh.rows[w] = 0u;
   if (tid == 0) sh.qcount[0] = 0;
-  if (tid < P) sh.ready[tid] = 0;
   __syncthreads();
 
   const float S = K::y_scale(a);
@@ -333,11 +313,11 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
   const uint32_t ag_s = smem_u32(sh.ag), rows_s = smem_u32(sh.rows);
   const uint32_t stride_b = 4u * (uint32_t)Np;
 
-  uint32_t* wq = sh.warpq + kSymWarpQ * warp;
-  int wcount = 0;                              // entries in the warp's queue (warp-uniform)
+  const int n_warps = T >> 5;
+  uint32_t* wq = a.slowq + ((size_t)b * n_warps + warp) * a.slowq_cap_w;   // this warp's region of the slow queue
+  int wcount = 0;                              // entries in it (warp-uniform)
 
-  // ---- diagonal blocks first (nobody else touches them yet): two per warp, every lane draws its own side of
-  //      {l, l ^ s} ----
+  // ---- diagonal blocks: two per warp, every lane draws its own side of {l, l ^ s} ----
   for (int d = 0; d < 2; ++d) {
     const int I = 2 * warp + d;
     const int i = (I << 5) + lane;
@@ -346,26 +326,18 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
 #pragma unroll 1
     for (int s = 1; s < 32; ++s) {
       const SymStep A = sym_eval<TORUS, FULL_FOV, RC, false>(a, lds_f4(rec_i0 ^ (16u * s)), me.x, me.y, me.z, c);
-      SymRmw ai;
-      rmw_load(ai, row_i, stride_b, A.ps_i, A.mask);
-      rmw_store(ai);
-      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, A.slow_i,
-                          (uint32_t)i | ((uint32_t)(i ^ s) << 10) | (1u << 20));
+      sym_red(row_i, stride_b, A.ps_i, A.mask);
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, i ^ s, A.slow_i, false, false, false);
     }
   }
-  if (wcount) { sym_flush<TORUS, RC>(a, sh, wq, wcount, lane); wcount = 0; }
-  __syncwarp();
-  __threadfence_block();
-  if (lane < 2) sym_release_block(sh.ready, 2 * warp + lane, 1);
 
-  // ---- off-diagonal block pairs: round-robin tournament (circle method) over P blocks ----
+  // ---- off-diagonal block pairs: the P (P - 1) / 2 pairs are dealt to the warps like the rounds of a round-robin
+  //      tournament (circle method); draws are reductions, so the warps never wait for each other ----
   const int m = P - 1;
   for (int round = 0; round < m; ++round) {
     int I, J;
     if (warp == 0) { I = m; J = round; }
     else { I = (round + warp) % m; J = (round - warp + m) % m; }
-    sym_wait_block(sh.ready, lane & 1 ? J : I, round + 1);   // odd lanes watch J, even lanes I
-    __syncwarp();
     const int i = (I << 5) + lane, j0 = (J << 5) + lane;
     const float4 me = sh.ag[i];
     const uint32_t rec_j0 = ag_s + 16u * (uint32_t)j0, row_j0 = rows_s + 4u * (uint32_t)j0;
@@ -379,27 +351,28 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
       const float4 nA = lds_f4(rec_j0 ^ (16u * sn)), nB = lds_f4(rec_j0 ^ (16u * sn + 16u));
       const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, oA, me.x, me.y, me.z, c);
       const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true>(a, oB, me.x, me.y, me.z, c);
-      // draws of step s, then of step s + 1 (lane l's partner row of step s + 1 is lane l ^ 1's of step s); inside a
-      // step the own row and the partner row are different rows for every lane of the warp: both in flight together
-      SymRmw wi, wj;
-      rmw_load(wi, row_i, stride_b, A.ps_i, A.mask);
-      rmw_load(wj, row_j0 ^ (4u * s), stride_b, A.ps_j, A.mask);
-      rmw_store(wi);
-      rmw_store(wj);
-      rmw_load(wi, row_i, stride_b, B.ps_i, B.mask);
-      rmw_load(wj, row_j0 ^ (4u * s + 4u), stride_b, B.ps_j, B.mask);
-      rmw_store(wi);
-      rmw_store(wj);
-      // ---- off the fast path (~1 % of the directions): into the warp's queue ----
-      const bool any = A.slow_i | A.slow_j | B.slow_i | B.slow_j;
-      const uint32_t flags = (A.slow_i ? 1u : 0u) | (A.slow_j ? 2u : 0u) | (B.slow_i ? 4u : 0u) | (B.slow_j ? 8u : 0u);
-      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, any, (uint32_t)i | ((uint32_t)(j0 ^ s) << 10) | (flags << 20));
+      sym_red(row_i, stride_b, A.ps_i, A.mask);
+      sym_red(row_j0 ^ (4u * s), stride_b, A.ps_j, A.mask);
+      sym_red(row_i, stride_b, B.ps_i, B.mask);
+      sym_red(row_j0 ^ (4u * s + 4u), stride_b, B.ps_j, B.mask);
+      // ---- off the fast path (~1 % of the directions): into the warp's region of the slow queue ----
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j0 ^ s, A.slow_i, A.slow_j, B.slow_i, B.slow_j);
       oA = nA; oB = nB;
     }
-    if (wcount) { sym_flush<TORUS, RC>(a, sh, wq, wcount, lane); wcount = 0; }
-    __syncwarp();
-    __threadfence_block();
-    if (lane < 2) sym_release_block(sh.ready, lane ? J : I, round + 2);
+  }
+  if (lane == 0) sh.wcounts[warp] = wcount;
+  __syncthreads();
+
+  // ---- slow queue: all rows are quiescent now; one entry per thread, draws atomic, guard-band hits go on to the
+  //      fp64 queue ----
+  {
+    int total = 0;
+    for (int w = 0; w < n_warps; ++w) total += sh.wcounts[w];
+    int w = 0, base = 0, cnt = sh.wcounts[0];    // region holding flattened index g: [base, base + cnt)
+    for (int g = tid; g < total; g += T) {       // flattened over the warps' regions: every thread gets its share
+      while (g >= base + cnt) { base += cnt; cnt = sh.wcounts[++w]; }
+      sym_slow_entry<TORUS, RC>(a, sh, a.slowq[((size_t)b * n_warps + w) * a.slowq_cap_w + (g - base)]);
+    }
   }
   __syncthreads();
 
@@ -410,7 +383,8 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const VFKernelArgs 
     for (int e = tid; e < nq; e += T) {
       const uint32_t q0 = sh.queue[2 * e], q1 = sh.queue[2 * e + 1];
       const int f = (int)(q0 >> 16), o = (int)(q0 & 0xffffu);
-      n_mismatch += sym_exact_and_draw(a, sh.rows + Np + f, Np, rep_in[f], th_in[f], rep_in[o], (int)(short)(q1 >> 16),
+      n_mismatch += sym_exact_and_draw(a, sh.rows_s + stride_b + 4u * (uint32_t)f, stride_b, rep_in[f], th_in[f], rep_in[o],
+                                       (int)(short)(q1 >> 16),
                                        (int)(short)(q1 & 0xffffu));
     }
   }
@@ -431,6 +405,17 @@ bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t 
   const int Np = (a.N + 63) / 64 * 64;
   if (Np > 1024) return false;   // 16 warps at most; queue entries hold 16-bit agent indices
   return vf_sym_smem_bytes(Np, a.W) <= smem_limit;
+}
+
+// Slow-queue capacity: ~2 % of the ordered pairs of a replicate, split evenly between the warps.
+size_t vf_sym_slowq_entries(int B, int N, int* cap_w) {
+  const int Np = (N + 63) / 64 * 64;
+  const int warps = Np / 64;
+  long long per_cta = (long long)Np * Np / 48;
+  if (per_cta < 2048) per_cta = 2048;
+  const int cw = (int)((per_cta + warps - 1) / warps + 31) / 32 * 32;
+  if (cap_w) *cap_w = cw;
+  return (size_t)B * warps * cw;
 }
 
 template <bool TORUS, bool FULL_FOV, int RC>
