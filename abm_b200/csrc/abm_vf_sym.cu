@@ -160,6 +160,22 @@ __device__ __forceinline__ void sym_slow_entry(const VFKernelArgs& a, const SymS
     sym_slow_side<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (bit & 1) ? j : i, (bit & 1) ? i : j);
   }
 }
+// The same for a whole (converged) warp, one entry per lane (0: none): the lanes walk through their flagged directions
+// in lock step, so that the out-of-line evaluation always runs with as many lanes as there are entries left.
+template <bool TORUS, int RC>
+__device__ __forceinline__ void sym_slow_entries_warp(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
+  uint32_t flags = ent >> 20;
+  const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
+  while (__any_sync(0xffffffffu, flags != 0u)) {
+    if (flags) {
+      const int bit = __ffs(flags) - 1;
+      flags &= flags - 1;
+      const int j = jA ^ (bit >> 1);
+      sym_slow_side<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (bit & 1) ? j : i, (bit & 1) ? i : j);
+    }
+    __syncwarp();
+  }
+}
 template <bool TORUS, int RC>
 static __device__ __noinline__ void sym_slow_now(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
   sym_slow_entry<TORUS, RC>(a, sh, ent);
@@ -369,9 +385,15 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     int total = 0;
     for (int w = 0; w < n_warps; ++w) total += sh.wcounts[w];
     int w = 0, base = 0, cnt = sh.wcounts[0];    // region holding flattened index g: [base, base + cnt)
-    for (int g = tid; g < total; g += T) {       // flattened over the warps' regions: every thread gets its share
-      while (g >= base + cnt) { base += cnt; cnt = sh.wcounts[++w]; }
-      sym_slow_entry<TORUS, RC>(a, sh, a.slowq[((size_t)b * n_warps + w) * a.slowq_cap_w + (g - base)]);
+    for (int g0 = 0; g0 < total; g0 += T) {      // flattened over the warps' regions: every thread gets its share;
+      const int g = g0 + tid;                    // warp-uniform trip count, the warp reconverges in every iteration
+      uint32_t ent = 0u;
+      if (g < total) {
+        while (g >= base + cnt) { base += cnt; cnt = sh.wcounts[++w]; }
+        ent = a.slowq[((size_t)b * n_warps + w) * a.slowq_cap_w + (g - base)];
+      }
+      __syncwarp();
+      sym_slow_entries_warp<TORUS, RC>(a, sh, ent);
     }
   }
   __syncthreads();
@@ -380,12 +402,15 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   unsigned n_mismatch = 0;
   {
     const int nq = min(sh.qcount[0], kSymQueueCap);
-    for (int e = tid; e < nq; e += T) {
-      const uint32_t q0 = sh.queue[2 * e], q1 = sh.queue[2 * e + 1];
-      const int f = (int)(q0 >> 16), o = (int)(q0 & 0xffffu);
-      n_mismatch += sym_exact_and_draw(a, sh.rows_s + stride_b + 4u * (uint32_t)f, stride_b, rep_in[f], th_in[f], rep_in[o],
-                                       (int)(short)(q1 >> 16),
-                                       (int)(short)(q1 & 0xffffu));
+    for (int e0 = 0; e0 < nq; e0 += T) {         // warp-uniform trip count (see above)
+      const int e = e0 + tid;
+      if (e < nq) {
+        const uint32_t q0 = sh.queue[2 * e], q1 = sh.queue[2 * e + 1];
+        const int f = (int)(q0 >> 16), o = (int)(q0 & 0xffffu);
+        n_mismatch += sym_exact_and_draw(a, sh.rows_s + stride_b + 4u * (uint32_t)f, stride_b, rep_in[f], th_in[f], rep_in[o],
+                                         (int)(short)(q1 >> 16), (int)(short)(q1 & 0xffffu));
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
