@@ -425,6 +425,13 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.half_w = 0.5f * e->cfg.width; a.half_h = 0.5f * e->cfg.height;
   a.cull_scale = g.cull_scale;
   a.lin_step = g.lin_step; a.dphi = g.dphi;
+  {   // geometric-series constants of the integration grid Phi_k = -pi + k * delta (delta as numpy.arange computes it)
+    const double delta = (-ABM_PI_D + g.dphi) - (-ABM_PI_D);
+    const double sh = std::sin(0.5 * delta);
+    const double er = -2.0 * sh * sh, ei = std::sin(delta), n2 = er * er + ei * ei;   // exp(i delta) - 1
+    a.kappa_r = er / n2; a.kappa_i = -ei / n2;
+    a.rot_c = std::cos(delta); a.rot_s = std::sin(delta);
+  }
   a.width_d = e->cfg.width; a.height_d = e->cfg.height; a.pad_d = e->cfg.window_pad;
   a.max_vel = e->cfg.max_vel; a.max_th = e->cfg.max_th;
   a.theta = e->theta.p; a.vel = e->vel.p;

@@ -56,6 +56,8 @@ struct VFKernelArgs {
   // fp64 exact path / epilogue
   double lin_step;                // linspace step fl(2*pi_fl / (R-1))
   double dphi;                    // 2pi / R
+  double kappa_r, kappa_i;        // 1 / (exp(i d) - 1), d = step of the integration grid (vf_flock_terms_edges)
+  double rot_c, rot_s;            // cos d, sin d
   double width_d, height_d, pad_d, max_vel, max_th;
   // state
   const float4* rec_in;           // (x, y, r, cull^2) per agent, B*N

@@ -448,6 +448,62 @@ __device__ __forceinline__ FlockTerms vf_flock_terms(const uint32_t* f, int stri
   return t;
 }
 
+// The same terms for the step kernels, from the ring edges alone.  With E_k = exp(i Phi_k) and Phi_k = Phi_0 + k d:
+//   sum_{m<k} E_m = kappa (E_k - E_0),  kappa = 1 / (exp(i d) - 1)            (geometric series)
+// so the blob sums over all runs collapse to kappa (Z_fall - Z_rise) (+ the prefix at R if the last bin is set,
+// because trapz works on the linear array), and the edge sums are Z_rise + Z_fall, rotated by exp(-i d) under the
+// forward-difference rule (edge attributed to bin k - 1).  One 16-byte table read and four fp64 operations per edge.
+// etab_s: shared-space address of a copy of (cos Phi_k, sin Phi_k), k < R, or 0 (read the global table).
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ FlockTerms vf_flock_terms_edges(const uint32_t* f, int stride, const VFKernelArgs& a,
+                                                           uint32_t etab_s, double vel, const VFParams6& prm,
+                                                           double A0, double B0, double V0) {
+  const int R = a.R, W = a.W;
+  const PhiLut* __restrict__ lut = a.lut;
+  const uint32_t last_valid = (R & 31) ? ((1u << (R & 31)) - 1u) : 0xffffffffu;
+  const uint32_t w_last = f[(W - 1) * stride] & last_valid;
+  const uint32_t v_first = f[0] & 1u;
+  const uint32_t v_last = (w_last >> ((R - 1) & 31)) & 1u;
+  const bool backward = (v_first == 1u) && (v_last == 0u);
+  double zsr = 0.0, zsi = 0.0, zdr = 0.0, zdi = 0.0;   // Z_rise + Z_fall, Z_fall - Z_rise
+  uint32_t carry = v_last;   // ring predecessor of bin 0
+  for (int w = 0; w < W; ++w) {
+    uint32_t cur = f[w * stride];
+    if (w == W - 1) cur &= last_valid;
+    uint32_t diff = cur ^ ((cur << 1) | carry);   // bit b: V[k] != V[k-1], k = 32w + b
+    if (w == W - 1) diff &= last_valid;
+    carry = (w == W - 1) ? 0u : (cur >> 31);
+    while (diff) {
+      const int b = __ffs(diff) - 1;
+      diff &= diff - 1;
+      const int k = (w << 5) + b;
+      const double2 e = etab_s ? lds_d2(etab_s + 16u * (uint32_t)k) : *reinterpret_cast<const double2*>(&lut[k].c);
+      const double sg = ((cur >> b) & 1u) ? -1.0 : 1.0;   // rising edge (run starts at k): Z_rise
+      zsr += e.x; zsi += e.y;
+      zdr = fma(sg, e.x, zdr); zdi = fma(sg, e.y, zdi);
+    }
+  }
+  double Sc = a.kappa_r * zdr - a.kappa_i * zdi, Ss = a.kappa_r * zdi + a.kappa_i * zdr;
+  if (v_last) { Sc += lut[R].pc; Ss += lut[R].ps; }      // run reaching the end of the row
+  const double rc = backward ? 1.0 : a.rot_c, rs = backward ? 0.0 : -a.rot_s;   // exp(-i d) under the forward rule
+  const double Ec = rc * zsr - rs * zsi, Es = rc * zsi + rs * zsr;
+  const double c0 = lut[0].c, s0 = lut[0].s, cl = lut[R - 1].c, sl = lut[R - 1].s;
+  const double endc = 0.5 * (c0 * (double)v_first + cl * (double)v_last);
+  const double ends = 0.5 * (s0 * (double)v_first + sl * (double)v_last);
+  FlockTerms t;
+  t.a_blob = A0 * (a.dphi * (endc - Sc));
+  t.a_edge = A0 * prm.alp1 * Ec;
+  t.b_blob = B0 * (a.dphi * (ends - Ss));
+  t.b_edge = B0 * prm.bet1 * Es;
+  t.dvel = prm.gam * (V0 - vel) + t.a_blob + t.a_edge;
+  t.dpsi = t.b_blob + t.b_edge;
+  return t;
+}
+
 __device__ __forceinline__ double wrap_heading_once(double th) {   // agent.py:605-610
   if (th < 0.0) th = ABM_TWO_PI_D + th;
   if (th > ABM_TWO_PI_D) th = th - ABM_TWO_PI_D;
@@ -517,7 +573,7 @@ __device__ __forceinline__ uint32_t flipped_word(const uint32_t* f, int stride, 
 // padrow: padded word 0 of the agent's row (stride in words), me: (x, y, radius, cull^2).
 template <bool TORUS>
 __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, int i, int li, uint32_t* padrow,
-                                                  int stride, float4 me, float th) {
+                                                  int stride, float4 me, float th, uint32_t etab_s = 0u) {
   vf_fold_padding(padrow, stride, a.R, a.W);
   uint32_t* myrow = padrow + stride;   // real word 0
   const size_t gi = (size_t)b * a.N + i;
@@ -529,7 +585,7 @@ __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, 
   const double vel0 = a.vel[gi];
   FlockTerms ft;
   if (a.phi_ok) {
-    ft = vf_flock_terms(myrow, stride, a.R, a.W, a.lut, a.dphi, vel0, prm, A0, B0, V0);
+    ft = vf_flock_terms_edges(myrow, stride, a, etab_s, vel0, prm, A0, B0, V0);
   } else {   // len(PHI) != len(soc_v_field): the reference skips the calculation (vf_agent.py:282-284)
     ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
   }

@@ -421,7 +421,16 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   }
 
   // ---- epilogue: one agent per thread and pass (bank == lane) ----
-  for (int i = tid; i < N; i += T) vf_agent_epilogue<TORUS>(a, b, i, i, sh.rows + i, Np, rep_in[i], th_in[i]);
+  // the fp64 queue is dead now: it takes a copy of exp(i Phi_k) for the edge sums (19 KB at R = 1200)
+  uint32_t etab_s = 0u;
+  if ((size_t)a.R * sizeof(double2) <= 2 * sizeof(uint32_t) * kSymQueueCap) {
+    __syncthreads();
+    double2* etab = reinterpret_cast<double2*>(sh.queue);
+    for (int k = tid; k < a.R; k += T) etab[k] = *reinterpret_cast<const double2*>(&a.lut[k].c);
+    __syncthreads();
+    etab_s = sh.queue_s;
+  }
+  for (int i = tid; i < N; i += T) vf_agent_epilogue<TORUS>(a, b, i, i, sh.rows + i, Np, rep_in[i], th_in[i], etab_s);
 }
 
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit) {
