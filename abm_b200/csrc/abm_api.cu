@@ -412,12 +412,12 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.half_pi_b = (float)(0.5 * ABM_PI_D * inv); a.pi_b = (float)(ABM_PI_D * inv);
     a.seam_b = (float)((double)g.ca_guard * inv);
     a.nthr_h1 = -a.thr_h1;
-    // symmetric kernel: closed angle = bearing - heading, both rounded to fp32 bins.  Error budget at R = 1200:
-    // polynomial 1.1e-4 + octant / heading / difference / wrap roundings (half ulps of numbers <= 1.5 R) 2.4e-4 =
-    // 3.6e-4 bins worst case; 2.55e-4 is the largest seen in 2e7 emulated pairs (scratch/err_model.py)
-    const float tau_k_sym = (float)(3.5e-7 * (double)g.R + 3.0e-5);
-    a.sym_thr_k = exact ? 0.5f - tau_k_sym : 3.0e38f;
-    a.sym_seam_b = (float)((ABM_PI_D - 6.0e-6) * inv);
+    // symmetric kernel (binary angles): error of the bin coordinate = bearing polynomial (3.1 units of 2^-25 turn) +
+    // rounding to the integer (0.5 unit) + reciprocal / quotient rounding: 1.75e-4 bins worst case at R = 1200,
+    // 1.44e-4 the largest seen in 2e7 emulated pairs (scratch/err_model_bam.py); all terms scale with R
+    const double tau_k_sym = 2.0e-7 * (double)g.R + 1.0e-5;
+    a.sym_tie32 = exact ? (uint32_t)(tau_k_sym * 4294967296.0) : 0u;
+    a.sym_seam32 = exact ? (uint32_t)(6.0e-6 / ABM_TWO_PI_D * 4294967296.0) : 0u;   // 6e-6 rad either side of +-pi
     a.sym_thr_h = exact ? 0.5f - g.tau_h_abs - 17.5f * g.tau_h_rel : 3.0e38f;
     a.full_fov = (e->cfg.fov_px0 == 0 && e->cfg.fov_px1 == g.R - 1) ? 1 : 0;
   }

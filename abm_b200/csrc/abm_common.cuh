@@ -45,7 +45,8 @@ struct VFKernelArgs {
   float nthr_h1;                  // -thr_h1
   // symmetric kernel (abm_vf_sym.cu): wider k guard band (the closed angle is a difference of two rounded bin
   // angles), absolute h guard band of the fast path (h <= 16), the common radius
-  float sym_thr_k, sym_seam_b, sym_thr_h, sym_radius;
+  float sym_thr_h, sym_radius;
+  uint32_t sym_tie32, sym_seam32; // guard bands of the binary-angle bin index, in 2^-32 bins / 2^-32 turns
   uint32_t* slowq;                // symmetric kernel: B * warps * slowq_cap_w entries for directions off the fast path
   int slowq_cap_w;
   int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible

@@ -45,7 +45,7 @@ __device__ __forceinline__ float pin_f(float v) { asm volatile("" : "+f"(v)); re
 __device__ __forceinline__ uint32_t pin_u(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 
 struct SymShared {
-  float4* ag;          // [Np] (x, y, heading in bins, radius); padding agents beyond N are far away
+  float4* ag;          // [Np] (x, y, heading constant, the same + half a turn); padding agents beyond N are far away
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
   int* wcounts;        // [warps] entries in every warp's region of the slow queue (global memory)
@@ -64,42 +64,56 @@ static __device__ __noinline__ unsigned sym_exact_and_draw(const VFKernelArgs& a
   return (pe.valid && ((pe.k != k32) | (pe.h != h32))) ? 1u : 0u;
 }
 
-// Bearing of the partner in bins of the linspace grid, |.| parts for both directions:
-// pi_abs = |atan2(-dy, dx)|, pj_abs = |atan2(dy, -dx)| (each * (R-1)/2pi).
-template <int RC>
-__device__ __forceinline__ void sym_bearing(const VFKernelArgs& a, float dx, float dy, float a6, float& pi_abs,
-                                            float& pj_abs) {
-  using K = PairK<RC>;
+// ---- binary angles ----------------------------------------------------------------------------------------------
+// Angles live in 32-bit integers, 2^32 to the turn, so differences wrap for free.  The bearing atan2(-dy, dx) of the
+// partner comes out of the octant polynomial in units of 2^-25 turn (an octant = 2^22 units: it fits the integer
+// window of the 1.5 * 2^23 rounding constant), is unfolded with integer arithmetic and scaled by 128.  With
+//   v = bearing - heading + half a turn          (unsigned: the closed angle measured from -pi)
+// the nearest index on the linspace(-pi, pi, R) grid (vf_supcalc.py:102) is the high word of v * (R - 1) + 2^31, and
+// the low word is the distance from the rounding tie: one IMAD.WIDE yields the bin and its guard band.  The opposite
+// direction only differs by half a turn, which is folded into the partner's heading constant.
+constexpr uint32_t kQuarter = 1u << 23, kHalf = 1u << 24;      // in units of 2^-25 turn
+constexpr uint32_t kMB2 = 2u * (uint32_t)kMagicBits;
+
+// bits of (kMagic + bearing in 2^-25 turns), bearing in (-half turn, half turn]
+__device__ __forceinline__ uint32_t sym_bearing_bits(float dx, float dy, float a6) {
+  constexpr double kS = 33554432.0 / ABM_TWO_PI_D;             // 2^25 / 2pi
   const float au = fabsf(dx), aw = fabsf(dy);
   const float tq = fminf(au, aw) * rcp_approx(fmaxf(au, aw));
   const float z = tq * tq;
-  float p = fmaf(a6, z, K::ac(a, 5));
-  p = fmaf(p, z, K::ac(a, 4));
-  p = fmaf(p, z, K::ac(a, 3));
-  p = fmaf(p, z, K::ac(a, 2));
-  p = fmaf(p, z, K::ac(a, 1));
-  p = fmaf(p, z, K::ac(a, 0));
-  p *= tq;
-  if (aw > au) p = K::half_pi_b(a) - p;
-  const float pr = K::pi_b(a) - p;
-  const bool neg = dx < 0.0f;
-  pi_abs = neg ? pr : p;
-  pj_abs = neg ? p : pr;
+  float p = fmaf(a6, z, (float)(-0.037013452500104904 * kS));
+  p = fmaf(p, z, (float)(0.0838717594742775 * kS));
+  p = fmaf(p, z, (float)(-0.13487225770950317 * kS));
+  p = fmaf(p, z, (float)(0.19881492853164673 * kS));
+  p = fmaf(p, z, (float)(-0.33326515555381775 * kS));
+  p = fmaf(p, z, (float)(0.9999993443489075 * kS));
+  uint32_t nb = __float_as_uint(fmaf(p, tq, kMagic));          // kMagicBits + rint(octant angle)
+  if (aw > au) nb = (kMB2 + kQuarter) - nb;
+  if (dx < 0.0f) nb = (kMB2 + kHalf) - nb;
+  if (dy > 0.0f) nb = kMB2 - nb;                               // atan2(-dy, dx): screen y points down
+  return nb;
+}
+constexpr float kBearingA6 = (float)(0.007863515056669712 * (33554432.0 / ABM_TWO_PI_D));
+
+// Heading constant of an agent: v = 128 * bearing_bits - heading_const (mod 2^32).
+__device__ __forceinline__ uint32_t sym_heading_const(float theta) {
+  double turns = (double)theta * (1.0 / ABM_TWO_PI_D);
+  turns -= floor(turns);
+  const uint32_t th_bam = (uint32_t)(unsigned long long)rint(turns * 4294967296.0);
+  return th_bam + 128u * (uint32_t)kMagicBits - 0x80000000u;
 }
 
-// One direction of a pair on the fast path: closed angle -> padded start position of the interval
-// (h already folded into `bh`), `slow` is set when the bin index is within the fp32 error bound of
-// a rounding boundary or the angle is on the +-pi seam.
+// One direction on the fast path: nearest linspace index of the closed angle (returned as the padded start position of
+// the interval, h folded into `bh`); `slow` is set when the angle is within the fp32 error bound of a rounding tie or
+// of the +-pi seam.
 template <int RC>
-__device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, float phi, float thb, int bh, bool& slow) {
-  using K = PairK<RC>;
-  float cab = phi - thb;                                    // thb in [0, R-1] -> cab in [-1.5 (R-1), (R-1)/2]
-  if (cab < -K::pi_b(a)) cab += 2.0f * K::pi_b(a);
-  slow |= fabsf(cab) > a.sym_seam_b;
-  const float t = cab + K::t_half(a);
-  const float tr = t + kMagic;
-  slow |= fabsf(t - (tr - kMagic)) > a.sym_thr_k;
-  return __float_as_int(tr) + bh;
+__device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, uint32_t nb, uint32_t hconst, int bh, bool& slow) {
+  const uint32_t v = 128u * nb - hconst;
+  const uint32_t Rp = RC ? (uint32_t)(RC - 1) : (uint32_t)(a.R - 1);
+  const unsigned long long prod = (unsigned long long)v * Rp + 0x80000000ull;
+  slow |= ((uint32_t)prod + a.sym_tie32) < 2u * a.sym_tie32;
+  slow |= (v + a.sym_seam32) < 2u * a.sym_seam32;
+  return (int)(uint32_t)(prod >> 32) + bh;
 }
 
 // Slow path of one direction (focal f sees object o), run from the round queue by any thread: the
@@ -119,15 +133,13 @@ static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, uint32_
     if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
-  const float q = oa.w * rsqrt_approx(d2);
+  const float q = a.sym_radius * rsqrt_approx(d2);
   const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
   const float yr = y + kMagic;
   const int h = __float_as_int(yr) - kMagicBits;
   bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
-  float pi_abs, pj_abs;
-  sym_bearing<RC>(a, dx, dy, K::ac(a, 6), pi_abs, pj_abs);
   const int R = RC ? RC : a.R;
-  const int k = sym_side_k<RC>(a, copysignf(pi_abs, -dy), fa.z, K::k_bias(a), flagged) - 32;   // real bin index
+  const int k = sym_side_k<RC>(a, sym_bearing_bits(dx, dy, kBearingA6), __float_as_uint(fa.z), 0, flagged);   // bin index
   const uint32_t stride_b = 4u * (uint32_t)Np;
   const uint32_t row_s = rows_s + stride_b + 4u * (uint32_t)f;        // real word 0
   if (flagged) {
@@ -213,7 +225,7 @@ struct SymStep {
 // Pure arithmetic (no shared-memory access): the compiler interleaves two of these.
 // BOTH: evaluate both directions; otherwise only the lane's own.
 template <bool TORUS, bool FULL_FOV, int RC, bool BOTH>
-__device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, float xi, float yi, float thb_i,
+__device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, float xi, float yi, uint32_t hc_i,
                                             const SymConsts& c) {
   using K = PairK<RC>;
   SymStep r;
@@ -235,13 +247,11 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   const uint32_t hraw = __float_as_uint(yr);                 // h + kMagicBits
   const bool slow_h = !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);   // also d2 == 0 (NaN)
   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask) : "r"(2u * hraw - 2u * (uint32_t)kMagicBits));   // 2h ones
-  const int bh = K::k_bias(a) + kMagicBits - (int)hraw;      // ps = rint(t) + k_off + 32 - h
-  // ---- absolute bearing, both directions ----
-  float pi_abs, pj_abs;
-  sym_bearing<RC>(a, dx, dy, c.a6, pi_abs, pj_abs);
-  const float phi_i = __uint_as_float(__float_as_uint(pi_abs) | (~__float_as_uint(dy) & 0x80000000u));   // copysign(., -dy)
+  const int bh = 32 + kMagicBits - (int)hraw;                // ps = bin index + 32 - h
+  // ---- bearing (shared), bin index of both directions ----
+  const uint32_t nb = sym_bearing_bits(dx, dy, c.a6);
   r.slow_i = slow_h;
-  const int ps_i = sym_side_k<RC>(a, phi_i, thb_i, bh, r.slow_i);
+  const int ps_i = sym_side_k<RC>(a, nb, hc_i, bh, r.slow_i);
   bool draw_i = !r.slow_i;
   if (!FULL_FOV) {
     const int pe = ps_i + 2 * ((int)hraw - kMagicBits);
@@ -251,9 +261,8 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   r.slow_j = false;
   r.ps_j = c.scratch_pos;
   if (BOTH) {
-    const float phi_j = __uint_as_float(__float_as_uint(pj_abs) | (__float_as_uint(dy) & 0x80000000u));
     r.slow_j = slow_h;
-    const int ps_j = sym_side_k<RC>(a, phi_j, o.z, bh, r.slow_j);
+    const int ps_j = sym_side_k<RC>(a, nb, __float_as_uint(o.w), bh, r.slow_j);   // o.w: heading constant + half a turn
     bool draw_j = !r.slow_j;
     if (!FULL_FOV) {
       const int pe = ps_j + 2 * ((int)hraw - kMagicBits);
@@ -306,12 +315,10 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     float4 v;
     if (j < N) {
       const float4 r4 = rep_in[j];
-      double th = fmod((double)th_in[j], ABM_TWO_PI_D);
-      if (th < 0.0) th += ABM_TWO_PI_D;
-      const double inv = RC ? PairK<RC>::kInv : (double)a.inv_step;
-      v = make_float4(r4.x, r4.y, (float)(th * inv), r4.z);
+      const uint32_t hc = sym_heading_const(th_in[j]);
+      v = make_float4(r4.x, r4.y, __uint_as_float(hc), __uint_as_float(hc - 0x80000000u));
     } else {   // padding: far away (half width 0), all distinct
-      v = make_float4(-1.0e6f - 4096.0f * (float)(j - N), -1.0e6f, 0.f, a.sym_radius);
+      v = make_float4(-1.0e6f - 4096.0f * (float)(j - N), -1.0e6f, 0.f, 0.f);
     }
     sh.ag[j] = v;
   }
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   c.rS = a.sym_radius * S;
   c.c3s = -1.0f / (3.0f * S * S);
   c.c5s = pin_f(1.0f / (5.0f * S * S * S * S));
-  c.a6 = pin_f(K::ac(a, 6));
+  c.a6 = pin_f(kBearingA6);
   c.scratch_pos = 32 * (a.W + 2);
   const uint32_t ag_s = smem_u32(sh.ag), rows_s = smem_u32(sh.rows);
   const uint32_t stride_b = 4u * (uint32_t)Np;
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     const uint32_t rec_i0 = ag_s + 16u * (uint32_t)i, row_i = rows_s + 4u * (uint32_t)i;
 #pragma unroll 1
     for (int s = 1; s < 32; ++s) {
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, false>(a, lds_f4(rec_i0 ^ (16u * s)), me.x, me.y, me.z, c);
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, false>(a, lds_f4(rec_i0 ^ (16u * s)), me.x, me.y, __float_as_uint(me.z), c);
       sym_red(row_i, stride_b, A.ps_i, A.mask);
       sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, i ^ s, A.slow_i, false, false, false);
     }
@@ -365,8 +372,8 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     for (int s = 0; s < 32; s += 2) {
       const uint32_t sn = (uint32_t)(s + 2) & 31u;          // prefetch the next two partner records (wraps harmlessly)
       const float4 nA = lds_f4(rec_j0 ^ (16u * sn)), nB = lds_f4(rec_j0 ^ (16u * sn + 16u));
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, oA, me.x, me.y, me.z, c);
-      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true>(a, oB, me.x, me.y, me.z, c);
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, oA, me.x, me.y, __float_as_uint(me.z), c);
+      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true>(a, oB, me.x, me.y, __float_as_uint(me.z), c);
       sym_red(row_i, stride_b, A.ps_i, A.mask);
       sym_red(row_j0 ^ (4u * s), stride_b, A.ps_j, A.mask);
       sym_red(row_i, stride_b, B.ps_i, B.mask);
