@@ -110,6 +110,7 @@ struct abm_engine {
   float r_min = 0.f, r_max = 0.f;
   bool state_set = false;
   unsigned long long launches = 0;
+  const char* last_kernel = "";
   size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // spatial ordering (ABM_VF_SPATIAL_SORT)
   bool sort_enabled = false, needs_sort = false, perm_identity = true;
@@ -490,6 +491,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     }
     if (use_sym) abm::launch_vf_step_sym(a, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
+    e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : "abm::vf_step_kernel";
     e->cur ^= 1;
     ++e->launches;
   }
@@ -527,6 +529,8 @@ int abm_get_counters(abm_engine_t* e, uint64_t counters[4], void* stream) {
   counters[3] = e->launches;
   return ABM_OK;
 }
+
+const char* abm_vf_last_kernel(abm_engine_t* e) { return e ? e->last_kernel : ""; }
 
 int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent) {
   if (!e || !dev_ptr) return fail(ABM_E_INVALID, "abm_vf_record_table: null argument");

@@ -278,7 +278,9 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
 // scratch/red_bench.cu).  Nobody has to own a row, draws need no ordering, and the second word is written
 // unconditionally (its mask is usually 0): that is cheaper than a predicate.
 __device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps, uint32_t m) {
-  const uint32_t wa = row + (uint32_t)(ps >> 5) * stride_b;
+  uint32_t wa;   // row + (ps >> 5) * stride_b as ONE multiply-add (with a power-of-two immediate stride the compiler
+                 // would otherwise build it from a shift, a mask and an add)
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(wa) : "r"((uint32_t)(ps >> 5)), "r"(stride_b), "r"(row));
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(__funnelshift_l(0u, m, ps)));
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + stride_b), "r"(__funnelshift_l(m, 0u, ps)));
 }
@@ -288,8 +290,10 @@ size_t vf_sym_smem_bytes(int Np, int W) {
          sizeof(int) * (size_t)(Np / 64) + 16;
 }
 
-template <bool TORUS, bool FULL_FOV, int RC>
-__global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_constant__ VFKernelArgs a, int Np) {
+// NPC > 0: compile-time padded replicate size (row stride becomes an immediate), 0: the run-time argument.
+template <bool TORUS, bool FULL_FOV, int RC, int NPC>
+__global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_constant__ VFKernelArgs a, int Np_arg) {
+  const int Np = NPC ? NPC : Np_arg;
   using K = PairK<RC>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SymShared sh;
@@ -459,21 +463,23 @@ size_t vf_sym_slowq_entries(int B, int N, int* cap_w) {
   return (size_t)B * warps * cw;
 }
 
-template <bool TORUS, bool FULL_FOV, int RC>
+template <bool TORUS, bool FULL_FOV, int RC, int NPC>
 static void launch_sym_variant(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(vf_step_sym_kernel<TORUS, FULL_FOV, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
     configured = smem;
   }
-  vf_step_sym_kernel<TORUS, FULL_FOV, RC><<<a.B, threads, smem, stream>>>(a, Np);
+  vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC><<<a.B, threads, smem, stream>>>(a, Np);
 }
 
 template <bool TORUS>
 static void launch_sym_fov(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
-  if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200>(a, Np, threads, smem, stream);
-  else if (a.full_fov) launch_sym_variant<TORUS, true, 0>(a, Np, threads, smem, stream);
-  else launch_sym_variant<TORUS, false, 0>(a, Np, threads, smem, stream);
+  if (a.full_fov && a.R == 1200 && Np == 1024) launch_sym_variant<TORUS, true, 1200, 1024>(a, Np, threads, smem, stream);
+  else if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200, 0>(a, Np, threads, smem, stream);
+  else if (a.full_fov) launch_sym_variant<TORUS, true, 0, 0>(a, Np, threads, smem, stream);
+  else launch_sym_variant<TORUS, false, 0, 0>(a, Np, threads, smem, stream);
 }
 
 void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream) {

@@ -212,6 +212,10 @@ class VFEngine:
         _lib.check(self._lib.abm_vf_internal_arrays(self._h, C.byref(t), C.byref(v)), "abm_vf_internal_arrays")
         return int(t.value), int(v.value)
 
+    def last_kernel(self) -> str:
+        """Name of the step kernel the last step() launched."""
+        return (self._lib.abm_vf_last_kernel(self._h) or b"").decode()
+
     def record_table_ptr(self) -> tuple[int, int]:
         p = C.c_void_p()
         nbytes = C.c_int()

@@ -36,9 +36,10 @@ R = 1200
 RADIUS = 10.0
 PAD = 30.0
 PARAMS = dict(GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, BET0=1.0, BET1=0.09)
-# dram__bytes_read.sum + dram__bytes_write.sum of one vf_step_kernel launch at the default workload, from the
-# committed `ncu --set full` capture (profiles/r1_vf_step_ncu_summary.md); None for any other workload size
-NCU_DRAM_BYTES_PER_LAUNCH = 55.2e6 if (N_AGENTS, N_REPLICATES) == (1024, 1024) else None
+# dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch at the default workload, from the committed
+# `ncu --set full` captures (profiles/r1_*_ncu_summary.md); None for any other workload size or kernel
+NCU_DRAM_BYTES_PER_LAUNCH = {"abm::vf_step_kernel": 55.2e6, "abm::vf_step_sym_kernel": 41.3e6} \
+    if (N_AGENTS, N_REPLICATES) == (1024, 1024) else {}
 METRIC = "agent-steps/sec (visual field + flocking update)"
 UNIT = "agent-steps/s"
 
@@ -198,8 +199,8 @@ def workload_config(world):
             "fov_resolution": R, "boundary": "walls", "arena_px": arena_side(N_AGENTS), "agent_radius": RADIUS,
             "params": PARAMS, "parallelism": f"replicate-sharded x{world}, no data-path collective",
             "l2": "L2 flushed (256 MiB memset) between timed steps; flush excluded from the timing",
-            "update": "synchronous (Jacobi) step from a frozen snapshot; epilogue in fp64, pair path fp32 + fp64 "
-                      "re-evaluation of near-boundary pairs"}
+            "update": "synchronous (Jacobi) step from a frozen snapshot; every unordered pair evaluated once (fp32 + "
+                      "32-bit binary angles), near-tie pairs re-evaluated in fp64, epilogue in fp64"}
 
 
 def main():
@@ -218,7 +219,7 @@ def main():
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference_arm(args, rank, world)
         return
-    args.steps = 30 if args.steps is None else args.steps
+    args.steps = 100 if args.steps is None else args.steps
     args.warmup = 3 if args.warmup is None else max(args.warmup, 3)
 
     import torch
@@ -332,8 +333,8 @@ def main():
                     "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
-                         "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "kernel": "abm::vf_step_kernel", "algorithmic_ops_per_launch": ops_launch,
+                         "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(eng.last_kernel()), "kernel": eng.last_kernel(), "algorithmic_ops_per_launch": ops_launch,
                          "visible_pair_fraction": vis, "peak_source": f"{sms} SMs x 128 lanes x "
                          f"{sm_clock / 1e6:.0f} MHz ({peak_kind} sm_max_mhz)",
                          "hbm": {"achieved": bytes_launch / avg_s / 1e9, "peak": peaks.get("hbm_gbs"),

@@ -150,6 +150,12 @@ int abm_vf_get_permutation(abm_engine_t* e, int32_t* perm, int on_device, void* 
 int abm_vf_resort(abm_engine_t* e, void* stream);
 int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev);
 
+/* Name of the step kernel the last abm_vf_step launched ("abm::vf_step_sym_kernel": every unordered pair once, all rows
+ * of a replicate in one CTA's shared memory; "abm::vf_step_kernel": one thread per focal agent), "" before the first
+ * step.  The choice is made per step from the state (equal radii, replicate fits in shared memory, no distance
+ * culling -> symmetric); the environment variable ABM_VF_KERNEL=onesided|symmetric overrides it for tests. */
+const char* abm_vf_last_kernel(abm_engine_t* e);
+
 int abm_synchronize(abm_engine_t* e, void* stream);
 
 /* ---- stateless function-level entry points (host pointers, synchronous) ---- */
