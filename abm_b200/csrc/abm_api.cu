@@ -120,8 +120,6 @@ struct abm_engine {
   DevBuf<unsigned char> sort_temp;
   size_t sort_temp_bytes = 0;
   DevBuf<float4> tile_bbox;   // culling by record tiles (CULL variants on sorted state)
-  DevBuf<uint32_t> slowq;     // symmetric kernel: queue of directions off the fast path (allocated on first use)
-  int slowq_cap_w = 0;
   DevBuf<float> tile_cull2;
 };
 
@@ -267,7 +265,7 @@ int abm_destroy(abm_engine_t* e) {
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
-  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release(); e->slowq.release();
+  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release();
   e->radius_minmax.release();
   delete e;
   return ABM_OK;
@@ -462,11 +460,6 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.sym_radius = e->r_max;
   const bool use_sym = !(force && strcmp(force, "onesided") == 0) &&
                        abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
-  if (use_sym && !e->slowq.p) {
-    const size_t n = abm::vf_sym_slowq_entries(a.B, a.N, &e->slowq_cap_w);
-    ABM_CUDA(e->slowq.alloc(n));
-  }
-  a.slowq = e->slowq.p; a.slowq_cap_w = e->slowq_cap_w;
   const bool tiled = e->tile_count != e->cfg.n_agents;
   for (int s = 0; s < n_steps; ++s) {
     // (the symmetric kernel wants NO spatial order: its blocks should all hold the same mix of near and far pairs)

@@ -47,8 +47,6 @@ struct VFKernelArgs {
   // angles), absolute h guard band of the fast path (h <= 16), the common radius
   float sym_thr_h, sym_radius;
   uint32_t sym_tie32, sym_seam32; // guard bands of the binary-angle bin index, in 2^-32 bins / 2^-32 turns
-  uint32_t* slowq;                // symmetric kernel: B * warps * slowq_cap_w entries for directions off the fast path
-  int slowq_cap_w;
   int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible
   int fov0p;                      // fov_px0 + 33: first visible padded position
   unsigned span;                  // fov_px1 - fov_px0 - 1: number of visible positions
@@ -89,7 +87,6 @@ size_t vf_step_smem_bytes(int threads, int W);
 // symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
 void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
-size_t vf_sym_slowq_entries(int B, int N, int* cap_w);   // size of VFKernelArgs::slowq
 int vf_step_threads(int tile_count);
 
 struct VFProjArgs {

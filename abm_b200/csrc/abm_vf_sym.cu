@@ -29,6 +29,7 @@
 
 namespace abm {
 
+constexpr int kSymWarpQ = 64;        // entries per warp: worked off 32 at a time, as soon as 32 are there
 constexpr int kSymQueueCap = 3072;   // fp64 queue: ~0.2 % of the 1M ordered pairs of a 1024-agent replicate
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: low mantissa bits of x + kMagic = rint(x)
 constexpr int kMagicBits = 0x4B400000;
@@ -48,7 +49,7 @@ struct SymShared {
   float4* ag;          // [Np] (x, y, heading constant, the same + half a turn); padding agents beyond N are far away
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
-  int* wcounts;        // [warps] entries in every warp's region of the slow queue (global memory)
+  uint32_t* warpq;     // [warps][kSymWarpQ] per-warp ring of lane entries with directions off the fast path
   int* qcount;         // [0]: fp64 queue
   uint32_t ag_s, rows_s, queue_s, qcount_s;   // shared-space addresses of the above (code that is not inlined)
   int Np, N;
@@ -161,18 +162,7 @@ static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, uint32_
 // One entry of the slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own agent
 // sees the partner of the even step / is seen by it, bits 2 / 3: the same for the odd step, whose partner index
 // differs in bit 0.  Walk through the flagged directions (draws are atomic).
-template <bool TORUS, int RC>
-__device__ __forceinline__ void sym_slow_entry(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
-  uint32_t flags = ent >> 20;
-  const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
-  while (flags) {
-    const int bit = __ffs(flags) - 1;
-    flags &= flags - 1;
-    const int j = jA ^ (bit >> 1);
-    sym_slow_side<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (bit & 1) ? j : i, (bit & 1) ? i : j);
-  }
-}
-// The same for a whole (converged) warp, one entry per lane (0: none): the lanes walk through their flagged directions
+// For a whole (converged) warp, one entry per lane (0: none): the lanes walk through their flagged directions
 // in lock step, so that the out-of-line evaluation always runs with as many lanes as there are entries left.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_slow_entries_warp(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
@@ -189,26 +179,28 @@ __device__ __forceinline__ void sym_slow_entries_warp(const VFKernelArgs& a, con
   }
 }
 template <bool TORUS, int RC>
-static __device__ __noinline__ void sym_slow_now(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
-  sym_slow_entry<TORUS, RC>(a, sh, ent);
+static __device__ __noinline__ void sym_slow_batch(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
+  sym_slow_entries_warp<TORUS, RC>(a, sh, ent);
 }
 
-// Append this lane's entry (if it has flagged directions) to the warp's region of the slow queue in global memory
-// (fire-and-forget stores; the queue is worked off by the whole CTA after the last round, when every row is quiescent
-// and all lanes are busy).  Region full (crowded scene): on the spot.  Called by the converged warp.
+// Append this lane's entry (if it has flagged directions) to the warp's queue in shared memory.  As soon as 32 entries
+// are there the warp works them off, one per lane: draws are reductions, so this can happen at any time -- the
+// latency-bound out-of-line evaluation then overlaps the other warps' pair loops instead of forming a serial phase.
+// wq_s: shared-space address of the warp's queue; wcount: entries in it (warp-uniform).  Called by the converged warp.
 template <bool TORUS, int RC>
-__device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared& sh, uint32_t* wq, int& wcount, int lane,
+__device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount, int lane,
                                          int i, int jA, bool f0, bool f1, bool f2, bool f3) {
   const bool any = f0 | f1 | f2 | f3;
   const uint32_t bal = __ballot_sync(0xffffffffu, any);
   if (bal) {                                                   // warp-uniform
     const uint32_t flags = (f0 ? 1u : 0u) | (f1 ? 2u : 0u) | (f2 ? 4u : 0u) | (f3 ? 8u : 0u);
     const uint32_t entry = (uint32_t)i | ((uint32_t)jA << 10) | (flags << 20);
-    if (wcount + 32 <= a.slowq_cap_w) {
-      if (any) wq[wcount + __popc(bal & ((1u << lane) - 1u))] = entry;
-      wcount += __popc(bal);
-    } else {
-      if (any) sym_slow_now<TORUS, RC>(a, sh, entry);
+    if (any) sts_u32(wq_s + 4u * (uint32_t)(wcount + __popc(bal & ((1u << lane) - 1u))), entry);
+    wcount += __popc(bal);
+    if (wcount >= 32) {
+      wcount -= 32;
+      __syncwarp();
+      sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
       __syncwarp();
     }
   }
@@ -287,7 +279,7 @@ __device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps,
 
 size_t vf_sym_smem_bytes(int Np, int W) {
   return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + 3) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
-         sizeof(int) * (size_t)(Np / 64) + 16;
+         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + 16;
 }
 
 // NPC > 0: compile-time padded replicate size (row stride becomes an immediate), 0: the run-time argument.
@@ -300,8 +292,8 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   sh.ag = reinterpret_cast<float4*>(smem_raw);
   sh.rows = reinterpret_cast<uint32_t*>(sh.ag + Np);
   sh.queue = sh.rows + (size_t)(a.W + 3) * Np;
-  sh.wcounts = reinterpret_cast<int*>(sh.queue + 2 * kSymQueueCap);
-  sh.qcount = sh.wcounts + (Np / 64);
+  sh.warpq = sh.queue + 2 * kSymQueueCap;
+  sh.qcount = reinterpret_cast<int*>(sh.warpq + kSymWarpQ * (Np / 64));
   sh.Np = Np; sh.N = a.N;
   sh.ag_s = smem_u32(sh.ag); sh.rows_s = smem_u32(sh.rows); sh.queue_s = smem_u32(sh.queue);
   sh.qcount_s = smem_u32(sh.qcount);
@@ -340,8 +332,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   const uint32_t ag_s = smem_u32(sh.ag), rows_s = smem_u32(sh.rows);
   const uint32_t stride_b = 4u * (uint32_t)Np;
 
-  const int n_warps = T >> 5;
-  uint32_t* wq = a.slowq + ((size_t)b * n_warps + warp) * a.slowq_cap_w;   // this warp's region of the slow queue
+  const uint32_t wq = smem_u32(sh.warpq + kSymWarpQ * warp);   // this warp's queue of slow entries
   int wcount = 0;                              // entries in it (warp-uniform)
 
   // ---- diagonal blocks: two per warp, every lane draws its own side of {l, l ^ s} ----
@@ -387,26 +378,9 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
       oA = nA; oB = nB;
     }
   }
-  if (lane == 0) sh.wcounts[warp] = wcount;
-  __syncthreads();
-
-  // ---- slow queue: all rows are quiescent now; one entry per thread, draws atomic, guard-band hits go on to the
-  //      fp64 queue ----
-  {
-    int total = 0;
-    for (int w = 0; w < n_warps; ++w) total += sh.wcounts[w];
-    int w = 0, base = 0, cnt = sh.wcounts[0];    // region holding flattened index g: [base, base + cnt)
-    for (int g0 = 0; g0 < total; g0 += T) {      // flattened over the warps' regions: every thread gets its share;
-      const int g = g0 + tid;                    // warp-uniform trip count, the warp reconverges in every iteration
-      uint32_t ent = 0u;
-      if (g < total) {
-        while (g >= base + cnt) { base += cnt; cnt = sh.wcounts[++w]; }
-        ent = a.slowq[((size_t)b * n_warps + w) * a.slowq_cap_w + (g - base)];
-      }
-      __syncwarp();
-      sym_slow_entries_warp<TORUS, RC>(a, sh, ent);
-    }
-  }
+  // the rest of the warp's queue (fewer than 32 entries)
+  __syncwarp();
+  sym_slow_batch<TORUS, RC>(a, sh, lane < wcount ? lds_u32(wq + 4u * (uint32_t)lane) : 0u);
   __syncthreads();
 
   // ---- deferred pairs: fp64, the reference's own operation sequence ----
@@ -450,17 +424,6 @@ bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t 
   const int Np = (a.N + 63) / 64 * 64;
   if (Np > 1024) return false;   // 16 warps at most; queue entries hold 16-bit agent indices
   return vf_sym_smem_bytes(Np, a.W) <= smem_limit;
-}
-
-// Slow-queue capacity: ~2 % of the ordered pairs of a replicate, split evenly between the warps.
-size_t vf_sym_slowq_entries(int B, int N, int* cap_w) {
-  const int Np = (N + 63) / 64 * 64;
-  const int warps = Np / 64;
-  long long per_cta = (long long)Np * Np / 48;
-  if (per_cta < 2048) per_cta = 2048;
-  const int cw = (int)((per_cta + warps - 1) / warps + 31) / 32 * 32;
-  if (cap_w) *cap_w = cw;
-  return (size_t)B * warps * cw;
 }
 
 template <bool TORUS, bool FULL_FOV, int RC, int NPC>
