@@ -270,8 +270,7 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
     if (tid == 0 && *qcount) atomicAdd(&a.counters[0], (unsigned long long)*qcount);   // all flagged pairs
   }
 
-  if (!active) return;
-  vf_agent_epilogue<TORUS>(a, b, i, li, padrow, T, me, th);
+  vf_agent_epilogue<TORUS>(a, b, active ? i : a.tile_begin, active ? li : 0, padrow, T, me, th, 0u, active);
 }
 
 template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>

@@ -461,23 +461,36 @@ __device__ __forceinline__ double2 lds_d2(uint32_t addr) {
 }
 __device__ __forceinline__ FlockTerms vf_flock_terms_edges(const uint32_t* f, int stride, const VFKernelArgs& a,
                                                            uint32_t etab_s, double vel, const VFParams6& prm,
-                                                           double A0, double B0, double V0) {
+                                                           double A0, double B0, double V0, bool active) {
   const int R = a.R, W = a.W;
   const PhiLut* __restrict__ lut = a.lut;
   const uint32_t last_valid = (R & 31) ? ((1u << (R & 31)) - 1u) : 0xffffffffu;
-  const uint32_t w_last = f[(W - 1) * stride] & last_valid;
-  const uint32_t v_first = f[0] & 1u;
+  const uint32_t w_last = active ? f[(W - 1) * stride] & last_valid : 0u;
+  const uint32_t v_first = active ? f[0] & 1u : 0u;
   const uint32_t v_last = (w_last >> ((R - 1) & 31)) & 1u;
   const bool backward = (v_first == 1u) && (v_last == 0u);
   double zsr = 0.0, zsi = 0.0, zdr = 0.0, zdi = 0.0;   // Z_rise + Z_fall, Z_fall - Z_rise
-  uint32_t carry = v_last;   // ring predecessor of bin 0
-  for (int w = 0; w < W; ++w) {
-    uint32_t cur = f[w * stride];
-    if (w == W - 1) cur &= last_valid;
-    uint32_t diff = cur ^ ((cur << 1) | carry);   // bit b: V[k] != V[k-1], k = 32w + b
-    if (w == W - 1) diff &= last_valid;
-    carry = (w == W - 1) ? 0u : (cur >> 31);
-    while (diff) {
+  // One flat loop for the whole warp (all 32 lanes call this function, `active` or not): in every iteration a lane
+  // first moves on to the next word if the current one has no edge left, then takes ONE edge; the warp reconverges
+  // between the two halves, so each half always runs with as many lanes as have work.  (A loop over the edges of a
+  // word inside a loop over the words makes the warp wait, in every word, for the lane with the most edges there.)
+  int w = -1;
+  uint32_t cur = 0u, diff = 0u, carry = v_last;        // carry: ring predecessor of bin 0
+  bool done = !active;
+  while (__any_sync(0xffffffffu, !done)) {
+    if (!done && diff == 0u) {
+      if (++w >= W) {
+        done = true;
+      } else {
+        cur = f[w * stride];
+        if (w == W - 1) cur &= last_valid;
+        diff = cur ^ ((cur << 1) | carry);             // bit b: V[k] != V[k-1], k = 32w + b
+        if (w == W - 1) diff &= last_valid;
+        carry = cur >> 31;
+      }
+    }
+    __syncwarp();
+    if (diff) {
       const int b = __ffs(diff) - 1;
       diff &= diff - 1;
       const int k = (w << 5) + b;
@@ -486,6 +499,7 @@ __device__ __forceinline__ FlockTerms vf_flock_terms_edges(const uint32_t* f, in
       zsr += e.x; zsi += e.y;
       zdr = fma(sg, e.x, zdr); zdi = fma(sg, e.y, zdi);
     }
+    __syncwarp();
   }
   double Sc = a.kappa_r * zdr - a.kappa_i * zdi, Ss = a.kappa_r * zdi + a.kappa_i * zdr;
   if (v_last) { Sc += lut[R].pc; Ss += lut[R].ps; }      // run reaching the end of the row
@@ -571,24 +585,30 @@ __device__ __forceinline__ uint32_t flipped_word(const uint32_t* f, int stride, 
 // integrals, heading / speed / position update, walls or torus, outputs.
 // b: replicate, i: agent index in the replicate, li: index in this engine's tile,
 // padrow: padded word 0 of the agent's row (stride in words), me: (x, y, radius, cull^2).
+// Called by ALL lanes of the warp (the edge loop reconverges the warp with full-mask votes); lanes without an agent
+// pass active = false and touch no memory.
 template <bool TORUS>
 __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, int i, int li, uint32_t* padrow,
-                                                  int stride, float4 me, float th, uint32_t etab_s = 0u) {
-  vf_fold_padding(padrow, stride, a.R, a.W);
+                                                  int stride, float4 me, float th, uint32_t etab_s, bool active) {
+  if (active) vf_fold_padding(padrow, stride, a.R, a.W);
   uint32_t* myrow = padrow + stride;   // real word 0
   const size_t gi = (size_t)b * a.N + i;
   const VFParams6 prm = *reinterpret_cast<const VFParams6*>(a.params + (size_t)b * a.param_stride);
   double A0 = prm.alp0, B0 = prm.bet0, V0 = prm.v0;            // vf_supcalc.py:191-196
-  if (a.ov_alp0) { const float v = a.ov_alp0[gi]; if (v == v) A0 = v; }
-  if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
-  if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
-  const double vel0 = a.vel[gi];
+  double vel0 = 0.0;
+  if (active) {
+    if (a.ov_alp0) { const float v = a.ov_alp0[gi]; if (v == v) A0 = v; }
+    if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
+    if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
+    vel0 = a.vel[gi];
+  }
   FlockTerms ft;
   if (a.phi_ok) {
-    ft = vf_flock_terms_edges(myrow, stride, a, etab_s, vel0, prm, A0, B0, V0);
+    ft = vf_flock_terms_edges(myrow, stride, a, etab_s, vel0, prm, A0, B0, V0, active);
   } else {   // len(PHI) != len(soc_v_field): the reference skips the calculation (vf_agent.py:282-284)
     ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
   }
+  if (!active) return;
   double dpsi = ft.dpsi, dvel = ft.dvel;
   if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
   double nth = wrap_heading_once((double)th + dpsi);            // :295-296

@@ -415,7 +415,12 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     __syncthreads();
     etab_s = sh.queue_s;
   }
-  for (int i = tid; i < N; i += T) vf_agent_epilogue<TORUS>(a, b, i, i, sh.rows + i, Np, rep_in[i], th_in[i], etab_s);
+  for (int i0 = 0; i0 < N; i0 += T) {          // all lanes of a warp go through the epilogue together
+    const int i = i0 + tid;
+    const bool active = i < N;
+    const int ic = active ? i : 0;
+    vf_agent_epilogue<TORUS>(a, b, ic, ic, sh.rows + ic, Np, rep_in[ic], th_in[ic], etab_s, active);
+  }
 }
 
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit) {
