@@ -117,31 +117,16 @@ __device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, uint32_t nb, ui
   return (int)(uint32_t)(prod >> 32) + bh;
 }
 
-// Slow path of one direction (focal f sees object o), run from the round queue by any thread: the
-// complete fp32 evaluation (full-range arctangent for the half width, relative guard band);
-// guard-band hits are queued for fp64, anything else visible is drawn by the general rule (wide
-// intervals, wrap quirks) with atomics.
-template <bool TORUS, int RC>
-static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, uint32_t ag_s, uint32_t rows_s, uint32_t queue_s,
-                                                  uint32_t qcount_s, int Np, int f, int o) {
-  using K = PairK<RC>;
-  if ((f >= a.N) | (o >= a.N)) return;                                // padding agents
-  const float4 fa = lds_f4(ag_s + 16u * (uint32_t)f), oa = lds_f4(ag_s + 16u * (uint32_t)o);
-  if ((fa.x == oa.x) & (fa.y == oa.y)) return;                        // vf_supcalc.py:57
-  float dx = oa.x - fa.x, dy = oa.y - fa.y;
-  if (TORUS) {
-    if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
-    if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
-  }
-  const float d2 = fmaf(dx, dx, dy * dy);
-  const float q = a.sym_radius * rsqrt_approx(d2);
-  const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
-  const float yr = y + kMagic;
-  const int h = __float_as_int(yr) - kMagicBits;
-  bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
+// Slow path of one pair {i, j}; dirs bit 0: i sees j is off the fast path, bit 1: j sees i.  The complete fp32
+// evaluation (full-range arctangent for the half width, relative guard band), shared by both directions like on the
+// fast path; guard-band hits are queued for fp64, anything else visible is drawn by the general rule (wide
+// intervals, wrap quirks) with reductions.
+template <int RC>
+__device__ __forceinline__ void sym_slow_dir(const VFKernelArgs& a, uint32_t rows_s, uint32_t queue_s, uint32_t qcount_s,
+                                             uint32_t stride_b, int f, int o, uint32_t nb, uint32_t hconst, int h,
+                                             bool flagged) {
   const int R = RC ? RC : a.R;
-  const int k = sym_side_k<RC>(a, sym_bearing_bits(dx, dy, kBearingA6), __float_as_uint(fa.z), 0, flagged);   // bin index
-  const uint32_t stride_b = 4u * (uint32_t)Np;
+  const int k = sym_side_k<RC>(a, nb, hconst, 0, flagged);           // bin index
   const uint32_t row_s = rows_s + stride_b + 4u * (uint32_t)f;        // real word 0
   if (flagged) {
     const int slot = (int)atom_add_shared(qcount_s, 1u);              // keeps counting past the capacity
@@ -158,22 +143,44 @@ static __device__ __noinline__ void sym_slow_side(const VFKernelArgs& a, uint32_
     vf_draw_shared(row_s, stride_b, R, a.fov_px0, a.fov_px1, k, h);
   }
 }
+template <bool TORUS, int RC>
+static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_t ag_s, uint32_t rows_s, uint32_t queue_s,
+                                                  uint32_t qcount_s, int Np, int i, int j, uint32_t dirs) {
+  using K = PairK<RC>;
+  if ((i >= a.N) | (j >= a.N)) return;                                // padding agents
+  const float4 ia = lds_f4(ag_s + 16u * (uint32_t)i), ja = lds_f4(ag_s + 16u * (uint32_t)j);
+  if ((ia.x == ja.x) & (ia.y == ja.y)) return;                        // vf_supcalc.py:57
+  float dx = ja.x - ia.x, dy = ja.y - ia.y;
+  if (TORUS) {
+    if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
+    if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+  }
+  const float d2 = fmaf(dx, dx, dy * dy);
+  const float q = a.sym_radius * rsqrt_approx(d2);
+  const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
+  const float yr = y + kMagic;
+  const int h = __float_as_int(yr) - kMagicBits;
+  const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
+  const uint32_t nb = sym_bearing_bits(dx, dy, kBearingA6);           // bearing of j seen from i
+  const uint32_t stride_b = 4u * (uint32_t)Np;
+  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
+  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
+}
 
-// One entry of the slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own agent
-// sees the partner of the even step / is seen by it, bits 2 / 3: the same for the odd step, whose partner index
-// differs in bit 0.  Walk through the flagged directions (draws are atomic).
-// For a whole (converged) warp, one entry per lane (0: none): the lanes walk through their flagged directions
-// in lock step, so that the out-of-line evaluation always runs with as many lanes as there are entries left.
+// One entry of a warp's slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own
+// agent sees the partner of the even step / is seen by it, bits 2 / 3: the same for the odd step, whose partner index
+// differs in bit 0.  For a whole (converged) warp, one entry per lane (0: none): the lanes walk through their flagged
+// pairs in lock step, so that the out-of-line evaluation always runs with as many lanes as there are entries left.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_slow_entries_warp(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
   uint32_t flags = ent >> 20;
   const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
   while (__any_sync(0xffffffffu, flags != 0u)) {
     if (flags) {
-      const int bit = __ffs(flags) - 1;
-      flags &= flags - 1;
-      const int j = jA ^ (bit >> 1);
-      sym_slow_side<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (bit & 1) ? j : i, (bit & 1) ? i : j);
+      const bool odd = (flags & 3u) == 0u;                  // nothing (left) for the even step: take the odd one
+      const uint32_t dirs = odd ? flags >> 2 : flags & 3u;
+      flags = odd ? 0u : flags & 12u;
+      sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, i, jA ^ (odd ? 1 : 0), dirs);
     }
     __syncwarp();
   }
