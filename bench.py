@@ -281,22 +281,24 @@ def main():
         launches = args.steps
 
         # ---- end-to-end arm: host buffers in, host buffers out, every step ----
-        hx, hy, hth, hv, hr = (torch.from_numpy(a).pin_memory() for a in (x, y, th, v, rad))
-        ox, oy, oth, ov = (torch.empty(B, N).pin_memory() for _ in range(4))
-        h_in = [t.numpy() for t in (hx, hy, hth, hv, hr)]
-        h_out = {"x": ox.numpy(), "y": oy.numpy(), "theta": oth.numpy(), "vel": ov.numpy()}
-        e2e_steps = max(3, min(args.steps, 10))
+        # two sets of pinned host buffers used in turn: the state a step returns is the next step's input
+        hr = torch.from_numpy(rad).pin_memory().numpy()
+        host = [{k: torch.from_numpy(a.copy()).pin_memory().numpy() for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v))}
+                for _ in range(2)]
+        e2e_steps = max(3, min(args.steps, 20))
+        cur = 0
         for _ in range(2):
-            eng.set_state(*h_in); eng.step(1); eng.get_state(h_out)
+            eng.set_state(host[cur]["x"], host[cur]["y"], host[cur]["theta"], host[cur]["vel"], hr)
+            eng.step(1); eng.get_state(host[cur ^ 1]); cur ^= 1
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(e2e_steps):
-            eng.set_state(*h_in)               # H2D of the step's inputs (pinned)
+            h = host[cur]
+            eng.set_state(h["x"], h["y"], h["theta"], h["vel"], hr)   # H2D of the step's inputs (pinned)
             eng.step(1)
-            eng.get_state(h_out)               # D2H of the step's result
-            for k, a in zip(("x", "y", "theta", "vel"), h_in):   # feed the result back (host memcpy)
-                np.copyto(a, h_out[k])
+            eng.get_state(host[cur ^ 1])                              # D2H of the step's result (pinned)
+            cur ^= 1
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
