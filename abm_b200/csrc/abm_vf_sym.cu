@@ -342,17 +342,22 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   const uint32_t wq = smem_u32(sh.warpq + kSymWarpQ * warp);   // this warp's queue of slow entries
   int wcount = 0;                              // entries in it (warp-uniform)
 
-  // ---- diagonal blocks: two per warp, every lane draws its own side of {l, l ^ s} ----
-  for (int d = 0; d < 2; ++d) {
-    const int I = 2 * warp + d;
-    const int i = (I << 5) + lane;
-    const float4 me = sh.ag[i];
-    const uint32_t rec_i0 = ag_s + 16u * (uint32_t)i, row_i = rows_s + 4u * (uint32_t)i;
+  // ---- diagonal blocks, two per warp: the pair {x, x ^ s} of a block is taken, in step s, by the one of its two
+  //      lanes whose bit hb(s) (the highest set bit of s) is clear -- for the warp's first block; for its second block
+  //      by the lane whose bit is set.  So every lane has a pair in every step, each unordered pair of both blocks is
+  //      evaluated once, and own / partner rows of a warp instruction still hit 32 different banks. ----
+  {
+    const float4 me0 = sh.ag[(2 * warp << 5) + lane], me1 = sh.ag[((2 * warp + 1) << 5) + lane];
 #pragma unroll 1
     for (int s = 1; s < 32; ++s) {
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, false>(a, lds_f4(rec_i0 ^ (16u * s)), me.x, me.y, __float_as_uint(me.z), c);
-      sym_red(row_i, stride_b, A.ps_i, A.mask);
-      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, i ^ s, A.slow_i, false, false, false);
+      const int sel = (lane >> (31 - __clz(s))) & 1;
+      const int i = ((2 * warp + sel) << 5) + lane, j = i ^ s;
+      const float4 me = sel ? me1 : me0;
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, lds_f4(ag_s + 16u * (uint32_t)j), me.x, me.y,
+                                                            __float_as_uint(me.z), c);
+      sym_red(rows_s + 4u * (uint32_t)i, stride_b, A.ps_i, A.mask);
+      sym_red(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask);
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j, false, false);
     }
   }
 
