@@ -120,6 +120,7 @@ struct abm_engine {
   DevBuf<unsigned char> sort_temp;
   size_t sort_temp_bytes = 0;
   DevBuf<float4> tile_bbox;   // culling by record tiles (CULL variants on sorted state)
+  DevBuf<float> metrics;      // abm_vf_metrics staging (allocated on first use)
   DevBuf<float> tile_cull2;
 };
 
@@ -265,7 +266,7 @@ int abm_destroy(abm_engine_t* e) {
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
-  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release();
+  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release(); e->metrics.release();
   e->radius_minmax.release();
   delete e;
   return ABM_OK;
@@ -520,6 +521,27 @@ int abm_get_counters(abm_engine_t* e, uint64_t counters[4], void* stream) {
   ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   counters[0] = h[0]; counters[1] = h[1]; counters[2] = h[2];
   counters[3] = e->launches;
+  return ABM_OK;
+}
+
+int abm_vf_metrics(abm_engine_t* e, float* out, int on_device, void* stream) {
+  if (!e || !out) return fail(ABM_E_INVALID, "abm_vf_metrics: null argument");
+  if (!e->state_set) return fail(ABM_E_STATE, "abm_vf_metrics: no state has been set");
+  if (e->tile_count != e->cfg.n_agents) return fail(ABM_E_INVALID, "abm_vf_metrics: not available on a tiled engine");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = e->cfg.n_replicates;
+  if (sizeof(float2) * (size_t)e->cfg.n_agents > 48 * 1024)
+    return fail(ABM_E_INVALID, "abm_vf_metrics: more than 6144 agents per replicate are not supported");
+  if (!e->metrics.p) ABM_CUDA(e->metrics.alloc(4 * (size_t)B));
+  float* dst = on_device ? out : e->metrics.p;
+  abm::launch_vf_metrics(e->rec[e->cur].p, e->theta.p, B, e->cfg.n_agents, e->cfg.boundary == ABM_BOUNDARY_INFINITE ? 1 : 0,
+                         e->cfg.width, e->cfg.height, dst, st);
+  ABM_CUDA(cudaGetLastError());
+  if (!on_device) {
+    ABM_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    ABM_CUDA(cudaStreamSynchronize(st));
+  }
   return ABM_OK;
 }
 

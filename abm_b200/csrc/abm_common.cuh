@@ -111,6 +111,11 @@ void launch_pack_records(const float* x, const float* y, const float* r, const i
 void launch_unpack_records(const float4* rec, const int* perm, int N, float* x, float* y, long long n,
                            cudaStream_t stream);
 
+// summary metrics (abm_metrics.cu): out[b * 4 + {0: polarization, 1: mean inter-individual distance, 2: mean nearest-
+// neighbour distance, 3: collision flag}]
+void launch_vf_metrics(const float4* rec, const float* theta, int B, int N, int torus, float width, float height, float* out,
+                       cudaStream_t stream);
+
 // spatial re-ordering (abm_vf_sort.cu)
 size_t vf_sort_temp_bytes(int B, int N);
 cudaError_t vf_sort_order(const float4* rec, int B, int N, float x0, float y0, float extent, void* temp, size_t temp_bytes,

@@ -212,6 +212,16 @@ class VFEngine:
         _lib.check(self._lib.abm_vf_internal_arrays(self._h, C.byref(t), C.byref(v)), "abm_vf_internal_arrays")
         return int(t.value), int(v.value)
 
+    def metrics(self) -> dict:
+        """Per-replicate summary metrics of the current state, computed on the device (the
+        quantities of abm/loader/data_loader.py): dict of (B,) float32 arrays `polarization`, `mean_iid`,
+        `mean_nn_dist`, `collision` (1.0 where some pair is closer than 2 * radius)."""
+        out = np.empty((self.B, 4), np.float32)
+        _lib.check(self._lib.abm_vf_metrics(self._h, C.c_void_p(out.ctypes.data), 0, C.c_void_p(_current_stream())),
+                   "abm_vf_metrics")
+        return dict(polarization=out[:, 0].copy(), mean_iid=out[:, 1].copy(), mean_nn_dist=out[:, 2].copy(),
+                    collision=out[:, 3].copy())
+
     def last_kernel(self) -> str:
         """Name of the step kernel the last step() launched."""
         return (self._lib.abm_vf_last_kernel(self._h) or b"").decode()

@@ -156,6 +156,14 @@ int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev);
  * culling -> symmetric); the environment variable ABM_VF_KERNEL=onesided|symmetric overrides it for tests. */
 const char* abm_vf_last_kernel(abm_engine_t* e);
 
+/* Summary metrics of the current state, per replicate (the quantities abm/loader/data_loader.py computes
+ * offline from logged trajectories: calculate_polarization :1761-1836, calculate_interindividual_distance :1367-1460,
+ * calculate_mean_NN_dist :1461-1488, calculate_collision_time :1838-1869).  out[b * 4 + k], k = 0: polarization
+ * |sum_i (cos theta_i, sin theta_i)| / N; 1: mean distance over pairs i < j (minimal image with BOUNDARY infinite);
+ * 2: mean over agents of the distance to the nearest other agent; 3: 1.0 if any pair is closer than 2 * radius (the
+ * reference's agent-agent collision criterion; its time average is the "aacoll" fraction), else 0.0. */
+int abm_vf_metrics(abm_engine_t* e, float* out, int on_device, void* stream);
+
 int abm_synchronize(abm_engine_t* e, void* stream);
 
 /* ---- stateless function-level entry points (host pointers, synchronous) ---- */

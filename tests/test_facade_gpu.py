@@ -1,4 +1,6 @@
 """GPU tests of the class-level drop-in interface (Simulation / VFSimulation / MetaProtocol)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -85,3 +87,36 @@ def test_tiled_swarm_matches_single_gpu_if_two_gpus(built_lib):
                         "--master-addr", "127.0.0.1", "--master-port", "29544",
                         os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTIGPU_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
+    """per-step state appended on the device, chunks copied out asynchronously and written as the
+    reference's `ag_*.zarr` arrays (ifdb.py:470-508: shape (num_agents, T), float64; posx / posy int-truncated
+    like ifdb.py:83-84) -- checked against per-step get_state() and by parsing the zarr-v2 metadata."""
+    import json
+    from abm_b200 import VFEngine
+    from abm_b200.recorder import VFRecorder, read_zarr_v2
+    rng = np.random.default_rng(3)
+    B, N, W, T = 4, 40, 500.0, 11
+    x = rng.uniform(60, W, (B, N)).astype(np.float32); y = rng.uniform(60, W, (B, N)).astype(np.float32)
+    th = rng.uniform(0, 2 * np.pi, (B, N)).astype(np.float32); v = rng.uniform(0, 2, (B, N)).astype(np.float32)
+    eng = VFEngine(B, N, resolution=1200, width=W, height=W)
+    eng.set_params(); eng.set_state(x, y, th, v, 10.0)
+    rec = VFRecorder(eng, str(tmp_path / "run"), replicates=[0, 2], every=1, chunk=4, env_params={"N": N, "T": T})
+    expect = []
+    for _ in range(T):
+        eng.step(1)
+        rec.record()
+        expect.append(eng.get_state())
+    dirs = rec.close()
+    assert [os.path.basename(d) for d in dirs] == ["replicate_00000", "replicate_00002"]
+    for d, b in zip(dirs, (0, 2)):
+        meta = json.load(open(os.path.join(d, "ag_posx.zarr", ".zarray")))
+        assert meta["shape"] == [N, T] and meta["chunks"] == [N, 4] and meta["dtype"] == "<f8" and meta["zarr_format"] == 2
+        assert json.load(open(os.path.join(d, "env_params.json")))["T"] == T
+        for name, key, trunc in (("posx", "x", True), ("posy", "y", True), ("ori", "theta", False), ("vel", "vel", False)):
+            got = read_zarr_v2(os.path.join(d, f"ag_{name}.zarr"))
+            want = np.stack([e[key][b].astype(np.float64) for e in expect], axis=1)
+            assert np.array_equal(got, np.trunc(want) if trunc else want), name
+        assert not read_zarr_v2(os.path.join(d, "ag_mode.zarr")).any()
+    eng.close()

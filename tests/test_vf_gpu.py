@@ -341,3 +341,40 @@ def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, b
     for k in ("x", "y", "theta", "vel"):
         assert np.array_equal(a[4][k], b[4][k]), k
     print("fp64 pairs onesided / symmetric:", a[5]["fp64_pairs"], b[5]["fp64_pairs"])
+
+
+@pytest.mark.parametrize("boundary", ["walls", "infinite"])
+def test_summary_metrics_match_numpy(built_lib, boundary):
+    """On-device per-replicate summary metrics against the formulas of the reference's offline
+    analysis (data_loader.py: polarization :1817-1823, inter-individual distance restricted to the upper
+    triangle :1440-1452 with supcalc.distance_torus on the torus, nearest-neighbour distance :1480-1485,
+    collision criterion iid < 2 * RADIUS_AGENT :1860-1861), evaluated in float64 numpy on the same state."""
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(5)
+    B, N, W = 6, 173, 700.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    x[1] = rng.uniform(300, 340, N); y[1] = rng.uniform(300, 340, N)        # a crowded replicate: collisions
+    spread = np.linspace(60, 640, N).astype(np.float32)
+    x[2], y[2] = spread, spread[::-1].copy()                                 # a sparse one: none
+    th[3] = 1.0                                                              # fully polarized
+    eng = VFEngine(B, N, resolution=1200, width=W, height=W, boundary=boundary)
+    eng.set_params(); eng.set_state(x, y, th, v, 10.0)
+    for _ in range(2):                                                       # before and after a step
+        st = eng.get_state()
+        m = eng.metrics()
+        for b in range(B):
+            X, Y, T = (st[k][b].astype(np.float64) for k in ("x", "y", "theta"))
+            pol = np.hypot(np.cos(T).sum(), np.sin(T).sum()) / N
+            dx = np.abs(X[:, None] - X[None, :]); dy = np.abs(Y[:, None] - Y[None, :])
+            if boundary == "infinite":
+                dx = np.where(dx > W / 2, W - dx, dx); dy = np.where(dy > W / 2, W - dy, dy)
+            d = np.hypot(dx, dy)
+            iu = np.triu_indices(N, k=1)
+            dn = d.copy(); np.fill_diagonal(dn, np.inf)
+            np.testing.assert_allclose(m["polarization"][b], pol, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(m["mean_iid"][b], d[iu].mean(), rtol=1e-5)
+            np.testing.assert_allclose(m["mean_nn_dist"][b], dn.min(axis=1).mean(), rtol=1e-5)
+            assert m["collision"][b] == float(((d[iu] > 0) & (d[iu] < 20.0)).any())
+        eng.step(1)
+    assert m["collision"][1] == 1.0 and m["polarization"].max() <= 1.0 + 1e-6
+    eng.close()
