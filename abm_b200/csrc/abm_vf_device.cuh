@@ -11,6 +11,8 @@
 //   Agent.reflect_from_walls / prove_orientation   agent.py:347-394, 605-610
 //   VFAgent.teleport_infinite_arena      vf_agent.py:188-204
 #pragma once
+#include <type_traits>
+
 #include "abm_common.cuh"
 
 namespace abm {
@@ -474,33 +476,40 @@ __device__ __forceinline__ FlockTerms vf_flock_terms_edges(const uint32_t* f, in
   // first moves on to the next word if the current one has no edge left, then takes ONE edge; the warp reconverges
   // between the two halves, so each half always runs with as many lanes as have work.  (A loop over the edges of a
   // word inside a loop over the words makes the warp wait, in every word, for the lane with the most edges there.)
-  int w = -1;
-  uint32_t cur = 0u, diff = 0u, carry = v_last;        // carry: ring predecessor of bin 0
-  bool done = !active;
-  while (__any_sync(0xffffffffu, !done)) {
-    if (!done && diff == 0u) {
-      if (++w >= W) {
-        done = true;
-      } else {
-        cur = f[w * stride];
-        if (w == W - 1) cur &= last_valid;
-        diff = cur ^ ((cur << 1) | carry);             // bit b: V[k] != V[k-1], k = 32w + b
-        if (w == W - 1) diff &= last_valid;
-        carry = cur >> 31;
+  // (vf_fold_padding has cleared the bits at and beyond bin R of the last word; only the difference needs the mask.)
+  auto edge_loop = [&](auto smem_tab) {
+    int w = -1;
+    uint32_t cur = 0u, diff = 0u, carry = v_last;        // carry: ring predecessor of bin 0
+    bool done = !active;
+    while (__any_sync(0xffffffffu, !done)) {
+      if (!done && diff == 0u) {
+        if (++w >= W) {
+          done = true;
+        } else {
+          cur = f[w * stride];
+          diff = cur ^ ((cur << 1) | carry);             // bit b: V[k] != V[k-1], k = 32w + b
+          if (w == W - 1) diff &= last_valid;
+          carry = cur >> 31;
+        }
       }
+      __syncwarp();
+      if (diff) {
+        const int b = __ffs(diff) - 1;
+        diff &= diff - 1;
+        const int k = (w << 5) + b;
+        double2 e;
+        if (decltype(smem_tab)::value) e = lds_d2(etab_s + 16u * (uint32_t)k);
+        else e = *reinterpret_cast<const double2*>(&lut[k].c);
+        // rising edge (run starts at k, V[k] = 1) counts into Z_rise: negative in Z_fall - Z_rise
+        const int sgn = (int)((cur >> b) << 31);
+        zsr += e.x; zsi += e.y;
+        zdr += __hiloint2double(__double2hiint(e.x) ^ sgn, __double2loint(e.x));
+        zdi += __hiloint2double(__double2hiint(e.y) ^ sgn, __double2loint(e.y));
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    if (diff) {
-      const int b = __ffs(diff) - 1;
-      diff &= diff - 1;
-      const int k = (w << 5) + b;
-      const double2 e = etab_s ? lds_d2(etab_s + 16u * (uint32_t)k) : *reinterpret_cast<const double2*>(&lut[k].c);
-      const double sg = ((cur >> b) & 1u) ? -1.0 : 1.0;   // rising edge (run starts at k): Z_rise
-      zsr += e.x; zsi += e.y;
-      zdr = fma(sg, e.x, zdr); zdi = fma(sg, e.y, zdi);
-    }
-    __syncwarp();
-  }
+  };
+  if (etab_s) edge_loop(std::true_type{}); else edge_loop(std::false_type{});
   double Sc = a.kappa_r * zdr - a.kappa_i * zdi, Ss = a.kappa_r * zdi + a.kappa_i * zdr;
   if (v_last) { Sc += lut[R].pc; Ss += lut[R].ps; }      // run reaching the end of the row
   const double rc = backward ? 1.0 : a.rot_c, rs = backward ? 0.0 : -a.rot_s;   // exp(-i d) under the forward rule
