@@ -119,6 +119,7 @@ SYMBOLS = {
     "abm_vf_record_table": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
     "abm_vf_last_kernel": (C.c_char_p, [_P]),
     "abm_vf_metrics": (C.c_int, [_P, _P, C.c_int, _P]),
+    "abm_vf_slow_entries": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P]),
     "abm_vf_get_permutation": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_vf_resort": (C.c_int, [_P, _P]),
     "abm_vf_internal_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),

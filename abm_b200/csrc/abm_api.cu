@@ -111,6 +111,13 @@ struct abm_engine {
   bool state_set = false;
   unsigned long long launches = 0;
   const char* last_kernel = "";
+  // adaptive kernel choice: the symmetric kernel reports how many lane entries left its fast path; in crowded scenes
+  // (most intervals wider than 32 bins) the one-thread-per-focal-agent kernel is faster (both give identical results)
+  unsigned long long* slow_host = nullptr;   // pinned copy of counters[4]
+  cudaEvent_t slow_event = nullptr;
+  bool slow_pending = false;
+  unsigned long long slow_seen = 0, sym_launches = 0, slow_req_launch = 0, slow_seen_launch = 0;
+  int onesided_steps_left = 0;
   size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // spatial ordering (ABM_VF_SPATIAL_SORT)
   bool sort_enabled = false, needs_sort = false, perm_identity = true;
@@ -226,7 +233,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   A(e->stage_r.alloc(e->n_total));
   A(e->params.alloc((size_t)cfg->n_replicates * ABM_VF_NPARAM));
   A(e->lut.alloc(e->grid.lut.size()));
-  A(e->counters.alloc(4));
+  A(e->counters.alloc(8));
   A(e->radius_minmax.alloc(2));
   e->sort_enabled = (cfg->flags & ABM_VF_SPATIAL_SORT) != 0 && cfg->n_agents >= 64;
   if (e->sort_enabled) {
@@ -242,7 +249,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   if (cfg->flags & ABM_VF_KEEP_TERMS) A(e->terms.alloc(e->n_tile * 6));
   if (err == cudaSuccess) err = cudaMemcpy(e->lut.p, e->grid.lut.data(), sizeof(abm::PhiLut) * e->grid.lut.size(),
                                            cudaMemcpyHostToDevice);
-  if (err == cudaSuccess) err = cudaMemset(e->counters.p, 0, 4 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(e->counters.p, 0, 8 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(e->rec[0].p, 0, sizeof(float4) * e->n_total);
   if (err == cudaSuccess) err = cudaMemset(e->rec[1].p, 0, sizeof(float4) * e->n_total);
   const double defaults[ABM_VF_NPARAM] = {0.1, 1.0, 1.0, 0.09, 1.0, 0.09};   // vf_params.py:12-19 defaults
@@ -268,6 +275,8 @@ int abm_destroy(abm_engine_t* e) {
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
   e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release(); e->metrics.release();
   e->radius_minmax.release();
+  if (e->slow_host) cudaFreeHost(e->slow_host);
+  if (e->slow_event) cudaEventDestroy(e->slow_event);
   delete e;
   return ABM_OK;
 }
@@ -459,11 +468,27 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   // forces the one-thread-per-focal-agent kernel (abm_vf.cu)
   const char* force = getenv("ABM_VF_KERNEL");
   a.sym_radius = e->r_max;
-  const bool use_sym = !(force && strcmp(force, "onesided") == 0) &&
-                       abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
+  const bool sym_ok = !(force && strcmp(force, "onesided") == 0) && abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
+  const bool adaptive = sym_ok && !force;
+  if (adaptive && !e->slow_host) {
+    ABM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->slow_host), sizeof(unsigned long long)));
+    ABM_CUDA(cudaEventCreateWithFlags(&e->slow_event, cudaEventDisableTiming));
+    *e->slow_host = 0;
+  }
   const bool tiled = e->tile_count != e->cfg.n_agents;
   for (int s = 0; s < n_steps; ++s) {
     // (the symmetric kernel wants NO spatial order: its blocks should all hold the same mix of near and far pairs)
+    // ---- kernel of this step ----
+    if (adaptive && e->slow_pending && cudaEventQuery(e->slow_event) == cudaSuccess) {
+      e->slow_pending = false;
+      const unsigned long long entries = *e->slow_host - e->slow_seen;      // of the symmetric launches since the last look
+      const unsigned long long n_launch = e->slow_req_launch - e->slow_seen_launch;
+      e->slow_seen = *e->slow_host; e->slow_seen_launch = e->slow_req_launch;
+      const double lane_iters = 0.25 * (double)a.B * (double)a.N * (double)(a.N - 1);   // 2 unordered pairs each
+      if (n_launch && (double)entries > 0.18 * lane_iters * (double)n_launch) e->onesided_steps_left = 64;   // crowded
+    }
+    bool use_sym = sym_ok;
+    if (adaptive && e->onesided_steps_left > 0) { use_sym = false; --e->onesided_steps_left; }
     if (e->sort_enabled && !use_sym && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
                                                            e->steps_since_sort >= e->cfg.resort_every))) {
       int rc = resort_engine(e, st);
@@ -486,6 +511,13 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     if (use_sym) abm::launch_vf_step_sym(a, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
     e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : "abm::vf_step_kernel";
+    if (use_sym) ++e->sym_launches;
+    if (adaptive && use_sym && !e->slow_pending) {
+      e->slow_req_launch = e->sym_launches;
+      ABM_CUDA(cudaMemcpyAsync(e->slow_host, e->counters.p + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      ABM_CUDA(cudaEventRecord(e->slow_event, st));
+      e->slow_pending = true;
+    }
     e->cur ^= 1;
     ++e->launches;
   }
@@ -542,6 +574,17 @@ int abm_vf_metrics(abm_engine_t* e, float* out, int on_device, void* stream) {
     ABM_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
     ABM_CUDA(cudaStreamSynchronize(st));
   }
+  return ABM_OK;
+}
+
+int abm_vf_slow_entries(abm_engine_t* e, uint64_t* entries, uint64_t* sym_launches, void* stream) {
+  if (!e || !entries) return fail(ABM_E_INVALID, "abm_vf_slow_entries: null argument");
+  ABM_CUDA(cudaSetDevice(e->device));
+  unsigned long long h = 0;
+  ABM_CUDA(cudaMemcpyAsync(&h, e->counters.p + 4, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  *entries = h;
+  if (sym_launches) *sym_launches = e->sym_launches;
   return ABM_OK;
 }
 

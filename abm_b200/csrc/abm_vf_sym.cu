@@ -50,7 +50,7 @@ struct SymShared {
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
   uint32_t* warpq;     // [warps][kSymWarpQ] per-warp ring of lane entries with directions off the fast path
-  int* qcount;         // [0]: fp64 queue
+  int* qcount;         // [0]: fp64 queue, [1]: lane entries off the fast path (statistics)
   uint32_t ag_s, rows_s, queue_s, qcount_s;   // shared-space addresses of the above (code that is not inlined)
   int Np, N;
 };
@@ -206,6 +206,7 @@ __device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared&
     wcount += __popc(bal);
     if (wcount >= 32) {
       wcount -= 32;
+      if (lane == 0) atom_add_shared(sh.qcount_s + 4u, 32u);   // statistics: entries off the fast path (kernel choice)
       __syncwarp();
       sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
       __syncwarp();
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     sh.ag[j] = v;
   }
   for (int w = tid; w < (a.W + 3) * Np; w += T) sh.rows[w] = 0u;
-  if (tid == 0) sh.qcount[0] = 0;
+  if (tid < 2) sh.qcount[tid] = 0;
   __syncthreads();
 
   const float S = K::y_scale(a);
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   }
   // the rest of the warp's queue (fewer than 32 entries)
   __syncwarp();
+  if (lane == 0) atom_add_shared(sh.qcount_s + 4u, (uint32_t)wcount);
   sym_slow_batch<TORUS, RC>(a, sh, lane < wcount ? lds_u32(wq + 4u * (uint32_t)lane) : 0u);
   __syncthreads();
 
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     const unsigned nm = __reduce_add_sync(0xffffffffu, n_mismatch);
     if (lane == 0 && nm) atomicAdd(&a.counters[2], (unsigned long long)nm);
     if (tid == 0 && sh.qcount[0]) atomicAdd(&a.counters[0], (unsigned long long)sh.qcount[0]);
+    if (tid == 0 && sh.qcount[1]) atomicAdd(&a.counters[4], (unsigned long long)sh.qcount[1]);
   }
 
   // ---- epilogue: one agent per thread and pass (bank == lane) ----

@@ -222,6 +222,13 @@ class VFEngine:
         return dict(polarization=out[:, 0].copy(), mean_iid=out[:, 1].copy(), mean_nn_dist=out[:, 2].copy(),
                     collision=out[:, 3].copy())
 
+    def slow_entries(self) -> tuple[int, int]:
+        """(lane entries off the symmetric kernel's fast path so far, number of its launches)."""
+        n, l = C.c_uint64(), C.c_uint64()
+        _lib.check(self._lib.abm_vf_slow_entries(self._h, C.byref(n), C.byref(l), C.c_void_p(_current_stream())),
+                   "abm_vf_slow_entries")
+        return int(n.value), int(l.value)
+
     def last_kernel(self) -> str:
         """Name of the step kernel the last step() launched."""
         return (self._lib.abm_vf_last_kernel(self._h) or b"").decode()
