@@ -270,7 +270,14 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
     if (tid == 0 && *qcount) atomicAdd(&a.counters[0], (unsigned long long)*qcount);   // all flagged pairs
   }
 
-  vf_agent_epilogue<TORUS>(a, b, active ? i : a.tile_begin, active ? li : 0, padrow, T, me, th, 0u, active);
+  {
+    const int ii[1] = {active ? i : a.tile_begin}, lli[1] = {active ? li : 0};
+    uint32_t* const pr[1] = {padrow};
+    const float4 mm[1] = {me};
+    const float tt[1] = {th};
+    const bool aa[1] = {active};
+    vf_agent_epilogue<TORUS, 1>(a, b, ii, lli, pr, T, mm, tt, 0u, aa);
+  }
 }
 
 template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>

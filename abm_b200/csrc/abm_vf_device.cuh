@@ -461,62 +461,89 @@ __device__ __forceinline__ double2 lds_d2(uint32_t addr) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ FlockTerms vf_flock_terms_edges(const uint32_t* f, int stride, const VFKernelArgs& a,
-                                                           uint32_t etab_s, double vel, const VFParams6& prm,
-                                                           double A0, double B0, double V0, bool active) {
+struct EdgeSums {
+  double zsr, zsi, zdr, zdi;   // Z_rise + Z_fall, Z_fall - Z_rise (real, imaginary)
+  uint32_t v_first, v_last;
+};
+
+// Edge sums of K rows per thread, interleaved in ONE flat loop for the whole warp (all 32 lanes call this, `active` or
+// not): in every iteration a lane first moves each of its rows on to the next word if the current one has no edge
+// left, then takes ONE edge per row; the warp reconverges between the two halves, so each half always runs with as
+// many lanes as have work.  (A loop over the edges of a word inside a loop over the words makes the warp wait, in
+// every word, for the lane with the most edges there; K > 1 gives the latency-bound loop independent work.)
+template <int K>
+__device__ __forceinline__ void vf_edge_sums(const uint32_t* const (&f)[K], int stride, const VFKernelArgs& a,
+                                             uint32_t etab_s, const bool (&active)[K], EdgeSums (&out)[K]) {
   const int R = a.R, W = a.W;
   const PhiLut* __restrict__ lut = a.lut;
   const uint32_t last_valid = (R & 31) ? ((1u << (R & 31)) - 1u) : 0xffffffffu;
-  const uint32_t w_last = active ? f[(W - 1) * stride] & last_valid : 0u;
-  const uint32_t v_first = active ? f[0] & 1u : 0u;
-  const uint32_t v_last = (w_last >> ((R - 1) & 31)) & 1u;
-  const bool backward = (v_first == 1u) && (v_last == 0u);
-  double zsr = 0.0, zsi = 0.0, zdr = 0.0, zdi = 0.0;   // Z_rise + Z_fall, Z_fall - Z_rise
-  // One flat loop for the whole warp (all 32 lanes call this function, `active` or not): in every iteration a lane
-  // first moves on to the next word if the current one has no edge left, then takes ONE edge; the warp reconverges
-  // between the two halves, so each half always runs with as many lanes as have work.  (A loop over the edges of a
-  // word inside a loop over the words makes the warp wait, in every word, for the lane with the most edges there.)
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const uint32_t w_last = active[j] ? f[j][(W - 1) * stride] & last_valid : 0u;
+    out[j].v_first = active[j] ? f[j][0] & 1u : 0u;
+    out[j].v_last = (w_last >> ((R - 1) & 31)) & 1u;
+    out[j].zsr = out[j].zsi = out[j].zdr = out[j].zdi = 0.0;
+  }
   // (vf_fold_padding has cleared the bits at and beyond bin R of the last word; only the difference needs the mask.)
   auto edge_loop = [&](auto smem_tab) {
-    int w = -1;
-    uint32_t cur = 0u, diff = 0u, carry = v_last;        // carry: ring predecessor of bin 0
-    bool done = !active;
-    while (__any_sync(0xffffffffu, !done)) {
-      if (!done && diff == 0u) {
-        if (++w >= W) {
-          done = true;
-        } else {
-          cur = f[w * stride];
-          diff = cur ^ ((cur << 1) | carry);             // bit b: V[k] != V[k-1], k = 32w + b
-          if (w == W - 1) diff &= last_valid;
-          carry = cur >> 31;
+    int w[K];
+    uint32_t cur[K], diff[K], carry[K];
+    bool done[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { w[j] = -1; cur[j] = diff[j] = 0u; carry[j] = out[j].v_last; done[j] = !active[j]; }
+    for (;;) {
+      bool all_done = true;
+#pragma unroll
+      for (int j = 0; j < K; ++j) all_done &= done[j];
+      if (!__any_sync(0xffffffffu, !all_done)) break;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (!done[j] && diff[j] == 0u) {
+          if (++w[j] >= W) {
+            done[j] = true;
+          } else {
+            cur[j] = f[j][w[j] * stride];
+            diff[j] = cur[j] ^ ((cur[j] << 1) | carry[j]);        // bit b: V[k] != V[k-1], k = 32w + b
+            if (w[j] == W - 1) diff[j] &= last_valid;
+            carry[j] = cur[j] >> 31;                              // ring predecessor of the next word's bin 0
+          }
         }
       }
       __syncwarp();
-      if (diff) {
-        const int b = __ffs(diff) - 1;
-        diff &= diff - 1;
-        const int k = (w << 5) + b;
-        double2 e;
-        if (decltype(smem_tab)::value) e = lds_d2(etab_s + 16u * (uint32_t)k);
-        else e = *reinterpret_cast<const double2*>(&lut[k].c);
-        // rising edge (run starts at k, V[k] = 1) counts into Z_rise: negative in Z_fall - Z_rise
-        const int sgn = (int)((cur >> b) << 31);
-        zsr += e.x; zsi += e.y;
-        zdr += __hiloint2double(__double2hiint(e.x) ^ sgn, __double2loint(e.x));
-        zdi += __hiloint2double(__double2hiint(e.y) ^ sgn, __double2loint(e.y));
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (diff[j]) {
+          const int b = __ffs(diff[j]) - 1;
+          diff[j] &= diff[j] - 1;
+          const int k = (w[j] << 5) + b;
+          double2 e;
+          if (decltype(smem_tab)::value) e = lds_d2(etab_s + 16u * (uint32_t)k);
+          else e = *reinterpret_cast<const double2*>(&lut[k].c);
+          // rising edge (run starts at k, V[k] = 1) counts into Z_rise: negative in Z_fall - Z_rise
+          const int sgn = (int)((cur[j] >> b) << 31);
+          out[j].zsr += e.x; out[j].zsi += e.y;
+          out[j].zdr += __hiloint2double(__double2hiint(e.x) ^ sgn, __double2loint(e.x));
+          out[j].zdi += __hiloint2double(__double2hiint(e.y) ^ sgn, __double2loint(e.y));
+        }
       }
       __syncwarp();
     }
   };
   if (etab_s) edge_loop(std::true_type{}); else edge_loop(std::false_type{});
-  double Sc = a.kappa_r * zdr - a.kappa_i * zdi, Ss = a.kappa_r * zdi + a.kappa_i * zdr;
-  if (v_last) { Sc += lut[R].pc; Ss += lut[R].ps; }      // run reaching the end of the row
+}
+
+__device__ __forceinline__ FlockTerms vf_terms_from_edges(const EdgeSums& z, const VFKernelArgs& a, double vel,
+                                                          const VFParams6& prm, double A0, double B0, double V0) {
+  const int R = a.R;
+  const PhiLut* __restrict__ lut = a.lut;
+  const bool backward = (z.v_first == 1u) && (z.v_last == 0u);
+  double Sc = a.kappa_r * z.zdr - a.kappa_i * z.zdi, Ss = a.kappa_r * z.zdi + a.kappa_i * z.zdr;
+  if (z.v_last) { Sc += lut[R].pc; Ss += lut[R].ps; }      // run reaching the end of the row
   const double rc = backward ? 1.0 : a.rot_c, rs = backward ? 0.0 : -a.rot_s;   // exp(-i d) under the forward rule
-  const double Ec = rc * zsr - rs * zsi, Es = rc * zsi + rs * zsr;
+  const double Ec = rc * z.zsr - rs * z.zsi, Es = rc * z.zsi + rs * z.zsr;
   const double c0 = lut[0].c, s0 = lut[0].s, cl = lut[R - 1].c, sl = lut[R - 1].s;
-  const double endc = 0.5 * (c0 * (double)v_first + cl * (double)v_last);
-  const double ends = 0.5 * (s0 * (double)v_first + sl * (double)v_last);
+  const double endc = 0.5 * (c0 * (double)z.v_first + cl * (double)z.v_last);
+  const double ends = 0.5 * (s0 * (double)z.v_first + sl * (double)z.v_last);
   FlockTerms t;
   t.a_blob = A0 * (a.dphi * (endc - Sc));
   t.a_edge = A0 * prm.alp1 * Ec;
@@ -590,59 +617,66 @@ __device__ __forceinline__ uint32_t flipped_word(const uint32_t* f, int stride, 
   return out;
 }
 
-// Per-agent epilogue shared by the step kernels: fold the row padding, edges + flocking
-// integrals, heading / speed / position update, walls or torus, outputs.
-// b: replicate, i: agent index in the replicate, li: index in this engine's tile,
-// padrow: padded word 0 of the agent's row (stride in words), me: (x, y, radius, cull^2).
+// Epilogue shared by the step kernels, K agents per thread: fold the row padding, edges + flocking integrals, heading /
+// speed / position update, walls or torus, outputs.
+// b: replicate, i: agent index in the replicate, li: index in this engine's tile, padrow: padded word 0 of the agent's
+// row (stride in words), me: (x, y, radius, cull^2).
 // Called by ALL lanes of the warp (the edge loop reconverges the warp with full-mask votes); lanes without an agent
 // pass active = false and touch no memory.
-template <bool TORUS>
-__device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, int i, int li, uint32_t* padrow,
-                                                  int stride, float4 me, float th, uint32_t etab_s, bool active) {
-  if (active) vf_fold_padding(padrow, stride, a.R, a.W);
-  uint32_t* myrow = padrow + stride;   // real word 0
-  const size_t gi = (size_t)b * a.N + i;
+template <bool TORUS, int K>
+__device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, const int (&i)[K], const int (&li)[K],
+                                                  uint32_t* const (&padrow)[K], int stride, const float4 (&me)[K],
+                                                  const float (&th)[K], uint32_t etab_s, const bool (&active)[K]) {
   const VFParams6 prm = *reinterpret_cast<const VFParams6*>(a.params + (size_t)b * a.param_stride);
-  double A0 = prm.alp0, B0 = prm.bet0, V0 = prm.v0;            // vf_supcalc.py:191-196
-  double vel0 = 0.0;
-  if (active) {
+  const uint32_t* rows[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (active[j]) vf_fold_padding(padrow[j], stride, a.R, a.W);
+    rows[j] = padrow[j] + stride;      // real word 0
+  }
+  EdgeSums z[K];
+  if (a.phi_ok) vf_edge_sums<K>(rows, stride, a, etab_s, active, z);
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (!active[j]) continue;
+    const size_t gi = (size_t)b * a.N + i[j];
+    double A0 = prm.alp0, B0 = prm.bet0, V0 = prm.v0;            // vf_supcalc.py:191-196
     if (a.ov_alp0) { const float v = a.ov_alp0[gi]; if (v == v) A0 = v; }
     if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
     if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
-    vel0 = a.vel[gi];
-  }
-  FlockTerms ft;
-  if (a.phi_ok) {
-    ft = vf_flock_terms_edges(myrow, stride, a, etab_s, vel0, prm, A0, B0, V0, active);
-  } else {   // len(PHI) != len(soc_v_field): the reference skips the calculation (vf_agent.py:282-284)
-    ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
-  }
-  if (!active) return;
-  double dpsi = ft.dpsi, dvel = ft.dvel;
-  if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
-  double nth = wrap_heading_once((double)th + dpsi);            // :295-296
-  double nv = vel0 + dvel;                                      // :298
-  if (a.limit_movement) nv = limit_abs(nv, a.max_vel);          // :299-300
-  double sn, cn;
-  sincos(nth, &sn, &cn);
-  double nx = (double)me.x + nv * cn;                           // :303-306
-  double ny = (double)me.y - nv * sn;
-  if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
-  else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
+    const double vel0 = a.vel[gi];
+    FlockTerms ft;
+    if (a.phi_ok) {
+      ft = vf_terms_from_edges(z[j], a, vel0, prm, A0, B0, V0);
+    } else {   // len(PHI) != len(soc_v_field): the reference skips the calculation (vf_agent.py:282-284)
+      ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
+    }
+    double dpsi = ft.dpsi, dvel = ft.dvel;
+    if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
+    double nth = wrap_heading_once((double)th[j] + dpsi);         // :295-296
+    double nv = vel0 + dvel;                                      // :298
+    if (a.limit_movement) nv = limit_abs(nv, a.max_vel);          // :299-300
+    double sn, cn;
+    sincos(nth, &sn, &cn);
+    double nx = (double)me[j].x + nv * cn;                        // :303-306
+    double ny = (double)me[j].y - nv * sn;
+    if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me[j].z, a.width_d, a.height_d, a.pad_d);
+    else teleport_torus(nx, ny, (double)me[j].z, a.width_d, a.height_d, a.pad_d);
 
-  a.rec_out[gi] = make_float4((float)nx, (float)ny, me.z, me.w);
-  a.theta[gi] = (float)nth;
-  a.vel[gi] = (float)nv;
+    a.rec_out[gi] = make_float4((float)nx, (float)ny, me[j].z, me[j].w);
+    a.theta[gi] = (float)nth;
+    a.vel[gi] = (float)nv;
 
-  // outputs in API order when the engine keeps an internal (spatially sorted) order
-  const size_t oi = a.perm ? (size_t)b * a.N + a.perm[gi] : (size_t)b * a.tile_count + li;
-  if (a.terms_out) {
-    double* t = a.terms_out + oi * 6;
-    t[0] = ft.dvel; t[1] = ft.dpsi; t[2] = ft.a_blob; t[3] = ft.a_edge; t[4] = ft.b_blob; t[5] = ft.b_edge;
-  }
-  if (a.fields_out) {
-    uint32_t* out = a.fields_out + oi * a.W;
-    for (int ws = 0; ws < a.W; ++ws) out[ws] = flipped_word(myrow, stride, a.R, a.W, ws);
+    // outputs in API order when the engine keeps an internal (spatially sorted) order
+    const size_t oi = a.perm ? (size_t)b * a.N + a.perm[gi] : (size_t)b * a.tile_count + li[j];
+    if (a.terms_out) {
+      double* t = a.terms_out + oi * 6;
+      t[0] = ft.dvel; t[1] = ft.dpsi; t[2] = ft.a_blob; t[3] = ft.a_edge; t[4] = ft.b_blob; t[5] = ft.b_edge;
+    }
+    if (a.fields_out) {
+      uint32_t* out = a.fields_out + oi * a.W;
+      for (int ws = 0; ws < a.W; ++ws) out[ws] = flipped_word(rows[j], stride, a.R, a.W, ws);
+    }
   }
 }
 

@@ -430,11 +430,20 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     __syncthreads();
     etab_s = sh.queue_s;
   }
-  for (int i0 = 0; i0 < N; i0 += T) {          // all lanes of a warp go through the epilogue together
-    const int i = i0 + tid;
-    const bool active = i < N;
-    const int ic = active ? i : 0;
-    vf_agent_epilogue<TORUS>(a, b, ic, ic, sh.rows + ic, Np, rep_in[ic], th_in[ic], etab_s, active);
+  for (int i0 = 0; i0 < N; i0 += 2 * T) {      // all lanes of a warp go through the epilogue together; two agents per
+    int ii[2]; bool aa[2]; uint32_t* pr[2];    // thread give its latency-bound edge loop independent work
+    float4 mm[2]; float tt[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int i = i0 + j * T + tid;
+      aa[j] = i < N;
+      ii[j] = aa[j] ? i : 0;
+      pr[j] = sh.rows + ii[j];
+      mm[j] = rep_in[ii[j]];
+      tt[j] = th_in[ii[j]];
+    }
+    uint32_t* const prc[2] = {pr[0], pr[1]};
+    vf_agent_epilogue<TORUS, 2>(a, b, ii, ii, prc, Np, mm, tt, etab_s, aa);
   }
 }
 
