@@ -41,7 +41,7 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // 53-bit unif
 }
 
 // ---------------------------------------------------------------------------------------
-// environment phase: one thread per replicate, sequential in patch / agent order
+// environment phase: one warp per replicate, patches and agent chunks in the reference's order
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void notify(const BaseAgentPtrs& ag, size_t g, int status, int res_id, uint32_t tau_mask) {
   const int before = ag.env_status[g];                       // sims.py:31-32
@@ -51,92 +51,120 @@ __device__ __forceinline__ void notify(const BaseAgentPtrs& ag, size_t g, int st
   ag.patch_id[g] = res_id;                                   // :39-42 (None -> -1)
 }
 
-__global__ void base_env_kernel(const BaseKernelArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per replicate: lanes take the agents of a chunk of 32 in parallel (membership, bias, notify, teleport),
+// chunks and patches go in the reference's order, and the one truly sequential piece -- the depletion of a patch by
+// its exploiting agents in agent order (sims.py:824-836) -- is replayed by all lanes in lock step over the ballot of
+// the chunk's exploiters.  Per agent the notify sequence is the reference's: on a patch destroyed by agent d in this
+// step, agents i <= d see (+1, -1), agents i > d see (-1, -1); the second notification of each is the destroy loop's
+// (sims.py:829-836), applied after the patch's pass.
+__global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
+  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= a.B) return;
   const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * a.N, p0 = (size_t)b * a.P;
   const double r = a.radius;
-  // "agent is on some patch" marks live in bit 31 of a scratch copy of nothing: recomputed below
   for (int p = 0; p < a.P; ++p) {
     const double prad = a.pa.radius[p0 + p];
     const double pcx = (double)a.pa.x[p0 + p] + prad, pcy = (double)a.pa.y[p0 + p] + prad;
-    bool destroy = false;
-    for (int i = 0; i < a.N; ++i) {
-      const size_t g = a0 + i;
-      const double ddx = ((double)a.ag.x[g] + r) - pcx, ddy = ((double)a.ag.y[g] + r) - pcy;
-      if (!(sqrt(ddx * ddx + ddy * ddy) < prad)) continue;                         // sims.py:45-56
-      // bias_agent_towards_res_center (sims.py:544-552): no wrap of the heading
-      {
+    bool destroy = false;                       // warp-uniform
+    double left = a.pa.left[p0 + p];            // warp-uniform running value (stored as float after every take)
+    for (int c0 = 0; c0 < a.N; c0 += 32) {
+      const int i = c0 + lane;
+      const size_t g = a0 + (i < a.N ? i : 0);
+      bool member = false;
+      if (i < a.N) {
+        const double ddx = ((double)a.ag.x[g] + r) - pcx, ddy = ((double)a.ag.y[g] + r) - pcy;
+        member = sqrt(ddx * ddx + ddy * ddy) < prad;                                 // sims.py:45-56
+      }
+      if (member) {   // bias_agent_towards_res_center (sims.py:544-552): no wrap of the heading
         const double dx = pcx - ((double)a.ag.x[g] + r), dy = pcy - ((double)a.ag.y[g] + r);
         const double th = a.ag.theta[g];
         double cl = fmod(atan2(dy, dx) + th, ABM_TWO_PI_D);
         if (cl < 0.0) cl += ABM_TWO_PI_D;
         a.ag.theta[g] = (float)(th + (cl - ABM_PI_D) * 0.02);
       }
-      if (destroy) {
-        notify(a.ag, g, -1, -1, tau_mask);                                          // :812-813
-      } else {
-        notify(a.ag, g, 1, a.pa.id[p0 + p], tau_mask);                              // :816-818 (pooling_time == 0)
-        if (a.teleport_exploit) {                                                   // :820-821
-          a.ag.x[g] = (float)((double)a.pa.x[p0 + p] + prad - r);
-          a.ag.y[g] = (float)((double)a.pa.y[p0 + p] + prad - r);
-        }
-        if (a.ag.override_mode[g] == OV_EXPLOIT) {                                  // :824-828
-          double take = fmin(prm.consumption, (double)a.pa.quality[p0 + p]);        // rescource.py:121-122
-          double left = a.pa.left[p0 + p];
-          if (left >= take) left -= take; else { take = left; left = 0.0; }
-          a.pa.left[p0 + p] = (float)left;
-          destroy = !(left > 0.0);
-          const float c = a.ag.collected[g];
-          a.ag.collected_before[g] = c;
-          a.ag.collected[g] = (float)((double)c + take);
-          if (destroy) {                                                            // :829-836
-            for (int i2 = 0; i2 < a.N; ++i2) {
-              const size_t g2 = a0 + i2;
-              const double ex = ((double)a.ag.x[g2] + r) - pcx, ey = ((double)a.ag.y[g2] + r) - pcy;
-              if (sqrt(ex * ex + ey * ey) < prad) notify(a.ag, g2, -1, -1, tau_mask);
-            }
+      // ---- depletion in agent order among this chunk's exploiters (only while the patch still exists) ----
+      const bool expl = member && a.ag.override_mode[g] == OV_EXPLOIT;
+      uint32_t eb = destroy ? 0u : __ballot_sync(0xffffffffu, expl);
+      int d_lane = destroy ? -1 : 32;           // lanes <= d_lane still see the patch; 32: nobody destroyed it (yet)
+      double my_take = 0.0;
+      while (eb) {
+        const int l = __ffs(eb) - 1;
+        eb &= eb - 1;
+        double take = fmin(prm.consumption, (double)a.pa.quality[p0 + p]);           // rescource.py:121-122
+        if (left >= take) left -= take; else { take = left; left = 0.0; }
+        left = (double)(float)left;                                                   // resc_left lives in fp32 state
+        if (lane == l) my_take = take;
+        if (!(left > 0.0)) { destroy = true; d_lane = l; eb = 0u; }
+      }
+      if (member) {
+        if (lane > d_lane) {
+          notify(a.ag, g, -1, -1, tau_mask);                                          // :812-813
+        } else {
+          notify(a.ag, g, 1, a.pa.id[p0 + p], tau_mask);                              // :816-818 (pooling_time == 0)
+          if (a.teleport_exploit) {                                                   // :820-821
+            a.ag.x[g] = (float)((double)a.pa.x[p0 + p] + prad - r);
+            a.ag.y[g] = (float)((double)a.pa.y[p0 + p] + prad - r);
+          }
+          if (expl) {                                                                 // :824-828
+            const float c = a.ag.collected[g];
+            a.ag.collected_before[g] = c;
+            a.ag.collected[g] = (float)((double)c + my_take);
           }
         }
+        a.ag.mode[g] |= 0x100;   // scratch mark: on a patch this step
       }
-      a.ag.mode[g] |= 0x100;   // scratch mark: on a patch this step
+    }
+    if (lane == 0) a.pa.left[p0 + p] = (float)left;
+    if (destroy) {                                                                    // :829-836, for every agent on it
+      __syncwarp();
+      for (int c0 = 0; c0 < a.N; c0 += 32) {
+        const int i = c0 + lane;
+        if (i < a.N) {
+          const size_t g = a0 + i;
+          const double ex = ((double)a.ag.x[g] + r) - pcx, ey = ((double)a.ag.y[g] + r) - pcy;
+          if (sqrt(ex * ex + ey * ey) < prad) notify(a.ag, g, -1, -1, tau_mask);
+        }
+      }
     }
     if (destroy && a.regenerate) {   // kill_resource + add_new_resource_patch(force_id) (sims.py:321-374)
-      bool placed = false;
-      for (unsigned t = 0; t < 10000u && !placed; ++t) {
-        const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t),
-                                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x50415443u));
-        const double R_ = a.patch_radius;
-        double lox, hix, loy, hiy;
-        if (a.border_overlap) { lox = a.pad - R_; hix = a.width + a.pad - R_; loy = a.pad - R_; hiy = a.height + a.pad - R_; }
-        else { lox = a.pad; hix = a.width + a.pad - 2 * R_; loy = a.pad; hiy = a.height + a.pad - 2 * R_; }
-        const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
-        const double nx = floor(lox + floor(hix - lox) * u01(rn.x, rn.y));          // np.random.randint(lo, hi)
-        const double ny = floor(loy + floor(hiy - loy) * u01(rn.z, rn.w));
-        bool ok = true;
-        for (int p2 = 0; p2 < a.P; ++p2) {                                          // proove_sprite: no patch-patch overlap
-          if (p2 == p) continue;
-          const double r2 = a.pa.radius[p0 + p2];
-          const double ex = (nx + R_) - ((double)a.pa.x[p0 + p2] + r2), ey = (ny + R_) - ((double)a.pa.y[p0 + p2] + r2);
-          if (ex * ex + ey * ey <= (R_ + r2) * (R_ + r2)) { ok = false; break; }
+      if (lane == 0) {
+        bool placed = false;
+        for (unsigned t = 0; t < 10000u && !placed; ++t) {
+          const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t),
+                                      make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x50415443u));
+          const double R_ = a.patch_radius;
+          double lox, hix, loy, hiy;
+          if (a.border_overlap) { lox = a.pad - R_; hix = a.width + a.pad - R_; loy = a.pad - R_; hiy = a.height + a.pad - R_; }
+          else { lox = a.pad; hix = a.width + a.pad - 2 * R_; loy = a.pad; hiy = a.height + a.pad - 2 * R_; }
+          const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
+          const double nx = floor(lox + floor(hix - lox) * u01(rn.x, rn.y));          // np.random.randint(lo, hi)
+          const double ny = floor(loy + floor(hiy - loy) * u01(rn.z, rn.w));
+          bool ok = true;
+          for (int p2 = 0; p2 < a.P; ++p2) {                                          // proove_sprite: no patch-patch overlap
+            if (p2 == p) continue;
+            const double r2 = a.pa.radius[p0 + p2];
+            const double ex = (nx + R_) - ((double)a.pa.x[p0 + p2] + r2), ey = (ny + R_) - ((double)a.pa.y[p0 + p2] + r2);
+            if (ex * ex + ey * ey <= (R_ + r2) * (R_ + r2)) { ok = false; break; }
+          }
+          if (!ok) continue;
+          const int units = a.min_units + (int)floor((double)(a.max_units - a.min_units) * u01(rn2.x, rn2.y));
+          const double q = a.min_quality + (a.max_quality - a.min_quality) * u01(rn2.z, rn2.w);
+          a.pa.x[p0 + p] = (float)nx; a.pa.y[p0 + p] = (float)ny; a.pa.radius[p0 + p] = (float)R_;
+          a.pa.left[p0 + p] = (float)units; a.pa.quality[p0 + p] = (float)q;
+          placed = true;
+          atomicAdd(&a.counters[0], 1ull);
         }
-        if (!ok) continue;
-        const int units = a.min_units + (int)floor((double)(a.max_units - a.min_units) * u01(rn2.x, rn2.y));
-        const double q = a.min_quality + (a.max_quality - a.min_quality) * u01(rn2.z, rn2.w);
-        a.pa.x[p0 + p] = (float)nx; a.pa.y[p0 + p] = (float)ny; a.pa.radius[p0 + p] = (float)R_;
-        a.pa.left[p0 + p] = (float)units; a.pa.quality[p0 + p] = (float)q;
-        placed = true;
-        atomicAdd(&a.counters[0], 1ull);
+        if (!placed) atomicAdd(&a.counters[1], 1ull);
       }
-      if (!placed) atomicAdd(&a.counters[1], 1ull);
     } else if (destroy) {
-      a.pa.radius[p0 + p] = 0.0f;   // resource.kill() without regeneration: the patch no longer exists
+      if (lane == 0) a.pa.radius[p0 + p] = 0.0f;   // resource.kill() without regeneration: the patch no longer exists
     }
+    __syncwarp();   // the next patch reads what lane 0 wrote (and the agents' new positions / headings)
   }
   // agents on no patch (and not colliding) are told so (sims.py:847-855, pooling_time == 0)
-  for (int i = 0; i < a.N; ++i) {
+  for (int i = lane; i < a.N; i += 32) {
     const size_t g = a0 + i;
     const int m = a.ag.mode[g];
     if (m & 0x100) a.ag.mode[g] = m & 0xff;
@@ -149,8 +177,8 @@ __global__ void base_env_kernel(const BaseKernelArgs a) {
 }
 
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream) {
-  const int threads = 64;
-  base_env_kernel<<<(a.B + threads - 1) / threads, threads, 0, stream>>>(a);
+  const int threads = 128;   // 4 replicates (warps) per CTA
+  base_env_kernel<<<(unsigned)(((size_t)a.B * 32 + threads - 1) / threads), threads, 0, stream>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------
