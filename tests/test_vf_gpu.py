@@ -378,3 +378,41 @@ def test_summary_metrics_match_numpy(built_lib, boundary):
         eng.step(1)
     assert m["collision"][1] == 1.0 and m["polarization"].max() <= 1.0 + 1e-6
     eng.close()
+
+
+def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
+    """The step kernel is chosen per step: the symmetric kernel reports how many lane entries left its fast path and a
+    crowded scene (most intervals wider than 32 bins) switches to the one-thread-per-focal-agent kernel -- without
+    changing any result (both kernels are exact)."""
+    import torch
+    from abm_b200 import VFEngine
+    monkeypatch.delenv("ABM_VF_KERNEL", raising=False)
+    rng = np.random.default_rng(11)
+    B, N, W = 8, 256, 900.0
+    res = {}
+    for name, spread in (("crowded", 60.0), ("sparse", 420.0)):
+        ang = rng.uniform(0, 2 * np.pi, (B, N)); rr = np.sqrt(rng.uniform(0, 1, (B, N))) * spread
+        x = (450 + rr * np.cos(ang)).astype(np.float32); y = (450 + rr * np.sin(ang)).astype(np.float32)
+        th = rng.uniform(0, 2 * np.pi, (B, N)).astype(np.float32); v = np.zeros_like(x)
+        eng = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
+        eng.set_params(); eng.set_state(x, y, th, v, 10.0)
+        eng.step(1)
+        assert eng.last_kernel() == "abm::vf_step_sym_kernel"
+        entries, launches = eng.slow_entries()
+        frac = entries / launches / (0.25 * B * N * (N - 1))
+        torch.cuda.synchronize()
+        kernels = []
+        for _ in range(4):
+            eng.step(1); torch.cuda.synchronize(); kernels.append(eng.last_kernel())
+        res[name] = (frac, kernels, eng.fields_packed().copy(), eng.get_state())
+        eng.close()
+        monkeypatch.setenv("ABM_VF_KERNEL", "symmetric")          # the same five steps with one kernel throughout
+        ref = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
+        ref.set_params(); ref.set_state(x, y, th, v, 10.0); ref.step(5)
+        assert np.array_equal(ref.fields_packed(), res[name][2])
+        for k in ("x", "y", "theta", "vel"):
+            assert np.array_equal(ref.get_state()[k], res[name][3][k])
+        ref.close()
+        monkeypatch.delenv("ABM_VF_KERNEL")
+    assert res["crowded"][0] > 0.18 and "abm::vf_step_kernel" in res["crowded"][1]
+    assert res["sparse"][0] < 0.18 and set(res["sparse"][1]) == {"abm::vf_step_sym_kernel"}
