@@ -19,6 +19,7 @@ VF_KEEP_FIELDS = 1 << 1
 VF_KEEP_TERMS = 1 << 2
 VF_SPATIAL_SORT = 1 << 3
 VF_NPARAM = 6
+VF_IPC_BYTES = 256
 
 
 class AbmError(RuntimeError):
@@ -118,6 +119,8 @@ SYMBOLS = {
     "abm_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "abm_vf_record_table": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
     "abm_vf_last_kernel": (C.c_char_p, [_P]),
+    "abm_vf_ipc_export": (C.c_int, [_P, _P]),
+    "abm_vf_ipc_attach": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "abm_vf_metrics": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_vf_slow_entries": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P]),
     "abm_vf_get_permutation": (C.c_int, [_P, _P, C.c_int, _P]),

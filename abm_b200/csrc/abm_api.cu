@@ -111,6 +111,13 @@ struct abm_engine {
   bool state_set = false;
   unsigned long long launches = 0;
   const char* last_kernel = "";
+  // fused tile exchange (abm_vf_ipc_*)
+  DevBuf<uint32_t> xflags;          // [8] steps published by every rank (+ done counter at [8])
+  int n_peers = 0, my_rank = 0;
+  float4* peer_rec[7][2] = {};      // peers' record tables (both halves of the ping-pong)
+  uint32_t* peer_flags[7] = {};
+  void* peer_maps[7][3] = {};       // what cudaIpcOpenMemHandle returned (to close)
+  uint32_t steps_done = 0;
   // adaptive kernel choice: the symmetric kernel reports how many lane entries left its fast path; in crowded scenes
   // (most intervals wider than 32 bins) the one-thread-per-focal-agent kernel is faster (both give identical results)
   unsigned long long* slow_host = nullptr;   // pinned copy of counters[4]
@@ -119,6 +126,7 @@ struct abm_engine {
   unsigned long long slow_seen = 0, sym_launches = 0, slow_req_launch = 0, slow_seen_launch = 0;
   int onesided_steps_left = 0;
   size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  int n_sms = 148;
   // spatial ordering (ABM_VF_SPATIAL_SORT)
   bool sort_enabled = false, needs_sort = false, perm_identity = true;
   int steps_since_sort = 0;
@@ -215,7 +223,8 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   e->tile_count = tc;
   e->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   build_grid(cfg->resolution, e->grid);
-  const size_t smem = abm::vf_step_smem_bytes(abm::vf_step_threads(tc), e->grid.W);
+  e->n_sms = prop.multiProcessorCount;
+  const size_t smem = abm::vf_step_smem_bytes(abm::vf_step_threads(tc, cfg->n_replicates, e->n_sms), e->grid.W);
   if (smem > (size_t)prop.sharedMemPerBlockOptin) {
     delete e;
     return fail(ABM_E_INVALID, "abm_vf_create: resolution too large for shared memory");
@@ -275,6 +284,10 @@ int abm_destroy(abm_engine_t* e) {
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
   e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release(); e->metrics.release();
   e->radius_minmax.release();
+  for (int p = 0; p < e->n_peers; ++p)
+    for (int k = 0; k < 3; ++k)
+      if (e->peer_maps[p][k]) cudaIpcCloseMemHandle(e->peer_maps[p][k]);
+  e->xflags.release();
   if (e->slow_host) cudaFreeHost(e->slow_host);
   if (e->slow_event) cudaEventDestroy(e->slow_event);
   delete e;
@@ -404,7 +417,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   abm::VFKernelArgs a;
   memset(&a, 0, sizeof(a));
   a.B = e->cfg.n_replicates; a.N = e->cfg.n_agents; a.R = g.R; a.W = g.W;
-  a.tile_begin = e->tile_begin; a.tile_count = e->tile_count;
+  a.tile_begin = e->tile_begin; a.tile_count = e->tile_count; a.n_sms = e->n_sms;
   a.fov_px0 = e->cfg.fov_px0; a.fov_px1 = e->cfg.fov_px1;
   a.boundary = e->cfg.boundary; a.limit_movement = e->cfg.limit_movement;
   a.phi_ok = g.phi_ok; a.flags = e->cfg.flags;
@@ -502,6 +515,9 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.perm = (e->sort_enabled && !e->perm_identity && !tiled) ? e->perm.p : nullptr;
     a.rec_in = e->rec[e->cur].p;
     a.rec_out = e->rec[e->cur ^ 1].p;
+    a.n_peers = e->n_peers; a.my_rank = e->my_rank; a.step_no = e->steps_done;
+    for (int p = 0; p < e->n_peers; ++p) { a.peer_rec_out[p] = e->peer_rec[p][e->cur ^ 1]; a.peer_flags[p] = e->peer_flags[p]; }
+    a.xflags = e->xflags.p; a.done_counter = e->xflags.p ? reinterpret_cast<unsigned*>(e->xflags.p + 8) : nullptr;
     if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
       abm::launch_tile_bbox(a.rec_in, a.B, a.N, e->tile_bbox.p, e->tile_cull2.p, st);
       a.tile_bbox = e->tile_bbox.p; a.tile_cull2 = e->tile_cull2.p;
@@ -520,6 +536,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     }
     e->cur ^= 1;
     ++e->launches;
+    ++e->steps_done;
   }
   ABM_CUDA(cudaGetLastError());
   return ABM_OK;
@@ -594,6 +611,61 @@ int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent) {
   if (!e || !dev_ptr) return fail(ABM_E_INVALID, "abm_vf_record_table: null argument");
   *dev_ptr = e->rec[e->cur].p;
   if (bytes_per_agent) *bytes_per_agent = (int)sizeof(float4);
+  return ABM_OK;
+}
+
+namespace {
+struct IpcExport {   // ABM_VF_IPC_BYTES
+  cudaIpcMemHandle_t rec[2], flags;
+  int32_t n_agents, tile_begin, tile_count, cur;
+  char pad[ABM_VF_IPC_BYTES - 3 * sizeof(cudaIpcMemHandle_t) - 16];
+};
+static_assert(sizeof(IpcExport) == ABM_VF_IPC_BYTES, "IpcExport layout");
+}  // namespace
+
+int abm_vf_ipc_export(abm_engine_t* e, void* out) {
+  if (!e || !out) return fail(ABM_E_INVALID, "abm_vf_ipc_export: null argument");
+  if (e->cfg.n_replicates != 1) return fail(ABM_E_INVALID, "abm_vf_ipc_export: the tile exchange is for one swarm (B = 1)");
+  ABM_CUDA(cudaSetDevice(e->device));
+  if (!e->xflags.p) {
+    ABM_CUDA(e->xflags.alloc(16));
+    ABM_CUDA(cudaMemset(e->xflags.p, 0, 16 * sizeof(uint32_t)));
+  }
+  IpcExport x;
+  memset(&x, 0, sizeof(x));
+  ABM_CUDA(cudaIpcGetMemHandle(&x.rec[0], e->rec[0].p));
+  ABM_CUDA(cudaIpcGetMemHandle(&x.rec[1], e->rec[1].p));
+  ABM_CUDA(cudaIpcGetMemHandle(&x.flags, e->xflags.p));
+  x.n_agents = e->cfg.n_agents; x.tile_begin = e->tile_begin; x.tile_count = e->tile_count; x.cur = e->cur;
+  memcpy(out, &x, sizeof(x));
+  return ABM_OK;
+}
+
+int abm_vf_ipc_attach(abm_engine_t* e, int n_ranks, int my_rank, const void* exports) {
+  if (!e || !exports) return fail(ABM_E_INVALID, "abm_vf_ipc_attach: null argument");
+  if (n_ranks < 2 || n_ranks > 8 || my_rank < 0 || my_rank >= n_ranks)
+    return fail(ABM_E_INVALID, "abm_vf_ipc_attach: 2..8 ranks, 0 <= my_rank < n_ranks");
+  if (!e->xflags.p) return fail(ABM_E_STATE, "abm_vf_ipc_attach: call abm_vf_ipc_export first");
+  if (e->n_peers) return fail(ABM_E_STATE, "abm_vf_ipc_attach: already attached");
+  ABM_CUDA(cudaSetDevice(e->device));
+  const IpcExport* x = static_cast<const IpcExport*>(exports);
+  int p = 0;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == my_rank) continue;
+    if (x[r].n_agents != e->cfg.n_agents || x[r].cur != e->cur)
+      return fail(ABM_E_INVALID, "abm_vf_ipc_attach: the ranks' engines differ (n_agents / step parity)");
+    void* m[3];
+    ABM_CUDA(cudaIpcOpenMemHandle(&m[0], x[r].rec[0], cudaIpcMemLazyEnablePeerAccess));
+    ABM_CUDA(cudaIpcOpenMemHandle(&m[1], x[r].rec[1], cudaIpcMemLazyEnablePeerAccess));
+    ABM_CUDA(cudaIpcOpenMemHandle(&m[2], x[r].flags, cudaIpcMemLazyEnablePeerAccess));
+    for (int k = 0; k < 3; ++k) e->peer_maps[p][k] = m[k];
+    e->peer_rec[p][0] = static_cast<float4*>(m[0]);
+    e->peer_rec[p][1] = static_cast<float4*>(m[1]);
+    e->peer_flags[p] = static_cast<uint32_t*>(m[2]);
+    ++p;
+  }
+  e->my_rank = my_rank;
+  e->n_peers = p;
   return ABM_OK;
 }
 

@@ -24,9 +24,13 @@ size_t vf_step_smem_bytes(int threads, int W) {
          + sizeof(int) * (kMaxTileList + 4) + 64;   // tile list of the culling variants, focal bounding box
 }
 
-int vf_step_threads(int tile_count) {
+// Focal agents per CTA: 256, or fewer when that would leave the GPU short of CTAs (one large swarm, or its tile on one
+// of several GPUs: 65 536 agents are only 256 CTAs of 256) -- at least ~3 CTAs per SM are wanted.
+int vf_step_threads(int tile_count, int n_replicates, int n_sms) {
   int t = (tile_count + 31) / 32 * 32;
-  return t > kMaxThreads ? kMaxThreads : t;
+  if (t > kMaxThreads) t = kMaxThreads;
+  while (t > 64 && (long long)n_replicates * ((tile_count + t - 1) / t) < 3LL * n_sms) t >>= 1;
+  return (t + 31) / 32 * 32;
 }
 
 // Out-of-line fp64 evaluation + atomic draw of one pair (queue overflow / deferred pairs).
@@ -84,6 +88,15 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int w = 0; w < a.W + 2; ++w) rows[w * T + tid] = 0u;
+  if (a.n_peers > 0 && tid <= a.n_peers) {
+    // fused tile exchange: wait until every rank (thread r watches rank r, this rank included) has published the
+    // previous step -- its records have landed in our table and nobody reads the table this launch writes into any more
+    const uint32_t* f = a.xflags + tid;
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while ((int)(v - a.step_no) < 0);
+  }
   __syncthreads();
 
   uint32_t* padrow = rows + tid;        // padded word 0 (virtual bins [-32, 0))
@@ -278,6 +291,21 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
     const bool aa[1] = {active};
     vf_agent_epilogue<TORUS, 1>(a, b, ii, lli, pr, T, mm, tt, 0u, aa);
   }
+  if (a.n_peers > 0) {   // publish: the last CTA of the launch tells every rank that this step's records are in place
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned ticket = atomicAdd(a.done_counter, 1u);
+      if (ticket == gridDim.x - 1) {
+        *a.done_counter = 0u;
+        __threadfence_system();
+        const uint32_t done = a.step_no + 1u;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.xflags + a.my_rank), "r"(done) : "memory");
+        for (int p = 0; p < a.n_peers; ++p)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[p] + a.my_rank), "r"(done) : "memory");
+      }
+    }
+  }
 }
 
 template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>
@@ -301,7 +329,7 @@ static void launch_fov(const VFKernelArgs& a, unsigned grid, int T, size_t smem,
 }
 
 void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream) {
-  const int T = vf_step_threads(a.tile_count);
+  const int T = vf_step_threads(a.tile_count, a.B, a.n_sms);
   const int tiles_per_rep = (a.tile_count + T - 1) / T;
   const size_t smem = vf_step_smem_bytes(T, a.W);
   const unsigned grid = (unsigned)((size_t)a.B * tiles_per_rep);

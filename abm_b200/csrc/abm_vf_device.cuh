@@ -663,7 +663,9 @@ __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, 
     if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me[j].z, a.width_d, a.height_d, a.pad_d);
     else teleport_torus(nx, ny, (double)me[j].z, a.width_d, a.height_d, a.pad_d);
 
-    a.rec_out[gi] = make_float4((float)nx, (float)ny, me[j].z, me[j].w);
+    const float4 rec_new = make_float4((float)nx, (float)ny, me[j].z, me[j].w);
+    a.rec_out[gi] = rec_new;
+    for (int p = 0; p < a.n_peers; ++p) a.peer_rec_out[p][gi] = rec_new;   // NVLink peer stores (fused tile exchange)
     a.theta[gi] = (float)nth;
     a.vel[gi] = (float)nv;
 

@@ -229,6 +229,18 @@ class VFEngine:
                    "abm_vf_slow_entries")
         return int(n.value), int(l.value)
 
+    def ipc_export(self) -> bytes:
+        """Handles of this (tiled) engine's record tables and flags for the fused tile exchange."""
+        buf = C.create_string_buffer(_lib.VF_IPC_BYTES)
+        _lib.check(self._lib.abm_vf_ipc_export(self._h, buf), "abm_vf_ipc_export")
+        return buf.raw
+
+    def ipc_attach(self, my_rank: int, exports: list[bytes]):
+        """Map the peers' tables (exports of ALL ranks, in rank order): from now on step() exchanges the tiles
+        itself over NVLink peer memory and every rank must step in lock step."""
+        blob = b"".join(exports)
+        _lib.check(self._lib.abm_vf_ipc_attach(self._h, len(exports), int(my_rank), blob), "abm_vf_ipc_attach")
+
     def last_kernel(self) -> str:
         """Name of the step kernel the last step() launched."""
         return (self._lib.abm_vf_last_kernel(self._h) or b"").decode()

@@ -43,9 +43,14 @@ class _DeviceMemory:
 
 
 class TiledSwarm:
-    """One very large swarm (B = 1) across the ranks of a torch.distributed NCCL group."""
+    """One very large swarm (B = 1) across the ranks of a torch.distributed NCCL group.
 
-    def __init__(self, n_agents: int, *, group=None, **engine_kwargs):
+    ``fused=True`` (default): the step kernel itself stores its tile's new records into every peer's record table over
+    NVLink peer memory (CUDA IPC mappings of the tables, exchanged once through the process group) and the ranks
+    hand-shake through flags in each other's memory -- no collective on the step path.  ``fused=False``: one in-place
+    NCCL all-gather of the 16-byte records per step."""
+
+    def __init__(self, n_agents: int, *, group=None, fused: bool = True, **engine_kwargs):
         import torch
         import torch.distributed as dist
         from .engine import VFEngine
@@ -56,13 +61,30 @@ class TiledSwarm:
         self.engine = VFEngine(1, self.N, tile=(self.begin, self.count), device=torch.cuda.current_device(),
                                **engine_kwargs)
         self._tables = {}
+        self.fused = bool(fused) and self.world > 1
+        if self.fused:
+            mine = torch.frombuffer(bytearray(self.engine.ipc_export()), dtype=torch.uint8).cuda()
+            every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(every, mine, group=group)
+            blob = every.cpu().numpy().tobytes()
+            n = mine.numel()
+            self.engine.ipc_attach(self.rank, [blob[r * n:(r + 1) * n] for r in range(self.world)])
+
+    def _barrier(self):
+        self.torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
 
     def set_params(self, **kw):
         self.engine.set_params(**kw)
 
     def set_state(self, x, y, theta, vel, radius):
         """Every rank passes the FULL state (identical on all ranks)."""
+        if self.fused:
+            self._barrier()                  # nobody may still be stepping (and storing into our tables)
         self.engine.set_state(x, y, theta, vel, radius)
+        if self.fused:
+            self.engine.resort()             # the initial spatial sort, now: it rewrites both tables
+            self._barrier()
 
     def _table(self):
         ptr, nbytes = self.engine.record_table_ptr()
@@ -73,6 +95,9 @@ class TiledSwarm:
         return t
 
     def step(self, n_steps: int = 1):
+        if self.fused:
+            self.engine.step(n_steps)        # the kernels exchange the tiles themselves
+            return
         for _ in range(n_steps):
             self.engine.step(1)                       # writes this rank's tile of the next table
             table = self._table()
@@ -88,14 +113,20 @@ class TiledSwarm:
     def resync(self):
         """Make headings / speeds current on every rank (one all-gather each) and re-sort the
         internal order spatially -- call every few hundred steps of a long run."""
+        if self.fused:
+            self._barrier()
         for t in self._internal():
             self.dist.all_gather_into_tensor(t, t[self.begin:self.begin + self.count].clone(), group=self.group)
         self.engine.resort()
         self._tables = {}
+        if self.fused:
+            self._barrier()
 
     def get_state(self):
         """Full state in the caller's agent order: (x, y) from the gathered record table, headings /
         speeds gathered here (off the step path) from the tiles and un-permuted."""
+        if self.fused:
+            self._barrier()                  # every rank's last step has landed in our table
         st = self.engine.get_state()
         out = {"x": st["x"][0], "y": st["y"][0]}
         perm = self.engine.permutation()[0]

@@ -147,6 +147,19 @@ int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent);
  * abm_vf_resort: re-sort now (a tiled engine needs the full heading / speed arrays to be current on
  * every rank first: abm_vf_internal_arrays exposes them for the all-gather). */
 int abm_vf_get_permutation(abm_engine_t* e, int32_t* perm, int on_device, void* stream);
+
+/* Fused tile exchange of one large swarm across the GPUs of a node, instead of an all-gather per step: the
+ * step kernel of a tiled engine stores every new record of its tile straight into the peers' record tables over NVLink
+ * (CUDA IPC mappings), a launch starts only when every rank has published the previous step (flags in each GPU's
+ * memory, written by the peers' last CTAs) and publishes its own at its end.  One process per GPU:
+ *   abm_vf_ipc_export  -> ABM_VF_IPC_BYTES bytes describing this engine's tables and flags; exchange them between the
+ *                         ranks (e.g. torch.distributed.all_gather);
+ *   abm_vf_ipc_attach  <- the exports of ALL ranks in rank order (this engine's own entry at `my_rank` is skipped).
+ * All ranks must then call abm_vf_step the same number of times; abm_set_state on an attached engine needs a barrier
+ * between the ranks before the next step (the host's job). */
+#define ABM_VF_IPC_BYTES 256
+int abm_vf_ipc_export(abm_engine_t* e, void* out);
+int abm_vf_ipc_attach(abm_engine_t* e, int n_ranks, int my_rank, const void* exports);
 int abm_vf_resort(abm_engine_t* e, void* stream);
 int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev);
 

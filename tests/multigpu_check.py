@@ -30,21 +30,33 @@ def main():
     y = (W / 2 + rho * np.sin(th)).astype(np.float32)
     v = np.zeros(N, np.float32)
     kw = dict(resolution=1200, width=W, height=W, boundary="infinite")
-    swarm = TiledSwarm(N, **kw)
-    swarm.set_params()
-    swarm.set_state(x[None], y[None], th[None], v[None], 10.0)
-    swarm.step(steps)
-    got = swarm.get_state()
     ok = True
+    ref_state = None
     if rank == 0:
         ref = VFEngine(1, N, **kw)
         ref.set_params(); ref.set_state(x[None], y[None], th[None], v[None], 10.0); ref.step(steps)
-        st = ref.get_state()
-        for k in ("x", "y", "theta", "vel"):
-            same = np.array_equal(got[k], st[k][0])
-            ok &= same
-            print(f"[tiled x{world}] {k}: {'bit-identical' if same else 'MISMATCH'}", flush=True)
+        ref_state = ref.get_state()
         ref.close()
+    for fused in (True, False):
+        swarm = TiledSwarm(N, fused=fused, **kw)
+        swarm.set_params()
+        swarm.set_state(x[None], y[None], th[None], v[None], 10.0)
+        swarm.step(steps)
+        got = swarm.get_state()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record(); swarm.step(10); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        if rank == 0:
+            for k in ("x", "y", "theta", "vel"):
+                same = np.array_equal(got[k], ref_state[k][0])
+                ok &= same
+                print(f"[tiled x{world} {'fused peer stores' if fused else 'NCCL all-gather'}] {k}: "
+                      f"{'bit-identical' if same else 'MISMATCH'}", flush=True)
+            print(f"[tiled x{world} {'fused peer stores' if fused else 'NCCL all-gather'}] N={N}: {ms:.3f} ms/step", flush=True)
+        dist.barrier()
+        swarm.engine.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
