@@ -524,9 +524,13 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       a.bbox_slack = 2.0f * (e->r_max - e->r_min);
       ++e->launches;
     }
+    // one large sparse swarm (distance culling on) or an agent tile of it: a warp per focal agent
+    const bool use_warp = !use_sym && ((force && strcmp(force, "warp") == 0) ||
+                                       (!(force && strcmp(force, "onesided") == 0) && (cull || tiled)));
     if (use_sym) abm::launch_vf_step_sym(a, st);
+    else if (use_warp) abm::launch_vf_step_warp(a, cull, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
-    e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : "abm::vf_step_kernel";
+    e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : (use_warp ? "abm::vf_step_warp_kernel" : "abm::vf_step_kernel");
     if (use_sym) ++e->sym_launches;
     if (adaptive && use_sym && !e->slow_pending) {
       e->slow_req_launch = e->sym_launches;

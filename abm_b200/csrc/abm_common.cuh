@@ -99,6 +99,8 @@ size_t vf_step_smem_bytes(int threads, int W);
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
 void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
 int vf_step_threads(int tile_count, int n_replicates, int n_sms);
+// warp-per-focal-agent kernel (abm_vf_warp.cu): one large sparse swarm and its tiles
+void launch_vf_step_warp(const VFKernelArgs& a, bool cull, cudaStream_t stream);
 
 struct VFProjArgs {
   int R, W, n_obj, boundary;

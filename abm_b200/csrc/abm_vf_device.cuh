@@ -172,6 +172,61 @@ __device__ __forceinline__ PairFast vf_pair_fast(float dx, float dy, float d2, f
   return o;
 }
 
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: low mantissa bits of x + kMagic = rint(x)
+constexpr int kMagicBits = 0x4B400000;
+
+// ---- binary angles ----------------------------------------------------------------------------------------------
+// Angles live in 32-bit integers, 2^32 to the turn, so differences wrap for free.  The bearing atan2(-dy, dx) of the
+// partner comes out of the octant polynomial in units of 2^-25 turn (an octant = 2^22 units: it fits the integer
+// window of the 1.5 * 2^23 rounding constant), is unfolded with integer arithmetic and scaled by 128.  With
+//   v = bearing - heading + half a turn          (unsigned: the closed angle measured from -pi)
+// the nearest index on the linspace(-pi, pi, R) grid (vf_supcalc.py:102) is the high word of v * (R - 1) + 2^31, and
+// the low word is the distance from the rounding tie: one IMAD.WIDE yields the bin and its guard band.  The opposite
+// direction only differs by half a turn, which is folded into the partner's heading constant.
+constexpr uint32_t kQuarter = 1u << 23, kHalf = 1u << 24;      // in units of 2^-25 turn
+constexpr uint32_t kMB2 = 2u * (uint32_t)kMagicBits;
+
+// bits of (kMagic + bearing in 2^-25 turns), bearing in (-half turn, half turn]
+__device__ __forceinline__ uint32_t sym_bearing_bits(float dx, float dy, float a6) {
+  constexpr double kS = 33554432.0 / ABM_TWO_PI_D;             // 2^25 / 2pi
+  const float au = fabsf(dx), aw = fabsf(dy);
+  const float tq = fminf(au, aw) * rcp_approx(fmaxf(au, aw));
+  const float z = tq * tq;
+  float p = fmaf(a6, z, (float)(-0.037013452500104904 * kS));
+  p = fmaf(p, z, (float)(0.0838717594742775 * kS));
+  p = fmaf(p, z, (float)(-0.13487225770950317 * kS));
+  p = fmaf(p, z, (float)(0.19881492853164673 * kS));
+  p = fmaf(p, z, (float)(-0.33326515555381775 * kS));
+  p = fmaf(p, z, (float)(0.9999993443489075 * kS));
+  uint32_t nb = __float_as_uint(fmaf(p, tq, kMagic));          // kMagicBits + rint(octant angle)
+  if (aw > au) nb = (kMB2 + kQuarter) - nb;
+  if (dx < 0.0f) nb = (kMB2 + kHalf) - nb;
+  if (dy > 0.0f) nb = kMB2 - nb;                               // atan2(-dy, dx): screen y points down
+  return nb;
+}
+constexpr float kBearingA6 = (float)(0.007863515056669712 * (33554432.0 / ABM_TWO_PI_D));
+
+// Heading constant of an agent: v = 128 * bearing_bits - heading_const (mod 2^32).
+__device__ __forceinline__ uint32_t sym_heading_const(float theta) {
+  double turns = (double)theta * (1.0 / ABM_TWO_PI_D);
+  turns -= floor(turns);
+  const uint32_t th_bam = (uint32_t)(unsigned long long)rint(turns * 4294967296.0);
+  return th_bam + 128u * (uint32_t)kMagicBits - 0x80000000u;
+}
+
+// One direction on the fast path: nearest linspace index of the closed angle (returned as the padded start position of
+// the interval, h folded into `bh`); `slow` is set when the angle is within the fp32 error bound of a rounding tie or
+// of the +-pi seam.
+template <int RC>
+__device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, uint32_t nb, uint32_t hconst, int bh, bool& slow) {
+  const uint32_t v = 128u * nb - hconst;
+  const uint32_t Rp = RC ? (uint32_t)(RC - 1) : (uint32_t)(a.R - 1);
+  const unsigned long long prod = (unsigned long long)v * Rp + 0x80000000ull;
+  slow |= ((uint32_t)prod + a.sym_tie32) < 2u * a.sym_tie32;
+  slow |= (v + a.sym_seam32) < 2u * a.sym_seam32;
+  return (int)(uint32_t)(prod >> 32) + bh;
+}
+
 // ---------------------------------------------------------------------------------------
 // fp64 exact pair path: the reference's own operation sequence, individually rounded
 // ---------------------------------------------------------------------------------------

@@ -313,8 +313,8 @@ def test_spatial_sort_is_invisible(built_lib, monkeypatch):
     (1, 700, 2400, "infinite", 0.75),   # large R
 ])
 def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, boundary, fov_ratio):
-    """The two step kernels (every unordered pair once / one thread per focal agent) are independent
-    implementations of the same step; with the fp64 re-evaluation on, both must produce the exact
+    """The three step kernels (every unordered pair once / one thread per focal agent / one warp per focal agent) are
+    independent implementations of the same step; with the fp64 re-evaluation on, both must produce the exact
     fields, so they agree bit for bit -- fields, terms and new state -- also over several steps,
     crowded scenes (wide intervals, overlapping agents) included."""
     from abm_b200 import VFEngine
@@ -325,7 +325,7 @@ def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, b
     x[0, 3], y[0, 3] = x[0, 2] + 3.0, y[0, 2] # overlapping pair (d < r)
     fov = (-fov_ratio * np.pi, fov_ratio * np.pi)
     res = {}
-    for kern in ("onesided", "symmetric"):
+    for kern in ("onesided", "symmetric", "warp"):
         monkeypatch.setenv("ABM_VF_KERNEL", kern)
         eng = VFEngine(B, N, resolution=R, width=W, height=W, boundary=boundary, fov=fov, keep_fields=True,
                        keep_terms=True, spatial_sort=False)
@@ -335,12 +335,18 @@ def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, b
         eng.step(3)
         res[kern] = (f1, t1, eng.fields_packed(), eng.terms(), eng.get_state(), eng.counters())
         eng.close()
-    a, b = res["onesided"], res["symmetric"]
+    a = res["onesided"]
+    b = res["symmetric"]                      # same epilogue code: everything bit for bit, also after further steps
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
     for k in ("x", "y", "theta", "vel"):
         assert np.array_equal(a[4][k], b[4][k]), k
-    print("fp64 pairs onesided / symmetric:", a[5]["fp64_pairs"], b[5]["fp64_pairs"])
+    b = res["warp"]                           # its edge sums are reduced across lanes: same fields, terms to rounding
+    assert np.array_equal(a[0], b[0])
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-11, atol=1e-12)
+    for k in ("x", "y", "theta", "vel"):
+        np.testing.assert_allclose(b[4][k], a[4][k], rtol=1e-5, atol=1e-4, err_msg=k)
+    print("fp64 pairs onesided / symmetric / warp:", *(res[k][5]["fp64_pairs"] for k in ("onesided", "symmetric", "warp")))
 
 
 @pytest.mark.parametrize("boundary", ["walls", "infinite"])
@@ -416,3 +422,39 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
         monkeypatch.delenv("ABM_VF_KERNEL")
     assert res["crowded"][0] > 0.18 and "abm::vf_step_kernel" in res["crowded"][1]
     assert res["sparse"][0] < 0.18 and set(res["sparse"][1]) == {"abm::vf_step_sym_kernel"}
+
+
+@pytest.mark.parametrize("boundary", ["walls", "infinite"])
+def test_warp_kernel_on_a_sparse_heterogeneous_swarm(built_lib, monkeypatch, boundary):
+    """The warp-per-focal-agent kernel in its own territory -- one large sparse swarm with distance culling, record
+    tiles skipped by bounding box on the Morton-sorted state, heterogeneous radii -- against the one-thread-per-focal-
+    agent kernel (fields bit for bit; several steps incl. a re-sort) and against the oracle on sampled agents."""
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(77)
+    N, R, W = 6000, 1200, 9000.0
+    x, y, th, v = _random_scene(rng, 1, N, W)
+    rad = rng.choice([5.0, 10.0, 14.0], (1, N)).astype(np.float32)
+    res = {}
+    for kern in ("onesided", "warp"):
+        monkeypatch.setenv("ABM_VF_KERNEL", kern)
+        eng = VFEngine(1, N, resolution=R, width=W, height=W, boundary=boundary, keep_fields=True, keep_terms=True,
+                       resort_every=2)
+        eng.set_params(); eng.set_state(x, y, th, v, rad)
+        eng.step(1)
+        assert eng.last_kernel() == ("abm::vf_step_warp_kernel" if kern == "warp" else "abm::vf_step_kernel")
+        f1 = eng.fields_packed().copy()
+        eng.step(4)
+        res[kern] = (f1, eng.fields_packed(), eng.terms(), eng.get_state())
+        eng.close()
+    a, b = res["onesided"], res["warp"]
+    assert np.array_equal(a[0], b[0])                      # fields of the first step: bit for bit
+    # later steps: the warp kernel reduces its edge sums across lanes, so the fp64 terms agree to rounding and the fp32
+    # state to an ulp; fields are compared where both saw identical state
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-9, atol=1e-9)
+    for k in ("x", "y", "theta", "vel"):
+        np.testing.assert_allclose(b[3][k], a[3][k], rtol=1e-5, atol=1e-3, err_msg=k)
+    assert (a[1] != b[1]).any(axis=-1).mean() < 0.01
+    cfg = rs.VFConfig(R=R, width=W, height=W, boundary=boundary)
+    sample = [0, 1, 777, 3000, N - 1]
+    ref = rs.vf_step_frozen(x[0], y[0], th[0], v[0], rad[0], cfg, agents=sample)
+    assert np.array_equal(rs.unpack_bits(b[0][0], R)[sample], ref["rows"][sample][:, ::-1])
