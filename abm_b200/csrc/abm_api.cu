@@ -517,7 +517,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.rec_out = e->rec[e->cur ^ 1].p;
     a.n_peers = e->n_peers; a.my_rank = e->my_rank; a.step_no = e->steps_done;
     for (int p = 0; p < e->n_peers; ++p) { a.peer_rec_out[p] = e->peer_rec[p][e->cur ^ 1]; a.peer_flags[p] = e->peer_flags[p]; }
-    a.xflags = e->xflags.p; a.done_counter = e->xflags.p ? reinterpret_cast<unsigned*>(e->xflags.p + 8) : nullptr;
+    a.xflags = e->xflags.p;
     if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
       abm::launch_tile_bbox(a.rec_in, a.B, a.N, e->tile_bbox.p, e->tile_cull2.p, st);
       a.tile_bbox = e->tile_bbox.p; a.tile_cull2 = e->tile_cull2.p;
@@ -530,6 +530,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     if (use_sym) abm::launch_vf_step_sym(a, st);
     else if (use_warp) abm::launch_vf_step_warp(a, cull, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
+    if (e->n_peers > 0) { abm::launch_vf_publish(a, st); ++e->launches; }
     e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : (use_warp ? "abm::vf_step_warp_kernel" : "abm::vf_step_kernel");
     if (use_sym) ++e->sym_launches;
     if (adaptive && use_sym && !e->slow_pending) {

@@ -76,7 +76,7 @@ struct VFKernelArgs {
   float bbox_slack;               // 2 * (r_max - r_min): positions are top-left corners, distances are between centres
   // fused tile exchange of one large swarm over NVLink peer memory (abm_vf_ipc_attach): the epilogue stores every new
   // record into the peers' record tables as well; a kernel starts only when every peer has published the previous step
-  // (flags in this GPU's memory, written by the peers' last CTAs), and publishes its own step to all peers at its end
+  // (flags in this GPU's memory, written by the peers), and a one-thread kernel behind it publishes the step to all ranks
   int n_sms;                      // multiprocessors of the device (grid shaping)
   int n_peers;                    // 0: off
   int my_rank;                    // index of this engine among the attached engines
@@ -84,7 +84,6 @@ struct VFKernelArgs {
   float4* peer_rec_out[7];        // the peers' tables being written in this step
   uint32_t* peer_flags[7];        // the peers' flag arrays (entry my_rank is ours to write)
   uint32_t* xflags;               // this GPU's flag array [8]: xflags[r] = steps published by rank r
-  unsigned* done_counter;         // CTAs of this launch that have finished (last one publishes)
   const PhiLut* lut;              // R + 1 entries
   uint32_t* fields_out;           // nullable, B*tile*W
   double* terms_out;              // nullable, B*tile*6
@@ -101,6 +100,8 @@ void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
 int vf_step_threads(int tile_count, int n_replicates, int n_sms);
 // warp-per-focal-agent kernel (abm_vf_warp.cu): one large sparse swarm and its tiles
 void launch_vf_step_warp(const VFKernelArgs& a, bool cull, cudaStream_t stream);
+struct VFPeerFlags { uint32_t* p[7]; };
+void launch_vf_publish(const VFKernelArgs& a, cudaStream_t stream);   // fused tile exchange: step done -> all ranks
 
 struct VFProjArgs {
   int R, W, n_obj, boundary;

@@ -291,21 +291,6 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
     const bool aa[1] = {active};
     vf_agent_epilogue<TORUS, 1>(a, b, ii, lli, pr, T, mm, tt, 0u, aa);
   }
-  if (a.n_peers > 0) {   // publish: the last CTA of the launch tells every rank that this step's records are in place
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned ticket = atomicAdd(a.done_counter, 1u);
-      if (ticket == gridDim.x - 1) {
-        *a.done_counter = 0u;
-        __threadfence_system();
-        const uint32_t done = a.step_no + 1u;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.xflags + a.my_rank), "r"(done) : "memory");
-        for (int p = 0; p < a.n_peers; ++p)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[p] + a.my_rank), "r"(done) : "memory");
-      }
-    }
-  }
 }
 
 template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>
@@ -344,6 +329,22 @@ void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream
     case 6: launch_fov<true, true, false>(a, grid, T, smem, stream); break;
     default: launch_fov<true, true, true>(a, grid, T, smem, stream); break;
   }
+}
+
+// Fused tile exchange: publish the finished step to every rank.  Launched behind the step kernel on the same stream, so
+// all of its records -- the peer stores included -- are in place (kernel boundary); one release store per rank.
+__global__ void vf_publish_kernel(uint32_t* own_flags, int my_rank, uint32_t done, int n_peers, VFPeerFlags pf) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(own_flags + my_rank), "r"(done) : "memory");
+    for (int p = 0; p < n_peers; ++p)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.p[p] + my_rank), "r"(done) : "memory");
+  }
+}
+void launch_vf_publish(const VFKernelArgs& a, cudaStream_t stream) {
+  VFPeerFlags pf;
+  for (int p = 0; p < 7; ++p) pf.p[p] = a.peer_flags[p];
+  vf_publish_kernel<<<1, 32, 0, stream>>>(a.xflags, a.my_rank, a.step_no + 1u, a.n_peers, pf);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
       else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
       const float4 rec_new = make_float4((float)nx, (float)ny, me.z, me.w);
       a.rec_out[gi] = rec_new;
-      for (int p = 0; p < a.n_peers; ++p) a.peer_rec_out[p][gi] = rec_new;   // NVLink peer stores (fused tile exchange)
+      if (a.n_peers > 0) {                                            // NVLink peer stores (fused tile exchange)
+        for (int p = 0; p < a.n_peers; ++p) a.peer_rec_out[p][gi] = rec_new;
+      }
       a.theta[gi] = (float)nth;
       a.vel[gi] = (float)nv;
       if (a.terms_out) {
@@ -216,21 +218,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
     }
   }
 
-  if (a.n_peers > 0) {   // publish: the last CTA of the launch tells every rank that this step's records are in place
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned ticket = atomicAdd(a.done_counter, 1u);
-      if (ticket == gridDim.x - 1) {
-        *a.done_counter = 0u;
-        __threadfence_system();
-        const uint32_t done = a.step_no + 1u;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.xflags + a.my_rank), "r"(done) : "memory");
-        for (int p = 0; p < a.n_peers; ++p)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[p] + a.my_rank), "r"(done) : "memory");
-      }
-    }
-  }
 }
 
 template <bool TORUS, bool CULL>
