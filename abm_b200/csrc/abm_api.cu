@@ -251,7 +251,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
     A(e->keys_in.alloc(e->n_total)); A(e->keys_out.alloc(e->n_total));
     e->sort_temp_bytes = abm::vf_sort_temp_bytes(cfg->n_replicates, cfg->n_agents);
     A(e->sort_temp.alloc(e->sort_temp_bytes + 16));
-    const size_t nt = (size_t)cfg->n_replicates * ((cfg->n_agents + abm::kRecTile - 1) / abm::kRecTile);
+    const size_t nt = (size_t)cfg->n_replicates * ((cfg->n_agents + abm::kWarpTile - 1) / abm::kWarpTile);
     A(e->tile_bbox.alloc(nt)); A(e->tile_cull2.alloc(nt));
   }
   if (cfg->flags & ABM_VF_KEEP_FIELDS) A(e->fields.alloc(e->n_tile * e->grid.W));
@@ -518,15 +518,17 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.n_peers = e->n_peers; a.my_rank = e->my_rank; a.step_no = e->steps_done;
     for (int p = 0; p < e->n_peers; ++p) { a.peer_rec_out[p] = e->peer_rec[p][e->cur ^ 1]; a.peer_flags[p] = e->peer_flags[p]; }
     a.xflags = e->xflags.p;
-    if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
-      abm::launch_tile_bbox(a.rec_in, a.B, a.N, e->tile_bbox.p, e->tile_cull2.p, st);
-      a.tile_bbox = e->tile_bbox.p; a.tile_cull2 = e->tile_cull2.p;
-      a.bbox_slack = 2.0f * (e->r_max - e->r_min);
-      ++e->launches;
-    }
     // one large sparse swarm (distance culling on) or an agent tile of it: a warp per focal agent
     const bool use_warp = !use_sym && ((force && strcmp(force, "warp") == 0) ||
                                        (!(force && strcmp(force, "onesided") == 0) && (cull || tiled)));
+    if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
+      const int tile = (use_warp && (a.N + abm::kWarpTile - 1) / abm::kWarpTile <= abm::kMaxTileList) ? abm::kWarpTile
+                                                                                                    : abm::kRecTile;
+      abm::launch_tile_bbox(a.rec_in, a.B, a.N, tile, e->tile_bbox.p, e->tile_cull2.p, st);
+      a.tile_bbox = e->tile_bbox.p; a.tile_cull2 = e->tile_cull2.p; a.cull_tile = tile;
+      a.bbox_slack = 2.0f * (e->r_max - e->r_min);
+      ++e->launches;
+    }
     if (use_sym) abm::launch_vf_step_sym(a, st);
     else if (use_warp) abm::launch_vf_step_warp(a, cull, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);

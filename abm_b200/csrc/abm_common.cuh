@@ -9,7 +9,8 @@
 namespace abm {
 
 constexpr int kMaxThreads = 256;     // focal agents per CTA (one thread each)
-constexpr int kRecTile = 512;        // neighbour records per shared-memory stage
+constexpr int kRecTile = 512;        // neighbour records per shared-memory stage (one-thread-per-focal-agent kernel)
+constexpr int kWarpTile = 128;       // records per culling tile of the warp-per-focal-agent kernel (finer boxes, fewer candidates)
 constexpr int kQueueCap = 1024;      // per-CTA queue of pairs deferred to the fp64 path
 
 // per-replicate flocking parameters, order of ABM_VF_* in include/abm_b200.h
@@ -71,6 +72,7 @@ struct VFKernelArgs {
   const int* perm;                // nullable: internal slot -> API index (outputs are written in API order)
   // distance culling by whole record tiles (CULL variants, spatially sorted state): bounding box (xmin, ymin,
   // xmax, ymax) and largest cull^2 of every tile of kRecTile records; nullptr: every tile is visited
+  int cull_tile;                  // records per culling tile (kRecTile or kWarpTile)
   const float4* tile_bbox;
   const float* tile_cull2;
   float bbox_slack;               // 2 * (r_max - r_min): positions are top-left corners, distances are between centres
@@ -91,8 +93,9 @@ struct VFKernelArgs {
 };
 
 void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream);
-void launch_tile_bbox(const float4* rec, int B, int N, float4* bbox, float* cull2, cudaStream_t stream);
-constexpr int kMaxTileList = 1024;   // tiles per replicate the culling list can hold (N <= 262144)
+void launch_tile_bbox(const float4* rec, int B, int N, int tile, float4* bbox, float* cull2, cudaStream_t stream);
+constexpr int kMaxTileList = 1024;   // tiles per replicate the culling list can hold (N <= 524288 at 512 records per tile,
+                                     // N <= 131072 at 128)
 size_t vf_step_smem_bytes(int threads, int W);
 // symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);

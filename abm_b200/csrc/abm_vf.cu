@@ -408,12 +408,14 @@ void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const V
   vf_terms_kernel<<<1, 1, 0, stream>>>(packed_v, R, W, vel, prm, lut, dphi, out6);
 }
 
-// Bounding box and largest cull^2 of every tile of kRecTile records (culling variants, every step).
-__global__ void __launch_bounds__(kRecTile) vf_tile_bbox_kernel(const float4* rec, int N, int n_tiles, float4* bbox,
-                                                                 float* cull2) {
-  __shared__ float red[5][kRecTile / 32];
+// Bounding box and largest cull^2 of every tile of TILE records (culling variants, every step): one warp per 32
+// records, one CTA per tile.
+template <int TILE>
+__global__ void __launch_bounds__(TILE) vf_tile_bbox_kernel(const float4* rec, int N, int n_tiles, float4* bbox,
+                                                             float* cull2) {
+  __shared__ float red[5][TILE / 32];
   const int bt = blockIdx.x, b = bt / n_tiles, t = bt - b * n_tiles;
-  const int j = t * kRecTile + threadIdx.x;
+  const int j = t * TILE + threadIdx.x;
   float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f, c = 0.0f;
   if (j < N) {
     const float4 v = rec[(size_t)b * N + j];
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(kRecTile) vf_tile_bbox_kernel(const float4* re
   if ((threadIdx.x & 31) == 0) { red[0][w] = x0; red[1][w] = y0; red[2][w] = x1; red[3][w] = y1; red[4][w] = c; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < kRecTile / 32; ++k) {
+    for (int k = 1; k < TILE / 32; ++k) {
       x0 = fminf(x0, red[0][k]); y0 = fminf(y0, red[1][k]); x1 = fmaxf(x1, red[2][k]); y1 = fmaxf(y1, red[3][k]);
       c = fmaxf(c, red[4][k]);
     }
@@ -436,9 +438,10 @@ __global__ void __launch_bounds__(kRecTile) vf_tile_bbox_kernel(const float4* re
     cull2[bt] = c;
   }
 }
-void launch_tile_bbox(const float4* rec, int B, int N, float4* bbox, float* cull2, cudaStream_t stream) {
-  const int n_tiles = (N + kRecTile - 1) / kRecTile;
-  vf_tile_bbox_kernel<<<(unsigned)((size_t)B * n_tiles), kRecTile, 0, stream>>>(rec, N, n_tiles, bbox, cull2);
+void launch_tile_bbox(const float4* rec, int B, int N, int tile, float4* bbox, float* cull2, cudaStream_t stream) {
+  const int n_tiles = (N + tile - 1) / tile;
+  if (tile == kWarpTile) vf_tile_bbox_kernel<kWarpTile><<<(unsigned)((size_t)B * n_tiles), kWarpTile, 0, stream>>>(rec, N, n_tiles, bbox, cull2);
+  else vf_tile_bbox_kernel<kRecTile><<<(unsigned)((size_t)B * n_tiles), kRecTile, 0, stream>>>(rec, N, n_tiles, bbox, cull2);
 }
 
 // SoA host-facing state <-> packed neighbour records

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
   const float th = a.theta[gi];
 
   // ---- record tiles to visit: bounding box of the CTA's focal agents against the tiles' boxes ----
-  const int n_tiles = (a.N + kRecTile - 1) / kRecTile;
+  const int tile_sz = a.tile_bbox != nullptr ? a.cull_tile : kRecTile;
+  const int n_tiles = (a.N + tile_sz - 1) / tile_sz;
   const bool use_list = CULL && a.tile_bbox != nullptr && n_tiles <= kMaxTileList;
   int n_stage = n_tiles;
   if (use_list) {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
     const uint32_t row_s = smem_u32(row);
     for (int st = 0; st < n_stage; ++st) {
       const int t = use_list ? tile_list[st] : st;
-      const int j0 = t * kRecTile, j1 = min(a.N, j0 + kRecTile);
+      const int j0 = t * tile_sz, j1 = min(a.N, j0 + tile_sz);
       for (int j = j0 + lane; j < j1; j += 32) {
         const float4 o = __ldg(rep_in + j);
         const float dr = o.z - me.z;
