@@ -163,3 +163,59 @@ class VFRecorder:
             for name in _FIELDS + ("mode",):
                 _write_zarray(os.path.join(d, f"ag_{name}.zarr"), (self.N, self.n_recorded), (self.N, self.chunk))
         return list(self._dirs)
+
+
+class BaseRecorder:
+    """The same for the BASE / foraging engine (`ifdb.py:83-96, 235-253, 437-508`): per recorded replicate
+    `ag_posx/posy/ori/vel/mode/w/u/ipriv/collr/explr.zarr` of shape (num_agents, T) and `res_posx/posy/rad/left/
+    qual.zarr` of shape (num_patches, T).  A foraging replicate is small (50 agents, 3 patches), so the state of the
+    selected replicates is simply fetched after every recorded step (one bulk download of the batch) and kept in host
+    memory like the reference does, then written once by `close()`.  Patch rows are ordered by patch slot (the reference
+    orders them by resource id, which a regenerated patch keeps)."""
+
+    _AG = (("posx", "x"), ("posy", "y"), ("ori", "theta"), ("vel", "vel"), ("mode", "mode"), ("w", "w"), ("u", "u"),
+           ("ipriv", "i_priv"), ("collr", "collected"), ("explr", "patch_id"))
+    _RES = (("posx", "x"), ("posy", "y"), ("rad", "radius"), ("left", "left"), ("qual", "quality"))
+
+    def __init__(self, engine, save_dir, replicates=None, every: int = 1, env_params: dict | None = None):
+        self.eng, self.save_dir, self.every = engine, save_dir, int(every)
+        self.reps = list(range(engine.B)) if replicates is None else [int(b) for b in replicates]
+        self.env_params = env_params
+        self.calls = 0
+        self._ag = {n: [] for n, _ in self._AG}
+        self._res = {n: [] for n, _ in self._RES}
+
+    def record(self):
+        self.calls += 1
+        if (self.calls - 1) % self.every:
+            return
+        a = self.eng.get_agents([k for _, k in self._AG])
+        for n, k in self._AG:
+            v = a[k][self.reps].astype(np.float64)
+            self._ag[n].append(np.trunc(v) if n in ("posx", "posy") else v)       # int(agent.position[.]), ifdb.py:83-84
+        if self.eng.P:
+            p = self.eng.get_patches()
+            for n, k in self._RES:
+                self._res[n].append(p[k][self.reps].astype(np.float64))
+
+    def close(self):
+        dirs = []
+        T = len(self._ag["posx"])
+        for ri, b in enumerate(self.reps):
+            d = os.path.join(self.save_dir, f"replicate_{b:05d}")
+            os.makedirs(d, exist_ok=True)
+            if self.env_params is not None:
+                with open(os.path.join(d, "env_params.json"), "w") as f:
+                    json.dump(self.env_params, f, indent=4)
+            for prefix, store in (("ag", self._ag), ("res", self._res)):
+                for n, steps in store.items():
+                    if not steps:
+                        continue
+                    arr = np.ascontiguousarray(np.stack([s[ri] for s in steps], axis=1))     # (num, T)
+                    path = os.path.join(d, f"{prefix}_{n}.zarr")
+                    os.makedirs(path, exist_ok=True)
+                    arr.tofile(os.path.join(path, "0.0"))
+                    _write_zarray(path, arr.shape, arr.shape)      # one chunk, like the reference (ifdb.py:441-443)
+            dirs.append(d)
+        assert all(len(v) in (0, T) for v in list(self._ag.values()) + list(self._res.values()))
+        return dirs

@@ -269,3 +269,32 @@ def test_function_level_kat_b1(built_lib):
     for v, e in [([1, 1, 1, 0, 0, 0, 0, 0], [1, 0, 0, -1, 0, 0, 0, 0]), ([0, 0, 1, 1, 1, 0, 0, 0], [0, 1, 0, 0, -1, 0, 0, 0]),
                  ([0, 0, 0, 0, 0, 0, 1, 1], [0, 0, 0, 0, 0, 1, 0, -1])]:
         assert vf_supcalc.dPhi_V_of(np.zeros(8), np.array(v, float)).tolist() == e
+
+
+def test_base_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
+    """SURVEY f1 for the foraging engine: ag_*.zarr / res_*.zarr in the reference's layout (ifdb.py:437-508)."""
+    import json
+    import os
+    from abm_b200 import BaseEngine
+    from abm_b200.recorder import BaseRecorder, read_zarr_v2
+    B, N, P, W, T = 3, 12, 2, 300.0, 7
+    rng = np.random.default_rng(4)
+    eng = BaseEngine(B, N, P, resolution=320, width=W, height=W, seed=2)
+    eng.set_params()
+    eng.set_agents(x=rng.integers(30, 300, (B, N)), y=rng.integers(30, 300, (B, N)), theta=rng.uniform(0, 6.28, (B, N)))
+    eng.set_patches(x=rng.integers(60, 200, (B, P)), y=rng.integers(60, 200, (B, P)), radius=np.full((B, P), 30.0),
+                    left=np.full((B, P), 50.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
+    rec = BaseRecorder(eng, str(tmp_path / "run"), replicates=[1], env_params={"N": N})
+    want = []
+    for _ in range(T):
+        eng.step(1); rec.record(); want.append((eng.get_agents(), eng.get_patches()))
+    (d,) = rec.close()
+    assert json.load(open(os.path.join(d, "env_params.json")))["N"] == N
+    for name, key, trunc in (("posx", "x", True), ("ori", "theta", False), ("w", "w", False), ("mode", "mode", False),
+                             ("collr", "collected", False), ("explr", "patch_id", False)):
+        got = read_zarr_v2(os.path.join(d, f"ag_{name}.zarr"))
+        exp = np.stack([w[0][key][1].astype(np.float64) for w in want], axis=1)
+        assert got.shape == (N, T) and np.array_equal(got, np.trunc(exp) if trunc else exp), name
+    got = read_zarr_v2(os.path.join(d, "res_left.zarr"))
+    assert got.shape == (P, T) and np.array_equal(got, np.stack([w[1]["left"][1].astype(np.float64) for w in want], axis=1))
+    eng.close()
