@@ -481,7 +481,8 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   // forces the one-thread-per-focal-agent kernel (abm_vf.cu)
   const char* force = getenv("ABM_VF_KERNEL");
   a.sym_radius = e->r_max;
-  const bool sym_ok = !(force && strcmp(force, "onesided") == 0) && abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
+  const bool sym_ok = !(force && (strcmp(force, "onesided") == 0 || strcmp(force, "warp") == 0)) &&
+                      abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
   const bool adaptive = sym_ok && !force;
   if (adaptive && !e->slow_host) {
     ABM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->slow_host), sizeof(unsigned long long)));
