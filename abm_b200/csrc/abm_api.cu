@@ -97,6 +97,7 @@ struct abm_engine {
   DevBuf<float4> rec[2];
   int cur = 0;          // rec[cur] is the state of the current step
   DevBuf<float> theta, vel, stage_x, stage_y, stage_r;
+  DevBuf<float> radius_api;   // the radii of the last abm_set_state that passed them, caller's order (radius == NULL: keep)
   DevBuf<double> params;
   int n_param_sets = 1;
   DevBuf<float> ov_alp0, ov_bet0, ov_v0;
@@ -240,6 +241,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   A(e->stage_x.alloc(e->n_total));
   A(e->stage_y.alloc(e->n_total));
   A(e->stage_r.alloc(e->n_total));
+  A(e->radius_api.alloc(e->n_total));
   A(e->params.alloc((size_t)cfg->n_replicates * ABM_VF_NPARAM));
   A(e->lut.alloc(e->grid.lut.size()));
   A(e->counters.alloc(8));
@@ -278,7 +280,7 @@ int abm_destroy(abm_engine_t* e) {
   cudaDeviceSynchronize();
   e->rec[0].release(); e->rec[1].release();
   e->theta.release(); e->vel.release();
-  e->stage_x.release(); e->stage_y.release(); e->stage_r.release();
+  e->stage_x.release(); e->stage_y.release(); e->stage_r.release(); e->radius_api.release();
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
@@ -327,7 +329,8 @@ int abm_vf_set_agent_overrides(abm_engine_t* e, const float* alp0, const float* 
 
 int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* theta, const float* vel,
                   const float* radius, int on_device, void* stream) {
-  if (!e || !x || !y || !theta || !vel || !radius) return fail(ABM_E_INVALID, "abm_set_state: null argument");
+  if (!e || !x || !y || !theta || !vel) return fail(ABM_E_INVALID, "abm_set_state: null argument");
+  if (!radius && !e->state_set) return fail(ABM_E_STATE, "abm_set_state: radius == NULL needs an earlier call that passed the radii");
   ABM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = sizeof(float) * e->n_total;
@@ -336,13 +339,13 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
   // An existing spatial order is kept (positions of consecutive calls are usually close): the new state is
   // gathered into the current internal order and re-sorted on the usual schedule.
   const bool permuted = e->sort_enabled && !e->perm_identity;
-  const float *dx = x, *dy = y, *dr = radius, *dth = theta, *dv = vel;
+  const float *dx = x, *dy = y, *dr = e->radius_api.p, *dth = theta, *dv = vel;
   int rc;
+  if (radius && (rc = copy_in(e->radius_api.p, radius, bytes, on_device, st))) return rc;
   if (!on_device) {
     if ((rc = copy_in(e->stage_x.p, x, bytes, 0, st))) return rc;
     if ((rc = copy_in(e->stage_y.p, y, bytes, 0, st))) return rc;
-    if ((rc = copy_in(e->stage_r.p, radius, bytes, 0, st))) return rc;
-    dx = e->stage_x.p; dy = e->stage_y.p; dr = e->stage_r.p;
+    dx = e->stage_x.p; dy = e->stage_y.p;
   }
   const unsigned init_mm[2] = {0x7f800000u, 0u};
   ABM_CUDA(cudaMemcpyAsync(e->radius_minmax.p, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));

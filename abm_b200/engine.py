@@ -131,15 +131,19 @@ class VFEngine:
             self.synchronize()
 
     # -- state -------------------------------------------------------------------------
-    def set_state(self, x, y, theta, vel, radius):
+    def set_state(self, x, y, theta, vel, radius=None):
+        """``radius``: scalar or (B, N) array; None keeps the radii of the previous call."""
         keep = []
         total = self.B * self.N
-        if not _is_torch_cuda(radius):
-            radius = np.broadcast_to(np.asarray(radius, np.float32), np.asarray(x).shape)
-        ptrs = [self._ptr(a, np.float32, total, keep) for a in (x, y, theta, vel, radius)]
+        arrays = [x, y, theta, vel]
+        if radius is not None:
+            if not _is_torch_cuda(radius):
+                radius = np.broadcast_to(np.asarray(radius, np.float32), np.asarray(x).shape)
+            arrays.append(radius)
+        ptrs = [self._ptr(a, np.float32, total, keep) for a in arrays]
         side = self._same_side([p[1] for p in ptrs])
-        _lib.check(self._lib.abm_set_state(self._h, *[p[0] for p in ptrs], side, C.c_void_p(_current_stream())),
-                   "abm_set_state")
+        args = [p[0] for p in ptrs] + ([None] if radius is None else [])
+        _lib.check(self._lib.abm_set_state(self._h, *args, side, C.c_void_p(_current_stream())), "abm_set_state")
         if not side:
             self.synchronize()   # the host arrays in `keep` may go away after return
 

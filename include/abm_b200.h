@@ -112,7 +112,8 @@ int abm_vf_set_agent_overrides(abm_engine_t* e, const float* alp0, const float* 
                                int on_device, void* stream);
 
 /* Agent state in / out.  Replaces writing / reading Agent.position, .orientation,
- * .velocity, .radius (agent.py:52-68).  get: any pointer may be NULL. */
+ * .velocity, .radius (agent.py:52-68).  set: radius may be NULL after the first call (the radii stay what they were:
+ * they never change in the reference either).  get: any pointer may be NULL. */
 int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* theta, const float* vel,
                   const float* radius, int on_device, void* stream);
 int abm_get_state(abm_engine_t* e, float* x, float* y, float* theta, float* vel, int on_device, void* stream);

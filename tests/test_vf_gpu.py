@@ -487,3 +487,24 @@ def test_long_run_kernels_stay_identical(built_lib, monkeypatch):
     np.testing.assert_allclose(b[3]["polarization"], pol, rtol=1e-5, atol=1e-6)
     print("fp64 re-evaluations per 1e6 directions, onesided / symmetric:",
           *(round(1e6 * r[2]["fp64_pairs"] / (300.0 * B * N * (N - 1)), 1) for r in (a, b)))
+
+
+def test_set_state_keeps_radii_when_omitted(built_lib):
+    """abm_set_state with radius == NULL keeps the radii of the previous call (heterogeneous ones too)."""
+    from abm_b200 import VFEngine, _lib
+    rng = np.random.default_rng(8)
+    B, N, W = 2, 60, 500.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    rad = rng.choice([6.0, 10.0, 13.0], (B, N)).astype(np.float32)
+    a = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
+    b = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
+    with pytest.raises(_lib.AbmError):
+        a.set_state(x, y, th, v)                       # nothing to keep yet
+    for e in (a, b):
+        e.set_params(); e.set_state(x, y, th, v, rad); e.step(2)
+    st = a.get_state()
+    a.set_state(st["x"], st["y"], st["theta"], st["vel"])          # radii omitted
+    b.set_state(st["x"], st["y"], st["theta"], st["vel"], rad)
+    a.step(1); b.step(1)
+    assert np.array_equal(a.fields_packed(), b.fields_packed())
+    a.close(); b.close()
