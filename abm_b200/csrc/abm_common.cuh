@@ -48,6 +48,7 @@ struct VFKernelArgs {
   // angles), absolute h guard band of the fast path (h <= 16), the common radius
   float sym_thr_h, sym_radius;
   uint32_t sym_tie32, sym_seam32; // guard bands of the binary-angle bin index, in 2^-32 bins / 2^-32 turns
+  uint32_t opaque_zero;           // always 0: OR-ed into loop constants so that ptxas keeps them in registers
   int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible
   int fov0p;                      // fov_px0 + 33: first visible padded position
   unsigned span;                  // fov_px1 - fov_px0 - 1: number of visible positions

@@ -41,6 +41,10 @@ struct SymConsts {
   int scratch_pos;     // padded position of the scratch word
 };
 __device__ __forceinline__ float pin_f(float v) { asm volatile("" : "+f"(v)); return v; }
+// acc |= m under a predicate: ONE predicated LOP3 (the compiler's own choice is SEL + LOP3)
+__device__ __forceinline__ void or_if(uint32_t& acc, bool p, uint32_t m) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q or.b32 %0, %0, %2;\n\t}" : "+r"(acc) : "r"((uint32_t)p), "r"(m));
+}
 __device__ __forceinline__ uint32_t pin_u(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 
 struct SymShared {
@@ -109,8 +113,9 @@ static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_
   const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
   const uint32_t nb = sym_bearing_bits(dx, dy, kBearingA6);           // bearing of j seen from i
   const uint32_t stride_b = 4u * (uint32_t)Np;
-  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
-  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
+  const uint32_t fc = sym_fold_c<RC>(a);                             // the staged heading constants are the fast path's
+  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, i, j, nb, __float_as_uint(ia.z) + fc, h, flagged);
+  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w) + fc, h, flagged);
 }
 
 // One entry of a warp's slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own
@@ -160,6 +165,34 @@ __device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared&
   }
 }
 
+// The off-diagonal pair loop does not push inside its 16 iterations: every lane collects the four slow flags of an
+// iteration as bit t of four accumulators (one predicated OR each), and the round's entries are compacted into the
+// warp's queue here, once per round -- about 3 passes (the largest number of flagged iterations any lane had) instead
+// of a 20-instruction branch taken by 60 % of the iterations, and no call inside the inner loop.
+template <bool TORUS, int RC>
+__device__ __forceinline__ void sym_push_round(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount,
+                                               int lane, int i, int j0, uint32_t fAi, uint32_t fAj, uint32_t fBi,
+                                               uint32_t fBj) {
+  uint32_t pend = fAi | fAj | fBi | fBj;                        // bit t: iteration t (steps 2t, 2t + 1) has flagged directions
+  while (__any_sync(0xffffffffu, pend != 0u)) {
+    const bool have = pend != 0u;
+    const int t = __ffs((int)pend) - 1;                         // -1 without entry (unused)
+    pend &= pend - 1u;
+    const uint32_t flags = ((fAi >> t) & 1u) | (((fAj >> t) & 1u) << 1) | (((fBi >> t) & 1u) << 2) | (((fBj >> t) & 1u) << 3);
+    const uint32_t entry = (uint32_t)i | ((uint32_t)(j0 ^ (2 * t)) << 10) | (flags << 20);
+    const uint32_t bal = __ballot_sync(0xffffffffu, have);
+    if (have) sts_u32(wq_s + 4u * (uint32_t)(wcount + __popc(bal & ((1u << lane) - 1u))), entry);
+    wcount += __popc(bal);
+    if (wcount >= 32) {
+      wcount -= 32;
+      if (lane == 0) atom_add_shared(sh.qcount_s + 4u, 32u);   // statistics: entries off the fast path (kernel choice)
+      __syncwarp();
+      sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
+      __syncwarp();
+    }
+  }
+}
+
 // Result of the fp32 evaluation of one unordered pair: padded start positions of the two intervals
 // (already redirected to the scratch word when the direction is off the fast path), the 2h-ones mask.
 struct SymStep {
@@ -197,7 +230,7 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   // ---- bearing (shared), bin index of both directions ----
   const uint32_t nb = sym_bearing_bits(dx, dy, c.a6);
   r.slow_i = slow_h;
-  const int ps_i = sym_side_k<RC>(a, nb, hc_i, bh, r.slow_i);
+  const int ps_i = sym_side_k<RC, true>(a, nb, hc_i, bh, r.slow_i);
   bool draw_i = !r.slow_i;
   if (!FULL_FOV) {
     const int pe = ps_i + 2 * ((int)hraw - kMagicBits);
@@ -208,7 +241,7 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   r.ps_j = c.scratch_pos;
   if (BOTH) {
     r.slow_j = slow_h;
-    const int ps_j = sym_side_k<RC>(a, nb, __float_as_uint(o.w), bh, r.slow_j);   // o.w: heading constant + half a turn
+    const int ps_j = sym_side_k<RC, true>(a, nb, __float_as_uint(o.w), bh, r.slow_j);   // o.w: heading constant + half a turn
     bool draw_j = !r.slow_j;
     if (!FULL_FOV) {
       const int pe = ps_j + 2 * ((int)hraw - kMagicBits);
@@ -265,7 +298,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     float4 v;
     if (j < N) {
       const float4 r4 = rep_in[j];
-      const uint32_t hc = sym_heading_const(th_in[j]);
+      const uint32_t hc = sym_heading_const(th_in[j]) - sym_fold_c<RC>(a);   // fast-path form (sym_side_k)
       v = make_float4(r4.x, r4.y, __uint_as_float(hc), __uint_as_float(hc - 0x80000000u));
     } else {   // padding: far away (half width 0), all distinct
       v = make_float4(-1.0e6f - 4096.0f * (float)(j - N), -1.0e6f, 0.f, 0.f);
@@ -280,8 +313,9 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   SymConsts c;
   c.rS = a.sym_radius * S;
   c.c3s = -1.0f / (3.0f * S * S);
-  c.c5s = pin_f(1.0f / (5.0f * S * S * S * S));
-  c.a6 = pin_f(kBearingA6);
+  // OR-ed with a kernel argument that is always 0: a value ptxas cannot rebuild with one MOV, so it stays in a register
+  c.c5s = __uint_as_float(__float_as_uint(1.0f / (5.0f * S * S * S * S)) | a.opaque_zero);
+  c.a6 = __uint_as_float(__float_as_uint(kBearingA6) | a.opaque_zero);
   c.scratch_pos = 32 * (a.W + 2);
   const uint32_t ag_s = smem_u32(sh.ag), rows_s = smem_u32(sh.rows);
   const uint32_t stride_b = 4u * (uint32_t)Np;
@@ -322,20 +356,28 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     // two steps per iteration: both evaluations are independent arithmetic (instruction-level parallelism for the
     // 4 warps per scheduler this kernel runs with)
     float4 oA = lds_f4(rec_j0), oB = lds_f4(rec_j0 ^ 16u);
+    uint32_t fAi = 0u, fAj = 0u, fBi = 0u, fBj = 0u, tbit = 1u;   // slow flags of the round, bit t = iteration t
+    const uint32_t rec_j1 = rec_j0 ^ 16u, row_j1 = row_j0 ^ 4u;
 #pragma unroll 1
-    for (int s = 0; s < 32; s += 2) {
-      const uint32_t sn = (uint32_t)(s + 2) & 31u;          // prefetch the next two partner records (wraps harmlessly)
-      const float4 nA = lds_f4(rec_j0 ^ (16u * sn)), nB = lds_f4(rec_j0 ^ (16u * sn + 16u));
+    for (uint32_t o16 = 32u; o16 <= 512u; o16 += 32u) {       // o16 = 16 (s + 2), s = 0, 2, .. 30: ONE induction variable
+      // prefetch the next two partner records (the last iteration reads block J ^ 1: harmless)
+      const float4 nA = lds_f4(rec_j0 ^ o16), nB = lds_f4(rec_j1 ^ o16);
       const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, oA, me.x, me.y, __float_as_uint(me.z), c);
       const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true>(a, oB, me.x, me.y, __float_as_uint(me.z), c);
+      const uint32_t o4 = (o16 >> 2) - 8u;                     // 4 s
       sym_red(row_i, stride_b, A.ps_i, A.mask);
-      sym_red(row_j0 ^ (4u * s), stride_b, A.ps_j, A.mask);
+      sym_red(row_j0 ^ o4, stride_b, A.ps_j, A.mask);
       sym_red(row_i, stride_b, B.ps_i, B.mask);
-      sym_red(row_j0 ^ (4u * s + 4u), stride_b, B.ps_j, B.mask);
-      // ---- off the fast path (~1 % of the directions): into the warp's region of the slow queue ----
-      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j0 ^ s, A.slow_i, A.slow_j, B.slow_i, B.slow_j);
+      sym_red(row_j1 ^ o4, stride_b, B.ps_j, B.mask);
+      // ---- off the fast path (~1 % of the directions): remembered, pushed after the round ----
+      or_if(fAi, A.slow_i, tbit);
+      or_if(fAj, A.slow_j, tbit);
+      or_if(fBi, B.slow_i, tbit);
+      or_if(fBj, B.slow_j, tbit);
+      tbit += tbit;
       oA = nA; oB = nB;
     }
+    sym_push_round<TORUS, RC>(a, sh, wq, wcount, lane, i, j0, fAi, fAj, fBi, fBj);
   }
   // the rest of the warp's queue (fewer than 32 entries)
   __syncwarp();
