@@ -221,28 +221,21 @@ __device__ __forceinline__ uint32_t sym_heading_const(float theta) {
 // R - 1, i.e. low word = 2^31, so "twice the low word is within 2T of 0 (mod 2^32)" flags every tie AND every bin
 // centre; the error bound of the bin coordinate is the same everywhere on the ring, so the tie band T serves both.
 // Bin centres other than the seam's are false positives (as rare as ties); the slow path, which uses the separate
-// tests below, just draws them.  The rounding constant 2^31 is folded into the heading constant (hconst_fast =
-// hconst - sym_fold_c: off by < R units of 2^-32 bins, which the band absorbs) and `bh` rides in the high word of
-// the multiply-add's addend, so bin + start offset come out of ONE IMAD.WIDE.
-template <int RC>
-__device__ __forceinline__ uint32_t sym_fold_c(const VFKernelArgs& a) {
-  const uint32_t Rp = RC ? (uint32_t)(RC - 1) : (uint32_t)(a.R - 1);
-  return (0x80000000u + Rp / 2u) / Rp;
-}
+// tests, just draws them.  `half64` is the rounding constant 2^31 as a 64-bit register pair the caller keeps alive
+// (IMAD.WIDE takes it as its addend).
 template <int RC, bool FAST = false>
-__device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, uint32_t nb, uint32_t hconst, int bh, bool& slow) {
+__device__ __forceinline__ int sym_side_k(const VFKernelArgs& a, uint32_t nb, uint32_t hconst, int bh, bool& slow,
+                                          unsigned long long half64 = 0x80000000ull) {
   const uint32_t v = 128u * nb - hconst;
   const uint32_t Rp = RC ? (uint32_t)(RC - 1) : (uint32_t)(a.R - 1);
+  const unsigned long long prod = (unsigned long long)v * Rp + half64;
   if (FAST) {
-    const unsigned long long prod = (unsigned long long)v * Rp + ((unsigned long long)(uint32_t)bh << 32);
     const uint32_t lo = (uint32_t)prod;
-    const uint32_t T = a.sym_tie32 ? a.sym_tie32 + Rp : 0u;
-    slow |= (lo + lo + 2u * T) < 4u * T;
-    return (int)(uint32_t)(prod >> 32);
+    slow |= (lo + lo + 2u * a.sym_tie32) < 4u * a.sym_tie32;
+  } else {
+    slow |= ((uint32_t)prod + a.sym_tie32) < 2u * a.sym_tie32;
+    slow |= (v + a.sym_seam32) < 2u * a.sym_seam32;
   }
-  const unsigned long long prod = (unsigned long long)v * Rp + 0x80000000ull;
-  slow |= ((uint32_t)prod + a.sym_tie32) < 2u * a.sym_tie32;
-  slow |= (v + a.sym_seam32) < 2u * a.sym_seam32;
   return (int)(uint32_t)(prod >> 32) + bh;
 }
 

@@ -39,6 +39,7 @@ struct SymConsts {
   float c3s, c5s;      // -1/(3 S^2), 1/(5 S^4), S = R/2pi: atan(q) S = qs (1 + c3s qs^2 + c5s qs^4)
   float a6;            // leading coefficient of the bearing polynomial
   int scratch_pos;     // padded position of the scratch word
+  unsigned long long half64;   // 2^31: rounding constant of the bin index, addend of its IMAD.WIDE
 };
 __device__ __forceinline__ float pin_f(float v) { asm volatile("" : "+f"(v)); return v; }
 // acc |= m under a predicate: ONE predicated LOP3 (the compiler's own choice is SEL + LOP3)
@@ -113,9 +114,8 @@ static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_
   const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
   const uint32_t nb = sym_bearing_bits(dx, dy, kBearingA6);           // bearing of j seen from i
   const uint32_t stride_b = 4u * (uint32_t)Np;
-  const uint32_t fc = sym_fold_c<RC>(a);                             // the staged heading constants are the fast path's
-  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, i, j, nb, __float_as_uint(ia.z) + fc, h, flagged);
-  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w) + fc, h, flagged);
+  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
+  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
 }
 
 // One entry of a warp's slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own
@@ -230,7 +230,7 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   // ---- bearing (shared), bin index of both directions ----
   const uint32_t nb = sym_bearing_bits(dx, dy, c.a6);
   r.slow_i = slow_h;
-  const int ps_i = sym_side_k<RC, true>(a, nb, hc_i, bh, r.slow_i);
+  const int ps_i = sym_side_k<RC, true>(a, nb, hc_i, bh, r.slow_i, c.half64);
   bool draw_i = !r.slow_i;
   if (!FULL_FOV) {
     const int pe = ps_i + 2 * ((int)hraw - kMagicBits);
@@ -241,7 +241,7 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   r.ps_j = c.scratch_pos;
   if (BOTH) {
     r.slow_j = slow_h;
-    const int ps_j = sym_side_k<RC, true>(a, nb, __float_as_uint(o.w), bh, r.slow_j);   // o.w: heading constant + half a turn
+    const int ps_j = sym_side_k<RC, true>(a, nb, __float_as_uint(o.w), bh, r.slow_j, c.half64);   // o.w: heading constant + half a turn
     bool draw_j = !r.slow_j;
     if (!FULL_FOV) {
       const int pe = ps_j + 2 * ((int)hraw - kMagicBits);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     float4 v;
     if (j < N) {
       const float4 r4 = rep_in[j];
-      const uint32_t hc = sym_heading_const(th_in[j]) - sym_fold_c<RC>(a);   // fast-path form (sym_side_k)
+      const uint32_t hc = sym_heading_const(th_in[j]);
       v = make_float4(r4.x, r4.y, __uint_as_float(hc), __uint_as_float(hc - 0x80000000u));
     } else {   // padding: far away (half width 0), all distinct
       v = make_float4(-1.0e6f - 4096.0f * (float)(j - N), -1.0e6f, 0.f, 0.f);
@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   c.c5s = __uint_as_float(__float_as_uint(1.0f / (5.0f * S * S * S * S)) | a.opaque_zero);
   c.a6 = __uint_as_float(__float_as_uint(kBearingA6) | a.opaque_zero);
   c.scratch_pos = 32 * (a.W + 2);
+  c.half64 = ((unsigned long long)a.opaque_zero << 32) | (0x80000000u | a.opaque_zero);
   const uint32_t ag_s = smem_u32(sh.ag), rows_s = smem_u32(sh.rows);
   const uint32_t stride_b = 4u * (uint32_t)Np;
 
