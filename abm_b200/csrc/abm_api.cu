@@ -119,7 +119,7 @@ struct abm_engine {
   uint32_t* peer_flags[7] = {};
   void* peer_maps[7][3] = {};       // what cudaIpcOpenMemHandle returned (to close)
   uint32_t steps_done = 0;
-  // adaptive kernel choice: the symmetric kernel reports how many lane entries left its fast path; in crowded scenes
+  // adaptive kernel choice: the symmetric kernel reports how many pairs left its fast path; in crowded scenes
   // (most intervals wider than 32 bins) the one-thread-per-focal-agent kernel is faster (both give identical results)
   unsigned long long* slow_host = nullptr;   // pinned copy of counters[4]
   cudaEvent_t slow_event = nullptr;
@@ -501,8 +501,8 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       const unsigned long long entries = *e->slow_host - e->slow_seen;      // of the symmetric launches since the last look
       const unsigned long long n_launch = e->slow_req_launch - e->slow_seen_launch;
       e->slow_seen = *e->slow_host; e->slow_seen_launch = e->slow_req_launch;
-      const double lane_iters = 0.25 * (double)a.B * (double)a.N * (double)(a.N - 1);   // 2 unordered pairs each
-      if (n_launch && (double)entries > 0.18 * lane_iters * (double)n_launch) e->onesided_steps_left = 64;   // crowded
+      const double pairs = 0.5 * (double)a.B * (double)a.N * (double)(a.N - 1);   // unordered; one queue entry each
+      if (n_launch && (double)entries > 0.095 * pairs * (double)n_launch) e->onesided_steps_left = 64;   // crowded
     }
     bool use_sym = sym_ok;
     if (adaptive && e->onesided_steps_left > 0) { use_sym = false; --e->onesided_steps_left; }

@@ -52,8 +52,8 @@ struct SymShared {
   float4* ag;          // [Np] (x, y, heading constant, the same + half a turn); padding agents beyond N are far away
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
-  uint32_t* warpq;     // [warps][kSymWarpQ] per-warp ring of lane entries with directions off the fast path
-  int* qcount;         // [0]: fp64 queue, [1]: lane entries off the fast path (statistics)
+  uint32_t* warpq;     // [warps][kSymWarpQ] per-warp queue of pairs with directions off the fast path
+  int* qcount;         // [0]: fp64 queue, [1]: pairs off the fast path (statistics)
   uint32_t ag_s, rows_s, queue_s, qcount_s;   // shared-space addresses of the above (code that is not inlined)
   int Np, N;
 };
@@ -118,77 +118,81 @@ static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_
   if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
 }
 
-// One entry of a warp's slow queue: own agent | partner of the even step << 10 | 4 flags << 20.  Flag bit 0 / 1: own
-// agent sees the partner of the even step / is seen by it, bits 2 / 3: the same for the odd step, whose partner index
-// differs in bit 0.  For a whole (converged) warp, one entry per lane (0: none): the lanes walk through their flagged
-// pairs in lock step, so that the out-of-line evaluation always runs with as many lanes as there are entries left.
+// One entry of a warp's slow queue = one unordered pair with directions off the fast path: agent i | agent j << 10 |
+// dirs << 20 (bit 0: i sees j, bit 1: j sees i; 0 = no entry).  A batch is 32 entries, one per lane of the converged
+// warp, so the out-of-line evaluation always runs with as many lanes as there are entries.
 template <bool TORUS, int RC>
-__device__ __forceinline__ void sym_slow_entries_warp(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
-  uint32_t flags = ent >> 20;
-  const int i = (int)(ent & 1023u), jA = (int)((ent >> 10) & 1023u);
-  while (__any_sync(0xffffffffu, flags != 0u)) {
-    if (flags) {
-      const bool odd = (flags & 3u) == 0u;                  // nothing (left) for the even step: take the odd one
-      const uint32_t dirs = odd ? flags >> 2 : flags & 3u;
-      flags = odd ? 0u : flags & 12u;
-      sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, i, jA ^ (odd ? 1 : 0), dirs);
-    }
+static __device__ __noinline__ void sym_slow_batch(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
+  const uint32_t dirs = ent >> 20;
+  if (dirs) sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (int)(ent & 1023u),
+                                     (int)((ent >> 10) & 1023u), dirs);
+  __syncwarp();
+}
+
+// Work off full batches of the warp's queue (wcount entries, warp-uniform).
+template <bool TORUS, int RC>
+__device__ __forceinline__ void sym_drain(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount, int lane) {
+  while (wcount >= 32) {
+    wcount -= 32;
+    if (lane == 0) atom_add_shared(sh.qcount_s + 4u, 32u);     // statistics: pairs off the fast path (kernel choice)
+    __syncwarp();
+    sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
     __syncwarp();
   }
 }
-template <bool TORUS, int RC>
-static __device__ __noinline__ void sym_slow_batch(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
-  sym_slow_entries_warp<TORUS, RC>(a, sh, ent);
-}
 
-// Append this lane's entry (if it has flagged directions) to the warp's queue in shared memory.  As soon as 32 entries
-// are there the warp works them off, one per lane: draws are reductions, so this can happen at any time -- the
-// latency-bound out-of-line evaluation then overlaps the other warps' pair loops instead of forming a serial phase.
-// wq_s: shared-space address of the warp's queue; wcount: entries in it (warp-uniform).  Called by the converged warp.
+// Diagonal blocks: append this lane's pair (if it has flagged directions) to the warp's queue.  Draws are reductions,
+// so a batch can be worked off at any time -- the latency-bound out-of-line evaluation overlaps the other warps' pair
+// loops instead of forming a serial phase.  wq_s: shared-space address of the warp's queue; wcount: entries in it
+// (warp-uniform).  Called by the converged warp.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount, int lane,
-                                         int i, int jA, bool f0, bool f1, bool f2, bool f3) {
-  const bool any = f0 | f1 | f2 | f3;
+                                         int i, int j, bool f0, bool f1) {
+  const bool any = f0 | f1;
   const uint32_t bal = __ballot_sync(0xffffffffu, any);
   if (bal) {                                                   // warp-uniform
-    const uint32_t flags = (f0 ? 1u : 0u) | (f1 ? 2u : 0u) | (f2 ? 4u : 0u) | (f3 ? 8u : 0u);
-    const uint32_t entry = (uint32_t)i | ((uint32_t)jA << 10) | (flags << 20);
+    const uint32_t entry = (uint32_t)i | ((uint32_t)j << 10) | ((f0 ? 1u : 0u) << 20) | ((f1 ? 2u : 0u) << 20);
     if (any) sts_u32(wq_s + 4u * (uint32_t)(wcount + __popc(bal & ((1u << lane) - 1u))), entry);
     wcount += __popc(bal);
-    if (wcount >= 32) {
-      wcount -= 32;
-      if (lane == 0) atom_add_shared(sh.qcount_s + 4u, 32u);   // statistics: entries off the fast path (kernel choice)
-      __syncwarp();
-      sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
-      __syncwarp();
-    }
+    sym_drain<TORUS, RC>(a, sh, wq_s, wcount, lane);
   }
 }
 
-// The off-diagonal pair loop does not push inside its 16 iterations: every lane collects the four slow flags of an
-// iteration as bit t of four accumulators (one predicated OR each), and the round's entries are compacted into the
-// warp's queue here, once per round -- about 3 passes (the largest number of flagged iterations any lane had) instead
-// of a 20-instruction branch taken by 60 % of the iterations, and no call inside the inner loop.
+// The off-diagonal pair loop does not push inside its 16 iterations: every lane collects the slow flags of the round's
+// 32 steps as bit s of two accumulators (own direction / partner's direction; one predicated OR each), and the round's
+// pairs are appended to the warp's queue here, once per round: a warp scan of the lanes' counts gives every lane its
+// place, then each lane stores its own entries (no ballot per entry).  A round that would overflow the queue (crowded
+// scenes) takes the ballot loop, 32 entries at a time.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_push_round(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount,
-                                               int lane, int i, int j0, uint32_t fAi, uint32_t fAj, uint32_t fBi,
-                                               uint32_t fBj) {
-  uint32_t pend = fAi | fAj | fBi | fBj;                        // bit t: iteration t (steps 2t, 2t + 1) has flagged directions
-  while (__any_sync(0xffffffffu, pend != 0u)) {
-    const bool have = pend != 0u;
-    const int t = __ffs((int)pend) - 1;                         // -1 without entry (unused)
-    pend &= pend - 1u;
-    const uint32_t flags = ((fAi >> t) & 1u) | (((fAj >> t) & 1u) << 1) | (((fBi >> t) & 1u) << 2) | (((fBj >> t) & 1u) << 3);
-    const uint32_t entry = (uint32_t)i | ((uint32_t)(j0 ^ (2 * t)) << 10) | (flags << 20);
-    const uint32_t bal = __ballot_sync(0xffffffffu, have);
-    if (have) sts_u32(wq_s + 4u * (uint32_t)(wcount + __popc(bal & ((1u << lane) - 1u))), entry);
-    wcount += __popc(bal);
-    if (wcount >= 32) {
-      wcount -= 32;
-      if (lane == 0) atom_add_shared(sh.qcount_s + 4u, 32u);   // statistics: entries off the fast path (kernel choice)
-      __syncwarp();
-      sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
-      __syncwarp();
+                                               int lane, int i, int j0, uint32_t fi, uint32_t fj) {
+  uint32_t pend = fi | fj;                                     // bit s: the pair of step s has flagged directions
+  const int cnt = __popc(pend);
+  int incl = cnt;                                              // inclusive warp scan
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (wcount + total <= kSymWarpQ) {                           // warp-uniform; the usual case
+    uint32_t pos = wq_s + 4u * (uint32_t)(wcount + incl - cnt);
+    while (pend) {
+      const int st = __ffs((int)pend) - 1;
+      pend &= pend - 1u;
+      const uint32_t dirs = ((fi >> st) & 1u) | (((fj >> st) & 1u) << 1);
+      sts_u32(pos, (uint32_t)i | ((uint32_t)(j0 ^ st) << 10) | (dirs << 20));
+      pos += 4u;
+    }
+    wcount += total;
+    __syncwarp();
+    sym_drain<TORUS, RC>(a, sh, wq_s, wcount, lane);
+  } else {
+    while (__any_sync(0xffffffffu, pend != 0u)) {
+      const bool have = pend != 0u;
+      const int st = have ? __ffs((int)pend) - 1 : 0;
+      pend &= pend - 1u;
+      sym_push<TORUS, RC>(a, sh, wq_s, wcount, lane, i, j0 ^ st, have && ((fi >> st) & 1u), have && ((fj >> st) & 1u));
     }
   }
 }
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
                                                             __float_as_uint(me.z), c);
       sym_red(rows_s + 4u * (uint32_t)i, stride_b, A.ps_i, A.mask);
       sym_red(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask);
-      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j, false, false);
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j);
     }
   }
 
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     // two steps per iteration: both evaluations are independent arithmetic (instruction-level parallelism for the
     // 4 warps per scheduler this kernel runs with)
     float4 oA = lds_f4(rec_j0), oB = lds_f4(rec_j0 ^ 16u);
-    uint32_t fAi = 0u, fAj = 0u, fBi = 0u, fBj = 0u, tbit = 1u;   // slow flags of the round, bit t = iteration t
+    uint32_t fi = 0u, fj = 0u, tbit = 1u;                  // slow flags of the round (own / partner's direction), bit s = step s
     const uint32_t rec_j1 = rec_j0 ^ 16u, row_j1 = row_j0 ^ 4u;
 #pragma unroll 1
     for (uint32_t o16 = 32u; o16 <= 512u; o16 += 32u) {       // o16 = 16 (s + 2), s = 0, 2, .. 30: ONE induction variable
@@ -371,14 +375,14 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
       sym_red(row_i, stride_b, B.ps_i, B.mask);
       sym_red(row_j1 ^ o4, stride_b, B.ps_j, B.mask);
       // ---- off the fast path (~1 % of the directions): remembered, pushed after the round ----
-      or_if(fAi, A.slow_i, tbit);
-      or_if(fAj, A.slow_j, tbit);
-      or_if(fBi, B.slow_i, tbit);
-      or_if(fBj, B.slow_j, tbit);
-      tbit += tbit;
+      or_if(fi, A.slow_i, tbit);
+      or_if(fj, A.slow_j, tbit);
+      or_if(fi, B.slow_i, tbit + tbit);
+      or_if(fj, B.slow_j, tbit + tbit);
+      tbit <<= 2;
       oA = nA; oB = nB;
     }
-    sym_push_round<TORUS, RC>(a, sh, wq, wcount, lane, i, j0, fAi, fAj, fBi, fBj);
+    sym_push_round<TORUS, RC>(a, sh, wq, wcount, lane, i, j0, fi, fj);
   }
   // the rest of the warp's queue (fewer than 32 entries)
   __syncwarp();

@@ -227,7 +227,7 @@ class VFEngine:
                     collision=out[:, 3].copy())
 
     def slow_entries(self) -> tuple[int, int]:
-        """(lane entries off the symmetric kernel's fast path so far, number of its launches)."""
+        """(pairs off the symmetric kernel's fast path so far, number of its launches)."""
         n, l = C.c_uint64(), C.c_uint64()
         _lib.check(self._lib.abm_vf_slow_entries(self._h, C.byref(n), C.byref(l), C.c_void_p(_current_stream())),
                    "abm_vf_slow_entries")

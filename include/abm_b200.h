@@ -169,9 +169,9 @@ int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev);
  * step.  The choice is made per step from the state (equal radii, replicate fits in shared memory, no distance
  * culling -> symmetric); the environment variable ABM_VF_KERNEL=onesided|symmetric overrides it for tests. */
 const char* abm_vf_last_kernel(abm_engine_t* e);
-/* Statistics behind the automatic choice: lane entries (two unordered pairs each) that left the symmetric kernel's fast
+/* Statistics behind the automatic choice: unordered pairs that left the symmetric kernel's fast
  * path -- wide intervals, guard-band hits -- summed over its launches so far, and the number of those launches.  When
- * more than 18 % of the entries of a step are slow (crowded scene) the next 64 steps use the other kernel. */
+ * more than 9.5 % of the pairs of a step are slow (crowded scene) the next 64 steps use the other kernel. */
 int abm_vf_slow_entries(abm_engine_t* e, uint64_t* entries, uint64_t* sym_launches, void* stream);
 
 /* Summary metrics of the current state, per replicate (the quantities abm/loader/data_loader.py computes
