@@ -53,9 +53,12 @@ struct SymShared {
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
   uint32_t* warpq;     // [warps][kSymWarpQ] per-warp queue of pairs with directions off the fast path
-  int* qcount;         // [0]: fp64 queue, [1]: pairs off the fast path (statistics)
+  int* qcount;         // [0]: fp64 entries (statistics), [1]: pairs off the fast path (statistics), [2 + w]: fp64 entries
+                       // waiting in warp w's part of the queue
   uint32_t ag_s, rows_s, queue_s, qcount_s;   // shared-space addresses of the above (code that is not inlined)
   int Np, N;
+  int fq_cap;          // fp64 queue entries per warp
+  const float4* rep_in; const float* th_in;   // the replicate's records and headings in global memory (fp64 path)
 };
 
 // Out-of-line fp64 evaluation + atomic draw of one ordered pair.  Returns 1 if the fp64 indices
@@ -74,19 +77,20 @@ static __device__ __noinline__ unsigned sym_exact_and_draw(const VFKernelArgs& a
 // intervals, wrap quirks) with reductions.
 template <int RC>
 __device__ __forceinline__ void sym_slow_dir(const VFKernelArgs& a, uint32_t rows_s, uint32_t queue_s, uint32_t qcount_s,
-                                             uint32_t stride_b, int f, int o, uint32_t nb, uint32_t hconst, int h,
-                                             bool flagged) {
+                                             int fq_cap, uint32_t stride_b, int f, int o, uint32_t nb, uint32_t hconst,
+                                             int h, bool flagged) {
   const int R = RC ? RC : a.R;
   const int k = sym_side_k<RC>(a, nb, hconst, 0, flagged);           // bin index
   const uint32_t row_s = rows_s + stride_b + 4u * (uint32_t)f;        // real word 0
-  if (flagged) {
-    const int slot = (int)atom_add_shared(qcount_s, 1u);              // keeps counting past the capacity
-    if (slot < kSymQueueCap) {
+  if (flagged) {                                                      // into this warp's part of the fp64 queue
+    const int slot = (int)atom_add_shared(qcount_s, 1u);
+    if (slot < fq_cap) {
       sts_u32(queue_s + 8u * (uint32_t)slot, ((uint32_t)f << 16) | (uint32_t)o);
       sts_u32(queue_s + 8u * (uint32_t)slot + 4u, ((uint32_t)k << 16) | ((uint32_t)h & 0xffffu));
-    } else {
+    } else {                                                          // full (cannot happen with batches of 32 pairs)
       const size_t g = (size_t)blockIdx.x * a.N;
       const unsigned diff = sym_exact_and_draw(a, row_s, stride_b, a.rec_in[g + f], a.theta[g + f], a.rec_in[g + o], k, h);
+      atomicAdd(&a.counters[0], 1ull);
       atomicAdd(&a.counters[1], 1ull);
       if (diff) atomicAdd(&a.counters[2], 1ull);
     }
@@ -96,7 +100,7 @@ __device__ __forceinline__ void sym_slow_dir(const VFKernelArgs& a, uint32_t row
 }
 template <bool TORUS, int RC>
 static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_t ag_s, uint32_t rows_s, uint32_t queue_s,
-                                                  uint32_t qcount_s, int Np, int i, int j, uint32_t dirs) {
+                                                  uint32_t qcount_s, int fq_cap, int Np, int i, int j, uint32_t dirs) {
   using K = PairK<RC>;
   if ((i >= a.N) | (j >= a.N)) return;                                // padding agents
   const float4 ia = lds_f4(ag_s + 16u * (uint32_t)i), ja = lds_f4(ag_s + 16u * (uint32_t)j);
@@ -114,29 +118,62 @@ static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_
   const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
   const uint32_t nb = sym_bearing_bits(dx, dy, kBearingA6);           // bearing of j seen from i
   const uint32_t stride_b = 4u * (uint32_t)Np;
-  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
-  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
+  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
+  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
 }
 
 // One entry of a warp's slow queue = one unordered pair with directions off the fast path: agent i | agent j << 10 |
 // dirs << 20 (bit 0: i sees j, bit 1: j sees i; 0 = no entry).  A batch is 32 entries, one per lane of the converged
 // warp, so the out-of-line evaluation always runs with as many lanes as there are entries.
+// Guard-band hits wait in the warp's own part of the fp64 queue and are worked off by the warp itself, 32 at a time
+// (`all`: whatever is left), as soon as a slow batch has left at least 32 there: like the slow batches, the
+// latency-bound fp64 evaluation (the reference's own operation sequence) then overlaps the other warps' pair loops
+// instead of forming a serial phase of the CTA.  Called by the converged warp.
+struct SymWarpStats { unsigned n_fp64, n_mismatch; };
+template <bool TORUS, int RC>
+static __device__ __noinline__ void sym_fp64_drain(const VFKernelArgs& a, const SymShared& sh, SymWarpStats& ws, bool all) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t cnt_s = sh.qcount_s + 8u + 4u * (uint32_t)warp;
+  const uint32_t q_s = sh.queue_s + 8u * (uint32_t)(warp * sh.fq_cap);
+  const uint32_t stride_b = 4u * (uint32_t)sh.Np;
+  int n = min((int)lds_u32(cnt_s), sh.fq_cap);
+  __syncwarp();
+  while (n >= 32 || (all && n > 0)) {
+    const int take = min(n, 32);
+    n -= take;
+    if (lane < take) {
+      const uint32_t q0 = lds_u32(q_s + 8u * (uint32_t)(n + lane)), q1 = lds_u32(q_s + 8u * (uint32_t)(n + lane) + 4u);
+      const int f = (int)(q0 >> 16), o = (int)(q0 & 0xffffu);
+      ws.n_mismatch += sym_exact_and_draw(a, sh.rows_s + stride_b + 4u * (uint32_t)f, stride_b, sh.rep_in[f], sh.th_in[f],
+                                          sh.rep_in[o], (int)(short)(q1 >> 16), (int)(short)(q1 & 0xffffu));
+    }
+    ws.n_fp64 += (unsigned)take;                               // (every lane counts the batch; lane 0 reports)
+    __syncwarp();
+  }
+  if (lane == 0) sts_u32(cnt_s, (uint32_t)n);
+  __syncwarp();
+}
+
 template <bool TORUS, int RC>
 static __device__ __noinline__ void sym_slow_batch(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
   const uint32_t dirs = ent >> 20;
-  if (dirs) sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s, sh.qcount_s, sh.Np, (int)(ent & 1023u),
+  const int warp = threadIdx.x >> 5;
+  if (dirs) sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s + 8u * (uint32_t)(warp * sh.fq_cap),
+                                     sh.qcount_s + 8u + 4u * (uint32_t)warp, sh.fq_cap, sh.Np, (int)(ent & 1023u),
                                      (int)((ent >> 10) & 1023u), dirs);
   __syncwarp();
 }
 
 // Work off full batches of the warp's queue (wcount entries, warp-uniform).
 template <bool TORUS, int RC>
-__device__ __forceinline__ void sym_drain(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount, int lane) {
+__device__ __forceinline__ void sym_drain(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount, int lane,
+                                          SymWarpStats& ws) {
   while (wcount >= 32) {
     wcount -= 32;
     if (lane == 0) atom_add_shared(sh.qcount_s + 4u, 32u);     // statistics: pairs off the fast path (kernel choice)
     __syncwarp();
     sym_slow_batch<TORUS, RC>(a, sh, lds_u32(wq_s + 4u * (uint32_t)(wcount + lane)));
+    if (lds_u32(sh.qcount_s + 8u + 4u * (uint32_t)(threadIdx.x >> 5)) >= 32u) sym_fp64_drain<TORUS, RC>(a, sh, ws, false);
     __syncwarp();
   }
 }
@@ -147,14 +184,14 @@ __device__ __forceinline__ void sym_drain(const VFKernelArgs& a, const SymShared
 // (warp-uniform).  Called by the converged warp.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount, int lane,
-                                         int i, int j, bool f0, bool f1) {
+                                         int i, int j, bool f0, bool f1, SymWarpStats& ws) {
   const bool any = f0 | f1;
   const uint32_t bal = __ballot_sync(0xffffffffu, any);
   if (bal) {                                                   // warp-uniform
     const uint32_t entry = (uint32_t)i | ((uint32_t)j << 10) | ((f0 ? 1u : 0u) << 20) | ((f1 ? 2u : 0u) << 20);
     if (any) sts_u32(wq_s + 4u * (uint32_t)(wcount + __popc(bal & ((1u << lane) - 1u))), entry);
     wcount += __popc(bal);
-    sym_drain<TORUS, RC>(a, sh, wq_s, wcount, lane);
+    sym_drain<TORUS, RC>(a, sh, wq_s, wcount, lane, ws);
   }
 }
 
@@ -165,7 +202,7 @@ __device__ __forceinline__ void sym_push(const VFKernelArgs& a, const SymShared&
 // scenes) takes the ballot loop, 32 entries at a time.
 template <bool TORUS, int RC>
 __device__ __forceinline__ void sym_push_round(const VFKernelArgs& a, const SymShared& sh, uint32_t wq_s, int& wcount,
-                                               int lane, int i, int j0, uint32_t fi, uint32_t fj) {
+                                               int lane, int i, int j0, uint32_t fi, uint32_t fj, SymWarpStats& ws) {
   uint32_t pend = fi | fj;                                     // bit s: the pair of step s has flagged directions
   const int cnt = __popc(pend);
   int incl = cnt;                                              // inclusive warp scan
@@ -186,13 +223,13 @@ __device__ __forceinline__ void sym_push_round(const VFKernelArgs& a, const SymS
     }
     wcount += total;
     __syncwarp();
-    sym_drain<TORUS, RC>(a, sh, wq_s, wcount, lane);
+    sym_drain<TORUS, RC>(a, sh, wq_s, wcount, lane, ws);
   } else {
     while (__any_sync(0xffffffffu, pend != 0u)) {
       const bool have = pend != 0u;
       const int st = have ? __ffs((int)pend) - 1 : 0;
       pend &= pend - 1u;
-      sym_push<TORUS, RC>(a, sh, wq_s, wcount, lane, i, j0 ^ st, have && ((fi >> st) & 1u), have && ((fj >> st) & 1u));
+      sym_push<TORUS, RC>(a, sh, wq_s, wcount, lane, i, j0 ^ st, have && ((fi >> st) & 1u), have && ((fj >> st) & 1u), ws);
     }
   }
 }
@@ -270,7 +307,7 @@ __device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps,
 
 size_t vf_sym_smem_bytes(int Np, int W) {
   return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + 3) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
-         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + 16;
+         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + 96;   // counters: 2 + one per warp (<= 16)
 }
 
 // NPC > 0: compile-time padded replicate size (row stride becomes an immediate), 0: the run-time argument.
@@ -286,6 +323,8 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   sh.warpq = sh.queue + 2 * kSymQueueCap;
   sh.qcount = reinterpret_cast<int*>(sh.warpq + kSymWarpQ * (Np / 64));
   sh.Np = Np; sh.N = a.N;
+  sh.fq_cap = kSymQueueCap / (int)(blockDim.x >> 5);
+  sh.rep_in = a.rec_in + (size_t)blockIdx.x * a.N; sh.th_in = a.theta + (size_t)blockIdx.x * a.N;
   sh.ag_s = smem_u32(sh.ag); sh.rows_s = smem_u32(sh.rows); sh.queue_s = smem_u32(sh.queue);
   sh.qcount_s = smem_u32(sh.qcount);
 
@@ -310,7 +349,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     sh.ag[j] = v;
   }
   for (int w = tid; w < (a.W + 3) * Np; w += T) sh.rows[w] = 0u;
-  if (tid < 2) sh.qcount[tid] = 0;
+  if (tid < 18) sh.qcount[tid] = 0;
   __syncthreads();
 
   const float S = K::y_scale(a);
@@ -327,6 +366,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
 
   const uint32_t wq = smem_u32(sh.warpq + kSymWarpQ * warp);   // this warp's queue of slow entries
   int wcount = 0;                              // entries in it (warp-uniform)
+  SymWarpStats ws{0u, 0u};                     // fp64 entries worked off by this warp (warp-uniform) / mismatches (per lane)
 
   // ---- diagonal blocks, two per warp: the pair {x, x ^ s} of a block is taken, in step s, by the one of its two
   //      lanes whose bit hb(s) (the highest set bit of s) is clear -- for the warp's first block; for its second block
@@ -343,7 +383,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
                                                             __float_as_uint(me.z), c);
       sym_red(rows_s + 4u * (uint32_t)i, stride_b, A.ps_i, A.mask);
       sym_red(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask);
-      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j);
+      sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j, ws);
     }
   }
 
@@ -382,42 +422,25 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
       tbit <<= 2;
       oA = nA; oB = nB;
     }
-    sym_push_round<TORUS, RC>(a, sh, wq, wcount, lane, i, j0, fi, fj);
+    sym_push_round<TORUS, RC>(a, sh, wq, wcount, lane, i, j0, fi, fj, ws);
   }
-  // the rest of the warp's queue (fewer than 32 entries)
+  // the rest of the warp's queue (fewer than 32 entries), then the rest of its fp64 queue
   __syncwarp();
   if (lane == 0) atom_add_shared(sh.qcount_s + 4u, (uint32_t)wcount);
   sym_slow_batch<TORUS, RC>(a, sh, lane < wcount ? lds_u32(wq + 4u * (uint32_t)lane) : 0u);
-  __syncthreads();
-
-  // ---- deferred pairs: fp64, the reference's own operation sequence ----
-  unsigned n_mismatch = 0;
+  sym_fp64_drain<TORUS, RC>(a, sh, ws, true);
   {
-    const int nq = min(sh.qcount[0], kSymQueueCap);
-    for (int e0 = 0; e0 < nq; e0 += T) {         // warp-uniform trip count (see above)
-      const int e = e0 + tid;
-      if (e < nq) {
-        const uint32_t q0 = sh.queue[2 * e], q1 = sh.queue[2 * e + 1];
-        const int f = (int)(q0 >> 16), o = (int)(q0 & 0xffffu);
-        n_mismatch += sym_exact_and_draw(a, sh.rows_s + stride_b + 4u * (uint32_t)f, stride_b, rep_in[f], th_in[f], rep_in[o],
-                                         (int)(short)(q1 >> 16), (int)(short)(q1 & 0xffffu));
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  {
-    const unsigned nm = __reduce_add_sync(0xffffffffu, n_mismatch);
+    const unsigned nm = __reduce_add_sync(0xffffffffu, ws.n_mismatch);
+    if (lane == 0 && ws.n_fp64) atomicAdd(&a.counters[0], (unsigned long long)ws.n_fp64);
     if (lane == 0 && nm) atomicAdd(&a.counters[2], (unsigned long long)nm);
-    if (tid == 0 && sh.qcount[0]) atomicAdd(&a.counters[0], (unsigned long long)sh.qcount[0]);
-    if (tid == 0 && sh.qcount[1]) atomicAdd(&a.counters[4], (unsigned long long)sh.qcount[1]);
   }
+  __syncthreads();
+  if (tid == 0 && sh.qcount[1]) atomicAdd(&a.counters[4], (unsigned long long)sh.qcount[1]);
 
   // ---- epilogue: one agent per thread and pass (bank == lane) ----
   // the fp64 queue is dead now: it takes a copy of exp(i Phi_k) for the edge sums (19 KB at R = 1200)
   uint32_t etab_s = 0u;
   if ((size_t)a.R * sizeof(double2) <= 2 * sizeof(uint32_t) * kSymQueueCap) {
-    __syncthreads();
     double2* etab = reinterpret_cast<double2*>(sh.queue);
     for (int k = tid; k < a.R; k += T) etab[k] = *reinterpret_cast<const double2*>(&a.lut[k].c);
     __syncthreads();
