@@ -331,13 +331,15 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
 __global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const size_t per_warp = warp_field_bytes(a.N, a.W) + 4 * sizeof(int) * (size_t)a.N;
+  const size_t per_warp = warp_field_bytes(a.N, a.W) + 6 * sizeof(int) * (size_t)a.N;
   unsigned char* base = smem_raw + per_warp * wib;
   WarpField wf = warp_field_at(base, a.N);
   int* ov = reinterpret_cast<int*>(base + warp_field_bytes(a.N, a.W));   // override_mode, mutable
   int* md = ov + a.N;                                                    // mode
   float* th = reinterpret_cast<float*>(md + a.N);                        // heading
   int* col = reinterpret_cast<int*>(th + a.N);                           // member of collided_agents
+  float* px = reinterpret_cast<float*>(col + a.N);                       // positions (this phase does not move anybody):
+  float* py = px + a.N;                                                  // staged once, the loops below are latency-bound
   const int b = blockIdx.x * wpb + wib;
   if (b >= a.B) return;
   const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
@@ -347,17 +349,18 @@ __global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArg
   const double r = a.radius;
   for (int i = lane; i < N; i += 32) {
     ov[i] = a.ag.override_mode[a0 + i]; md[i] = a.ag.mode[a0 + i]; th[i] = a.ag.theta[a0 + i]; col[i] = 0;
+    px[i] = a.ag.x[a0 + i]; py[i] = a.ag.y[a0 + i];
   }
   __syncwarp();
   const float lim2 = (float)((2.0 * (r + 2.0)) * (2.0 * (r + 2.0)));     // (r1 + 2 + r2 + 2)^2, sims.py:739-752
 
   for (int a1 = 0; a1 < N; ++a1) {
-    const float x1 = truncf(a.ag.x[a0 + a1]), y1 = truncf(a.ag.y[a0 + a1]);   // rect.x = int(position) (agent.py:303-304)
+    const float x1 = truncf(px[a1]), y1 = truncf(py[a1]);                     // rect.x = int(position) (agent.py:303-304)
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int jj = j0 + lane;
       bool hit = false;
       if (jj < N && jj != a1) {
-        const float dx = truncf(a.ag.x[a0 + jj]) - x1, dy = truncf(a.ag.y[a0 + jj]) - y1;
+        const float dx = truncf(px[jj]) - x1, dy = truncf(py[jj]) - y1;
         hit = dx * dx + dy * dy <= lim2;
       }
       unsigned hits = __ballot_sync(0xffffffffu, hit);
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArg
           __syncwarp();
           if (lane == 0 && ov[a2] != OV_EXPLOIT) { ov[a2] = OV_COLLIDE; md[a2] = MODE_COLLIDE; }   // :442-443
           for (int w = lane; w < W + 1; w += 32) wf.row[w] = 0u;
-          const float x2 = a.ag.x[a0 + a2], y2 = a.ag.y[a0 + a2];
+          const float x2 = px[a2], y2 = py[a2];
           const FocalExact fe = vf_focal_exact(x2, y2, (float)r, th[a2]);
           int M = 0, last_j = -1;
           double last_d = 0.0;
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArg
             ObjRec o; o.s = 0; o.e = 0; o.d = 0.0;
             double dist = 0.0;
             if (j < N && j != a2) {
-              const float xj = a.ag.x[a0 + j], yj = a.ag.y[a0 + j];
+              const float xj = px[j], yj = py[j];
               if (base_centre_distance(fe, r, xj, yj) < 2.0 * r + 20.0) {           // :446-447
                 counted = !((xj == x2) && (yj == y2));
                 rec = base_interval(fe, r, x2, y2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o, dist);
@@ -440,7 +443,7 @@ void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
   cudaGetDevice(&dev);
   int smem_max = 48 * 1024;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t per_warp = warp_field_bytes(a.N, a.W) + 4 * sizeof(int) * (size_t)a.N;
+  const size_t per_warp = warp_field_bytes(a.N, a.W) + 6 * sizeof(int) * (size_t)a.N;
   int warps = 4;
   while (warps > 1 && per_warp * warps > (size_t)smem_max) warps >>= 1;
   const size_t smem = per_warp * warps;

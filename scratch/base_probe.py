@@ -11,5 +11,9 @@ eng = BaseEngine(B, N, P, resolution=1200, width=W, height=W, visual_exclusion=T
 eng.set_params(Eps_w=2.0, Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5,
                reloc_theta_max=1.8, exp_stop_ratio=0.175)
 eng.set_agents(x=x0, y=y0, theta=th0); eng.set_patches(**pa)
-eng.step(int(sys.argv[1]) if len(sys.argv) > 1 else 30)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+eng.step(5)
 torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record(); eng.step(n); e1.record(); torch.cuda.synchronize()
+print('BASE C3 probe: %.3f ms/step, %.3g agent-steps/s' % (e0.elapsed_time(e1) / n, B * N * n / e0.elapsed_time(e1) * 1e3))
