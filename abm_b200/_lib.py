@@ -139,6 +139,7 @@ SYMBOLS = {
     "abm_base_step": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_uint32, _P]),
     "abm_base_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_base_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
+    "abm_base_metrics": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "abm_base_projection_field": (C.c_int, [C.POINTER(BaseProjArgs), _P, C.POINTER(C.c_double)]),
     "abm_base_reloc_lr": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.POINTER(C.c_double)]),

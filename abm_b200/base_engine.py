@@ -162,6 +162,18 @@ class BaseEngine:
         bits = (w[..., :, None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)
         return bits.reshape(self.B, self.N, -1)[..., :self.R].astype(bool)
 
+    def metrics(self, reset: bool = False) -> dict:
+        """Per-replicate summary metrics reduced on the device (abm/loader/data_loader.py
+        calculate_search_efficiency :1294-1353, calculate_relocation_time :1903-1928): dict of (B,) float32 arrays
+        `search_efficiency` (mean collected_r / T), `relocation_time`, `explore_time`, `exploit_time`,
+        `collide_time` (fractions of the agent-steps logged in that mode) and `mean_collected`; T counts the steps
+        since creation or the last `reset`."""
+        out = np.empty((self.B, 6), np.float32)
+        _lib.check(self._lib.abm_base_metrics(self._h, C.c_void_p(out.ctypes.data), 0, int(reset),
+                                              C.c_void_p(_current_stream())), "abm_base_metrics")
+        names = ("search_efficiency", "relocation_time", "explore_time", "exploit_time", "collide_time", "mean_collected")
+        return {k: out[:, i].copy() for i, k in enumerate(names)}
+
     def counters(self) -> dict:
         c = (C.c_uint64 * 4)()
         _lib.check(self._lib.abm_base_get_counters(self._h, c, C.c_void_p(_current_stream())), "abm_base_get_counters")

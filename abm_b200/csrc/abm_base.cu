@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
   a.ag.w[gi] = (float)w; a.ag.u[gi] = (float)u; a.ag.i_priv[gi] = (float)I_priv;
   a.ag.override_mode[gi] = override; a.ag.mode[gi] = mode;
   a.ag.collected_before[gi] = (float)collected;              // :283
+  atomicAdd(&a.mode_steps[(size_t)b * 4 + mode], 1u);        // the mode this agent is logged with at the end of the step
 }
 
 // ---------------------------------------------------------------------------------------
@@ -540,6 +541,36 @@ void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream) {
   const long long total = (long long)a.B * a.N;
   const unsigned grid = (unsigned)((total + warps - 1) / warps);
   base_agent_kernel<<<grid, warps * 32, smem, stream>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------
+// summary metrics of the foraging runs, one warp per replicate:
+//   search efficiency  mean over agents of collected_r / T        (data_loader.py calculate_search_efficiency :1294-1353)
+//   relocation time    fraction of the agent-steps logged in mode "relocate" (calculate_relocation_time :1903-1928);
+//                      the other three modes come with it
+// ---------------------------------------------------------------------------------------
+__global__ void base_metrics_kernel(const float* __restrict__ collected, const unsigned int* __restrict__ mode_steps, int B,
+                                    int N, unsigned long long steps, float* __restrict__ out) {
+  const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  double sum = 0.0;
+  for (int i = lane; i < N; i += 32) sum += (double)collected[(size_t)b * N + i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) {
+    const double T = steps ? (double)steps : 1.0, NT = T * (double)N;
+    float* o = out + (size_t)b * 6;
+    o[0] = (float)(sum / (double)N / T);
+    o[1] = (float)((double)mode_steps[b * 4 + MODE_RELOCATE] / NT);
+    o[2] = (float)((double)mode_steps[b * 4 + MODE_EXPLORE] / NT);
+    o[3] = (float)((double)mode_steps[b * 4 + MODE_EXPLOIT] / NT);
+    o[4] = (float)((double)mode_steps[b * 4 + MODE_COLLIDE] / NT);
+    o[5] = (float)(sum / (double)N);
+  }
+}
+void launch_base_metrics(const float* collected, const unsigned int* mode_steps, int B, int N, unsigned long long steps,
+                         float* out, cudaStream_t stream) {
+  base_metrics_kernel<<<(B + 3) / 4, 128, 0, stream>>>(collected, mode_steps, B, N, steps, out);
 }
 
 }  // namespace abm

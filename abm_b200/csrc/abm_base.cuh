@@ -54,11 +54,15 @@ struct BaseKernelArgs {
   const float* inject_dtheta;  // nullable, B*N: replaces the random-walk draw (parity tests)
   uint32_t* fields_out;        // nullable, B*N*W, stored order
   unsigned long long* counters;   // [0] patches regenerated, [1] regeneration retries exhausted
+  unsigned int* mode_steps;    // B*4: agent-steps spent in mode explore / exploit / relocate / collide since the last
+                               // reset (the mode an agent is logged with, ifdb.py:197-206); summary metrics
 };
 
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream);
+void launch_base_metrics(const float* collected, const unsigned int* mode_steps, int B, int N, unsigned long long steps,
+                         float* out, cudaStream_t stream);
 
 struct BaseProjArgs {
   int R, W, n_social, n_occ, visual_exclusion, keep_distance;

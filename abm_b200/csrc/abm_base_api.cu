@@ -24,6 +24,9 @@ struct abm_base_engine {
   DevBuf<double> params;
   DevBuf<float> inject;
   DevBuf<unsigned long long> counters;
+  DevBuf<unsigned int> mode_steps;      // B*4, see BaseKernelArgs
+  DevBuf<float> metrics;                // B*6 staging of abm_base_metrics
+  unsigned long long metric_steps = 0;  // full steps since the last metrics reset
   int n_param_sets = 1;
   bool agents_set = false, patches_set = false;
   unsigned step = 0;
@@ -102,6 +105,9 @@ int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t*
   A(e->params.alloc((size_t)cfg->n_replicates * abm::kBaseNParam));
   A(e->counters.alloc(4));
   if (err == cudaSuccess) err = cudaMemset(e->counters.p, 0, 4 * sizeof(unsigned long long));
+  A(e->mode_steps.alloc(4 * (size_t)cfg->n_replicates));
+  A(e->metrics.alloc(6 * (size_t)cfg->n_replicates));
+  if (err == cudaSuccess) err = cudaMemset(e->mode_steps.p, 0, 4 * sizeof(unsigned int) * (size_t)cfg->n_replicates);
   // defaults of decision_params.py / movement_params.py
   const double defaults[abm::kBaseNParam] = {0.5, 3, 0.085, 0, 1, 0.5, 3, 0.085, 0, 1, 0.25, 0.01, 2, 1,
                                              1, -0.3, 0.3, 0.5, 0.08, 1};
@@ -130,7 +136,7 @@ int abm_base_destroy(abm_base_engine_t* e) {
                            &e->pquality}) b->release();
   for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid,
                              &e->collided}) b->release();
-  e->novelty.release(); e->fields.release(); e->params.release(); e->counters.release();
+  e->novelty.release(); e->fields.release(); e->params.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
   delete e;
   return ABM_OK;
 }
@@ -232,7 +238,7 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
                             e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p};
   a.pa = abm::BasePatchPtrs{e->px.p, e->py.p, e->pradius.p, e->pleft.p, e->pquality.p, e->pid.p};
   a.params = e->params.p; a.param_stride = (e->n_param_sets == 1) ? 0 : abm::kBaseNParam;
-  a.fields_out = e->fields.p; a.counters = e->counters.p;
+  a.fields_out = e->fields.p; a.counters = e->counters.p; a.mode_steps = e->mode_steps.p;
   if (inject_dtheta) {
     const float* src = inject_dtheta;
     if (!inject_on_device) {
@@ -251,7 +257,7 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
       ABM_CUDA(cudaMemcpyAsync(e->snap_override.p, e->override_mode.p, sizeof(int32_t) * e->n_agents_total,
                                cudaMemcpyDeviceToDevice, st));
     }
-    if (phases & ABM_BASE_PHASE_AGENTS) { abm::launch_base_agents(a, st); ++e->launches; }
+    if (phases & ABM_BASE_PHASE_AGENTS) { abm::launch_base_agents(a, st); ++e->launches; ++e->metric_steps; }
     ++e->step; ++e->steps;
   }
   ABM_CUDA(cudaGetLastError());
@@ -279,6 +285,26 @@ int abm_base_get_counters(abm_base_engine_t* e, uint64_t counters[4], void* stre
   return ABM_OK;
 }
 
+int abm_base_metrics(abm_base_engine_t* e, float* out, int on_device, int reset, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_metrics: null engine");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = e->cfg.n_replicates;
+  if (out) {
+    float* dst = on_device ? out : e->metrics.p;
+    abm::launch_base_metrics(e->collected.p, e->mode_steps.p, B, e->cfg.n_agents, e->metric_steps, dst, st);
+    ABM_CUDA(cudaGetLastError());
+    if (!on_device) {
+      ABM_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * 6 * (size_t)B, cudaMemcpyDeviceToHost, st));
+      ABM_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  if (reset) {   // the time window of the mode fractions starts again (collected_r keeps counting, like the reference's)
+    ABM_CUDA(cudaMemsetAsync(e->mode_steps.p, 0, 4 * sizeof(unsigned int) * (size_t)B, st));
+    e->metric_steps = 0;
+  }
+  return ABM_OK;
+}
 
 // ---- stateless function-level entry points ----
 

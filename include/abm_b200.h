@@ -300,6 +300,15 @@ int abm_base_get_fields(abm_base_engine_t* e, uint32_t* packed, int on_device, v
  * [2] = kernel launches, [3] = steps. */
 int abm_base_get_counters(abm_base_engine_t* e, uint64_t counters[4], void* stream);
 
+/* Summary metrics of the foraging runs, per replicate, reduced on the device (the quantities
+ * abm/loader/data_loader.py computes offline from the logged collresource / mode arrays): out[b * 6 + k], k = 0: search
+ * efficiency = mean over agents of collected_r / T (calculate_search_efficiency :1294-1353 with t_start = 0); 1: relative
+ * relocation time = fraction of the agent-steps logged in mode "relocate" (calculate_relocation_time :1903-1928; the mode
+ * is the one ifdb.save_agent_data_RAM logs at the end of a step, codes of ifdb.mode_to_int :197-206); 2, 3, 4: the same
+ * for explore, exploit, collide; 5: mean collected_r.  T = steps with an agent phase since creation or the last reset.
+ * out == NULL with reset != 0 only restarts the time window (collected_r keeps counting, as in the reference). */
+int abm_base_metrics(abm_base_engine_t* e, float* out, int on_device, int reset, void* stream);
+
 /* ---- stateless function-level entry points of the BASE variant (host pointers, synchronous) ---- */
 
 /* Agent.projection_field(obstacles, keep_distance_info, non_expl_agents, fov) (agent.py:457-597)

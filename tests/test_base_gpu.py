@@ -179,6 +179,46 @@ def test_full_loop_runs_and_forages(built_lib):
     eng.close()
 
 
+def test_summary_metrics_match_logged_arrays(built_lib):
+    """SURVEY f3 for the foraging path: search efficiency and relative relocation time reduced on the device against
+    the reference's offline definitions (data_loader.py :1294-1353, :1903-1928) applied with numpy to the per-step
+    `mode` / `collresource` arrays the reference would have logged (fetched from the engine after every step)."""
+    from abm_b200 import BaseEngine
+    B, N, P, W, T = 6, 12, 3, 500.0, 120
+    rng = np.random.default_rng(5)
+    eng = BaseEngine(B, N, P, resolution=1200, width=W, height=W, visual_exclusion=True, collide_agents=True,
+                     patch_radius=30.0, min_resc_perpatch=20, max_resc_perpatch=30, min_resc_quality=0.25, seed=7)
+    eng.set_params(Eps_w=2.0, Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5,
+                   reloc_theta_max=1.8, exp_stop_ratio=0.175)
+    eng.set_agents(x=rng.integers(20, 520, (B, N)), y=rng.integers(20, 520, (B, N)),
+                   theta=rng.uniform(0, 2 * np.pi, (B, N)))
+    eng.set_patches(x=rng.integers(40, 440, (B, P)), y=rng.integers(40, 440, (B, P)), radius=np.full((B, P), 30.0),
+                    left=np.full((B, P), 25.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
+    mode = np.empty((B, N, T), np.int32)
+    coll = np.empty((B, N, T), np.float64)
+    for t in range(T):
+        eng.step(1)
+        a = eng.get_agents()
+        mode[..., t] = a["mode"]; coll[..., t] = a["collected"]
+    m = eng.metrics()
+    eff = coll[..., -1] / T                                                       # collres / dT with t_start = 0
+    np.testing.assert_allclose(m["search_efficiency"], eff.mean(axis=1), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(m["mean_collected"], coll[..., -1].mean(axis=1), rtol=1e-5, atol=1e-7)
+    for code, key in ((2, "relocation_time"), (0, "explore_time"), (1, "exploit_time"), (3, "collide_time")):
+        ref = (mode == code).astype(int).mean(axis=2).mean(axis=1)                # mean over time, then over agents
+        np.testing.assert_allclose(m[key], ref, rtol=1e-6, atol=1e-7)
+    assert m["relocation_time"].max() > 0 and m["exploit_time"].max() > 0
+    # a new time window: the mode fractions start again, collected_r keeps counting
+    eng.metrics(reset=True)
+    eng.step(10)
+    m2 = eng.metrics()
+    a = eng.get_agents()
+    np.testing.assert_allclose(m2["search_efficiency"], a["collected"].mean(axis=1) / 10, rtol=1e-5, atol=1e-7)
+    s = m2["relocation_time"] + m2["explore_time"] + m2["exploit_time"] + m2["collide_time"]
+    np.testing.assert_allclose(s, 1.0, rtol=1e-6)
+    eng.close()
+
+
 @pytest.mark.parametrize("ghost,teleport,vis_excl", [(True, False, False), (False, False, True), (True, True, True)])
 def test_collision_phase_matches_oracle(built_lib, ghost, teleport, vis_excl):
     """Agent-agent collision avoidance (sims.py:736-783, 421-468) against the oracle restatement
