@@ -486,7 +486,29 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.sym_radius = e->r_max;
   const bool sym_ok = !(force && (strcmp(force, "onesided") == 0 || strcmp(force, "warp") == 0)) &&
                       abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
-  const bool adaptive = sym_ok && !force;
+  // Small batches cannot fill the GPU with one CTA per replicate (or per tile of 256 focal agents): a warp per focal
+  // agent spreads them over all SMs.  Cost models fitted to B200 measurements at R = 1200 (scratch/c2_probe.py), in
+  // microseconds: warp kernel 10 + 1.2e-3 agents + 4.0e-6 ordered pairs; symmetric kernel 45 + 0.05 Np + 1.6e-4 Np^2
+  // per wave of resident CTAs; one-sided kernel 45 + 0.2 N per wave.  E.g. one run of 100 agents: 12 us instead of 54
+  // per step; 16 x 1024: 97 instead of 270; from 48 x 1024 or 256 x 256 upwards the symmetric kernel wins.
+  bool small_grid = false;
+  if (!force && e->tile_count == e->cfg.n_agents) {
+    const double agents = (double)a.B * a.N, pairs = agents * (a.N - 1);
+    const double t_warp = 10.0 + 1.2e-3 * agents + 4.0e-6 * pairs;
+    double t_cta;
+    if (sym_ok) {
+      const int Np = (a.N + 63) / 64 * 64;
+      const size_t smem = abm::vf_sym_smem_bytes(Np, a.W);
+      const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
+      const double waves = std::ceil((double)a.B / ((double)e->n_sms * resident));
+      t_cta = waves * (45.0 + 0.05 * Np + 1.6e-4 * (double)Np * Np);
+    } else {
+      const double ctas = (double)a.B * ((a.N + 255) / 256);
+      t_cta = std::ceil(ctas / (3.0 * e->n_sms)) * (45.0 + 0.2 * a.N);
+    }
+    small_grid = t_warp < 0.9 * t_cta;
+  }
+  const bool adaptive = sym_ok && !force && !small_grid;
   if (adaptive && !e->slow_host) {
     ABM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->slow_host), sizeof(unsigned long long)));
     ABM_CUDA(cudaEventCreateWithFlags(&e->slow_event, cudaEventDisableTiming));
@@ -504,9 +526,9 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       const double pairs = 0.5 * (double)a.B * (double)a.N * (double)(a.N - 1);   // unordered; one queue entry each
       if (n_launch && (double)entries > 0.095 * pairs * (double)n_launch) e->onesided_steps_left = 64;   // crowded
     }
-    bool use_sym = sym_ok;
+    bool use_sym = sym_ok && !small_grid;
     if (adaptive && e->onesided_steps_left > 0) { use_sym = false; --e->onesided_steps_left; }
-    if (e->sort_enabled && !use_sym && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
+    if (e->sort_enabled && !use_sym && !(small_grid && !cull) && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
                                                            e->steps_since_sort >= e->cfg.resort_every))) {
       int rc = resort_engine(e, st);
       if (rc) return rc;
@@ -524,7 +546,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.xflags = e->xflags.p;
     // one large sparse swarm (distance culling on) or an agent tile of it: a warp per focal agent
     const bool use_warp = !use_sym && ((force && strcmp(force, "warp") == 0) ||
-                                       (!(force && strcmp(force, "onesided") == 0) && (cull || tiled)));
+                                       (!(force && strcmp(force, "onesided") == 0) && (cull || tiled || small_grid)));
     if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
       const int tile = (use_warp && (a.N + abm::kWarpTile - 1) / abm::kWarpTile <= abm::kMaxTileList) ? abm::kWarpTile
                                                                                                     : abm::kRecTile;

@@ -99,6 +99,7 @@ constexpr int kMaxTileList = 1024;   // tiles per replicate the culling list can
                                      // N <= 131072 at 128)
 size_t vf_step_smem_bytes(int threads, int W);
 // symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
+size_t vf_sym_smem_bytes(int Np, int W);
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
 void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
 int vf_step_threads(int tile_count, int n_replicates, int n_sms);

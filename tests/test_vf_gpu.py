@@ -394,7 +394,7 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
     from abm_b200 import VFEngine
     monkeypatch.delenv("ABM_VF_KERNEL", raising=False)
     rng = np.random.default_rng(11)
-    B, N, W = 8, 256, 900.0
+    B, N, W = 160, 256, 900.0          # (a batch large enough for one CTA per replicate to fill the GPU, see below)
     res = {}
     for name, spread in (("crowded", 60.0), ("sparse", 420.0)):
         ang = rng.uniform(0, 2 * np.pi, (B, N)); rr = np.sqrt(rng.uniform(0, 1, (B, N))) * spread
@@ -422,6 +422,14 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
         monkeypatch.delenv("ABM_VF_KERNEL")
     assert res["crowded"][0] > 0.095 and "abm::vf_step_kernel" in res["crowded"][1]
     assert res["sparse"][0] < 0.095 and set(res["sparse"][1]) == {"abm::vf_step_sym_kernel"}
+    # a batch that cannot fill the GPU with one CTA per replicate runs with a warp per focal agent -- same results
+    small = VFEngine(2, N, resolution=1200, width=W, height=W, keep_fields=True)
+    small.set_params(); small.set_state(x[:2], y[:2], th[:2], v[:2], 10.0); small.step(5)
+    assert small.last_kernel() == "abm::vf_step_warp_kernel"
+    assert np.array_equal(small.fields_packed(), res["sparse"][2][:2])
+    for k in ("x", "y", "theta", "vel"):
+        np.testing.assert_allclose(small.get_state()[k], res["sparse"][3][k][:2], rtol=1e-6, atol=1e-6)
+    small.close()
 
 
 @pytest.mark.parametrize("boundary", ["walls", "infinite"])
