@@ -323,57 +323,62 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
 }
 
 // ---------------------------------------------------------------------------------------
-// collision phase (sims.py:736-783, 421-468): one warp per replicate, sequential over the
-// colliding (a1, a2) pairs in group order -- an agent that collides with several others is
-// turned once per partner, each time from its already-turned heading.  PARITY UNPINNED for the
+// collision phase (sims.py:736-783, 421-468): the colliding (a1, a2) pairs in group order -- an
+// agent that collides with several others is turned once per partner, each time from its
+// already-turned heading.  PARITY UNPINNED for the
 // pair detection (pygame.sprite.collide_circle on int-truncated rect centres, not in the
 // reference tree); the proximity field itself is Agent.projection_field (agent.py:457-597).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArgs a) {
+// Mapping: one CTA per replicate, its warps take the HIT agents a2 = warp, warp + warps, ...  The reference walks the
+// ordered pairs (a1, a2) sequentially, but everything an event (a1, a2) reads besides a2's own heading is fixed during
+// the phase -- positions do not move, and the only override mode that is tested, "exploit", is neither set nor cleared
+// here -- so the events of different a2 are independent and only those of the same a2 (its heading turns with every
+// hit) have to stay in a1 order.  `collided_agents` is a set: the warps mark its members with plain stores.
+__global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const size_t per_warp = warp_field_bytes(a.N, a.W) + 6 * sizeof(int) * (size_t)a.N;
-  unsigned char* base = smem_raw + per_warp * wib;
-  WarpField wf = warp_field_at(base, a.N);
-  int* ov = reinterpret_cast<int*>(base + warp_field_bytes(a.N, a.W));   // override_mode, mutable
-  int* md = ov + a.N;                                                    // mode
-  float* th = reinterpret_cast<float*>(md + a.N);                        // heading
-  int* col = reinterpret_cast<int*>(th + a.N);                           // member of collided_agents
-  float* px = reinterpret_cast<float*>(col + a.N);                       // positions (this phase does not move anybody):
-  float* py = px + a.N;                                                  // staged once, the loops below are latency-bound
-  const int b = blockIdx.x * wpb + wib;
-  if (b >= a.B) return;
+  const int N = a.N, R = a.R, W = a.W, h = R / 2;
+  const size_t per_warp = warp_field_bytes(N, W);
+  WarpField wf = warp_field_at(smem_raw + per_warp * wib, N);
+  int* ov = reinterpret_cast<int*>(smem_raw + per_warp * wpb);          // override_mode (entry a2: its warp's)
+  int* md = ov + N;                                                      // mode
+  float* th = reinterpret_cast<float*>(md + N);                          // heading
+  int* col = reinterpret_cast<int*>(th + N);                             // member of collided_agents
+  float* px = reinterpret_cast<float*>(col + N);                         // positions (this phase does not move anybody)
+  float* py = px + N;
+  const int b = blockIdx.x;
   const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
-  const size_t a0 = (size_t)b * a.N;
-  const int N = a.N, R = a.R, W = a.W, h = R / 2;
+  const size_t a0 = (size_t)b * N;
   const double r = a.radius;
-  for (int i = lane; i < N; i += 32) {
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
     ov[i] = a.ag.override_mode[a0 + i]; md[i] = a.ag.mode[a0 + i]; th[i] = a.ag.theta[a0 + i]; col[i] = 0;
     px[i] = a.ag.x[a0 + i]; py[i] = a.ag.y[a0 + i];
   }
-  __syncwarp();
+  __syncthreads();
   const float lim2 = (float)((2.0 * (r + 2.0)) * (2.0 * (r + 2.0)));     // (r1 + 2 + r2 + 2)^2, sims.py:739-752
 
-  for (int a1 = 0; a1 < N; ++a1) {
-    const float x1 = truncf(px[a1]), y1 = truncf(py[a1]);                     // rect.x = int(position) (agent.py:303-304)
+  for (int a2 = wib; a2 < N; a2 += wpb) {
+    const float tx2 = truncf(px[a2]), ty2 = truncf(py[a2]);               // rect.x = int(position) (agent.py:303-304)
+    const bool expl2 = ov[a2] == OV_EXPLOIT;                               // (fixed during the phase)
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int jj = j0 + lane;
       bool hit = false;
-      if (jj < N && jj != a1) {
-        const float dx = truncf(px[jj]) - x1, dy = truncf(py[jj]) - y1;
+      if (jj < N && jj != a2) {
+        const float dx = truncf(px[jj]) - tx2, dy = truncf(py[jj]) - ty2;
         hit = dx * dx + dy * dy <= lim2;
       }
       unsigned hits = __ballot_sync(0xffffffffu, hit);
-      while (hits) {
-        const int a2 = j0 + __ffs(hits) - 1;
+      while (hits) {                                                       // the agents a1 that hit a2, in group order
+        const int a1 = j0 + __ffs(hits) - 1;
         hits &= hits - 1;
+        const bool expl1 = ov[a1] == OV_EXPLOIT;
         // ---- agent_agent_collision_proximity(a1, a2) (sims.py:421-468) ----
         bool do_coll = true;
-        if (a.ghost_mode) do_coll = (ov[a2] != OV_EXPLOIT) && (ov[a1] != OV_EXPLOIT);
+        if (a.ghost_mode) do_coll = !expl2 && !expl1;
         if (do_coll) {
           __syncwarp();
-          if (lane == 0 && ov[a2] != OV_EXPLOIT) { ov[a2] = OV_COLLIDE; md[a2] = MODE_COLLIDE; }   // :442-443
+          if (lane == 0 && !expl2) { ov[a2] = OV_COLLIDE; md[a2] = MODE_COLLIDE; }   // :442-443
           for (int w = lane; w < W + 1; w += 32) wf.row[w] = 0u;
           const float x2 = px[a2], y2 = py[a2];
           const FocalExact fe = vf_focal_exact(x2, y2, (float)r, th[a2]);
@@ -413,25 +418,24 @@ __global__ void __launch_bounds__(128) base_collision_kernel(const BaseKernelArg
             const double left = amp * (double)n_left / (double)h, right = amp * (double)n_right / (double)(R - h);
             double D = (left > right) ? 1.0 : ((left < right) ? -1.0 : 0.0);
             if (D == 0.0) D = -1.0;                                                  // :456
-            if (ov[a2] != OV_EXPLOIT) th[a2] = (float)((double)th[a2] - D * 0.2);   // :458-459 (not wrapped)
+            if (!expl2) th[a2] = (float)((double)th[a2] - D * 0.2);                 // :458-459 (not wrapped)
             if (amp * (double)n_front > 0.0) a.ag.vel[a0 + a2] = 0.0f;              // :462-463
-            else if (ov[a2] != OV_EXPLOIT) a.ag.vel[a0 + a2] = (float)prm.exp_vel_max;
+            else if (!expl2) a.ag.vel[a0 + a2] = (float)prm.exp_vel_max;
           }
           __syncwarp();
         }
         // ---- collided_agents bookkeeping (sims.py:759-776) ----
         if (lane == 0) {
-          const bool e1 = ov[a1] == OV_EXPLOIT, e2 = ov[a2] == OV_EXPLOIT;
-          if (a.teleport_exploit) { if (!e1) col[a1] = 1; if (!e2) col[a2] = 1; }
+          if (a.teleport_exploit) { if (!expl1) col[a1] = 1; if (!expl2) col[a2] = 1; }
           else if (!a.ghost_mode) { col[a1] = 1; col[a2] = 1; }
-          else if (!e1 && !e2) { col[a1] = 1; col[a2] = 1; }
+          else if (!expl1 && !expl2) { col[a1] = 1; col[a2] = 1; }
         }
         __syncwarp();
       }
     }
   }
-  __syncwarp();
-  for (int i = lane; i < N; i += 32) {                                              // sims.py:778-783
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {                               // sims.py:778-783
     const size_t g = a0 + i;
     if (!col[i] && ov[i] == OV_COLLIDE) { ov[i] = OV_NONE; md[i] = MODE_EXPLORE; }
     if (col[i] && ov[i] == OV_COLLIDE) notify(a.ag, g, -1, -1, tau_mask);
@@ -444,16 +448,16 @@ void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
   cudaGetDevice(&dev);
   int smem_max = 48 * 1024;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t per_warp = warp_field_bytes(a.N, a.W) + 6 * sizeof(int) * (size_t)a.N;
-  int warps = 4;
-  while (warps > 1 && per_warp * warps > (size_t)smem_max) warps >>= 1;
-  const size_t smem = per_warp * warps;
+  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 6 * sizeof(int) * (size_t)a.N;
+  int warps = 16;
+  while (warps > 1 && (warps / 2 >= a.N || per_warp * warps + shared > (size_t)smem_max)) warps >>= 1;
+  const size_t smem = per_warp * warps + shared;
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(base_collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  base_collision_kernel<<<(a.B + warps - 1) / warps, warps * 32, smem, stream>>>(a);
+  base_collision_kernel<<<a.B, warps * 32, smem, stream>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------
