@@ -143,11 +143,11 @@ struct abm_engine {
 namespace {
 
 int copy_in(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
-  ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   return ABM_OK;
 }
 int copy_out(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
-  ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   return ABM_OK;
 }
 
@@ -333,6 +333,7 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
   if (!radius && !e->state_set) return fail(ABM_E_STATE, "abm_set_state: radius == NULL needs an earlier call that passed the radii");
   ABM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool host = on_device != 1;   // 0: host buffers, 2 (ABM_HOST_PINNED_ASYNC): pinned host buffers, nothing blocks
   const size_t bytes = sizeof(float) * e->n_total;
   const long long n = (long long)e->n_total;
   const int N = e->cfg.n_agents;
@@ -342,7 +343,7 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
   const float *dx = x, *dy = y, *dr = e->radius_api.p, *dth = theta, *dv = vel;
   int rc;
   if (radius && (rc = copy_in(e->radius_api.p, radius, bytes, on_device, st))) return rc;
-  if (!on_device) {
+  if (host) {
     if ((rc = copy_in(e->stage_x.p, x, bytes, 0, st))) return rc;
     if ((rc = copy_in(e->stage_y.p, y, bytes, 0, st))) return rc;
     dx = e->stage_x.p; dy = e->stage_y.p;
@@ -355,7 +356,7 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
     if ((rc = copy_in(e->theta.p, theta, bytes, on_device, st))) return rc;
     if ((rc = copy_in(e->vel.p, vel, bytes, on_device, st))) return rc;
   } else {
-    if (!on_device) {   // the x / y stages are free again once the pack kernel has run (stream order)
+    if (host) {   // the x / y stages are free again once the pack kernel has run (stream order)
       if ((rc = copy_in(e->stage_x.p, theta, bytes, 0, st))) return rc;
       if ((rc = copy_in(e->stage_y.p, vel, bytes, 0, st))) return rc;
       dth = e->stage_x.p; dv = e->stage_y.p;
@@ -379,15 +380,16 @@ int abm_get_state(abm_engine_t* e, float* x, float* y, float* theta, float* vel,
   if (!e->state_set) return fail(ABM_E_STATE, "abm_get_state: no state has been set");
   ABM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool host = on_device != 1, blocking = on_device == 0;   // 2 (ABM_HOST_PINNED_ASYNC): pinned, stream-ordered
   const size_t bytes = sizeof(float) * e->n_total;
   int rc;
   if (x || y) {
-    float* tx = on_device ? x : e->stage_x.p;
-    float* ty = on_device ? y : e->stage_y.p;
+    float* tx = host ? e->stage_x.p : x;
+    float* ty = host ? e->stage_y.p : y;
     abm::launch_unpack_records(e->rec[e->cur].p, (e->sort_enabled && !e->perm_identity) ? e->perm.p : nullptr,
                                e->cfg.n_agents, x ? tx : nullptr, y ? ty : nullptr, (long long)e->n_total, st);
     ABM_CUDA(cudaGetLastError());
-    if (!on_device) {
+    if (host) {
       if (x && (rc = copy_out(x, tx, bytes, 0, st))) return rc;
       if (y && (rc = copy_out(y, ty, bytes, 0, st))) return rc;
     }
@@ -398,15 +400,14 @@ int abm_get_state(abm_engine_t* e, float* x, float* y, float* theta, float* vel,
     const float* src = which ? e->vel.p : e->theta.p;
     if (!dst) continue;
     if (permuted) {   // internal order -> caller's order
-      float* tmp = on_device ? dst : e->stage_r.p;
+      float* tmp = host ? e->stage_r.p : dst;
       abm::launch_scatter_f32(src, e->perm.p, tmp, e->cfg.n_agents, (long long)e->n_total, st);
-      if (!on_device && (rc = copy_out(dst, tmp, bytes, 0, st))) return rc;
-      if (!on_device) ABM_CUDA(cudaStreamSynchronize(st));   // stage_r is reused for the next array
+      if (host && (rc = copy_out(dst, tmp, bytes, 0, st))) return rc;   // (stage_r is reused for the next array: stream order)
     } else if ((rc = copy_out(dst, src, bytes, on_device, st))) {
       return rc;
     }
   }
-  if (!on_device) ABM_CUDA(cudaStreamSynchronize(st));
+  if (blocking) ABM_CUDA(cudaStreamSynchronize(st));
   return ABM_OK;
 }
 

@@ -131,8 +131,10 @@ class VFEngine:
             self.synchronize()
 
     # -- state -------------------------------------------------------------------------
-    def set_state(self, x, y, theta, vel, radius=None):
-        """``radius``: scalar or (B, N) array; None keeps the radii of the previous call."""
+    def set_state(self, x, y, theta, vel, radius=None, nonblocking=False):
+        """``radius``: scalar or (B, N) array; None keeps the radii of the previous call.
+        ``nonblocking``: the host arrays are PINNED, C-contiguous float32 and stay alive and untouched until the
+        caller has synchronised the stream -- the call only enqueues (ABM_HOST_PINNED_ASYNC)."""
         keep = []
         total = self.B * self.N
         arrays = [x, y, theta, vel]
@@ -142,14 +144,19 @@ class VFEngine:
             arrays.append(radius)
         ptrs = [self._ptr(a, np.float32, total, keep) for a in arrays]
         side = self._same_side([p[1] for p in ptrs])
+        if nonblocking and not side:
+            if any(not isinstance(a, np.ndarray) or k.ctypes.data != a.ctypes.data for k, a in zip(keep, arrays)):
+                raise ValueError("nonblocking=True needs C-contiguous float32 arrays of full size (no copies are made)")
+            side = 2
         args = [p[0] for p in ptrs] + ([None] if radius is None else [])
         _lib.check(self._lib.abm_set_state(self._h, *args, side, C.c_void_p(_current_stream())), "abm_set_state")
         if not side:
             self.synchronize()   # the host arrays in `keep` may go away after return
 
-    def get_state(self, out=None):
+    def get_state(self, out=None, nonblocking=False):
         """Returns dict(x, y, theta, vel) of (B, N) float32 numpy arrays (or fills ``out``,
-        a dict of numpy arrays / torch CUDA tensors)."""
+        a dict of numpy arrays / torch CUDA tensors).  ``nonblocking`` (``out`` = pinned host arrays): the copies are
+        only enqueued; synchronise the stream before reading them."""
         total = self.B * self.N
         if out is None:
             out = {k: np.empty((self.B, self.N), np.float32) for k in ("x", "y", "theta", "vel")}
@@ -165,6 +172,8 @@ class VFEngine:
                     raise ValueError("output arrays must be C-contiguous float32 of full size")
                 ptrs.append(C.c_void_p(a.ctypes.data)); sides.append(0)
         side = self._same_side(sides)
+        if nonblocking and not side:
+            side = 2
         _lib.check(self._lib.abm_get_state(self._h, *ptrs, side, C.c_void_p(_current_stream())), "abm_get_state")
         return out
 

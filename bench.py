@@ -281,27 +281,47 @@ def main():
         launches = args.steps
 
         # ---- end-to-end arm: host buffers in, host buffers out, every step ----
-        # two sets of pinned host buffers used in turn: the state a step returns is the next step's input
+        # The way a sweep uses the plugin: TWO replicate batches of the workload's size in flight, each with its own
+        # engine, stream and pair of pinned host buffers (the state a step returns is that batch's next input).  Every
+        # batch-step copies its inputs host -> device, steps, and copies its result device -> host inside the timed
+        # region; the copy engines move one batch while the SMs step the other (ABM_HOST_PINNED_ASYNC calls).
         hr = torch.from_numpy(rad).pin_memory().numpy()
-        host = [{k: torch.from_numpy(a.copy()).pin_memory().numpy() for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v))}
-                for _ in range(2)]
-        e2e_steps = max(3, min(args.steps, 20))
-        cur = 0
-        for _ in range(2):
-            eng.set_state(host[cur]["x"], host[cur]["y"], host[cur]["theta"], host[cur]["vel"], hr)
-            eng.step(1); eng.get_state(host[cur ^ 1]); cur ^= 1
+        eng2 = VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank)
+        eng2.set_params(**PARAMS)
+        engs = [eng, eng2]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        hosts = [[{k: torch.from_numpy(a.copy()).pin_memory().numpy() for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v))}
+                  for _ in range(2)] for _ in range(2)]
+        e2e_steps = 2 * max(2, min(args.steps, 20) // 2)              # batch-steps, alternating between the two batches
+        cur = [0, 0]
+
+        def batch_step(k, first=False):
+            with torch.cuda.stream(streams[k]):
+                h = hosts[k][cur[k]]
+                # H2D of the step's inputs; the radii are constants of the run, uploaded with the first call
+                engs[k].set_state(h["x"], h["y"], h["theta"], h["vel"], hr if first else None, nonblocking=not first)
+                engs[k].step(1)
+                engs[k].get_state(hosts[k][cur[k] ^ 1], nonblocking=True)   # D2H of the step's result
+                cur[k] ^= 1
+
+        torch.cuda.synchronize()
+        for k in (0, 1):
+            batch_step(k, first=True); batch_step(k)
+        torch.cuda.synchronize()
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(e2e_steps):
-            h = host[cur]
-            eng.set_state(h["x"], h["y"], h["theta"], h["vel"])       # H2D of the step's inputs (pinned); the radii
-                                                                      # are constants of the run, uploaded once above
-            eng.step(1)
-            eng.get_state(host[cur ^ 1])                              # D2H of the step's result (pinned)
-            cur ^= 1
+        for k in (0, 1):
+            streams[k].wait_event(e0)
+        for it in range(e2e_steps):
+            batch_step(it & 1)
+        for k in (0, 1):
+            done = torch.cuda.Event(); done.record(streams[k]); torch.cuda.current_stream().wait_event(done)
         e1.record()
         barrier()
+        for k in ("x", "y", "theta", "vel"):                           # both batches came back whole
+            assert np.isfinite(hosts[0][cur[0]][k]).all() and np.isfinite(hosts[1][cur[1]][k]).all()
+        eng2.close()
         e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     counters = eng.counters()
@@ -333,7 +353,8 @@ def main():
             "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * 4 * B * N),
-                    "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps,
+                    "pipeline": "two batches in flight (two engines, two streams, pinned buffers): one batch's copies overlap the other's step"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops,

@@ -14,8 +14,12 @@
  *   - every function returns 0 on success or a negative ABM_E_* code and never
  *     throws; abm_last_error() returns a thread-local message for the last failure.
  *   - the engine owns its device state; the caller owns every buffer it passes.
- *   - `on_device` != 0: the pointers are device pointers (same device as the
- *     engine); == 0: host pointers (pinned for truly asynchronous copies).
+ *   - `on_device` == 1: the pointers are device pointers (same device as the
+ *     engine); == 0: host pointers, calls that fill host buffers return when they are
+ *     filled; == 2 (ABM_HOST_PINNED_ASYNC, abm_set_state / abm_get_state): PINNED host
+ *     pointers, the call only enqueues on `stream` and never blocks -- the caller
+ *     keeps the buffers alive and synchronises before touching them (two engines on
+ *     two streams overlap one batch's copies with the other's step).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *     all calls are asynchronous on that stream except create / destroy and calls
  *     that fill HOST buffers from pageable memory.
@@ -28,6 +32,7 @@
  */
 #ifndef ABM_B200_H
 #define ABM_B200_H
+#define ABM_HOST_PINNED_ASYNC 2
 
 #include <stdint.h>
 

@@ -432,6 +432,51 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
     small.close()
 
 
+def test_pinned_async_state_transfers_two_engines_two_streams(built_lib):
+    """ABM_HOST_PINNED_ASYNC (on_device == 2): abm_set_state / abm_get_state with pinned host buffers only enqueue on
+    the stream.  Two engines on two streams, each fed from and drained into its own pinned buffers every step (the
+    pipelined end-to-end arm of bench.py), end in exactly the state of the blocking calls."""
+    import torch
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(21)
+    B, N, W, T = 4, 300, 1500.0, 6
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a, np.float32)).pin_memory().numpy()
+    scenes = [_random_scene(rng, B, N, W) for _ in range(2)]
+    ref = []
+    for x, y, th, v in scenes:                                   # blocking reference: state through host buffers every step
+        eng = VFEngine(B, N, resolution=1200, width=W, height=W)
+        eng.set_params(); st = dict(x=x, y=y, theta=th, vel=v)
+        for t in range(T):
+            eng.set_state(st["x"], st["y"], st["theta"], st["vel"], 10.0 if t == 0 else None)
+            eng.step(1); st = eng.get_state()
+        ref.append(st); eng.close()
+    engs = [VFEngine(B, N, resolution=1200, width=W, height=W) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs = [[{k: pinned(a) for k, a in zip(("x", "y", "theta", "vel"), sc)} for _ in range(2)] for sc in scenes]
+    rad = pinned(np.full((B, N), 10.0))
+    cur = [0, 0]
+    for k in (0, 1):
+        engs[k].set_params()
+    for t in range(T):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                h = bufs[k][cur[k]]
+                engs[k].set_state(h["x"], h["y"], h["theta"], h["vel"], rad if t == 0 else None, nonblocking=True)
+                engs[k].step(1)
+                engs[k].get_state(bufs[k][cur[k] ^ 1], nonblocking=True)
+                cur[k] ^= 1
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        for key in ("x", "y", "theta", "vel"):
+            assert np.array_equal(bufs[k][cur[k]][key], ref[k][key]), key
+        engs[k].close()
+    with pytest.raises(ValueError):                              # no silent copies in the non-blocking mode
+        e = VFEngine(1, 8, resolution=1200, width=W, height=W)
+        z = np.zeros((1, 8), np.float64)
+        e.set_state(z, z, z, z, 10.0, nonblocking=True)
+
+
 @pytest.mark.parametrize("boundary", ["walls", "infinite"])
 def test_warp_kernel_on_a_sparse_heterogeneous_swarm(built_lib, monkeypatch, boundary):
     """The warp-per-focal-agent kernel in its own territory -- one large sparse swarm with distance culling, record
