@@ -281,19 +281,21 @@ def main():
         launches = args.steps
 
         # ---- end-to-end arm: host buffers in, host buffers out, every step ----
-        # The way a sweep uses the plugin: TWO replicate batches of the workload's size in flight, each with its own
+        # The way a sweep uses the plugin: THREE replicate batches of the workload's size in flight, each with its own
         # engine, stream and pair of pinned host buffers (the state a step returns is that batch's next input).  Every
         # batch-step copies its inputs host -> device, steps, and copies its result device -> host inside the timed
-        # region; the copy engines move one batch while the SMs step the other (ABM_HOST_PINNED_ASYNC calls).
+        # region; the copy engines move two batches while the SMs step the third (ABM_HOST_PINNED_ASYNC calls).
         hr = torch.from_numpy(rad).pin_memory().numpy()
-        eng2 = VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank)
-        eng2.set_params(**PARAMS)
-        engs = [eng, eng2]
-        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        NB = int(os.environ.get('ABM_E2E_BATCHES', '3'))   # measured: 1 -> 4.0e8, 2 -> 4.8e8, 3 -> 5.2e8, 4 -> 5.2e8 agent-steps/s
+        extra = [VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank) for _ in range(NB - 1)]
+        for e_ in extra:
+            e_.set_params(**PARAMS)
+        engs = [eng] + extra
+        streams = [torch.cuda.Stream() for _ in range(NB)]
         hosts = [[{k: torch.from_numpy(a.copy()).pin_memory().numpy() for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v))}
-                  for _ in range(2)] for _ in range(2)]
-        e2e_steps = 2 * max(2, min(args.steps, 20) // 2)              # batch-steps, alternating between the two batches
-        cur = [0, 0]
+                  for _ in range(2)] for _ in range(NB)]
+        e2e_steps = NB * max(2, min(args.steps, 20) // NB)            # batch-steps, round robin over the batches
+        cur = [0] * NB
 
         def batch_step(k, first=False):
             with torch.cuda.stream(streams[k]):
@@ -305,23 +307,24 @@ def main():
                 cur[k] ^= 1
 
         torch.cuda.synchronize()
-        for k in (0, 1):
+        for k in range(NB):
             batch_step(k, first=True); batch_step(k)
         torch.cuda.synchronize()
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        for k in (0, 1):
+        for k in range(NB):
             streams[k].wait_event(e0)
         for it in range(e2e_steps):
-            batch_step(it & 1)
-        for k in (0, 1):
+            batch_step(it % NB)
+        for k in range(NB):
             done = torch.cuda.Event(); done.record(streams[k]); torch.cuda.current_stream().wait_event(done)
         e1.record()
         barrier()
         for k in ("x", "y", "theta", "vel"):                           # both batches came back whole
-            assert np.isfinite(hosts[0][cur[0]][k]).all() and np.isfinite(hosts[1][cur[1]][k]).all()
-        eng2.close()
+            assert all(np.isfinite(hosts[j][cur[j]][k]).all() for j in range(NB))
+        for e_ in extra:
+            e_.close()
         e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     counters = eng.counters()
@@ -354,7 +357,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * 4 * B * N),
                     "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps,
-                    "pipeline": "two batches in flight (two engines, two streams, pinned buffers): one batch's copies overlap the other's step"},
+                    "pipeline": "%d batches in flight (one engine, stream and pair of pinned buffers each): copies overlap the other batches' steps" % NB},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops,
