@@ -229,6 +229,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # NCCL prints its version banner on STDOUT, where the
+            os.environ["NCCL_DEBUG"] = "WARN"                        # one JSON line goes; any other setting is left alone
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import __graft_entry__ as g
