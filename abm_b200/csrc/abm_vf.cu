@@ -196,8 +196,9 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
           dx = (o.x - me.x) + dr; dy = (o.y - me.y) + dr;
         }
         if (TORUS) {                                         // vf_supcalc.py:70-83
-          if (fabsf(dx) > half_w) dx -= copysignf(width, dx);
-          if (fabsf(dy) > half_h) dy -= copysignf(height, dy);
+          const float dr = UNIFORM_R ? 0.0f : o.z - me.z;
+          dx = torus_delta_r(o.x, me.x, dr, width, half_w);
+          dy = torus_delta_r(o.y, me.y, dr, height, half_h);
         }
         const float d2 = fmaf(dx, dx, dy * dy);
         if (CULL) { if (d2 > o.w) continue; }                // o.w: beyond it the half width is 0
@@ -365,8 +366,8 @@ __global__ void vf_projection_kernel(const VFProjArgs a) {
     const float dr = orad - a.fr;
     float dx = (ox - a.fx) + dr, dy = (oy - a.fy) + dr;
     if (a.boundary == 1) {
-      if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
-      if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+      dx = torus_delta_r(ox, a.fx, dr, a.width, a.half_w);
+      dy = torus_delta_r(oy, a.fy, dr, a.height, a.half_h);
     }
     const float d2 = fmaf(dx, dx, dy * dy);
     bool in_range = true;

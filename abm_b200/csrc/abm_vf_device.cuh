@@ -186,6 +186,27 @@ constexpr int kMagicBits = 0x4B400000;
 constexpr uint32_t kQuarter = 1u << 23, kHalf = 1u << 24;      // in units of 2^-25 turn
 constexpr uint32_t kMB2 = 2u * (uint32_t)kMagicBits;
 
+// Minimal-image difference o - f on a periodic axis (vf_supcalc.py:70-83), rounded ONCE at the magnitude of the result.
+// fl(o - f) of two coordinates far apart carries a rounding error of ulp(period) / 2; after the wrap that is a relative
+// error without bound for a close neighbour across the seam (found by scratch/soak_compare.py: 2 wrong bins in 1e11
+// directions).  So the period goes first to whichever coordinate it makes SMALLER -- that subtraction is exact --
+// and the difference is taken afterwards.
+__device__ __forceinline__ float torus_delta(float o, float f, float period, float half) {
+  const float d0 = o - f;
+  float d = d0;
+  if (d0 > half) d = (o - period) - f;
+  if (d0 < -half) d = o - (f - period);
+  return d;
+}
+// the same for centres = positions + radii (dr = object radius - focal radius): positions first, then radii
+__device__ __forceinline__ float torus_delta_r(float o, float f, float dr, float period, float half) {
+  const float d0 = (o - f) + dr;
+  float d = d0;
+  if (d0 > half) d = ((o - period) - f) + dr;
+  if (d0 < -half) d = (o - (f - period)) + dr;
+  return d;
+}
+
 // bits of (kMagic + bearing in 2^-25 turns), bearing in (-half turn, half turn]
 __device__ __forceinline__ uint32_t sym_bearing_bits(float dx, float dy, float a6) {
   constexpr double kS = 33554432.0 / ABM_TWO_PI_D;             // 2^25 / 2pi

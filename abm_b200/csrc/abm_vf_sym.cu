@@ -107,8 +107,8 @@ static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_
   if ((ia.x == ja.x) & (ia.y == ja.y)) return;                        // vf_supcalc.py:57
   float dx = ja.x - ia.x, dy = ja.y - ia.y;
   if (TORUS) {
-    if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
-    if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+    dx = torus_delta(ja.x, ia.x, a.width, a.half_w);
+    dy = torus_delta(ja.y, ia.y, a.height, a.half_h);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
   const float q = a.sym_radius * rsqrt_approx(d2);
@@ -251,8 +251,8 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   SymStep r;
   float dx = o.x - xi, dy = o.y - yi;
   if (TORUS) {                                               // vf_supcalc.py:70-83
-    if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
-    if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+    dx = torus_delta(o.x, xi, a.width, a.half_w);
+    dy = torus_delta(o.y, yi, a.height, a.half_h);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
   // ---- half width h = floor(atan(r/d) * R/2pi) (vf_supcalc.py:96-99, :114-117), shared by both directions.

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
         const float dr = o.z - me.z;
         float dx = (o.x - me.x) + dr, dy = (o.y - me.y) + dr;   // positions first (exact for close neighbours), then radii
         if (TORUS) {                                           // vf_supcalc.py:70-83
-          if (fabsf(dx) > a.half_w) dx -= copysignf(a.width, dx);
-          if (fabsf(dy) > a.half_h) dy -= copysignf(a.height, dy);
+          dx = torus_delta_r(o.x, me.x, dr, a.width, a.half_w);
+          dy = torus_delta_r(o.y, me.y, dr, a.height, a.half_h);
         }
         const float d2 = fmaf(dx, dx, dy * dy);
         if (CULL) { if (d2 > o.w) continue; }                  // beyond it the half width is 0

@@ -432,6 +432,29 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
     small.close()
 
 
+@pytest.mark.parametrize("kernel", ["symmetric", "onesided", "warp"])
+def test_torus_neighbour_across_the_seam_near_a_tie(built_lib, monkeypatch, kernel):
+    """Regression (found by scratch/soak_compare.py, 2 wrong bins in 1e11 directions): on the torus the minimal-image
+    difference must be rounded at the magnitude of the RESULT -- fl(x_j - x_i) of coordinates an arena apart carries
+    ulp(arena) / 2, which for a close neighbour across the periodic seam exceeded the fp32 guard band of the bin index.
+    The two scenes (tests/golden/torus_seam_cases.npz, states of the soak run) have such a pair right at a rounding tie."""
+    import os
+    from abm_b200 import VFEngine
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "torus_seam_cases.npz"))
+    W = float(d["W"])
+    monkeypatch.setenv("ABM_VF_KERNEL", kernel)
+    for c in (0, 1):
+        x, y, th, v = (d[f"{k}{c}"][None, :] for k in ("x", "y", "theta", "vel"))
+        i = int(d[f"agent{c}"])
+        eng = VFEngine(1, x.shape[1], resolution=1200, width=W, height=W, boundary="infinite", keep_fields=True)
+        eng.set_params(); eng.set_state(x, y, th, v, 10.0); eng.step(1)
+        cfg = rs.VFConfig(R=1200, width=W, height=W, boundary="infinite")
+        idx = sorted({i, 0, 17, 500})
+        ref = rs.vf_step_frozen(x[0], y[0], th[0], v[0], 10.0, cfg, agents=idx)
+        assert np.array_equal(eng.fields()[0][idx], ref["rows"][idx][:, ::-1])
+        eng.close()
+
+
 def test_pinned_async_state_transfers_two_engines_two_streams(built_lib):
     """ABM_HOST_PINNED_ASYNC (on_device == 2): abm_set_state / abm_get_state with pinned host buffers only enqueue on
     the stream.  Two engines on two streams, each fed from and drained into its own pinned buffers every step (the
