@@ -195,10 +195,11 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
           const float dr = o.z - me.z;
           dx = (o.x - me.x) + dr; dy = (o.y - me.y) + dr;
         }
+        bool wrap_tie = false;
         if (TORUS) {                                         // vf_supcalc.py:70-83
           const float dr = UNIFORM_R ? 0.0f : o.z - me.z;
-          dx = torus_delta_r(o.x, me.x, dr, width, half_w);
-          dy = torus_delta_r(o.y, me.y, dr, height, half_h);
+          dx = torus_delta_r(o.x, me.x, dr, width, half_w, wrap_tie);
+          dy = torus_delta_r(o.y, me.y, dr, height, half_h, wrap_tie);
         }
         const float d2 = fmaf(dx, dx, dy * dy);
         if (CULL) { if (d2 > o.w) continue; }                // o.w: beyond it the half width is 0
@@ -225,7 +226,7 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
         const float tr = tk + MAGIC;                         // rint(tk) in the low mantissa bits
         const int k = __float_as_int(tr) + K::k_bias(a);     // centre bin, padded position
         const float dfk = tk - (tr - MAGIC);
-        bool flagged = (fabsf(dfk) > a.thr_k) | (fabsf(cab) > a.seam_b);
+        bool flagged = (fabsf(dfk) > a.thr_k) | (fabsf(cab) > a.seam_b) | wrap_tie;
         // ---- half width h = floor(atan(r / d) * R / 2pi) (vf_supcalc.py:96-99, :114-117) ----
         const float q = o.z * rsqrt_approx(d2);
         flagged |= !(q <= 1.0f);                             // also d2 == 0 (inf / NaN)
@@ -365,9 +366,10 @@ __global__ void vf_projection_kernel(const VFProjArgs a) {
   if (!same) {
     const float dr = orad - a.fr;
     float dx = (ox - a.fx) + dr, dy = (oy - a.fy) + dr;
+    bool wrap_tie = false;
     if (a.boundary == 1) {
-      dx = torus_delta_r(ox, a.fx, dr, a.width, a.half_w);
-      dy = torus_delta_r(oy, a.fy, dr, a.height, a.half_h);
+      dx = torus_delta_r(ox, a.fx, dr, a.width, a.half_w, wrap_tie);
+      dy = torus_delta_r(oy, a.fy, dr, a.height, a.half_h, wrap_tie);
     }
     const float d2 = fmaf(dx, dx, dy * dy);
     bool in_range = true;
@@ -381,7 +383,7 @@ __global__ void vf_projection_kernel(const VFProjArgs a) {
       const BinConsts bc{a.inv_step, a.t_half, a.k_bias, a.y_scale, a.thr_k, a.thr_h0, a.thr_h1, a.ca_guard};
       const PairFast pf = vf_pair_fast(dx, dy, d2, orad, (float)cd, (float)(-sd), bc);
       int k = pf.k - 32, h = pf.h;
-      if (pf.flagged) {
+      if (pf.flagged | wrap_tie) {
         const FocalExact fe = vf_focal_exact(a.fx, a.fy, a.fr, a.ftheta);
         const PairExact pe = vf_pair_exact(fe, ox, oy, orad, a.boundary, a.width_d, a.height_d, a.R, a.lin_step);
         k = pe.k; h = pe.valid ? pe.h : 0;

@@ -191,16 +191,20 @@ constexpr uint32_t kMB2 = 2u * (uint32_t)kMagicBits;
 // error without bound for a close neighbour across the seam (found by scratch/soak_compare.py: 2 wrong bins in 1e11
 // directions).  So the period goes first to whichever coordinate it makes SMALLER -- that subtraction is exact --
 // and the difference is taken afterwards.
-__device__ __forceinline__ float torus_delta(float o, float f, float period, float half) {
+// `tie`: the wrap decision |difference| > half (taken by the reference on the exact difference) cannot be made from
+// the rounded one (a neighbour exactly half an arena away: 1 wrong pair in 2.5e11) -> fp64 path.
+__device__ __forceinline__ float torus_delta(float o, float f, float period, float half, bool& tie) {
   const float d0 = o - f;
+  tie |= fabsf(fabsf(d0) - half) <= half * 2.4e-7f;
   float d = d0;
   if (d0 > half) d = (o - period) - f;
   if (d0 < -half) d = o - (f - period);
   return d;
 }
 // the same for centres = positions + radii (dr = object radius - focal radius): positions first, then radii
-__device__ __forceinline__ float torus_delta_r(float o, float f, float dr, float period, float half) {
+__device__ __forceinline__ float torus_delta_r(float o, float f, float dr, float period, float half, bool& tie) {
   const float d0 = (o - f) + dr;
+  tie |= fabsf(fabsf(d0) - half) <= half * 2.4e-7f;
   float d = d0;
   if (d0 > half) d = ((o - period) - f) + dr;
   if (d0 < -half) d = (o - (f - period)) + dr;

@@ -106,16 +106,17 @@ static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_
   const float4 ia = lds_f4(ag_s + 16u * (uint32_t)i), ja = lds_f4(ag_s + 16u * (uint32_t)j);
   if ((ia.x == ja.x) & (ia.y == ja.y)) return;                        // vf_supcalc.py:57
   float dx = ja.x - ia.x, dy = ja.y - ia.y;
+  bool wrap_tie = false;
   if (TORUS) {
-    dx = torus_delta(ja.x, ia.x, a.width, a.half_w);
-    dy = torus_delta(ja.y, ia.y, a.height, a.half_h);
+    dx = torus_delta(ja.x, ia.x, a.width, a.half_w, wrap_tie);
+    dy = torus_delta(ja.y, ia.y, a.height, a.half_h, wrap_tie);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
   const float q = a.sym_radius * rsqrt_approx(d2);
   const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
   const float yr = y + kMagic;
   const int h = __float_as_int(yr) - kMagicBits;
-  const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
+  const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
   const uint32_t nb = sym_bearing_bits(dx, dy, kBearingA6);           // bearing of j seen from i
   const uint32_t stride_b = 4u * (uint32_t)Np;
   if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
@@ -250,9 +251,10 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   using K = PairK<RC>;
   SymStep r;
   float dx = o.x - xi, dy = o.y - yi;
+  bool wrap_tie = false;
   if (TORUS) {                                               // vf_supcalc.py:70-83
-    dx = torus_delta(o.x, xi, a.width, a.half_w);
-    dy = torus_delta(o.y, yi, a.height, a.half_h);
+    dx = torus_delta(o.x, xi, a.width, a.half_w, wrap_tie);
+    dy = torus_delta(o.y, yi, a.height, a.half_h, wrap_tie);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
   // ---- half width h = floor(atan(r/d) * R/2pi) (vf_supcalc.py:96-99, :114-117), shared by both directions.
@@ -265,7 +267,7 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   const float y = fmaf(qs, p, -0.5f);
   const float yr = y + kMagic;
   const uint32_t hraw = __float_as_uint(yr);                 // h + kMagicBits
-  const bool slow_h = !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);   // also d2 == 0 (NaN)
+  const bool slow_h = !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h) | wrap_tie;   // also d2 == 0 (NaN)
   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask) : "r"(2u * hraw - 2u * (uint32_t)kMagicBits));   // 2h ones
   const int bh = 32 + kMagicBits - (int)hraw;                // ps = bin index + 32 - h
   // ---- bearing (shared), bin index of both directions ----

@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
         const float4 o = __ldg(rep_in + j);
         const float dr = o.z - me.z;
         float dx = (o.x - me.x) + dr, dy = (o.y - me.y) + dr;   // positions first (exact for close neighbours), then radii
+        bool wrap_tie = false;
         if (TORUS) {                                           // vf_supcalc.py:70-83
-          dx = torus_delta_r(o.x, me.x, dr, a.width, a.half_w);
-          dy = torus_delta_r(o.y, me.y, dr, a.height, a.half_h);
+          dx = torus_delta_r(o.x, me.x, dr, a.width, a.half_w, wrap_tie);
+          dy = torus_delta_r(o.y, me.y, dr, a.height, a.half_h, wrap_tie);
         }
         const float d2 = fmaf(dx, dx, dy * dy);
         if (CULL) { if (d2 > o.w) continue; }                  // beyond it the half width is 0
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
         const float y = fmaf(atan_unit(q), a.y_scale, -0.5f);
         const float yr = y + kMagic;
         int h = __float_as_int(yr) - kMagicBits;
-        bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0);
+        bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
         int k = sym_side_k<0>(a, sym_bearing_bits(dx, dy, kBearingA6), hc, 0, flagged);   // bin index
         if (flagged) {                                         // fp64, the reference's own operation sequence
           const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, R, a.lin_step);

@@ -437,7 +437,9 @@ def test_torus_neighbour_across_the_seam_near_a_tie(built_lib, monkeypatch, kern
     """Regression (found by scratch/soak_compare.py, 2 wrong bins in 1e11 directions): on the torus the minimal-image
     difference must be rounded at the magnitude of the RESULT -- fl(x_j - x_i) of coordinates an arena apart carries
     ulp(arena) / 2, which for a close neighbour across the periodic seam exceeded the fp32 guard band of the bin index.
-    The two scenes (tests/golden/torus_seam_cases.npz, states of the soak run) have such a pair right at a rounding tie."""
+    Second cause, second scene: a neighbour exactly half an arena away in fp32 (|dy| = 1440.00003 in the reference's
+    float64) -- the wrap decision cannot be taken from the rounded difference; such pairs go to the fp64 path.
+    The scenes (tests/golden/torus_seam_cases.npz) are states of the soak run that exposed them."""
     import os
     from abm_b200 import VFEngine
     d = np.load(os.path.join(os.path.dirname(__file__), "golden", "torus_seam_cases.npz"))
