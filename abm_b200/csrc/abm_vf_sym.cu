@@ -8,23 +8,26 @@
 // operations are paid once per unordered pair; what is left per direction is one subtraction, the
 // rounding to a bin with its guard band, and the read-modify-write of one or two row words.
 //
-// Mapping.  CTA = one replicate.  ALL rows of the replicate live in the CTA's shared memory
-// ([word][agent]: bank == agent mod 32; 160 B per agent at R = 1200 -> 1024 agents in 160 KB).
-// The 32-agent blocks are paired by a round-robin tournament: in every round each block belongs
-// to exactly one block pair and each block pair to exactly one warp, so a warp OWNS the rows it
-// writes -- no atomics.  Lane l owns agent l of block I and visits agent (l XOR s) of block J in
-// step s: own-row and partner-row accesses are both bank-conflict free, and the partner's
-// addresses are one LOP3 away from a per-round base.  One __syncthreads per round; the diagonal
-// blocks (pairs inside a block) take one extra round in which every lane draws its own side.
+// Mapping.  CTA = one replicate, 16 warps at N = 1024.  ALL rows of the replicate live in the CTA's shared memory
+// ([word][agent]: bank == agent mod 32; 164 B per agent at R = 1200 -> 1024 agents in 164 KB).  The 32-agent blocks
+// are paired like the rounds of a round-robin tournament (circle method): P (P - 1) / 2 block pairs, dealt to the
+// warps; lane l owns agent l of block I and visits agent (l XOR s) of block J in step s, so own-row and partner-row
+// accesses of a warp instruction hit 32 different banks and the partner's addresses are one LOP3 away from a
+// per-round base.  Draws are shared-memory reductions (red.shared.or runs at the rate of a plain store), so nobody
+// owns a row and the warps never wait for each other between the staging barrier and the epilogue.  The diagonal
+// blocks (pairs inside a block) are evaluated once per unordered pair as well, two blocks per warp.
 //
-// Fast path: intervals of 1..32 bins (1 <= h <= 16) whose bin arithmetic is clear of every fp32
-// guard band are drawn with straight-line code (no divergence inside a step).  Everything else is
-// "slow" (about 1 % of the pairs of the benchmark scene): guard-band hits go to the per-CTA fp64
-// queue (the reference's own operation sequence, abm_vf_device.cuh), wide intervals are drawn by
-// the general rule.  The slow path sits behind one warp-uniform branch per step.
+// Fast path: intervals of 1..32 bins (1 <= h <= 16) whose bin arithmetic is clear of every fp32 guard band are drawn
+// with straight-line code: the inner loop of a round (16 iterations of two unordered pairs per lane) has no branch,
+// vote or call.  Everything else is "slow" (1-2 % of the pairs of the benchmark scene): its draw is redirected to a
+// scratch word and the pair remembered as a flag bit; after the round the flagged pairs are compacted into the warp's
+// queue and worked off 32 at a time by the warp itself -- wide intervals by the general rule, guard-band hits by the
+// fp64 path (the reference's own operation sequence, abm_vf_device.cuh), also per warp and 32 at a time -- while the
+// other warps keep running their pair loops.
 //
-// Used when all radii are equal, no distance culling is wanted, the engine owns whole
-// replicates, and the rows fit in shared memory; otherwise vf_step_kernel (abm_vf.cu) runs.
+// Used when all radii are equal, no distance culling is wanted, the engine owns whole replicates, the rows fit in
+// shared memory and the batch is large enough to fill the GPU with one CTA per replicate; otherwise vf_step_kernel
+// (abm_vf.cu) or vf_step_warp_kernel (abm_vf_warp.cu) runs (abm_api.cu).
 #include "abm_vf_device.cuh"
 
 namespace abm {
