@@ -443,11 +443,23 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
   }
 }
 
-void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
+// opt-in shared memory per block of the current device, asked once per device (the attribute query costs more host time
+// than a launch, and a foraging step is three launches of a few hundred microseconds together)
+static int base_smem_optin() {
+  static int cached[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  int smem_max = 48 * 1024;
-  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cached[dev]) {
+    int v = 48 * 1024;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
+  const int smem_max = base_smem_optin();
   const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 6 * sizeof(int) * (size_t)a.N;
   int warps = 16;
   while (warps > 1 && (warps / 2 >= a.N || per_warp * warps + shared > (size_t)smem_max)) warps >>= 1;
@@ -531,10 +543,7 @@ void launch_vf_dphi(const uint32_t* v, int R, int W, signed char* out, cudaStrea
 }
 
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  int smem_max = 48 * 1024;
-  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int smem_max = base_smem_optin();
   const int warps = base_agents_warps(a.N, a.W, (size_t)smem_max);
   const size_t smem = base_agents_smem_bytes(a.N, a.W, warps);
   static size_t configured = 0;

@@ -96,8 +96,68 @@ __device__ __forceinline__ void base_draw(uint32_t* row, int R, int s, int e) { 
 
 // Occlusion (Agent.exlude_V_source_data, agent.py:421-445) and fill (agent.py:569-590) of the M
 // recorded objects into wf.row (which must be zeroed).  Ends with a __syncwarp.
+//
+// The reference sorts all objects by distance (stable) and clips every social cue f, in that order, against each
+// strictly closer object o: (1) f.s' <= o.s <= f.e' -> f.e' = o.s; (2) f.s' <= o.e <= f.e' -> f.s' = o.e; (3) o covers
+// [f.s', f.e'] -> (0, 0), on f's CURRENT interval with o's raw ends.  Every rule needs [o.s, o.e] to meet f's current
+// interval, which only ever shrinks inside the original one (or is (0, 0) for good), so only the closer objects that
+// OVERLAP f's raw interval matter -- usually none to three of M -- and only their order among themselves.  So nothing
+// is sorted: the warp takes the social cues one after the other, the lanes test all objects in parallel (closer and
+// overlapping?), and the few hits are applied in (distance, list order) order by repeated warp-wide minimum.
+// (Before: an O(M^2) rank count for ALL objects plus a scan over the sorted prefix for every cue -- a third of the
+// agent kernel's instructions.)
 __device__ __forceinline__ void base_occlude_fill(WarpField& wf, int M, bool visual_exclusion, int R, int lane) {
-  if (visual_exclusion) {
+  if (visual_exclusion && M <= 1024) {
+    const int NQ = (M + 31) >> 5;                        // objects per lane: list positions lane + 32 t
+    for (int c0 = 0; c0 < M; c0 += 32) {
+      const int c = c0 + lane;
+      unsigned cues = __ballot_sync(0xffffffffu, c < M && (wf.key[c] & (1 << 30)));   // :447-455 only social cues are drawn
+      while (cues) {
+        const int ci = c0 + __ffs((int)cues) - 1;
+        cues &= cues - 1;
+        const ObjRec f = wf.raw[ci];                                                  // (all lanes read the same entry)
+        int sx = f.s, ex = f.e;
+        unsigned rel = 0u;                               // bit t: object lane + 32 t is strictly closer (:430) and meets f
+        for (int t = 0; t < NQ; ++t) {
+          const int q = lane + 32 * t;
+          if (q < M) {
+            const ObjRec o = wf.raw[q];
+            if ((o.d < f.d) && (o.s <= f.e) && (o.e >= f.s)) rel |= 1u << t;
+          }
+        }
+        while (__any_sync(0xffffffffu, rel != 0u)) {     // the hits in (distance, list order) order
+          // this lane's first remaining hit ... (distances are >= 0: their bit patterns order like the values)
+          unsigned bhi = 0xffffffffu, blo = 0xffffffffu, bk = 0xffffffffu;
+          int bt = 0, bs = 0, be = 0;
+          for (unsigned m = rel; m; m &= m - 1u) {
+            const int t = __ffs((int)m) - 1, q = lane + 32 * t;
+            const ObjRec o = wf.raw[q];
+            const unsigned long long db = (unsigned long long)__double_as_longlong(o.d);
+            const unsigned hi = (unsigned)(db >> 32), lo = (unsigned)db, kq = (unsigned)(wf.key[q] & 0x3fffffff);
+            if (hi < bhi || (hi == bhi && (lo < blo || (lo == blo && kq < bk)))) {
+              bhi = hi; blo = lo; bk = kq; bt = t; bs = o.s; be = o.e;
+            }
+          }
+          // ... and the warp's
+          bool cand = rel != 0u;
+          const unsigned mhi = __reduce_min_sync(0xffffffffu, cand ? bhi : 0xffffffffu);
+          cand = cand && bhi == mhi;
+          const unsigned mlo = __reduce_min_sync(0xffffffffu, cand ? blo : 0xffffffffu);
+          cand = cand && blo == mlo;
+          const unsigned mk = __reduce_min_sync(0xffffffffu, cand ? bk : 0xffffffffu);
+          cand = cand && bk == mk;
+          const int src = __ffs((int)__ballot_sync(0xffffffffu, cand)) - 1;           // exactly one lane (keys are unique)
+          const int os = __shfl_sync(0xffffffffu, bs, src), oe = __shfl_sync(0xffffffffu, be, src);
+          if (sx <= os && os <= ex) ex = os;                                          // :432-433
+          if (sx <= oe && oe <= ex) sx = oe;                                          // :435-436
+          if (os <= sx && oe >= ex) { sx = 0; ex = 0; }                               // :438-440
+          if (lane == src) rel &= ~(1u << bt);
+        }
+        if (lane == (ci & 31)) base_draw(wf.row, R, sx, ex);
+        __syncwarp();
+      }
+    }
+  } else if (visual_exclusion) {                         // more than 1024 objects: rank everything, scan the sorted prefix
     for (int m = lane; m < M; m += 32) {   // rank by (distance, list order): the stable sort of :424
       const ObjRec f = wf.raw[m];
       const int kf = wf.key[m] & 0x3fffffff;
