@@ -33,7 +33,8 @@
 namespace abm {
 
 constexpr int kSymWarpQ = 64;        // entries per warp: worked off 32 at a time, as soon as 32 are there
-constexpr int kSymQueueCap = 3072;   // fp64 queue: ~0.2 % of the 1M ordered pairs of a 1024-agent replicate
+constexpr int kSymQueueCap = 3072;   // fp64 queue entries of a CTA, split evenly among its warps (192 each at 16 warps; a
+                                     // batch of 32 slow pairs adds at most 64); afterwards the exp(i Phi) table lives there
 
 // Loop-invariant values of the pair loop that must live in registers (the compiler would otherwise
 // re-materialise them with a MOV in every step).
@@ -44,17 +45,15 @@ struct SymConsts {
   int scratch_pos;     // padded position of the scratch word
   unsigned long long half64;   // 2^31: rounding constant of the bin index, addend of its IMAD.WIDE
 };
-__device__ __forceinline__ float pin_f(float v) { asm volatile("" : "+f"(v)); return v; }
 // acc |= m under a predicate: ONE predicated LOP3 (the compiler's own choice is SEL + LOP3)
 __device__ __forceinline__ void or_if(uint32_t& acc, bool p, uint32_t m) {
   asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q or.b32 %0, %0, %2;\n\t}" : "+r"(acc) : "r"((uint32_t)p), "r"(m));
 }
-__device__ __forceinline__ uint32_t pin_u(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 
 struct SymShared {
   float4* ag;          // [Np] (x, y, heading constant, the same + half a turn); padding agents beyond N are far away
   uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
-  uint32_t* queue;     // [kSymQueueCap][2]  directions deferred to fp64 (focal << 16 | object, k << 16 | h)
+  uint32_t* queue;     // [kSymQueueCap][2]  directions waiting for fp64 (focal << 16 | object, k << 16 | h), per warp
   uint32_t* warpq;     // [warps][kSymWarpQ] per-warp queue of pairs with directions off the fast path
   int* qcount;         // [0]: fp64 entries (statistics), [1]: pairs off the fast path (statistics), [2 + w]: fp64 entries
                        // waiting in warp w's part of the queue
