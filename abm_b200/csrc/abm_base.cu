@@ -191,21 +191,18 @@ int base_agents_warps(int N, int W, size_t smem_limit) {
   return w;
 }
 
-__global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  WarpField wf = warp_field_at(smem_raw + warp_field_bytes(a.N, a.W) * wib, a.N);
+// Field phase of one focal agent gw = (replicate, agent), run by a whole warp: returns the set bins of the stored field's
+// left and right halves (what the decision process needs of it).
+__device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpField& wf, long long gw, int lane, int& n_left_out,
+                                                 int& n_right_out) {
   uint32_t* row = wf.row;
-
-  const long long gw = (long long)blockIdx.x * wpb + wib;   // global warp = (replicate, focal agent)
-  if (gw >= (long long)a.B * a.N) return;
   const int b = (int)(gw / a.N), i = (int)(gw - (long long)b * a.N);
   const size_t a0 = (size_t)b * a.N, gi = a0 + i;
   const int R = a.R, W = a.W, N = a.N;
   for (int w = lane; w < W + 1; w += 32) row[w] = 0u;
 
   const float xi_f = a.ag.snap_x[gi], yi_f = a.ag.snap_y[gi];
-  const double xi = xi_f, yi = yi_f, r = a.radius;
+  const double r = a.radius;
   const FocalExact fe = vf_focal_exact(xi_f, yi_f, (float)a.radius, a.ag.theta[gi]);   // same v1 construction (agent.py:484-495)
   const int my_patch = a.ag.patch_id[gi];
 
@@ -250,8 +247,8 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
   // ---- flip + FOV mask (agent.py:593-595): stored[b] = v[R-1-b], kept for b in [mask_lo, mask_hi] ----
   const int h = R / 2;                                       // int(V_field_len / 2) (supcalc.py:86-88)
   const int va = R - 1 - a.mask_hi, vb = R - a.mask_lo;      // kept bins in v coordinates [va, vb)
-  const int n_left = popc_range(row, W, max(va, R - h), min(vb, R), lane);    // stored[0:h]  <-> v[R-h:R]
-  const int n_right = popc_range(row, W, max(va, 0), min(vb, R - h), lane);   // stored[h:]   <-> v[0:R-h]
+  n_left_out = popc_range(row, W, max(va, R - h), min(vb, R), lane);    // stored[0:h]  <-> v[R-h:R]
+  n_right_out = popc_range(row, W, max(va, 0), min(vb, R - h), lane);   // stored[h:]   <-> v[0:R-h]
   if (a.fields_out) {
     uint32_t* out = a.fields_out + gi * W;
     for (int ws = lane; ws < W; ws += 32) {
@@ -262,9 +259,16 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
       out[ws] = word & m;
     }
   }
-  if (lane != 0) return;
+}
 
-  // ---- decision process, mode machine, kinematics (agent.py:168-283), fp64 ----
+// Decision process, mode machine, kinematics (agent.py:168-283) of one focal agent, fp64, one THREAD per agent: the
+// threads 0 .. warps-1 of the CTA take the agents of its warps after a barrier, so that this serial code runs with as many
+// lanes as the CTA has agents instead of on lane 0 of every warp.
+__device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long long gw, int n_left, int n_right) {
+  const int b = (int)(gw / a.N), i = (int)(gw - (long long)b * a.N);
+  const size_t gi = (size_t)b * a.N + i;
+  const int R = a.R, h = R / 2;
+  const double xi = a.ag.snap_x[gi], yi = a.ag.snap_y[gi], r = a.radius;
   const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
   const double mean_all = (double)(n_left + n_right) / (double)R;
   const double collected = a.ag.collected[gi];
@@ -320,6 +324,25 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
   a.ag.override_mode[gi] = override; a.ag.mode[gi] = mode;
   a.ag.collected_before[gi] = (float)collected;              // :283
   atomicAdd(&a.mode_steps[(size_t)b * 4 + mode], 1u);        // the mode this agent is logged with at the end of the step
+}
+
+__global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int halves[2 * 8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long total = (long long)a.B * a.N;
+  const long long gw = (long long)blockIdx.x * wpb + wib;   // global warp = (replicate, focal agent)
+  if (gw < total) {
+    WarpField wf = warp_field_at(smem_raw + warp_field_bytes(a.N, a.W) * wib, a.N);
+    int n_left = 0, n_right = 0;
+    base_agent_field(a, wf, gw, lane, n_left, n_right);
+    if (lane == 0) { halves[2 * wib] = n_left; halves[2 * wib + 1] = n_right; }
+  }
+  __syncthreads();
+  if (threadIdx.x < wpb) {
+    const long long g2 = (long long)blockIdx.x * wpb + threadIdx.x;
+    if (g2 < total) base_agent_decide(a, g2, halves[2 * threadIdx.x], halves[2 * threadIdx.x + 1]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
