@@ -381,7 +381,36 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
   __syncthreads();
   const float lim2 = (float)((2.0 * (r + 2.0)) * (2.0 * (r + 2.0)));     // (r1 + 2 + r2 + 2)^2, sims.py:739-752
 
+  // hit agents first (cheap), then the warps pull them from a list: the events of one hit agent are a sequential chain
+  // of fp64 latency, and with a fixed assignment the CTA waited at the final barrier for its unluckiest warp (more than
+  // half of the kernel's warp time)
+  // (agents hit by several others -- the long chains -- are listed from the front and taken first, the rest from the back)
+  int* work = reinterpret_cast<int*>(py + N);                            // [N] hit agents, then: front count, back count, next
+  if (threadIdx.x == 0) { work[N] = 0; work[N + 1] = 0; work[N + 2] = 0; }
+  __syncthreads();
   for (int a2 = wib; a2 < N; a2 += wpb) {
+    const float tx2 = truncf(px[a2]), ty2 = truncf(py[a2]);
+    int n_hit = 0;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+      const int jj = j0 + lane;
+      bool hit = false;
+      if (jj < N && jj != a2) {
+        const float dx = truncf(px[jj]) - tx2, dy = truncf(py[jj]) - ty2;
+        hit = dx * dx + dy * dy <= lim2;
+      }
+      n_hit += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == 0 && n_hit >= 2) work[atomicAdd(&work[N], 1)] = a2;
+    if (lane == 0 && n_hit == 1) work[N - 1 - atomicAdd(&work[N + 1], 1)] = a2;
+  }
+  __syncthreads();
+  const int n_front = work[N], n_work = n_front + work[N + 1];
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&work[N + 2], 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= n_work) break;
+    const int a2 = work[slot < n_front ? slot : N - 1 - (slot - n_front)];
     const float tx2 = truncf(px[a2]), ty2 = truncf(py[a2]);               // rect.x = int(position) (agent.py:303-304)
     const bool expl2 = ov[a2] == OV_EXPLOIT;                               // (fixed during the phase)
     for (int j0 = 0; j0 < N; j0 += 32) {
@@ -483,7 +512,7 @@ static int base_smem_optin() {
 
 void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
   const int smem_max = base_smem_optin();
-  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 6 * sizeof(int) * (size_t)a.N;
+  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 7 * sizeof(int) * (size_t)a.N + 4 * sizeof(int);
   int warps = 16;
   while (warps > 1 && (warps / 2 >= a.N || per_warp * warps + shared > (size_t)smem_max)) warps >>= 1;
   const size_t smem = per_warp * warps + shared;
