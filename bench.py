@@ -296,7 +296,7 @@ def main():
         streams = [torch.cuda.Stream() for _ in range(NB)]
         hosts = [[{k: torch.from_numpy(a.copy()).pin_memory().numpy() for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v))}
                   for _ in range(2)] for _ in range(NB)]
-        e2e_steps = NB * max(2, min(args.steps, 20) // NB)            # batch-steps, round robin over the batches
+        e2e_steps = NB * max(2, min(args.steps, 60) // NB)            # batch-steps, round robin over the batches
         cur = [0] * NB
 
         def batch_step(k, first=False):
