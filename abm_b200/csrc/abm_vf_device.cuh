@@ -563,6 +563,8 @@ struct EdgeSums {
 // left, then takes ONE edge per row; the warp reconverges between the two halves, so each half always runs with as
 // many lanes as have work.  (A loop over the edges of a word inside a loop over the words makes the warp wait, in
 // every word, for the lane with the most edges there; K > 1 gives the latency-bound loop independent work.)
+// edges taken per row and loop iteration (the vote, the two reconvergence points and the word bookkeeping are paid once)
+constexpr int kEdgesPerIteration = 2;   // (4: slower; two word advances per iteration: slower)
 template <int K>
 __device__ __forceinline__ void vf_edge_sums(const uint32_t* const (&f)[K], int stride, const VFKernelArgs& a,
                                              uint32_t etab_s, const bool (&active)[K], EdgeSums (&out)[K]) {
@@ -602,6 +604,8 @@ __device__ __forceinline__ void vf_edge_sums(const uint32_t* const (&f)[K], int 
         }
       }
       __syncwarp();
+#pragma unroll
+      for (int rep = 0; rep < kEdgesPerIteration; ++rep)
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         if (diff[j]) {
