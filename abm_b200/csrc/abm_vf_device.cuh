@@ -564,7 +564,7 @@ struct EdgeSums {
 // many lanes as have work.  (A loop over the edges of a word inside a loop over the words makes the warp wait, in
 // every word, for the lane with the most edges there; K > 1 gives the latency-bound loop independent work.)
 // edges taken per row and loop iteration (the vote, the two reconvergence points and the word bookkeeping are paid once)
-constexpr int kEdgesPerIteration = 2;   // (4: slower; two word advances per iteration: slower)
+constexpr int kEdgesPerIteration = 2;   // (3: 1.906 ms, 4: 1.925 ms against 1.891; two word advances per iteration: slower)
 template <int K>
 __device__ __forceinline__ void vf_edge_sums(const uint32_t* const (&f)[K], int stride, const VFKernelArgs& a,
                                              uint32_t etab_s, const bool (&active)[K], EdgeSums (&out)[K]) {
