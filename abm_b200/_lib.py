@@ -53,6 +53,18 @@ class VFProjArgs(C.Structure):
     ]
 
 
+class CSProjArgs(C.Structure):
+    """abm_cs_proj_args_t"""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("resolution", C.c_int32),
+        ("fov0", C.c_double), ("fov1", C.c_double),
+        ("x", C.c_double), ("y", C.c_double), ("radius", C.c_double), ("orientation", C.c_double),
+        ("n_obj", C.c_int32),
+        ("obj_x", C.POINTER(C.c_double)), ("obj_y", C.POINTER(C.c_double)),
+        ("max_proj_size", C.c_double),
+    ]
+
+
 class BaseConfig(C.Structure):
     """abm_base_config_t"""
     _fields_ = [
@@ -128,6 +140,7 @@ SYMBOLS = {
     "abm_vf_internal_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "abm_synchronize": (C.c_int, [_P, _P]),
     "abm_vf_projection_field": (C.c_int, [C.POINTER(VFProjArgs), _P]),
+    "abm_cs_projection_field": (C.c_int, [C.POINTER(CSProjArgs), _P]),
     "abm_vf_flocking_terms": (C.c_int, [_P, C.c_int, C.c_double, _P, C.POINTER(C.c_double)]),
     "abm_base_create": (C.c_int, [C.POINTER(BaseConfig), C.c_int, C.POINTER(_P)]),
     "abm_base_destroy": (C.c_int, [_P]),

@@ -808,6 +808,54 @@ int abm_vf_projection_field(const abm_vf_proj_args_t* args, uint32_t* out_rows) 
   return rc;
 }
 
+int abm_cs_projection_field(const abm_cs_proj_args_t* args, uint32_t* out_rows) {
+  if (!args || !out_rows) return fail(ABM_E_INVALID, "abm_cs_projection_field: null argument");
+  if (args->struct_size != (int32_t)sizeof(abm_cs_proj_args_t))
+    return fail(ABM_E_INVALID, "abm_cs_projection_field: struct_size mismatch");
+  if (args->resolution < 8 || args->resolution > 4096)
+    return fail(ABM_E_INVALID, "abm_cs_projection_field: resolution must be in [8, 4096]");
+  if (args->n_obj < 0 || (args->n_obj > 0 && (!args->obj_x || !args->obj_y)))
+    return fail(ABM_E_INVALID, "abm_cs_projection_field: bad object list");
+  if (args->n_obj == 0) return ABM_OK;
+  GridConsts g;
+  build_grid(args->resolution, g);
+  const int n = args->n_obj;
+  // bins of the returned (flipped) rows that survive cs_supcalc.py:290-291, on numpy's linspace values
+  std::vector<uint32_t> keep(g.W, 0u);
+  for (int k = 0; k < g.R; ++k) {
+    const double phi = (k == g.R - 1) ? ABM_PI_D : ((double)k * g.lin_step + (-ABM_PI_D));
+    if (!(phi < args->fov0) && !(phi > args->fov1)) keep[k >> 5] |= 1u << (k & 31);
+  }
+  DevBuf<double> dx, dy;
+  DevBuf<uint32_t> dkeep, rows;
+  ABM_CUDA(dx.alloc(n)); ABM_CUDA(dy.alloc(n)); ABM_CUDA(dkeep.alloc(g.W)); ABM_CUDA(rows.alloc((size_t)n * g.W));
+  int rc = ABM_OK;
+  do {
+    cudaError_t ce;
+    if ((ce = cudaMemcpy(dx.p, args->obj_x, sizeof(double) * n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(dy.p, args->obj_y, sizeof(double) * n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(dkeep.p, keep.data(), sizeof(uint32_t) * g.W, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+      break;
+    }
+    abm::CSProjArgs a;
+    memset(&a, 0, sizeof(a));
+    a.R = g.R; a.W = g.W; a.n_obj = n;
+    a.lin_step = g.lin_step; a.fov0 = args->fov0; a.fov1 = args->fov1;
+    a.fx = args->x; a.fy = args->y; a.fr = args->radius; a.ftheta = args->orientation;
+    a.max_proj_size = args->max_proj_size;
+    a.ox = dx.p; a.oy = dy.p; a.keep = dkeep.p; a.rows = rows.p;
+    abm::launch_cs_projection(a, 0);
+    if ((ce = cudaGetLastError()) != cudaSuccess ||
+        (ce = cudaMemcpy(out_rows, rows.p, sizeof(uint32_t) * (size_t)n * g.W, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+      rc = fail(ABM_E_CUDA, cudaGetErrorString(ce));
+      break;
+    }
+  } while (0);
+  dx.release(); dy.release(); dkeep.release(); rows.release();
+  return rc;
+}
+
 int abm_vf_flocking_terms(const uint32_t* packed_v_now, int resolution, double vel_now, const double* params,
                           double out[6]) {
   if (!packed_v_now || !params || !out) return fail(ABM_E_INVALID, "abm_vf_flocking_terms: null argument");

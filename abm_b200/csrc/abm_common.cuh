@@ -120,6 +120,16 @@ struct VFProjArgs {
   uint32_t* rows;                 // n_obj * W, stored order
 };
 void launch_vf_projection(const VFProjArgs& a, cudaStream_t stream);
+struct CSProjArgs {
+  int R, W, n_obj;
+  double lin_step, fov0, fov1;
+  double fx, fy, fr, ftheta;      // focal agent, float64 as passed
+  double max_proj_size;           // < 0: none
+  const double* ox; const double* oy;
+  const uint32_t* keep;           // W words, stored order: bins with fov0 <= linspace angle <= fov1
+  uint32_t* rows;                 // n_obj * W, stored order
+};
+void launch_cs_projection(const CSProjArgs& a, cudaStream_t stream);
 void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const VFParams6* prm,
                      const PhiLut* lut, double dphi, double* out6, cudaStream_t stream);
 // radius_minmax: 2 uints (bit patterns of min / max radius; init 0x7f800000 / 0)

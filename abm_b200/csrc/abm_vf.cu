@@ -12,6 +12,7 @@
 // lanes of a warp read the same neighbour record (shared-memory broadcast, LDS.128).
 // Replaces VFSimulation.step_sim -> VFAgent.update for all agents (vf_sims.py:291-302,
 // vf_agent.py:52-80).
+#include <climits>
 #include "abm_vf_device.cuh"
 
 namespace abm {
@@ -397,6 +398,54 @@ __global__ void vf_projection_kernel(const VFProjArgs a) {
 void launch_vf_projection(const VFProjArgs& a, cudaStream_t stream) {
   const int threads = 64;
   vf_projection_kernel<<<(a.n_obj + threads - 1) / threads, threads, 0, stream>>>(a);
+}
+
+// cs_supcalc.projection_field (cooperative_signaling/cs_agent/cs_supcalc.py:204-289): one thread per
+// object, the reference's operation sequence in float64 on float64 inputs.  Differences from the VF
+// function above: object centre = position + FOCAL radius (:242); visibility decided on the angle,
+// fov0 <= angle <= fov1 (:260); projections wider than max_proj_size bins dropped (:268); after the
+// flip, bins whose linspace angle is outside the FOV are cleared (:290-291, `keep` = their mask).
+// The meter amplitudes (:283-284) scale whole rows and are applied by the host.
+__global__ void cs_projection_kernel(const CSProjArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n_obj) return;
+  uint32_t* row = a.rows + (size_t)j * a.W;
+  uint32_t tmp[128];                          // W <= 128 (R <= 4096) for this entry point
+  for (int w = 0; w < a.W; ++w) tmp[w] = 0u;
+  const double ox = a.ox[j], oy = a.oy[j];
+  if (!(ox == a.fx && oy == a.fy)) {                                          // :233
+    const double cix = __dadd_rn(a.fx, a.fr), ciy = __dadd_rn(a.fy, a.fr);    // :224
+    const double ex = __dadd_rn(a.fx, __dmul_rn(__dadd_rn(1.0, cos(a.ftheta)), a.fr));   // :227-228
+    const double ey = __dadd_rn(a.fy, __dmul_rn(__dadd_rn(1.0, -sin(a.ftheta)), a.fr));
+    const double v1x = __dadd_rn(ex, -cix), v1y = __dadd_rn(ey, -ciy);        // :231
+    const double n1 = __dsqrt_rn(__dadd_rn(__dmul_rn(v1x, v1x), __dmul_rn(v1y, v1y)));
+    const double u1x = __ddiv_rn(v1x, n1), u1y = __ddiv_rn(v1y, n1);
+    const double v2x = __dadd_rn(__dadd_rn(ox, a.fr), -cix);                  // :242, :245
+    const double v2y = __dadd_rn(__dadd_rn(oy, a.fr), -ciy);
+    const double n2 = __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+    const double u2x = __ddiv_rn(v2x, n2), u2y = __ddiv_rn(v2y, n2);
+    double dot = __dadd_rn(__dmul_rn(u1x, u2x), __dmul_rn(u1y, u2y));
+    dot = fmin(1.0, fmax(-1.0, dot));
+    double ang = acos(dot);                                                   // supcalc.py:31
+    if (__dadd_rn(__dmul_rn(u1x, u2y), -__dmul_rn(u1y, u2x)) < 0.0) ang = -ang;
+    if (ang < 0.0) ang = __dadd_rn(ang, ABM_TWO_PI_D);                        // :317
+    const double ca = (ang >= 0.0 && ang <= ABM_PI_D) ? -ang : __dadd_rn(ABM_TWO_PI_D, -ang);   // :321-324
+    const double vis = __dmul_rn(2.0, atan(__ddiv_rn(a.fr, n2)));             // :253
+    const double proj = __dmul_rn(__ddiv_rn(vis, ABM_TWO_PI_D), (double)a.R); // :265
+    const bool in_fov = (a.fov0 <= ca) && (ca <= a.fov1);                     // :260 (false for NaN)
+    const bool size_ok = (a.max_proj_size < 0.0) || (proj <= a.max_proj_size);   // :286-296
+    if (in_fov && size_ok && n2 > 0.0) {
+      const int k = nearest_bin_exact(ca, a.R, a.lin_step);                   // :256
+      const int h = (int)floor(__ddiv_rn(proj, 2.0));                         // :271-272
+      vf_draw<false>(tmp, 1, a.R, INT_MIN, INT_MAX, k, h);                    // :274-281 (no test on the ends)
+    }
+  }
+  for (int ws = 0; ws < a.W; ++ws) row[ws] = flipped_word(tmp, 1, a.R, a.W, ws) & a.keep[ws];   // :288-291
+}
+
+void launch_cs_projection(const CSProjArgs& a, cudaStream_t stream) {
+  const int threads = 64;
+  cs_projection_kernel<<<(a.n_obj + threads - 1) / threads, threads, 0, stream>>>(a);
 }
 
 __global__ void vf_terms_kernel(const uint32_t* packed_v, int R, int W, double vel, const VFParams6* prm,

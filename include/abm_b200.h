@@ -209,6 +209,23 @@ typedef struct {
 } abm_vf_proj_args_t;
 int abm_vf_projection_field(const abm_vf_proj_args_t* args, uint32_t* out_rows);
 
+/* cooperative-signaling projection_field (abm/projects/cooperative_signaling/cs_agent/cs_supcalc.py:204-289):
+ * one focal agent, n_obj objects of the FOCAL radius; visibility decided on the angle (fov0 <= angle <= fov1),
+ * projections wider than max_proj_size bins dropped, bins outside the FOV cleared after the flip.  Evaluated in
+ * float64 on the float64 inputs.  out_rows as above (bits); the meter amplitudes of the reference
+ * (object_meters, :283-284) scale whole rows and are applied by the caller. */
+typedef struct {
+  int32_t struct_size;
+  int32_t resolution;
+  double fov0, fov1;
+  double x, y, radius, orientation; /* focal agent */
+  int32_t n_obj;
+  const double* obj_x;
+  const double* obj_y;
+  double max_proj_size; /* < 0: None */
+} abm_cs_proj_args_t;
+int abm_cs_projection_field(const abm_cs_proj_args_t* args, uint32_t* out_rows);
+
 /* VSWRM_flocking_state_variables (vf_supcalc.py:161-254), verbose form, on a packed
  * UN-flipped field V_now (what vf_agent.py:270 passes: np.flip(soc_v_field)).
  * params: ABM_VF_NPARAM doubles.  out: dvel, dpsi, a_blob, a_edge, b_blob, b_edge. */

@@ -63,3 +63,18 @@ def load_base_cases():
         cases.append(dict(cfg=cfg, st=st, dth=z[p + "dth"], fields=z[p + "fields"],
                           out={k: z[p + "out_" + k] for k in BASE_OUT_KEYS}))
     return cases
+
+
+def load_cs_cases():
+    """tests/golden/cs_golden.npz (written by make_golden_cs.py from real reference output of
+    cooperative_signaling/cs_agent/cs_supcalc.py::projection_field)."""
+    z = np.load(os.path.join(GOLDEN, "cs_golden.npz"))
+    cases = []
+    for c in range(int(z["n_cases"])):
+        p = f"c{c}_"
+        s = z[p + "scalars"]
+        meters = z[p + "meters"]
+        cases.append(dict(fov=(s[0], s[1]), R=int(s[2]), pos=np.array([s[3], s[4]]), r=float(s[5]), th=float(s[6]),
+                          mps=None if s[7] < 0 else float(s[7]), objs=z[p + "objs"],
+                          meters=None if meters.size == 0 else meters, rows=z[p + "rows"]))
+    return cases

@@ -31,6 +31,7 @@ def test_struct_sizes_match_header_layout():
     from abm_b200 import _lib
     assert C.sizeof(_lib.VFConfig) == 17 * 4
     assert C.sizeof(_lib.VFProjArgs) == 8 + 6 * 8 + 8 + 3 * 8 + 8 + 3 * 8
+    assert C.sizeof(_lib.CSProjArgs) == 8 + 6 * 8 + 8 + 2 * 8 + 8
 
 
 def test_version_and_words(built_lib):
