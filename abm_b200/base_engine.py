@@ -73,8 +73,9 @@ class BaseEngine:
 
     # -- parameters ----------------------------------------------------------------------
     def set_params(self, **kw):
-        """Decision / movement parameters by name (_lib.BASE_PARAM_NAMES); scalars or length-B
-        arrays (one set per replicate, e.g. a DEC_EPSW sweep)."""
+        """Decision / movement parameters by name (_lib.BASE_PARAM_NAMES): scalars, length-B arrays (one set
+        per replicate, e.g. a DEC_EPSW sweep) or (B, N) arrays (one set per agent: the heterogeneous agents of
+        agent.py:83-108 / sims.py:499-517)."""
         defaults = dict(T_w=0.5, Eps_w=3, g_w=0.085, B_w=0, w_max=1, T_u=0.5, Eps_u=3, g_u=0.085, B_u=0, u_max=1,
                         S_wu=0.25, S_uw=0.01, F_N=2, F_R=1, exp_vel_max=1, exp_theta_min=-0.3, exp_theta_max=0.3,
                         reloc_theta_max=0.5, exp_stop_ratio=0.08, agent_consumption=1)
@@ -82,11 +83,18 @@ class BaseEngine:
         if unknown:
             raise TypeError(f"unknown parameter(s): {sorted(unknown)}")
         defaults.update(kw)
-        vals = [np.atleast_1d(np.asarray(defaults[n], np.float64)) for n in _lib.BASE_PARAM_NAMES]
-        n = max(v.size for v in vals)
-        if n not in (1, self.B):
-            raise ValueError("parameter arrays must have length 1 or n_replicates")
-        tab = np.ascontiguousarray(np.stack([np.broadcast_to(v, (n,)) for v in vals], axis=1))
+        vals = [np.asarray(defaults[n], np.float64) for n in _lib.BASE_PARAM_NAMES]
+        for v in vals:
+            if v.shape not in ((), (1,), (self.B,), (self.B, self.N)):
+                raise ValueError("parameter arrays must have length 1 or n_replicates, or shape (n_replicates, n_agents)")
+        if any(v.ndim == 2 for v in vals):                    # one set per agent, replicate-major
+            n = self.B * self.N
+            vals = [np.broadcast_to(v[:, None] if v.shape == (self.B,) and self.B != 1 else v,
+                                    (self.B, self.N)).reshape(-1) for v in vals]
+        else:
+            n = max(v.size for v in vals)
+            vals = [np.broadcast_to(v.reshape(-1), (n,)) for v in vals]
+        tab = np.ascontiguousarray(np.stack(vals, axis=1))
         _lib.check(self._lib.abm_base_set_params(self._h, C.c_void_p(tab.ctypes.data), n), "abm_base_set_params")
 
     # -- state -----------------------------------------------------------------------------

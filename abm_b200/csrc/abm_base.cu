@@ -51,6 +51,12 @@ __device__ __forceinline__ void notify(const BaseAgentPtrs& ag, size_t g, int st
   ag.patch_id[g] = res_id;                                   // :39-42 (None -> -1)
 }
 
+// Parameter set of agent i of replicate b: one set for the whole batch, one per replicate (sweeps), or one per agent
+// (heterogeneous agents, agent.py:83-108).
+__device__ __forceinline__ const BaseParams& base_params_of(const BaseKernelArgs& a, int b, int i) {
+  return *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride + (size_t)i * a.param_stride_agent);
+}
+
 // One WARP per replicate: lanes take the agents of a chunk of 32 in parallel (membership, bias, notify, teleport),
 // chunks and patches go in the reference's order, and the one truly sequential piece -- the depletion of a patch by
 // its exploiting agents in agent order (sims.py:824-836) -- is replayed by all lanes in lock step over the ballot of
@@ -60,7 +66,6 @@ __device__ __forceinline__ void notify(const BaseAgentPtrs& ag, size_t g, int st
 __global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
   const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= a.B) return;
-  const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * a.N, p0 = (size_t)b * a.P;
   const double r = a.radius;
@@ -89,10 +94,11 @@ __global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
       uint32_t eb = destroy ? 0u : __ballot_sync(0xffffffffu, expl);
       int d_lane = destroy ? -1 : 32;           // lanes <= d_lane still see the patch; 32: nobody destroyed it (yet)
       double my_take = 0.0;
+      const double my_consumption = base_params_of(a, b, i < a.N ? i : 0).consumption;   // agent.consumption
       while (eb) {
         const int l = __ffs(eb) - 1;
         eb &= eb - 1;
-        double take = fmin(prm.consumption, (double)a.pa.quality[p0 + p]);           // rescource.py:121-122
+        double take = fmin(__shfl_sync(0xffffffffu, my_consumption, l), (double)a.pa.quality[p0 + p]);   // rescource.py:121-122
         if (left >= take) left -= take; else { take = left; left = 0.0; }
         left = (double)(float)left;                                                   // resc_left lives in fp32 state
         if (lane == l) my_take = take;
@@ -269,7 +275,7 @@ __device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long 
   const size_t gi = (size_t)b * a.N + i;
   const int R = a.R, h = R / 2;
   const double xi = a.ag.snap_x[gi], yi = a.ag.snap_y[gi], r = a.radius;
-  const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
+  const BaseParams prm = base_params_of(a, b, i);
   const double mean_all = (double)(n_left + n_right) / (double)R;
   const double collected = a.ag.collected[gi];
   const double I_priv = prm.F_N * ((a.ag.novelty[gi] != 0u) ? 1.0 : 0.0) +
@@ -370,7 +376,6 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
   float* px = reinterpret_cast<float*>(col + N);                         // positions (this phase does not move anybody)
   float* py = px + N;
   const int b = blockIdx.x;
-  const BaseParams prm = *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride);
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * N;
   const double r = a.radius;
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
             if (D == 0.0) D = -1.0;                                                  // :456
             if (!expl2) th[a2] = (float)((double)th[a2] - D * 0.2);                 // :458-459 (not wrapped)
             if (amp * (double)n_front > 0.0) a.ag.vel[a0 + a2] = 0.0f;              // :462-463
-            else if (!expl2) a.ag.vel[a0 + a2] = (float)prm.exp_vel_max;
+            else if (!expl2) a.ag.vel[a0 + a2] = (float)base_params_of(a, b, a2).exp_vel_max;   // agent2.max_exp_vel (:465)
           }
           __syncwarp();
         }

@@ -50,7 +50,9 @@ struct BaseKernelArgs {
   BaseAgentPtrs ag;            // B*N, updated in place
   BasePatchPtrs pa;            // B*P, updated in place
   const double* params;        // n_sets * kBaseNParam
-  int param_stride;            // 0 or kBaseNParam
+  int param_stride;            // doubles between the sets of consecutive replicates: 0, kBaseNParam or N * kBaseNParam
+  int param_stride_agent;      // doubles between the sets of consecutive agents: 0, or kBaseNParam with one set per
+                               // agent (heterogeneous agents: agent.py:83-108 behave_params, sims.py:499-517)
   const float* inject_dtheta;  // nullable, B*N: replaces the random-walk draw (parity tests)
   uint32_t* fields_out;        // nullable, B*N*W, stored order
   unsigned long long* counters;   // [0] patches regenerated, [1] regeneration retries exhausted

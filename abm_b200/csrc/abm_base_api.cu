@@ -102,7 +102,7 @@ int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t*
   if (cfg->keep_fields) A(e->fields.alloc(na * e->W));
   for (DevBuf<float>* b : {&e->px, &e->py, &e->pradius, &e->pleft, &e->pquality}) A(b->alloc(np));
   A(e->pid.alloc(np));
-  A(e->params.alloc((size_t)cfg->n_replicates * abm::kBaseNParam));
+  A(e->params.alloc((size_t)cfg->n_replicates * cfg->n_agents * abm::kBaseNParam));   // up to one set per agent
   A(e->counters.alloc(4));
   if (err == cudaSuccess) err = cudaMemset(e->counters.p, 0, 4 * sizeof(unsigned long long));
   A(e->mode_steps.alloc(4 * (size_t)cfg->n_replicates));
@@ -143,8 +143,9 @@ int abm_base_destroy(abm_base_engine_t* e) {
 
 int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets) {
   if (!e || !params) return fail(ABM_E_INVALID, "abm_base_set_params: null argument");
-  if (n_sets != 1 && n_sets != e->cfg.n_replicates)
-    return fail(ABM_E_INVALID, "abm_base_set_params: n_sets must be 1 or n_replicates");
+  if (n_sets != 1 && n_sets != e->cfg.n_replicates &&
+      (long long)n_sets != (long long)e->cfg.n_replicates * e->cfg.n_agents)
+    return fail(ABM_E_INVALID, "abm_base_set_params: n_sets must be 1, n_replicates or n_replicates * n_agents");
   ABM_CUDA(cudaSetDevice(e->device));
   ABM_CUDA(cudaMemcpy(e->params.p, params, sizeof(double) * abm::kBaseNParam * n_sets, cudaMemcpyHostToDevice));
   e->n_param_sets = n_sets;
@@ -237,7 +238,10 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
                             e->collected_before.p, e->i_priv.p, e->env_status.p, e->override_mode.p, e->mode.p,
                             e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p};
   a.pa = abm::BasePatchPtrs{e->px.p, e->py.p, e->pradius.p, e->pleft.p, e->pquality.p, e->pid.p};
-  a.params = e->params.p; a.param_stride = (e->n_param_sets == 1) ? 0 : abm::kBaseNParam;
+  a.params = e->params.p;
+  if (e->n_param_sets == 1) { a.param_stride = 0; a.param_stride_agent = 0; }
+  else if (e->n_param_sets == e->cfg.n_replicates && e->cfg.n_agents != 1) { a.param_stride = abm::kBaseNParam; a.param_stride_agent = 0; }
+  else { a.param_stride = e->cfg.n_agents * abm::kBaseNParam; a.param_stride_agent = abm::kBaseNParam; }
   a.fields_out = e->fields.p; a.counters = e->counters.p; a.mode_steps = e->mode_steps.p;
   if (inject_dtheta) {
     const float* src = inject_dtheta;

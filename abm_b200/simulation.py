@@ -249,8 +249,12 @@ class Simulation:
             raise NotImplementedError("rendering is out of scope of abm_b200 (headless only)")
         if pooling_time != 0:
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
-        if agent_behave_param_list is not None:
-            raise NotImplementedError("heterogeneous agent_behave_param_list is not supported yet (SURVEY f4)")
+        self.heterogen_agents = agent_behave_param_list is not None                # sims.py:170-173
+        if self.heterogen_agents:
+            agent_radius, v_field_res, agent_fov, vision_range = self._check_behave_params(
+                agent_behave_param_list, int(N), agent_radius, v_field_res, agent_fov, vision_range,
+                (decision_params or DecisionParams()).Tau)
+        self.agent_behave_param_list = agent_behave_param_list
         self.N, self.T, self.t = int(N), int(T), 0
         self.WIDTH, self.HEIGHT, self.window_pad = width, height, window_pad
         self.agent_radii, self.N_resc, self.resc_radius = agent_radius, int(N_resc), patch_radius
@@ -274,9 +278,42 @@ class Simulation:
                                  max_resc_perpatch=max_resc_perpatch, tau=self.decision_params.Tau,
                                  keep_fields=keep_fields, collide_agents=collide_agents, ghost_mode=ghost_mode,
                                  seed=0 if seed is None else int(seed), device=device)
-        self.engine.set_params(agent_consumption=agent_consumption, **self.decision_params.engine_kwargs())
+        prm = dict(agent_consumption=agent_consumption, **self.decision_params.engine_kwargs())
+        if self.heterogen_agents:
+            # agent.py:83-108: these keys of behave_params replace the param modules' values, per agent;
+            # sims.py:509 agent_consumption.  The same list is used in every replicate.
+            for key in self._BEHAVE_DECISION_KEYS + ("exp_vel_max", "exp_stop_ratio", "agent_consumption"):
+                row = np.array([float(bp[key]) for bp in agent_behave_param_list], np.float64)
+                prm[key] = np.broadcast_to(row, (self.B, self.N)).copy()
+        self.engine.set_params(**prm)
         self.agents, self.rescources = [], []
         self._a = self._p = self._f = None
+
+    _BEHAVE_DECISION_KEYS = ("S_wu", "T_w", "Eps_w", "g_w", "B_w", "w_max", "S_uw", "T_u", "Eps_u", "g_u", "B_u",
+                             "u_max", "F_N", "F_R")
+
+    @staticmethod
+    def _check_behave_params(plist, N, agent_radius, v_field_res, agent_fov, vision_range, tau):
+        """agent_behave_param_list (sims.py:499-517, template: contrib/evolution.py:1-26): the decision / movement
+        entries and agent_consumption may differ between agents; the geometry entries (agent_radius, v_field_res,
+        agent_fov, vision_range), Tau and pooling must be the same for all agents (they are engine-wide) and then
+        replace the constructor's values like the reference does."""
+        if len(plist) != N:
+            raise ValueError("agent_behave_param_list must hold one dictionary per agent")
+        geo = []
+        for key, default in (("agent_radius", agent_radius), ("v_field_res", v_field_res), ("agent_fov", agent_fov),
+                             ("vision_range", vision_range)):
+            vals = {float(bp.get(key, default)) for bp in plist}
+            if len(vals) != 1:
+                raise NotImplementedError(f"agent_behave_param_list: '{key}' must be the same for all agents "
+                                          "(per-agent geometry is not supported, SURVEY f4)")
+            geo.append(vals.pop())
+        if any(int(bp.get("Tau", tau)) != int(tau) for bp in plist):
+            raise NotImplementedError("agent_behave_param_list: 'Tau' must equal decision_params.Tau for all agents")
+        if any(float(bp.get("pooling_time", 0)) != 0 for bp in plist):
+            raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
+        radius = geo[0]
+        return (int(radius) if radius.is_integer() else radius), int(geo[1]), geo[2], geo[3]
 
     def create_agents(self):
         """sims.py:526-537: integer positions, heading ~ U(0, 2pi)."""

@@ -300,6 +300,10 @@ enum { ABM_BASE_PHASE_ENV = 1, ABM_BASE_PHASE_AGENTS = 2, ABM_BASE_PHASE_COLLISI
 /* Replaces: Simulation(**kwargs) + create_agents / create_resources (sims.py:526-541). */
 int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t** out);
 int abm_base_destroy(abm_base_engine_t* e);
+/* params: n_sets * ABM_BASE_NPARAM doubles.  n_sets = 1 (one set for the batch), n_replicates (one per replicate:
+ * parameter sweeps) or n_replicates * n_agents (one per agent, replicate-major: heterogeneous agents, the
+ * behave_params of agent.py:83-108 / agent_behave_param_list of sims.py:499-517 -- decision parameters,
+ * exp_vel_max, exp_stop_ratio, agent_consumption; radius, resolution, FOV and vision range stay per engine). */
 int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets);
 int abm_base_set_agents(abm_base_engine_t* e, const abm_base_agents_t* src, int on_device, void* stream);
 int abm_base_get_agents(abm_base_engine_t* e, const abm_base_agents_t* dst, int on_device, void* stream);

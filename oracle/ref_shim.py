@@ -198,7 +198,7 @@ DECISION_KEYS = ("T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "
                  "F_N", "F_R")
 
 
-def make_base_agents(st, cfg):
+def make_base_agents(st, cfg, behave_params_list=None):
     """Build real reference Agent objects (abm/agent/agent.py) from an oracle state dict
     (see oracle/restate_base.base_step_frozen) and a BaseConfig.  Constructor kwargs follow
     sims.py:481-498; decision / movement parameters are set on the instances and on the
@@ -216,7 +216,8 @@ def make_base_agents(st, cfg):
             env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0), v_field_res=cfg.R, FOV=tuple(cfg.fov),
             window_pad=int(cfg.window_pad), pooling_time=0, pooling_prob=0, consumption=cfg.agent_consumption,
             vision_range=cfg.vision_range, visual_exclusion=cfg.visual_exclusion,
-            patchwise_exclusion=cfg.patchwise_exclusion, behave_params=None)
+            patchwise_exclusion=cfg.patchwise_exclusion,
+            behave_params=None if behave_params_list is None else behave_params_list[i])
         a.velocity = float(st["vel"][i])
         a.w, a.u = float(st["w"][i]), float(st["u"][i])
         a.novelty = np.array(st["novelty"][i], dtype=np.float64)
@@ -227,10 +228,11 @@ def make_base_agents(st, cfg):
         ov = int(st["override"][i])
         a.overriding_mode = {0: None, 1: "exploit", 3: "collide"}[ov]
         a.mode = mode_names[int(st["mode"][i])]
-        for k in DECISION_KEYS:
-            setattr(a, k, getattr(cfg, k))
-        a.max_exp_vel = cfg.exp_vel_max
-        a.exp_stop_ratio = cfg.exp_stop_ratio
+        if behave_params_list is None:   # else: the reference's own constructor took them from behave_params (agent.py:83-108)
+            for k in DECISION_KEYS:
+                setattr(a, k, getattr(cfg, k))
+            a.max_exp_vel = cfg.exp_vel_max
+            a.exp_stop_ratio = cfg.exp_stop_ratio
         agents.append(a)
     movement_params.exp_vel_max = cfg.exp_vel_max
     movement_params.exp_theta_min = cfg.exp_theta_min

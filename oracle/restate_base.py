@@ -214,17 +214,20 @@ def base_agent_update(i, st, cfg: BaseConfig, dtheta_random):
                 mode=mode, collected_before=st["collected"][i])
 
 
-def base_step_frozen(st, cfg: BaseConfig, dtheta_random, agents=None):
+def base_step_frozen(st, cfg: BaseConfig, dtheta_random, agents=None, agent_cfgs=None):
     """Synchronous agent phase (sims.py:861 with every agent seeing the same snapshot).
     st: dict with x, y, theta, vel, w, u (N,), novelty (N, Tau), env_status, override, mode,
-    patch_id (N,) ints, collected, collected_before (N,), radius (scalar)."""
+    patch_id (N,) ints, collected, collected_before (N,), radius (scalar).
+    ``agent_cfgs``: optional list of one BaseConfig per agent (heterogeneous agents, agent.py:83-108: the
+    behave_params entries replace the decision parameters, max_exp_vel and exp_stop_ratio of that agent;
+    the geometry fields must equal ``cfg``'s)."""
     N = len(st["x"])
     out = {k: np.array(st[k], copy=True) for k in ("x", "y", "theta", "vel", "w", "u", "override", "mode",
                                                    "collected_before")}
     out["I_priv"] = np.zeros(N)
     out["fields"] = np.zeros((N, cfg.R), bool)
     for i in (range(N) if agents is None else agents):
-        r = base_agent_update(i, st, cfg, dtheta_random[i])
+        r = base_agent_update(i, st, cfg if agent_cfgs is None else agent_cfgs[i], dtheta_random[i])
         out["fields"][i] = r["field"]
         for k in ("x", "y", "theta", "vel", "w", "u", "override", "mode", "collected_before", "I_priv"):
             out[k][i] = r[k]
@@ -244,7 +247,7 @@ def notify(st, i, status, res_id=None):
     st["patch_id"][i] = -1 if res_id is None else res_id
 
 
-def base_patch_phase(st, patches, cfg: BaseConfig, collided=()):
+def base_patch_phase(st, patches, cfg: BaseConfig, collided=(), agent_cfgs=None):
     """Agent-patch interaction of one time step, in place.  ``patches``: dict with arrays
     x, y (top-left), radius, left, quality, id (n_patch,).  Patches are visited in slot order,
     agents in index order (group order, sims.py:805-844).  Returns the list of depleted slots
@@ -271,7 +274,8 @@ def base_patch_phase(st, patches, cfg: BaseConfig, collided=()):
                     st["x"][i] = patches["x"][p] + patches["radius"][p] - r
                     st["y"][i] = patches["y"][p] + patches["radius"][p] - r
                 if st["override"][i] == OV_EXPLOIT:                               # :824
-                    take = min(cfg.agent_consumption, patches["quality"][p])      # rescource.py:121-122
+                    consumption = (cfg if agent_cfgs is None else agent_cfgs[i]).agent_consumption   # agent.consumption
+                    take = min(consumption, patches["quality"][p])                # rescource.py:121-122
                     if patches["left"][p] >= take:
                         patches["left"][p] -= take
                     else:
@@ -296,7 +300,7 @@ def base_patch_phase(st, patches, cfg: BaseConfig, collided=()):
 # collision phase (sims.py:736-783, 421-468; interactions.py:5-10)  -- PARITY UNPINNED
 # --------------------------------------------------------------------------------------
 
-def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool):
+def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool, agent_cfgs=None):
     """Agent-agent collision avoidance of one time step, in place.  Restated from the
     reference's control flow plus pygame's DOCUMENTED semantics (pygame itself is not in the
     reference tree, so this part cannot be pinned against reference output -- SURVEY 8c):
@@ -347,7 +351,7 @@ def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool):
             if amp * field[lo:hi].sum() > 0:                                      # :462-463
                 st["vel"][a2] = 0
             elif st["override"][a2] != OV_EXPLOIT:
-                st["vel"][a2] = cfg.exp_vel_max
+                st["vel"][a2] = (cfg if agent_cfgs is None else agent_cfgs[a2]).exp_vel_max   # agent2.max_exp_vel (:465)
         for a2 in partners:                                                       # sims.py:759-776
             e1, e2 = st["override"][a1] == OV_EXPLOIT, st["override"][a2] == OV_EXPLOIT
             if cfg.teleport_exploit:

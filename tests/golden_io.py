@@ -78,3 +78,31 @@ def load_cs_cases():
                           mps=None if s[7] < 0 else float(s[7]), objs=z[p + "objs"],
                           meters=None if meters.size == 0 else meters, rows=z[p + "rows"]))
     return cases
+
+
+def load_base_hetero_cases():
+    """tests/golden/base_hetero_golden.npz (make_golden_hetero.py): heterogeneous agents, the per-agent
+    parameters went through the reference's own constructor (agent.py:83-108).  ``agent_cfgs``: one
+    BaseConfig per agent; ``agent_params``: dict name -> (N,) array."""
+    import dataclasses
+    from oracle import restate_base as rb
+    z = np.load(os.path.join(GOLDEN, "base_hetero_golden.npz"))
+    keys = [str(k) for k in z["agent_keys"]]
+    cases = []
+    for c in range(int(z["n_cases"])):
+        p = f"c{c}_"
+        vals = dict(zip(BASE_CFG_KEYS, z[p + "cfg"]))
+        for k in ("R", "Tau"):
+            vals[k] = int(vals[k])
+        for k in ("visual_exclusion", "patchwise_exclusion"):
+            vals[k] = bool(vals[k])
+        cfg = rb.BaseConfig(fov=tuple(z[p + "fov"]), **vals)
+        tab = z[p + "agent_params"]
+        agent_params = {k: tab[:, j] for j, k in enumerate(keys)}
+        agent_cfgs = [dataclasses.replace(cfg, **{k: float(agent_params[k][i]) for k in keys})
+                      for i in range(tab.shape[0])]
+        st = {k: z[p + "st_" + k] for k in BASE_STATE_KEYS}
+        st["radius"] = 10.0
+        cases.append(dict(cfg=cfg, st=st, dth=z[p + "dth"], fields=z[p + "fields"], agent_cfgs=agent_cfgs,
+                          agent_params=agent_params, out={k: z[p + "out_" + k] for k in BASE_OUT_KEYS}))
+    return cases

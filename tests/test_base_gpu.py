@@ -4,7 +4,7 @@ Fields: bit-exact.  Scalars (w, u, velocity, heading, position): 1e-5 relative (
 import numpy as np
 import pytest
 
-from golden_io import BASE_OUT_KEYS, load_base_cases
+from golden_io import BASE_OUT_KEYS, load_base_cases, load_base_hetero_cases
 from oracle import restate as rs
 from oracle import restate_base as rb
 
@@ -56,6 +56,78 @@ def test_agent_phase_matches_reference_fixture(built_lib, case):
     eng.step(1, inject_dtheta=case["dth"], phases=PHASE_AGENTS)
     assert np.array_equal(rs.pack_bits(eng.fields()[0]), case["fields"])          # bit-exact stored fields
     _compare_agents(eng.get_agents(), case["out"])
+    eng.close()
+
+
+@pytest.mark.parametrize("case", load_base_hetero_cases(), ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_agent_phase_matches_reference_fixture_heterogeneous_agents(built_lib, case):
+    """One parameter set per agent (agent_behave_param_list, sims.py:499-517; agent.py:83-108); the fixture went
+    through the reference's own constructor.  Two replicates: the second gets the agents' sets in reverse order,
+    so that the (replicate, agent) indexing of the table is exercised."""
+    cfg, st = case["cfg"], case["st"]
+    N = len(case["dth"])
+    eng = _engine_for(cfg, 2, N)
+    eng.set_params(exp_theta_min=cfg.exp_theta_min, exp_theta_max=cfg.exp_theta_max,
+                   reloc_theta_max=cfg.reloc_theta_max,
+                   **{k: np.stack([v, v[::-1]]) for k, v in case["agent_params"].items()})
+    two = {k: np.stack([np.asarray(v), np.asarray(v)]) for k, v in st.items() if k != "radius"}
+    eng.set_agents(x=two["x"], y=two["y"], theta=two["theta"], vel=two["vel"], w=two["w"], u=two["u"],
+                   collected=two["collected"], collected_before=two["collected_before"],
+                   env_status=two["env_status"], override_mode=two["override"], mode=two["mode"],
+                   patch_id=two["patch_id"], novelty=two["novelty"])
+    eng.step(1, inject_dtheta=np.stack([case["dth"], case["dth"]]), phases=PHASE_AGENTS)
+    got = eng.get_agents()
+    assert np.array_equal(rs.pack_bits(eng.fields()[0]), case["fields"])          # bit-exact stored fields
+    _compare_agents(got, case["out"], 0)
+    ref1 = rb.base_step_frozen(st, cfg, case["dth"], agent_cfgs=case["agent_cfgs"][::-1])
+    _compare_agents(got, ref1, 1)
+    assert not np.allclose(got["w"][0], got["w"][1])
+    eng.close()
+
+
+def test_env_phase_with_per_agent_consumption(built_lib):
+    """agent.consumption in the depletion order (sims.py:824-828, rescource.py:118-133), one parameter set per
+    agent, against the oracle."""
+    import dataclasses
+    from abm_b200 import BaseEngine
+    rng = np.random.default_rng(18)
+    B, N, P, W = 3, 40, 3, 300.0
+    cfg = rb.BaseConfig(R=320, width=W, height=W, vision_range=2000.0, visual_exclusion=True)
+    cons = rng.choice([0.25, 0.5, 1.0, 2.0], (B, N))
+    vmax = np.asarray(rng.uniform(1, 4, (B, N)), np.float32).astype(np.float64)
+    eng = BaseEngine(B, N, P, resolution=320, width=W, height=W, regenerate_patches=False, tau=cfg.Tau,
+                     vision_range=2000.0, visual_exclusion=True, collide_agents=True, ghost_mode=False)
+    eng.set_params(agent_consumption=cons, exp_vel_max=vmax)
+    states, patches = [], []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 1], N); st["mode"] = st["override"].copy()
+        states.append(st)
+        patches.append(dict(x=np.array([40.0, 150.0, 230.0]), y=np.array([50.0, 160.0, 60.0]),
+                            radius=np.array([45.0, 40.0, 35.0]), left=np.array([2.5, 400.0, 0.5]),
+                            quality=np.array([0.75, 1.5, 1.0]), id=np.array([0, 1, 2])))
+    S = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    Pm = {k: np.stack([p[k] for p in patches]) for k in patches[0]}
+    eng.set_agents(x=S["x"], y=S["y"], theta=S["theta"], vel=S["vel"], w=S["w"], u=S["u"], collected=S["collected"],
+                   collected_before=S["collected_before"], env_status=S["env_status"], override_mode=S["override"],
+                   mode=S["mode"], patch_id=S["patch_id"], novelty=S["novelty"])
+    eng.set_patches(**Pm)
+    eng.step(1, phases=PHASE_ENV)
+    got, gp = eng.get_agents(), eng.get_patches()
+    takes = set()
+    for b in range(B):
+        acfg = [dataclasses.replace(cfg, agent_consumption=float(cons[b, i]), exp_vel_max=float(vmax[b, i]))
+                for i in range(N)]
+        st = {k: (np.array(v, dtype=float) if k in ("theta", "collected", "collected_before") else np.array(v))
+              for k, v in states[b].items()}
+        before = st["collected"].copy()
+        rb.base_patch_phase(st, patches[b], cfg, agent_cfgs=acfg)
+        takes |= set(np.round(st["collected"] - before, 6).tolist())
+        np.testing.assert_allclose(got["collected"][b], st["collected"], rtol=RTOL)
+        np.testing.assert_allclose(got["collected_before"][b], st["collected_before"], rtol=RTOL)
+        np.testing.assert_allclose(gp["left"][b], patches[b]["left"], rtol=RTOL, atol=1e-6)
+        assert np.array_equal(got["env_status"][b], st["env_status"])
+    assert len(takes) >= 4          # several different amounts were taken: the per-agent consumption is in use
     eng.close()
 
 
@@ -256,6 +328,41 @@ def test_collision_phase_matches_oracle(built_lib, ghost, teleport, vis_excl):
         assert np.array_equal(got["env_status"][b], st["env_status"])
         assert np.array_equal(got["patch_id"][b], st["patch_id"])
     assert n_coll > 10
+    eng.close()
+
+
+def test_collision_phase_with_per_agent_max_exp_vel(built_lib):
+    """agent2.velocity = agent2.max_exp_vel (sims.py:465) with one parameter set per agent."""
+    import dataclasses
+    from abm_b200 import BaseEngine
+    rng = np.random.default_rng(77)
+    B, N, W = 3, 40, 200.0
+    cfg = rb.BaseConfig(R=1200, width=W, height=W, visual_exclusion=True)
+    vmax = np.asarray(rng.uniform(1, 4, (B, N)), np.float32).astype(np.float64)
+    eng = BaseEngine(B, N, 0, resolution=1200, width=W, height=W, visual_exclusion=True, collide_agents=True,
+                     ghost_mode=False, tau=cfg.Tau)
+    eng.set_params(exp_vel_max=vmax)
+    states = []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 0, 1, 3], N)
+        st["mode"] = st["override"].copy()
+        states.append(st)
+    S = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    eng.set_agents(x=S["x"], y=S["y"], theta=S["theta"], vel=S["vel"], w=S["w"], u=S["u"], collected=S["collected"],
+                   collected_before=S["collected_before"], env_status=S["env_status"], override_mode=S["override"],
+                   mode=S["mode"], patch_id=S["patch_id"], novelty=S["novelty"])
+    eng.step(1, phases=4)     # collision phase only
+    got = eng.get_agents()
+    n_set = 0
+    for b in range(B):
+        acfg = [dataclasses.replace(cfg, exp_vel_max=float(vmax[b, i])) for i in range(N)]
+        st = {k: (np.array(v, dtype=float) if k in ("theta", "vel") else np.array(v)) for k, v in states[b].items()}
+        rb.base_collision_phase(st, cfg, ghost_mode=False, agent_cfgs=acfg)
+        np.testing.assert_allclose(got["theta"][b], st["theta"], rtol=RTOL, err_msg="theta")
+        np.testing.assert_allclose(got["vel"][b], st["vel"], rtol=RTOL, atol=1e-6, err_msg="vel")
+        n_set += int(np.isclose(st["vel"], vmax[b]).sum())
+    assert n_set > 3          # some agents were sent straight on with their own max_exp_vel
     eng.close()
 
 

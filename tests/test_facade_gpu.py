@@ -55,6 +55,40 @@ def test_simulation_facade_runs(built_lib):
     assert sim.rescources[0].radius == 30.0 and sim.rescources[0].resc_left <= 101
 
 
+def _behave_template(**over):
+    """contrib/evolution.py:1-26."""
+    d = dict(S_wu=0, T_w=0.5, Eps_w=0, g_w=0.085, B_w=0, w_max=1, Tau=10, S_uw=0, T_u=0.5, Eps_u=3, g_u=0.085, B_u=0,
+             u_max=1, F_N=2, F_R=1, exp_vel_max=3, exp_stop_ratio=0.15, agent_radius=10, v_field_res=1200,
+             pooling_time=0, pooling_prob=0, agent_consumption=1, vision_range=2000, agent_fov=0.9,
+             evo_summary_path=None)
+    d.update(over)
+    return d
+
+
+def test_simulation_facade_heterogeneous_agents(built_lib):
+    """agent_behave_param_list (sims.py:170-173, 499-517): the dictionaries' geometry replaces the constructor's,
+    their decision entries become one parameter set per agent.  Agents whose Eps_u is 0 never reach the
+    exploitation threshold, so only the others can collect."""
+    from abm_b200.simulation import Simulation
+    N = 12
+    plist = [_behave_template(Eps_u=0.0 if i % 2 else 3.0, exp_vel_max=2.0 + 0.1 * i) for i in range(N)]
+    sim = Simulation(N=N, T=400, v_field_res=320, width=300, height=300, N_resc=3, patch_radius=40,
+                     min_resc_perpatch=500, max_resc_perpatch=-1, min_resc_quality=0.25, max_resc_quality=-1,
+                     vision_range=150, agent_fov=0.5, visual_exclusion=True, teleport_exploit=False,
+                     allow_border_patch_overlap=True, collide_agents=False, n_replicates=8, seed=11,
+                     agent_behave_param_list=plist)
+    assert sim.heterogen_agents and sim.engine.R == 1200            # v_field_res / fov / range from the list
+    sim.start()
+    a = sim.engine.get_agents()
+    assert np.isfinite(a["x"]).all()
+    assert (a["collected"][:, 1::2] == 0).all()                     # Eps_u = 0: u stays at its baseline
+    assert (a["collected"][:, 0::2] > 0).any()
+    explore = a["mode"] == 0
+    vmax = np.array([p["exp_vel_max"] for p in plist])
+    v = np.abs(a["vel"])
+    assert np.allclose(v[explore], np.broadcast_to(vmax, v.shape)[explore], rtol=1e-6)   # own max_exp_vel
+
+
 def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
     from abm_b200 import metarunner as mr
     env = dict(N="12", T="20", VISUAL_FIELD_RESOLUTION="1200", ENV_WIDTH="400", ENV_HEIGHT="400", RADIUS_AGENT="10",

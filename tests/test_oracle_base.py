@@ -4,7 +4,7 @@ and, when /root/reference is mounted, the reference's own notify / deplete / bia
 import numpy as np
 import pytest
 
-from golden_io import BASE_OUT_KEYS, load_base_cases
+from golden_io import BASE_OUT_KEYS, load_base_cases, load_base_hetero_cases
 from oracle import ref_shim
 from oracle import restate as rs
 from oracle import restate_base as rb
@@ -49,6 +49,19 @@ def test_restatement_matches_reference_fixture(case):
     assert np.array_equal(rs.pack_bits(out["fields"]), case["fields"])
     for k in BASE_OUT_KEYS:
         np.testing.assert_allclose(out[k], case["out"][k], rtol=1e-12, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.parametrize("case", load_base_hetero_cases(), ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_restatement_matches_reference_fixture_heterogeneous_agents(case):
+    """agent_behave_param_list (sims.py:499-517): per-agent decision parameters, max_exp_vel, exp_stop_ratio taken
+    by the reference's own constructor (agent.py:83-108)."""
+    out = rb.base_step_frozen(case["st"], case["cfg"], case["dth"], agent_cfgs=case["agent_cfgs"])
+    assert np.array_equal(rs.pack_bits(out["fields"]), case["fields"])
+    for k in BASE_OUT_KEYS:
+        np.testing.assert_allclose(out[k], case["out"][k], rtol=1e-12, atol=1e-12, err_msg=k)
+    # the fixture must not be reproducible with one shared parameter set
+    shared = rb.base_step_frozen(case["st"], case["agent_cfgs"][0], case["dth"])
+    assert not np.allclose(shared["w"], case["out"]["w"]) and not np.allclose(shared["vel"], case["out"]["vel"])
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
