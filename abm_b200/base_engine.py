@@ -32,6 +32,7 @@ class BaseEngine:
         self._lib = _lib.load()
         self.B, self.N, self.P, self.R = int(n_replicates), int(n_agents), int(n_patches), int(resolution)
         self.W = (self.R + 31) // 32
+        self._agent_fov, self._vision_range = float(agent_fov), float(vision_range)
         self.tau = int(tau)
         # "negative maximum = use the minimum" rule of sims.py:176-179
         if max_resc_quality < 0:
@@ -96,6 +97,24 @@ class BaseEngine:
             vals = [np.broadcast_to(v.reshape(-1), (n,)) for v in vals]
         tab = np.ascontiguousarray(np.stack(vals, axis=1))
         _lib.check(self._lib.abm_base_set_params(self._h, C.c_void_p(tab.ctypes.data), n), "abm_base_set_params")
+
+    def set_agent_geometry(self, agent_fov=None, vision_range=None):
+        """Per-agent FOV (as the fraction of pi the reference's AGENT_FOV is) and vision range, (B, N) or (N,)
+        arrays (heterogeneous agents, sims.py:499-517); None keeps the engine-wide value of the constructor.
+        Calling it without arguments returns to the engine-wide values."""
+        if agent_fov is None and vision_range is None:
+            _lib.check(self._lib.abm_base_set_agent_geometry(self._h, None, None, None, 0),
+                       "abm_base_set_agent_geometry")
+            return
+        shape = (self.B, self.N)
+        fov = np.broadcast_to(np.asarray(self._agent_fov if agent_fov is None else agent_fov, np.float64), shape)
+        vr = np.ascontiguousarray(np.broadcast_to(
+            np.asarray(self._vision_range if vision_range is None else vision_range, np.float64), shape))
+        f0 = np.ascontiguousarray(-fov * np.pi)                                    # sims.py:506
+        f1 = np.ascontiguousarray(fov * np.pi)
+        _lib.check(self._lib.abm_base_set_agent_geometry(
+            self._h, C.c_void_p(f0.ctypes.data), C.c_void_p(f1.ctypes.data), C.c_void_p(vr.ctypes.data),
+            self.B * self.N), "abm_base_set_agent_geometry")
 
     # -- state -----------------------------------------------------------------------------
     def _fill(self, struct_cls, fields, arrays, count, keep):

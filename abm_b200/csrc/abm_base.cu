@@ -211,6 +211,12 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
   const double r = a.radius;
   const FocalExact fe = vf_focal_exact(xi_f, yi_f, (float)a.radius, a.ag.theta[gi]);   // same v1 construction (agent.py:484-495)
   const int my_patch = a.ag.patch_id[gi];
+  double fov0 = a.fov0, fov1 = a.fov1, vision_range = a.vision_range;
+  int mask_lo = a.mask_lo, mask_hi = a.mask_hi;
+  if (a.agent_geo) {                                                                // this agent's own FOV / range
+    const BaseAgentGeo g = a.agent_geo[gi];
+    fov0 = g.fov0; fov1 = g.fov1; vision_range = g.vision_range; mask_lo = g.mask_lo; mask_hi = g.mask_hi;
+  }
 
   // ---- candidates, classes, raw intervals (agent.py:396-419, 497-556) ----
   int M = 0;
@@ -223,7 +229,7 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
       const size_t gj = a0 + j;
       const float xj_f = a.ag.snap_x[gj], yj_f = a.ag.snap_y[gj];
       const double n2 = base_centre_distance(fe, r, xj_f, yj_f);
-      const bool in_range = n2 <= a.vision_range;                                   // agent.py:400
+      const bool in_range = n2 <= vision_range;                                     // agent.py:400
       const bool is_expl = (j != i) && (a.ag.snap_override[gj] == OV_EXPLOIT);      // :402-403
       int cls = 0;   // 0 none, 1 social, 2 occluder (other), 3 occluder (same-patch exploiter)
       if (in_range) {
@@ -238,7 +244,7 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
       if (!a.visual_exclusion && cls != 1) cls = 0;                                 // :415-419
       if (cls != 0) {
         double dist;
-        rec = base_interval(fe, r, xi_f, yi_f, xj_f, yj_f, a.fov0, a.fov1, R, a.lin_step, o, dist);
+        rec = base_interval(fe, r, xi_f, yi_f, xj_f, yj_f, fov0, fov1, R, a.lin_step, o, dist);
         // list order of the reference: social cues, then other occluders, then same-patch
         // exploiters, each in agent order (agent.py:402-410, 472-477)
         k2 = (((cls == 1) ? 0 : (cls == 2 ? 1 : 2)) * N + j) | ((cls == 1) ? (1 << 30) : 0);
@@ -252,14 +258,14 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
 
   // ---- flip + FOV mask (agent.py:593-595): stored[b] = v[R-1-b], kept for b in [mask_lo, mask_hi] ----
   const int h = R / 2;                                       // int(V_field_len / 2) (supcalc.py:86-88)
-  const int va = R - 1 - a.mask_hi, vb = R - a.mask_lo;      // kept bins in v coordinates [va, vb)
+  const int va = R - 1 - mask_hi, vb = R - mask_lo;          // kept bins in v coordinates [va, vb)
   n_left_out = popc_range(row, W, max(va, R - h), min(vb, R), lane);    // stored[0:h]  <-> v[R-h:R]
   n_right_out = popc_range(row, W, max(va, 0), min(vb, R - h), lane);   // stored[h:]   <-> v[0:R-h]
   if (a.fields_out) {
     uint32_t* out = a.fields_out + gi * W;
     for (int ws = lane; ws < W; ws += 32) {
       uint32_t word = flipped_word(row, 1, R, W, ws);
-      const int lo = max(a.mask_lo - (ws << 5), 0), hi = min(a.mask_hi + 1 - (ws << 5), 32);
+      const int lo = max(mask_lo - (ws << 5), 0), hi = min(mask_hi + 1 - (ws << 5), 32);
       uint32_t m = 0u;
       if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
       out[ws] = word & m;
@@ -471,7 +477,8 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
           flo = min(flo, R); fhi = min(fhi, R);
           const int n_front = (fhi > flo) ? popc_range(wf.row, W, R - fhi, R - flo, lane) : 0;
           if (lane == 0) {
-            const double amp = (last_j >= 0) ? 1.0 - last_d / a.vision_range : 1.0;
+            const double vr2 = a.agent_geo ? a.agent_geo[a0 + a2].vision_range : a.vision_range;   // agent2's own
+            const double amp = (last_j >= 0) ? 1.0 - last_d / vr2 : 1.0;
             const double left = amp * (double)n_left / (double)h, right = amp * (double)n_right / (double)(R - h);
             double D = (left > right) ? 1.0 : ((left < right) ? -1.0 : 0.0);
             if (D == 0.0) D = -1.0;                                                  // :456

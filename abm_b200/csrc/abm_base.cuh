@@ -35,6 +35,13 @@ struct BasePatchPtrs {
   int32_t* id;
 };
 
+// Per-agent field geometry (heterogeneous agents, sims.py:499-517: FOV and vision_range are constructor arguments of
+// every agent): FOV in radians, vision range, and the stored bins the FOV mask keeps (agent.py:594-595).
+struct BaseAgentGeo {
+  double fov0, fov1, vision_range;
+  int mask_lo, mask_hi;
+};
+
 struct BaseKernelArgs {
   int B, N, P, R, W, Tau;
   int visual_exclusion, patchwise_exclusion, teleport_exploit, regenerate, border_overlap, ghost_mode;
@@ -53,6 +60,7 @@ struct BaseKernelArgs {
   int param_stride;            // doubles between the sets of consecutive replicates: 0, kBaseNParam or N * kBaseNParam
   int param_stride_agent;      // doubles between the sets of consecutive agents: 0, or kBaseNParam with one set per
                                // agent (heterogeneous agents: agent.py:83-108 behave_params, sims.py:499-517)
+  const BaseAgentGeo* agent_geo;   // nullable, B*N: replaces fov0 / fov1 / mask_lo / mask_hi / vision_range per focal agent
   const float* inject_dtheta;  // nullable, B*N: replaces the random-walk draw (parity tests)
   uint32_t* fields_out;        // nullable, B*N*W, stored order
   unsigned long long* counters;   // [0] patches regenerated, [1] regeneration retries exhausted

@@ -1,6 +1,8 @@
 // C ABI of the BASE / collective-foraging engine (declared in include/abm_b200.h).
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <utility>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,6 +24,8 @@ struct abm_base_engine {
   DevBuf<float> px, py, pradius, pleft, pquality;
   DevBuf<int32_t> pid;
   DevBuf<double> params;
+  DevBuf<abm::BaseAgentGeo> agent_geo;   // B*N once abm_base_set_agent_geometry was called
+  bool has_agent_geo = false;
   DevBuf<float> inject;
   DevBuf<unsigned long long> counters;
   DevBuf<unsigned int> mode_steps;      // B*4, see BaseKernelArgs
@@ -136,7 +140,7 @@ int abm_base_destroy(abm_base_engine_t* e) {
                            &e->pquality}) b->release();
   for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid,
                              &e->collided}) b->release();
-  e->novelty.release(); e->fields.release(); e->params.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
+  e->novelty.release(); e->fields.release(); e->params.release(); e->agent_geo.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
   delete e;
   return ABM_OK;
 }
@@ -160,6 +164,36 @@ static int agents_xfer(abm_base_engine_t* e, const abm_base_agents_t* s, bool to
   F(collected_before, collected_before) F(i_priv, i_priv) F(env_status, env_status)
   F(override_mode, override_mode) F(mode, mode) F(patch_id, patch_id) F(novelty, novelty)
 #undef F
+  return ABM_OK;
+}
+
+int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const double* fov1,
+                                const double* vision_range, int n) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: null engine");
+  if (n == 0) { e->has_agent_geo = false; return ABM_OK; }   // back to the engine-wide values
+  if (!fov0 || !fov1 || !vision_range) return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: null argument");
+  if ((size_t)n != e->n_agents_total)
+    return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: n must be n_replicates * n_agents (or 0)");
+  const int R = e->cfg.resolution;
+  std::vector<abm::BaseAgentGeo> geo((size_t)n);
+  std::map<std::pair<double, double>, std::pair<int, int>> masks;   // few distinct FOVs: one O(R) scan each
+  for (int i = 0; i < n; ++i) {
+    const std::pair<double, double> key(fov0[i], fov1[i]);
+    auto it = masks.find(key);
+    if (it == masks.end()) {
+      int lo = R, hi = -1;   // FOV mask in stored coordinates (agent.py:594-595) on the numpy linspace grid
+      for (int k = 0; k < R; ++k) {
+        const double phi = (k == R - 1) ? ABM_PI_D : ((double)k * e->lin_step + (-ABM_PI_D));
+        if (!(phi < fov0[i]) && !(phi > fov1[i])) { if (k < lo) lo = k; if (k > hi) hi = k; }
+      }
+      it = masks.emplace(key, std::make_pair(lo, hi)).first;
+    }
+    geo[i] = abm::BaseAgentGeo{fov0[i], fov1[i], vision_range[i], it->second.first, it->second.second};
+  }
+  ABM_CUDA(cudaSetDevice(e->device));
+  if (!e->agent_geo.p) ABM_CUDA(e->agent_geo.alloc((size_t)n));
+  ABM_CUDA(cudaMemcpy(e->agent_geo.p, geo.data(), sizeof(abm::BaseAgentGeo) * (size_t)n, cudaMemcpyHostToDevice));
+  e->has_agent_geo = true;
   return ABM_OK;
 }
 
@@ -239,6 +273,7 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
                             e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p};
   a.pa = abm::BasePatchPtrs{e->px.p, e->py.p, e->pradius.p, e->pleft.p, e->pquality.p, e->pid.p};
   a.params = e->params.p;
+  a.agent_geo = e->has_agent_geo ? e->agent_geo.p : nullptr;
   if (e->n_param_sets == 1) { a.param_stride = 0; a.param_stride_agent = 0; }
   else if (e->n_param_sets == e->cfg.n_replicates && e->cfg.n_agents != 1) { a.param_stride = abm::kBaseNParam; a.param_stride_agent = 0; }
   else { a.param_stride = e->cfg.n_agents * abm::kBaseNParam; a.param_stride_agent = abm::kBaseNParam; }

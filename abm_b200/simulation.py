@@ -251,8 +251,8 @@ class Simulation:
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
         self.heterogen_agents = agent_behave_param_list is not None                # sims.py:170-173
         if self.heterogen_agents:
-            agent_radius, v_field_res, agent_fov, vision_range = self._check_behave_params(
-                agent_behave_param_list, int(N), agent_radius, v_field_res, agent_fov, vision_range,
+            agent_radius, v_field_res = self._check_behave_params(
+                agent_behave_param_list, int(N), agent_radius, v_field_res,
                 (decision_params or DecisionParams()).Tau)
         self.agent_behave_param_list = agent_behave_param_list
         self.N, self.T, self.t = int(N), int(T), 0
@@ -285,6 +285,10 @@ class Simulation:
             for key in self._BEHAVE_DECISION_KEYS + ("exp_vel_max", "exp_stop_ratio", "agent_consumption"):
                 row = np.array([float(bp[key]) for bp in agent_behave_param_list], np.float64)
                 prm[key] = np.broadcast_to(row, (self.B, self.N)).copy()
+            # sims.py:506, 511: every agent is constructed with its own FOV and vision_range
+            self.engine.set_agent_geometry(
+                agent_fov=np.array([float(bp["agent_fov"]) for bp in agent_behave_param_list]),
+                vision_range=np.array([float(bp["vision_range"]) for bp in agent_behave_param_list]))
         self.engine.set_params(**prm)
         self.agents, self.rescources = [], []
         self._a = self._p = self._f = None
@@ -293,27 +297,26 @@ class Simulation:
                              "u_max", "F_N", "F_R")
 
     @staticmethod
-    def _check_behave_params(plist, N, agent_radius, v_field_res, agent_fov, vision_range, tau):
+    def _check_behave_params(plist, N, agent_radius, v_field_res, tau):
         """agent_behave_param_list (sims.py:499-517, template: contrib/evolution.py:1-26): the decision / movement
-        entries and agent_consumption may differ between agents; the geometry entries (agent_radius, v_field_res,
-        agent_fov, vision_range), Tau and pooling must be the same for all agents (they are engine-wide) and then
-        replace the constructor's values like the reference does."""
+        entries, agent_consumption, agent_fov and vision_range may differ between agents; agent_radius, v_field_res,
+        Tau and pooling must be the same for all agents (they are engine-wide) and then replace the constructor's
+        values like the reference does."""
         if len(plist) != N:
             raise ValueError("agent_behave_param_list must hold one dictionary per agent")
         geo = []
-        for key, default in (("agent_radius", agent_radius), ("v_field_res", v_field_res), ("agent_fov", agent_fov),
-                             ("vision_range", vision_range)):
+        for key, default in (("agent_radius", agent_radius), ("v_field_res", v_field_res)):
             vals = {float(bp.get(key, default)) for bp in plist}
             if len(vals) != 1:
                 raise NotImplementedError(f"agent_behave_param_list: '{key}' must be the same for all agents "
-                                          "(per-agent geometry is not supported, SURVEY f4)")
+                                          "(per-agent radius / resolution is not supported, SURVEY f4)")
             geo.append(vals.pop())
         if any(int(bp.get("Tau", tau)) != int(tau) for bp in plist):
             raise NotImplementedError("agent_behave_param_list: 'Tau' must equal decision_params.Tau for all agents")
         if any(float(bp.get("pooling_time", 0)) != 0 for bp in plist):
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
         radius = geo[0]
-        return (int(radius) if radius.is_integer() else radius), int(geo[1]), geo[2], geo[3]
+        return (int(radius) if radius.is_integer() else radius), int(geo[1])
 
     def create_agents(self):
         """sims.py:526-537: integer positions, heading ~ U(0, 2pi)."""

@@ -303,8 +303,14 @@ int abm_base_destroy(abm_base_engine_t* e);
 /* params: n_sets * ABM_BASE_NPARAM doubles.  n_sets = 1 (one set for the batch), n_replicates (one per replicate:
  * parameter sweeps) or n_replicates * n_agents (one per agent, replicate-major: heterogeneous agents, the
  * behave_params of agent.py:83-108 / agent_behave_param_list of sims.py:499-517 -- decision parameters,
- * exp_vel_max, exp_stop_ratio, agent_consumption; radius, resolution, FOV and vision range stay per engine). */
+ * exp_vel_max, exp_stop_ratio, agent_consumption; FOV and vision range: abm_base_set_agent_geometry). */
 int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets);
+/* Per-agent field geometry of heterogeneous agents (sims.py:499-517: every Agent gets its own FOV and vision_range):
+ * fov0 / fov1 in radians (the reference's (-agent_fov * pi, agent_fov * pi)) and vision_range, n = n_replicates *
+ * n_agents values each, replicate-major, host pointers.  n = 0 returns to the engine-wide values of the config.
+ * Radius and resolution stay per engine. */
+int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const double* fov1,
+                                const double* vision_range, int n);
 int abm_base_set_agents(abm_base_engine_t* e, const abm_base_agents_t* src, int on_device, void* stream);
 int abm_base_get_agents(abm_base_engine_t* e, const abm_base_agents_t* dst, int on_device, void* stream);
 int abm_base_set_patches(abm_base_engine_t* e, const abm_base_patches_t* src, int on_device, void* stream);

@@ -213,9 +213,12 @@ def make_base_agents(st, cfg, behave_params_list=None):
     for i in range(N):
         a = agent_mod.Agent(
             id=i, radius=rad, position=(float(st["x"][i]), float(st["y"][i])), orientation=float(st["theta"][i]),
-            env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0), v_field_res=cfg.R, FOV=tuple(cfg.fov),
+            env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0), v_field_res=cfg.R,
+            FOV=tuple(cfg.fov) if behave_params_list is None else                      # sims.py:506
+            (-float(behave_params_list[i]["agent_fov"]) * np.pi, float(behave_params_list[i]["agent_fov"]) * np.pi),
             window_pad=int(cfg.window_pad), pooling_time=0, pooling_prob=0, consumption=cfg.agent_consumption,
-            vision_range=cfg.vision_range, visual_exclusion=cfg.visual_exclusion,
+            vision_range=cfg.vision_range if behave_params_list is None else behave_params_list[i]["vision_range"],
+            visual_exclusion=cfg.visual_exclusion,
             patchwise_exclusion=cfg.patchwise_exclusion,
             behave_params=None if behave_params_list is None else behave_params_list[i])
         a.velocity = float(st["vel"][i])

@@ -99,8 +99,11 @@ def load_base_hetero_cases():
         cfg = rb.BaseConfig(fov=tuple(z[p + "fov"]), **vals)
         tab = z[p + "agent_params"]
         agent_params = {k: tab[:, j] for j, k in enumerate(keys)}
-        agent_cfgs = [dataclasses.replace(cfg, **{k: float(agent_params[k][i]) for k in keys})
-                      for i in range(tab.shape[0])]
+        agent_cfgs = []
+        for i in range(tab.shape[0]):
+            kw = {k: float(agent_params[k][i]) for k in keys if k != "agent_fov"}
+            f = float(agent_params["agent_fov"][i])
+            agent_cfgs.append(dataclasses.replace(cfg, fov=(-f * np.pi, f * np.pi), **kw))      # sims.py:506
         st = {k: z[p + "st_" + k] for k in BASE_STATE_KEYS}
         st["radius"] = 10.0
         cases.append(dict(cfg=cfg, st=st, dth=z[p + "dth"], fields=z[p + "fields"], agent_cfgs=agent_cfgs,

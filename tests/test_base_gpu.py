@@ -61,15 +61,17 @@ def test_agent_phase_matches_reference_fixture(built_lib, case):
 
 @pytest.mark.parametrize("case", load_base_hetero_cases(), ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
 def test_agent_phase_matches_reference_fixture_heterogeneous_agents(built_lib, case):
-    """One parameter set per agent (agent_behave_param_list, sims.py:499-517; agent.py:83-108); the fixture went
-    through the reference's own constructor.  Two replicates: the second gets the agents' sets in reverse order,
+    """One parameter set per agent (agent_behave_param_list, sims.py:499-517; agent.py:83-108) and, in the last two
+    cases, the agent's own FOV and vision range; the fixture went through the reference's own constructor.  Two replicates: the second gets the agents' sets in reverse order,
     so that the (replicate, agent) indexing of the table is exercised."""
     cfg, st = case["cfg"], case["st"]
     N = len(case["dth"])
     eng = _engine_for(cfg, 2, N)
+    geo = ("agent_fov", "vision_range")
     eng.set_params(exp_theta_min=cfg.exp_theta_min, exp_theta_max=cfg.exp_theta_max,
                    reloc_theta_max=cfg.reloc_theta_max,
-                   **{k: np.stack([v, v[::-1]]) for k, v in case["agent_params"].items()})
+                   **{k: np.stack([v, v[::-1]]) for k, v in case["agent_params"].items() if k not in geo})
+    eng.set_agent_geometry(**{k: np.stack([case["agent_params"][k], case["agent_params"][k][::-1]]) for k in geo})
     two = {k: np.stack([np.asarray(v), np.asarray(v)]) for k, v in st.items() if k != "radius"}
     eng.set_agents(x=two["x"], y=two["y"], theta=two["theta"], vel=two["vel"], w=two["w"], u=two["u"],
                    collected=two["collected"], collected_before=two["collected_before"],
@@ -82,6 +84,19 @@ def test_agent_phase_matches_reference_fixture_heterogeneous_agents(built_lib, c
     ref1 = rb.base_step_frozen(st, cfg, case["dth"], agent_cfgs=case["agent_cfgs"][::-1])
     _compare_agents(got, ref1, 1)
     assert not np.allclose(got["w"][0], got["w"][1])
+    assert np.array_equal(eng.fields()[1], ref1["fields"])
+    if len(set(case["agent_params"]["agent_fov"])) > 1:                   # back to the engine-wide geometry
+        eng.set_agent_geometry()
+        eng.set_agents(x=two["x"], y=two["y"], theta=two["theta"], vel=two["vel"], w=two["w"], u=two["u"],
+                       collected=two["collected"], collected_before=two["collected_before"],
+                       env_status=two["env_status"], override_mode=two["override"], mode=two["mode"],
+                       patch_id=two["patch_id"], novelty=two["novelty"])
+        eng.step(1, inject_dtheta=np.stack([case["dth"], case["dth"]]), phases=PHASE_AGENTS)
+        import dataclasses
+        same_geo = [dataclasses.replace(c, fov=cfg.fov, vision_range=cfg.vision_range) for c in case["agent_cfgs"]]
+        ref2 = rb.base_step_frozen(st, cfg, case["dth"], agent_cfgs=same_geo)
+        assert np.array_equal(eng.fields()[0], ref2["fields"])
+        assert not np.array_equal(rs.pack_bits(ref2["fields"]), case["fields"])   # the geometry mattered
     eng.close()
 
 

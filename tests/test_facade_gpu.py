@@ -71,7 +71,8 @@ def test_simulation_facade_heterogeneous_agents(built_lib):
     exploitation threshold, so only the others can collect."""
     from abm_b200.simulation import Simulation
     N = 12
-    plist = [_behave_template(Eps_u=0.0 if i % 2 else 3.0, exp_vel_max=2.0 + 0.1 * i) for i in range(N)]
+    plist = [_behave_template(Eps_u=0.0 if i % 2 else 3.0, exp_vel_max=2.0 + 0.1 * i, agent_fov=0.5 + 0.04 * i,
+                              vision_range=100 + 50 * i) for i in range(N)]
     sim = Simulation(N=N, T=400, v_field_res=320, width=300, height=300, N_resc=3, patch_radius=40,
                      min_resc_perpatch=500, max_resc_perpatch=-1, min_resc_quality=0.25, max_resc_quality=-1,
                      vision_range=150, agent_fov=0.5, visual_exclusion=True, teleport_exploit=False,
