@@ -90,8 +90,10 @@ class VFSimulation:
                  keep_fields: bool = True, **ignored):
         if with_visualization:
             raise NotImplementedError("rendering is out of scope of abm_b200 (headless only)")
-        if agent_behave_param_list is not None:
-            raise NotImplementedError("heterogeneous agent_behave_param_list is not supported yet (SURVEY f4)")
+        # vf_sims.py:184-210, 222-228: the visual-flocking simulation accepts the list but constructs every VFAgent
+        # with behave_params=None -- the dictionaries change nothing; kept for the evolution summary only (:368-371)
+        self.agent_behave_param_list = agent_behave_param_list
+        self.heterogen_agents = agent_behave_param_list is not None
         self.N, self.T, self.t = int(N), int(T), 0
         self.WIDTH, self.HEIGHT, self.window_pad = width, height, window_pad
         self.agent_radii = agent_radius
