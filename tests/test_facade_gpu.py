@@ -14,8 +14,10 @@ def test_vfsimulation_programmatic_stepping(built_lib):
     mutate agents, step_sim, read dv / dphi / ablob ... -- checked against the oracle."""
     from abm_b200.simulation import VFSimulation
     from abm_b200.params import VFParams
+    # vf_sims.py:184-228: the list is accepted and every VFAgent is still built with behave_params=None
     sim = VFSimulation(N=2, T=10, v_field_res=1200, width=500, height=500, agent_radius=10, agent_fov=1.0,
-                       vf_params=VFParams(ALP0=1.0, BET0=1.0, ALP1=0.09, BET1=0.09), seed=3)
+                       vf_params=VFParams(ALP0=1.0, BET0=1.0, ALP1=0.09, BET1=0.09), seed=3,
+                       agent_behave_param_list=[{"Eps_w": 5.0, "agent_fov": 0.25}] * 2)
     sim.prepare_start()
     a0, a1 = sim.agents
     a0.position = [250.0, 250.0]; a0.orientation = 0.0; a0.velocity = 1.0
