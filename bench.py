@@ -229,9 +229,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # NCCL prints its version banner on STDOUT, where the
-            os.environ["NCCL_DEBUG"] = "WARN"                        # one JSON line goes; any other setting is left alone
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION or WARN; the GPU boxes set VERSION) with printf on STDOUT,
+        # where the one JSON line goes, when the communicator is created: file descriptor 1 points to stderr while
+        # that happens (NCCL_DEBUG_FILE does not catch the banner)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     import __graft_entry__ as g
     if rank == 0:
