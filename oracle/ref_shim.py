@@ -211,6 +211,8 @@ def make_base_agents(st, cfg, behave_params_list=None):
     rad = st["radius"]
     rad = int(rad) if float(rad).is_integer() else float(rad)
     for i in range(N):
+        if behave_params_list is not None:                                             # sims.py:502
+            rad = behave_params_list[i]["agent_radius"]
         a = agent_mod.Agent(
             id=i, radius=rad, position=(float(st["x"][i]), float(st["y"][i])), orientation=float(st["theta"][i]),
             env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0), v_field_res=cfg.R,

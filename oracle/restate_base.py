@@ -61,7 +61,8 @@ def base_candidates(i, x, y, r, is_exploit, patch_id, cfg: BaseConfig):
     """Agent.calc_social_V_proj (agent.py:396-419): returns (social, occluders) index lists
     in the reference's list order.  ``is_exploit[j]`` = (agents[j].get_mode() == "exploit")."""
     N = len(x)
-    d = np.sqrt(((x + r) - (x[i] + r)) ** 2 + ((y + r) - (y[i] + r)) ** 2)        # supcalc.distance :73-78
+    ra = np.broadcast_to(np.asarray(r, np.float64), (N,))                         # every agent's OWN radius here
+    d = np.sqrt(((x + ra) - (x[i] + ra[i])) ** 2 + ((y + ra) - (y[i] + ra[i])) ** 2)   # supcalc.distance :73-78
     cand = [j for j in range(N) if d[j] <= cfg.vision_range]                      # :400 (includes self)
     expl = [j for j in cand if j != i and is_exploit[j]]                          # :402-403
     non_expl = [j for j in cand if j not in expl]                                 # :405
@@ -147,6 +148,8 @@ def base_fill(src, cfg: BaseConfig, fov=None):
 def base_field(i, x, y, r, theta, is_exploit, patch_id, cfg: BaseConfig):
     """agent.soc_v_field after Agent.calc_social_V_proj (agent.py:396-419, 457-597)."""
     social, occl = base_candidates(i, x, y, r, is_exploit, patch_id, cfg)
+    if np.ndim(r):      # heterogeneous radii: the projection uses the FOCAL radius for both centres (agent.py:504-509)
+        r = float(np.asarray(r)[i])
     if cfg.visual_exclusion:
         src = base_source_data(i, x, y, r, theta, social, occl, cfg)
         src = base_occlude(src)                                                   # :559-560
@@ -168,9 +171,11 @@ def base_agent_update(i, st, cfg: BaseConfig, dtheta_random):
     """Agent.update (agent.py:212-283) for agent i from the frozen snapshot ``st`` (dict of
     arrays, see base_step_frozen).  ``dtheta_random`` replaces the np.random.uniform draw of
     supcalc.random_walk (supcalc.py:45).  Returns a dict of agent i's new scalars + field."""
-    r = st["radius"]
+    r = st["radius"]                                 # scalar, or (N,) for heterogeneous radii (sims.py:502)
     is_exploit = st["override"] == OV_EXPLOIT        # get_mode() == "exploit" (agent.py:659-669)
     field, _src = base_field(i, st["x"], st["y"], r, st["theta"], is_exploit, st["patch_id"], cfg)
+    if np.ndim(r):
+        r = float(np.asarray(r)[i])                  # own radius in reflect_from_walls (agent.py:347-394)
     # calc_I_priv (agent.py:168-175)
     collected_unit = st["collected"][i] - st["collected_before"][i]
     I_priv = cfg.F_N * np.max(st["novelty"][i]) + cfg.F_R * collected_unit

@@ -80,13 +80,15 @@ def load_cs_cases():
     return cases
 
 
-def load_base_hetero_cases():
+def load_base_hetero_cases(fixture="base_hetero_golden.npz"):
     """tests/golden/base_hetero_golden.npz (make_golden_hetero.py): heterogeneous agents, the per-agent
     parameters went through the reference's own constructor (agent.py:83-108).  ``agent_cfgs``: one
-    BaseConfig per agent; ``agent_params``: dict name -> (N,) array."""
+    BaseConfig per agent; ``agent_params``: dict name -> (N,) array.  With
+    fixture="base_hetero_radius_golden.npz" (make_golden_hetero_radius.py, oracle-only) the state's radius is
+    the (N,) array of the agents' own radii."""
     import dataclasses
     from oracle import restate_base as rb
-    z = np.load(os.path.join(GOLDEN, "base_hetero_golden.npz"))
+    z = np.load(os.path.join(GOLDEN, fixture))
     keys = [str(k) for k in z["agent_keys"]]
     cases = []
     for c in range(int(z["n_cases"])):
@@ -101,11 +103,11 @@ def load_base_hetero_cases():
         agent_params = {k: tab[:, j] for j, k in enumerate(keys)}
         agent_cfgs = []
         for i in range(tab.shape[0]):
-            kw = {k: float(agent_params[k][i]) for k in keys if k != "agent_fov"}
+            kw = {k: float(agent_params[k][i]) for k in keys if k not in ("agent_fov", "agent_radius")}
             f = float(agent_params["agent_fov"][i])
             agent_cfgs.append(dataclasses.replace(cfg, fov=(-f * np.pi, f * np.pi), **kw))      # sims.py:506
         st = {k: z[p + "st_" + k] for k in BASE_STATE_KEYS}
-        st["radius"] = 10.0
+        st["radius"] = agent_params["agent_radius"].copy() if "agent_radius" in agent_params else 10.0
         cases.append(dict(cfg=cfg, st=st, dth=z[p + "dth"], fields=z[p + "fields"], agent_cfgs=agent_cfgs,
                           agent_params=agent_params, out={k: z[p + "out_" + k] for k in BASE_OUT_KEYS}))
     return cases

@@ -64,6 +64,22 @@ def test_restatement_matches_reference_fixture_heterogeneous_agents(case):
     assert not np.allclose(shared["w"], case["out"]["w"]) and not np.allclose(shared["vel"], case["out"]["vel"])
 
 
+@pytest.mark.parametrize("case", load_base_hetero_cases("base_hetero_radius_golden.npz"),
+                         ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_restatement_matches_reference_fixture_heterogeneous_radii(case):
+    """agent_radius of agent_behave_param_list (sims.py:502): every agent's own radius in the candidate distance
+    (supcalc.py:73-78) and in its wall reflection, the FOCAL radius for both centres and the projection size
+    (agent.py:504-509, 529).  Oracle-only: the CUDA path refuses per-agent radii."""
+    assert np.ndim(case["st"]["radius"]) == 1 and len(set(case["st"]["radius"])) > 1
+    out = rb.base_step_frozen(case["st"], case["cfg"], case["dth"], agent_cfgs=case["agent_cfgs"])
+    assert np.array_equal(rs.pack_bits(out["fields"]), case["fields"])
+    for k in BASE_OUT_KEYS:
+        np.testing.assert_allclose(out[k], case["out"][k], rtol=1e-12, atol=1e-12, err_msg=k)
+    # one shared radius does not reproduce it
+    shared = rb.base_step_frozen(dict(case["st"], radius=10.0), case["cfg"], case["dth"], agent_cfgs=case["agent_cfgs"])
+    assert not np.array_equal(rs.pack_bits(shared["fields"]), case["fields"])
+
+
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
 def test_patch_phase_pieces_match_live_reference():
     """notify_agent (sims.py:29-42), Rescource.deplete (rescource.py:118-133) and
