@@ -268,7 +268,7 @@ typedef struct {
   uint64_t seed;                /* counter-based RNG key (random walk, patch regeneration) */
 } abm_base_config_t;
 
-/* Per-replicate parameters, in this order (decision_params.py:13-42, movement_params.py:13-23,
+/* One parameter set (per batch, replicate or agent: abm_base_set_params), in this order (decision_params.py:13-42, movement_params.py:13-23,
  * sims.py agent_consumption). */
 enum {
   ABM_BASE_T_W = 0, ABM_BASE_EPS_W, ABM_BASE_G_W, ABM_BASE_B_W, ABM_BASE_W_MAX,
