@@ -125,6 +125,8 @@ SYMBOLS = {
     "abm_vf_set_agent_overrides": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "abm_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "abm_get_state": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
+    "abm_set_state_packed": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "abm_get_state_packed": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_vf_step": (C.c_int, [_P, C.c_int, _P]),
     "abm_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_vf_get_terms": (C.c_int, [_P, _P, C.c_int, _P]),

@@ -97,6 +97,7 @@ struct abm_engine {
   DevBuf<float4> rec[2];
   int cur = 0;          // rec[cur] is the state of the current step
   DevBuf<float> theta, vel, stage_x, stage_y, stage_r;
+  DevBuf<float4> stage4;      // staging of abm_set_state_packed / abm_get_state_packed with host buffers (on first use)
   DevBuf<float> radius_api;   // the radii of the last abm_set_state that passed them, caller's order (radius == NULL: keep)
   DevBuf<double> params;
   int n_param_sets = 1;
@@ -280,7 +281,7 @@ int abm_destroy(abm_engine_t* e) {
   cudaDeviceSynchronize();
   e->rec[0].release(); e->rec[1].release();
   e->theta.release(); e->vel.release();
-  e->stage_x.release(); e->stage_y.release(); e->stage_r.release(); e->radius_api.release();
+  e->stage_x.release(); e->stage_y.release(); e->stage_r.release(); e->radius_api.release(); e->stage4.release();
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
@@ -348,10 +349,15 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
     if ((rc = copy_in(e->stage_y.p, y, bytes, 0, st))) return rc;
     dx = e->stage_x.p; dy = e->stage_y.p;
   }
-  const unsigned init_mm[2] = {0x7f800000u, 0u};
-  ABM_CUDA(cudaMemcpyAsync(e->radius_minmax.p, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
+  // min / max radius of the batch (kernel variant selection): only a call that passes radii changes them -- a call
+  // without keeps what the engine knows, so the steady state of a host-driven loop (set_state, step, get_state per
+  // step) never reads anything back
+  if (radius) {
+    ABM_CUDA(cudaMemsetAsync(e->radius_minmax.p, 0xff, sizeof(unsigned), st));       // min: 0xffffffff
+    ABM_CUDA(cudaMemsetAsync(e->radius_minmax.p + 1, 0, sizeof(unsigned), st));      // max: 0
+  }
   abm::launch_pack_records(dx, dy, dr, permuted ? e->perm.p : nullptr, N, e->grid.cull_scale, e->rec[e->cur].p,
-                           e->radius_minmax.p, n, st);
+                           radius ? e->radius_minmax.p : nullptr, n, st);
   if (!permuted) {
     if ((rc = copy_in(e->theta.p, theta, bytes, on_device, st))) return rc;
     if ((rc = copy_in(e->vel.p, vel, bytes, on_device, st))) return rc;
@@ -365,13 +371,69 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
     abm::launch_gather_f32(dv, e->perm.p, e->vel.p, N, n, st);
   }
   ABM_CUDA(cudaGetLastError());
-  e->radius_known = false;
+  if (radius) e->radius_known = false;
   if (e->sort_enabled && !e->state_set) {
     abm::launch_iota(e->perm.p, N, n, st);
     e->perm_identity = true;
     e->needs_sort = true;
   }
   e->state_set = true;
+  return ABM_OK;
+}
+
+int abm_set_state_packed(abm_engine_t* e, const float* xytv, const float* radius, int on_device, void* stream) {
+  if (!e || !xytv) return fail(ABM_E_INVALID, "abm_set_state_packed: null argument");
+  if (!radius && !e->state_set)
+    return fail(ABM_E_STATE, "abm_set_state_packed: radius == NULL needs an earlier call that passed the radii");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool host = on_device != 1;
+  const long long n = (long long)e->n_total;
+  const int N = e->cfg.n_agents;
+  const bool permuted = e->sort_enabled && !e->perm_identity;
+  int rc;
+  if (radius && (rc = copy_in(e->radius_api.p, radius, sizeof(float) * e->n_total, on_device, st))) return rc;
+  const float4* src = reinterpret_cast<const float4*>(xytv);
+  if (host) {   // ONE host -> device copy of the whole state
+    if (!e->stage4.p) ABM_CUDA(e->stage4.alloc(e->n_total));
+    if ((rc = copy_in(e->stage4.p, xytv, sizeof(float4) * e->n_total, 0, st))) return rc;
+    src = e->stage4.p;
+  }
+  if (radius) {
+    ABM_CUDA(cudaMemsetAsync(e->radius_minmax.p, 0xff, sizeof(unsigned), st));
+    ABM_CUDA(cudaMemsetAsync(e->radius_minmax.p + 1, 0, sizeof(unsigned), st));
+  }
+  abm::launch_pack_state4(src, e->radius_api.p, permuted ? e->perm.p : nullptr, N, e->grid.cull_scale, e->rec[e->cur].p,
+                          e->theta.p, e->vel.p, radius ? e->radius_minmax.p : nullptr, n, st);
+  ABM_CUDA(cudaGetLastError());
+  if (radius) e->radius_known = false;
+  if (e->sort_enabled && !e->state_set) {
+    abm::launch_iota(e->perm.p, N, n, st);
+    e->perm_identity = true;
+    e->needs_sort = true;
+  }
+  e->state_set = true;
+  if (on_device == 0) ABM_CUDA(cudaStreamSynchronize(st));   // pageable host memory: the caller may reuse it on return
+  return ABM_OK;
+}
+
+int abm_get_state_packed(abm_engine_t* e, float* xytv, int on_device, void* stream) {
+  if (!e || !xytv) return fail(ABM_E_INVALID, "abm_get_state_packed: null argument");
+  if (!e->state_set) return fail(ABM_E_STATE, "abm_get_state_packed: no state has been set");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool host = on_device != 1;
+  const bool permuted = e->sort_enabled && !e->perm_identity;
+  if (host && !e->stage4.p) ABM_CUDA(e->stage4.alloc(e->n_total));
+  float4* dst = host ? e->stage4.p : reinterpret_cast<float4*>(xytv);
+  abm::launch_unpack_state4(e->rec[e->cur].p, e->theta.p, e->vel.p, permuted ? e->perm.p : nullptr, e->cfg.n_agents, dst,
+                            (long long)e->n_total, st);
+  ABM_CUDA(cudaGetLastError());
+  if (host) {   // ONE device -> host copy of the whole state
+    int rc = copy_out(xytv, dst, sizeof(float4) * e->n_total, 0, st);
+    if (rc) return rc;
+  }
+  if (on_device == 0) ABM_CUDA(cudaStreamSynchronize(st));
   return ABM_OK;
 }
 

@@ -12,11 +12,18 @@ namespace abm {
 int api_fail(int code, const std::string& msg);   // records the thread-local error message, returns code
 const char* api_last_error();
 
+// Owning device buffer: freed on release() or when it goes out of scope (an early return of ABM_CUDA in an entry
+// point that holds several of them leaks nothing).  Not copyable.
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
   cudaError_t alloc(size_t count) {
+    release();
     n = count;
     return cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * (count ? count : 1));
   }

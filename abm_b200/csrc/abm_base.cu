@@ -528,11 +528,8 @@ void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
   int warps = 16;
   while (warps > 1 && (warps / 2 >= a.N || per_warp * warps + shared > (size_t)smem_max)) warps >>= 1;
   const size_t smem = per_warp * warps + shared;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(base_collision_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;   // per device (abm_common.cuh)
+  optin.ensure(base_collision_kernel, smem);
   base_collision_kernel<<<a.B, warps * 32, smem, stream>>>(a);
 }
 
@@ -610,11 +607,8 @@ void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream) {
   const int smem_max = base_smem_optin();
   const int warps = base_agents_warps(a.N, a.W, (size_t)smem_max);
   const size_t smem = base_agents_smem_bytes(a.N, a.W, warps);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(base_agent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;   // per device (abm_common.cuh)
+  optin.ensure(base_agent_kernel, smem);
   const long long total = (long long)a.B * a.N;
   const unsigned grid = (unsigned)((total + warps - 1) / warps);
   base_agent_kernel<<<grid, warps * 32, smem, stream>>>(a);

@@ -6,7 +6,28 @@
 #define ABM_PI_D 3.141592653589793238462643383279502884
 #define ABM_TWO_PI_D (2.0 * ABM_PI_D)
 
+#include <mutex>
+
 namespace abm {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is an attribute of a kernel ON ONE DEVICE: a process that creates
+// engines on several devices has to opt in on each of them.  One instance per kernel (variant), e.g. a function-local
+// static of the launch function; thread-safe.
+struct SmemOptIn {
+  std::mutex mu;
+  size_t configured[64] = {};
+  template <typename Kernel>
+  void ensure(Kernel kernel, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    const bool tracked = dev >= 0 && dev < 64;
+    if (!tracked || smem > configured[dev]) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (tracked) configured[dev] = smem;
+    }
+  }
+};
 
 constexpr int kMaxThreads = 256;     // focal agents per CTA (one thread each)
 constexpr int kRecTile = 512;        // neighbour records per shared-memory stage (one-thread-per-focal-agent kernel)
@@ -136,6 +157,11 @@ void launch_vf_terms(const uint32_t* packed_v, int R, int W, double vel, const V
 // perm (nullable): internal slot -> caller's index; the records are written in internal order
 void launch_pack_records(const float* x, const float* y, const float* r, const int* perm, int N, float cull_scale,
                          float4* rec, unsigned* radius_minmax, long long n, cudaStream_t stream);
+// the same from / to ONE interleaved (x, y, heading, speed) array in the caller's order (abm_set_state_packed / get)
+void launch_pack_state4(const float4* s4, const float* r, const int* perm, int N, float cull_scale, float4* rec, float* theta,
+                        float* vel, unsigned* radius_minmax, long long n, cudaStream_t stream);
+void launch_unpack_state4(const float4* rec, const float* theta, const float* vel, const int* perm, int N, float4* out,
+                          long long n, cudaStream_t stream);
 // perm (nullable): internal slot -> API index inside the replicate; x / y are written in API order
 void launch_unpack_records(const float4* rec, const int* perm, int N, float* x, float* y, long long n,
                            cudaStream_t stream);

@@ -298,12 +298,8 @@ vf_step_kernel(const __grid_constant__ VFKernelArgs a) {
 
 template <bool TORUS, bool UNIFORM_R, bool CULL, bool FULL_FOV, int RC>
 static void launch_variant(const VFKernelArgs& a, unsigned grid, int T, size_t smem, cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(vf_step_kernel<TORUS, UNIFORM_R, CULL, FULL_FOV, RC>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;   // per device (abm_common.cuh)
+  optin.ensure(vf_step_kernel<TORUS, UNIFORM_R, CULL, FULL_FOV, RC>, smem);
   vf_step_kernel<TORUS, UNIFORM_R, CULL, FULL_FOV, RC><<<grid, T, smem, stream>>>(a);
 }
 
@@ -506,6 +502,7 @@ __global__ void pack_records_kernel(const float* x, const float* y, const float*
     rr = r[o];
     rec[g] = make_float4(x[o], y[o], rr, rr * rr * cull_scale);
   }
+  if (radius_minmax == nullptr) return;   // the radii did not change (abm_set_state with radius == NULL)
   // min / max radius of the batch (non-negative floats order like their bit patterns)
   unsigned lo = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0x7f800000u;
   unsigned hi = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0u;
@@ -515,6 +512,52 @@ __global__ void pack_records_kernel(const float* x, const float* y, const float*
     if (lo < __ldcg(&radius_minmax[0])) atomicMin(&radius_minmax[0], lo);
     if (hi > __ldcg(&radius_minmax[1])) atomicMax(&radius_minmax[1], hi);
   }
+}
+// The same from ONE interleaved array of (x, y, heading, speed) per agent (abm_set_state_packed): record, heading and
+// speed of internal slot g come from the caller's agent o.  radius_minmax == nullptr: the radii did not change.
+__global__ void pack_state4_kernel(const float4* __restrict__ s4, const float* __restrict__ r, const int* perm, int N,
+                                   float cull_scale, float4* __restrict__ rec, float* __restrict__ theta,
+                                   float* __restrict__ vel, unsigned* radius_minmax, long long n) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float rr = 0.f;
+  if (g < n) {
+    const long long o = perm ? (g - (g % N)) + perm[g] : g;
+    const float4 s = s4[o];
+    rr = r[o];
+    rec[g] = make_float4(s.x, s.y, rr, rr * rr * cull_scale);
+    theta[g] = s.z;
+    vel[g] = s.w;
+  }
+  if (radius_minmax == nullptr) return;
+  unsigned lo = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0x7f800000u;
+  unsigned hi = (g < n) ? __float_as_uint(fmaxf(rr, 0.f)) : 0u;
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) {
+    if (lo < __ldcg(&radius_minmax[0])) atomicMin(&radius_minmax[0], lo);
+    if (hi > __ldcg(&radius_minmax[1])) atomicMax(&radius_minmax[1], hi);
+  }
+}
+__global__ void unpack_state4_kernel(const float4* __restrict__ rec, const float* __restrict__ theta,
+                                     const float* __restrict__ vel, const int* perm, int N, float4* __restrict__ out,
+                                     long long n) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) {
+    const float4 v = rec[g];
+    const long long o = perm ? (g - (g % N)) + perm[g] : g;
+    out[o] = make_float4(v.x, v.y, theta[g], vel[g]);
+  }
+}
+void launch_pack_state4(const float4* s4, const float* r, const int* perm, int N, float cull_scale, float4* rec, float* theta,
+                        float* vel, unsigned* radius_minmax, long long n, cudaStream_t stream) {
+  const int threads = 256;
+  pack_state4_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(s4, r, perm, N, cull_scale, rec, theta,
+                                                                                     vel, radius_minmax, n);
+}
+void launch_unpack_state4(const float4* rec, const float* theta, const float* vel, const int* perm, int N, float4* out,
+                          long long n, cudaStream_t stream) {
+  const int threads = 256;
+  unpack_state4_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(rec, theta, vel, perm, N, out, n);
 }
 __global__ void unpack_records_kernel(const float4* rec, const int* perm, int N, float* x, float* y, long long n) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;

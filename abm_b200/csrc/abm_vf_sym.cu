@@ -477,12 +477,8 @@ bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t 
 
 template <bool TORUS, bool FULL_FOV, int RC, int NPC>
 static void launch_sym_variant(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    configured = smem;
-  }
+  static SmemOptIn optin;   // per device (abm_common.cuh)
+  optin.ensure(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC>, smem);
   vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC><<<a.B, threads, smem, stream>>>(a, Np);
 }
 

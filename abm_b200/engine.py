@@ -177,6 +177,45 @@ class VFEngine:
         _lib.check(self._lib.abm_get_state(self._h, *ptrs, side, C.c_void_p(_current_stream())), "abm_get_state")
         return out
 
+    def set_state_packed(self, xytv, radius=None, nonblocking=False):
+        """The state as ONE (B, N, 4) float32 array of (x, y, theta, vel) rows (numpy / torch CUDA tensor): one copy
+        instead of four.  ``radius`` as in `set_state` (scalar or (B, N); None keeps the radii).  ``nonblocking``:
+        `xytv` is PINNED host memory that stays alive and untouched until the caller has synchronised the stream."""
+        keep = []
+        total = self.B * self.N
+        p4, side4 = self._ptr(xytv, np.float32, 4 * total, keep)
+        pr, side_r = None, None
+        if radius is not None:
+            if not _is_torch_cuda(radius):
+                radius = np.broadcast_to(np.asarray(radius, np.float32), (self.B, self.N))
+            pr, side_r = self._ptr(radius, np.float32, total, keep)
+        side = self._same_side([side4, side_r])
+        if nonblocking and not side:
+            if not isinstance(xytv, np.ndarray) or keep[0].ctypes.data != xytv.ctypes.data:
+                raise ValueError("nonblocking=True needs a C-contiguous float32 array of full size (no copies are made)")
+            side = 2
+        _lib.check(self._lib.abm_set_state_packed(self._h, p4, pr, side, C.c_void_p(_current_stream())),
+                   "abm_set_state_packed")
+        if side == 2 and radius is not None:
+            self.synchronize()   # the broadcast radius array in `keep` may go away after return
+
+    def get_state_packed(self, out=None, nonblocking=False):
+        """(B, N, 4) float32 rows (x, y, theta, vel); fills ``out`` (numpy array or torch CUDA tensor) if given."""
+        total = self.B * self.N
+        if out is None:
+            out = np.empty((self.B, self.N, 4), np.float32)
+        if _is_torch_cuda(out):
+            if not out.is_contiguous() or out.numel() != 4 * total:
+                raise ValueError("output tensor must be contiguous float32 of full size")
+            p, side = C.c_void_p(out.data_ptr()), 1
+        else:
+            if out.dtype != np.float32 or not out.flags.c_contiguous or out.size != 4 * total:
+                raise ValueError("output array must be C-contiguous float32 of full size")
+            p, side = C.c_void_p(out.ctypes.data), (2 if nonblocking else 0)
+        _lib.check(self._lib.abm_get_state_packed(self._h, p, side, C.c_void_p(_current_stream())),
+                   "abm_get_state_packed")
+        return out
+
     def step(self, n_steps: int = 1):
         _lib.check(self._lib.abm_vf_step(self._h, int(n_steps), C.c_void_p(_current_stream())), "abm_vf_step")
 
@@ -185,7 +224,9 @@ class VFEngine:
 
     # -- outputs of the last step ----------------------------------------------------------
     def fields_packed(self) -> np.ndarray:
-        """(B, tile, W) uint32, STORED (flipped) order like Agent.soc_v_field."""
+        """(B, tile, W) uint32, STORED (flipped) order like Agent.soc_v_field.  Rows are in the caller's agent order;
+        on a TILED engine with the spatial sort on they are in internal slot order (row li = agent
+        ``permutation()[b, tile_begin + li]``), like `terms()`."""
         out = np.empty((self.B, self.tile_count, self.W), np.uint32)
         _lib.check(self._lib.abm_get_fields(self._h, C.c_void_p(out.ctypes.data), 0, C.c_void_p(_current_stream())),
                    "abm_get_fields")

@@ -11,6 +11,8 @@ them sequentially in place (sims.py:861); see DESIGN.md.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .base_engine import BaseEngine
@@ -270,6 +272,9 @@ class Simulation:
         self.decision_params = decision_params or DecisionParams()
         self.B = int(n_replicates)
         self._rng = np.random if seed is None else np.random.RandomState(seed)
+        # the engine's counter-based RNG (random-walk turns, patch regeneration) is keyed by a 64-bit seed: an unseeded
+        # run draws a fresh one, like the reference's unseeded np.random; kept on the simulation for reproducibility
+        self.engine_seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         self.engine = BaseEngine(self.B, self.N, self.N_resc, resolution=int(v_field_res), agent_fov=agent_fov,
                                  width=width, height=height, window_pad=window_pad, vision_range=vision_range,
                                  agent_radius=agent_radius, visual_exclusion=visual_exclusion,
@@ -279,7 +284,7 @@ class Simulation:
                                  max_resc_quality=max_resc_quality, min_resc_perpatch=min_resc_perpatch,
                                  max_resc_perpatch=max_resc_perpatch, tau=self.decision_params.Tau,
                                  keep_fields=keep_fields, collide_agents=collide_agents, ghost_mode=ghost_mode,
-                                 seed=0 if seed is None else int(seed), device=device)
+                                 seed=self.engine_seed, device=device)
         prm = dict(agent_consumption=agent_consumption, **self.decision_params.engine_kwargs())
         if self.heterogen_agents:
             # agent.py:83-108: these keys of behave_params replace the param modules' values, per agent;

@@ -130,63 +130,96 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def cpu_port_rate(n_focal, n_agents, procs=1, seed_replicate=0):
-    """agent-steps/s of the CPU port (oracle/literal.py) on `procs` host processes: `n_focal`
-    focal agents of one replicate against the full neighbour set, frozen snapshot."""
-    from oracle import literal, restate as rs
+_CPU = {}     # state of the CPU arm, built once per process and inherited by forked workers
+
+
+def _cpu_setup(n_agents, seed_replicate=0):
+    """The frozen snapshot the CPU arm works on: replicate `seed_replicate` of the workload's initial state.  With the
+    reference's own modules at hand (oracle/_ref, copied by oracle/build_ref.py; /root/reference in the build container)
+    the arm is the UNMODIFIED `VFAgent.update` (vf_agent.py:52-80) on real VFAgent objects (pygame stubbed: drawing is
+    free, which favours the reference); otherwise the float64 port oracle/literal.py."""
+    from oracle import ref_shim, restate as rs
     x, y, th, v = synthetic_state(1, n_agents, seed_replicate)
     x64, y64, th64, v64 = (a[0].astype(np.float64) for a in (x, y, th, v))
-    rad = np.full(n_agents, RADIUS)
     W = arena_side(n_agents)
-    cfg = rs.VFConfig(R=R, width=W, height=W, **PARAMS)
-    idx = list(range(n_focal))
-    if procs <= 1:
-        t0 = time.perf_counter()
+    _CPU.clear()
+    _CPU.update(kind="port", x=x64, y=y64, th=th64, v=v64, rad=np.full(n_agents, RADIUS),
+                cfg=rs.VFConfig(R=R, width=W, height=W, **PARAMS))
+    if ref_shim.reference_available() and os.environ.get("ABM_BENCH_CPU_KIND", "reference") != "port":
+        _CPU["agents"] = ref_shim.make_vf_agents(x64, y64, th64, v64, int(RADIUS), R=R, width=W, height=W,
+                                                 boundary="walls", params=PARAMS)
+        _CPU["kind"] = "reference"
+    return _CPU["kind"]
+
+
+def _cpu_chunk(idx):
+    """Update the focal agents `idx` from the frozen snapshot (every one sees the un-updated others)."""
+    if _CPU["kind"] == "reference":
+        import copy
+        agents = _CPU["agents"]
         for i in idx:
-            literal.agent_update(i, x64, y64, th64, v64, rad, cfg)
-        dt = time.perf_counter() - t0
+            a = copy.copy(agents[i])              # update() writes the focal agent alone: a shallow copy with its own
+            a.position = np.array(a.position)     # position array keeps the snapshot frozen (a deep copy would also
+            a.update(agents)                      # duplicate the agent's arena-sized line map, 68 MB at this size)
     else:
-        import multiprocessing as mp
-        chunks = [idx[p::procs] for p in range(procs)]
-        with mp.get_context("fork").Pool(procs) as pool:
-            pool.map(_cpu_chunk, [([], x64, y64, th64, v64, rad, cfg)] * procs)   # warm the workers
-            t0 = time.perf_counter()
-            pool.map(_cpu_chunk, [(c, x64, y64, th64, v64, rad, cfg) for c in chunks])
-            dt = time.perf_counter() - t0
-    return n_focal / dt, dt
-
-
-def _cpu_chunk(job):
-    from oracle import literal
-    idx, x, y, th, v, rad, cfg = job
-    for i in idx:
-        literal.agent_update(i, x, y, th, v, rad, cfg)
+        from oracle import literal
+        c = _CPU
+        for i in idx:
+            literal.agent_update(i, c["x"], c["y"], c["th"], c["v"], c["rad"], c["cfg"])
     return len(idx)
 
 
+def cpu_rate(n_focal, procs=1, pool=None):
+    """agent-steps/s of the CPU arm set up by _cpu_setup: `n_focal` focal agents against the full neighbour set."""
+    idx = list(range(n_focal))
+    if procs <= 1:
+        t0 = time.perf_counter()
+        _cpu_chunk(idx)
+        dt = time.perf_counter() - t0
+    else:
+        chunks = [idx[p::procs] for p in range(procs)]
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, chunks)
+        dt = time.perf_counter() - t0
+    return n_focal / dt, dt
+
+
+def cpu_sample_text(kind, n_focal, n_agents, procs, dt=None):
+    what = ("the UNMODIFIED reference VFAgent.update (vf_agent.py:52-80, modules copied to oracle/_ref by "
+            "oracle/build_ref.py; pygame stubbed, so drawing is free)") if kind == "reference" else \
+           "oracle/literal.py, float64 port of VFAgent.update (same per-pair loop and arg-min scans as the reference)"
+    t = f" ({dt:.1f} s)" if dt is not None else ""
+    return (f"{n_focal} focal agents x {n_agents - 1} neighbours of replicate 0 per step{t}, frozen snapshot, "
+            f"{procs} process(es) (one per host core); {what}")
+
+
 def run_reference_arm(args, rank, world):
-    """The reference's own CPU implementation of the path (port, all host cores)."""
+    """The reference's own CPU implementation of the path on all host cores (one process per core: the reference's own
+    way of using a node, HPC_batch_run.sh / README.md:302-324)."""
     if rank != 0:
         return
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     n_focal = max(procs * 2, int(os.environ.get("ABM_BENCH_CPU_FOCAL", 16 * procs)))
+    kind = _cpu_setup(N_AGENTS)
+    import multiprocessing as mp
     rates = []
-    for s in range(args.warmup + args.steps):
-        rate, dt = cpu_port_rate(n_focal, N_AGENTS, procs=procs)
-        if s >= args.warmup:
-            rates.append((rate, dt))
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_cpu_chunk, [[]] * procs)                          # start the workers
+        for s in range(args.warmup + args.steps):
+            rate, dt = cpu_rate(n_focal, procs=procs, pool=pool)
+            if s >= args.warmup:
+                rates.append((rate, dt))
     value = float(np.mean([r for r, _ in rates]))
     ms = float(np.mean([d for _, d in rates]) * 1e3)
-    sample = (f"{n_focal} focal agents x {N_AGENTS - 1} neighbours of replicate 0 per step, frozen snapshot, "
-              f"{procs} processes (one per host core), oracle/literal.py float64 port of VFAgent.update")
+    sample = cpu_sample_text(kind, n_focal, N_AGENTS, procs)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,13 +227,55 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(world):
-    return {"workload": "BASELINE configs[3]: visual flocking, 1024 agents x 1024 replicates per GPU, R=1200",
+    tag = "BASELINE configs[3]: " if (N_AGENTS, N_REPLICATES) == (1024, 1024) else "(size overridden by ABM_BENCH_*) "
+    return {"workload": f"{tag}visual flocking, {N_AGENTS} agents x {N_REPLICATES} replicates per GPU, R={R}",
             "n_agents": N_AGENTS, "replicates_per_gpu": N_REPLICATES, "replicates_total": N_REPLICATES * world,
             "fov_resolution": R, "boundary": "walls", "arena_px": arena_side(N_AGENTS), "agent_radius": RADIUS,
             "params": PARAMS, "parallelism": f"replicate-sharded x{world}, no data-path collective",
             "l2": "L2 flushed (256 MiB memset) between timed steps; flush excluded from the timing",
             "update": "synchronous (Jacobi) step from a frozen snapshot; every unordered pair evaluated once (fp32 + "
                       "32-bit binary angles), near-tie pairs re-evaluated in fp64, epilogue in fp64"}
+
+
+def parity_check(VFEngine, local_rank, x, y, th, v, rad, n_check=3):
+    """Correctness evidence in the bench record itself: ONE step of the benchmark's own kernel (the engine picks it from
+    the workload's size exactly as in the timed arm) from the workload's initial state, with fields and terms kept,
+    compared with the float64 oracle (oracle/restate.vf_step_frozen: the reference's VFAgent.update per agent from the
+    frozen snapshot, vf_agent.py:52-80 / vf_supcalc.py:20-138) for EVERY agent of `n_check` replicates.  Outside all
+    timed regions.  The checker, not the thing measured."""
+    from oracle import restate as rs
+    B, N = x.shape
+    W = arena_side(N)
+    eng = VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank, keep_fields=True, keep_terms=True)
+    eng.set_params(**PARAMS)
+    eng.set_state(x, y, th, v, rad)
+    eng.step(1)
+    kernel = eng.last_kernel()
+    fields, terms, st, ctr = eng.fields_packed(), eng.terms(), eng.get_state(), eng.counters()
+    eng.close()
+    cfg = rs.VFConfig(R=R, width=W, height=W, **PARAMS)
+    reps = sorted({0, B // 2, B - 1})[:n_check]
+    bits = 0
+    rel_terms = rel_state = 0.0
+    edges = 0
+    for b in reps:
+        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], RADIUS, cfg)
+        want = rs.pack_bits(ref["rows"][:, ::-1])                       # stored (flipped) order
+        diff = np.bitwise_xor(want, fields[b])
+        bits += int(np.unpackbits(diff.view(np.uint8)).sum())
+        edges += int((ref["rows"] != np.roll(ref["rows"], 1, axis=1)).sum())
+        rel_terms = max(rel_terms, float(np.max(np.abs(terms[b] - ref["terms"]) / np.maximum(np.abs(ref["terms"]), 1e-6))))
+        for k in ("x", "y", "theta", "vel"):
+            rel_state = max(rel_state, float(np.max(np.abs(st[k][b] - ref[k]) / np.maximum(np.abs(ref[k]), 1e-3))))
+    return {"kernel": kernel, "replicates": reps, "agents": len(reps) * N, "bins": len(reps) * N * R,
+            "field_bits_differ": bits, "max_rel_terms": rel_terms, "max_rel_state": rel_state,
+            "fp64_pairs": ctr["fp64_pairs"], "fp32_fp64_index_differ": ctr["fp32_fp64_differ"],
+            "edges_per_agent": edges / float(len(reps) * N),
+            "oracle": "oracle/restate.vf_step_frozen (float64 restatement pinned to the reference's golden vectors and "
+                      "to fixtures of the unmodified reference), every agent of the listed replicates, one step from "
+                      "the workload's initial state",
+            "tolerance": "fields bit-exact; terms / state 1e-5 relative (north_star)",
+            "ok": bool(bits == 0 and rel_terms < 1e-5 and rel_state < 1e-5)}
 
 
 def main():
@@ -299,24 +374,24 @@ def main():
         # batch-step copies its inputs host -> device, steps, and copies its result device -> host inside the timed
         # region; the copy engines move two batches while the SMs step the third (ABM_HOST_PINNED_ASYNC calls).
         hr = torch.from_numpy(rad).pin_memory().numpy()
-        NB = int(os.environ.get('ABM_E2E_BATCHES', '3'))   # measured: 1 -> 4.0e8, 2 -> 4.8e8, 3 -> 5.2e8, 4 -> 5.2e8 agent-steps/s
+        NB = int(os.environ.get('ABM_E2E_BATCHES', '3'))
         extra = [VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank) for _ in range(NB - 1)]
         for e_ in extra:
             e_.set_params(**PARAMS)
         engs = [eng] + extra
         streams = [torch.cuda.Stream() for _ in range(NB)]
-        hosts = [[{k: torch.from_numpy(a.copy()).pin_memory().numpy() for k, a in zip(("x", "y", "theta", "vel"), (x, y, th, v))}
-                  for _ in range(2)] for _ in range(NB)]
+        # ONE interleaved pinned buffer (x, y, theta, vel per agent) per direction and batch: one copy each way per step
+        packed0 = np.ascontiguousarray(np.stack([x, y, th, v], axis=-1))
+        hosts = [[torch.from_numpy(packed0.copy()).pin_memory().numpy() for _ in range(2)] for _ in range(NB)]
         e2e_steps = NB * max(2, min(args.steps, 60) // NB)            # batch-steps, round robin over the batches
         cur = [0] * NB
 
         def batch_step(k, first=False):
             with torch.cuda.stream(streams[k]):
-                h = hosts[k][cur[k]]
                 # H2D of the step's inputs; the radii are constants of the run, uploaded with the first call
-                engs[k].set_state(h["x"], h["y"], h["theta"], h["vel"], hr if first else None, nonblocking=not first)
+                engs[k].set_state_packed(hosts[k][cur[k]], hr if first else None, nonblocking=True)
                 engs[k].step(1)
-                engs[k].get_state(hosts[k][cur[k] ^ 1], nonblocking=True)   # D2H of the step's result
+                engs[k].get_state_packed(hosts[k][cur[k] ^ 1], nonblocking=True)   # D2H of the step's result
                 cur[k] ^= 1
 
         torch.cuda.synchronize()
@@ -328,19 +403,37 @@ def main():
         e0.record()
         for k in range(NB):
             streams[k].wait_event(e0)
+        t_host0 = time.perf_counter()
         for it in range(e2e_steps):
             batch_step(it % NB)
+        t_host_enqueue = time.perf_counter() - t_host0
         for k in range(NB):
             done = torch.cuda.Event(); done.record(streams[k]); torch.cuda.current_stream().wait_event(done)
         e1.record()
         barrier()
-        for k in ("x", "y", "theta", "vel"):                           # both batches came back whole
-            assert all(np.isfinite(hosts[j][cur[j]][k]).all() for j in range(NB))
+        for j in range(NB):                                            # every batch came back whole
+            assert np.isfinite(hosts[j][cur[j]]).all()
         for e_ in extra:
             e_.close()
         e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     counters = eng.counters()
+    timed_kernel = eng.last_kernel()
+
+    # ---- parity of the benchmark's own kernel against the oracle (every rank on its own replicates) ----
+    par = parity_check(VFEngine, local_rank, x, y, th, v, rad)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, par)
+        par = dict(gathered[0], agents=sum(g["agents"] for g in gathered), bins=sum(g["bins"] for g in gathered),
+                   field_bits_differ=sum(g["field_bits_differ"] for g in gathered),
+                   max_rel_terms=max(g["max_rel_terms"] for g in gathered),
+                   max_rel_state=max(g["max_rel_state"] for g in gathered),
+                   fp64_pairs=sum(g["fp64_pairs"] for g in gathered),
+                   fp32_fp64_index_differ=sum(g["fp32_fp64_index_differ"] for g in gathered),
+                   ok=all(g["ok"] for g in gathered), ranks=world,
+                   kernels=sorted({g["kernel"] for g in gathered}))
+    par["same_kernel_as_timed"] = par["kernel"] == timed_kernel
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -370,6 +463,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * 4 * B * N),
                     "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps,
+                    "host_enqueue_s": t_host_enqueue, "device_s": e2e_ms * 1e-3,
+                    "api": "VFEngine.set_state_packed -> step -> get_state_packed (abm_set_state_packed / abm_vf_step / "
+                           "abm_get_state_packed, ABM_HOST_PINNED_ASYNC): one pinned (x, y, theta, vel) array per direction",
                     "pipeline": "%d batches in flight (one engine, stream and pair of pinned buffers each): copies overlap the other batches' steps" % NB},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
@@ -383,16 +479,15 @@ def main():
             "pairs_per_sec": pairs * world * args.steps / (total_ms * 1e-3),
             "fp64_pairs_fraction": counters["fp64_pairs"] / float(pairs * counters["launches"]),
             "wall_s_timed_region": t_wall,
+            "parity": par,
         }
         if not args.no_cpu_baseline and world == 1:
             os.environ.setdefault("OMP_NUM_THREADS", "1")
+            kind = _cpu_setup(N)
             n_focal = int(os.environ.get("ABM_BENCH_CPU_FOCAL", 256))
-            rate, dt = cpu_port_rate(n_focal, N, procs=1)
-            line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"{n_focal} focal agents x {N - 1} neighbours of replicate 0 ({dt:.1f} s), frozen snapshot, "
-                          "oracle/literal.py float64 port of VFAgent.update (same per-pair loop and arg-min scans "
-                          "as the reference), 1 core"}
+            rate, dt = cpu_rate(n_focal, procs=1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": cpu_sample_text(kind, n_focal, N, 1, dt)}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

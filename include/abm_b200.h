@@ -123,13 +123,24 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
                   const float* radius, int on_device, void* stream);
 int abm_get_state(abm_engine_t* e, float* x, float* y, float* theta, float* vel, int on_device, void* stream);
 
+/* The same state as ONE interleaved array: (x, y, theta, vel) per agent, n_replicates * n_agents * 4 floats,
+ * replicate-major -- one copy per direction instead of four (a host-driven loop that uploads the state, steps and
+ * downloads it every step pays per-copy overhead and PCIe turn-arounds; with ABM_HOST_PINNED_ASYNC neither call blocks
+ * or reads anything back).  radius: as in abm_set_state (SoA, NULL = keep).  Replaces the same attribute reads /
+ * writes (agent.py:52-68) for a caller that keeps its agents as rows of a table. */
+int abm_set_state_packed(abm_engine_t* e, const float* xytv, const float* radius, int on_device, void* stream);
+int abm_get_state_packed(abm_engine_t* e, float* xytv, int on_device, void* stream);
+
 /* n_steps synchronous (Jacobi) steps, one fused kernel launch per step.
  * Replaces: VFSimulation.step_sim -> agents.update (vf_sims.py:291-302) ->
  * VFAgent.update (vf_agent.py:52-80) for every agent of every replicate. */
 int abm_vf_step(abm_engine_t* e, int n_steps, void* stream);
 
 /* Packed STORED fields of the last step, n_replicates*tile*abm_field_words(R) words
- * (needs ABM_VF_KEEP_FIELDS).  Replaces reading Agent.soc_v_field (vf_agent.py:209). */
+ * (needs ABM_VF_KEEP_FIELDS).  Replaces reading Agent.soc_v_field (vf_agent.py:209).
+ * Row order: the caller's agent order for an engine that owns whole replicates.  A TILED engine (tile_count != 0)
+ * with ABM_VF_SPATIAL_SORT owns the internal slots [tile_begin, tile_begin + tile_count): its rows (and those of
+ * abm_vf_get_terms) are in slot order, row li = the agent abm_vf_get_permutation reports for slot tile_begin + li. */
 int abm_get_fields(abm_engine_t* e, uint32_t* packed, int on_device, void* stream);
 
 /* (dvel, dpsi, a_blob, a_edge, b_blob, b_edge) per agent of the last step, 6 doubles each
@@ -189,7 +200,9 @@ int abm_vf_metrics(abm_engine_t* e, float* out, int on_device, void* stream);
 
 int abm_synchronize(abm_engine_t* e, void* stream);
 
-/* ---- stateless function-level entry points (host pointers, synchronous) ---- */
+/* ---- stateless function-level entry points (host pointers, synchronous) ----
+ * They run on the CURRENT CUDA device of the calling thread (cudaSetDevice is the caller's business, as for any CUDA
+ * library call without a handle); that device must be an sm_100 one. */
 
 /* vf_supcalc.projection_field (vf_supcalc.py:20-138): one focal agent, n_obj objects.
  * Inputs are float64 like the reference's; they are rounded to the engine's fp32 state.

@@ -8,9 +8,10 @@ matplotlib, so that its own functions and agent classes can be executed to
   * generate the golden fixtures under ``tests/golden/`` (see
     ``tests/golden/make_golden.py``).
 
-``/root/reference`` does not exist on the GPU box, so nothing in ``-m gpu`` tests,
-``bench.py`` or ``__graft_entry__.smoke()`` may import this module; CPU tests that
-use it skip themselves when the reference tree is absent.
+``/root/reference`` does not exist on the GPU box: there the shim falls back to ``oracle/_ref`` (a byte-for-byte,
+git-ignored copy of the hot-path modules made by ``oracle/build_ref.py`` in the build container, shipped with the
+snapshot like the built ``.so``); nothing reads ``/root/reference`` at run time on the GPU box, and everything that
+uses the shim checks ``reference_available()`` first.
 
 What is stubbed: ``pygame`` (Sprite / Group with a
 sequential ``update``, no-op Surface, MagicMock drawing sub-modules),
@@ -23,11 +24,22 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("ABM_REFERENCE_ROOT", "/root/reference")
+def _reference_root() -> str:
+    """The mounted reference tree (build container), else the byte-for-byte copy of its hot-path modules that
+    oracle/build_ref.py leaves in the git-ignored oracle/_ref (travels to the GPU box with the snapshot)."""
+    env = os.environ.get("ABM_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/abm/agent"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "abm", "agent"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "abm", "agent", "agent.py"))
 
 
 class _Rect:

@@ -23,15 +23,42 @@ def _engine(c_or_cfg, B, N, **kw):
     return VFEngine(B, N, keep_fields=True, keep_terms=True, **kw)
 
 
+# Every step kernel meets the fixtures and the oracle ITSELF (not only through kernel-vs-kernel equality): "auto" is
+# the engine's own choice for the scene, the others are forced with ABM_VF_KERNEL (abm_api.cu).
+KERNELS = ["auto", "symmetric", "onesided", "warp"]
+KERNEL_NAMES = {"symmetric": "abm::vf_step_sym_kernel", "onesided": "abm::vf_step_kernel",
+                "warp": "abm::vf_step_warp_kernel"}
+
+
+def _force_kernel(monkeypatch, kernel):
+    if kernel == "auto":
+        monkeypatch.delenv("ABM_VF_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("ABM_VF_KERNEL", kernel)
+
+
+def _ran_forced_kernel(eng, kernel):
+    """False when the forced kernel does not apply to the scene (the symmetric kernel needs equal radii and
+    N <= 1024) -- the caller skips; any other mismatch is a failure."""
+    if kernel == "auto":
+        return True
+    if eng.last_kernel() == KERNEL_NAMES[kernel]:
+        return True
+    assert kernel == "symmetric", f"{kernel} was forced but {eng.last_kernel()} ran"
+    return False
+
+
 def _check_state(st, ref, b=None):
     for k in ("x", "y", "theta", "vel"):
         got = st[k] if b is None else st[k][b]
         np.testing.assert_allclose(got.reshape(-1), ref[k], rtol=RTOL, atol=1e-5, err_msg=k)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("case", load_vf_cases(), ids=lambda c: f"N{c['N']}_R{c['R']}_{c['boundary']}")
-def test_step_matches_reference_fixture(built_lib, case):
+def test_step_matches_reference_fixture(built_lib, monkeypatch, case, kernel):
     c = case
+    _force_kernel(monkeypatch, kernel)
     fov = (-c["fov_ratio"] * np.pi, c["fov_ratio"] * np.pi)
     eng = _engine(None, 1, c["N"], resolution=c["R"], fov=fov, boundary=c["boundary"], width=c["W"],
                   height=c["W"], limit_movement=c["limit"])
@@ -40,6 +67,9 @@ def test_step_matches_reference_fixture(built_lib, case):
         eng.set_agent_overrides(c["alp0"], c["bet0"], c["v0"])
     eng.set_state(c["x"], c["y"], c["theta"], c["vel"], c["radius"])
     eng.step(1)
+    if not _ran_forced_kernel(eng, kernel):
+        eng.close()
+        pytest.skip("the symmetric kernel does not apply to this scene (heterogeneous radii)")
     assert np.array_equal(eng.fields_packed()[0], c["fields"])          # bit-exact stored fields
     np.testing.assert_allclose(eng.terms()[0], c["terms"], rtol=RTOL, atol=1e-9)
     st = eng.get_state()
@@ -106,8 +136,10 @@ SCENES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("B,N,R,W,boundary,fovr,radius", SCENES)
-def test_step_matches_oracle_random(built_lib, B, N, R, W, boundary, fovr, radius):
+def test_step_matches_oracle_random(built_lib, monkeypatch, B, N, R, W, boundary, fovr, radius, kernel):
+    _force_kernel(monkeypatch, kernel)
     rng = np.random.default_rng(1234 + N + R)
     x, y, th, v = _random_scene(rng, B, N, W)
     fov = (-fovr * np.pi, fovr * np.pi)
@@ -115,6 +147,7 @@ def test_step_matches_oracle_random(built_lib, B, N, R, W, boundary, fovr, radiu
     eng.set_params()
     eng.set_state(x, y, th, v, radius)
     eng.step(1)
+    assert _ran_forced_kernel(eng, kernel)                               # equal radii, N <= 1024: every kernel applies
     fields, terms, st = eng.fields(), eng.terms(), eng.get_state()
     cfg = rs.VFConfig(R=R, fov=fov, boundary=boundary, width=W, height=W)
     sample = range(N) if N <= 120 else sorted(rng.choice(N, 60, replace=False).tolist())
@@ -203,12 +236,14 @@ def test_empty_field_and_single_agent(built_lib):
     eng.close()
 
 
-def test_full_size_properties(built_lib):
-    """BASELINE configs[3] shape at reduced replicate count (1024 agents x 8 replicates,
-    R=1200): size-independent properties instead of the (too slow) oracle --
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_properties(built_lib, monkeypatch, kernel):
+    """BASELINE configs[3] shape at reduced replicate count (1024 agents x 8 replicates, R=1200), under every step
+    kernel (the benchmark's own, `symmetric`, forced at this batch size):
     (1) replicates are independent: replicate b of a batch == the same replicate alone;
     (2) agent order inside the neighbour table does not matter (union is commutative);
-    (3) mirror symmetry: reflecting the scene left-right flips every field."""
+    (3) the oracle on EVERY agent of one replicate of the full-size scene."""
+    _force_kernel(monkeypatch, kernel)
     rng = np.random.default_rng(2024)
     B, N, R = 8, 1024, 1200
     W = float(np.ceil(900 * np.sqrt(N / 100)))
@@ -216,7 +251,8 @@ def test_full_size_properties(built_lib):
     from abm_b200 import VFEngine
     eng = VFEngine(B, N, resolution=R, width=W, height=W, keep_fields=True, keep_terms=True)
     eng.set_params(); eng.set_state(x, y, th, v, 10.0); eng.step(1)
-    f_all, t_all = eng.fields_packed(), eng.terms()
+    assert _ran_forced_kernel(eng, kernel)
+    f_all, t_all, st_all = eng.fields_packed(), eng.terms(), eng.get_state()
     eng.close()
     # (1)
     e1 = VFEngine(1, N, resolution=R, width=W, height=W, keep_fields=True, keep_terms=True)
@@ -227,13 +263,12 @@ def test_full_size_properties(built_lib):
     perm = rng.permutation(N)
     e1.set_state(x[3:4, perm], y[3:4, perm], th[3:4, perm], v[3:4, perm], 10.0); e1.step(1)
     assert np.array_equal(e1.fields_packed()[0], f_all[3][perm])
-    # (3) oracle spot check on a few agents of the full-size scene
+    # (3) the oracle on all 1024 agents of replicate 3 of the full-size scene
     cfg = rs.VFConfig(R=R, width=W, height=W)
-    sample = [0, 17, 511, 1023]
-    ref = rs.vf_step_frozen(x[3], y[3], th[3], v[3], 10.0, cfg, agents=sample)
-    bits = rs.unpack_bits(f_all[3], R)
-    assert np.array_equal(bits[sample], ref["rows"][sample][:, ::-1])
-    np.testing.assert_allclose(t_all[3][sample], ref["terms"][sample], rtol=RTOL, atol=1e-9)
+    ref = rs.vf_step_frozen(x[3], y[3], th[3], v[3], 10.0, cfg)
+    assert np.array_equal(rs.unpack_bits(f_all[3], R), ref["rows"][:, ::-1])
+    np.testing.assert_allclose(t_all[3], ref["terms"], rtol=RTOL, atol=1e-9)
+    _check_state(st_all, ref, 3)
     e1.close()
 
 
@@ -586,3 +621,103 @@ def test_set_state_keeps_radii_when_omitted(built_lib):
     a.step(1); b.step(1)
     assert np.array_equal(a.fields_packed(), b.fields_packed())
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("sorted_swarm", [False, True])
+def test_packed_state_matches_soa_state(built_lib, monkeypatch, sorted_swarm):
+    """abm_set_state_packed / abm_get_state_packed (ONE interleaved (x, y, theta, vel) array per direction) against the
+    four-array calls: the same bits in, the same bits out -- host arrays, device tensors, pinned non-blocking, and on an
+    engine that keeps its agents in an internal (Morton) order (one large sparse swarm)."""
+    import torch
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(31)
+    B, N, W = (1, 5000, 9000.0) if sorted_swarm else (5, 200, 1200.0)
+    x, y, th, v = _random_scene(rng, B, N, W)
+    packed = np.ascontiguousarray(np.stack([x, y, th, v], axis=-1))
+    ea = VFEngine(B, N, resolution=1200, width=W, height=W, resort_every=2)
+    eb = VFEngine(B, N, resolution=1200, width=W, height=W, resort_every=2)
+    for e in (ea, eb):
+        e.set_params()
+    ea.set_state(x, y, th, v, 10.0)
+    eb.set_state_packed(packed, 10.0)
+    got = eb.get_state_packed()
+    assert np.array_equal(got, packed)                                   # round trip before any step
+    ea.step(3); eb.step(3)
+    if sorted_swarm:
+        assert eb.last_kernel() == "abm::vf_step_warp_kernel" and not np.array_equal(eb.permutation()[0], np.arange(N))
+    sa, pb = ea.get_state(), eb.get_state_packed()
+    for i, k in enumerate(("x", "y", "theta", "vel")):
+        assert np.array_equal(pb[..., i], sa[k]), k
+    # the radii are kept when omitted; device tensors; pinned non-blocking
+    dev = torch.from_numpy(pb).cuda()
+    eb.set_state_packed(dev)
+    out_dev = torch.empty_like(dev)
+    eb.get_state_packed(out_dev)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_dev.cpu().numpy(), pb)
+    pin_in = torch.from_numpy(pb.copy()).pin_memory().numpy()
+    pin_out = torch.empty(B, N, 4).pin_memory().numpy()
+    eb.set_state_packed(pin_in, nonblocking=True)
+    eb.step(2)
+    eb.get_state_packed(pin_out, nonblocking=True)
+    torch.cuda.synchronize()
+    ea.set_state(sa["x"], sa["y"], sa["theta"], sa["vel"])
+    ea.step(2)
+    sa2 = ea.get_state()
+    for i, k in enumerate(("x", "y", "theta", "vel")):
+        assert np.array_equal(pin_out[..., i], sa2[k]), k
+    ea.close(); eb.close()
+
+
+def test_host_driven_loop_never_reads_back(built_lib):
+    """A call of abm_set_state / abm_set_state_packed WITHOUT radii keeps what the engine knows about them: the next
+    step must not fetch the batch's min / max radius again (a device -> host copy and a stream synchronisation on every
+    step of a host-driven loop, VERDICT r1 weak #6).  Observable: with non-blocking transfers a step enqueued behind a
+    long-running kernel returns immediately."""
+    import time
+    import torch
+    from abm_b200 import VFEngine
+    B, N, W = 64, 1024, 2880.0
+    rng = np.random.default_rng(5)
+    x, y, th, v = _random_scene(rng, B, N, W)
+    pin = torch.from_numpy(np.ascontiguousarray(np.stack([x, y, th, v], axis=-1))).pin_memory().numpy()
+    out = torch.empty(B, N, 4).pin_memory().numpy()
+    eng = VFEngine(B, N, resolution=1200, width=W, height=W)
+    eng.set_params()
+    eng.set_state_packed(pin, 10.0)
+    eng.step(1)                                   # learns the radii (one read-back, once)
+    torch.cuda.synchronize()
+    blocker = torch.empty(1 << 28, device="cuda")
+    t0 = time.perf_counter()
+    for _ in range(40):
+        blocker.normal_()                         # ~1 ms of GPU work each, queued ahead of the loop below
+    for _ in range(5):
+        eng.set_state_packed(pin, nonblocking=True)
+        eng.step(1)
+        eng.get_state_packed(out, nonblocking=True)
+    t_enqueue = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_total = time.perf_counter() - t0
+    assert t_enqueue < 0.5 * t_total, (t_enqueue, t_total)      # the host ran ahead of the device
+    eng.close()
+
+
+def test_engines_on_two_devices_in_one_process(built_lib):
+    """The opt-in to > 48 KB of dynamic shared memory is per DEVICE: a process that creates engines on two devices must
+    be able to launch the large-shared-memory kernels on both (VERDICT r1 weak #7)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(9)
+    B, N, W = 160, 1024, 2880.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    res = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            eng = VFEngine(B, N, resolution=1200, width=W, height=W, device=dev)
+            eng.set_params(); eng.set_state(x, y, th, v, 10.0); eng.step(2)
+            assert eng.last_kernel() == "abm::vf_step_sym_kernel"
+            res.append(eng.get_state()); eng.close()
+    for k in ("x", "y", "theta", "vel"):
+        assert np.array_equal(res[0][k], res[1][k])
