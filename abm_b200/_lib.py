@@ -19,7 +19,8 @@ VF_KEEP_FIELDS = 1 << 1
 VF_KEEP_TERMS = 1 << 2
 VF_SPATIAL_SORT = 1 << 3
 VF_NPARAM = 6
-VF_IPC_BYTES = 256
+VF_IPC_BYTES = 512
+VF_TILE_BLOCK = 128
 
 
 class AbmError(RuntimeError):
@@ -37,6 +38,7 @@ class VFConfig(C.Structure):
         ("width", C.c_float), ("height", C.c_float), ("window_pad", C.c_float),
         ("max_vel", C.c_float), ("max_th", C.c_float), ("flags", C.c_uint32),
         ("tile_begin", C.c_int32), ("tile_count", C.c_int32), ("resort_every", C.c_int32),
+        ("tile_cycle", C.c_int32), ("tile_phase", C.c_int32),
     ]
 
 

@@ -90,7 +90,7 @@ void build_grid(int R, GridConsts& g) {
 struct abm_engine {
   abm_vf_config_t cfg;
   int device = 0;
-  int tile_begin = 0, tile_count = 0;
+  int tile_begin = 0, tile_count = 0, tile_cycle = 0, tile_phase = 0;
   GridConsts grid;
   size_t n_total = 0;   // B * N
   size_t n_tile = 0;    // B * tile_count
@@ -118,7 +118,11 @@ struct abm_engine {
   int n_peers = 0, my_rank = 0;
   float4* peer_rec[7][2] = {};      // peers' record tables (both halves of the ping-pong)
   uint32_t* peer_flags[7] = {};
-  void* peer_maps[7][3] = {};       // what cudaIpcOpenMemHandle returned (to close)
+  float4* peer_bbox[7][2] = {};     // peers' tile-box tables (one per record table)
+  void* peer_maps[7][5] = {};       // what cudaIpcOpenMemHandle returned (to close)
+  DevBuf<uint32_t> ticket;          // CTA ticket of the warp kernel's last-CTA step close
+  bool host_synced = false;         // fused exchange: the current record table was completed under a host barrier
+                                    // (abm_set_state / abm_vf_resort), no peer is writing into it
   uint32_t steps_done = 0;
   // adaptive kernel choice: the symmetric kernel reports how many pairs left its fast path; in crowded scenes
   // (most intervals wider than 32 bins) the one-thread-per-focal-agent kernel is faster (both give identical results)
@@ -136,7 +140,9 @@ struct abm_engine {
   DevBuf<uint32_t> keys_in, keys_out;
   DevBuf<unsigned char> sort_temp;
   size_t sort_temp_bytes = 0;
-  DevBuf<float4> tile_bbox;   // culling by record tiles (CULL variants on sorted state)
+  DevBuf<float4> tile_bbox[2];   // culling by record tiles (CULL variants on sorted state): boxes of rec[0] / rec[1]
+  bool bbox_valid[2] = {false, false};
+  int bbox_tile[2] = {0, 0};     // records per tile the boxes were computed for
   DevBuf<float> metrics;      // abm_vf_metrics staging (allocated on first use)
   DevBuf<float> tile_cull2;
 };
@@ -173,6 +179,8 @@ int resort_engine(abm_engine* e, cudaStream_t st) {
   e->needs_sort = false;
   e->perm_identity = false;
   e->steps_since_sort = 0;
+  e->bbox_valid[0] = e->bbox_valid[1] = false;
+  e->host_synced = true;
   return ABM_OK;
 }
 
@@ -208,6 +216,16 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   int tb = cfg->tile_begin, tc = cfg->tile_count;
   if (tc == 0) { tb = 0; tc = cfg->n_agents; }
   if (tb < 0 || tc < 1 || tb + tc > cfg->n_agents) return fail(ABM_E_INVALID, "abm_vf_create: bad agent tile");
+  const int cyc = cfg->tile_cycle > 1 ? cfg->tile_cycle : 0;
+  if (cyc) {
+    if (cfg->n_replicates != 1 || cfg->tile_phase < 0 || cfg->tile_phase >= cyc ||
+        cfg->n_agents % (cyc * ABM_VF_TILE_BLOCK) != 0 || cfg->tile_count != cfg->n_agents / cyc)
+      return fail(ABM_E_INVALID, "abm_vf_create: cyclic tiles need one swarm (B = 1), n_agents a multiple of tile_cycle * "
+                                 "ABM_VF_TILE_BLOCK, tile_count = n_agents / tile_cycle and 0 <= tile_phase < tile_cycle");
+    if (!(cfg->flags & ABM_VF_SPATIAL_SORT))
+      return fail(ABM_E_INVALID, "abm_vf_create: cyclic tiles are defined on the spatially sorted order (ABM_VF_SPATIAL_SORT)");
+    tb = 0;
+  }
   int ndev = 0;
   ABM_CUDA(cudaGetDeviceCount(&ndev));
   if (ndev < 1 || device < 0 || device >= ndev) return fail(ABM_E_NO_DEVICE, "abm_vf_create: no such CUDA device");
@@ -223,6 +241,8 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
   e->device = device;
   e->tile_begin = tb;
   e->tile_count = tc;
+  e->tile_cycle = cyc;
+  e->tile_phase = cyc ? cfg->tile_phase : 0;
   e->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   build_grid(cfg->resolution, e->grid);
   e->n_sms = prop.multiProcessorCount;
@@ -255,7 +275,7 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
     e->sort_temp_bytes = abm::vf_sort_temp_bytes(cfg->n_replicates, cfg->n_agents);
     A(e->sort_temp.alloc(e->sort_temp_bytes + 16));
     const size_t nt = (size_t)cfg->n_replicates * ((cfg->n_agents + abm::kWarpTile - 1) / abm::kWarpTile);
-    A(e->tile_bbox.alloc(nt)); A(e->tile_cull2.alloc(nt));
+    A(e->tile_bbox[0].alloc(nt)); A(e->tile_bbox[1].alloc(nt)); A(e->tile_cull2.alloc(nt));
   }
   if (cfg->flags & ABM_VF_KEEP_FIELDS) A(e->fields.alloc(e->n_tile * e->grid.W));
   if (cfg->flags & ABM_VF_KEEP_TERMS) A(e->terms.alloc(e->n_tile * 6));
@@ -285,10 +305,10 @@ int abm_destroy(abm_engine_t* e) {
   e->params.release(); e->ov_alp0.release(); e->ov_bet0.release(); e->ov_v0.release();
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
-  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox.release(); e->tile_cull2.release(); e->metrics.release();
+  e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox[0].release(); e->tile_bbox[1].release(); e->tile_cull2.release(); e->ticket.release(); e->metrics.release();
   e->radius_minmax.release();
   for (int p = 0; p < e->n_peers; ++p)
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 5; ++k)
       if (e->peer_maps[p][k]) cudaIpcCloseMemHandle(e->peer_maps[p][k]);
   e->xflags.release();
   if (e->slow_host) cudaFreeHost(e->slow_host);
@@ -372,6 +392,8 @@ int abm_set_state(abm_engine_t* e, const float* x, const float* y, const float* 
   }
   ABM_CUDA(cudaGetLastError());
   if (radius) e->radius_known = false;
+  e->bbox_valid[0] = e->bbox_valid[1] = false;
+  e->host_synced = true;
   if (e->sort_enabled && !e->state_set) {
     abm::launch_iota(e->perm.p, N, n, st);
     e->perm_identity = true;
@@ -407,6 +429,8 @@ int abm_set_state_packed(abm_engine_t* e, const float* xytv, const float* radius
                           e->theta.p, e->vel.p, radius ? e->radius_minmax.p : nullptr, n, st);
   ABM_CUDA(cudaGetLastError());
   if (radius) e->radius_known = false;
+  e->bbox_valid[0] = e->bbox_valid[1] = false;
+  e->host_synced = true;
   if (e->sort_enabled && !e->state_set) {
     abm::launch_iota(e->perm.p, N, n, st);
     e->perm_identity = true;
@@ -484,6 +508,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   memset(&a, 0, sizeof(a));
   a.B = e->cfg.n_replicates; a.N = e->cfg.n_agents; a.R = g.R; a.W = g.W;
   a.tile_begin = e->tile_begin; a.tile_count = e->tile_count; a.n_sms = e->n_sms;
+  a.tile_cycle = e->tile_cycle; a.tile_phase = e->tile_phase;
   a.fov_px0 = e->cfg.fov_px0; a.fov_px1 = e->cfg.fov_px1;
   a.boundary = e->cfg.boundary; a.limit_movement = e->cfg.limit_movement;
   a.phi_ok = g.phi_ok; a.flags = e->cfg.flags;
@@ -608,20 +633,52 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     for (int p = 0; p < e->n_peers; ++p) { a.peer_rec_out[p] = e->peer_rec[p][e->cur ^ 1]; a.peer_flags[p] = e->peer_flags[p]; }
     a.xflags = e->xflags.p;
     // one large sparse swarm (distance culling on) or an agent tile of it: a warp per focal agent
-    const bool use_warp = !use_sym && ((force && strcmp(force, "warp") == 0) ||
+    const bool use_warp = !use_sym && (e->tile_cycle > 1 || (force && strcmp(force, "warp") == 0) ||
                                        (!(force && strcmp(force, "onesided") == 0) && (cull || tiled || small_grid)));
+    a.tile_bbox = nullptr; a.tile_cull2 = nullptr; a.step_ticket = nullptr; a.bbox_out = nullptr;
+    const bool fused_close = e->n_peers > 0 && use_warp;   // the warp kernel's last CTA closes the step (boxes + publish)
+    bool next_boxes = false;
     if (cull && e->sort_enabled && !e->perm_identity) {   // tile-level culling needs spatially compact tiles
       const int tile = (use_warp && (a.N + abm::kWarpTile - 1) / abm::kWarpTile <= abm::kMaxTileList) ? abm::kWarpTile
                                                                                                     : abm::kRecTile;
-      abm::launch_tile_bbox(a.rec_in, a.B, a.N, tile, e->tile_bbox.p, e->tile_cull2.p, st);
-      a.tile_bbox = e->tile_bbox.p; a.tile_cull2 = e->tile_cull2.p; a.cull_tile = tile;
-      a.bbox_slack = 2.0f * (e->r_max - e->r_min);
-      ++e->launches;
+      const int c = e->cur;
+      bool have = e->bbox_valid[c] && e->bbox_tile[c] == tile;
+      // Boxes computed by a separate kernel read the WHOLE record table.  With the fused exchange attached that is only
+      // safe while no peer can be writing into it, i.e. right after a state upload / re-sort under a host barrier;
+      // otherwise the boxes come from the previous launch's last CTA (own tiles) and the peers' last CTAs, or -- tiles
+      // that straddle two ranks -- the step visits every tile.
+      if (!have && (e->n_peers == 0 || e->host_synced)) {
+        abm::launch_tile_bbox(a.rec_in, a.B, a.N, tile, e->tile_bbox[c].p, e->tile_cull2.p, st);
+        e->bbox_valid[c] = true; e->bbox_tile[c] = tile;
+        ++e->launches;
+        have = true;
+      }
+      if (have) {
+        a.tile_bbox = e->tile_bbox[c].p; a.tile_cull2 = e->tile_cull2.p; a.cull_tile = tile;
+        a.bbox_slack = 2.0f * (e->r_max - e->r_min);
+        const int end = e->tile_begin + e->tile_count;
+        next_boxes = fused_close && tile == abm::kWarpTile && a.B == 1 &&
+                     (e->tile_cycle > 1 || (e->tile_begin % tile == 0 && (end % tile == 0 || end == a.N)));
+      }
     }
+    e->bbox_valid[e->cur ^ 1] = false;
+    if (fused_close) {
+      if (!e->ticket.p) {
+        ABM_CUDA(e->ticket.alloc(1));
+        ABM_CUDA(cudaMemsetAsync(e->ticket.p, 0, sizeof(uint32_t), st));
+      }
+      a.step_ticket = e->ticket.p;
+      if (next_boxes) {
+        a.bbox_out = e->tile_bbox[e->cur ^ 1].p;
+        for (int p = 0; p < e->n_peers; ++p) a.peer_bbox_out[p] = e->peer_bbox[p][e->cur ^ 1];
+        e->bbox_valid[e->cur ^ 1] = true; e->bbox_tile[e->cur ^ 1] = abm::kWarpTile;
+      }
+    }
+    e->host_synced = false;
     if (use_sym) abm::launch_vf_step_sym(a, st);
     else if (use_warp) abm::launch_vf_step_warp(a, cull, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
-    if (e->n_peers > 0) { abm::launch_vf_publish(a, st); ++e->launches; }
+    if (e->n_peers > 0 && !fused_close) { abm::launch_vf_publish(a, st); ++e->launches; }
     e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : (use_warp ? "abm::vf_step_warp_kernel" : "abm::vf_step_kernel");
     if (use_sym) ++e->sym_launches;
     if (adaptive && use_sym && !e->slow_pending) {
@@ -712,9 +769,9 @@ int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent) {
 
 namespace {
 struct IpcExport {   // ABM_VF_IPC_BYTES
-  cudaIpcMemHandle_t rec[2], flags;
-  int32_t n_agents, tile_begin, tile_count, cur;
-  char pad[ABM_VF_IPC_BYTES - 3 * sizeof(cudaIpcMemHandle_t) - 16];
+  cudaIpcMemHandle_t rec[2], flags, bbox[2];
+  int32_t n_agents, tile_begin, tile_count, cur, has_bbox;
+  char pad[ABM_VF_IPC_BYTES - 5 * sizeof(cudaIpcMemHandle_t) - 20];
 };
 static_assert(sizeof(IpcExport) == ABM_VF_IPC_BYTES, "IpcExport layout");
 }  // namespace
@@ -732,6 +789,11 @@ int abm_vf_ipc_export(abm_engine_t* e, void* out) {
   ABM_CUDA(cudaIpcGetMemHandle(&x.rec[0], e->rec[0].p));
   ABM_CUDA(cudaIpcGetMemHandle(&x.rec[1], e->rec[1].p));
   ABM_CUDA(cudaIpcGetMemHandle(&x.flags, e->xflags.p));
+  if (e->tile_bbox[0].p && e->tile_bbox[1].p) {
+    ABM_CUDA(cudaIpcGetMemHandle(&x.bbox[0], e->tile_bbox[0].p));
+    ABM_CUDA(cudaIpcGetMemHandle(&x.bbox[1], e->tile_bbox[1].p));
+    x.has_bbox = 1;
+  }
   x.n_agents = e->cfg.n_agents; x.tile_begin = e->tile_begin; x.tile_count = e->tile_count; x.cur = e->cur;
   memcpy(out, &x, sizeof(x));
   return ABM_OK;
@@ -750,14 +812,22 @@ int abm_vf_ipc_attach(abm_engine_t* e, int n_ranks, int my_rank, const void* exp
     if (r == my_rank) continue;
     if (x[r].n_agents != e->cfg.n_agents || x[r].cur != e->cur)
       return fail(ABM_E_INVALID, "abm_vf_ipc_attach: the ranks' engines differ (n_agents / step parity)");
-    void* m[3];
+    if ((x[r].has_bbox != 0) != (e->tile_bbox[0].p != nullptr))
+      return fail(ABM_E_INVALID, "abm_vf_ipc_attach: the ranks' engines differ (spatial sort)");
+    void* m[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     ABM_CUDA(cudaIpcOpenMemHandle(&m[0], x[r].rec[0], cudaIpcMemLazyEnablePeerAccess));
     ABM_CUDA(cudaIpcOpenMemHandle(&m[1], x[r].rec[1], cudaIpcMemLazyEnablePeerAccess));
     ABM_CUDA(cudaIpcOpenMemHandle(&m[2], x[r].flags, cudaIpcMemLazyEnablePeerAccess));
-    for (int k = 0; k < 3; ++k) e->peer_maps[p][k] = m[k];
+    if (x[r].has_bbox) {
+      ABM_CUDA(cudaIpcOpenMemHandle(&m[3], x[r].bbox[0], cudaIpcMemLazyEnablePeerAccess));
+      ABM_CUDA(cudaIpcOpenMemHandle(&m[4], x[r].bbox[1], cudaIpcMemLazyEnablePeerAccess));
+    }
+    for (int k = 0; k < 5; ++k) e->peer_maps[p][k] = m[k];
     e->peer_rec[p][0] = static_cast<float4*>(m[0]);
     e->peer_rec[p][1] = static_cast<float4*>(m[1]);
     e->peer_flags[p] = static_cast<uint32_t*>(m[2]);
+    e->peer_bbox[p][0] = static_cast<float4*>(m[3]);
+    e->peer_bbox[p][1] = static_cast<float4*>(m[4]);
     ++p;
   }
   e->my_rank = my_rank;

@@ -68,6 +68,72 @@ __device__ __forceinline__ bool base_interval(const FocalExact& fe, double r, fl
   return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// fp32 fast path of the same obstacle (the scheme of the visual-flocking kernels): closed angle by rotation into the
+// heading frame + polynomial arctangent, bin index and half width by the 1.5 * 2^23 rounding constant, and a guard band
+// around every decision the float64 reference takes on a real number -- rounding tie of the bin index, integer
+// crossings of the half width (int() truncation of k -+ size / 2), the strict FOV bounds, the dead-ahead / dead-astern
+// angles the reference makes invisible (agent.py:520-523).  A pair inside a guard band is re-evaluated by
+// base_interval (fp64, the reference's own operation sequence); everything else has the reference's integers.
+// ---------------------------------------------------------------------------------------
+struct BaseFast {
+  float c, ns;                 // cos / -sin of the focal heading
+  float r;                     // focal radius (both centres, agent.py:504-509)
+  float fov0, fov1;            // strict bounds on the closed angle (agent.py:535)
+  float inv_step, t_half;      // (R - 1) / 2pi; 0.5 (even R) or 1.0 (odd R)
+  int k_off;                   // R/2 - 1 or (R - 3)/2: k = rint(ca * inv_step + t_half) + k_off
+  float y_scale;               // R / 2pi: size / 2 = atan(r / d) * y_scale
+  float thr_k, thr_h0, thr_h1; // guard bands in bins (abm_vf_device.cuh: BinConsts)
+};
+constexpr float kBaseAngleGuard = 4.0e-6f;   // rad: error bound of the fp32 closed angle (polynomial 1e-6 + rotation)
+
+__device__ __forceinline__ BaseFast base_fast_consts(float theta, double r, double fov0, double fov1, int R) {
+  BaseFast f;
+  float sn, cs;
+  sincosf(theta, &sn, &cs);
+  f.c = cs; f.ns = -sn;
+  f.r = (float)r;
+  f.fov0 = (float)fov0; f.fov1 = (float)fov1;
+  f.inv_step = (float)((double)(R - 1) / ABM_TWO_PI_D);
+  f.t_half = (R & 1) ? 1.0f : 0.5f;
+  f.k_off = (R & 1) ? (R - 3) / 2 : R / 2 - 1;
+  f.y_scale = (float)((double)R / ABM_TWO_PI_D);
+  const float tau_k = (float)(2.0e-6 * (double)R / ABM_TWO_PI_D + 2.5e-7 * (double)R + 1e-5);
+  f.thr_k = 0.5f - tau_k;
+  f.thr_h0 = 0.5f - 2.0e-5f - 0.5f * 3.0e-6f;
+  f.thr_h1 = -3.0e-6f;
+  return f;
+}
+
+// (dx, dy): position difference object - focal (fp32, one rounding).  Returns true when the pair must be re-evaluated
+// in fp64; otherwise `visible` and the raw interval ends (s, e) are the reference's.
+__device__ __forceinline__ bool base_interval_fast(float dx, float dy, const BaseFast& f, int& s, int& e, bool& visible) {
+  const float u = fmaf(dx, f.c, dy * f.ns);            //  dx cos - dy sin
+  const float w = fmaf(dx, f.ns, -(dy * f.c));         // -dx sin - dy cos: closed angle = atan2(w, u)
+  const float ca = atan2_fast(w, u);
+  const float aca = fabsf(ca);
+  bool flagged = (aca < kBaseAngleGuard) | (aca > 3.14159265f - kBaseAngleGuard);        // agent.py:520-523
+  flagged |= (fabsf(ca - f.fov0) < kBaseAngleGuard) | (fabsf(ca - f.fov1) < kBaseAngleGuard);
+  visible = (ca > f.fov0) & (ca < f.fov1);                                               // :535
+  const float t = fmaf(ca, f.inv_step, f.t_half);
+  const float tr = t + kMagic;
+  const int k = __float_as_int(tr) - kMagicBits + f.k_off;                               // :532
+  flagged |= fabsf(t - (tr - kMagic)) > f.thr_k;
+  const float d2 = fmaf(dx, dx, dy * dy);
+  const float q = f.r * rsqrt_approx(d2);                                                // r / d
+  const bool big = q > 1.0f;
+  float at = atan_unit(big ? rcp_approx(q) : q);
+  if (big) at = 1.57079632679489662f - at;
+  const float y = fmaf(at, f.y_scale, -0.5f);                                            // size / 2 - 0.5 (:529, :543)
+  const float yr = y + kMagic;
+  const int hf = __float_as_int(yr) - kMagicBits;                                        // floor(size / 2)
+  flagged |= !(fabsf(y - (yr - kMagic)) <= fmaf(y, f.thr_h1, f.thr_h0));                 // also NaN (d == 0)
+  // int(k - size/2), int(k + size/2): truncation toward zero (:545-546); size/2 is not an integer here
+  s = (k >= hf + 1) ? k - hf - 1 : k - hf;
+  e = k + hf;
+  return flagged;
+}
+
 // append this lane's object (if `rec`) in lane order; returns the new object count
 __device__ __forceinline__ int base_record(WarpField& wf, int M, bool rec, const ObjRec& o, int key, int lane) {
   const unsigned mask = __ballot_sync(0xffffffffu, rec);

@@ -48,6 +48,7 @@ struct __align__(32) PhiLut {
 struct VFKernelArgs {
   int B, N, R, W;                 // replicates, agents / replicate, bins, words / field
   int tile_begin, tile_count;     // focal agents handled by this engine
+  int tile_cycle, tile_phase;     // > 1: cyclic blocks of kWarpTile slots instead of the contiguous range (vf_tile_slot)
   int fov_px0, fov_px1;
   int boundary, limit_movement;
   int phi_ok;                     // len(arange grid) == R (vf_agent.py:267); else dv = dphi = 0
@@ -108,11 +109,23 @@ struct VFKernelArgs {
   float4* peer_rec_out[7];        // the peers' tables being written in this step
   uint32_t* peer_flags[7];        // the peers' flag arrays (entry my_rank is ours to write)
   uint32_t* xflags;               // this GPU's flag array [8]: xflags[r] = steps published by rank r
+  // the warp kernel closes a step of the fused exchange itself (abm_vf_warp.cu): its last CTA (ticket counter) computes
+  // the bounding boxes of this rank's record tiles in the table just written, stores them into every rank's box table
+  // of the next step and publishes the step
+  uint32_t* step_ticket;          // nullptr: no ticket / publish in this launch
+  float4* bbox_out;               // nullptr: the boxes of the next step are not produced by this launch
+  float4* peer_bbox_out[7];
   const PhiLut* lut;              // R + 1 entries
   uint32_t* fields_out;           // nullable, B*tile*W
   double* terms_out;              // nullable, B*tile*6
   unsigned long long* counters;   // 4
 };
+
+// internal slot of focal agent li of this engine's tile
+__host__ __device__ inline int vf_tile_slot(const VFKernelArgs& a, int li) {
+  if (a.tile_cycle <= 1) return a.tile_begin + li;
+  return (((li / kWarpTile) * a.tile_cycle + a.tile_phase) * kWarpTile) + (li % kWarpTile);
+}
 
 void launch_vf_step(const VFKernelArgs& a, bool uniform_r, bool cull, cudaStream_t stream);
 void launch_tile_bbox(const float4* rec, int B, int N, int tile, float4* bbox, float* cull2, cudaStream_t stream);
@@ -126,6 +139,7 @@ void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
 int vf_step_threads(int tile_count, int n_replicates, int n_sms);
 // warp-per-focal-agent kernel (abm_vf_warp.cu): one large sparse swarm and its tiles
 void launch_vf_step_warp(const VFKernelArgs& a, bool cull, cudaStream_t stream);
+int vf_warp_focal_per_cta(long long focal_total, int n_sms);
 struct VFPeerFlags { uint32_t* p[7]; };
 void launch_vf_publish(const VFKernelArgs& a, cudaStream_t stream);   // fused tile exchange: step done -> all ranks
 

@@ -1,79 +1,149 @@
-// Warp-per-focal-agent visual-flocking step kernel for sm_100a: the kernel for ONE LARGE, SPARSE swarm and for its
-// agent tiles on several GPUs.
+// Visual-flocking step kernel for ONE LARGE, SPARSE swarm, for its agent tiles on several GPUs, and for batches too small
+// to fill the GPU with a CTA per replicate (sm_100a).
 //
-// Why: with one thread per focal agent (abm_vf.cu) a 65 536-agent swarm is only 2048 warps -- 3.5 per scheduler on one
-// B200, 0.4 on each of 8 -- and every thread walks thousands of neighbour records in sequence: latency-bound (ncu: 32 %
-// of the issue slots).  Here a WARP owns a focal agent: its lanes stride over the neighbour records that survive the
-// tile-level culling (coalesced 512-byte reads straight from the L2-resident record table), evaluate the pair with the
-// same arithmetic as the symmetric kernel (32-bit binary angles, one IMAD.WIDE for bin + guard band; full-range
-// arctangent for the half width) and OR the interval into the warp's row in shared memory with RED.OR reductions
-// (abm_vf_sym.cu explains why those are cheap).  65 536 warps per step instead of 2048; per-lane culling costs no
-// divergence.  Guard-band hits are re-evaluated on the spot in fp64 (the reference's own operation sequence).
-// The epilogue is warp-cooperative: lanes take the words of the row, edge sums are reduced with shuffles, lane 0
-// finishes (terms, kinematics, walls / torus, outputs, peer stores of the fused tile exchange).
+// Mapping.  CTA = F consecutive focal agents of one replicate (spatially close when the engine keeps its Morton order)
+// x 256 threads.  The CTA builds ONE list of record tiles to visit (bounding box of its focal agents against the tiles'
+// boxes); its threads stride over the RECORDS of the listed tiles -- one coalesced 16-byte load per record from the
+// L2-resident table -- and evaluate every loaded record against all F focal agents (focal constants broadcast from
+// shared memory): F independent pair evaluations per load give the latency-bound loop its instruction-level
+// parallelism, all 8 warps of the CTA carry the same load whatever the focal agents see, and the work of a focal
+// agent in a dense region is spread over 256 threads instead of the 32 lanes of one warp.  F is chosen from the number
+// of focal agents of the launch (8 for a whole 65 536-agent swarm; 2 for an eighth of it on each of 8 GPUs; 1 for one
+// small run) so that the grid keeps every SM busy with several CTAs: the first version of this kernel gave each focal
+// agent one warp and an eighth of the swarm took almost as long as the whole (the warps of the agents in the dense
+// centre of the disc ran alone at the end).
+// Pair arithmetic as in the symmetric kernel (32-bit binary angles, one IMAD.WIDE for bin + guard band; full-range
+// arctangent for the half width); intervals are OR-ed into the focal agent's row in shared memory with RED.OR
+// (abm_vf_sym.cu explains why those are cheap); guard-band hits are re-evaluated on the spot in fp64 (the reference's own
+// operation sequence).  Epilogue: warp f takes focal agent f -- lanes take the words of the row, edge sums are reduced
+// with shuffles, lane 0 finishes (terms, kinematics, walls / torus, outputs, peer stores of the fused tile exchange).
 //
-// CTA = 8 warps = 8 consecutive focal agents of one replicate (spatially close when the engine keeps its Morton
-// order), sharing one list of record tiles to visit (bounding boxes, as in abm_vf.cu).
+// Fused tile exchange (abm_vf_ipc_attach; one process per GPU): a launch starts when every rank has published the
+// previous step (flags in this GPU's memory); the epilogue stores the new records into the peers' tables over NVLink;
+// the LAST CTA of the launch (ticket counter) computes the bounding boxes of this rank's record tiles for the next step,
+// stores them into every rank's box table, and publishes the step to all ranks (st.release.sys) -- one launch per step,
+// no collective, and nothing reads a table a peer may still be writing.
 #include "abm_vf_device.cuh"
 
 namespace abm {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpThreads = 256;
+constexpr int kWarpMaxFocal = 8;     // focal agents per CTA <= warps per CTA (a warp per focal agent in the epilogue)
 
-size_t vf_warp_smem_bytes(int W) {
-  return sizeof(uint32_t) * (size_t)(W + 1) * kWarpsPerCta + sizeof(int) * (kMaxTileList + 4) + 64;
+struct WarpFocal {                   // per focal agent of the CTA, in shared memory
+  float x, y, r;                     // top-left position, radius
+  uint32_t hc;                       // heading constant of the binary-angle bin index
+  FocalExact fe;                     // fp64 path (vf_pair_exact)
+};
+
+size_t vf_warp_smem_bytes(int W, int F) {
+  return sizeof(uint32_t) * (size_t)(W + 1) * F + sizeof(WarpFocal) * F + sizeof(int) * (kMaxTileList + 4) + 64;
 }
 
+// ordered-integer image of a float (monotonic for all finite values): min / max by integer atomics
+__device__ __forceinline__ int float_ordered(float v) {
+  const int b = __float_as_int(v);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// One (focal, record) pair: evaluate and OR the interval into the focal agent's row.
 template <bool TORUS, bool CULL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a) {
+__device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const WarpFocal& f, uint32_t row_s, const float4 o,
+                                          unsigned& n_fp64, unsigned& n_differ) {
+  const int R = a.R;
+  const float dr = o.z - f.r;
+  float dx = (o.x - f.x) + dr, dy = (o.y - f.y) + dr;   // positions first (exact for close neighbours), then radii
+  bool wrap_tie = false;
+  if (TORUS) {                                           // vf_supcalc.py:70-83
+    dx = torus_delta_r(o.x, f.x, dr, a.width, a.half_w, wrap_tie);
+    dy = torus_delta_r(o.y, f.y, dr, a.height, a.half_h, wrap_tie);
+  }
+  const float d2 = fmaf(dx, dx, dy * dy);
+  if (CULL) { if (d2 > o.w) return; }                    // beyond it the half width is 0
+  if ((o.x == f.x) & (o.y == f.y)) return;               // self / coincident positions (vf_supcalc.py:57)
+  const float q = o.z * rsqrt_approx(d2);
+  const float y = fmaf(atan_unit(q), a.y_scale, -0.5f);
+  const float yr = y + kMagic;
+  int h = __float_as_int(yr) - kMagicBits;
+  bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
+  int k = sym_side_k<0>(a, sym_bearing_bits(dx, dy, kBearingA6), f.hc, 0, flagged);   // bin index
+  if (flagged) {                                         // fp64, the reference's own operation sequence
+    const PairExact pe = vf_pair_exact(f.fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, R, a.lin_step);
+    ++n_fp64;
+    if (!pe.valid) return;
+    if ((pe.k != k) | (pe.h != h)) ++n_differ;
+    k = pe.k; h = pe.h;
+  }
+  const int ps = k - h, pe_ = k + h;
+  if (((unsigned)(h - 1) < 16u) & (ps >= 0) & (pe_ < R) &
+      (((a.fov_px0 < ps) & (ps < a.fov_px1)) | ((a.fov_px0 < pe_) & (pe_ < a.fov_px1)))) {
+    // interval of <= 32 bins inside the row: at most two words
+    const uint32_t m = 0xffffffffu >> (32 - 2 * h);
+    const uint32_t wa = row_s + 4u * (uint32_t)(ps >> 5);
+    red_or_shared(wa, __funnelshift_l(0u, m, ps));
+    const uint32_t hi = __funnelshift_l(m, 0u, ps);
+    if (hi) red_or_shared(wa + 4u, hi);
+  } else {
+    vf_draw_shared(row_s, 4u, R, a.fov_px0, a.fov_px1, k, h);   // wide / wrapping / outside the FOV: general rule
+  }
+}
+
+template <bool TORUS, bool CULL, int F>
+__global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw);                        // [warps][W + 1]
-  int* tile_list = reinterpret_cast<int*>(rows + (size_t)(a.W + 1) * kWarpsPerCta);   // [kMaxTileList] + count
-  float* fbox = reinterpret_cast<float*>(tile_list + kMaxTileList + 4);
+  WarpFocal* focal = reinterpret_cast<WarpFocal*>(smem_raw);                         // [F]
+  uint32_t* rows = reinterpret_cast<uint32_t*>(focal + F);                           // [F][W + 1]
+  int* tile_list = reinterpret_cast<int*>(rows + (size_t)(a.W + 1) * F);             // [kMaxTileList] + count
+  int* fbox = tile_list + kMaxTileList + 4;                                          // focal bounding box (ordered ints)
+  __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per_rep = (a.tile_count + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int per_rep = (a.tile_count + F - 1) / F;
   const int b = blockIdx.x / per_rep;
-  const int li = (blockIdx.x - b * per_rep) * kWarpsPerCta + warp;   // index inside this engine's focal tile
-  const bool active = li < a.tile_count;
-  const int i = a.tile_begin + (active ? li : 0);
-  const size_t gi = (size_t)b * a.N + i;
+  const int li0 = (blockIdx.x - b * per_rep) * F;          // first focal agent of the CTA inside this engine's tile
+  const int nf = min(F, a.tile_count - li0);               // focal agents of this CTA
   const float4* rep_in = a.rec_in + (size_t)b * a.N;
   const int R = a.R, W = a.W;
 
-  uint32_t* row = rows + (size_t)(W + 1) * warp;
-  for (int w = lane; w < W + 1; w += 32) row[w] = 0u;
-  if (a.n_peers > 0 && tid <= a.n_peers) {   // fused tile exchange: wait for every rank's previous step (abm_vf.cu)
-    const uint32_t* f = a.xflags + tid;
+  for (int w = tid; w < (W + 1) * F; w += kWarpThreads) rows[w] = 0u;
+  if (a.n_peers > 0 && tid <= a.n_peers) {   // fused tile exchange: wait for every rank's previous step (thread r: rank r)
+    const uint32_t* fl = a.xflags + tid;
     uint32_t v;
     do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
     } while ((int)(v - a.step_no) < 0);
   }
-  const float4 me = rep_in[i];
-  const float th = a.theta[gi];
+  if (tid < 4) fbox[tid] = (tid < 2) ? 0x7fffffff : (int)0x80000000;
+  if (tid == 0) tile_list[kMaxTileList] = 0;
+  __syncthreads();                                          // (also: nobody reads the record table before the hand-shake)
+  if (tid < nf) {                                           // focal constants, one thread per focal agent
+    const int i = vf_tile_slot(a, li0 + tid);
+    const float4 me = __ldcg(rep_in + i);
+    const float th = a.theta[(size_t)b * a.N + i];
+    WarpFocal f;
+    f.x = me.x; f.y = me.y; f.r = me.z;
+    f.hc = sym_heading_const(th);
+    f.fe = vf_focal_exact(me.x, me.y, me.z, th);
+    focal[tid] = f;
+    atomicMin(&fbox[0], float_ordered(me.x)); atomicMin(&fbox[1], float_ordered(me.y));
+    atomicMax(&fbox[2], float_ordered(me.x)); atomicMax(&fbox[3], float_ordered(me.y));
+  }
+  __syncthreads();
 
   // ---- record tiles to visit: bounding box of the CTA's focal agents against the tiles' boxes ----
-  const int tile_sz = a.tile_bbox != nullptr ? a.cull_tile : kRecTile;
+  const int tile_sz = a.tile_bbox != nullptr ? a.cull_tile : kRecTile;   // a power of two
+  const int tile_sh = 31 - __clz(tile_sz);
   const int n_tiles = (a.N + tile_sz - 1) / tile_sz;
   const bool use_list = CULL && a.tile_bbox != nullptr && n_tiles <= kMaxTileList;
   int n_stage = n_tiles;
   if (use_list) {
-    if (tid < 4) fbox[tid] = (tid < 2) ? 3.0e38f : -3.0e38f;
-    if (tid == 0) tile_list[kMaxTileList] = 0;
-    __syncthreads();
-    if (lane == 0 && active) {
-      atomicMin(reinterpret_cast<int*>(&fbox[0]), __float_as_int(fmaxf(me.x, 0.0f)));
-      atomicMin(reinterpret_cast<int*>(&fbox[1]), __float_as_int(fmaxf(me.y, 0.0f)));
-      atomicMax(reinterpret_cast<int*>(&fbox[2]), __float_as_int(fmaxf(me.x, 0.0f)));
-      atomicMax(reinterpret_cast<int*>(&fbox[3]), __float_as_int(fmaxf(me.y, 0.0f)));
-    }
-    __syncthreads();
-    const float fx0 = fbox[0], fy0 = fbox[1], fx1 = fbox[2], fy1 = fbox[3];
+    const float fx0 = ordered_float(fbox[0]), fy0 = ordered_float(fbox[1]);
+    const float fx1 = ordered_float(fbox[2]), fy1 = ordered_float(fbox[3]);
     const float4* bb = a.tile_bbox + (size_t)b * n_tiles;
     const float* c2 = a.tile_cull2 + (size_t)b * n_tiles;
-    for (int t = tid; t < n_tiles; t += blockDim.x) {
-      const float4 q = bb[t];
+    for (int t = tid; t < n_tiles; t += kWarpThreads) {
+      const float4 q = __ldcg(bb + t);
       float gx = fmaxf(0.0f, fmaxf(q.x - fx1, fx0 - q.z));
       float gy = fmaxf(0.0f, fmaxf(q.y - fy1, fy0 - q.w));
       if (TORUS) {   // minimal image: the tile shifted by one period either way
@@ -87,68 +157,37 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
     }
     __syncthreads();
     n_stage = tile_list[kMaxTileList];
-  } else {
-    __syncthreads();
   }
 
-  // ---- pair loop: lanes stride over the records of the visited tiles ----
+  // ---- pair loop: threads stride over the records of the visited tiles, every record against all focal agents ----
   unsigned n_fp64 = 0, n_differ = 0;
-  if (active) {
-    const uint32_t hc = sym_heading_const(th);
-    const FocalExact fe = vf_focal_exact(me.x, me.y, me.z, th);
-    const uint32_t row_s = smem_u32(row);
-    for (int st = 0; st < n_stage; ++st) {
-      const int t = use_list ? tile_list[st] : st;
-      const int j0 = t * tile_sz, j1 = min(a.N, j0 + tile_sz);
-      for (int j = j0 + lane; j < j1; j += 32) {
-        const float4 o = __ldg(rep_in + j);
-        const float dr = o.z - me.z;
-        float dx = (o.x - me.x) + dr, dy = (o.y - me.y) + dr;   // positions first (exact for close neighbours), then radii
-        bool wrap_tie = false;
-        if (TORUS) {                                           // vf_supcalc.py:70-83
-          dx = torus_delta_r(o.x, me.x, dr, a.width, a.half_w, wrap_tie);
-          dy = torus_delta_r(o.y, me.y, dr, a.height, a.half_h, wrap_tie);
-        }
-        const float d2 = fmaf(dx, dx, dy * dy);
-        if (CULL) { if (d2 > o.w) continue; }                  // beyond it the half width is 0
-        if ((o.x == me.x) & (o.y == me.y)) continue;           // self / coincident positions (vf_supcalc.py:57)
-        const float q = o.z * rsqrt_approx(d2);
-        const float y = fmaf(atan_unit(q), a.y_scale, -0.5f);
-        const float yr = y + kMagic;
-        int h = __float_as_int(yr) - kMagicBits;
-        bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
-        int k = sym_side_k<0>(a, sym_bearing_bits(dx, dy, kBearingA6), hc, 0, flagged);   // bin index
-        if (flagged) {                                         // fp64, the reference's own operation sequence
-          const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, R, a.lin_step);
-          ++n_fp64;
-          if (!pe.valid) continue;
-          if ((pe.k != k) | (pe.h != h)) ++n_differ;
-          k = pe.k; h = pe.h;
-        }
-        const int ps = k - h, pe_ = k + h;
-        if (((unsigned)(h - 1) < 16u) & (ps >= 0) & (pe_ < R) &
-            (((a.fov_px0 < ps) & (ps < a.fov_px1)) | ((a.fov_px0 < pe_) & (pe_ < a.fov_px1)))) {
-          // interval of <= 32 bins inside the row: at most two words
-          const uint32_t m = 0xffffffffu >> (32 - 2 * h);
-          const uint32_t wa = row_s + 4u * (uint32_t)(ps >> 5);
-          red_or_shared(wa, __funnelshift_l(0u, m, ps));
-          const uint32_t hi = __funnelshift_l(m, 0u, ps);
-          if (hi) red_or_shared(wa + 4u, hi);
-        } else {
-          vf_draw_shared(row_s, 4u, R, a.fov_px0, a.fov_px1, k, h);   // wide / wrapping / outside the FOV: general rule
-        }
-      }
+  {
+    const uint32_t rows_s = smem_u32(rows);
+    const int total = n_stage << tile_sh;
+    for (int idx = tid; idx < total; idx += kWarpThreads) {
+      const int st = idx >> tile_sh;
+      const int j = ((use_list ? tile_list[st] : st) << tile_sh) + (idx & (tile_sz - 1));
+      if (j >= a.N) continue;
+      const float4 o = __ldcg(rep_in + j);
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+        if (f < nf) warp_pair<TORUS, CULL>(a, focal[f], rows_s + 4u * (uint32_t)((W + 1) * f), o, n_fp64, n_differ);
     }
   }
-  __syncwarp();
   {
-    const unsigned nf = __reduce_add_sync(0xffffffffu, n_fp64), nd = __reduce_add_sync(0xffffffffu, n_differ);
-    if (lane == 0 && nf) atomicAdd(&a.counters[0], (unsigned long long)nf);
+    const unsigned nfp = __reduce_add_sync(0xffffffffu, n_fp64), nd = __reduce_add_sync(0xffffffffu, n_differ);
+    if (lane == 0 && nfp) atomicAdd(&a.counters[0], (unsigned long long)nfp);
     if (lane == 0 && nd) atomicAdd(&a.counters[2], (unsigned long long)nd);
   }
+  __syncthreads();
 
-  // ---- epilogue: lanes take the words of the row, edge sums reduced with shuffles ----
-  if (active) {
+  // ---- epilogue: warp f takes focal agent f; lanes take the words of the row, edge sums reduced with shuffles ----
+  if (warp < nf) {
+    const int li = li0 + warp;
+    const int i = vf_tile_slot(a, li);
+    const size_t gi = (size_t)b * a.N + i;
+    const uint32_t* row = rows + (size_t)(W + 1) * warp;
+    const WarpFocal& me = focal[warp];
     const uint32_t last_valid = (R & 31) ? ((1u << (R & 31)) - 1u) : 0xffffffffu;
     const uint32_t v_first = row[0] & 1u;
     const uint32_t v_last = (row[W - 1] >> ((R - 1) & 31)) & 1u;
@@ -181,6 +220,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
       if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
       if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
       const double vel0 = a.vel[gi];
+      const float th = a.theta[gi];
       FlockTerms ft;
       if (a.phi_ok) {
         EdgeSums z;
@@ -198,9 +238,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
       sincos(nth, &sn, &cn);
       double nx = (double)me.x + nv * cn;                           // :303-306
       double ny = (double)me.y - nv * sn;
-      if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
-      else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
-      const float4 rec_new = make_float4((float)nx, (float)ny, me.z, me.w);
+      if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.r, a.width_d, a.height_d, a.pad_d);
+      else teleport_torus(nx, ny, (double)me.r, a.width_d, a.height_d, a.pad_d);
+      const float4 rec_new = make_float4((float)nx, (float)ny, me.r, rep_in[i].w);
       a.rec_out[gi] = rec_new;
       if (a.n_peers > 0) {                                            // NVLink peer stores (fused tile exchange)
         for (int p = 0; p < a.n_peers; ++p) a.peer_rec_out[p][gi] = rec_new;
@@ -220,18 +260,82 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) vf_step_warp_kernel(const _
     }
   }
 
+  // ---- fused tile exchange: the LAST CTA of the launch closes the step for this rank ----
+  if (a.step_ticket == nullptr) return;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();                                   // this CTA's records (local and peer stores) before its ticket
+    s_last = (atomicAdd(a.step_ticket, 1u) == gridDim.x - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();                                            // every CTA's records are visible to this one
+  if (a.bbox_out != nullptr) {
+    // bounding boxes of this rank's record tiles in the table just written (B == 1), a warp per tile
+    // (own tiles: the contiguous range, or every tile_cycle-th tile from tile_phase on)
+    const bool cyc = a.tile_cycle > 1;
+    const int t0 = cyc ? a.tile_phase : a.tile_begin >> tile_sh;
+    const int t1 = cyc ? n_tiles : (a.tile_begin + a.tile_count + tile_sz - 1) >> tile_sh;
+    const int dt = cyc ? a.tile_cycle : 1;
+    for (int t = t0 + warp * dt; t < t1; t += (kWarpThreads / 32) * dt) {
+      float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
+      for (int j = (t << tile_sh) + lane; j < min(a.N, (t + 1) << tile_sh); j += 32) {
+        const float4 v = __ldcg(a.rec_out + j);
+        x0 = fminf(x0, v.x); y0 = fminf(y0, v.y); x1 = fmaxf(x1, v.x); y1 = fmaxf(y1, v.y);
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, off)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, off));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, off)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, off));
+      }
+      if (lane == 0) {
+        const float4 box = make_float4(x0, y0, x1, y1);
+        a.bbox_out[t] = box;
+        for (int p = 0; p < a.n_peers; ++p) a.peer_bbox_out[p][t] = box;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *a.step_ticket = 0u;                                      // for the next launch (stream order)
+    __threadfence_system();
+    const uint32_t done = a.step_no + 1u;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.xflags + a.my_rank), "r"(done) : "memory");
+    for (int p = 0; p < a.n_peers; ++p)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[p] + a.my_rank), "r"(done) : "memory");
+  }
 }
 
-template <bool TORUS, bool CULL>
+// focal agents per CTA: as many as keep >= 16 CTAs per SM in the grid
+int vf_warp_focal_per_cta(long long focal_total, int n_sms) {
+  int F = kWarpMaxFocal;
+  while (F > 1 && focal_total / F < 16LL * n_sms) F >>= 1;
+  return F;
+}
+
+template <bool TORUS, bool CULL, int F>
 static void launch_warp_variant(const VFKernelArgs& a, cudaStream_t stream) {
-  const int per_rep = (a.tile_count + kWarpsPerCta - 1) / kWarpsPerCta;
-  const size_t smem = vf_warp_smem_bytes(a.W);
-  vf_step_warp_kernel<TORUS, CULL><<<(unsigned)((size_t)a.B * per_rep), kWarpsPerCta * 32, smem, stream>>>(a);
+  const int per_rep = (a.tile_count + F - 1) / F;
+  const size_t smem = vf_warp_smem_bytes(a.W, F);
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, F>, smem);
+  vf_step_warp_kernel<TORUS, CULL, F><<<(unsigned)((size_t)a.B * per_rep), kWarpThreads, smem, stream>>>(a);
+}
+template <bool TORUS, bool CULL>
+static void launch_warp_f(const VFKernelArgs& a, int F, cudaStream_t stream) {
+  switch (F) {
+    case 8: launch_warp_variant<TORUS, CULL, 8>(a, stream); break;
+    case 4: launch_warp_variant<TORUS, CULL, 4>(a, stream); break;
+    case 2: launch_warp_variant<TORUS, CULL, 2>(a, stream); break;
+    default: launch_warp_variant<TORUS, CULL, 1>(a, stream); break;
+  }
 }
 
 void launch_vf_step_warp(const VFKernelArgs& a, bool cull, cudaStream_t stream) {
-  if (a.boundary == 1) { if (cull) launch_warp_variant<true, true>(a, stream); else launch_warp_variant<true, false>(a, stream); }
-  else { if (cull) launch_warp_variant<false, true>(a, stream); else launch_warp_variant<false, false>(a, stream); }
+  const char* env = getenv("ABM_VF_WARP_FOCAL");              // measurement probes only
+  int F = env ? atoi(env) : vf_warp_focal_per_cta((long long)a.B * a.tile_count, a.n_sms);
+  if (F != 1 && F != 2 && F != 4 && F != 8) F = 1;
+  if (a.boundary == 1) { if (cull) launch_warp_f<true, true>(a, F, stream); else launch_warp_f<true, false>(a, F, stream); }
+  else { if (cull) launch_warp_f<false, true>(a, F, stream); else launch_warp_f<false, false>(a, F, stream); }
 }
 
 }  // namespace abm

@@ -44,7 +44,10 @@ class VFEngine:
                  window_pad: float = 30.0, limit_movement: bool = False, max_vel: float = 3.0,
                  max_th: float = 0.1, exact_fixup: bool = True, keep_fields: bool = False,
                  keep_terms: bool = False, device: int = 0, tile: tuple[int, int] | None = None,
-                 spatial_sort: bool = True, resort_every: int = 32):
+                 tile_cycle: tuple[int, int] | None = None, spatial_sort: bool = True, resort_every: int = 32):
+        """``tile`` = (begin, count): this engine updates that contiguous range of (internal) agent slots of one large
+        swarm; ``tile_cycle`` = (G, r): it updates every G-th block of 128 slots starting with block r (balanced work
+        across G GPUs whatever the density distribution); both read all N neighbour records."""
         if boundary not in ("walls", "infinite"):
             raise ValueError(f"boundary must be 'walls' or 'infinite', got {boundary!r}")
         self._lib = _lib.load()
@@ -52,6 +55,12 @@ class VFEngine:
         self.W = (self.R + 31) // 32
         self.device = int(device)
         self.tile_begin, self.tile_count = (0, self.N) if tile is None else (int(tile[0]), int(tile[1]))
+        cyc, phase = (0, 0) if tile_cycle is None else (int(tile_cycle[0]), int(tile_cycle[1]))
+        if cyc > 1:
+            if tile is not None:
+                raise ValueError("give either tile or tile_cycle")
+            self.tile_begin, self.tile_count = 0, self.N // cyc
+        self.tile_cycle, self.tile_phase = cyc, phase
         f0, f1 = _fov_pixels(self.R, fov)
         flags = (_lib.VF_EXACT_FIXUP if exact_fixup else 0) | (_lib.VF_KEEP_FIELDS if keep_fields else 0) \
             | (_lib.VF_KEEP_TERMS if keep_terms else 0) | (_lib.VF_SPATIAL_SORT if spatial_sort else 0)
@@ -61,8 +70,8 @@ class VFEngine:
             boundary=_lib.BOUNDARY_INFINITE if boundary == "infinite" else _lib.BOUNDARY_WALLS,
             limit_movement=int(bool(limit_movement)), width=float(width), height=float(height),
             window_pad=float(window_pad), max_vel=float(max_vel), max_th=float(max_th), flags=flags,
-            tile_begin=self.tile_begin, tile_count=0 if tile is None else self.tile_count,
-            resort_every=int(resort_every))
+            tile_begin=self.tile_begin, tile_count=0 if (tile is None and cyc <= 1) else self.tile_count,
+            resort_every=int(resort_every), tile_cycle=cyc, tile_phase=phase)
         self._h = C.c_void_p()
         _lib.check(self._lib.abm_vf_create(C.byref(cfg), self.device, C.byref(self._h)), "abm_vf_create")
         self.keep_fields, self.keep_terms = keep_fields, keep_terms
@@ -223,10 +232,18 @@ class VFEngine:
         _lib.check(self._lib.abm_synchronize(self._h, C.c_void_p(_current_stream())), "abm_synchronize")
 
     # -- outputs of the last step ----------------------------------------------------------
+    def tile_slots(self) -> np.ndarray:
+        """Internal slot of every focal agent li of this engine's tile (contiguous range or cyclic blocks)."""
+        li = np.arange(self.tile_count)
+        if self.tile_cycle > 1:
+            blk = _lib.VF_TILE_BLOCK
+            return ((li // blk) * self.tile_cycle + self.tile_phase) * blk + li % blk
+        return self.tile_begin + li
+
     def fields_packed(self) -> np.ndarray:
         """(B, tile, W) uint32, STORED (flipped) order like Agent.soc_v_field.  Rows are in the caller's agent order;
         on a TILED engine with the spatial sort on they are in internal slot order (row li = agent
-        ``permutation()[b, tile_begin + li]``), like `terms()`."""
+        ``permutation()[b, tile_slots()[li]]``), like `terms()`."""
         out = np.empty((self.B, self.tile_count, self.W), np.uint32)
         _lib.check(self._lib.abm_get_fields(self._h, C.c_void_p(out.ctypes.data), 0, C.c_void_p(_current_stream())),
                    "abm_get_fields")

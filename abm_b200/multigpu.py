@@ -26,6 +26,25 @@ def agent_tile(n_agents: int, world: int, rank: int) -> tuple[int, int]:
     return rank * count, count
 
 
+def cyclic_slots(n_agents: int, world: int, rank: int, block: int = 128) -> np.ndarray:
+    """Slots owned by `rank` when the blocks of `block` consecutive slots are dealt to the ranks round robin (the
+    engine's tile_cycle): balanced work whatever the density distribution along the spatially sorted order."""
+    if n_agents % (world * block):
+        raise ValueError(f"n_agents ({n_agents}) must be a multiple of ranks * {block} ({world * block})")
+    li = np.arange(n_agents // world)
+    return ((li // block) * world + rank) * block + li % block
+
+
+def gather_cyclic(local: "torch.Tensor", world: int, block: int = 128, group=None) -> "torch.Tensor":
+    """All-gather of cyclic tiles (`local` = this rank's slots in tile order) into slot order."""
+    import torch
+    import torch.distributed as dist
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    stacked = torch.stack([p.view(-1, block) for p in parts], dim=1)     # (blocks per rank, world, block)
+    return stacked.reshape(-1)
+
+
 def gather_tiles(local: "torch.Tensor", world: int, group=None) -> "torch.Tensor":
     """All-gather of equal tiles along dim 0 (works on gloo/CPU and nccl/CUDA)."""
     import torch
@@ -57,11 +76,17 @@ class TiledSwarm:
         self.torch, self.dist, self.group = torch, dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.N = int(n_agents)
-        self.begin, self.count = agent_tile(self.N, self.world, self.rank)
-        self.engine = VFEngine(1, self.N, tile=(self.begin, self.count), device=torch.cuda.current_device(),
-                               **engine_kwargs)
-        self._tables = {}
         self.fused = bool(fused) and self.world > 1
+        self.begin, self.count = agent_tile(self.N, self.world, self.rank)
+        # fused exchange: cyclic blocks of 128 slots (balanced work: a contiguous range of the sorted order is a region
+        # of the arena, and the regions of the reference's disc initial condition differ in density by a factor of ten);
+        # the in-place all-gather of the NCCL path needs the contiguous range
+        self.cyclic = self.fused and self.N % (self.world * 128) == 0
+        tile_kw = dict(tile_cycle=(self.world, self.rank)) if self.cyclic else \
+            (dict(tile=(self.begin, self.count)) if self.world > 1 else {})
+        self.engine = VFEngine(1, self.N, device=torch.cuda.current_device(), **tile_kw, **engine_kwargs)
+        self._slots = torch.from_numpy(self.engine.tile_slots()).cuda()
+        self._tables = {}
         if self.fused:
             mine = torch.frombuffer(bytearray(self.engine.ipc_export()), dtype=torch.uint8).cuda()
             every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device="cuda")
@@ -116,7 +141,10 @@ class TiledSwarm:
         if self.fused:
             self._barrier()
         for t in self._internal():
-            self.dist.all_gather_into_tensor(t, t[self.begin:self.begin + self.count].clone(), group=self.group)
+            if self.cyclic:
+                t.copy_(gather_cyclic(t[self._slots], self.world, group=self.group))
+            else:
+                self.dist.all_gather_into_tensor(t, t[self.begin:self.begin + self.count].clone(), group=self.group)
         self.engine.resort()
         self._tables = {}
         if self.fused:
@@ -131,7 +159,10 @@ class TiledSwarm:
         out = {"x": st["x"][0], "y": st["y"][0]}
         perm = self.engine.permutation()[0]
         for k, t in zip(("theta", "vel"), self._internal()):
-            full = gather_tiles(t[self.begin:self.begin + self.count].clone(), self.world, self.group).cpu().numpy()
+            if self.cyclic:
+                full = gather_cyclic(t[self._slots], self.world, group=self.group).cpu().numpy()
+            else:
+                full = gather_tiles(t[self.begin:self.begin + self.count].clone(), self.world, self.group).cpu().numpy()
             api = np.empty_like(full)
             api[perm] = full
             out[k] = api

@@ -278,6 +278,81 @@ def parity_check(VFEngine, local_rank, x, y, th, v, rad, n_check=3):
             "ok": bool(bits == 0 and rel_terms < 1e-5 and rel_state < 1e-5)}
 
 
+def swarm_arm(VFEngine, local_rank, rank, world, dist, steps=20):
+    """BASELINE configs[4]: ONE swarm of 65 536 agents (visual flocking, R = 1200, arena 23 040 px, walls, disc initial
+    condition), agent tiles sharded across the ranks; the only data exchanged per step are the 16-byte records
+    (1 MiB), stored by the step kernel straight into the peers' tables over NVLink (abm_b200/multigpu.TiledSwarm,
+    fused=True).  STRONG scaling: total work fixed.  Reports ms per step (CUDA events, max over ranks),
+    the same swarm on ONE GPU timed by rank 0 in the same process, whether the sharded run ends in the single-GPU run's
+    exact state, and an oracle check of sampled agents of the 65 536-agent scene."""
+    import torch
+    from abm_b200.multigpu import TiledSwarm
+    from oracle import restate as rs
+    N = int(os.environ.get("ABM_BENCH_SWARM_AGENTS", 65536))
+    W = arena_side(N)
+    x, y, th, v = synthetic_state(1, N)
+    kw = dict(resolution=R, width=W, height=W, boundary="walls")
+    warm = 4
+    out = {"n_agents": N, "arena_px": W, "steps": steps, "boundary": "walls"}
+
+    def timed(step_fn):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record(); step_fn(steps); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ref_state = None
+    if rank == 0:      # the same swarm on one GPU: oracle spot check after one step, reference state, 1-GPU time
+        e1 = VFEngine(1, N, device=local_rank, keep_fields=True, keep_terms=True, **kw)
+        e1.set_params(**PARAMS); e1.set_state(x, y, th, v, RADIUS); e1.step(1)
+        sample = sorted(np.random.default_rng(5).choice(N, 8, replace=False).tolist())
+        cfg = rs.VFConfig(R=R, width=W, height=W, **PARAMS)
+        ref = rs.vf_step_frozen(x[0], y[0], th[0], v[0], RADIUS, cfg, agents=sample)
+        f1, t1, s1 = e1.fields()[0], e1.terms()[0], e1.get_state()
+        bits = int((f1[sample] != ref["rows"][sample][:, ::-1]).sum())
+        rel = float(np.max(np.abs(t1[sample] - ref["terms"][sample]) / np.maximum(np.abs(ref["terms"][sample]), 1e-6)))
+        for k in ("x", "y", "theta", "vel"):
+            rel = max(rel, float(np.max(np.abs(s1[k][0][sample] - ref[k][sample]) / np.maximum(np.abs(ref[k][sample]), 1e-3))))
+        out["oracle_check"] = {"agents": sample, "field_bits_differ": bits, "max_rel": rel,
+                               "ok": bool(bits == 0 and rel < 1e-5), "kernel": e1.last_kernel()}
+        e1.step(warm - 1)
+        ref_state = e1.get_state()
+    if world == 1:
+        ms1 = timed(e1.step)
+        out.update(ms_per_step=ms1, ms_per_step_1gpu=ms1, exchange="none (one GPU)", strong_scaling_eff=1.0,
+                   bit_identical_to_1gpu=True, agent_steps_per_s=N / ms1 * 1e3)
+        e1.close()
+        return out
+    # rank 0 times the single-GPU swarm while the other ranks wait at the barrier inside timed()
+    t1gpu = torch.zeros(1, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        e0 = torch.cuda.Event(enable_timing=True); e1e = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(); e1.step(steps); e1e.record(); torch.cuda.synchronize()
+        t1gpu[0] = e0.elapsed_time(e1e) / steps
+        e1.close()
+    dist.broadcast(t1gpu, 0)
+    swarm = TiledSwarm(N, fused=True, **kw)
+    swarm.set_params(**PARAMS)
+    swarm.set_state(x, y, th, v, RADIUS)
+    swarm.step(warm)
+    got = swarm.get_state()
+    same = True
+    if rank == 0:
+        same = all(np.array_equal(got[k], ref_state[k][0]) for k in ("x", "y", "theta", "vel"))
+    ms = torch.tensor([timed(swarm.step)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    flag = torch.tensor([1 if same else 0], device="cuda"); dist.broadcast(flag, 0)
+    swarm.engine.close()
+    ms, t1 = float(ms.item()), float(t1gpu.item())
+    out.update(ms_per_step=ms, ms_per_step_1gpu=t1, exchange="peer-store" if swarm.fused else "nccl",
+               tiles="cyclic blocks of 128 slots" if swarm.cyclic else "contiguous", strong_scaling_eff=t1 / (world * ms),
+               bit_identical_to_1gpu=bool(flag.item()), agent_steps_per_s=N / ms * 1e3)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,6 +509,12 @@ def main():
                    ok=all(g["ok"] for g in gathered), ranks=world,
                    kernels=sorted({g["kernel"] for g in gathered}))
     par["same_kernel_as_timed"] = par["kernel"] == timed_kernel
+    eng.close()
+
+    # ---- BASELINE configs[4]: one swarm of 65 536 agents, agent tiles sharded across the ranks ----
+    swarm = None
+    if os.environ.get("ABM_BENCH_SWARM", "1") != "0":
+        swarm = swarm_arm(VFEngine, local_rank, rank, world, dist)
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -470,7 +551,10 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(eng.last_kernel()), "kernel": eng.last_kernel(), "algorithmic_ops_per_launch": ops_launch,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(timed_kernel), "kernel": timed_kernel,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, committed `ncu --set full` "
+                                           "capture under profiles/ (not measured in this run)",
+                         "algorithmic_ops_per_launch": ops_launch,
                          "visible_pair_fraction": vis, "peak_source": f"{sms} SMs x 128 lanes x "
                          f"{sm_clock / 1e6:.0f} MHz ({peak_kind} sm_max_mhz)",
                          "hbm": {"achieved": bytes_launch / avg_s / 1e9, "peak": peaks.get("hbm_gbs"),
@@ -480,6 +564,7 @@ def main():
             "fp64_pairs_fraction": counters["fp64_pairs"] / float(pairs * counters["launches"]),
             "wall_s_timed_region": t_wall,
             "parity": par,
+            "swarm": swarm,
         }
         if not args.no_cpu_baseline and world == 1:
             os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -489,7 +574,6 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": cpu_sample_text(kind, n_focal, N, 1, dt)}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -90,7 +90,16 @@ typedef struct {
   int32_t tile_count;
   int32_t resort_every;   /* with ABM_VF_SPATIAL_SORT: re-sort after this many steps (0: only when the state is set
                              or abm_vf_resort is called) */
+  /* Cyclic agent tiles (load balance of one large swarm across G GPUs: a contiguous range of the spatially sorted
+   * order is a REGION of the arena, and regions differ in density by an order of magnitude on the reference's disc
+   * initial condition): with tile_cycle = G > 1 this engine owns the blocks of ABM_VF_TILE_BLOCK consecutive internal
+   * slots whose block index is congruent to tile_phase modulo G; tile_begin is ignored, tile_count must be
+   * n_agents / G and n_agents a multiple of G * ABM_VF_TILE_BLOCK.  Focal agent li of the tile is slot
+   * ((li / BLOCK) * G + tile_phase) * BLOCK + li % BLOCK.  0 / 1: the contiguous tile above. */
+  int32_t tile_cycle;
+  int32_t tile_phase;
 } abm_vf_config_t;
+#define ABM_VF_TILE_BLOCK 128
 
 /* The six per-replicate flocking parameters, in this order (vf_params.py:12-19;
  * ALP2/BET2 multiply an all-zero dt_V at vf_supcalc.py:199 and do not exist here). */
@@ -139,8 +148,9 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream);
 /* Packed STORED fields of the last step, n_replicates*tile*abm_field_words(R) words
  * (needs ABM_VF_KEEP_FIELDS).  Replaces reading Agent.soc_v_field (vf_agent.py:209).
  * Row order: the caller's agent order for an engine that owns whole replicates.  A TILED engine (tile_count != 0)
- * with ABM_VF_SPATIAL_SORT owns the internal slots [tile_begin, tile_begin + tile_count): its rows (and those of
- * abm_vf_get_terms) are in slot order, row li = the agent abm_vf_get_permutation reports for slot tile_begin + li. */
+ * with ABM_VF_SPATIAL_SORT owns the internal slots [tile_begin, tile_begin + tile_count) (or the cyclic blocks of
+ * tile_cycle): its rows (and those of abm_vf_get_terms) are in the order of its focal agents li, row li = the agent
+ * abm_vf_get_permutation reports for that focal agent's slot. */
 int abm_get_fields(abm_engine_t* e, uint32_t* packed, int on_device, void* stream);
 
 /* (dvel, dpsi, a_blob, a_edge, b_blob, b_edge) per agent of the last step, 6 doubles each
@@ -174,7 +184,7 @@ int abm_vf_get_permutation(abm_engine_t* e, int32_t* perm, int on_device, void* 
  *   abm_vf_ipc_attach  <- the exports of ALL ranks in rank order (this engine's own entry at `my_rank` is skipped).
  * All ranks must then call abm_vf_step the same number of times; abm_set_state on an attached engine needs a barrier
  * between the ranks before the next step (the host's job). */
-#define ABM_VF_IPC_BYTES 256
+#define ABM_VF_IPC_BYTES 512
 int abm_vf_ipc_export(abm_engine_t* e, void* out);
 int abm_vf_ipc_attach(abm_engine_t* e, int n_ranks, int my_rank, const void* exports);
 int abm_vf_resort(abm_engine_t* e, void* stream);

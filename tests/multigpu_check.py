@@ -21,7 +21,7 @@ def main():
     from abm_b200 import VFEngine
     from abm_b200.multigpu import TiledSwarm
     N = 4096 if len(sys.argv) < 2 else int(sys.argv[1])
-    steps = 4
+    steps = 12
     W = float(np.ceil(900 * np.sqrt(N / 100)))
     rng = np.random.default_rng(99)
     th = rng.uniform(0, 2 * np.pi, N).astype(np.float32)
@@ -29,19 +29,21 @@ def main():
     x = (W / 2 + rho * np.cos(th)).astype(np.float32)
     y = (W / 2 + rho * np.sin(th)).astype(np.float32)
     v = np.zeros(N, np.float32)
-    kw = dict(resolution=1200, width=W, height=W, boundary="infinite")
     ok = True
-    ref_state = None
-    if rank == 0:
-        ref = VFEngine(1, N, **kw)
-        ref.set_params(); ref.set_state(x[None], y[None], th[None], v[None], 10.0); ref.step(steps)
-        ref_state = ref.get_state()
-        ref.close()
-    for fused in (True, False):
+    for boundary, fused in (("infinite", True), ("infinite", False), ("walls", True)):
+        kw = dict(resolution=1200, width=W, height=W, boundary=boundary)
+        ref_state = None
+        if rank == 0:
+            ref = VFEngine(1, N, **kw)
+            ref.set_params(); ref.set_state(x[None], y[None], th[None], v[None], 10.0); ref.step(steps)
+            ref_state = ref.get_state()
+            ref.close()
         swarm = TiledSwarm(N, fused=fused, **kw)
         swarm.set_params()
         swarm.set_state(x[None], y[None], th[None], v[None], 10.0)
-        swarm.step(steps)
+        swarm.step(steps // 2)
+        swarm.resync()                          # headings / speeds to every rank + spatial re-sort, mid-run
+        swarm.step(steps - steps // 2)
         got = swarm.get_state()
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -52,9 +54,10 @@ def main():
             for k in ("x", "y", "theta", "vel"):
                 same = np.array_equal(got[k], ref_state[k][0])
                 ok &= same
-                print(f"[tiled x{world} {'fused peer stores' if fused else 'NCCL all-gather'}] {k}: "
+                print(f"[tiled x{world} {boundary} {'fused peer stores' if fused else 'NCCL all-gather'}] {k}: "
                       f"{'bit-identical' if same else 'MISMATCH'}", flush=True)
-            print(f"[tiled x{world} {'fused peer stores' if fused else 'NCCL all-gather'}] N={N}: {ms:.3f} ms/step", flush=True)
+            print(f"[tiled x{world} {boundary} {'fused peer stores' if fused else 'NCCL all-gather'}"
+                  f"{' cyclic tiles' if swarm.cyclic else ''}] N={N}: {ms:.3f} ms/step", flush=True)
         dist.barrier()
         swarm.engine.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -29,7 +29,7 @@ def test_python_binding_covers_header(built_lib):
 
 def test_struct_sizes_match_header_layout():
     from abm_b200 import _lib
-    assert C.sizeof(_lib.VFConfig) == 17 * 4
+    assert C.sizeof(_lib.VFConfig) == 19 * 4
     assert C.sizeof(_lib.VFProjArgs) == 8 + 6 * 8 + 8 + 3 * 8 + 8 + 3 * 8
     assert C.sizeof(_lib.CSProjArgs) == 8 + 6 * 8 + 8 + 2 * 8 + 8
 

@@ -31,6 +31,17 @@ def test_agent_tiles():
         pass
 
 
+def test_cyclic_slots():
+    s = [mg.cyclic_slots(2048, 4, r) for r in range(4)]
+    assert sorted(np.concatenate(s).tolist()) == list(range(2048))
+    assert s[1][:3].tolist() == [128, 129, 130] and s[1][128] == 128 * 5
+    try:
+        mg.cyclic_slots(1000, 4, 0)
+        assert False
+    except ValueError:
+        pass
+
+
 def test_gloo_tile_allgather_world2(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(textwrap.dedent(f"""
@@ -47,6 +58,13 @@ def test_gloo_tile_allgather_world2(tmp_path):
         table[begin:begin + count] = full[begin:begin + count] * (1.0)      # this rank's tile of records
         out = mg.gather_tiles(table[begin:begin + count], world)
         assert torch.equal(out, full), (rank, out)
+        # cyclic tiles (blocks of 128 slots dealt round robin): gathered back into slot order
+        Nc = 128 * world * 3
+        slots = torch.from_numpy(mg.cyclic_slots(Nc, world, rank))
+        vals = torch.arange(Nc, dtype=torch.float32) * 0.5
+        assert torch.equal(mg.gather_cyclic(vals[slots], world), vals)
+        owned = torch.zeros(Nc); owned[slots] = 1.0
+        dist.all_reduce(owned); assert bool((owned == 1.0).all())         # the ranks' slots partition the swarm
         b0, c0 = mg.replicate_shard(10, world, rank)
         tot = torch.tensor([c0]); dist.all_reduce(tot); assert int(tot) == 10
         dist.destroy_process_group()
