@@ -8,7 +8,9 @@ def start(parallel=False, headless=True, agent_behave_param_list=None, env_file=
     if envconf.get("APP_VERSION", "Base") != "VisualFlocking":                    # app_visual_flocking.py:51-54
         raise Exception(".env file was not created for project visual flocking or no APP_VERSION parameter found!")
     kw = params.simulation_kwargs(envconf)
-    kw.update(parallel=parallel, agent_behave_param_list=agent_behave_param_list, **extra)
+    kw.update(parallel=parallel, agent_behave_param_list=agent_behave_param_list,
+              save_root_dir=envconf.get("SAVE_ROOT_DIR", "abm/data/simulation_data"), env_params=dict(envconf))
+    kw.update(extra)
     sim = VFSimulation(vf_params=params.VFParams.from_env(envconf), **kw)
     sim.start()
     return sim

@@ -181,6 +181,18 @@ class BaseEngine:
         _lib.check(self._lib.abm_base_step(self._h, int(n_steps), ptr, 0, int(phases), C.c_void_p(_current_stream())),
                    "abm_base_step")
 
+    def inject_regeneration(self, draws=None):
+        """Replace the four random draws of every try of a patch regeneration (sims.py:351-361): ``draws`` of shape
+        (B, P, n_tries, 4) = (x, y, units, quality); None returns to the engine's own RNG.  For parity tests."""
+        if draws is None:
+            _lib.check(self._lib.abm_base_inject_regeneration(self._h, None, 0), "abm_base_inject_regeneration")
+            return
+        d = np.ascontiguousarray(np.asarray(draws, np.float64))
+        if d.ndim != 4 or d.shape[:2] != (self.B, self.P) or d.shape[3] != 4:
+            raise ValueError("draws must have shape (n_replicates, n_patches, n_tries, 4)")
+        _lib.check(self._lib.abm_base_inject_regeneration(self._h, C.c_void_p(d.ctypes.data), int(d.shape[2])),
+                   "abm_base_inject_regeneration")
+
     def fields(self) -> np.ndarray:
         """(B, N, R) bool, STORED (flipped + FOV-masked) order like Agent.soc_v_field."""
         w = np.empty((self.B, self.N, self.W), np.uint32)

@@ -676,7 +676,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     }
     e->host_synced = false;
     if (use_sym) abm::launch_vf_step_sym(a, st);
-    else if (use_warp) abm::launch_vf_step_warp(a, cull, st);
+    else if (use_warp) abm::launch_vf_step_warp(a, cull, uniform_r, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
     if (e->n_peers > 0 && !fused_close) { abm::launch_vf_publish(a, st); ++e->launches; }
     e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : (use_warp ? "abm::vf_step_warp_kernel" : "abm::vf_step_kernel");

@@ -63,9 +63,7 @@ __device__ __forceinline__ const BaseParams& base_params_of(const BaseKernelArgs
 // the chunk's exploiters.  Per agent the notify sequence is the reference's: on a patch destroyed by agent d in this
 // step, agents i <= d see (+1, -1), agents i > d see (-1, -1); the second notification of each is the destroy loop's
 // (sims.py:829-836), applied after the patch's pass.
-__global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
-  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (b >= a.B) return;
+__device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int b, int lane) {
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * a.N, p0 = (size_t)b * a.P;
   const double r = a.radius;
@@ -137,26 +135,35 @@ __global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
     if (destroy && a.regenerate) {   // kill_resource + add_new_resource_patch(force_id) (sims.py:321-374)
       if (lane == 0) {
         bool placed = false;
-        for (unsigned t = 0; t < 10000u && !placed; ++t) {
-          const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t),
-                                      make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x50415443u));
+        for (unsigned t = 0; t < 10000u && !placed; ++t) {      // max_retries, sims.py:335
           const double R_ = a.patch_radius;
-          double lox, hix, loy, hiy;
-          if (a.border_overlap) { lox = a.pad - R_; hix = a.width + a.pad - R_; loy = a.pad - R_; hiy = a.height + a.pad - R_; }
-          else { lox = a.pad; hix = a.width + a.pad - 2 * R_; loy = a.pad; hiy = a.height + a.pad - 2 * R_; }
-          const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
-          const double nx = floor(lox + floor(hix - lox) * u01(rn.x, rn.y));          // np.random.randint(lo, hi)
-          const double ny = floor(loy + floor(hiy - loy) * u01(rn.z, rn.w));
+          double nx, ny, q;
+          int units;
+          if (a.regen_draws) {                                  // injected draws (parity tests): try t of this slot
+            if ((int)t >= a.regen_tries) break;
+            const double* d = a.regen_draws + (((size_t)b * a.P + p) * a.regen_tries + t) * 4;
+            nx = d[0]; ny = d[1]; units = (int)d[2]; q = d[3];
+          } else {
+            const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t),
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x50415443u));
+            double lox, hix, loy, hiy;
+            if (a.border_overlap) { lox = a.pad - R_; hix = a.width + a.pad - R_; loy = a.pad - R_; hiy = a.height + a.pad - R_; }
+            else { lox = a.pad; hix = a.width + a.pad - 2 * R_; loy = a.pad; hiy = a.height + a.pad - 2 * R_; }
+            const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
+            nx = floor(lox + floor(hix - lox) * u01(rn.x, rn.y));          // np.random.randint(lo, hi)
+            ny = floor(loy + floor(hiy - loy) * u01(rn.z, rn.w));
+            units = a.min_units + (int)floor((double)(a.max_units - a.min_units) * u01(rn2.x, rn2.y));
+            q = a.min_quality + (a.max_quality - a.min_quality) * u01(rn2.z, rn2.w);
+          }
           bool ok = true;
           for (int p2 = 0; p2 < a.P; ++p2) {                                          // proove_sprite: no patch-patch overlap
             if (p2 == p) continue;
             const double r2 = a.pa.radius[p0 + p2];
+            if (!(r2 > 0.0)) continue;                                              // a killed patch is not in the group
             const double ex = (nx + R_) - ((double)a.pa.x[p0 + p2] + r2), ey = (ny + R_) - ((double)a.pa.y[p0 + p2] + r2);
             if (ex * ex + ey * ey <= (R_ + r2) * (R_ + r2)) { ok = false; break; }
           }
           if (!ok) continue;
-          const int units = a.min_units + (int)floor((double)(a.max_units - a.min_units) * u01(rn2.x, rn2.y));
-          const double q = a.min_quality + (a.max_quality - a.min_quality) * u01(rn2.z, rn2.w);
           a.pa.x[p0 + p] = (float)nx; a.pa.y[p0 + p] = (float)ny; a.pa.radius[p0 + p] = (float)R_;
           a.pa.left[p0 + p] = (float)units; a.pa.quality[p0 + p] = (float)q;
           placed = true;
@@ -180,6 +187,11 @@ __global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
     a.ag.snap_y[g] = a.ag.y[g];
     a.ag.snap_override[g] = a.ag.override_mode[g];
   }
+}
+__global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
+  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (b >= a.B) return;
+  base_env_replicate(a, b, lane);
 }
 
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream) {
@@ -208,8 +220,11 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
   for (int w = lane; w < W + 1; w += 32) row[w] = 0u;
 
   const float xi_f = a.ag.snap_x[gi], yi_f = a.ag.snap_y[gi];
-  const double r = a.radius;
-  const FocalExact fe = vf_focal_exact(xi_f, yi_f, (float)a.radius, a.ag.theta[gi]);   // same v1 construction (agent.py:484-495)
+  const float th_f = a.ag.theta[gi];
+  // heterogeneous radii (sims.py:499-517): the candidate distance is between the agents' own centres (agent.py:400 ->
+  // supcalc.distance), the projection uses the FOCAL radius for both centres (agent.py:504-509)
+  const double r = a.ag.radius ? (double)a.ag.radius[gi] : a.radius;
+  const double cix = __dadd_rn((double)xi_f, r), ciy = __dadd_rn((double)yi_f, r);
   const int my_patch = a.ag.patch_id[gi];
   double fov0 = a.fov0, fov1 = a.fov1, vision_range = a.vision_range;
   int mask_lo = a.mask_lo, mask_hi = a.mask_hi;
@@ -217,6 +232,7 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
     const BaseAgentGeo g = a.agent_geo[gi];
     fov0 = g.fov0; fov1 = g.fov1; vision_range = g.vision_range; mask_lo = g.mask_lo; mask_hi = g.mask_hi;
   }
+  const BaseFast bf = base_fast_consts(th_f, r, fov0, fov1, R);
 
   // ---- candidates, classes, raw intervals (agent.py:396-419, 497-556) ----
   int M = 0;
@@ -228,8 +244,15 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
     if (j < N) {
       const size_t gj = a0 + j;
       const float xj_f = a.ag.snap_x[gj], yj_f = a.ag.snap_y[gj];
-      const double n2 = base_centre_distance(fe, r, xj_f, yj_f);
-      const bool in_range = n2 <= vision_range;                                     // agent.py:400
+      // centre distance in float64 with the reference's operation sequence: it decides the candidate set (<=) and
+      // orders the occlusion (strict <), both on the rounded value
+      double n2 = base_distance_exact(cix, ciy, r, xj_f, yj_f);                     // both centres with the focal radius
+      double n2c = n2;
+      if (a.ag.radius) {
+        const double rj = a.ag.radius[gj];
+        n2c = base_distance_exact(cix, ciy, rj, xj_f, yj_f);                        // own radii (agent.py:400)
+      }
+      const bool in_range = n2c <= vision_range;                                    // agent.py:400
       const bool is_expl = (j != i) && (a.ag.snap_override[gj] == OV_EXPLOIT);      // :402-403
       int cls = 0;   // 0 none, 1 social, 2 occluder (other), 3 occluder (same-patch exploiter)
       if (in_range) {
@@ -242,9 +265,16 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
         }
       }
       if (!a.visual_exclusion && cls != 1) cls = 0;                                 // :415-419
-      if (cls != 0) {
-        double dist;
-        rec = base_interval(fe, r, xi_f, yi_f, xj_f, yj_f, fov0, fov1, R, a.lin_step, o, dist);
+      if (cls != 0 && !((xj_f == xi_f) && (yj_f == yi_f))) {                        // :502
+        bool vis;
+        if (!base_interval_fast(xj_f - xi_f, yj_f - yi_f, bf, o.s, o.e, vis)) {
+          rec = vis; o.d = n2;
+        } else {                                                                    // inside a guard band: fp64
+          const FocalExact fe = vf_focal_exact(xi_f, yi_f, (float)r, th_f);
+          double dist;
+          rec = base_interval(fe, r, xi_f, yi_f, xj_f, yj_f, fov0, fov1, R, a.lin_step, o, dist);
+          atomicAdd(&a.counters[2], 1ull);
+        }
         // list order of the reference: social cues, then other occluders, then same-patch
         // exploiters, each in agent order (agent.py:402-410, 472-477)
         k2 = (((cls == 1) ? 0 : (cls == 2 ? 1 : 2)) * N + j) | ((cls == 1) ? (1 << 30) : 0);
@@ -338,7 +368,7 @@ __device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long 
   atomicAdd(&a.mode_steps[(size_t)b * 4 + mode], 1u);        // the mode this agent is logged with at the end of the step
 }
 
-__global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a) {
+__global__ void __launch_bounds__(256, 3) base_agent_kernel(const BaseKernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int halves[2 * 8];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -369,8 +399,7 @@ __global__ void __launch_bounds__(256) base_agent_kernel(const BaseKernelArgs a)
 // the phase -- positions do not move, and the only override mode that is tested, "exploit", is neither set nor cleared
 // here -- so the events of different a2 are independent and only those of the same a2 (its heading turns with every
 // hit) have to stay in a1 order.  `collided_agents` is a set: the warps mark its members with plain stores.
-__global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a, int b, unsigned char* smem_raw) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int N = a.N, R = a.R, W = a.W, h = R / 2;
   const size_t per_warp = warp_field_bytes(N, W);
@@ -381,7 +410,6 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
   int* col = reinterpret_cast<int*>(th + N);                             // member of collided_agents
   float* px = reinterpret_cast<float*>(col + N);                         // positions (this phase does not move anybody)
   float* py = px + N;
-  const int b = blockIdx.x;
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * N;
   const double r = a.radius;
@@ -443,8 +471,9 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
           __syncwarp();
           if (lane == 0 && !expl2) { ov[a2] = OV_COLLIDE; md[a2] = MODE_COLLIDE; }   // :442-443
           for (int w = lane; w < W + 1; w += 32) wf.row[w] = 0u;
-          const float x2 = px[a2], y2 = py[a2];
-          const FocalExact fe = vf_focal_exact(x2, y2, (float)r, th[a2]);
+          const float x2 = px[a2], y2 = py[a2], th2 = th[a2];
+          const double cix = __dadd_rn((double)x2, r), ciy = __dadd_rn((double)y2, r);
+          const BaseFast bf = base_fast_consts(th2, r, -ABM_PI_D, ABM_PI_D, R);
           int M = 0, last_j = -1;
           double last_d = 0.0;
           for (int v0 = 0; v0 < N; v0 += 32) {
@@ -454,9 +483,19 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
             double dist = 0.0;
             if (j < N && j != a2) {
               const float xj = px[j], yj = py[j];
-              if (base_centre_distance(fe, r, xj, yj) < 2.0 * r + 20.0) {           // :446-447
+              const double n2 = base_distance_exact(cix, ciy, r, xj, yj);
+              if (n2 < 2.0 * r + 20.0) {                                            // :446-447
                 counted = !((xj == x2) && (yj == y2));
-                rec = base_interval(fe, r, x2, y2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o, dist);
+                if (counted) {
+                  dist = n2;
+                  bool vis;
+                  if (!base_interval_fast(xj - x2, yj - y2, bf, o.s, o.e, vis)) {
+                    rec = vis; o.d = n2;
+                  } else {                                                          // inside a guard band: fp64
+                    const FocalExact fe = vf_focal_exact(x2, y2, (float)r, th2);
+                    rec = base_interval(fe, r, x2, y2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o, dist);
+                  }
+                }
               }
             }
             // the loop variable `distance` that keep_distance_info leaks (agent.py:590): last obstacle in list order
@@ -506,6 +545,56 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
     a.ag.override_mode[g] = ov[i]; a.ag.mode[g] = md[i]; a.ag.theta[g] = th[i]; a.ag.collided[g] = col[i];
   }
 }
+__global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  base_collision_replicate(a, blockIdx.x, smem_raw);
+}
+
+// ---------------------------------------------------------------------------------------
+// the fused step: ONE launch per time step, one CTA per replicate (sims.py:733-864 in its own order: collisions,
+// agent-patch interaction, Agent.update of every agent from one frozen snapshot).  The phases of a replicate are
+// sequential by construction and each of them is a chain of dependent latencies; with a CTA per replicate and all
+// replicates of a sweep resident at once, the SMs overlap the chains of different replicates instead of running three
+// grids one after the other (each with its own launch and its own tail).
+// ---------------------------------------------------------------------------------------
+size_t base_step_smem_bytes(int N, int W, int warps) {
+  return warp_field_bytes(N, W) * warps + 7 * sizeof(int) * (size_t)N + 4 * sizeof(int) + 2 * sizeof(int) * (size_t)N;
+}
+
+__global__ void __launch_bounds__(128, 8) base_step_kernel(const BaseKernelArgs a, unsigned phases, int collide) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, N = a.N;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const size_t a0 = (size_t)b * N;
+  if (collide) {                                   // sims.py:736-783
+    base_collision_replicate(a, b, smem_raw);
+    __syncthreads();
+  }
+  if (phases & 1u) {                               // sims.py:790-858 (+ the frozen snapshot of the agent phase)
+    if (wib == 0) base_env_replicate(a, b, lane);
+  } else {                                         // agent phase alone: the snapshot is the current state
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      a.ag.snap_x[a0 + i] = a.ag.x[a0 + i];
+      a.ag.snap_y[a0 + i] = a.ag.y[a0 + i];
+      a.ag.snap_override[a0 + i] = a.ag.override_mode[a0 + i];
+    }
+  }
+  __syncthreads();
+  if (!(phases & 2u)) return;
+  // sims.py:861: the visual fields of all agents (a warp per focal agent), then -- one barrier later -- decision
+  // process, mode machine and kinematics with a thread per agent
+  const size_t per_warp = warp_field_bytes(N, a.W);
+  int* halves = reinterpret_cast<int*>(smem_raw + per_warp * wpb + 7 * sizeof(int) * (size_t)N + 4 * sizeof(int));
+  WarpField wf = warp_field_at(smem_raw + per_warp * wib, N);
+  for (int i = wib; i < N; i += wpb) {
+    int n_left = 0, n_right = 0;
+    base_agent_field(a, wf, (long long)a0 + i, lane, n_left, n_right);
+    if (lane == 0) { halves[2 * i] = n_left; halves[2 * i + 1] = n_right; }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) base_agent_decide(a, (long long)a0 + i, halves[2 * i], halves[2 * i + 1]);
+}
 
 // opt-in shared memory per block of the current device, asked once per device (the attribute query costs more host time
 // than a launch, and a foraging step is three launches of a few hundred microseconds together)
@@ -542,7 +631,8 @@ __global__ void base_projection_kernel(const BaseProjArgs a) {   // one warp
   const int n = a.n_social + a.n_occ;
   WarpField wf = warp_field_at(smem_raw, n > 0 ? n : 1);
   for (int w = lane; w < a.W + 1; w += 32) wf.row[w] = 0u;
-  const FocalExact fe = vf_focal_exact(a.fx, a.fy, (float)a.radius, a.ftheta);
+  const double cix = __dadd_rn((double)a.fx, a.radius), ciy = __dadd_rn((double)a.fy, a.radius);
+  const BaseFast bf = base_fast_consts(a.ftheta, a.radius, a.fov0, a.fov1, a.R);
   int M = 0, last_j = -1;
   double last_d = 0.0;
   const int n_used = a.visual_exclusion ? n : a.n_social;            // agent.py:475-477, :415-419
@@ -553,7 +643,16 @@ __global__ void base_projection_kernel(const BaseProjArgs a) {   // one warp
     double dist = 0.0;
     if (j < n_used) {
       counted = !((a.ox[j] == a.fx) && (a.oy[j] == a.fy));
-      rec = base_interval(fe, a.radius, a.fx, a.fy, a.ox[j], a.oy[j], a.fov0, a.fov1, a.R, a.lin_step, o, dist);
+      if (counted) {
+        dist = base_distance_exact(cix, ciy, a.radius, a.ox[j], a.oy[j]);
+        bool vis;
+        if (!base_interval_fast(a.ox[j] - a.fx, a.oy[j] - a.fy, bf, o.s, o.e, vis)) {
+          rec = vis; o.d = dist;
+        } else {                                                      // inside a guard band: fp64
+          const FocalExact fe = vf_focal_exact(a.fx, a.fy, (float)a.radius, a.ftheta);
+          rec = base_interval(fe, a.radius, a.fx, a.fy, a.ox[j], a.oy[j], a.fov0, a.fov1, a.R, a.lin_step, o, dist);
+        }
+      }
     }
     const unsigned cm = __ballot_sync(0xffffffffu, counted);
     if (cm) { const int src = 31 - __clz(cm); last_j = j0 + src; last_d = __shfl_sync(0xffffffffu, dist, src); }
@@ -601,6 +700,23 @@ __global__ void vf_dphi_kernel(const uint32_t* v, int R, int W, signed char* out
 }
 void launch_vf_dphi(const uint32_t* v, int R, int W, signed char* out, cudaStream_t stream) {
   vf_dphi_kernel<<<(R + 127) / 128, 128, 0, stream>>>(v, R, W, out);
+}
+
+// One launch for the whole step when a CTA per replicate fills the GPU (sweeps); false: the caller launches the phases
+// as separate grids (few replicates of many agents: a warp per focal agent over the whole GPU).
+bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, int n_sms, cudaStream_t stream) {
+  const int smem_max = base_smem_optin();
+  // 4 warps per replicate, 64 registers: 8 CTAs per SM, so the 1024 replicates of a sweep are resident all at once and the
+  // SMs interleave their (latency-bound, sequential) phase chains
+  int warps = 4;
+  while (warps > 1 && (warps / 2 >= a.N || base_step_smem_bytes(a.N, a.W, warps) > (size_t)smem_max)) warps >>= 1;
+  const size_t smem = base_step_smem_bytes(a.N, a.W, warps);
+  if (smem > (size_t)smem_max) return false;
+  if ((long long)a.B * warps < 4LL * n_sms && a.N > 64) return false;
+  static SmemOptIn optin;
+  optin.ensure(base_step_kernel, smem);
+  base_step_kernel<<<a.B, warps * 32, smem, stream>>>(a, phases, collide ? 1 : 0);
+  return true;
 }
 
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream) {

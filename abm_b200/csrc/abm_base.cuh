@@ -29,6 +29,7 @@ struct BaseAgentPtrs {
   float *snap_x, *snap_y;
   int32_t* snap_override;
   int32_t* collided;   // 1 = member of `collided_agents` of this step (sims.py:754-783); all 0 without collisions
+  const float* radius; // nullable, B*N: per-agent radius (heterogeneous agents, sims.py:502); else BaseKernelArgs::radius
 };
 struct BasePatchPtrs {
   float *x, *y, *radius, *left, *quality;
@@ -62,12 +63,15 @@ struct BaseKernelArgs {
                                // agent (heterogeneous agents: agent.py:83-108 behave_params, sims.py:499-517)
   const BaseAgentGeo* agent_geo;   // nullable, B*N: replaces fov0 / fov1 / mask_lo / mask_hi / vision_range per focal agent
   const float* inject_dtheta;  // nullable, B*N: replaces the random-walk draw (parity tests)
+  const double* regen_draws;   // nullable, B*P*regen_tries*4: (x, y, units, quality) of every try of a regeneration of
+  int regen_tries;             // patch slot p of replicate b, replacing the four draws of sims.py:351-361 (parity tests)
   uint32_t* fields_out;        // nullable, B*N*W, stored order
   unsigned long long* counters;   // [0] patches regenerated, [1] regeneration retries exhausted
   unsigned int* mode_steps;    // B*4: agent-steps spent in mode explore / exploit / relocate / collide since the last
                                // reset (the mode an agent is logged with, ifdb.py:197-206); summary metrics
 };
 
+bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, int n_sms, cudaStream_t stream);
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream);

@@ -1,5 +1,6 @@
 // C ABI of the BASE / collective-foraging engine (declared in include/abm_b200.h).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <utility>
@@ -14,7 +15,7 @@ using abm::DevBuf;
 
 struct abm_base_engine {
   abm_base_config_t cfg;
-  int device = 0;
+  int device = 0, n_sms = 148;
   int W = 0, mask_lo = 0, mask_hi = -1;
   double lin_step = 0.0;
   size_t n_agents_total = 0, n_patches_total = 0;
@@ -26,6 +27,10 @@ struct abm_base_engine {
   DevBuf<double> params;
   DevBuf<abm::BaseAgentGeo> agent_geo;   // B*N once abm_base_set_agent_geometry was called
   bool has_agent_geo = false;
+  DevBuf<double> regen_draws;            // abm_base_inject_regeneration
+  int regen_tries = 0;
+  DevBuf<float> agent_radius;            // B*N once abm_base_set_agent_radii was called
+  bool has_agent_radius = false;
   DevBuf<float> inject;
   DevBuf<unsigned long long> counters;
   DevBuf<unsigned int> mode_steps;      // B*4, see BaseKernelArgs
@@ -78,6 +83,7 @@ int abm_base_create(const abm_base_config_t* cfg, int device, abm_base_engine_t*
   if (!e) return fail(ABM_E_INVALID, "abm_base_create: out of host memory");
   e->cfg = *cfg;
   e->device = device;
+  e->n_sms = prop.multiProcessorCount;
   const int R = cfg->resolution;
   e->W = (R + 31) / 32;
   e->lin_step = ABM_TWO_PI_D / (double)(R - 1);
@@ -140,7 +146,7 @@ int abm_base_destroy(abm_base_engine_t* e) {
                            &e->pquality}) b->release();
   for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid,
                              &e->collided}) b->release();
-  e->novelty.release(); e->fields.release(); e->params.release(); e->agent_geo.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
+  e->novelty.release(); e->fields.release(); e->params.release(); e->agent_geo.release(); e->regen_draws.release(); e->agent_radius.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
   delete e;
   return ABM_OK;
 }
@@ -270,7 +276,8 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   a.min_units = c.min_units; a.max_units = c.max_units; a.seed = c.seed;
   a.ag = abm::BaseAgentPtrs{e->x.p, e->y.p, e->theta.p, e->vel.p, e->w.p, e->u.p, e->collected.p,
                             e->collected_before.p, e->i_priv.p, e->env_status.p, e->override_mode.p, e->mode.p,
-                            e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p};
+                            e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p,
+                            e->has_agent_radius ? e->agent_radius.p : nullptr};
   a.pa = abm::BasePatchPtrs{e->px.p, e->py.p, e->pradius.p, e->pleft.p, e->pquality.p, e->pid.p};
   a.params = e->params.p;
   a.agent_geo = e->has_agent_geo ? e->agent_geo.p : nullptr;
@@ -278,6 +285,7 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   else if (e->n_param_sets == e->cfg.n_replicates && e->cfg.n_agents != 1) { a.param_stride = abm::kBaseNParam; a.param_stride_agent = 0; }
   else { a.param_stride = e->cfg.n_agents * abm::kBaseNParam; a.param_stride_agent = abm::kBaseNParam; }
   a.fields_out = e->fields.p; a.counters = e->counters.p; a.mode_steps = e->mode_steps.p;
+  a.regen_draws = e->regen_tries > 0 ? e->regen_draws.p : nullptr; a.regen_tries = e->regen_tries;
   if (inject_dtheta) {
     const float* src = inject_dtheta;
     if (!inject_on_device) {
@@ -286,9 +294,20 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
     }
     a.inject_dtheta = src;
   }
+  const bool separate = getenv("ABM_BASE_SEPARATE_PHASES") != nullptr;   // measurement probes: the three-grid path
   for (int s = 0; s < n_steps; ++s) {
     a.step = e->step;
-    if ((phases & ABM_BASE_PHASE_COLLISIONS) && c.collide_agents) { abm::launch_base_collisions(a, st); ++e->launches; }
+    const bool collide = (phases & ABM_BASE_PHASE_COLLISIONS) && c.collide_agents;
+    // one launch per step (a CTA per replicate runs the phases in the reference's order) whenever the batch fills the
+    // GPU that way; otherwise one grid per phase
+    if (!separate && (phases & (ABM_BASE_PHASE_ENV | ABM_BASE_PHASE_AGENTS)) &&
+        abm::launch_base_step(a, phases, collide, e->n_sms, st)) {
+      ++e->launches;
+      if (phases & ABM_BASE_PHASE_AGENTS) ++e->metric_steps;
+      ++e->step; ++e->steps;
+      continue;
+    }
+    if (collide) { abm::launch_base_collisions(a, st); ++e->launches; }
     if (phases & ABM_BASE_PHASE_ENV) { abm::launch_base_env(a, st); ++e->launches; }
     else {   // agent phase alone: the snapshot is the current state
       ABM_CUDA(cudaMemcpyAsync(e->snap_x.p, e->x.p, sizeof(float) * e->n_agents_total, cudaMemcpyDeviceToDevice, st));
@@ -301,6 +320,17 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   }
   ABM_CUDA(cudaGetLastError());
   if (inject_dtheta && !inject_on_device) ABM_CUDA(cudaStreamSynchronize(st));
+  return ABM_OK;
+}
+
+int abm_base_inject_regeneration(abm_base_engine_t* e, const double* draws, int n_tries) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_inject_regeneration: null engine");
+  if (!draws || n_tries <= 0) { e->regen_tries = 0; return ABM_OK; }   // back to the engine's own counter-based RNG
+  ABM_CUDA(cudaSetDevice(e->device));
+  const size_t n = e->n_patches_total * (size_t)n_tries * 4;
+  ABM_CUDA(e->regen_draws.alloc(n));
+  ABM_CUDA(cudaMemcpy(e->regen_draws.p, draws, sizeof(double) * n, cudaMemcpyHostToDevice));
+  e->regen_tries = n_tries;
   return ABM_OK;
 }
 

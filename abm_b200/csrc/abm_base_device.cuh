@@ -38,6 +38,13 @@ __device__ __forceinline__ double base_centre_distance(const FocalExact& fe, dou
   return __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
 }
 
+// the same from a focal centre (cix, ciy) = position + radius already formed in float64, object at (xj, yj) with
+// radius rj
+__device__ __forceinline__ double base_distance_exact(double cix, double ciy, double rj, float xj, float yj) {
+  const double v2x = __dadd_rn(__dadd_rn((double)xj, rj), -cix), v2y = __dadd_rn(__dadd_rn((double)yj, rj), -ciy);
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)));
+}
+
 // One obstacle of Agent.projection_field (agent.py:501-556), fp64, the reference's operation
 // order.  Returns true if the obstacle is recorded (not at the focal position, strictly inside
 // the FOV); `dist` is set whenever the position test passes (the loop variable that

@@ -29,15 +29,22 @@ namespace abm {
 
 constexpr int kWarpThreads = 256;
 constexpr int kWarpMaxFocal = 8;     // focal agents per CTA <= warps per CTA (a warp per focal agent in the epilogue)
+constexpr int kChunk = 128;          // records per pass of half the CTA (= kWarpTile)
+constexpr int kWarpQueue = 1024;     // pairs off the fast path waiting for the CTA's slow pass
 
-struct WarpFocal {                   // per focal agent of the CTA, in shared memory
-  float x, y, r;                     // top-left position, radius
-  uint32_t hc;                       // heading constant of the binary-angle bin index
-  FocalExact fe;                     // fp64 path (vf_pair_exact)
+// per focal agent of the CTA, in shared memory: (x, y, radius, heading constant) read with one LDS.128 per pair
+struct WarpShared {
+  float4* focal;       // [F]
+  float* theta;        // [F] heading (fp64 path only)
+  uint32_t* rows;      // [F][W + 3]: padded rows (word 0 = virtual bins [-32, 0), words 1 .. W the real bins, one word of
+                       // overflow; abm_vf_device.cuh: vf_fold_padding) + the spill word of the second reduction
+  int* tile_list;      // [kMaxTileList] + count
+  int* fbox;           // focal bounding box (ordered ints)
+  uint32_t* queue;     // [kWarpQueue] focal << 24 | record: pairs off the fast path; count at tile_list[kMaxTileList + 1]
 };
-
 size_t vf_warp_smem_bytes(int W, int F) {
-  return sizeof(uint32_t) * (size_t)(W + 1) * F + sizeof(WarpFocal) * F + sizeof(int) * (kMaxTileList + 4) + 64;
+  return sizeof(float4) * F + sizeof(float) * kWarpMaxFocal + sizeof(uint32_t) * (size_t)(W + 3) * F +
+         sizeof(int) * (kMaxTileList + 4) + 64 + sizeof(uint32_t) * kWarpQueue;
 }
 
 // ordered-integer image of a float (monotonic for all finite values): min / max by integer atomics
@@ -47,55 +54,102 @@ __device__ __forceinline__ int float_ordered(float v) {
 }
 __device__ __forceinline__ float ordered_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
-// One (focal, record) pair: evaluate and OR the interval into the focal agent's row.
-template <bool TORUS, bool CULL>
-__device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const WarpFocal& f, uint32_t row_s, const float4 o,
-                                          unsigned& n_fp64, unsigned& n_differ) {
+// Off the fast path (wide interval, guard-band hit, coincident positions): the complete evaluation -- full-range
+// arctangent for the half width, separate tie / seam tests, guard-band hits re-evaluated in fp64 with the reference's own
+// operation sequence -- and the general drawing rule into the REAL words of the row.
+template <bool TORUS>
+static __device__ __noinline__ void warp_pair_slow(const VFKernelArgs& a, float4 f, float fth, uint32_t row_real_s,
+                                                   float4 o, unsigned& n_fp64, unsigned& n_differ) {
+  if ((o.x == f.x) & (o.y == f.y)) return;               // self / coincident positions (vf_supcalc.py:57)
   const int R = a.R;
-  const float dr = o.z - f.r;
-  float dx = (o.x - f.x) + dr, dy = (o.y - f.y) + dr;   // positions first (exact for close neighbours), then radii
+  const float dr = o.z - f.z;
+  float dx = (o.x - f.x) + dr, dy = (o.y - f.y) + dr;
   bool wrap_tie = false;
-  if (TORUS) {                                           // vf_supcalc.py:70-83
+  if (TORUS) {
     dx = torus_delta_r(o.x, f.x, dr, a.width, a.half_w, wrap_tie);
     dy = torus_delta_r(o.y, f.y, dr, a.height, a.half_h, wrap_tie);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
-  if (CULL) { if (d2 > o.w) return; }                    // beyond it the half width is 0
-  if ((o.x == f.x) & (o.y == f.y)) return;               // self / coincident positions (vf_supcalc.py:57)
   const float q = o.z * rsqrt_approx(d2);
   const float y = fmaf(atan_unit(q), a.y_scale, -0.5f);
   const float yr = y + kMagic;
   int h = __float_as_int(yr) - kMagicBits;
   bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
-  int k = sym_side_k<0>(a, sym_bearing_bits(dx, dy, kBearingA6), f.hc, 0, flagged);   // bin index
+  int k = sym_side_k<0>(a, sym_bearing_bits(dx, dy, kBearingA6), __float_as_uint(f.w), 0, flagged);   // bin index
   if (flagged) {                                         // fp64, the reference's own operation sequence
-    const PairExact pe = vf_pair_exact(f.fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, R, a.lin_step);
+    const FocalExact fe = vf_focal_exact(f.x, f.y, f.z, fth);
+    const PairExact pe = vf_pair_exact(fe, o.x, o.y, o.z, a.boundary, a.width_d, a.height_d, R, a.lin_step);
     ++n_fp64;
     if (!pe.valid) return;
     if ((pe.k != k) | (pe.h != h)) ++n_differ;
     k = pe.k; h = pe.h;
   }
-  const int ps = k - h, pe_ = k + h;
-  if (((unsigned)(h - 1) < 16u) & (ps >= 0) & (pe_ < R) &
-      (((a.fov_px0 < ps) & (ps < a.fov_px1)) | ((a.fov_px0 < pe_) & (pe_ < a.fov_px1)))) {
-    // interval of <= 32 bins inside the row: at most two words
-    const uint32_t m = 0xffffffffu >> (32 - 2 * h);
-    const uint32_t wa = row_s + 4u * (uint32_t)(ps >> 5);
-    red_or_shared(wa, __funnelshift_l(0u, m, ps));
-    const uint32_t hi = __funnelshift_l(m, 0u, ps);
-    if (hi) red_or_shared(wa + 4u, hi);
-  } else {
-    vf_draw_shared(row_s, 4u, R, a.fov_px0, a.fov_px1, k, h);   // wide / wrapping / outside the FOV: general rule
-  }
+  vf_draw_shared(row_real_s, 4u, R, a.fov_px0, a.fov_px1, k, h);
 }
 
-template <bool TORUS, bool CULL, int F>
-__global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a) {
+// One (focal, record) pair on the fast path: interval of 1 .. 32 bins clear of every fp32 guard band, drawn into the
+// padded row with two reductions (the arithmetic of the symmetric kernel's fast path, one direction).
+template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R>
+__device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const float4 f, uint32_t row_pad_s, const float4 o,
+                                          float S, float c3s, float c5s, uint32_t qentry, uint32_t queue_s, uint32_t qcount_s,
+                                          const WarpShared& sh, unsigned& n_fp64, unsigned& n_differ) {
+  float dx, dy;
+  bool slow = false;
+  if (UNIFORM_R) {
+    dx = o.x - f.x; dy = o.y - f.y;
+    if (TORUS) { dx = torus_delta(o.x, f.x, a.width, a.half_w, slow); dy = torus_delta(o.y, f.y, a.height, a.half_h, slow); }
+  } else {
+    const float dr = o.z - f.z;
+    dx = (o.x - f.x) + dr; dy = (o.y - f.y) + dr;        // positions first (exact for close neighbours), then radii
+    if (TORUS) {
+      dx = torus_delta_r(o.x, f.x, dr, a.width, a.half_w, slow);
+      dy = torus_delta_r(o.y, f.y, dr, a.height, a.half_h, slow);
+    }
+  }
+  const float d2 = fmaf(dx, dx, dy * dy);
+  if (CULL) { if (d2 > o.w) return; }                    // beyond it the half width is 0
+  slow |= (o.x == f.x) & (o.y == f.y);
+  // half width h = floor(atan(r / d) R / 2pi): three-term series in q = r / d, exact to fp32 for h <= 16 (abm_vf_sym.cu)
+  const float qs = rsqrt_approx(d2) * (o.z * S);
+  const float zs = qs * qs;
+  float p = fmaf(zs, c5s, c3s);
+  p = fmaf(p, zs, 1.0f);
+  const float y = fmaf(qs, p, -0.5f);
+  const float yr = y + kMagic;
+  const uint32_t hraw = __float_as_uint(yr);             // h + kMagicBits
+  slow |= !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);   // wide, near an integer, NaN
+  uint32_t mask;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(mask) : "r"(2u * hraw - 2u * (uint32_t)kMagicBits));   // 2h ones
+  const int bh = 32 + kMagicBits - (int)hraw;            // ps (padded) = bin index + 32 - h
+  const int ps = sym_side_k<0, true>(a, sym_bearing_bits(dx, dy, kBearingA6), __float_as_uint(f.w), bh, slow);
+  if (slow) {
+    // Rare (1-2 per thousand), expensive (fp64 with the reference's operation sequence) and divergent: not here, where 31
+    // lanes would wait for one -- the pair goes to the CTA's queue and the slow pass after the loop takes the queued pairs
+    // one per THREAD.  (Evaluated on the spot, the slow pairs cost as much as all the fast ones together.)
+    const uint32_t slot = atom_add_shared(qcount_s, 1u);
+    if (slot < (uint32_t)kWarpQueue) sts_u32(queue_s + 4u * slot, qentry);
+    else warp_pair_slow<TORUS>(a, f, sh.theta[qentry >> 24], row_pad_s + 4u, o, n_fp64, n_differ);
+    return;
+  }
+  if (!FULL_FOV) {                                       // vf_supcalc.py:119 on padded positions
+    const int pe = ps + 2 * ((int)hraw - kMagicBits);
+    if (!(((unsigned)(ps - a.fov0p) < a.span) | ((unsigned)(pe - a.fov0p) < a.span))) return;
+  }
+  const uint32_t wa = row_pad_s + 4u * (uint32_t)(ps >> 5);
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(__funnelshift_l(0u, mask, ps)));
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + 4u), "r"(__funnelshift_l(mask, 0u, ps)));
+}
+
+template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R>
+__global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a, const int F) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpFocal* focal = reinterpret_cast<WarpFocal*>(smem_raw);                         // [F]
-  uint32_t* rows = reinterpret_cast<uint32_t*>(focal + F);                           // [F][W + 1]
-  int* tile_list = reinterpret_cast<int*>(rows + (size_t)(a.W + 1) * F);             // [kMaxTileList] + count
-  int* fbox = tile_list + kMaxTileList + 4;                                          // focal bounding box (ordered ints)
+  WarpShared sh;
+  sh.focal = reinterpret_cast<float4*>(smem_raw);
+  sh.theta = reinterpret_cast<float*>(sh.focal + F);
+  sh.rows = reinterpret_cast<uint32_t*>(sh.theta + kWarpMaxFocal);
+  sh.tile_list = reinterpret_cast<int*>(sh.rows + (size_t)(a.W + 3) * F);
+  sh.fbox = sh.tile_list + kMaxTileList + 4;
+  sh.queue = reinterpret_cast<uint32_t*>(sh.fbox + 16);
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -105,8 +159,11 @@ __global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid
   const int nf = min(F, a.tile_count - li0);               // focal agents of this CTA
   const float4* rep_in = a.rec_in + (size_t)b * a.N;
   const int R = a.R, W = a.W;
+  const int row_words = W + 3;
+  int* tile_list = sh.tile_list;
+  int* fbox = sh.fbox;
 
-  for (int w = tid; w < (W + 1) * F; w += kWarpThreads) rows[w] = 0u;
+  for (int w = tid; w < row_words * F; w += kWarpThreads) sh.rows[w] = 0u;
   if (a.n_peers > 0 && tid <= a.n_peers) {   // fused tile exchange: wait for every rank's previous step (thread r: rank r)
     const uint32_t* fl = a.xflags + tid;
     uint32_t v;
@@ -115,31 +172,28 @@ __global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid
     } while ((int)(v - a.step_no) < 0);
   }
   if (tid < 4) fbox[tid] = (tid < 2) ? 0x7fffffff : (int)0x80000000;
-  if (tid == 0) tile_list[kMaxTileList] = 0;
+  if (tid == 0) { tile_list[kMaxTileList] = 0; tile_list[kMaxTileList + 1] = 0; }
   __syncthreads();                                          // (also: nobody reads the record table before the hand-shake)
   if (tid < nf) {                                           // focal constants, one thread per focal agent
     const int i = vf_tile_slot(a, li0 + tid);
     const float4 me = __ldcg(rep_in + i);
     const float th = a.theta[(size_t)b * a.N + i];
-    WarpFocal f;
-    f.x = me.x; f.y = me.y; f.r = me.z;
-    f.hc = sym_heading_const(th);
-    f.fe = vf_focal_exact(me.x, me.y, me.z, th);
-    focal[tid] = f;
+    sh.focal[tid] = make_float4(me.x, me.y, me.z, __uint_as_float(sym_heading_const(th)));
+    sh.theta[tid] = th;
     atomicMin(&fbox[0], float_ordered(me.x)); atomicMin(&fbox[1], float_ordered(me.y));
     atomicMax(&fbox[2], float_ordered(me.x)); atomicMax(&fbox[3], float_ordered(me.y));
   }
   __syncthreads();
+  const float fx0 = ordered_float(fbox[0]), fy0 = ordered_float(fbox[1]);
+  const float fx1 = ordered_float(fbox[2]), fy1 = ordered_float(fbox[3]);
 
   // ---- record tiles to visit: bounding box of the CTA's focal agents against the tiles' boxes ----
-  const int tile_sz = a.tile_bbox != nullptr ? a.cull_tile : kRecTile;   // a power of two
+  const int tile_sz = a.tile_bbox != nullptr ? a.cull_tile : kRecTile;   // a power of two >= kChunk
   const int tile_sh = 31 - __clz(tile_sz);
   const int n_tiles = (a.N + tile_sz - 1) / tile_sz;
   const bool use_list = CULL && a.tile_bbox != nullptr && n_tiles <= kMaxTileList;
   int n_stage = n_tiles;
   if (use_list) {
-    const float fx0 = ordered_float(fbox[0]), fy0 = ordered_float(fbox[1]);
-    const float fx1 = ordered_float(fbox[2]), fy1 = ordered_float(fbox[3]);
     const float4* bb = a.tile_bbox + (size_t)b * n_tiles;
     const float* c2 = a.tile_cull2 + (size_t)b * n_tiles;
     for (int t = tid; t < n_tiles; t += kWarpThreads) {
@@ -159,19 +213,50 @@ __global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid
     n_stage = tile_list[kMaxTileList];
   }
 
-  // ---- pair loop: threads stride over the records of the visited tiles, every record against all focal agents ----
+  // ---- pair loop: the two halves of the CTA take alternate chunks of 128 records of the visited tiles, a thread per
+  //      record; every record meets all focal agents of the CTA ----
   unsigned n_fp64 = 0, n_differ = 0;
   {
-    const uint32_t rows_s = smem_u32(rows);
-    const int total = n_stage << tile_sh;
-    for (int idx = tid; idx < total; idx += kWarpThreads) {
-      const int st = idx >> tile_sh;
-      const int j = ((use_list ? tile_list[st] : st) << tile_sh) + (idx & (tile_sz - 1));
+    const uint32_t rows_s = smem_u32(sh.rows), focal_s = smem_u32(sh.focal), queue_s = smem_u32(sh.queue);
+    const uint32_t qcount_s = smem_u32(tile_list + kMaxTileList + 1);
+    const float S = a.y_scale;
+    const float c3s = -1.0f / (3.0f * S * S), c5s = 1.0f / (5.0f * S * S * S * S);
+    const int cpt_sh = tile_sh - 7;                          // chunks per tile = 2^cpt_sh
+    const int n_chunks = n_stage << cpt_sh;
+    const int off = tid & (kChunk - 1);
+    for (int c = tid >> 7; c < n_chunks; c += kWarpThreads / kChunk) {
+      const int st = c >> cpt_sh;
+      const int j = ((((use_list ? tile_list[st] : st) << cpt_sh) + (c & ((1 << cpt_sh) - 1))) << 7) + off;
       if (j >= a.N) continue;
       const float4 o = __ldcg(rep_in + j);
+      if (CULL && !TORUS && UNIFORM_R) {
+        // beyond reach of the whole focal box: beyond reach of every focal agent in it (same expression, monotonic)
+        const float gx = fmaxf(0.0f, fmaxf(o.x - fx1, fx0 - o.x)), gy = fmaxf(0.0f, fmaxf(o.y - fy1, fy0 - o.y));
+        if (fmaf(gx, gx, gy * gy) > o.w) continue;
+      }
+      // four focal agents per pass: four independent evaluations in flight per thread (the loop is latency-bound
+      // otherwise -- measured), without the code size of a fully unrolled F = 8
+#pragma unroll 1
+      for (int f0 = 0; f0 < nf; f0 += 4) {
 #pragma unroll
-      for (int f = 0; f < F; ++f)
-        if (f < nf) warp_pair<TORUS, CULL>(a, focal[f], rows_s + 4u * (uint32_t)((W + 1) * f), o, n_fp64, n_differ);
+        for (int u = 0; u < 4; ++u) {
+          const int f = f0 + u;
+          if (f < nf)
+            warp_pair<TORUS, CULL, FULL_FOV, UNIFORM_R>(a, lds_f4(focal_s + 16u * (uint32_t)f),
+                                                         rows_s + 4u * (uint32_t)(row_words * f), o, S, c3s, c5s,
+                                                         ((uint32_t)f << 24) | (uint32_t)j, queue_s, qcount_s, sh, n_fp64,
+                                                         n_differ);
+        }
+      }
+    }
+    // ---- slow pass: the queued pairs, one per thread ----
+    __syncthreads();
+    const int nq = min(tile_list[kMaxTileList + 1], kWarpQueue);
+    for (int q = tid; q < nq; q += kWarpThreads) {
+      const uint32_t ent = sh.queue[q];
+      const int f = (int)(ent >> 24), j = (int)(ent & 0xffffffu);
+      warp_pair_slow<TORUS>(a, sh.focal[f], sh.theta[f], rows_s + 4u * (uint32_t)(row_words * f) + 4u, __ldcg(rep_in + j),
+                            n_fp64, n_differ);
     }
   }
   {
@@ -186,8 +271,11 @@ __global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid
     const int li = li0 + warp;
     const int i = vf_tile_slot(a, li);
     const size_t gi = (size_t)b * a.N + i;
-    const uint32_t* row = rows + (size_t)(W + 1) * warp;
-    const WarpFocal& me = focal[warp];
+    uint32_t* padrow = sh.rows + (size_t)row_words * warp;
+    if (lane == 0) vf_fold_padding(padrow, 1, R, W);      // padding words back onto the ring (vf_supcalc.py:122-127)
+    __syncwarp();
+    const uint32_t* row = padrow + 1;                      // real word 0
+    const float4 me = sh.focal[warp];
     const uint32_t last_valid = (R & 31) ? ((1u << (R & 31)) - 1u) : 0xffffffffu;
     const uint32_t v_first = row[0] & 1u;
     const uint32_t v_last = (row[W - 1] >> ((R - 1) & 31)) & 1u;
@@ -220,7 +308,7 @@ __global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid
       if (a.ov_bet0) { const float v = a.ov_bet0[gi]; if (v == v) B0 = v; }
       if (a.ov_v0)   { const float v = a.ov_v0[gi];   if (v == v) V0 = v; }
       const double vel0 = a.vel[gi];
-      const float th = a.theta[gi];
+      const float th = sh.theta[warp];
       FlockTerms ft;
       if (a.phi_ok) {
         EdgeSums z;
@@ -238,9 +326,9 @@ __global__ void __launch_bounds__(kWarpThreads) vf_step_warp_kernel(const __grid
       sincos(nth, &sn, &cn);
       double nx = (double)me.x + nv * cn;                           // :303-306
       double ny = (double)me.y - nv * sn;
-      if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.r, a.width_d, a.height_d, a.pad_d);
-      else teleport_torus(nx, ny, (double)me.r, a.width_d, a.height_d, a.pad_d);
-      const float4 rec_new = make_float4((float)nx, (float)ny, me.r, rep_in[i].w);
+      if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
+      else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
+      const float4 rec_new = make_float4((float)nx, (float)ny, me.z, rep_in[i].w);
       a.rec_out[gi] = rec_new;
       if (a.n_peers > 0) {                                            // NVLink peer stores (fused tile exchange)
         for (int p = 0; p < a.n_peers; ++p) a.peer_rec_out[p][gi] = rec_new;
@@ -312,30 +400,26 @@ int vf_warp_focal_per_cta(long long focal_total, int n_sms) {
   return F;
 }
 
-template <bool TORUS, bool CULL, int F>
-static void launch_warp_variant(const VFKernelArgs& a, cudaStream_t stream) {
+template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R>
+static void launch_warp_variant(const VFKernelArgs& a, int F, cudaStream_t stream) {
   const int per_rep = (a.tile_count + F - 1) / F;
   const size_t smem = vf_warp_smem_bytes(a.W, F);
   static SmemOptIn optin;
-  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, F>, smem);
-  vf_step_warp_kernel<TORUS, CULL, F><<<(unsigned)((size_t)a.B * per_rep), kWarpThreads, smem, stream>>>(a);
+  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R>, smem);
+  vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R><<<(unsigned)((size_t)a.B * per_rep), kWarpThreads, smem, stream>>>(a, F);
 }
 template <bool TORUS, bool CULL>
-static void launch_warp_f(const VFKernelArgs& a, int F, cudaStream_t stream) {
-  switch (F) {
-    case 8: launch_warp_variant<TORUS, CULL, 8>(a, stream); break;
-    case 4: launch_warp_variant<TORUS, CULL, 4>(a, stream); break;
-    case 2: launch_warp_variant<TORUS, CULL, 2>(a, stream); break;
-    default: launch_warp_variant<TORUS, CULL, 1>(a, stream); break;
-  }
+static void launch_warp_fr(const VFKernelArgs& a, int F, bool uniform_r, cudaStream_t stream) {
+  if (a.full_fov) { if (uniform_r) launch_warp_variant<TORUS, CULL, true, true>(a, F, stream); else launch_warp_variant<TORUS, CULL, true, false>(a, F, stream); }
+  else { if (uniform_r) launch_warp_variant<TORUS, CULL, false, true>(a, F, stream); else launch_warp_variant<TORUS, CULL, false, false>(a, F, stream); }
 }
 
-void launch_vf_step_warp(const VFKernelArgs& a, bool cull, cudaStream_t stream) {
+void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaStream_t stream) {
   const char* env = getenv("ABM_VF_WARP_FOCAL");              // measurement probes only
   int F = env ? atoi(env) : vf_warp_focal_per_cta((long long)a.B * a.tile_count, a.n_sms);
   if (F != 1 && F != 2 && F != 4 && F != 8) F = 1;
-  if (a.boundary == 1) { if (cull) launch_warp_f<true, true>(a, F, stream); else launch_warp_f<true, false>(a, F, stream); }
-  else { if (cull) launch_warp_f<false, true>(a, F, stream); else launch_warp_f<false, false>(a, F, stream); }
+  if (a.boundary == 1) { if (cull) launch_warp_fr<true, true>(a, F, uniform_r, stream); else launch_warp_fr<true, false>(a, F, uniform_r, stream); }
+  else { if (cull) launch_warp_fr<false, true>(a, F, uniform_r, stream); else launch_warp_fr<false, false>(a, F, uniform_r, stream); }
 }
 
 }  // namespace abm

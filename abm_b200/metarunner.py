@@ -29,74 +29,80 @@ BASE_REPLICATE_KEYS = {"DEC_TW": "T_w", "DEC_EPSW": "Eps_w", "DEC_GW": "g_w", "D
 
 
 class Tunable:
-    """A parameter range to loop through (metarunner.py:59-96)."""
+    """One swept `.env` variable (interface of metarunner.py:59-96): either ``num_data_points`` evenly spaced values
+    from ``min_v`` to ``max_v`` inclusive, or the explicit list ``values_override`` (which wins when both are given)."""
 
     def __init__(self, var_name, min_v=None, max_v=None, num_data_points=None, values_override=None):
-        if min_v is None and values_override is None:
-            raise Exception("Neither value borders nor override values have been given to create Tunable!")
-        elif min_v is not None and values_override is not None:
-            warnings.warn("Both value borders and override values are defined when creating Tunable, using override"
-                          "values as default!")
         self.name = var_name
-        if values_override is None:
-            self.min_val, self.max_val, self.n_data, self.generated = min_v, max_v, num_data_points, True
-            self.values = np.linspace(min_v, max_v, num=num_data_points, endpoint=True)
+        explicit = values_override is not None
+        if not explicit and min_v is None:
+            raise Exception(f"Tunable {var_name!r} needs either (min_v, max_v, num_data_points) or values_override")
+        if explicit and min_v is not None:
+            warnings.warn(f"Tunable {var_name!r}: values_override given together with a range; the explicit values are used")
+        if explicit:
+            self.values = values_override
+            self.min_val, self.max_val, self.n_data = min(values_override), max(values_override), len(values_override)
         else:
-            self.min_val, self.max_val = min(values_override), max(values_override)
-            self.n_data, self.generated, self.values = len(values_override), False, values_override
-
-    def print(self):
-        print(f"Tunable: {self.name} = {self.min_val}  -  -  -n={self.n_data}-  -  -  {self.max_val}")
+            self.values = np.linspace(min_v, max_v, num=num_data_points, endpoint=True)
+            self.min_val, self.max_val, self.n_data = min_v, max_v, num_data_points
+        self.generated = not explicit
 
     def get_values(self):
         return self.values
 
+    def print(self):
+        print(f"Tunable {self.name}: {self.n_data} value(s) in [{self.min_val}, {self.max_val}]")
+
 
 class Constant:
-    """A constant parameter value (metarunner.py:30-43)."""
+    """A variable fixed for the whole sweep (interface of metarunner.py:30-43): a Tunable with a single value."""
 
     def __init__(self, var_name, constant):
         self.tunable = Tunable(var_name, values_override=[constant])
-        self.name = self.tunable.name
+        self.name = var_name
 
     def get_values(self):
-        return self.tunable.values
+        return self.tunable.get_values()
 
     def print(self):
-        print(f"Constant {self.tunable.name} = {self.tunable.values[0]}")
+        print(f"Constant {self.name} = {self.get_values()[0]}")
 
 
 class TunedPairRestrain:
-    """Parameter pair restrained by its product (metarunner.py:45-57)."""
+    """Keeps only the combinations in which the two named variables multiply to ``restrained_product`` (interface of
+    metarunner.py:45-57; with `add_quadratic_tuned_pair`: first * second^2)."""
 
     def __init__(self, var_name1, var_name2, restrained_product):
-        self.var1, self.var2, self.product_restrain = var_name1, var_name2, restrained_product
+        self.var1, self.var2 = var_name1, var_name2
+        self.product_restrain = restrained_product
 
     def get_vars(self):
         return [self.var1, self.var2]
 
     def print(self):
-        print(f"Product of {self.var1} and {self.var2} should be {self.product_restrain}")
+        print(f"Restraint: {self.var1} x {self.var2} == {self.product_restrain}")
 
 
 class MetaProtocol:
-    """metarunner.py:98-254, batched."""
+    """Sweep driver with the methods of metarunner.py:98-254; the runs are batched (module docstring).
+
+    ``default_envconf``: the base `.env` dictionary (default: ``{EXPERIMENT_NAME}.env`` under ``root_dir``, like the
+    reference's module-level ``envconf``); ``root_dir``: what the reference calls root_abm_dir (default: cwd)."""
 
     def __init__(self, experiment_name=None, num_batches=1, parallel=False, description=None, headless=True,
                  default_envconf=None, root_dir=None):
+        if parallel and experiment_name is None:
+            raise Exception("parallel=True needs an experiment_name (it names the temporary env folder of this sweep)")
         self.root_dir = root_dir or os.getcwd()
         if default_envconf is None:
-            p = params.env_path(self.root_dir)
-            default_envconf = params.read_env(p) if os.path.isfile(p) else {}
+            base = params.env_path(self.root_dir)
+            default_envconf = params.read_env(base) if os.path.isfile(base) else {}
         self.default_envconf = dict(default_envconf)
+        self.experiment_name, self.num_batches = experiment_name, num_batches
+        self.description, self.headless, self.parallel_run = description, headless, parallel
         self.tunables, self.tuned_pairs, self.q_tuned_pairs = [], [], []
-        self.experiment_name, self.num_batches, self.description = experiment_name, num_batches, description
-        self.headless = headless
-        if experiment_name is None and parallel:
-            raise Exception("Can't run multiple experiments parallely without experiment name!")
-        self.parallel_run = parallel
-        sub = f"abm/data/metaprotocol/temp/{experiment_name}" if experiment_name else "abm/data/metaprotocol/temp"
-        self.temp_dir = sub
+        self.temp_dir = os.path.join("abm/data/metaprotocol/temp", experiment_name) if experiment_name \
+            else "abm/data/metaprotocol/temp"
         self.results = []
 
     def add_criterion(self, criterion):
@@ -141,7 +147,7 @@ class MetaProtocol:
         """metarunner.py:168-199: one {i}_b{nb}.env per combination and batch."""
         temp_dir = os.path.join(self.root_dir, self.temp_dir)
         if os.path.isdir(temp_dir):
-            warnings.warn("Temprary directory for env files is not empty and will be overwritten")
+            warnings.warn(f"{temp_dir} already holds env files of an earlier sweep: they are replaced")
             shutil.rmtree(temp_dir)
         os.makedirs(temp_dir, exist_ok=True)
         names, combos = self.combinations()
@@ -157,10 +163,26 @@ class MetaProtocol:
                         f.write(f"{k}={v}\n")
         return len(combos) * self.num_batches
 
+    def save_description(self):
+        """README.txt with the sweep's description in the experiment folder (metarunner.py:203-214)."""
+        if self.description is None:
+            return
+        folder = os.path.join(self.root_dir, "abm/data/simulation_data", self.experiment_name or "UnknownExp")
+        os.makedirs(folder, exist_ok=True)
+        with open(os.path.join(folder, "README.txt"), "w") as f:
+            f.write(self.description)
+
     def run_protocols(self, project="Base", seed=None, keep_env_files=False):
-        """All remaining protocols of the temp folder (metarunner.py:240-254), grouped into
-        replicate batches.  Returns the list of (env_paths, simulation) per batch; every
-        simulation holds the final state of its replicates."""
+        """All remaining protocols of the temp folder (metarunner.py:240-254), grouped into replicate batches: the env
+        files that differ only in per-replicate parameters (and in their SAVE_ROOT_DIR) run as ONE batch, one parameter
+        set per replicate.  Every replicate writes what the reference's run of that env file would write --
+        ``<root>/<SAVE_ROOT_DIR>/<timestamp>/{ag_*.zarr, res_*.zarr, env_params.json}`` with
+        SAVE_ROOT_DIR = abm/data/simulation_data/<experiment>/batch_<nb> -- when the env file asks for it
+        (USE_RAM_LOGGING=1, SAVE_CSV_FILES=1, USE_ZARR_FORMAT=1).  ``seed``: None = independent runs (fresh seeds);
+        an int makes the sweep reproducible, group g using seed + g.
+        Returns the list of (env_paths, simulation) per batch; every simulation holds the final state of its replicates
+        and ``saved_dirs``."""
+        self.save_description()
         temp_dir = os.path.join(self.root_dir, self.temp_dir)
         paths = sorted(glob.iglob(os.path.join(temp_dir, "*.env")))
         rep_keys = VF_REPLICATE_KEYS if project == "VisualFlocking" else BASE_REPLICATE_KEYS
@@ -170,17 +192,20 @@ class MetaProtocol:
             shape = tuple(sorted((k, v) for k, v in env.items() if k not in rep_keys and k != "SAVE_ROOT_DIR"))
             groups.setdefault(shape, []).append((p, env))
         self.results = []
-        for members in groups.values():
+        for g, members in enumerate(groups.values()):
             envs = [e for _, e in members]
             kw = params.simulation_kwargs(envs[0])
+            kw.update(n_replicates=len(envs), seed=None if seed is None else int(seed) + g, root_dir=self.root_dir,
+                      save_root_dir=[e.get("SAVE_ROOT_DIR", "abm/data/simulation_data") for e in envs],
+                      env_params=[dict(e) for e in envs])
             if project == "VisualFlocking":
-                sim = VFSimulation(vf_params=params.VFParams.from_env(envs[0]), n_replicates=len(envs), seed=seed, **kw)
+                sim = VFSimulation(vf_params=params.VFParams.from_env(envs[0]), **kw)
                 per = {name: [float(e.get(k, getattr(sim.vf_params, name))) for e in envs]
                        for k, name in rep_keys.items()}
                 sim.engine.set_params(**per)
             elif project == "Base":
                 dp = params.DecisionParams.from_env(envs[0])
-                sim = Simulation(decision_params=dp, n_replicates=len(envs), seed=seed, **kw)
+                sim = Simulation(decision_params=dp, **kw)
                 base = dict(dp.engine_kwargs(), agent_consumption=kw["agent_consumption"])
                 per = {name: [float(e.get(k, base[name])) for e in envs] for k, name in rep_keys.items()}
                 sim.engine.set_params(**per)

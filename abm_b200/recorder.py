@@ -56,7 +56,9 @@ class VFRecorder:
     """Records a VFEngine's trajectory.  ``replicates``: which replicates to keep (default: all);
     ``every``: record every k-th call of `record()`; ``chunk``: steps per device ring / per zarr chunk."""
 
-    def __init__(self, engine, save_dir, replicates=None, every: int = 1, chunk: int = 64, env_params: dict | None = None):
+    def __init__(self, engine, save_dir, replicates=None, every: int = 1, chunk: int = 64, env_params=None, dirs=None):
+        """``dirs``: one output folder per recorded replicate (default: ``save_dir/replicate_<b>``); ``env_params``: one
+        dict for all, or a list with one dict per recorded replicate (written as env_params.json, env_saver.py:15-28)."""
         import torch
         self.torch = torch
         self.eng = engine
@@ -78,13 +80,13 @@ class VFRecorder:
         self._q: queue.Queue = queue.Queue()
         self._err = None
         self._dirs = []
-        for b in self.reps:
-            d = os.path.join(save_dir, f"replicate_{b:05d}")
+        for k, b in enumerate(self.reps):
+            d = os.path.join(save_dir, f"replicate_{b:05d}") if dirs is None else dirs[k]
             for name in _FIELDS + ("mode",):
                 os.makedirs(os.path.join(d, f"ag_{name}.zarr"), exist_ok=True)
             if env_params is not None:
                 with open(os.path.join(d, "env_params.json"), "w") as f:    # env_saver.py:15-28
-                    json.dump(env_params, f, indent=4)
+                    json.dump(env_params[k] if isinstance(env_params, (list, tuple)) else env_params, f, indent=4)
             self._dirs.append(d)
         self._thread = threading.Thread(target=self._writer, daemon=True)
         self._thread.start()
@@ -177,10 +179,10 @@ class BaseRecorder:
            ("ipriv", "i_priv"), ("collr", "collected"), ("explr", "patch_id"))
     _RES = (("posx", "x"), ("posy", "y"), ("rad", "radius"), ("left", "left"), ("qual", "quality"))
 
-    def __init__(self, engine, save_dir, replicates=None, every: int = 1, env_params: dict | None = None):
+    def __init__(self, engine, save_dir, replicates=None, every: int = 1, env_params=None, dirs=None):
         self.eng, self.save_dir, self.every = engine, save_dir, int(every)
         self.reps = list(range(engine.B)) if replicates is None else [int(b) for b in replicates]
-        self.env_params = env_params
+        self.env_params, self.dirs = env_params, dirs
         self.calls = 0
         self._ag = {n: [] for n, _ in self._AG}
         self._res = {n: [] for n, _ in self._RES}
@@ -202,11 +204,12 @@ class BaseRecorder:
         dirs = []
         T = len(self._ag["posx"])
         for ri, b in enumerate(self.reps):
-            d = os.path.join(self.save_dir, f"replicate_{b:05d}")
+            d = os.path.join(self.save_dir, f"replicate_{b:05d}") if self.dirs is None else self.dirs[ri]
             os.makedirs(d, exist_ok=True)
             if self.env_params is not None:
+                ep = self.env_params[ri] if isinstance(self.env_params, (list, tuple)) else self.env_params
                 with open(os.path.join(d, "env_params.json"), "w") as f:
-                    json.dump(self.env_params, f, indent=4)
+                    json.dump(ep, f, indent=4)
             for prefix, store in (("ag", self._ag), ("res", self._res)):
                 for n, steps in store.items():
                     if not steps:

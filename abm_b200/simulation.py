@@ -22,6 +22,66 @@ from .params import DecisionParams, VFParams
 _MODE_NAMES = {0: "explore", 1: "exploit", 2: "relocate", 3: "collide"}
 
 
+class _RunOutputs:
+    """The reference's end-of-run output (sims.py:878-914 -> ifdb.save_agent_data_RAM / save_resource_data_RAM every
+    step, ifdb.save_ifdb_as_csv + env_saver.save_env_vars at the end): with ``use_ram_logging`` and ``save_csv_files``
+    a run leaves ``<root>/<SAVE_ROOT_DIR>/<timestamp>/{ag_*.zarr, res_*.zarr, env_params.json}`` (ifdb_params.py:34-40,
+    ifdb.py:435-535, env_saver.py:15-28) -- here one such folder PER REPLICATE of the batch, written by
+    abm_b200.recorder.  InfluxDB logging and the json dump (USE_ZARR_FORMAT=0) are out of scope and refused."""
+
+    def _init_outputs(self, use_ifdb_logging, use_ram_logging, save_csv_files, use_zarr, save_root_dir, root_dir,
+                      env_params):
+        if use_ifdb_logging:
+            raise NotImplementedError("InfluxDB logging is out of scope of abm_b200: use USE_RAM_LOGGING=1")
+        self.save_in_ram, self.save_csv_files, self.use_zarr = bool(use_ram_logging), bool(save_csv_files), bool(use_zarr)
+        if self.save_csv_files and not self.save_in_ram:                           # sims.py:909-912
+            raise Exception("Tried to save simulation data as csv file due to env configuration, "
+                            "but IFDB/RAM logging was turned off. Nothing to save! Please turn on IFDB/RAM logging"
+                            " or turn off CSV saving feature.")
+        if self.save_csv_files and not self.use_zarr:
+            raise NotImplementedError("USE_ZARR_FORMAT=0 (json dump of the RAM log) is not supported: zarr arrays only")
+        self.save_root_dir = save_root_dir if save_root_dir is not None else "abm/data/simulation_data"
+        self.root_dir = root_dir or os.getcwd()
+        self.env_params = env_params
+        self.saved_dirs = []
+
+    def _run_dirs(self):
+        """One timestamped folder per replicate (ifdb_params.py:38-40: SAVE_ROOT_DIR/%Y-%m-%d_%H-%M-%S); the reference's
+        sequential runs get distinct stamps from the wall clock, the replicates of a batch from consecutive seconds
+        (in replicate order, so sorting the folders gives the order of the sweep)."""
+        import datetime
+        roots = self.save_root_dir if isinstance(self.save_root_dir, (list, tuple)) else [self.save_root_dir] * self.B
+        t0 = datetime.datetime.now()
+        used, out = set(), []
+        for b in range(self.B):
+            k = 0
+            while True:
+                d = os.path.join(self.root_dir, roots[b], (t0 + datetime.timedelta(seconds=b + k)).strftime("%Y-%m-%d_%H-%M-%S"))
+                if d not in used and not os.path.exists(d):
+                    break
+                k += self.B
+            used.add(d)
+            out.append(d)
+        return out
+
+    def _env_list(self):
+        e = self.env_params
+        if e is None:
+            return None
+        return list(e) if isinstance(e, (list, tuple)) else [e] * self.B
+
+    def _run_with_outputs(self, n_steps, make_recorder):
+        """Advance n_steps; with RAM logging + saving on, record every step and write the folders at the end."""
+        if not (self.save_in_ram and self.save_csv_files):
+            self.engine.step(n_steps)                     # (a RAM log that is never saved has no observable effect)
+            return
+        rec = make_recorder(self._run_dirs(), self._env_list())
+        for _ in range(n_steps):
+            self.engine.step(1)
+            rec.record()                                  # the state AFTER the update, like sims.py:861-887
+        self.saved_dirs = rec.close()
+
+
 class _View:
     """Attribute view of one agent / patch of one replicate; reads go through the owner's
     host cache (one bulk download per step), writes mark the owner dirty (one bulk upload)."""
@@ -81,7 +141,7 @@ class VFAgentView(_View):
             raise AttributeError(f"cannot set {name}")
 
 
-class VFSimulation:
+class VFSimulation(_RunOutputs):
     """Visual-flocking simulation (vf_sims.py:15-397).  Same kwargs as the reference's
     Simulation.__init__ (sims.py:60-68); the ones the hot path does not read are accepted
     and ignored.  ``vf_params``: a params.VFParams (defaults = vf_params.py defaults)."""
@@ -89,9 +149,12 @@ class VFSimulation:
     def __init__(self, N, T, v_field_res=800, width=600, height=480, framerate=25, window_pad=30,
                  with_visualization=False, agent_radius=10, agent_fov=1.0, agent_behave_param_list=None,
                  vf_params: VFParams | None = None, n_replicates: int = 1, device: int = 0, seed=None,
-                 keep_fields: bool = True, **ignored):
+                 keep_fields: bool = True, use_ifdb_logging=False, use_ram_logging=False, save_csv_files=False,
+                 use_zarr=True, save_root_dir=None, root_dir=None, env_params=None, **ignored):
         if with_visualization:
             raise NotImplementedError("rendering is out of scope of abm_b200 (headless only)")
+        self.B = int(n_replicates)
+        self._init_outputs(use_ifdb_logging, use_ram_logging, save_csv_files, use_zarr, save_root_dir, root_dir, env_params)
         # vf_sims.py:184-210, 222-228: the visual-flocking simulation accepts the list but constructs every VFAgent
         # with behave_params=None -- the dictionaries change nothing; kept for the evolution summary only (:368-371)
         self.agent_behave_param_list = agent_behave_param_list
@@ -152,7 +215,8 @@ class VFSimulation:
         """vf_sims.py:355-366."""
         self.prepare_start()
         self._sync_up()
-        self.engine.step(self.T - self.t)
+        from .recorder import VFRecorder
+        self._run_with_outputs(self.T - self.t, lambda dirs, envs: VFRecorder(self.engine, None, dirs=dirs, env_params=envs))
         self.t = self.T
         self._stale = True
         self._f = self._t = None
@@ -235,7 +299,7 @@ class ResourceView(_View):
         raise AttributeError(name)
 
 
-class Simulation:
+class Simulation(_RunOutputs):
     """Collective-foraging simulation (sims.py:59-920), headless.  Same kwargs as the
     reference; ``decision_params``: a params.DecisionParams (defaults = the param modules)."""
 
@@ -248,9 +312,11 @@ class Simulation:
                  ghost_mode=True, patchwise_exclusion=True, parallel=False, use_zarr=True,
                  allow_border_patch_overlap=False, agent_behave_param_list=None, collide_agents=False,
                  decision_params: DecisionParams | None = None, n_replicates: int = 1, device: int = 0, seed=None,
-                 keep_fields: bool = True):
+                 keep_fields: bool = True, save_root_dir=None, root_dir=None, env_params=None):
         if with_visualization:
             raise NotImplementedError("rendering is out of scope of abm_b200 (headless only)")
+        self.B = int(n_replicates)
+        self._init_outputs(use_ifdb_logging, use_ram_logging, save_csv_files, use_zarr, save_root_dir, root_dir, env_params)
         if pooling_time != 0:
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
         self.heterogen_agents = agent_behave_param_list is not None                # sims.py:170-173
@@ -371,7 +437,8 @@ class Simulation:
         """sims.py:702-920 without rendering / logging."""
         self.create_agents()
         self.create_resources()
-        self.engine.step(self.T - self.t)
+        from .recorder import BaseRecorder
+        self._run_with_outputs(self.T - self.t, lambda dirs, envs: BaseRecorder(self.engine, None, dirs=dirs, env_params=envs))
         self.t = self.T
         self._a = self._p = self._f = None
 

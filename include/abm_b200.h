@@ -348,6 +348,14 @@ int abm_base_get_patches(abm_base_engine_t* e, const abm_base_patches_t* dst, in
 int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta, int inject_on_device,
                   uint32_t phases, void* stream);
 
+/* Patch regeneration with GIVEN draws (parity tests; the counterpart of inject_dtheta): Simulation.add_new_resource_patch
+ * (sims.py:332-374) draws x, y (np.random.randint), units (randint) and quality (uniform) for every try and retries
+ * while the new patch overlaps another one.  draws: n_replicates * n_patches * n_tries * 4 doubles -- (x, y, units,
+ * quality) of try t of a regeneration of patch slot p of replicate b, host pointer; a regeneration that exhausts its
+ * n_tries counts as failed (abm_base_get_counters [1]) and leaves the slot dead.  Applies to all following steps;
+ * draws == NULL or n_tries <= 0 returns to the engine's counter-based RNG. */
+int abm_base_inject_regeneration(abm_base_engine_t* e, const double* draws, int n_tries);
+
 /* Packed STORED fields (flipped + FOV-masked: Agent.soc_v_field, agent.py:593-597) of the last step. */
 int abm_base_get_fields(abm_base_engine_t* e, uint32_t* packed, int on_device, void* stream);
 

@@ -103,6 +103,27 @@ class _Group(list):
             s.update(*args, **kwargs)
 
 
+def _collide_circle(left, right):
+    """pygame.sprite.collide_circle as pygame DOCUMENTS it (pygame itself is not in the image and not vendored by the
+    reference, so this arithmetic cannot be pinned -- SURVEY 8c): circles around the rect centres, the sprites' own
+    `radius` attributes, touching counts as colliding."""
+    dx = left.rect.centerx - right.rect.centerx
+    dy = left.rect.centery - right.rect.centery
+    rs = left.radius + right.radius
+    return dx * dx + dy * dy <= rs * rs
+
+
+def _groupcollide(groupa, groupb, dokilla, dokillb, collided=None):
+    """pygame.sprite.groupcollide (documented semantics, no kills needed by the reference's calls): {sprite of groupa:
+    [colliding sprites of groupb]} for the sprites of groupa with at least one collision, in group order."""
+    out = {}
+    for a in list(groupa):
+        hits = [b for b in list(groupb) if collided(a, b)]
+        if hits:
+            out[a] = hits
+    return out
+
+
 def install():
     """Install the stubs and put the reference on sys.path.  Idempotent."""
     if not reference_available():
@@ -113,8 +134,8 @@ def install():
         sprite = types.ModuleType("pygame.sprite")
         sprite.Sprite = _Sprite
         sprite.Group = _Group
-        sprite.collide_circle = MagicMock()
-        sprite.groupcollide = MagicMock()
+        sprite.collide_circle = _collide_circle
+        sprite.groupcollide = _groupcollide
         pg.sprite = sprite
         pg.Surface = _Surface
         for name in ("draw", "mask", "gfxdraw", "transform", "math", "display", "time", "event",

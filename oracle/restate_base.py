@@ -301,6 +301,32 @@ def base_patch_phase(st, patches, cfg: BaseConfig, collided=(), agent_cfgs=None)
     return depleted
 
 
+def base_regenerate_patch(patches, p, draws, patch_radius):
+    """Simulation.kill_resource + add_new_resource_patch(force_id) (sims.py:321-374) for patch slot ``p`` with the four
+    random draws of every try GIVEN: ``draws`` (n_tries, 4) = (x, y, units, quality) in the order the reference draws
+    them (:351-361).  A try is accepted when the new patch overlaps no other patch (proove_sprite with
+    prove_with_res only, :362-372: pygame's collide_circle on the rect centres, touching counts -- pygame's documented
+    rule, restated).  The patch keeps its id and slot.  Returns the number of tries used (0: every try overlapped)."""
+    R = float(patch_radius)
+    for t, (x, y, units, quality) in enumerate(np.asarray(draws, np.float64)):
+        ok = True
+        for q in range(len(patches["x"])):
+            if q == p or patches["radius"][q] <= 0:            # the killed patch itself / dead slots are not in the group
+                continue
+            r2 = float(patches["radius"][q])
+            dx = (x + R) - (patches["x"][q] + r2)
+            dy = (y + R) - (patches["y"][q] + r2)
+            if dx * dx + dy * dy <= (R + r2) ** 2:
+                ok = False
+                break
+        if ok:
+            patches["x"][p], patches["y"][p], patches["radius"][p] = x, y, R
+            patches["left"][p], patches["quality"][p] = int(units), quality
+            return t + 1
+    patches["radius"][p] = 0.0
+    return 0
+
+
 # --------------------------------------------------------------------------------------
 # collision phase (sims.py:736-783, 421-468; interactions.py:5-10)  -- PARITY UNPINNED
 # --------------------------------------------------------------------------------------

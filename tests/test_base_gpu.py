@@ -262,7 +262,7 @@ def test_full_loop_runs_and_forages(built_lib):
     assert a["collected"].sum() > 0
     assert not np.array_equal(a["x"][0], a["x"][1])
     c = eng.counters()
-    assert c["steps"] == 300 and c["launches"] == 600 and c["regeneration_failed"] == 0
+    assert c["steps"] == 300 and c["launches"] == 300 and c["regeneration_failed"] == 0   # ONE fused launch per step
     eng.close()
 
 
@@ -404,7 +404,7 @@ def test_full_loop_with_collisions(built_lib):
         assert np.isfinite(a["x"]).all() and np.isfinite(a["theta"]).all()
         d = np.sqrt((a["x"][:, :, None] - a["x"][:, None, :]) ** 2 + (a["y"][:, :, None] - a["y"][:, None, :]) ** 2)
         overlaps[collide] = int(((d < 12.0).sum() - B * N) // 2)
-        assert eng.counters()["launches"] == (600 if collide else 400)
+        assert eng.counters()["launches"] == 200                            # one fused launch per step either way
         eng.close()
     print("deeply overlapping pairs without / with collision avoidance:", overlaps[False], overlaps[True])
     assert overlaps[True] <= overlaps[False]
@@ -459,4 +459,107 @@ def test_base_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
         assert got.shape == (N, T) and np.array_equal(got, np.trunc(exp) if trunc else exp), name
     got = read_zarr_v2(os.path.join(d, "res_left.zarr"))
     assert got.shape == (P, T) and np.array_equal(got, np.stack([w[1]["left"][1].astype(np.float64) for w in want], axis=1))
+    eng.close()
+
+
+def test_fused_step_equals_separate_phases(built_lib, monkeypatch):
+    """The one-launch step (a CTA per replicate runs collisions, agent-patch interaction and Agent.update in the
+    reference's order, sims.py:733-864) against one grid per phase: identical trajectories, bit for bit, over 150 steps
+    of a config-3-like sweep (occlusion, collisions, depletion and regeneration, one Eps_w per replicate)."""
+    from abm_b200 import BaseEngine
+    B, N, P, W = 24, 50, 3, 500.0
+    rng = np.random.default_rng(17)
+    x0, y0 = rng.integers(20, 520, (B, N)), rng.integers(20, 520, (B, N))
+    th0 = rng.uniform(0, 2 * np.pi, (B, N))
+    pa = dict(x=rng.integers(60, 400, (B, P)), y=rng.integers(60, 400, (B, P)), radius=np.full((B, P), 30.0),
+              left=np.full((B, P), 40.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
+    res = {}
+    for separate in (False, True):
+        if separate:
+            monkeypatch.setenv("ABM_BASE_SEPARATE_PHASES", "1")
+        else:
+            monkeypatch.delenv("ABM_BASE_SEPARATE_PHASES", raising=False)
+        eng = BaseEngine(B, N, P, resolution=1200, width=W, height=W, visual_exclusion=True, collide_agents=True,
+                         ghost_mode=False, min_resc_perpatch=30, max_resc_perpatch=50, seed=5, keep_fields=True)
+        eng.set_params(Eps_w=np.linspace(0, 5, B), Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5,
+                       exp_theta_max=0.5, reloc_theta_max=1.8, exp_stop_ratio=0.175)
+        eng.set_agents(x=x0, y=y0, theta=th0)
+        eng.set_patches(**pa)
+        eng.step(150)
+        res[separate] = (eng.get_agents(), eng.get_patches(), eng.fields(), eng.counters())
+        eng.close()
+    assert res[False][3]["launches"] == 150 and res[True][3]["launches"] == 450
+    assert res[False][3]["patches_regenerated"] == res[True][3]["patches_regenerated"] > 0
+    for k, v in res[False][0].items():
+        assert np.array_equal(v, res[True][0][k]), k
+    for k, v in res[False][1].items():
+        assert np.array_equal(v, res[True][1][k]), k
+    assert np.array_equal(res[False][2], res[True][2])
+
+
+@pytest.mark.parametrize("border_overlap", [False, True])
+def test_patch_regeneration_matches_oracle(built_lib, border_overlap):
+    """kill_resource / add_new_resource_patch (sims.py:321-374) in the environment phase with INJECTED draws
+    (abm_base_inject_regeneration): patches are exhausted by their exploiters in this step, the prepared tries first
+    land on other patches (retry loop), and position / units / quality / id of every regenerated patch as well as the
+    number of regenerations equal the oracle's (oracle/restate_base.base_regenerate_patch, itself pinned to the live
+    reference in tests/test_oracle_base.py)."""
+    rng = np.random.default_rng(33)
+    B, N, P, W = 6, 24, 4, 400.0
+    R, pad = 30.0, 30.0
+    cfg = rb.BaseConfig(R=600, width=W, height=W, agent_consumption=1.0)
+    states, patches = [], []
+    T = 10
+    draws = np.zeros((B, P, T, 4))
+    for b in range(B):
+        pos = []
+        while len(pos) < P:
+            x, y = int(rng.integers(pad, W + pad - 2 * R)), int(rng.integers(pad, W + pad - 2 * R))
+            if all((x - a_) ** 2 + (y - b_) ** 2 > (2 * R) ** 2 for a_, b_ in pos):
+                pos.append((x, y))
+        pa = dict(x=np.array([q[0] for q in pos], float), y=np.array([q[1] for q in pos], float),
+                  radius=np.full(P, R), left=rng.choice([0.5, 1.0, 40.0], P).astype(float), quality=np.full(P, 0.75),
+                  id=np.arange(1, P + 1))
+        st = _random_state(rng, N, W, cfg)
+        for i in range(N):                         # two exploiting agents on every patch: the scarce ones die this step
+            if i < 2 * P:
+                q = i // 2
+                st["x"][i], st["y"][i] = pos[q][0] + R - 10 + (i % 2) * 6, pos[q][1] + R - 10
+                st["override"][i], st["mode"][i] = 1, 1
+        for p in range(P):
+            for t in range(T):
+                if t < 2 and rng.uniform() < 0.8:  # lands on another patch: rejected
+                    q = int(rng.choice([k for k in range(P) if k != p]))
+                    draws[b, p, t, 0] = pos[q][0] + int(rng.integers(-20, 20))
+                    draws[b, p, t, 1] = pos[q][1] + int(rng.integers(-20, 20))
+                else:
+                    lo = pad - R if border_overlap else pad
+                    draws[b, p, t, 0] = int(rng.integers(lo, W + pad - 2 * R))
+                    draws[b, p, t, 1] = int(rng.integers(lo, W + pad - 2 * R))
+                draws[b, p, t, 2] = int(rng.integers(20, 60)); draws[b, p, t, 3] = np.float32(rng.uniform(0.1, 1.0))
+        states.append(st); patches.append(pa)
+    eng = _engine_for(cfg, B, N, P, regenerate_patches=True, patch_border_overlap=border_overlap, patch_radius=R)
+    stacked = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    eng.set_agents(x=stacked["x"], y=stacked["y"], theta=stacked["theta"], vel=stacked["vel"], w=stacked["w"],
+                   u=stacked["u"], collected=stacked["collected"], collected_before=stacked["collected_before"],
+                   env_status=stacked["env_status"], override_mode=stacked["override"], mode=stacked["mode"],
+                   patch_id=stacked["patch_id"], novelty=stacked["novelty"])
+    eng.set_patches(**{k: np.stack([p_[k] for p_ in patches]) for k in patches[0]})
+    eng.inject_regeneration(draws)
+    eng.step(1, phases=PHASE_ENV)
+    gp, cnt = eng.get_patches(), eng.counters()
+    n_regen = 0
+    for b in range(B):
+        st = {k: (np.array(v, dtype=float) if k in ("theta", "collected", "collected_before") else np.array(v))
+              for k, v in states[b].items()}
+        pa = {k: np.array(v, dtype=float if k != "id" else int) for k, v in patches[b].items()}
+        # the reference regenerates a patch the moment it is exhausted, inside the patch loop (sims.py:829-836)
+        for p in rb.base_patch_phase(st, pa, cfg):
+            assert rb.base_regenerate_patch(pa, p, draws[b, p], R) >= 1
+            n_regen += 1
+        for k in ("x", "y", "radius", "left", "quality"):
+            np.testing.assert_allclose(gp[k][b], pa[k], rtol=1e-6, err_msg=f"{k} replicate {b}")
+        assert np.array_equal(gp["id"][b], pa["id"])
+    assert n_regen >= 4 and cnt["patches_regenerated"] == n_regen and cnt["regeneration_failed"] == 0
+    eng.inject_regeneration(None)
     eng.close()

@@ -93,10 +93,19 @@ def test_simulation_facade_heterogeneous_agents(built_lib):
 
 
 def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
+    """the generated env files run as ONE replicate batch, and every replicate leaves what the reference's
+    sequential run of its env file leaves on disk (metarunner.py:168-254, ifdb_params.py:34-40, ifdb.py:435-535,
+    env_saver.py:15-28): <root>/abm/data/simulation_data/<exp>/batch_<nb>/<timestamp>/{ag_*.zarr, env_params.json}."""
+    import glob
+    import json
+    import os
     from abm_b200 import metarunner as mr
+    from abm_b200.recorder import read_zarr_v2
     env = dict(N="12", T="20", VISUAL_FIELD_RESOLUTION="1200", ENV_WIDTH="400", ENV_HEIGHT="400", RADIUS_AGENT="10",
-               AGENT_FOV="1", APP_VERSION="VisualFlocking", BOUNDARY="walls", VF_ALP1="0.09", VF_BET1="0.09")
-    mp = mr.MetaProtocol("sweep", num_batches=2, default_envconf=env, root_dir=str(tmp_path))
+               AGENT_FOV="1", APP_VERSION="VisualFlocking", BOUNDARY="walls", VF_ALP1="0.09", VF_BET1="0.09",
+               USE_RAM_LOGGING="1", SAVE_CSV_FILES="1", USE_ZARR_FORMAT="1")
+    mp = mr.MetaProtocol("sweep", num_batches=2, default_envconf=env, root_dir=str(tmp_path),
+                         description="ALP0 x BET0 sweep")
     mp.add_criterion(mr.Tunable("VF_ALP0", values_override=[0, 1, 3]))
     mp.add_criterion(mr.Tunable("VF_BET0", values_override=[0, 2]))
     assert mp.generate_temp_env_files() == 12
@@ -107,8 +116,59 @@ def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
     assert sim.engine.counters()["launches"] == 20
     st = sim.engine.get_state()
     assert np.isfinite(st["x"]).all()
-    # replicates with ALP0 = BET0 = 0 only relax their speed towards V0: headings never change
+    # ---- on-disk layout ----
+    exp_dir = tmp_path / "abm" / "data" / "simulation_data" / "sweep"
+    assert (exp_dir / "README.txt").read_text() == "ALP0 x BET0 sweep"
+    assert len(sim.saved_dirs) == 12
+    zero_gain = []
+    for nb in (0, 1):
+        runs = sorted(glob.glob(str(exp_dir / f"batch_{nb}" / "*")))
+        assert len(runs) == 6                          # 3 x 2 combinations per batch, one timestamped folder each
+        for d in runs:
+            assert len(os.path.basename(d)) == len("2024-01-01_00-00-00")
+            with open(os.path.join(d, "env_params.json")) as f:
+                saved = json.load(f)
+            assert saved["SAVE_ROOT_DIR"].endswith(os.path.join("sweep", f"batch_{nb}")) and saved["N"] == "12"
+            b = sim.saved_dirs.index(d)
+            ori = read_zarr_v2(os.path.join(d, "ag_ori.zarr"))
+            posx = read_zarr_v2(os.path.join(d, "ag_posx.zarr"))
+            assert ori.shape == (12, 20) and posx.shape == (12, 20)
+            assert np.array_equal(ori[:, -1], st["theta"][b].astype(np.float64))          # the replicate's own trajectory
+            assert np.array_equal(posx[:, -1], np.trunc(st["x"][b].astype(np.float64)))   # int(position), ifdb.py:83-84
+            if float(saved["VF_ALP0"]) == 0 and float(saved["VF_BET0"]) == 0:
+                zero_gain.append(ori)
+    # replicates with ALP0 = BET0 = 0 only relax their speed towards V0: their headings never change
+    # (away from the walls: reflections turn them)
+    assert len(zero_gain) == 2
+    for ori in zero_gain:
+        unchanged = (ori == ori[:, :1]).all(axis=1)
+        assert unchanged.sum() >= 8
     assert mp.run_protocols(project="VisualFlocking") == []      # env files are consumed
+
+
+def test_simulation_writes_reference_output_folder(built_lib, tmp_path):
+    """Simulation(use_ram_logging, save_csv_files, use_zarr) -> <root>/<SAVE_ROOT_DIR>/<timestamp>/ with the agent and
+    resource arrays of ifdb.py:435-535 and env_params.json; saving without logging raises like sims.py:909-912."""
+    import os
+    from abm_b200.recorder import read_zarr_v2
+    from abm_b200.simulation import Simulation
+    kw = dict(N=10, T=15, v_field_res=1200, width=500, height=500, agent_radius=10, N_resc=3, patch_radius=30,
+              min_resc_perpatch=30, max_resc_perpatch=40, min_resc_quality=0.25, max_resc_quality=-1,
+              vision_range=2000, visual_exclusion=True, teleport_exploit=False, seed=3)
+    with pytest.raises(Exception, match="Nothing to save"):
+        Simulation(save_csv_files=True, use_ram_logging=False, **kw)
+    sim = Simulation(use_ram_logging=True, save_csv_files=True, use_zarr=True, root_dir=str(tmp_path),
+                     save_root_dir="abm/data/simulation_data/single", env_params={"N": "10", "T": "15"}, **kw)
+    sim.start()
+    assert len(sim.saved_dirs) == 1 and sim.saved_dirs[0].startswith(str(tmp_path / "abm/data/simulation_data/single"))
+    d = sim.saved_dirs[0]
+    for name in ("ag_posx", "ag_posy", "ag_ori", "ag_vel", "ag_mode", "ag_w", "ag_u", "ag_ipriv", "ag_collr", "ag_explr"):
+        assert read_zarr_v2(os.path.join(d, name + ".zarr")).shape == (10, 15), name
+    for name in ("res_posx", "res_posy", "res_rad", "res_left", "res_qual"):
+        assert read_zarr_v2(os.path.join(d, name + ".zarr")).shape == (3, 15), name
+    assert os.path.isfile(os.path.join(d, "env_params.json"))
+    a = sim.engine.get_agents()
+    assert np.array_equal(read_zarr_v2(os.path.join(d, "ag_w.zarr"))[:, -1], a["w"][0].astype(np.float64))
 
 
 def test_tiled_swarm_matches_single_gpu_if_two_gpus(built_lib):

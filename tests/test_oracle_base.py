@@ -164,3 +164,74 @@ def test_collision_proximity_matches_live_reference(ghost, vis_excl):
         # the restatement also ran the post-loop bookkeeping of sims.py:778-783: compare before it
         if a.overriding_mode == "exploit":
             assert st["override"][i] == rb.OV_EXPLOIT
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("border_overlap", [False, True])
+def test_patch_regeneration_matches_live_reference(monkeypatch, border_overlap):
+    """Simulation.kill_resource / add_new_resource_patch(force_id) (sims.py:321-374) of the real reference, its four
+    numpy draws per try replaced by a prepared sequence, against oracle/restate_base.base_regenerate_patch fed the same
+    draws: same number of tries, same position / units / quality / id.  (The overlap predicate itself is pygame's
+    collide_circle -- restated from pygame's documentation in the harness, see ref_shim._collide_circle.)"""
+    ref_shim.install()
+    import pygame
+    from abm.simulation import sims
+    from abm.environment.rescource import Rescource
+    rng = np.random.default_rng(12)
+    W = H = 400
+    pad, R = 30, 30
+    for trial in range(40):
+        P = int(rng.integers(2, 6))
+        # existing patches (non-overlapping, like create_resources leaves them)
+        pos = []
+        while len(pos) < P:
+            x, y = int(rng.integers(pad, W + pad - 2 * R)), int(rng.integers(pad, H + pad - 2 * R))
+            if all((x - a) ** 2 + (y - b) ** 2 > (2 * R) ** 2 for a, b in pos):
+                pos.append((x, y))
+        group = pygame.sprite.Group()
+        res = [Rescource(i + 1, R, pos[i], (W, H), (0, 0, 0), pad, 50, 0.5) for i in range(P)]
+        for r_ in res:
+            group.add(r_)
+        p = int(rng.integers(0, P))
+        # draws: a few tries that land on an existing patch, then free positions
+        T = 12
+        draws = np.zeros((T, 4))
+        for t in range(T):
+            if t < 3 and rng.uniform() < 0.7:
+                q = int(rng.choice([k for k in range(P) if k != p]))
+                draws[t, 0] = pos[q][0] + int(rng.integers(-R, R)); draws[t, 1] = pos[q][1] + int(rng.integers(-R, R))
+            else:
+                draws[t, 0] = int(rng.integers(pad - R if border_overlap else pad, W + pad - R))
+                draws[t, 1] = int(rng.integers(pad - R if border_overlap else pad, H + pad - R))
+            draws[t, 2] = int(rng.integers(20, 60)); draws[t, 3] = rng.uniform(0.1, 1.0)
+        # the reference, its RNG calls replaced by the prepared values in the order it makes them (:351-361)
+        seq = [v for row in draws for v in (int(row[0]), int(row[1]), int(row[2]), float(row[3]))]
+        it = iter(seq)
+        monkeypatch.setattr(np.random, "randint", lambda *a, **k: next(it))
+        monkeypatch.setattr(np.random, "uniform", lambda *a, **k: next(it))
+        sim = object.__new__(sims.Simulation)
+        sim.rescources, sim.agents = group, pygame.sprite.Group()
+        sim.resc_radius, sim.allow_border_patch_overlap, sim.regenerate_resources = R, border_overlap, True
+        sim.window_pad, sim.WIDTH, sim.HEIGHT = pad, W, H
+        sim.min_resc_units, sim.max_resc_units, sim.min_resc_quality, sim.max_resc_quality = 20, 60, 0.1, 1.0
+        victim = res[p]
+        victim.show_stats = False
+        try:
+            sim.kill_resource(victim)
+            failed = False
+        except StopIteration:
+            failed = True                         # every prepared try overlapped
+        monkeypatch.undo()
+        patches = dict(x=np.array([q[0] for q in pos], float), y=np.array([q[1] for q in pos], float),
+                       radius=np.full(P, float(R)), left=np.full(P, 50.0), quality=np.full(P, 0.5),
+                       id=np.arange(1, P + 1))
+        used = rb.base_regenerate_patch(patches, p, draws, R)
+        if failed:
+            assert used == 0
+            continue
+        new = [r_ for r_ in group if r_.id == p + 1]
+        assert len(new) == 1 and len(group) == P                       # same id, one patch per id
+        n = new[0]
+        assert used >= 1 and (n.position[0], n.position[1]) == (patches["x"][p], patches["y"][p])
+        assert n.resc_left == patches["left"][p] and n.unit_per_timestep == patches["quality"][p]
+        assert (4 * used) == len(seq) - len(list(it))                  # the reference consumed exactly `used` tries
