@@ -116,6 +116,15 @@ class BaseEngine:
             self._h, C.c_void_p(f0.ctypes.data), C.c_void_p(f1.ctypes.data), C.c_void_p(vr.ctypes.data),
             self.B * self.N), "abm_base_set_agent_geometry")
 
+    def set_agent_radii(self, radius=None):
+        """Per-agent radius, (B, N) or (N,) (heterogeneous agents, sims.py:502); None returns to the engine-wide one."""
+        if radius is None:
+            _lib.check(self._lib.abm_base_set_agent_radii(self._h, None, 0), "abm_base_set_agent_radii")
+            return
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float64), (self.B, self.N)))
+        _lib.check(self._lib.abm_base_set_agent_radii(self._h, C.c_void_p(r.ctypes.data), self.B * self.N),
+                   "abm_base_set_agent_radii")
+
     # -- state -----------------------------------------------------------------------------
     def _fill(self, struct_cls, fields, arrays, count, keep):
         s = struct_cls()

@@ -16,6 +16,8 @@
 // sequence (unit vectors -> arccos -> first-arg-min bin -> int() truncation), so the integer
 // interval ends agree with the float64 reference without guard bands; with N <= a few hundred
 // agents per replicate the all-pairs work is small next to the occlusion pass.
+#include <algorithm>
+
 #include "abm_base.cuh"
 #include "abm_base_device.cuh"
 
@@ -51,6 +53,11 @@ __device__ __forceinline__ void notify(const BaseAgentPtrs& ag, size_t g, int st
   ag.patch_id[g] = res_id;                                   // :39-42 (None -> -1)
 }
 
+// radius of agent g (global index): its own (heterogeneous agents, sims.py:502) or the engine-wide one
+__device__ __forceinline__ double base_radius_of(const BaseKernelArgs& a, size_t g) {
+  return a.ag.radius ? (double)a.ag.radius[g] : a.radius;
+}
+
 // Parameter set of agent i of replicate b: one set for the whole batch, one per replicate (sweeps), or one per agent
 // (heterogeneous agents, agent.py:83-108).
 __device__ __forceinline__ const BaseParams& base_params_of(const BaseKernelArgs& a, int b, int i) {
@@ -63,10 +70,9 @@ __device__ __forceinline__ const BaseParams& base_params_of(const BaseKernelArgs
 // the chunk's exploiters.  Per agent the notify sequence is the reference's: on a patch destroyed by agent d in this
 // step, agents i <= d see (+1, -1), agents i > d see (-1, -1); the second notification of each is the destroy loop's
 // (sims.py:829-836), applied after the patch's pass.
-__device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int b, int lane) {
+__device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int b, int lane, unsigned step) {
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * a.N, p0 = (size_t)b * a.P;
-  const double r = a.radius;
   for (int p = 0; p < a.P; ++p) {
     const double prad = a.pa.radius[p0 + p];
     const double pcx = (double)a.pa.x[p0 + p] + prad, pcy = (double)a.pa.y[p0 + p] + prad;
@@ -76,6 +82,7 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
       const int i = c0 + lane;
       const size_t g = a0 + (i < a.N ? i : 0);
       bool member = false;
+      const double r = base_radius_of(a, g);       // the agent's own radius: its centre is position + radius
       if (i < a.N) {
         const double ddx = ((double)a.ag.x[g] + r) - pcx, ddy = ((double)a.ag.y[g] + r) - pcy;
         member = sqrt(ddx * ddx + ddy * ddy) < prad;                                 // sims.py:45-56
@@ -127,6 +134,7 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
         const int i = c0 + lane;
         if (i < a.N) {
           const size_t g = a0 + i;
+          const double r = base_radius_of(a, g);
           const double ex = ((double)a.ag.x[g] + r) - pcx, ey = ((double)a.ag.y[g] + r) - pcy;
           if (sqrt(ex * ex + ey * ey) < prad) notify(a.ag, g, -1, -1, tau_mask);
         }
@@ -144,12 +152,12 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
             const double* d = a.regen_draws + (((size_t)b * a.P + p) * a.regen_tries + t) * 4;
             nx = d[0]; ny = d[1]; units = (int)d[2]; q = d[3];
           } else {
-            const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t),
+            const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, step, t),
                                         make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x50415443u));
             double lox, hix, loy, hiy;
             if (a.border_overlap) { lox = a.pad - R_; hix = a.width + a.pad - R_; loy = a.pad - R_; hiy = a.height + a.pad - R_; }
             else { lox = a.pad; hix = a.width + a.pad - 2 * R_; loy = a.pad; hiy = a.height + a.pad - 2 * R_; }
-            const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, a.step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
+            const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
             nx = floor(lox + floor(hix - lox) * u01(rn.x, rn.y));          // np.random.randint(lo, hi)
             ny = floor(loy + floor(hiy - loy) * u01(rn.z, rn.w));
             units = a.min_units + (int)floor((double)(a.max_units - a.min_units) * u01(rn2.x, rn2.y));
@@ -191,7 +199,7 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
 __global__ void __launch_bounds__(128) base_env_kernel(const BaseKernelArgs a) {
   const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= a.B) return;
-  base_env_replicate(a, b, lane);
+  base_env_replicate(a, b, lane, a.step);
 }
 
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream) {
@@ -270,9 +278,9 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
         if (!base_interval_fast(xj_f - xi_f, yj_f - yi_f, bf, o.s, o.e, vis)) {
           rec = vis; o.d = n2;
         } else {                                                                    // inside a guard band: fp64
-          const FocalExact fe = vf_focal_exact(xi_f, yi_f, (float)r, th_f);
           double dist;
-          rec = base_interval(fe, r, xi_f, yi_f, xj_f, yj_f, fov0, fov1, R, a.lin_step, o, dist);
+          rec = base_interval_cold(xi_f, yi_f, r, th_f, xj_f, yj_f, fov0, fov1, R, a.lin_step, o.s, o.e, dist);
+          o.d = dist;
           atomicAdd(&a.counters[2], 1ull);
         }
         // list order of the reference: social cues, then other occluders, then same-patch
@@ -306,11 +314,11 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
 // Decision process, mode machine, kinematics (agent.py:168-283) of one focal agent, fp64, one THREAD per agent: the
 // threads 0 .. warps-1 of the CTA take the agents of its warps after a barrier, so that this serial code runs with as many
 // lanes as the CTA has agents instead of on lane 0 of every warp.
-__device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long long gw, int n_left, int n_right) {
+__device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long long gw, int n_left, int n_right, unsigned step) {
   const int b = (int)(gw / a.N), i = (int)(gw - (long long)b * a.N);
   const size_t gi = (size_t)b * a.N + i;
   const int R = a.R, h = R / 2;
-  const double xi = a.ag.snap_x[gi], yi = a.ag.snap_y[gi], r = a.radius;
+  const double xi = a.ag.snap_x[gi], yi = a.ag.snap_y[gi], r = base_radius_of(a, gi);   // own radius at the walls
   const BaseParams prm = base_params_of(a, b, i);
   const double mean_all = (double)(n_left + n_right) / (double)R;
   const double collected = a.ag.collected[gi];
@@ -335,7 +343,7 @@ __device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long 
       double rnd;
       if (a.inject_dtheta) rnd = a.inject_dtheta[gi];
       else {
-        const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)i, a.step, 0u),
+        const uint4 rn = philox4x32(make_uint4((uint32_t)b, (uint32_t)i, step, 0u),
                                     make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
         rnd = prm.exp_theta_min + (prm.exp_theta_max - prm.exp_theta_min) * u01(rn.x, rn.y);
       }
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(256, 3) base_agent_kernel(const BaseKernelArgs
   __syncthreads();
   if (threadIdx.x < wpb) {
     const long long g2 = (long long)blockIdx.x * wpb + threadIdx.x;
-    if (g2 < total) base_agent_decide(a, g2, halves[2 * threadIdx.x], halves[2 * threadIdx.x + 1]);
+    if (g2 < total) base_agent_decide(a, g2, halves[2 * threadIdx.x], halves[2 * threadIdx.x + 1], a.step);
   }
 }
 
@@ -410,33 +418,35 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
   int* col = reinterpret_cast<int*>(th + N);                             // member of collided_agents
   float* px = reinterpret_cast<float*>(col + N);                         // positions (this phase does not move anybody)
   float* py = px + N;
+  float* rad = py + N;                                                   // radii (own: heterogeneous agents)
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * N;
-  const double r = a.radius;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     ov[i] = a.ag.override_mode[a0 + i]; md[i] = a.ag.mode[a0 + i]; th[i] = a.ag.theta[a0 + i]; col[i] = 0;
-    px[i] = a.ag.x[a0 + i]; py[i] = a.ag.y[a0 + i];
+    px[i] = a.ag.x[a0 + i]; py[i] = a.ag.y[a0 + i]; rad[i] = (float)base_radius_of(a, a0 + i);
   }
   __syncthreads();
-  const float lim2 = (float)((2.0 * (r + 2.0)) * (2.0 * (r + 2.0)));     // (r1 + 2 + r2 + 2)^2, sims.py:739-752
+  // pygame's collide_circle (documented): circles of the sprites' radii (+2 each, sims.py:739-752) around the rect
+  // centres = int-truncated position + half the integer rect size
+  auto hits = [&](int p, int q) {
+    const float dx = (truncf(px[p]) + truncf(rad[p])) - (truncf(px[q]) + truncf(rad[q]));
+    const float dy = (truncf(py[p]) + truncf(rad[p])) - (truncf(py[q]) + truncf(rad[q]));
+    const float rs = rad[p] + rad[q] + 4.0f;
+    return dx * dx + dy * dy <= rs * rs;
+  };
 
   // hit agents first (cheap), then the warps pull them from a list: the events of one hit agent are a sequential chain
   // of fp64 latency, and with a fixed assignment the CTA waited at the final barrier for its unluckiest warp (more than
   // half of the kernel's warp time)
   // (agents hit by several others -- the long chains -- are listed from the front and taken first, the rest from the back)
-  int* work = reinterpret_cast<int*>(py + N);                            // [N] hit agents, then: front count, back count, next
+  int* work = reinterpret_cast<int*>(rad + N);                           // [N] hit agents, then: front count, back count, next
   if (threadIdx.x == 0) { work[N] = 0; work[N + 1] = 0; work[N + 2] = 0; }
   __syncthreads();
   for (int a2 = wib; a2 < N; a2 += wpb) {
-    const float tx2 = truncf(px[a2]), ty2 = truncf(py[a2]);
     int n_hit = 0;
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int jj = j0 + lane;
-      bool hit = false;
-      if (jj < N && jj != a2) {
-        const float dx = truncf(px[jj]) - tx2, dy = truncf(py[jj]) - ty2;
-        hit = dx * dx + dy * dy <= lim2;
-      }
+      const bool hit = jj < N && jj != a2 && hits(jj, a2);
       n_hit += __popc(__ballot_sync(0xffffffffu, hit));
     }
     if (lane == 0 && n_hit >= 2) work[atomicAdd(&work[N], 1)] = a2;
@@ -450,19 +460,15 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= n_work) break;
     const int a2 = work[slot < n_front ? slot : N - 1 - (slot - n_front)];
-    const float tx2 = truncf(px[a2]), ty2 = truncf(py[a2]);               // rect.x = int(position) (agent.py:303-304)
     const bool expl2 = ov[a2] == OV_EXPLOIT;                               // (fixed during the phase)
+    const double r = rad[a2];                                              // the hit agent is the focal agent of its LIDAR field
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int jj = j0 + lane;
-      bool hit = false;
-      if (jj < N && jj != a2) {
-        const float dx = truncf(px[jj]) - tx2, dy = truncf(py[jj]) - ty2;
-        hit = dx * dx + dy * dy <= lim2;
-      }
-      unsigned hits = __ballot_sync(0xffffffffu, hit);
-      while (hits) {                                                       // the agents a1 that hit a2, in group order
-        const int a1 = j0 + __ffs(hits) - 1;
-        hits &= hits - 1;
+      const bool hit = jj < N && jj != a2 && hits(jj, a2);                 // rect.x = int(position) (agent.py:303-304)
+      unsigned hitm = __ballot_sync(0xffffffffu, hit);
+      while (hitm) {                                                       // the agents a1 that hit a2, in group order
+        const int a1 = j0 + __ffs(hitm) - 1;
+        hitm &= hitm - 1;
         const bool expl1 = ov[a1] == OV_EXPLOIT;
         // ---- agent_agent_collision_proximity(a1, a2) (sims.py:421-468) ----
         bool do_coll = true;
@@ -483,8 +489,11 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
             double dist = 0.0;
             if (j < N && j != a2) {
               const float xj = px[j], yj = py[j];
+              // vicinity: distance between the agents' OWN centres (supcalc.distance); the field's distance: both
+              // centres with the focal radius (agent.py:504-509)
               const double n2 = base_distance_exact(cix, ciy, r, xj, yj);
-              if (n2 < 2.0 * r + 20.0) {                                            // :446-447
+              const double n2own = a.ag.radius ? base_distance_exact(cix, ciy, (double)rad[j], xj, yj) : n2;
+              if (n2own < 2.0 * r + 20.0) {                                         // :446-447
                 counted = !((xj == x2) && (yj == y2));
                 if (counted) {
                   dist = n2;
@@ -492,8 +501,8 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
                   if (!base_interval_fast(xj - x2, yj - y2, bf, o.s, o.e, vis)) {
                     rec = vis; o.d = n2;
                   } else {                                                          // inside a guard band: fp64
-                    const FocalExact fe = vf_focal_exact(x2, y2, (float)r, th2);
-                    rec = base_interval(fe, r, x2, y2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o, dist);
+                    rec = base_interval_cold(x2, y2, r, th2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o.s, o.e, dist);
+                    o.d = dist;
                   }
                 }
               }
@@ -551,6 +560,236 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
 }
 
 // ---------------------------------------------------------------------------------------
+// agent phase of one replicate by the whole CTA (N <= 64 agents, R <= 8192): the work is dealt to the THREADS by item,
+// not to warps by focal agent -- (focal, object) pairs, then (focal, social cue) occlusion scans, then (focal, word)
+// popcounts -- so every lane has work whatever N is (a warp per focal agent runs 49 objects as two ragged passes of 32
+// lanes and spends most of its instructions on per-focal bookkeeping).  Focal agents go in groups of kBlkGroup (the pair
+// table of a group lives in shared memory).
+// ---------------------------------------------------------------------------------------
+constexpr int kBlkMaxGroup = 32;    // focal agents per group (the pair table of a group lives in shared memory)
+constexpr int kBlkMaxN = 64;        // objects per focal agent fit one 64-bit mask
+
+struct BlkShared {
+  float *x, *y, *th;                // [N] frozen snapshot positions, headings
+  int *ov, *pid;                    // [N] snapshot override mode, patch id
+  float* rad;                       // [N] per-agent radius (or the engine-wide one)
+  BaseFast* bf;                     // [G] fast-path constants of the group's focal agents
+  double2* fovd;                    // [G] (fov0, fov1) in float64 (fp64 fallback)
+  int2* mask;                       // [G] stored bins kept by the FOV mask (mask_lo, mask_hi)
+  float* vr2;                       // [G] vision range squared
+  uint32_t* se;                     // [G][N] raw interval ends: (uint16)s | (uint16)e << 16
+  double* d;                        // [G][N] centre distance, float64 with the reference's operation sequence (:526-528):
+                                    // what the occlusion orders by (strict <, stable in list order)
+  unsigned char* cls;               // [G][N] 0 not recorded, 1 social cue, 2 occluder, 3 occluder (same-patch exploiter)
+  unsigned short* cues;             // [G * N] list of (focal slot << 8 | object) of the group's social cues
+  uint32_t* rows;                   // [G][W + 1] un-flipped fields
+  int* halves;                      // [N][2] set bins of the stored field's left / right half
+  int* ncue;                        // [1]
+};
+size_t base_block_smem_bytes(int N, int W, int G) {
+  size_t b = 6 * 4 * (size_t)N;                                        // x, y, th, ov, pid, rad
+  b = (b + 15) / 16 * 16 + sizeof(BaseFast) * G + 16 * G + 8 * G + 4 * G;   // bf, fovd, mask, vr2
+  b = (b + 15) / 16 * 16 + (8 + 4 + 1 + 2) * (size_t)G * N + 16;        // d, se, cls, cues
+  b = (b + 15) / 16 * 16 + 4 * (size_t)G * (W + 1) + 8 * (size_t)N + 16;
+  return b + 64;
+}
+// focal agents per group: equal groups, as few as fit `budget` bytes of shared memory per CTA
+int base_block_group(int N, int W, size_t budget) {
+  for (int n_groups = 1; n_groups <= N; ++n_groups) {
+    const int G = (N + n_groups - 1) / n_groups;
+    if (G <= kBlkMaxGroup && base_block_smem_bytes(N, W, G) <= budget) return G;
+  }
+  return 1;
+}
+__device__ __forceinline__ BlkShared base_block_carve(unsigned char* p, int N, int W, int G) {
+  auto up = [](unsigned char* q) { return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15)); };
+  BlkShared s;
+  s.x = reinterpret_cast<float*>(p); s.y = s.x + N; s.th = s.y + N;
+  s.ov = reinterpret_cast<int*>(s.th + N); s.pid = s.ov + N; s.rad = reinterpret_cast<float*>(s.pid + N);
+  p = up(reinterpret_cast<unsigned char*>(s.rad + N));
+  s.fovd = reinterpret_cast<double2*>(p); p += 16 * G;
+  s.bf = reinterpret_cast<BaseFast*>(p); p += sizeof(BaseFast) * G;
+  s.mask = reinterpret_cast<int2*>(p); p += 8 * G;
+  s.vr2 = reinterpret_cast<float*>(p); p += 4 * G;
+  p = up(p);
+  s.d = reinterpret_cast<double*>(p); p += 8 * (size_t)G * N;
+  s.se = reinterpret_cast<uint32_t*>(p); p += 4 * (size_t)G * N;
+  s.cues = reinterpret_cast<unsigned short*>(p); p += 2 * (size_t)G * N;
+  s.cls = p; p += (size_t)G * N;
+  p = up(p);
+  s.rows = reinterpret_cast<uint32_t*>(p); p += 4 * (size_t)G * (W + 1);
+  s.halves = reinterpret_cast<int*>(p); p += 8 * (size_t)N;
+  s.ncue = reinterpret_cast<int*>(p);
+  return s;
+}
+
+__device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b, unsigned char* smem_raw, unsigned step,
+                                                  const int G) {
+  const int N = a.N, R = a.R, W = a.W;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const size_t a0 = (size_t)b * N;
+  BlkShared sh = base_block_carve(smem_raw, N, W, G);
+  for (int i = tid; i < N; i += T) {
+    sh.x[i] = a.ag.snap_x[a0 + i]; sh.y[i] = a.ag.snap_y[a0 + i]; sh.th[i] = a.ag.theta[a0 + i];
+    sh.ov[i] = a.ag.snap_override[a0 + i]; sh.pid[i] = a.ag.patch_id[a0 + i];
+    sh.rad[i] = a.ag.radius ? a.ag.radius[a0 + i] : (float)a.radius;
+    sh.halves[2 * i] = 0; sh.halves[2 * i + 1] = 0;
+  }
+  const int h = R / 2;                                       // int(V_field_len / 2) (supcalc.py:86-88)
+  for (int g0 = 0; g0 < N; g0 += G) {
+    const int ng = min(G, N - g0);
+    __syncthreads();                                         // staging done / previous group's rows and table are free
+    // ---- per focal agent of the group: constants of the fast path, FOV, zeroed row ----
+    if (tid < ng) {
+      const int i = g0 + tid;
+      double fov0 = a.fov0, fov1 = a.fov1, vr = a.vision_range;
+      int mlo = a.mask_lo, mhi = a.mask_hi;
+      if (a.agent_geo) { const BaseAgentGeo q = a.agent_geo[a0 + i]; fov0 = q.fov0; fov1 = q.fov1; vr = q.vision_range; mlo = q.mask_lo; mhi = q.mask_hi; }
+      sh.bf[tid] = base_fast_consts(sh.th[i], a.ag.radius ? (double)sh.rad[i] : a.radius, fov0, fov1, R);
+      sh.fovd[tid] = make_double2(fov0, fov1);
+      sh.mask[tid] = make_int2(mlo, mhi);
+      sh.vr2[tid] = (float)(vr * vr);
+    }
+    for (int w = tid; w < ng * (W + 1); w += T) sh.rows[w] = 0u;
+    if (tid == 0) *sh.ncue = 0;
+    __syncthreads();
+    // ---- (focal, object) pairs: class and raw interval (agent.py:396-419, 497-556) ----
+    for (int it = tid; it < ng * N; it += T) {
+      const int gi = it / N, j = it - gi * N, i = g0 + gi;
+      const float xi = sh.x[i], yi = sh.y[i], xj = sh.x[j], yj = sh.y[j];
+      const double ri = a.ag.radius ? (double)sh.rad[i] : a.radius;
+      const float dxf = xj - xi, dyf = yj - yi;
+      const float d2 = fmaf(dxf, dxf, dyf * dyf);
+      // candidate test (agent.py:400) on the distance between the agents' OWN centres
+      bool in_range;
+      {
+        float dc2 = d2;
+        if (a.ag.radius) { const float dr = sh.rad[j] - sh.rad[i]; const float ex = dxf + dr, ey = dyf + dr; dc2 = fmaf(ex, ex, ey * ey); }
+        const float v2 = sh.vr2[gi];
+        if (dc2 < v2 * (1.0f - 2.0e-6f)) in_range = true;
+        else if (dc2 > v2 * (1.0f + 2.0e-6f)) in_range = false;
+        else {   // within rounding of the range: float64, the reference's operation sequence
+          const double rj = a.ag.radius ? (double)sh.rad[j] : a.radius;
+          const double vr = a.agent_geo ? a.agent_geo[a0 + i].vision_range : a.vision_range;
+          in_range = base_distance_exact(__dadd_rn((double)xi, ri), __dadd_rn((double)yi, ri), rj, xj, yj) <= vr;
+        }
+      }
+      const bool is_expl = (j != i) && (sh.ov[j] == OV_EXPLOIT);                     // :402-403
+      int cls = 0;
+      if (in_range) {
+        if (is_expl) {
+          const int pj = sh.pid[j];
+          if (a.patchwise_exclusion && pj == sh.pid[i]) cls = 3;                     // :406-409
+          else if (pj != -1) cls = 1;                                                // :410, :413
+        } else {
+          cls = 2;                                                                   // :405
+        }
+      }
+      if (!a.visual_exclusion && cls != 1) cls = 0;                                  // :415-419
+      uint32_t se = 0u;
+      double dist_ij = 0.0;
+      if (cls != 0) {
+        if ((xj == xi) && (yj == yi)) cls = 0;                                       // :502 (self, coincident positions)
+        else {
+          int s_, e_;
+          bool vis;
+          // (every pair's distance here, in parallel: the occlusion scans below only compare)
+          if (a.visual_exclusion)
+            dist_ij = base_distance_exact(__dadd_rn((double)xi, ri), __dadd_rn((double)yi, ri), ri, xj, yj);
+          if (base_interval_fast(dxf, dyf, sh.bf[gi], s_, e_, vis)) {                // inside a guard band: float64
+            double dist;
+            vis = base_interval_cold(xi, yi, ri, sh.th[i], xj, yj, sh.fovd[gi].x, sh.fovd[gi].y, R, a.lin_step, s_, e_, dist);
+            atomicAdd(&a.counters[2], 1ull);
+          }
+          if (!vis) cls = 0;
+          se = ((uint32_t)s_ & 0xffffu) | ((uint32_t)e_ << 16);
+        }
+      }
+      sh.se[it] = se; sh.d[it] = dist_ij; sh.cls[it] = (unsigned char)cls;
+      if (cls == 1) sh.cues[atomicAdd(sh.ncue, 1)] = (unsigned short)((gi << 8) | j);
+    }
+    __syncthreads();
+    // ---- (focal, social cue): occlusion by the strictly closer objects that meet the cue's interval, applied in
+    //      (distance, list order) order (agent.py:421-445), then the fill (agent.py:569-590) ----
+    const int n_cues = *sh.ncue;
+    for (int c = tid; c < n_cues; c += T) {
+      const int gi = sh.cues[c] >> 8, jc = sh.cues[c] & 0xff;
+      const uint32_t sec = sh.se[gi * N + jc];
+      const int fs = (int)(short)(sec & 0xffffu), fe_ = (int)(short)(sec >> 16);
+      int sx = fs, ex = fe_;
+      if (a.visual_exclusion) {
+        const double dc = sh.d[gi * N + jc];
+        unsigned long long rel = 0ull;                       // objects strictly closer than the cue that meet its raw interval
+        const unsigned char* cl = sh.cls + gi * N;
+        const uint32_t* sep = sh.se + gi * N;
+        const double* dp = sh.d + gi * N;
+#pragma unroll 2
+        for (int j = 0; j < N; ++j) {
+          const uint32_t so = sep[j];
+          const int os = (int)(short)(so & 0xffffu), oe = (int)(short)(so >> 16);
+          if ((cl[j] != 0) & (os <= fe_) & (oe >= fs) & (j != jc)) {
+            if (dp[j] < dc) rel |= 1ull << j;                // :430 strict, on the float64 values
+          }
+        }
+        while (rel) {                                        // usually none to three
+          int best = -1;
+          if ((rel & (rel - 1ull)) == 0ull) {
+            best = __ffsll((long long)rel) - 1;
+          } else {                                           // several: nearest first, ties in list order (stable sort, :424)
+            double bd = 0.0; int bk = 0;
+            for (unsigned long long m = rel; m; m &= m - 1ull) {
+              const int j = __ffsll((long long)m) - 1;
+              const double dj = dp[j];
+              const int cj = cl[j];
+              const int kj = ((cj == 1) ? 0 : (cj == 2 ? 1 : 2)) * N + j;
+              if (best < 0 || dj < bd || (dj == bd && kj < bk)) { best = j; bd = dj; bk = kj; }
+            }
+          }
+          rel &= ~(1ull << best);
+          const uint32_t so = sep[best];
+          const int os = (int)(short)(so & 0xffffu), oe = (int)(short)(so >> 16);
+          if (sx <= os && os <= ex) ex = os;                                          // :432-433
+          if (sx <= oe && oe <= ex) sx = oe;                                          // :435-436
+          if (os <= sx && oe >= ex) { sx = 0; ex = 0; }                               // :438-440
+        }
+      }
+      base_draw(sh.rows + (size_t)gi * (W + 1), R, sx, ex);
+    }
+    __syncthreads();
+    // ---- (focal, word): set bins of the stored field's halves (flip + FOV mask, agent.py:593-595; supcalc.py:86-91)
+    //      and the packed stored field ----
+    for (int it = tid; it < ng * W; it += T) {
+      const int gi = it / W, w = it - gi * W, i = g0 + gi;
+      const uint32_t* row = sh.rows + (size_t)gi * (W + 1);
+      const int mlo = sh.mask[gi].x, mhi = sh.mask[gi].y;
+      const int va = R - 1 - mhi, vb = R - mlo;              // kept bins in v coordinates [va, vb)
+      const uint32_t word = row[w];
+      if (word) {
+        auto cnt = [&](int lo_, int hi_) {
+          const int lo = max(lo_ - (w << 5), 0), hi = min(hi_ - (w << 5), 32);
+          if (hi <= lo) return 0;
+          const uint32_t m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+          return __popc(word & m);
+        };
+        const int nl = cnt(max(va, R - h), min(vb, R));      // stored[0:h]  <-> v[R-h:R]
+        const int nr = cnt(max(va, 0), min(vb, R - h));      // stored[h:]   <-> v[0:R-h]
+        if (nl) atomicAdd(&sh.halves[2 * i], nl);
+        if (nr) atomicAdd(&sh.halves[2 * i + 1], nr);
+      }
+      if (a.fields_out) {
+        uint32_t fw = flipped_word(row, 1, R, W, w);
+        const int lo = max(mlo - (w << 5), 0), hi = min(mhi + 1 - (w << 5), 32);
+        uint32_t m = 0u;
+        if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        a.fields_out[(a0 + i) * W + w] = fw & m;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += T) base_agent_decide(a, (long long)a0 + i, sh.halves[2 * i], sh.halves[2 * i + 1], step);
+}
+
+// ---------------------------------------------------------------------------------------
 // the fused step: ONE launch per time step, one CTA per replicate (sims.py:733-864 in its own order: collisions,
 // agent-patch interaction, Agent.update of every agent from one frozen snapshot).  The phases of a replicate are
 // sequential by construction and each of them is a chain of dependent latencies; with a CTA per replicate and all
@@ -558,42 +797,38 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
 // grids one after the other (each with its own launch and its own tail).
 // ---------------------------------------------------------------------------------------
 size_t base_step_smem_bytes(int N, int W, int warps) {
-  return warp_field_bytes(N, W) * warps + 7 * sizeof(int) * (size_t)N + 4 * sizeof(int) + 2 * sizeof(int) * (size_t)N;
+  return warp_field_bytes(N, W) * warps + 8 * sizeof(int) * (size_t)N + 4 * sizeof(int) + 2 * sizeof(int) * (size_t)N;
 }
 
-__global__ void __launch_bounds__(128, 8) base_step_kernel(const BaseKernelArgs a, unsigned phases, int collide) {
+__global__ void __launch_bounds__(128, 7) base_step_kernel(const __grid_constant__ BaseKernelArgs a, unsigned phases, int collide, int n_steps,
+                                                           int blk_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, N = a.N;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const size_t a0 = (size_t)b * N;
-  if (collide) {                                   // sims.py:736-783
-    base_collision_replicate(a, b, smem_raw);
-    __syncthreads();
-  }
-  if (phases & 1u) {                               // sims.py:790-858 (+ the frozen snapshot of the agent phase)
-    if (wib == 0) base_env_replicate(a, b, lane);
-  } else {                                         // agent phase alone: the snapshot is the current state
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      a.ag.snap_x[a0 + i] = a.ag.x[a0 + i];
-      a.ag.snap_y[a0 + i] = a.ag.y[a0 + i];
-      a.ag.snap_override[a0 + i] = a.ag.override_mode[a0 + i];
+  // Replicates never interact: the CTA runs ALL n_steps time steps of its replicate in this one launch (one barrier
+  // between steps instead of a launch; a single small run -- config 1 -- is bound by nothing else).
+  for (int s = 0; s < n_steps; ++s) {
+    const unsigned step = a.step + (unsigned)s;
+    if (s) __syncthreads();
+    if (collide) {                                   // sims.py:736-783
+      base_collision_replicate(a, b, smem_raw);
+      __syncthreads();
     }
+    if (phases & 1u) {                               // sims.py:790-858 (+ the frozen snapshot of the agent phase)
+      if (wib == 0) base_env_replicate(a, b, lane, step);
+    } else {                                         // agent phase alone: the snapshot is the current state
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        a.ag.snap_x[a0 + i] = a.ag.x[a0 + i];
+        a.ag.snap_y[a0 + i] = a.ag.y[a0 + i];
+        a.ag.snap_override[a0 + i] = a.ag.override_mode[a0 + i];
+      }
+    }
+    __syncthreads();
+    if (!(phases & 2u)) continue;
+    // sims.py:861: Agent.update of every agent from the frozen snapshot
+    base_agents_block(a, b, smem_raw, step, blk_group);   // the whole CTA, work dealt by item
   }
-  __syncthreads();
-  if (!(phases & 2u)) return;
-  // sims.py:861: the visual fields of all agents (a warp per focal agent), then -- one barrier later -- decision
-  // process, mode machine and kinematics with a thread per agent
-  const size_t per_warp = warp_field_bytes(N, a.W);
-  int* halves = reinterpret_cast<int*>(smem_raw + per_warp * wpb + 7 * sizeof(int) * (size_t)N + 4 * sizeof(int));
-  WarpField wf = warp_field_at(smem_raw + per_warp * wib, N);
-  for (int i = wib; i < N; i += wpb) {
-    int n_left = 0, n_right = 0;
-    base_agent_field(a, wf, (long long)a0 + i, lane, n_left, n_right);
-    if (lane == 0) { halves[2 * i] = n_left; halves[2 * i + 1] = n_right; }
-    __syncwarp();
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) base_agent_decide(a, (long long)a0 + i, halves[2 * i], halves[2 * i + 1]);
 }
 
 // opt-in shared memory per block of the current device, asked once per device (the attribute query costs more host time
@@ -613,7 +848,7 @@ static int base_smem_optin() {
 
 void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
   const int smem_max = base_smem_optin();
-  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 7 * sizeof(int) * (size_t)a.N + 4 * sizeof(int);
+  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 8 * sizeof(int) * (size_t)a.N + 4 * sizeof(int);
   int warps = 16;
   while (warps > 1 && (warps / 2 >= a.N || per_warp * warps + shared > (size_t)smem_max)) warps >>= 1;
   const size_t smem = per_warp * warps + shared;
@@ -649,8 +884,9 @@ __global__ void base_projection_kernel(const BaseProjArgs a) {   // one warp
         if (!base_interval_fast(a.ox[j] - a.fx, a.oy[j] - a.fy, bf, o.s, o.e, vis)) {
           rec = vis; o.d = dist;
         } else {                                                      // inside a guard band: fp64
-          const FocalExact fe = vf_focal_exact(a.fx, a.fy, (float)a.radius, a.ftheta);
-          rec = base_interval(fe, a.radius, a.fx, a.fy, a.ox[j], a.oy[j], a.fov0, a.fov1, a.R, a.lin_step, o, dist);
+          rec = base_interval_cold(a.fx, a.fy, a.radius, a.ftheta, a.ox[j], a.oy[j], a.fov0, a.fov1, a.R, a.lin_step, o.s,
+                                   o.e, dist);
+          o.d = dist;
         }
       }
     }
@@ -704,18 +940,22 @@ void launch_vf_dphi(const uint32_t* v, int R, int W, signed char* out, cudaStrea
 
 // One launch for the whole step when a CTA per replicate fills the GPU (sweeps); false: the caller launches the phases
 // as separate grids (few replicates of many agents: a warp per focal agent over the whole GPU).
-bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, int n_sms, cudaStream_t stream) {
+bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, int n_steps, int n_sms, cudaStream_t stream) {
   const int smem_max = base_smem_optin();
-  // 4 warps per replicate, 64 registers: 8 CTAs per SM, so the 1024 replicates of a sweep are resident all at once and the
+  // 4 warps per replicate, 72 registers: 7 CTAs per SM, so the 1024 replicates of a sweep are resident all at once and the
   // SMs interleave their (latency-bound, sequential) phase chains
   int warps = 4;
   while (warps > 1 && (warps / 2 >= a.N || base_step_smem_bytes(a.N, a.W, warps) > (size_t)smem_max)) warps >>= 1;
-  const size_t smem = base_step_smem_bytes(a.N, a.W, warps);
+  // (larger replicates, or resolutions beyond the packed interval ends: one grid per phase, a warp per focal agent)
+  if (a.N > kBlkMaxN || a.R > 8192) return false;
+  size_t smem = base_step_smem_bytes(a.N, a.W, warps);
+  // agent phase by the whole CTA: as few groups of focal agents as 7 resident CTAs per SM (1024 replicates on 148 SMs) leave room for
+  const int blk_group = base_block_group(a.N, a.W, (size_t)(224 * 1024) / 7 - 1024);
+  smem = std::max(smem, base_block_smem_bytes(a.N, a.W, blk_group));
   if (smem > (size_t)smem_max) return false;
-  if ((long long)a.B * warps < 4LL * n_sms && a.N > 64) return false;
   static SmemOptIn optin;
   optin.ensure(base_step_kernel, smem);
-  base_step_kernel<<<a.B, warps * 32, smem, stream>>>(a, phases, collide ? 1 : 0);
+  base_step_kernel<<<a.B, warps * 32, smem, stream>>>(a, phases, collide ? 1 : 0, n_steps, blk_group);
   return true;
 }
 

@@ -71,7 +71,7 @@ struct BaseKernelArgs {
                                // reset (the mode an agent is logged with, ifdb.py:197-206); summary metrics
 };
 
-bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, int n_sms, cudaStream_t stream);
+bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, int n_steps, int n_sms, cudaStream_t stream);
 void launch_base_env(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_agents(const BaseKernelArgs& a, cudaStream_t stream);
 void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream);

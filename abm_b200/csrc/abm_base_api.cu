@@ -1,4 +1,5 @@
 // C ABI of the BASE / collective-foraging engine (declared in include/abm_b200.h).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -203,6 +204,24 @@ int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const 
   return ABM_OK;
 }
 
+int abm_base_set_agent_radii(abm_base_engine_t* e, const double* radius, int n) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_set_agent_radii: null engine");
+  if (n == 0) { e->has_agent_radius = false; return ABM_OK; }   // back to the engine-wide radius of the config
+  if (!radius) return fail(ABM_E_INVALID, "abm_base_set_agent_radii: null argument");
+  if ((size_t)n != e->n_agents_total)
+    return fail(ABM_E_INVALID, "abm_base_set_agent_radii: n must be n_replicates * n_agents (or 0)");
+  std::vector<float> h((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    if (!(radius[i] > 0.0)) return fail(ABM_E_INVALID, "abm_base_set_agent_radii: radii must be > 0");
+    h[i] = (float)radius[i];
+  }
+  ABM_CUDA(cudaSetDevice(e->device));
+  if (!e->agent_radius.p) ABM_CUDA(e->agent_radius.alloc((size_t)n));
+  ABM_CUDA(cudaMemcpy(e->agent_radius.p, h.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+  e->has_agent_radius = true;
+  return ABM_OK;
+}
+
 int abm_base_set_agents(abm_base_engine_t* e, const abm_base_agents_t* src, int on_device, void* stream) {
   if (!e || !src) return fail(ABM_E_INVALID, "abm_base_set_agents: null argument");
   if (!e->agents_set && (!src->x || !src->y || !src->theta))
@@ -295,18 +314,28 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
     a.inject_dtheta = src;
   }
   const bool separate = getenv("ABM_BASE_SEPARATE_PHASES") != nullptr;   // measurement probes: the three-grid path
-  for (int s = 0; s < n_steps; ++s) {
+  const bool collide = (phases & ABM_BASE_PHASE_COLLISIONS) && c.collide_agents;
+  // ONE launch for all n_steps (a CTA per replicate runs the phases in the reference's order, step after step: replicates
+  // never interact) whenever the batch fills the GPU that way; otherwise one grid per phase and step
+  // (the decision process of a step reads the mode marks the SAME step's environment phase leaves: both in the launch)
+  // All n_steps in one launch only while every CTA has an SM to itself: with several replicates per SM, CTAs that drift
+  // apart in the step loop execute different phases of this (large) kernel at the same time and evict each other's
+  // code from the instruction cache (measured: 0.35 against 0.30 ms per step at 1024 x 50); a launch per step keeps
+  // the CTAs of an SM in the same phase.
+  const int per_launch = (getenv("ABM_BASE_ONE_STEP_PER_LAUNCH") || c.n_replicates > e->n_sms) ? 1 : n_steps;
+  int done = 0;
+  a.step = e->step;
+  while (!separate && done < n_steps && (phases & (ABM_BASE_PHASE_ENV | ABM_BASE_PHASE_AGENTS))) {
+    const int chunk = std::min(per_launch, n_steps - done);
     a.step = e->step;
-    const bool collide = (phases & ABM_BASE_PHASE_COLLISIONS) && c.collide_agents;
-    // one launch per step (a CTA per replicate runs the phases in the reference's order) whenever the batch fills the
-    // GPU that way; otherwise one grid per phase
-    if (!separate && (phases & (ABM_BASE_PHASE_ENV | ABM_BASE_PHASE_AGENTS)) &&
-        abm::launch_base_step(a, phases, collide, e->n_sms, st)) {
-      ++e->launches;
-      if (phases & ABM_BASE_PHASE_AGENTS) ++e->metric_steps;
-      ++e->step; ++e->steps;
-      continue;
-    }
+    if (!abm::launch_base_step(a, phases, collide, chunk, e->n_sms, st)) break;
+    ++e->launches;
+    if (phases & ABM_BASE_PHASE_AGENTS) e->metric_steps += (unsigned long long)chunk;
+    e->step += (unsigned)chunk; e->steps += (unsigned long long)chunk;
+    done += chunk;
+  }
+  for (int s = done; s < n_steps; ++s) {
+    a.step = e->step;
     if (collide) { abm::launch_base_collisions(a, st); ++e->launches; }
     if (phases & ABM_BASE_PHASE_ENV) { abm::launch_base_env(a, st); ++e->launches; }
     else {   // agent phase alone: the snapshot is the current state

@@ -141,6 +141,18 @@ __device__ __forceinline__ bool base_interval_fast(float dx, float dy, const Bas
   return flagged;
 }
 
+// The fp64 re-evaluation of a pair inside a guard band, out of line: ONE copy of the (large: software double-precision
+// sincos, acos, atan) code for every caller, and none of it inside the callers' hot loops.
+static __device__ __noinline__ bool base_interval_cold(float xi, float yi, double r, float theta, float xj, float yj,
+                                                       double fov0, double fov1, int R, double lin_step, int& s, int& e,
+                                                       double& dist) {
+  const FocalExact fe = vf_focal_exact(xi, yi, (float)r, theta);
+  ObjRec o; o.s = 0; o.e = 0; o.d = 0.0;
+  const bool rec = base_interval(fe, r, xi, yi, xj, yj, fov0, fov1, R, lin_step, o, dist);
+  s = o.s; e = o.e;
+  return rec;
+}
+
 // append this lane's object (if `rec`) in lane order; returns the new object count
 __device__ __forceinline__ int base_record(WarpField& wf, int M, bool rec, const ObjRec& o, int key, int lane) {
   const unsigned mask = __ballot_sync(0xffffffffu, rec);

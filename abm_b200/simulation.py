@@ -320,8 +320,9 @@ class Simulation(_RunOutputs):
         if pooling_time != 0:
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
         self.heterogen_agents = agent_behave_param_list is not None                # sims.py:170-173
+        agent_radii_list = None
         if self.heterogen_agents:
-            agent_radius, v_field_res = self._check_behave_params(
+            agent_radius, v_field_res, agent_radii_list = self._check_behave_params(
                 agent_behave_param_list, int(N), agent_radius, v_field_res,
                 (decision_params or DecisionParams()).Tau)
         self.agent_behave_param_list = agent_behave_param_list
@@ -362,6 +363,9 @@ class Simulation(_RunOutputs):
             self.engine.set_agent_geometry(
                 agent_fov=np.array([float(bp["agent_fov"]) for bp in agent_behave_param_list]),
                 vision_range=np.array([float(bp["vision_range"]) for bp in agent_behave_param_list]))
+            if agent_radii_list is not None:                                       # sims.py:502: the agent's own radius
+                self.engine.set_agent_radii(agent_radii_list)
+        self.agent_radii_list = agent_radii_list
         self.engine.set_params(**prm)
         self.agents, self.rescources = [], []
         self._a = self._p = self._f = None
@@ -372,24 +376,23 @@ class Simulation(_RunOutputs):
     @staticmethod
     def _check_behave_params(plist, N, agent_radius, v_field_res, tau):
         """agent_behave_param_list (sims.py:499-517, template: contrib/evolution.py:1-26): the decision / movement
-        entries, agent_consumption, agent_fov and vision_range may differ between agents; agent_radius, v_field_res,
+        entries, agent_consumption, agent_fov, vision_range and agent_radius may differ between agents; v_field_res,
         Tau and pooling must be the same for all agents (they are engine-wide) and then replace the constructor's
-        values like the reference does."""
+        values like the reference does.  Returns (engine-wide radius, resolution, per-agent radii or None)."""
         if len(plist) != N:
             raise ValueError("agent_behave_param_list must hold one dictionary per agent")
-        geo = []
-        for key, default in (("agent_radius", agent_radius), ("v_field_res", v_field_res)):
-            vals = {float(bp.get(key, default)) for bp in plist}
-            if len(vals) != 1:
-                raise NotImplementedError(f"agent_behave_param_list: '{key}' must be the same for all agents "
-                                          "(per-agent radius / resolution is not supported, SURVEY f4)")
-            geo.append(vals.pop())
+        res = {float(bp.get("v_field_res", v_field_res)) for bp in plist}
+        if len(res) != 1:
+            raise NotImplementedError("agent_behave_param_list: 'v_field_res' must be the same for all agents "
+                                      "(a per-agent resolution is not supported, SURVEY f4)")
         if any(int(bp.get("Tau", tau)) != int(tau) for bp in plist):
             raise NotImplementedError("agent_behave_param_list: 'Tau' must equal decision_params.Tau for all agents")
         if any(float(bp.get("pooling_time", 0)) != 0 for bp in plist):
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
-        radius = geo[0]
-        return (int(radius) if radius.is_integer() else radius), int(geo[1])
+        radii = np.array([float(bp.get("agent_radius", agent_radius)) for bp in plist])
+        radius = float(radii[0])
+        hetero = None if np.all(radii == radii[0]) else radii
+        return (int(radius) if radius.is_integer() else radius), int(res.pop()), hetero
 
     def create_agents(self):
         """sims.py:526-537: integer positions, heading ~ U(0, 2pi)."""

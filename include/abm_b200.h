@@ -331,9 +331,15 @@ int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets);
 /* Per-agent field geometry of heterogeneous agents (sims.py:499-517: every Agent gets its own FOV and vision_range):
  * fov0 / fov1 in radians (the reference's (-agent_fov * pi, agent_fov * pi)) and vision_range, n = n_replicates *
  * n_agents values each, replicate-major, host pointers.  n = 0 returns to the engine-wide values of the config.
- * Radius and resolution stay per engine. */
+ * The radius: abm_base_set_agent_radii; the resolution stays per engine. */
 int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const double* fov1,
                                 const double* vision_range, int n);
+/* Per-agent radius of heterogeneous agents (sims.py:502: Agent(radius = behave_params["agent_radius"])): n =
+ * n_replicates * n_agents values, replicate-major, host pointer; n = 0 returns to the config's agent_radius.  As in the
+ * reference the candidate test (agent.py:400), the patch membership (sims.py:45-56), the wall reflection
+ * (agent.py:347-394) and the collision circles use each agent's OWN radius, the projection the FOCAL agent's radius for
+ * both centres and for the projected size (agent.py:504-509, :529). */
+int abm_base_set_agent_radii(abm_base_engine_t* e, const double* radius, int n);
 int abm_base_set_agents(abm_base_engine_t* e, const abm_base_agents_t* src, int on_device, void* stream);
 int abm_base_get_agents(abm_base_engine_t* e, const abm_base_agents_t* dst, int on_device, void* stream);
 int abm_base_set_patches(abm_base_engine_t* e, const abm_base_patches_t* src, int on_device, void* stream);

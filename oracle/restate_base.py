@@ -258,15 +258,16 @@ def base_patch_phase(st, patches, cfg: BaseConfig, collided=(), agent_cfgs=None)
     agents in index order (group order, sims.py:805-844).  Returns the list of depleted slots
     (to be regenerated: sims.py:321-374, RNG-driven, not part of the parity contract)."""
     N = len(st["x"])
-    r = st["radius"]
+    ra = np.broadcast_to(np.asarray(st["radius"], np.float64), (N,))   # every agent's own radius (supcalc.distance :73-78)
     on_patch = np.zeros(N, bool)
     depleted = []
     for p in range(len(patches["x"])):
         pcx, pcy = patches["x"][p] + patches["radius"][p], patches["y"][p] + patches["radius"][p]
         members = [i for i in range(N)
-                   if np.sqrt((st["x"][i] + r - pcx) ** 2 + (st["y"][i] + r - pcy) ** 2) < patches["radius"][p]]   # :45-56
+                   if np.sqrt((st["x"][i] + ra[i] - pcx) ** 2 + (st["y"][i] + ra[i] - pcy) ** 2) < patches["radius"][p]]   # :45-56
         destroy = False
         for i in members:
+            r = ra[i]
             # bias_agent_towards_res_center (sims.py:544-552), relative_speed 0.02, no wrap
             dx, dy = pcx - (st["x"][i] + r), pcy - (st["y"][i] + r)
             cl = (np.arctan2(dy, dx) + st["theta"][i]) % (2 * np.pi)
@@ -340,15 +341,15 @@ def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool, agent_cfgs=None)
     rect.x / rect.y = int-truncated position (agent.py:303-304).  Returns the list
     `collided_agents` (with repetitions, as the reference builds it)."""
     N = len(st["x"])
-    r = st["radius"]
-    ix, iy = np.trunc(st["x"]), np.trunc(st["y"])
-    lim2 = (2 * (r + 2)) ** 2                                                     # sims.py:739-752
+    ra = np.broadcast_to(np.asarray(st["radius"], np.float64), (N,))              # own radii (heterogeneous agents)
+    # rect centres: int-truncated position + half the (integer) rect size (agent.py:303-304; pygame Rect)
+    ix, iy = np.trunc(st["x"]) + np.trunc(ra), np.trunc(st["y"]) + np.trunc(ra)
     collided = []
     R = cfg.R
     h = int(R / 2)
     for a1 in range(N):
-        partners = [a2 for a2 in range(N)
-                    if a2 != a1 and (ix[a1] - ix[a2]) ** 2 + (iy[a1] - iy[a2]) ** 2 <= lim2]
+        partners = [a2 for a2 in range(N)                                         # radii + 2 each, sims.py:739-752
+                    if a2 != a1 and (ix[a1] - ix[a2]) ** 2 + (iy[a1] - iy[a2]) ** 2 <= (ra[a1] + ra[a2] + 4) ** 2]
         if not partners:
             continue
         for a2 in partners:                                                       # agent_agent_collision_proximity :421-468
@@ -360,8 +361,9 @@ def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool, agent_cfgs=None)
             if st["override"][a2] != OV_EXPLOIT:
                 st["override"][a2] = OV_COLLIDE
                 st["mode"][a2] = MODE_COLLIDE
-            d = np.sqrt(((st["x"] + r) - (st["x"][a2] + r)) ** 2 + ((st["y"] + r) - (st["y"][a2] + r)) ** 2)
-            vicinity = [j for j in range(N) if d[j] < 2 * r + 20 and j != a2]     # :446-447
+            r = ra[a2]                                                            # the hit agent is the focal agent
+            d = np.sqrt(((st["x"] + ra) - (st["x"][a2] + r)) ** 2 + ((st["y"] + ra) - (st["y"][a2] + r)) ** 2)
+            vicinity = [j for j in range(N) if d[j] < 2 * r + 20 and j != a2]     # :446-447 (own centres)
             full = (-np.pi, np.pi)
             src = base_source_data(a2, st["x"], st["y"], r, st["theta"], vicinity, [], cfg, fov=full)
             if cfg.visual_exclusion:
@@ -369,8 +371,10 @@ def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool, agent_cfgs=None)
             field = base_fill(src, cfg, fov=full)                                 # :449 (binary part)
             last = [j for j in vicinity if not (st["x"][j] == st["x"][a2] and st["y"][j] == st["y"][a2])]
             amp = 1.0
-            if last:
-                amp = 1 - d[last[-1]] / cfg.vision_range                          # leaked loop variable, agent.py:590
+            if last:                      # leaked loop variable of projection_field (agent.py:526-528, :590): the distance
+                j = last[-1]              # with BOTH centres formed with the focal radius
+                dl = np.sqrt(((st["x"][j] + r) - (st["x"][a2] + r)) ** 2 + ((st["y"][j] + r) - (st["y"][a2] + r)) ** 2)
+                amp = 1 - dl / cfg.vision_range
             left = amp * field[0:h].sum() / h
             right = amp * field[h:].sum() / (R - h)
             D = np.sign(left - right)

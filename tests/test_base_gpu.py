@@ -262,7 +262,7 @@ def test_full_loop_runs_and_forages(built_lib):
     assert a["collected"].sum() > 0
     assert not np.array_equal(a["x"][0], a["x"][1])
     c = eng.counters()
-    assert c["steps"] == 300 and c["launches"] == 300 and c["regeneration_failed"] == 0   # ONE fused launch per step
+    assert c["steps"] == 300 and c["launches"] == 1 and c["regeneration_failed"] == 0   # ONE launch for all 300 steps
     eng.close()
 
 
@@ -404,7 +404,7 @@ def test_full_loop_with_collisions(built_lib):
         assert np.isfinite(a["x"]).all() and np.isfinite(a["theta"]).all()
         d = np.sqrt((a["x"][:, :, None] - a["x"][:, None, :]) ** 2 + (a["y"][:, :, None] - a["y"][:, None, :]) ** 2)
         overlaps[collide] = int(((d < 12.0).sum() - B * N) // 2)
-        assert eng.counters()["launches"] == 200                            # one fused launch per step either way
+        assert eng.counters()["launches"] == 1                              # one launch for the whole run either way
         eng.close()
     print("deeply overlapping pairs without / with collision avoidance:", overlaps[False], overlaps[True])
     assert overlaps[True] <= overlaps[False]
@@ -488,7 +488,7 @@ def test_fused_step_equals_separate_phases(built_lib, monkeypatch):
         eng.step(150)
         res[separate] = (eng.get_agents(), eng.get_patches(), eng.fields(), eng.counters())
         eng.close()
-    assert res[False][3]["launches"] == 150 and res[True][3]["launches"] == 450
+    assert res[False][3]["launches"] == 1 and res[True][3]["launches"] == 450
     assert res[False][3]["patches_regenerated"] == res[True][3]["patches_regenerated"] > 0
     for k, v in res[False][0].items():
         assert np.array_equal(v, res[True][0][k]), k
@@ -562,4 +562,75 @@ def test_patch_regeneration_matches_oracle(built_lib, border_overlap):
         assert np.array_equal(gp["id"][b], pa["id"])
     assert n_regen >= 4 and cnt["patches_regenerated"] == n_regen and cnt["regeneration_failed"] == 0
     eng.inject_regeneration(None)
+    eng.close()
+
+
+@pytest.mark.parametrize("case", load_base_hetero_cases("base_hetero_radius_golden.npz"),
+                         ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_agent_phase_matches_reference_fixture_heterogeneous_radii(built_lib, case):
+    """agent_radius of agent_behave_param_list (sims.py:502) in the kernels (abm_base_set_agent_radii): every agent's own
+    radius in the candidate distance and at the walls, the FOCAL radius for both centres and the projected size
+    (agent.py:504-509, 529) -- against the fixture the unmodified reference's constructor path produced."""
+    cfg, st = case["cfg"], case["st"]
+    N = len(case["dth"])
+    eng = _engine_for(cfg, 1, N)
+    geo = ("agent_fov", "vision_range", "agent_radius")
+    eng.set_params(exp_theta_min=cfg.exp_theta_min, exp_theta_max=cfg.exp_theta_max, reloc_theta_max=cfg.reloc_theta_max,
+                   **{k: v[None] for k, v in case["agent_params"].items() if k not in geo})
+    eng.set_agent_geometry(agent_fov=case["agent_params"]["agent_fov"][None],
+                           vision_range=case["agent_params"]["vision_range"][None])
+    eng.set_agent_radii(np.asarray(st["radius"])[None])
+    _upload(eng, st)
+    eng.step(1, inject_dtheta=case["dth"], phases=PHASE_AGENTS)
+    assert np.array_equal(rs.pack_bits(eng.fields()[0]), case["fields"])          # bit-exact stored fields
+    _compare_agents(eng.get_agents(), case["out"])
+    eng.set_agent_radii(None)                                                     # back to one radius: different fields
+    _upload(eng, st)
+    eng.step(1, inject_dtheta=case["dth"], phases=PHASE_AGENTS)
+    assert not np.array_equal(rs.pack_bits(eng.fields()[0]), case["fields"])
+    eng.close()
+
+
+@pytest.mark.parametrize("ghost,vis_excl", [(True, False), (False, True)])
+def test_env_and_collision_phases_with_per_agent_radii(built_lib, ghost, vis_excl):
+    """The agents' own radii in the patch membership / bias / teleport (sims.py:45-56, 544-552, 820-821) and in the
+    collision circles, the vicinity test and the LIDAR field of the hit agent (sims.py:421-468, 739-752) against the
+    oracle (the pair detection restates pygame's documented collide_circle: parity unpinned)."""
+    rng = np.random.default_rng(55)
+    B, N, P, W = 3, 40, 3, 300.0
+    cfg = rb.BaseConfig(R=1200, width=W, height=W, visual_exclusion=vis_excl, teleport_exploit=True, exp_vel_max=2.0)
+    radii = rng.choice([6.0, 10.0, 14.0], (B, N))
+    states, patches = [], []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 0, 0, 1], N); st["mode"] = np.where(st["override"] == 1, 1, 0)
+        st["radius"] = radii[b].copy()
+        states.append(st)
+        patches.append(dict(x=rng.integers(40, 250, P).astype(float), y=rng.integers(40, 250, P).astype(float),
+                            radius=np.full(P, 35.0), left=np.full(P, 100.0), quality=np.full(P, 0.5),
+                            id=np.arange(1, P + 1)))
+    eng = _engine_for(cfg, B, N, P, collide_agents=True, ghost_mode=ghost, regenerate_patches=False)
+    eng.set_agent_radii(radii)
+    stacked = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    eng.set_agents(x=stacked["x"], y=stacked["y"], theta=stacked["theta"], vel=stacked["vel"], w=stacked["w"],
+                   u=stacked["u"], collected=stacked["collected"], collected_before=stacked["collected_before"],
+                   env_status=stacked["env_status"], override_mode=stacked["override"], mode=stacked["mode"],
+                   patch_id=stacked["patch_id"], novelty=stacked["novelty"])
+    eng.set_patches(**{k: np.stack([p_[k] for p_ in patches]) for k in patches[0]})
+    eng.step(1, phases=4 | PHASE_ENV)                       # collisions, then the environment phase (sims.py order)
+    got = eng.get_agents()
+    n_coll = 0
+    for b in range(B):
+        st = {k: (np.array(v, dtype=float) if k in ("theta", "vel", "collected", "collected_before", "x", "y") else np.array(v))
+              for k, v in states[b].items()}
+        pa = {k: np.array(v, dtype=float if k != "id" else int) for k, v in patches[b].items()}
+        collided = rb.base_collision_phase(st, cfg, ghost)
+        n_coll += len(set(collided))
+        rb.base_patch_phase(st, pa, cfg, collided=set(collided))
+        for k, g in dict(x="x", y="y", theta="theta", vel="vel").items():
+            np.testing.assert_allclose(got[g][b], st[k], rtol=RTOL, atol=1e-5, err_msg=k)
+        assert np.array_equal(got["override_mode"][b], st["override"].astype(int))
+        assert np.array_equal(got["env_status"][b], st["env_status"])
+        assert np.array_equal(got["patch_id"][b], st["patch_id"])
+    assert n_coll > 6
     eng.close()

@@ -84,8 +84,8 @@ def test_tunable_requires_values():
 
 
 def test_simulation_facade_rejects_per_agent_geometry():
-    """agent_behave_param_list (sims.py:499-517): per-agent decision parameters, FOV and vision range are supported,
-    per-agent radius / resolution / Tau are refused loudly, before any engine is created."""
+    """agent_behave_param_list (sims.py:499-517): per-agent decision parameters, FOV, vision range and radius are
+    supported, per-agent resolution / Tau are refused loudly, before any engine is created."""
     from abm_b200.simulation import Simulation
     base = dict(S_wu=0, T_w=0.5, Eps_w=0, g_w=0.085, B_w=0, w_max=1, Tau=10, S_uw=0, T_u=0.5, Eps_u=3, g_u=0.085,
                 B_u=0, u_max=1, F_N=2, F_R=1, exp_vel_max=3, exp_stop_ratio=0.15, agent_radius=10, v_field_res=1200,
