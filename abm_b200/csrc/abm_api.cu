@@ -733,15 +733,15 @@ int abm_vf_metrics(abm_engine_t* e, float* out, int on_device, void* stream) {
   ABM_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int B = e->cfg.n_replicates;
-  if (sizeof(float2) * (size_t)e->cfg.n_agents > 48 * 1024)
-    return fail(ABM_E_INVALID, "abm_vf_metrics: more than 6144 agents per replicate are not supported");
-  if (!e->metrics.p) ABM_CUDA(e->metrics.alloc(4 * (size_t)B));
+  if ((sizeof(float2) + sizeof(int)) * (size_t)e->cfg.n_agents > 48 * 1024)
+    return fail(ABM_E_INVALID, "abm_vf_metrics: more than 4096 agents per replicate are not supported");
+  if (!e->metrics.p) ABM_CUDA(e->metrics.alloc(5 * (size_t)B));
   float* dst = on_device ? out : e->metrics.p;
-  abm::launch_vf_metrics(e->rec[e->cur].p, e->theta.p, B, e->cfg.n_agents, e->cfg.boundary == ABM_BOUNDARY_INFINITE ? 1 : 0,
-                         e->cfg.width, e->cfg.height, dst, st);
+  abm::launch_vf_metrics(e->rec[e->cur].p, e->theta.p, (e->sort_enabled && !e->perm_identity) ? e->perm.p : nullptr, B,
+                         e->cfg.n_agents, e->cfg.boundary == ABM_BOUNDARY_INFINITE ? 1 : 0, e->cfg.width, e->cfg.height, dst, st);
   ABM_CUDA(cudaGetLastError());
   if (!on_device) {
-    ABM_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    ABM_CUDA(cudaMemcpyAsync(out, dst, sizeof(float) * 5 * (size_t)B, cudaMemcpyDeviceToHost, st));
     ABM_CUDA(cudaStreamSynchronize(st));
   }
   return ABM_OK;

@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(128, 7) base_step_kernel(const __grid_constant
                                                            int blk_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, N = a.N;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const size_t a0 = (size_t)b * N;
   // Replicates never interact: the CTA runs ALL n_steps time steps of its replicate in this one launch (one barrier
   // between steps instead of a launch; a single small run -- config 1 -- is bound by nothing else).

@@ -180,10 +180,10 @@ void launch_unpack_state4(const float4* rec, const float* theta, const float* ve
 void launch_unpack_records(const float4* rec, const int* perm, int N, float* x, float* y, long long n,
                            cudaStream_t stream);
 
-// summary metrics (abm_metrics.cu): out[b * 4 + {0: polarization, 1: mean inter-individual distance, 2: mean nearest-
-// neighbour distance, 3: collision flag}]
-void launch_vf_metrics(const float4* rec, const float* theta, int B, int N, int torus, float width, float height, float* out,
-                       cudaStream_t stream);
+// summary metrics (abm_metrics.cu): out[b * 5 + {0: polarization, 1: mean inter-individual distance, 2: mean nearest-
+// neighbour distance, 3: collision flag, 4: fraction of colliding agents}]; perm (nullable): internal slot -> caller's index
+void launch_vf_metrics(const float4* rec, const float* theta, const int* perm, int B, int N, int torus, float width,
+                       float height, float* out, cudaStream_t stream);
 
 // spatial re-ordering (abm_vf_sort.cu)
 size_t vf_sort_temp_bytes(int B, int N);

@@ -286,12 +286,14 @@ class VFEngine:
     def metrics(self) -> dict:
         """Per-replicate summary metrics of the current state, computed on the device (the
         quantities of abm/loader/data_loader.py): dict of (B,) float32 arrays `polarization`, `mean_iid`,
-        `mean_nn_dist`, `collision` (1.0 where some pair is closer than 2 * radius)."""
-        out = np.empty((self.B, 4), np.float32)
+        `mean_nn_dist`, `collision` (1.0 where some pair is closer than 2 * radius), `colliding_agents` (fraction of
+        the agents with a higher-indexed agent closer than 2 * radius: the per-agent indicator whose time average is
+        the loader's "aacoll")."""
+        out = np.empty((self.B, 5), np.float32)
         _lib.check(self._lib.abm_vf_metrics(self._h, C.c_void_p(out.ctypes.data), 0, C.c_void_p(_current_stream())),
                    "abm_vf_metrics")
         return dict(polarization=out[:, 0].copy(), mean_iid=out[:, 1].copy(), mean_nn_dist=out[:, 2].copy(),
-                    collision=out[:, 3].copy())
+                    collision=out[:, 3].copy(), colliding_agents=out[:, 4].copy())
 
     def slow_entries(self) -> tuple[int, int]:
         """(pairs off the symmetric kernel's fast path so far, number of its launches)."""

@@ -353,6 +353,95 @@ def swarm_arm(VFEngine, local_rank, rank, world, dist, steps=20):
     return out
 
 
+def other_configs_arm(VFEngine, local_rank, peaks):
+    """The other BASELINE configs on one GPU (SURVEY 8d lists all five; the headline line is configs[3], the swarm arm
+    configs[4]): configs[0] foraging N = 10, 3 patches, T = 1000; configs[1] visual flocking N = 100, one run;
+    configs[2] foraging sweep 1024 replicates x 50 agents with occlusion and collisions -- device-resident steps timed
+    with CUDA events, plus for configs[2] an oracle check of the agent phase and its issue roofline."""
+    import torch
+    from abm_b200 import BaseEngine
+    from oracle import restate_base as rb
+    out = {}
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(n); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    prm = dict(Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5,
+               reloc_theta_max=1.8, exp_stop_ratio=0.175)
+    # ---- configs[2]: figExp3BN50PatchyCollOcc-like sweep (DEC_EPSW one value per replicate) ----
+    B, N, P, W = 1024, 50, 3, 500.0
+    rng = np.random.default_rng(3)
+    eng = BaseEngine(B, N, P, resolution=R, width=W, height=W, visual_exclusion=True, collide_agents=True,
+                     ghost_mode=False, seed=9, keep_fields=True, device=local_rank)
+    eng.set_params(Eps_w=np.tile(np.array([0, .25, .5, .75, 1, 2, 5, 3], np.float64), B // 8), **prm)
+    eng.set_agents(x=rng.integers(20, 520, (B, N)), y=rng.integers(20, 520, (B, N)), theta=rng.uniform(0, 2 * np.pi, (B, N)))
+    eng.set_patches(x=rng.integers(60, 400, (B, P)), y=rng.integers(60, 400, (B, P)), radius=np.full((B, P), 30.0),
+                    left=np.full((B, P), 200.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
+    eng.step(100)
+    l0 = eng.counters()["launches"]
+    ms = timed(eng.step, 200)
+    launches = eng.counters()["launches"] - l0
+    st = eng.get_agents()
+    # parity of the agent phase from the state the timed run ended in: two replicates against the oracle
+    dth = np.asarray(rng.uniform(-0.5, 0.5, (B, N)), np.float32)
+    eng.step(1, inject_dtheta=dth, phases=2)
+    got, fields = eng.get_agents(), eng.fields()
+    bits, rel = 0, 0.0
+    for b in (0, B - 1):
+        cfg = rb.BaseConfig(R=R, width=W, height=W, visual_exclusion=True, Eps_w=float([0, .25, .5, .75, 1, 2, 5, 3][b % 8]), **prm)
+        nov = ((st["novelty"][b][:, None] >> np.arange(cfg.Tau, dtype=np.uint32)) & 1).astype(float)
+        s0 = dict(x=st["x"][b].astype(float), y=st["y"][b].astype(float), theta=st["theta"][b].astype(float),
+                  vel=st["vel"][b].astype(float), radius=10.0, w=st["w"][b].astype(float), u=st["u"][b].astype(float),
+                  novelty=nov, env_status=st["env_status"][b], override=st["override_mode"][b], mode=st["mode"][b],
+                  patch_id=st["patch_id"][b], collected=st["collected"][b].astype(float),
+                  collected_before=st["collected_before"][b].astype(float))
+        ref = rb.base_step_frozen(s0, cfg, dth[b].astype(np.float64))
+        bits += int((fields[b] != ref["fields"]).sum())
+        for k, g in dict(x="x", y="y", theta="theta", vel="vel", w="w", u="u").items():
+            rel = max(rel, float(np.max(np.abs(got[g][b] - ref[k]) / np.maximum(np.abs(ref[k]), 1e-3))))
+    n_expl = float((st["override_mode"] == 1).sum()) / B
+    ops = 48.0 * B * N * (N - 1) + 334.0 * B * N                      # VERDICT r1: the C3 roofline formula
+    ops_occl = 8.0 * B * N * n_expl * (N - 1) / 2.0                   # OPS_OCCL estimate: every cue against half the others
+    props = torch.cuda.get_device_properties(local_rank)
+    peak = props.multi_processor_count * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    out["c3"] = {"workload": "BASELINE configs[2]: foraging sweep, 1024 replicates x 50 agents, 3 patches, R=1200, occlusion + "
+                             "collisions, one DEC_EPSW per replicate", "ms_per_step": ms, "agent_steps_per_s": B * N / ms * 1e3,
+                 "gpu_launches_per_step": launches / 200.0, "kernel": "abm::base_step_kernel (collisions, environment and "
+                 "agent phases of a replicate in one CTA)",
+                 "roofline": {"bound": "fp32 issue", "achieved": (ops + ops_occl) / (ms * 1e-3) / 1e12, "peak": peak / 1e12,
+                              "unit": "Tlaneop/s", "frac": (ops + ops_occl) / (ms * 1e-3) / peak, "ops_pairs_agents": ops,
+                              "ops_occlusion_estimate": ops_occl, "exploiters_per_replicate": n_expl},
+                 "parity": {"replicates": [0, B - 1], "agents": 2 * N, "field_bits_differ": bits, "max_rel_state": rel,
+                            "ok": bool(bits == 0 and rel < 1e-5), "oracle": "oracle/restate_base.base_step_frozen"}}
+    eng.close()
+    # ---- configs[0]: one foraging run, N = 10, 3 patches, T = 1000 (every step of the run inside ONE launch) ----
+    eng = BaseEngine(1, 10, 3, resolution=R, width=W, height=W, visual_exclusion=True, seed=4, device=local_rank)
+    eng.set_params(Eps_w=2.0, **prm)
+    eng.set_agents(x=rng.integers(20, 520, (1, 10)), y=rng.integers(20, 520, (1, 10)), theta=rng.uniform(0, 2 * np.pi, (1, 10)))
+    eng.set_patches(x=rng.integers(60, 400, (1, 3)), y=rng.integers(60, 400, (1, 3)), radius=np.full((1, 3), 30.0),
+                    left=np.full((1, 3), 200.0), quality=np.full((1, 3), 0.25), id=np.arange(3)[None])
+    eng.step(50)
+    l0 = eng.counters()["launches"]
+    ms = timed(eng.step, 1000)
+    out["c1"] = {"workload": "BASELINE configs[0]: foraging, N=10, 3 patches, R=1200, T=1000", "us_per_step": ms * 1e3,
+                 "agent_steps_per_s": 10 / ms * 1e3, "gpu_launches_for_1000_steps": eng.counters()["launches"] - l0}
+    eng.close()
+    # ---- configs[1]: one visual-flocking run of 100 agents ----
+    N2 = 100
+    x, y, th, v = synthetic_state(1, N2)
+    W2 = arena_side(N2)
+    e2 = VFEngine(1, N2, resolution=R, width=W2, height=W2, device=local_rank)
+    e2.set_params(**PARAMS); e2.set_state(x, y, th, v, RADIUS); e2.step(20)
+    ms = timed(e2.step, 2000)
+    out["c2"] = {"workload": "BASELINE configs[1]: visual flocking, N=100, one run, R=1200", "us_per_step": ms * 1e3,
+                 "agent_steps_per_s": N2 / ms * 1e3, "kernel": e2.last_kernel()}
+    e2.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -515,6 +604,9 @@ def main():
     swarm = None
     if os.environ.get("ABM_BENCH_SWARM", "1") != "0":
         swarm = swarm_arm(VFEngine, local_rank, rank, world, dist)
+    others = None
+    if world == 1 and os.environ.get("ABM_BENCH_OTHER_CONFIGS", "1") != "0":
+        others = other_configs_arm(VFEngine, local_rank, measured_peaks()[0])
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -565,6 +657,7 @@ def main():
             "wall_s_timed_region": t_wall,
             "parity": par,
             "swarm": swarm,
+            "other_configs": others,
         }
         if not args.no_cpu_baseline and world == 1:
             os.environ.setdefault("OMP_NUM_THREADS", "1")

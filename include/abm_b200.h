@@ -202,10 +202,12 @@ int abm_vf_slow_entries(abm_engine_t* e, uint64_t* entries, uint64_t* sym_launch
 
 /* Summary metrics of the current state, per replicate (the quantities abm/loader/data_loader.py computes
  * offline from logged trajectories: calculate_polarization :1761-1836, calculate_interindividual_distance :1367-1460,
- * calculate_mean_NN_dist :1461-1488, calculate_collision_time :1838-1869).  out[b * 4 + k], k = 0: polarization
+ * calculate_mean_NN_dist :1461-1488, calculate_collision_time :1838-1869).  out[b * 5 + k], k = 0: polarization
  * |sum_i (cos theta_i, sin theta_i)| / N; 1: mean distance over pairs i < j (minimal image with BOUNDARY infinite);
  * 2: mean over agents of the distance to the nearest other agent; 3: 1.0 if any pair is closer than 2 * radius (the
- * reference's agent-agent collision criterion; its time average is the "aacoll" fraction), else 0.0. */
+ * reference's agent-agent collision criterion), else 0.0; 4: the fraction of agents i that have an agent j > i (caller's
+ * order) at 0 < distance < 2 * radius -- the loader's own per-agent indicator (it works on the upper triangle of the
+ * distance matrix); its mean over time is an experiment's "aacoll" value. */
 int abm_vf_metrics(abm_engine_t* e, float* out, int on_device, void* stream);
 
 int abm_synchronize(abm_engine_t* e, void* stream);

@@ -185,6 +185,36 @@ def load_base():
     return supcalc, agent, decision_params, movement_params
 
 
+def load_loader():
+    """The real reference's offline analysis module (abm/loader/data_loader.py: ExperimentLoader with
+    calculate_polarization, calculate_interindividual_distance, calculate_mean_NN_dist, calculate_collision_time,
+    calculate_search_efficiency, calculate_relocation_time); plotting / zarr back ends stubbed."""
+    install()
+    import matplotlib
+    if "matplotlib.pyplot" not in sys.modules:
+        sys.modules["matplotlib.pyplot"] = MagicMock()
+        matplotlib.pyplot = sys.modules["matplotlib.pyplot"]
+    from abm.loader import data_loader
+    return data_loader
+
+
+def make_loader(tmp_dir, agent_summary, env):
+    """An ExperimentLoader of the real reference around in-memory summary arrays, without touching a data folder: what
+    its calculate_* methods read.  ``agent_summary``: arrays of shape (batches, agents, T); the loader's convention is
+    (batches, *varying parameter dims, agents, T) and some of its means need at least one parameter dimension, so a
+    singleton one is inserted: results come back as (batches, 1, ...)."""
+    import numpy as np
+    dl = load_loader()
+    ld = object.__new__(dl.ExperimentLoader)
+    ld.experiment_path = str(tmp_dir)
+    os.makedirs(os.path.join(str(tmp_dir), "summary"), exist_ok=True)
+    agent_summary = {k: np.asarray(v)[:, None] for k, v in agent_summary.items()}
+    ld.varying_params, ld.agent_summary, ld.env = {"SWEPT": [0]}, agent_summary, env
+    ld.num_batches = next(iter(agent_summary.values())).shape[0]
+    ld.iid_matrix, ld.t_end, ld.undersample = None, None, 1
+    return ld
+
+
 def make_vf_agents(x, y, theta, vel, radius, *, R, fov_ratio=1.0, width, height, window_pad=30,
                    boundary="walls", params=None, alp0=None, bet0=None, v0=None,
                    limit_movement=False, max_vel=3.0, max_th=0.1):
