@@ -149,6 +149,8 @@ struct abm_engine {
 
 namespace {
 
+inline bool sym_ok_forced_off(const char* force) { return force && strcmp(force, "onesided") == 0; }
+
 int copy_in(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
   ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   return ABM_OK;
@@ -603,6 +605,30 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     *e->slow_host = 0;
   }
   const bool tiled = e->tile_count != e->cfg.n_agents;
+  // A batch so small that a step is shorter than a launch (one run of 100 agents): all n_steps in ONE cooperative launch
+  // of the warp kernel, a grid-wide barrier between steps.  Needs the plain path: no peers, no culling lists, no re-sort.
+  if (n_steps > 1 && small_grid && !sym_ok_forced_off(force) && !cull && !tiled && e->n_peers == 0 &&
+      !getenv("ABM_VF_ONE_STEP_PER_LAUNCH")) {
+    if (!e->ticket.p) ABM_CUDA(e->ticket.alloc(1));
+    ABM_CUDA(cudaMemsetAsync(e->ticket.p, 0, sizeof(uint32_t), st));
+    a.theta = e->theta.p; a.vel = e->vel.p;
+    a.perm = (e->sort_enabled && !e->perm_identity) ? e->perm.p : nullptr;
+    a.rec_in = e->rec[e->cur].p; a.rec_out = e->rec[e->cur ^ 1].p;
+    a.n_peers = 0; a.step_no = e->steps_done; a.xflags = nullptr;
+    a.tile_bbox = nullptr; a.tile_cull2 = nullptr; a.bbox_out = nullptr;
+    a.step_ticket = e->ticket.p;
+    if (abm::launch_vf_step_warp_multi(a, uniform_r, n_steps, st)) {
+      ABM_CUDA(cudaMemsetAsync(e->ticket.p, 0, sizeof(uint32_t), st));
+      e->cur ^= (n_steps & 1);
+      e->steps_done += (uint32_t)n_steps; e->steps_since_sort += n_steps;
+      ++e->launches;
+      e->bbox_valid[0] = e->bbox_valid[1] = false; e->host_synced = false;
+      e->last_kernel = "abm::vf_step_warp_kernel";
+      ABM_CUDA(cudaGetLastError());
+      return ABM_OK;
+    }
+    cudaGetLastError();   // the grid cannot be co-resident: one launch per step below
+  }
   for (int s = 0; s < n_steps; ++s) {
     // (the symmetric kernel wants NO spatial order: its blocks should all hold the same mix of near and far pairs)
     // ---- kernel of this step ----

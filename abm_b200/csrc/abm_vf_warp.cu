@@ -27,7 +27,8 @@
 
 namespace abm {
 
-constexpr int kWarpThreads = 256;
+constexpr int kWarpThreads = 256;      // default threads per CTA
+constexpr int kWarpMaxThreads = 512;   // F = 8 on a grid that would otherwise be a partial wave
 constexpr int kWarpMaxFocal = 8;     // focal agents per CTA <= warps per CTA (a warp per focal agent in the epilogue)
 constexpr int kChunk = 128;          // records per pass of half the CTA (= kWarpTile)
 constexpr int kWarpQueue = 1024;     // pairs off the fast path waiting for the CTA's slow pass
@@ -140,8 +141,12 @@ __device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const float4 f,
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + 4u), "r"(__funnelshift_l(mask, 0u, ps)));
 }
 
-template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R>
-__global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a, const int F) {
+// MULTI: n_steps time steps in ONE (cooperative) launch, a grid-wide barrier between steps -- for runs so small that a
+// step is shorter than a kernel launch (one run of 100 agents: BASELINE configs[1]); the record tables swap roles
+// every step.  Without peers, culling lists or re-sorting (abm_api.cu checks).
+template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R, bool MULTI>
+__global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a, const int F,
+                                                                       const int n_steps_arg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared sh;
   sh.focal = reinterpret_cast<float4*>(smem_raw);
@@ -153,17 +158,23 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x;                                // 256 or 512 threads
   const int per_rep = (a.tile_count + F - 1) / F;
   const int b = blockIdx.x / per_rep;
   const int li0 = (blockIdx.x - b * per_rep) * F;          // first focal agent of the CTA inside this engine's tile
   const int nf = min(F, a.tile_count - li0);               // focal agents of this CTA
-  const float4* rep_in = a.rec_in + (size_t)b * a.N;
   const int R = a.R, W = a.W;
   const int row_words = W + 3;
   int* tile_list = sh.tile_list;
   int* fbox = sh.fbox;
+  const int n_steps = MULTI ? n_steps_arg : 1;
+#pragma unroll 1
+  for (int step_i = 0; step_i < n_steps; ++step_i) {
+  const float4* rec_in_t = (MULTI && (step_i & 1)) ? a.rec_out : a.rec_in;
+  float4* rec_out_t = (MULTI && (step_i & 1)) ? const_cast<float4*>(a.rec_in) : a.rec_out;
+  const float4* rep_in = rec_in_t + (size_t)b * a.N;
 
-  for (int w = tid; w < row_words * F; w += kWarpThreads) sh.rows[w] = 0u;
+  for (int w = tid; w < row_words * F; w += T) sh.rows[w] = 0u;
   if (a.n_peers > 0 && tid <= a.n_peers) {   // fused tile exchange: wait for every rank's previous step (thread r: rank r)
     const uint32_t* fl = a.xflags + tid;
     uint32_t v;
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
   if (use_list) {
     const float4* bb = a.tile_bbox + (size_t)b * n_tiles;
     const float* c2 = a.tile_cull2 + (size_t)b * n_tiles;
-    for (int t = tid; t < n_tiles; t += kWarpThreads) {
+    for (int t = tid; t < n_tiles; t += T) {
       const float4 q = __ldcg(bb + t);
       float gx = fmaxf(0.0f, fmaxf(q.x - fx1, fx0 - q.z));
       float gy = fmaxf(0.0f, fmaxf(q.y - fy1, fy0 - q.w));
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
     const int cpt_sh = tile_sh - 7;                          // chunks per tile = 2^cpt_sh
     const int n_chunks = n_stage << cpt_sh;
     const int off = tid & (kChunk - 1);
-    for (int c = tid >> 7; c < n_chunks; c += kWarpThreads / kChunk) {
+    for (int c = tid >> 7; c < n_chunks; c += T / kChunk) {
       const int st = c >> cpt_sh;
       const int j = ((((use_list ? tile_list[st] : st) << cpt_sh) + (c & ((1 << cpt_sh) - 1))) << 7) + off;
       if (j >= a.N) continue;
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
     // ---- slow pass: the queued pairs, one per thread ----
     __syncthreads();
     const int nq = min(tile_list[kMaxTileList + 1], kWarpQueue);
-    for (int q = tid; q < nq; q += kWarpThreads) {
+    for (int q = tid; q < nq; q += T) {
       const uint32_t ent = sh.queue[q];
       const int f = (int)(ent >> 24), j = (int)(ent & 0xffffffu);
       warp_pair_slow<TORUS>(a, sh.focal[f], sh.theta[f], rows_s + 4u * (uint32_t)(row_words * f) + 4u, __ldcg(rep_in + j),
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
       if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
       else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
       const float4 rec_new = make_float4((float)nx, (float)ny, me.z, rep_in[i].w);
-      a.rec_out[gi] = rec_new;
+      rec_out_t[gi] = rec_new;
       if (a.n_peers > 0) {                                            // NVLink peer stores (fused tile exchange)
         for (int p = 0; p < a.n_peers; ++p) a.peer_rec_out[p][gi] = rec_new;
       }
@@ -348,6 +359,20 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
     }
   }
 
+  if (MULTI) {   // grid-wide barrier: every CTA's records of this step are in place before anybody reads them
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(a.step_ticket, 1u);
+      const uint32_t target = (uint32_t)(step_i + 1) * gridDim.x;
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.step_ticket) : "memory");
+      } while (v < target);
+    }
+    __syncthreads();
+    continue;
+  }
   // ---- fused tile exchange: the LAST CTA of the launch closes the step for this rank ----
   if (a.step_ticket == nullptr) return;
   __syncthreads();
@@ -365,7 +390,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
     const int t0 = cyc ? a.tile_phase : a.tile_begin >> tile_sh;
     const int t1 = cyc ? n_tiles : (a.tile_begin + a.tile_count + tile_sz - 1) >> tile_sh;
     const int dt = cyc ? a.tile_cycle : 1;
-    for (int t = t0 + warp * dt; t < t1; t += (kWarpThreads / 32) * dt) {
+    for (int t = t0 + warp * dt; t < t1; t += (T / 32) * dt) {
       float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
       for (int j = (t << tile_sh) + lane; j < min(a.N, (t + 1) << tile_sh); j += 32) {
         const float4 v = __ldcg(a.rec_out + j);
@@ -391,13 +416,23 @@ __global__ void __launch_bounds__(kWarpThreads, 4) vf_step_warp_kernel(const __g
     for (int p = 0; p < a.n_peers; ++p)
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[p] + a.my_rank), "r"(done) : "memory");
   }
+  }   // step loop (one pass unless MULTI)
 }
 
-// focal agents per CTA: as many as keep >= 16 CTAs per SM in the grid
+// focal agents per CTA: as many as keep >= 8 CTAs per SM (two waves of the 4 resident ones) in the grid -- measured on
+// an eighth of the 65 536-agent swarm (scratch/c5_tile_probe.py): F = 4 1.64, F = 2 1.87, F = 8 1.84 ms summed over the
+// eight tiles; the whole swarm: F = 8 1.15, F = 4 1.28 ms
 int vf_warp_focal_per_cta(long long focal_total, int n_sms) {
   int F = kWarpMaxFocal;
-  while (F > 1 && focal_total / F < 16LL * n_sms) F >>= 1;
+  while (F > 1 && focal_total / F < 8LL * n_sms) F >>= 1;
   return F;
+}
+
+static int warp_threads_choice(const VFKernelArgs& a, int F) {
+  const char* env = getenv("ABM_VF_WARP_THREADS");            // measurement probes only
+  if (env) return atoi(env) == 512 ? 512 : 256;
+  (void)a; (void)F;
+  return kWarpThreads;
 }
 
 template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R>
@@ -405,8 +440,9 @@ static void launch_warp_variant(const VFKernelArgs& a, int F, cudaStream_t strea
   const int per_rep = (a.tile_count + F - 1) / F;
   const size_t smem = vf_warp_smem_bytes(a.W, F);
   static SmemOptIn optin;
-  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R>, smem);
-  vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R><<<(unsigned)((size_t)a.B * per_rep), kWarpThreads, smem, stream>>>(a, F);
+  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R, false>, smem);
+  vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R, false>
+      <<<(unsigned)((size_t)a.B * per_rep), warp_threads_choice(a, F), smem, stream>>>(a, F, 1);
 }
 template <bool TORUS, bool CULL>
 static void launch_warp_fr(const VFKernelArgs& a, int F, bool uniform_r, cudaStream_t stream) {
@@ -414,12 +450,45 @@ static void launch_warp_fr(const VFKernelArgs& a, int F, bool uniform_r, cudaStr
   else { if (uniform_r) launch_warp_variant<TORUS, CULL, false, true>(a, F, stream); else launch_warp_variant<TORUS, CULL, false, false>(a, F, stream); }
 }
 
-void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaStream_t stream) {
+static int warp_focal_choice(const VFKernelArgs& a) {
   const char* env = getenv("ABM_VF_WARP_FOCAL");              // measurement probes only
   int F = env ? atoi(env) : vf_warp_focal_per_cta((long long)a.B * a.tile_count, a.n_sms);
   if (F != 1 && F != 2 && F != 4 && F != 8) F = 1;
+  return F;
+}
+
+void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaStream_t stream) {
+  const int F = warp_focal_choice(a);
   if (a.boundary == 1) { if (cull) launch_warp_fr<true, true>(a, F, uniform_r, stream); else launch_warp_fr<true, false>(a, F, uniform_r, stream); }
   else { if (cull) launch_warp_fr<false, true>(a, F, uniform_r, stream); else launch_warp_fr<false, false>(a, F, uniform_r, stream); }
+}
+
+// n_steps steps in one cooperative launch (no culling, no peers); false: the grid cannot be co-resident -- nothing launched
+template <bool TORUS, bool FULL_FOV, bool UNIFORM_R>
+static bool launch_warp_multi_variant(const VFKernelArgs& a, int F, int n_steps, cudaStream_t stream) {
+  auto kernel = vf_step_warp_kernel<TORUS, false, FULL_FOV, UNIFORM_R, true>;
+  const int per_rep = (a.tile_count + F - 1) / F;
+  const unsigned grid = (unsigned)((size_t)a.B * per_rep);
+  const size_t smem = vf_warp_smem_bytes(a.W, F);
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) optin.ensure(kernel, smem);
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpThreads, smem) != cudaSuccess) return false;
+  if ((long long)per_sm * a.n_sms < (long long)grid) return false;
+  VFKernelArgs args = a;
+  int f = F, n = n_steps;
+  void* params[3] = {&args, &f, &n};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kWarpThreads), params, smem, stream) ==
+         cudaSuccess;
+}
+bool launch_vf_step_warp_multi(const VFKernelArgs& a, bool uniform_r, int n_steps, cudaStream_t stream) {
+  const int F = warp_focal_choice(a);
+  if (a.boundary == 1) {
+    if (a.full_fov) return uniform_r ? launch_warp_multi_variant<true, true, true>(a, F, n_steps, stream) : launch_warp_multi_variant<true, true, false>(a, F, n_steps, stream);
+    return uniform_r ? launch_warp_multi_variant<true, false, true>(a, F, n_steps, stream) : launch_warp_multi_variant<true, false, false>(a, F, n_steps, stream);
+  }
+  if (a.full_fov) return uniform_r ? launch_warp_multi_variant<false, true, true>(a, F, n_steps, stream) : launch_warp_multi_variant<false, true, false>(a, F, n_steps, stream);
+  return uniform_r ? launch_warp_multi_variant<false, false, true>(a, F, n_steps, stream) : launch_warp_multi_variant<false, false, false>(a, F, n_steps, stream);
 }
 
 }  // namespace abm

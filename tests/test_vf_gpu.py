@@ -721,3 +721,44 @@ def test_engines_on_two_devices_in_one_process(built_lib):
             res.append(eng.get_state()); eng.close()
     for k in ("x", "y", "theta", "vel"):
         assert np.array_equal(res[0][k], res[1][k])
+
+
+@pytest.mark.parametrize("B,N,boundary,fovr,hetero", [(1, 100, "walls", 1.0, False), (3, 40, "infinite", 1.0, True),
+                                                      (2, 64, "walls", 0.5, False)])
+def test_small_runs_step_inside_one_launch(built_lib, monkeypatch, B, N, boundary, fovr, hetero):
+    """A run so small that a step is shorter than a kernel launch (BASELINE configs[1]: one run of 100 agents) takes all
+    n_steps in ONE cooperative launch with a grid-wide barrier between steps: the same trajectory, bit for bit, as a
+    launch per step, and the last step's fields / terms are the ones kept."""
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(40 + N)
+    W = 900.0 if N == 100 else 400.0
+    x, y, th, v = _random_scene(rng, B, N, W)
+    rad = rng.choice([6.0, 10.0], (B, N)).astype(np.float32) if hetero else 10.0
+    fov = (-fovr * np.pi, fovr * np.pi)
+    R = int(1200 / fovr)
+    res = {}
+    for per_step in (False, True):
+        if per_step:
+            monkeypatch.setenv("ABM_VF_ONE_STEP_PER_LAUNCH", "1")
+        else:
+            monkeypatch.delenv("ABM_VF_ONE_STEP_PER_LAUNCH", raising=False)
+        eng = VFEngine(B, N, resolution=R, fov=fov, boundary=boundary, width=W, height=W, keep_fields=True, keep_terms=True)
+        eng.set_params(); eng.set_state(x, y, th, v, rad)
+        eng.step(37)
+        assert eng.last_kernel() == "abm::vf_step_warp_kernel"
+        assert eng.counters()["launches"] == (37 if per_step else 1)
+        eng.step(2)                                   # an even and an odd count: both table parities
+        res[per_step] = (eng.get_state(), eng.fields_packed(), eng.terms())
+        eng.close()
+    for k in ("x", "y", "theta", "vel"):
+        assert np.array_equal(res[False][0][k], res[True][0][k]), k
+    assert np.array_equal(res[False][1], res[True][1]) and np.array_equal(res[False][2], res[True][2])
+    # and the last step against the oracle, from the state before it
+    eng = VFEngine(B, N, resolution=R, fov=fov, boundary=boundary, width=W, height=W)
+    eng.set_params(); eng.set_state(x, y, th, v, rad); eng.step(38)
+    st = eng.get_state(); eng.close()
+    cfg = rs.VFConfig(R=R, fov=fov, boundary=boundary, width=W, height=W)
+    for b in range(B):
+        ref = rs.vf_step_frozen(st["x"][b], st["y"][b], st["theta"][b], st["vel"][b], rad if not hetero else rad[b], cfg)
+        assert np.array_equal(rs.unpack_bits(res[False][1][b], R), ref["rows"][:, ::-1])
+        _check_state(res[False][0], ref, b)
