@@ -130,7 +130,8 @@ struct abm_engine {
   cudaEvent_t slow_event = nullptr;
   bool slow_pending = false;
   unsigned long long slow_seen = 0, sym_launches = 0, slow_req_launch = 0, slow_seen_launch = 0;
-  int onesided_steps_left = 0;
+  unsigned long long kstat[4] = {0, 0, 0, 0};   // launches: symmetric two-word / three-word, one-sided, warp
+  int wide_steps_left = 0;   // steps the symmetric kernel still runs with its three-word fast path (crowded scene)
   size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   int n_sms = 148;
   // spatial ordering (ABM_VF_SPATIAL_SORT)
@@ -148,6 +149,8 @@ struct abm_engine {
 };
 
 namespace {
+
+constexpr double kWideThreshold = 0.04;   // share of the unordered pairs off the two-word fast path
 
 inline bool sym_ok_forced_off(const char* force) { return force && strcmp(force, "onesided") == 0; }
 
@@ -533,7 +536,13 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     const double tau_k_sym = 2.0e-7 * (double)g.R + 1.0e-5;
     a.sym_tie32 = exact ? (uint32_t)(tau_k_sym * 4294967296.0) : 0u;
     a.sym_seam32 = exact ? (uint32_t)(6.0e-6 / ABM_TWO_PI_D * 4294967296.0) : 0u;   // 6e-6 rad either side of +-pi
-    a.sym_thr_h = exact ? 0.5f - g.tau_h_abs - 17.5f * g.tau_h_rel : 3.0e38f;
+    a.sym_thr_h = exact ? 0.5f - g.tau_h_abs - 33.5f * g.tau_h_rel : 3.0e38f;   // fast paths: h <= 32 (three-word), 16
+    {
+      const double S = (double)g.R / ABM_TWO_PI_D;
+      a.sym_qs_max = (float)(S * std::min(0.18, std::tan(32.49 / S)));    // four-term series
+      a.sym_qs_max2 = (float)(S * std::min(0.12, std::tan(16.49 / S)));   // three-term series
+      a.warp_qs_max = (float)(S * std::min(0.18, std::tan(16.49 / S)));
+    }
     a.full_fov = (e->cfg.fov_px0 == 0 && e->cfg.fov_px1 == g.R - 1) ? 1 : 0;
   }
   a.width = e->cfg.width; a.height = e->cfg.height;
@@ -588,7 +597,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     double t_cta;
     if (sym_ok) {
       const int Np = (a.N + 63) / 64 * 64;
-      const size_t smem = abm::vf_sym_smem_bytes(Np, a.W);
+      const size_t smem = abm::vf_sym_smem_bytes(Np, a.W, false);
       const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
       const double waves = std::ceil((double)a.B / ((double)e->n_sms * resident));
       t_cta = waves * (45.0 + 0.05 * Np + 1.6e-4 * (double)Np * Np);
@@ -624,6 +633,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       ++e->launches;
       e->bbox_valid[0] = e->bbox_valid[1] = false; e->host_synced = false;
       e->last_kernel = "abm::vf_step_warp_kernel";
+      ++e->kstat[3];
       ABM_CUDA(cudaGetLastError());
       return ABM_OK;
     }
@@ -638,10 +648,17 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       const unsigned long long n_launch = e->slow_req_launch - e->slow_seen_launch;
       e->slow_seen = *e->slow_host; e->slow_seen_launch = e->slow_req_launch;
       const double pairs = 0.5 * (double)a.B * (double)a.N * (double)(a.N - 1);   // unordered; one queue entry each
-      if (n_launch && (double)entries > 0.095 * pairs * (double)n_launch) e->onesided_steps_left = 64;   // crowded
+      // crowded scene (many intervals wider than 32 bins): the next 64 steps take the three-word fast path (measured on
+      // discs of decreasing radius, scratch/dense_probe.py); then a two-word step looks again
+      if (n_launch && (double)entries > kWideThreshold * pairs * (double)n_launch) e->wide_steps_left = 64;
     }
     bool use_sym = sym_ok && !small_grid;
-    if (adaptive && e->onesided_steps_left > 0) { use_sym = false; --e->onesided_steps_left; }
+    bool wide3 = false;
+    if (use_sym) {
+      const char* wenv = getenv("ABM_VF_SYM_WIDE");                        // measurement probes / tests: 0 | 1
+      if (wenv) wide3 = atoi(wenv) != 0;
+      else if (adaptive && e->wide_steps_left > 0) { wide3 = true; --e->wide_steps_left; }
+    }
     if (e->sort_enabled && !use_sym && !(small_grid && !cull) && (e->needs_sort || (e->cfg.resort_every > 0 && !tiled &&
                                                            e->steps_since_sort >= e->cfg.resort_every))) {
       int rc = resort_engine(e, st);
@@ -701,13 +718,14 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       }
     }
     e->host_synced = false;
-    if (use_sym) abm::launch_vf_step_sym(a, st);
+    if (use_sym) abm::launch_vf_step_sym(a, wide3, st);
     else if (use_warp) abm::launch_vf_step_warp(a, cull, uniform_r, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
     if (e->n_peers > 0 && !fused_close) { abm::launch_vf_publish(a, st); ++e->launches; }
     e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : (use_warp ? "abm::vf_step_warp_kernel" : "abm::vf_step_kernel");
+    ++e->kstat[use_sym ? (wide3 ? 1 : 0) : (use_warp ? 3 : 2)];
     if (use_sym) ++e->sym_launches;
-    if (adaptive && use_sym && !e->slow_pending) {
+    if (adaptive && use_sym && !wide3 && !e->slow_pending) {   // (the share of slow pairs is defined by the two-word path)
       e->slow_req_launch = e->sym_launches;
       ABM_CUDA(cudaMemcpyAsync(e->slow_host, e->counters.p + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       ABM_CUDA(cudaEventRecord(e->slow_event, st));
@@ -785,6 +803,12 @@ int abm_vf_slow_entries(abm_engine_t* e, uint64_t* entries, uint64_t* sym_launch
 }
 
 const char* abm_vf_last_kernel(abm_engine_t* e) { return e ? e->last_kernel : ""; }
+
+int abm_vf_kernel_stats(abm_engine_t* e, uint64_t stats[4]) {
+  if (!e || !stats) return fail(ABM_E_INVALID, "abm_vf_kernel_stats: null argument");
+  for (int k = 0; k < 4; ++k) stats[k] = e->kstat[k];
+  return ABM_OK;
+}
 
 int abm_vf_record_table(abm_engine_t* e, void** dev_ptr, int* bytes_per_agent) {
   if (!e || !dev_ptr) return fail(ABM_E_INVALID, "abm_vf_record_table: null argument");

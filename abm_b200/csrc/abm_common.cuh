@@ -69,6 +69,10 @@ struct VFKernelArgs {
   // symmetric kernel (abm_vf_sym.cu): wider k guard band (the closed angle is a difference of two rounded bin
   // angles), absolute h guard band of the fast path (h <= 16), the common radius
   float sym_thr_h, sym_radius;
+  // fast-path limits on qs = (r / d) * R / 2pi: the four-term arctangent series is exact to the guard band up to q = 0.18,
+  // and the interval must fit three (symmetric kernel: h <= 32) or two (warp kernel: h <= 16) row words; also catches
+  // NaN / inf (coincident centres) and the sign change of the truncated series at large q
+  float sym_qs_max, sym_qs_max2, warp_qs_max;   // three-word / two-word fast path of the symmetric kernel, warp kernel
   uint32_t sym_tie32, sym_seam32; // guard bands of the binary-angle bin index, in 2^-32 bins / 2^-32 turns
   uint32_t opaque_zero;           // always 0: OR-ed into loop constants so that ptxas keeps them in registers
   int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible
@@ -133,9 +137,9 @@ constexpr int kMaxTileList = 1024;   // tiles per replicate the culling list can
                                      // N <= 131072 at 128)
 size_t vf_step_smem_bytes(int threads, int W);
 // symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
-size_t vf_sym_smem_bytes(int Np, int W);
+size_t vf_sym_smem_bytes(int Np, int W, bool wide3);
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
-void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream);
+void launch_vf_step_sym(const VFKernelArgs& a, bool wide3, cudaStream_t stream);
 int vf_step_threads(int tile_count, int n_replicates, int n_sms);
 // warp-per-focal-agent kernel (abm_vf_warp.cu): one large sparse swarm and its tiles
 void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaStream_t stream);

@@ -40,7 +40,8 @@ constexpr int kSymQueueCap = 3072;   // fp64 queue entries of a CTA, split evenl
 // re-materialise them with a MOV in every step).
 struct SymConsts {
   float rS;            // radius * R/2pi
-  float c3s, c5s;      // -1/(3 S^2), 1/(5 S^4), S = R/2pi: atan(q) S = qs (1 + c3s qs^2 + c5s qs^4)
+  float c3s, c5s, c7s; // -1/(3 S^2), 1/(5 S^4), -1/(7 S^6), S = R/2pi: atan(q) S = qs (1 + c3s qs^2 + c5s qs^4 + c7s qs^6)
+  float qs_max;        // fast-path limit on qs (VFKernelArgs::sym_qs_max)
   float a6;            // leading coefficient of the bearing polynomial
   int scratch_pos;     // padded position of the scratch word
   unsigned long long half64;   // 2^31: rounding constant of the bin index, addend of its IMAD.WIDE
@@ -52,7 +53,7 @@ __device__ __forceinline__ void or_if(uint32_t& acc, bool p, uint32_t m) {
 
 struct SymShared {
   float4* ag;          // [Np] (x, y, heading constant, the same + half a turn); padding agents beyond N are far away
-  uint32_t* rows;      // [W + 3][Np] padded rows + one scratch word (draws of slow directions land there)
+  uint32_t* rows;      // [W + 5][Np] padded rows (W + 2 words) + three scratch words (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions waiting for fp64 (focal << 16 | object, k << 16 | h), per warp
   uint32_t* warpq;     // [warps][kSymWarpQ] per-warp queue of pairs with directions off the fast path
   int* qcount;         // [0]: fp64 entries (statistics), [1]: pairs off the fast path (statistics), [2 + w]: fp64 entries
@@ -241,13 +242,13 @@ __device__ __forceinline__ void sym_push_round(const VFKernelArgs& a, const SymS
 // (already redirected to the scratch word when the direction is off the fast path), the 2h-ones mask.
 struct SymStep {
   int ps_i, ps_j;
-  uint32_t mask;
+  uint32_t mask, mask_hi;   // 2h ones: bits 0..31 / 32..63
   bool slow_i, slow_j;
 };
 
 // Pure arithmetic (no shared-memory access): the compiler interleaves two of these.
 // BOTH: evaluate both directions; otherwise only the lane's own.
-template <bool TORUS, bool FULL_FOV, int RC, bool BOTH>
+template <bool TORUS, bool FULL_FOV, int RC, bool BOTH, bool WIDE3>
 __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, float xi, float yi, uint32_t hc_i,
                                             const SymConsts& c) {
   using K = PairK<RC>;
@@ -260,17 +261,28 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   }
   const float d2 = fmaf(dx, dx, dy * dy);
   // ---- half width h = floor(atan(r/d) * R/2pi) (vf_supcalc.py:96-99, :114-117), shared by both directions.
-  //      Three-term series in q = r/d (exact to fp32 for h <= 16, i.e. q < 0.09); larger q -> slow path. ----
+  //      Four-term series in q = r/d (truncation error 3e-6 bins at h = 32, q = 0.17, R = 1200); larger q -> slow path.
+  //      (With the fast path ending at h = 16 -- intervals of two words -- the pairs between 56 and 112 px, three
+  //      quarters of all wide ones, went through the out-of-line slow path: 29 % of the kernel's warp samples.) ----
   const float rs = rsqrt_approx(d2);
   const float qs = rs * c.rS;                                // q * R/2pi
   const float zs = qs * qs;
-  float p = fmaf(zs, c.c5s, c.c3s);
+  float p;
+  if (WIDE3) { p = fmaf(zs, c.c7s, c.c5s); p = fmaf(p, zs, c.c3s); }   // four terms: exact to the guard band up to q = 0.18
+  else p = fmaf(zs, c.c5s, c.c3s);                                      // three: up to q = 0.12
   p = fmaf(p, zs, 1.0f);
   const float y = fmaf(qs, p, -0.5f);
   const float yr = y + kMagic;
   const uint32_t hraw = __float_as_uint(yr);                 // h + kMagicBits
-  const bool slow_h = !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h) | wrap_tie;   // also d2 == 0 (NaN)
-  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask) : "r"(2u * hraw - 2u * (uint32_t)kMagicBits));   // 2h ones
+  // (the limit is on qs, not on y: beyond q = 0.18 / 0.12 the truncated series is inexact, and the four-term one finally
+  // changes sign; at R = 1200 the two-word limit h <= 16 is q < 0.087 and the three-term series only grows: the
+  // benchmark's variant keeps its immediate compare)
+  const bool too_wide = (!WIDE3 && RC == 1200) ? !(y < 16.5f) : !(qs < c.qs_max);   // also d2 == 0 (inf / NaN)
+  const bool slow_h = too_wide | (fabsf(y - (yr - kMagic)) > a.sym_thr_h) | wrap_tie;
+  const uint32_t w2 = 2u * hraw - 2u * (uint32_t)kMagicBits; // 2h
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask) : "r"(w2));                                      // min(2h, 32) ones
+  r.mask_hi = 0u;
+  if (WIDE3) asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask_hi) : "r"((uint32_t)max((int)w2 - 32, 0)));   // the ones beyond 32
   const int bh = 32 + kMagicBits - (int)hraw;                // ps = bin index + 32 - h
   // ---- bearing (shared), bin index of both directions ----
   const uint32_t nb = sym_bearing_bits(dx, dy, c.a6);
@@ -301,21 +313,30 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
 // at the rate of a plain shared store: one wavefront per conflict-free warp instruction, measured on B200 --
 // scratch/red_bench.cu).  Nobody has to own a row, draws need no ordering, and the second word is written
 // unconditionally (its mask is usually 0): that is cheaper than a predicate.
-__device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps, uint32_t m) {
+template <bool WIDE3>
+__device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps, uint32_t m, uint32_t mh) {
   uint32_t wa;   // row + (ps >> 5) * stride_b as ONE multiply-add (with a power-of-two immediate stride the compiler
                  // would otherwise build it from a shift, a mask and an add)
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(wa) : "r"((uint32_t)(ps >> 5)), "r"(stride_b), "r"(row));
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa), "r"(__funnelshift_l(0u, m, ps)));
-  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + stride_b), "r"(__funnelshift_l(m, 0u, ps)));
+  if (WIDE3) {   // up to 64 bins: three words
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + stride_b), "r"(__funnelshift_l(m, mh, ps)));
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + 2u * stride_b), "r"(__funnelshift_l(mh, 0u, ps)));
+  } else {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + stride_b), "r"(__funnelshift_l(m, 0u, ps)));
+  }
 }
 
-size_t vf_sym_smem_bytes(int Np, int W) {
-  return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + 3) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
+size_t vf_sym_smem_bytes(int Np, int W, bool wide3) {
+  return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + (wide3 ? 5 : 3)) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
          sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + 96;   // counters: 2 + one per warp (<= 16)
 }
 
 // NPC > 0: compile-time padded replicate size (row stride becomes an immediate), 0: the run-time argument.
-template <bool TORUS, bool FULL_FOV, int RC, int NPC>
+// WIDE3: the fast path takes intervals of up to 64 bins (three row words, four-term series) instead of 32 -- a few more
+// instructions on every pair, but in a crowded scene the pairs between 56 and 112 px stay out of the slow path (the
+// engine switches on the measured share of slow pairs, abm_api.cu).
+template <bool TORUS, bool FULL_FOV, int RC, int NPC, bool WIDE3>
 __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_constant__ VFKernelArgs a, int Np_arg) {
   const int Np = NPC ? NPC : Np_arg;
   using K = PairK<RC>;
@@ -323,7 +344,8 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   SymShared sh;
   sh.ag = reinterpret_cast<float4*>(smem_raw);
   sh.rows = reinterpret_cast<uint32_t*>(sh.ag + Np);
-  sh.queue = sh.rows + (size_t)(a.W + 3) * Np;
+  constexpr int kRowExtra = WIDE3 ? 5 : 3;   // padding (2) + scratch words for redirected draws (1 per word of a draw)
+  sh.queue = sh.rows + (size_t)(a.W + kRowExtra) * Np;
   sh.warpq = sh.queue + 2 * kSymQueueCap;
   sh.qcount = reinterpret_cast<int*>(sh.warpq + kSymWarpQ * (Np / 64));
   sh.Np = Np; sh.N = a.N;
@@ -352,7 +374,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     }
     sh.ag[j] = v;
   }
-  for (int w = tid; w < (a.W + 3) * Np; w += T) sh.rows[w] = 0u;
+  for (int w = tid; w < (a.W + kRowExtra) * Np; w += T) sh.rows[w] = 0u;
   if (tid < 18) sh.qcount[tid] = 0;
   __syncthreads();
 
@@ -360,6 +382,9 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   SymConsts c;
   c.rS = a.sym_radius * S;
   c.c3s = -1.0f / (3.0f * S * S);
+  c.qs_max = 0.f; c.c7s = 0.f;
+  if (WIDE3 || RC != 1200) c.qs_max = __uint_as_float(__float_as_uint(WIDE3 ? a.sym_qs_max : a.sym_qs_max2) | a.opaque_zero);
+  if (WIDE3) c.c7s = __uint_as_float(__float_as_uint(-1.0f / (7.0f * S * S * S * S * S * S)) | a.opaque_zero);
   // OR-ed with a kernel argument that is always 0: a value ptxas cannot rebuild with one MOV, so it stays in a register
   c.c5s = __uint_as_float(__float_as_uint(1.0f / (5.0f * S * S * S * S)) | a.opaque_zero);
   c.a6 = __uint_as_float(__float_as_uint(kBearingA6) | a.opaque_zero);
@@ -383,10 +408,10 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
       const int sel = (lane >> (31 - __clz(s))) & 1;
       const int i = ((2 * warp + sel) << 5) + lane, j = i ^ s;
       const float4 me = sel ? me1 : me0;
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, lds_f4(ag_s + 16u * (uint32_t)j), me.x, me.y,
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3>(a, lds_f4(ag_s + 16u * (uint32_t)j), me.x, me.y,
                                                             __float_as_uint(me.z), c);
-      sym_red(rows_s + 4u * (uint32_t)i, stride_b, A.ps_i, A.mask);
-      sym_red(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask);
+      sym_red<WIDE3>(rows_s + 4u * (uint32_t)i, stride_b, A.ps_i, A.mask, A.mask_hi);
+      sym_red<WIDE3>(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask, A.mask_hi);
       sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j, ws);
     }
   }
@@ -411,13 +436,13 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     for (uint32_t o16 = 32u; o16 <= 512u; o16 += 32u) {       // o16 = 16 (s + 2), s = 0, 2, .. 30: ONE induction variable
       // prefetch the next two partner records (the last iteration reads block J ^ 1: harmless)
       const float4 nA = lds_f4(rec_j0 ^ o16), nB = lds_f4(rec_j1 ^ o16);
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true>(a, oA, me.x, me.y, __float_as_uint(me.z), c);
-      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true>(a, oB, me.x, me.y, __float_as_uint(me.z), c);
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3>(a, oA, me.x, me.y, __float_as_uint(me.z), c);
+      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3>(a, oB, me.x, me.y, __float_as_uint(me.z), c);
       const uint32_t o4 = (o16 >> 2) - 8u;                     // 4 s
-      sym_red(row_i, stride_b, A.ps_i, A.mask);
-      sym_red(row_j0 ^ o4, stride_b, A.ps_j, A.mask);
-      sym_red(row_i, stride_b, B.ps_i, B.mask);
-      sym_red(row_j1 ^ o4, stride_b, B.ps_j, B.mask);
+      sym_red<WIDE3>(row_i, stride_b, A.ps_i, A.mask, A.mask_hi);
+      sym_red<WIDE3>(row_j0 ^ o4, stride_b, A.ps_j, A.mask, A.mask_hi);
+      sym_red<WIDE3>(row_i, stride_b, B.ps_i, B.mask, B.mask_hi);
+      sym_red<WIDE3>(row_j1 ^ o4, stride_b, B.ps_j, B.mask, B.mask_hi);
       // ---- off the fast path (~1 % of the directions): remembered, pushed after the round ----
       or_if(fi, A.slow_i, tbit);
       or_if(fj, A.slow_j, tbit);
@@ -472,30 +497,30 @@ bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t 
   if (a.tile_begin != 0 || a.tile_count != a.N) return false;
   const int Np = (a.N + 63) / 64 * 64;
   if (Np > 1024) return false;   // 16 warps at most; queue entries hold 16-bit agent indices
-  return vf_sym_smem_bytes(Np, a.W) <= smem_limit;
+  return vf_sym_smem_bytes(Np, a.W, true) <= smem_limit;
 }
 
-template <bool TORUS, bool FULL_FOV, int RC, int NPC>
+template <bool TORUS, bool FULL_FOV, int RC, int NPC, bool WIDE3>
 static void launch_sym_variant(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
   static SmemOptIn optin;   // per device (abm_common.cuh)
-  optin.ensure(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC>, smem);
-  vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC><<<a.B, threads, smem, stream>>>(a, Np);
+  optin.ensure(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC, WIDE3>, smem);
+  vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC, WIDE3><<<a.B, threads, smem, stream>>>(a, Np);
 }
 
-template <bool TORUS>
+template <bool TORUS, bool WIDE3>
 static void launch_sym_fov(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
-  if (a.full_fov && a.R == 1200 && Np == 1024) launch_sym_variant<TORUS, true, 1200, 1024>(a, Np, threads, smem, stream);
-  else if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200, 0>(a, Np, threads, smem, stream);
-  else if (a.full_fov) launch_sym_variant<TORUS, true, 0, 0>(a, Np, threads, smem, stream);
-  else launch_sym_variant<TORUS, false, 0, 0>(a, Np, threads, smem, stream);
+  if (a.full_fov && a.R == 1200 && Np == 1024) launch_sym_variant<TORUS, true, 1200, 1024, WIDE3>(a, Np, threads, smem, stream);
+  else if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200, 0, WIDE3>(a, Np, threads, smem, stream);
+  else if (a.full_fov) launch_sym_variant<TORUS, true, 0, 0, WIDE3>(a, Np, threads, smem, stream);
+  else launch_sym_variant<TORUS, false, 0, 0, WIDE3>(a, Np, threads, smem, stream);
 }
 
-void launch_vf_step_sym(const VFKernelArgs& a, cudaStream_t stream) {
+void launch_vf_step_sym(const VFKernelArgs& a, bool wide3, cudaStream_t stream) {
   const int Np = (a.N + 63) / 64 * 64;
   const int threads = 32 * (Np / 64);
-  const size_t smem = vf_sym_smem_bytes(Np, a.W);
-  if (a.boundary == 1) launch_sym_fov<true>(a, Np, threads, smem, stream);
-  else launch_sym_fov<false>(a, Np, threads, smem, stream);
+  const size_t smem = vf_sym_smem_bytes(Np, a.W, wide3);
+  if (a.boundary == 1) { if (wide3) launch_sym_fov<true, true>(a, Np, threads, smem, stream); else launch_sym_fov<true, false>(a, Np, threads, smem, stream); }
+  else { if (wide3) launch_sym_fov<false, true>(a, Np, threads, smem, stream); else launch_sym_fov<false, false>(a, Np, threads, smem, stream); }
 }
 
 }  // namespace abm

@@ -92,7 +92,7 @@ static __device__ __noinline__ void warp_pair_slow(const VFKernelArgs& a, float4
 // padded row with two reductions (the arithmetic of the symmetric kernel's fast path, one direction).
 template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R>
 __device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const float4 f, uint32_t row_pad_s, const float4 o,
-                                          float S, float c3s, float c5s, uint32_t qentry, uint32_t queue_s, uint32_t qcount_s,
+                                          float S, float c3s, float c5s, float c7s, uint32_t qentry, uint32_t queue_s, uint32_t qcount_s,
                                           const WarpShared& sh, unsigned& n_fp64, unsigned& n_differ) {
   float dx, dy;
   bool slow = false;
@@ -110,15 +110,17 @@ __device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const float4 f,
   const float d2 = fmaf(dx, dx, dy * dy);
   if (CULL) { if (d2 > o.w) return; }                    // beyond it the half width is 0
   slow |= (o.x == f.x) & (o.y == f.y);
-  // half width h = floor(atan(r / d) R / 2pi): three-term series in q = r / d, exact to fp32 for h <= 16 (abm_vf_sym.cu)
+  // half width h = floor(atan(r / d) R / 2pi): four-term series in q = r / d, exact to the guard band up to q = 0.18
+  // (abm_vf_sym.cu); the limit on qs also keeps the interval within two row words (h <= 16)
   const float qs = rsqrt_approx(d2) * (o.z * S);
   const float zs = qs * qs;
-  float p = fmaf(zs, c5s, c3s);
+  float p = fmaf(zs, c7s, c5s);
+  p = fmaf(p, zs, c3s);
   p = fmaf(p, zs, 1.0f);
   const float y = fmaf(qs, p, -0.5f);
   const float yr = y + kMagic;
   const uint32_t hraw = __float_as_uint(yr);             // h + kMagicBits
-  slow |= !(y < 16.5f) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);   // wide, near an integer, NaN
+  slow |= !(qs < a.warp_qs_max) | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);   // wide, near an integer, inf / NaN
   uint32_t mask;
   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(mask) : "r"(2u * hraw - 2u * (uint32_t)kMagicBits));   // 2h ones
   const int bh = 32 + kMagicBits - (int)hraw;            // ps (padded) = bin index + 32 - h
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
     const uint32_t rows_s = smem_u32(sh.rows), focal_s = smem_u32(sh.focal), queue_s = smem_u32(sh.queue);
     const uint32_t qcount_s = smem_u32(tile_list + kMaxTileList + 1);
     const float S = a.y_scale;
-    const float c3s = -1.0f / (3.0f * S * S), c5s = 1.0f / (5.0f * S * S * S * S);
+    const float c3s = -1.0f / (3.0f * S * S), c5s = 1.0f / (5.0f * S * S * S * S), c7s = -1.0f / (7.0f * S * S * S * S * S * S);
     const int cpt_sh = tile_sh - 7;                          // chunks per tile = 2^cpt_sh
     const int n_chunks = n_stage << cpt_sh;
     const int off = tid & (kChunk - 1);
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
           const int f = f0 + u;
           if (f < nf)
             warp_pair<TORUS, CULL, FULL_FOV, UNIFORM_R>(a, lds_f4(focal_s + 16u * (uint32_t)f),
-                                                         rows_s + 4u * (uint32_t)(row_words * f), o, S, c3s, c5s,
+                                                         rows_s + 4u * (uint32_t)(row_words * f), o, S, c3s, c5s, c7s,
                                                          ((uint32_t)f << 24) | (uint32_t)j, queue_s, qcount_s, sh, n_fp64,
                                                          n_differ);
         }

@@ -314,6 +314,12 @@ class VFEngine:
         blob = b"".join(exports)
         _lib.check(self._lib.abm_vf_ipc_attach(self._h, len(exports), int(my_rank), blob), "abm_vf_ipc_attach")
 
+    def kernel_stats(self) -> dict:
+        """Step-kernel launches so far, by kernel (and, for the symmetric one, by fast-path width)."""
+        c = (C.c_uint64 * 4)()
+        _lib.check(self._lib.abm_vf_kernel_stats(self._h, c), "abm_vf_kernel_stats")
+        return dict(symmetric=int(c[0]), symmetric_wide=int(c[1]), onesided=int(c[2]), warp=int(c[3]))
+
     def last_kernel(self) -> str:
         """Name of the step kernel the last step() launched."""
         return (self._lib.abm_vf_last_kernel(self._h) or b"").decode()

@@ -583,6 +583,7 @@ def main():
     clocks = sampler.summary()
     counters = eng.counters()
     timed_kernel = eng.last_kernel()
+    kernel_stats = eng.kernel_stats()
 
     # ---- parity of the benchmark's own kernel against the oracle (every rank on its own replicates) ----
     par = parity_check(VFEngine, local_rank, x, y, th, v, rad)
@@ -644,6 +645,7 @@ def main():
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(timed_kernel), "kernel": timed_kernel,
+                         "kernel_launches_by_variant": kernel_stats,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, committed `ncu --set full` "
                                            "capture under profiles/ (not measured in this run)",
                          "algorithmic_ops_per_launch": ops_launch,

@@ -191,13 +191,17 @@ int abm_vf_resort(abm_engine_t* e, void* stream);
 int abm_vf_internal_arrays(abm_engine_t* e, void** theta_dev, void** vel_dev);
 
 /* Name of the step kernel the last abm_vf_step launched ("abm::vf_step_sym_kernel": every unordered pair once, all rows
- * of a replicate in one CTA's shared memory; "abm::vf_step_kernel": one thread per focal agent), "" before the first
- * step.  The choice is made per step from the state (equal radii, replicate fits in shared memory, no distance
- * culling -> symmetric); the environment variable ABM_VF_KERNEL=onesided|symmetric overrides it for tests. */
+ * of a replicate in one CTA's shared memory; "abm::vf_step_kernel": one thread per focal agent; "abm::vf_step_warp_kernel":
+ * a CTA per few focal agents, a thread per neighbour record -- large sparse swarms, their tiles, small batches), ""
+ * before the first step.  The choice is made per step from the state; the environment variable
+ * ABM_VF_KERNEL=onesided|symmetric|warp overrides it for tests. */
 const char* abm_vf_last_kernel(abm_engine_t* e);
-/* Statistics behind the automatic choice: unordered pairs that left the symmetric kernel's fast
- * path -- wide intervals, guard-band hits -- summed over its launches so far, and the number of those launches.  When
- * more than 9.5 % of the pairs of a step are slow (crowded scene) the next 64 steps use the other kernel. */
+/* Step-kernel launches so far: [0] symmetric with the two-word fast path, [1] symmetric with the three-word fast path
+ * (crowded scenes: chosen when more than 4 % of the pairs of a two-word step left its fast path), [2] one thread per
+ * focal agent, [3] warp kernel (a multi-step cooperative launch counts once). */
+int abm_vf_kernel_stats(abm_engine_t* e, uint64_t stats[4]);
+/* Statistics behind the automatic choice: unordered pairs that left the symmetric kernel's (two-word) fast path -- wide
+ * intervals, guard-band hits -- summed over its launches so far, and the number of those launches. */
 int abm_vf_slow_entries(abm_engine_t* e, uint64_t* entries, uint64_t* sym_launches, void* stream);
 
 /* Summary metrics of the current state, per replicate (the quantities abm/loader/data_loader.py computes

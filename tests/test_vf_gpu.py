@@ -422,9 +422,9 @@ def test_summary_metrics_match_numpy(built_lib, boundary):
 
 
 def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
-    """The step kernel is chosen per step: the symmetric kernel reports how many pairs left its fast path and a
-    crowded scene (most intervals wider than 32 bins) switches to the one-thread-per-focal-agent kernel -- without
-    changing any result (both kernels are exact)."""
+    """The step kernel is chosen per step: the symmetric kernel reports how many pairs left its (two-word) fast path and
+    a crowded scene (many intervals wider than 32 bins) switches to its three-word fast path -- without changing any
+    result (every variant is exact)."""
     import torch
     from abm_b200 import VFEngine
     monkeypatch.delenv("ABM_VF_KERNEL", raising=False)
@@ -442,21 +442,22 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
         entries, launches = eng.slow_entries()
         frac = entries / launches / (0.5 * B * N * (N - 1))            # of the unordered pairs
         torch.cuda.synchronize()
-        kernels = []
         for _ in range(4):
-            eng.step(1); torch.cuda.synchronize(); kernels.append(eng.last_kernel())
-        res[name] = (frac, kernels, eng.fields_packed().copy(), eng.get_state())
+            eng.step(1); torch.cuda.synchronize()
+        res[name] = (frac, eng.kernel_stats(), eng.fields_packed().copy(), eng.get_state())
         eng.close()
-        monkeypatch.setenv("ABM_VF_KERNEL", "symmetric")          # the same five steps with one kernel throughout
-        ref = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
-        ref.set_params(); ref.set_state(x, y, th, v, 10.0); ref.step(5)
-        assert np.array_equal(ref.fields_packed(), res[name][2])
-        for k in ("x", "y", "theta", "vel"):
-            assert np.array_equal(ref.get_state()[k], res[name][3][k])
-        ref.close()
-        monkeypatch.delenv("ABM_VF_KERNEL")
-    assert res["crowded"][0] > 0.095 and "abm::vf_step_kernel" in res["crowded"][1]
-    assert res["sparse"][0] < 0.095 and set(res["sparse"][1]) == {"abm::vf_step_sym_kernel"}
+        for wide in ("0", "1"):                                   # the same five steps with ONE variant throughout
+            monkeypatch.setenv("ABM_VF_SYM_WIDE", wide)
+            ref = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
+            ref.set_params(); ref.set_state(x, y, th, v, 10.0); ref.step(5)
+            assert ref.kernel_stats()["symmetric_wide" if wide == "1" else "symmetric"] == 5
+            assert np.array_equal(ref.fields_packed(), res[name][2])
+            for k in ("x", "y", "theta", "vel"):
+                assert np.array_equal(ref.get_state()[k], res[name][3][k])
+            ref.close()
+        monkeypatch.delenv("ABM_VF_SYM_WIDE")
+    assert res["crowded"][0] > 0.04 and res["crowded"][1]["symmetric_wide"] >= 3
+    assert res["sparse"][0] < 0.04 and res["sparse"][1] == dict(symmetric=5, symmetric_wide=0, onesided=0, warp=0)
     # a batch that cannot fill the GPU with one CTA per replicate runs with a warp per focal agent -- same results
     small = VFEngine(2, N, resolution=1200, width=W, height=W, keep_fields=True)
     small.set_params(); small.set_state(x[:2], y[:2], th[:2], v[:2], 10.0); small.step(5)
