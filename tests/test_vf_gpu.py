@@ -429,11 +429,11 @@ def test_kernel_choice_adapts_to_crowding(built_lib, monkeypatch):
     from abm_b200 import VFEngine
     monkeypatch.delenv("ABM_VF_KERNEL", raising=False)
     rng = np.random.default_rng(11)
-    B, N, W = 160, 256, 900.0          # (a batch large enough for one CTA per replicate to fill the GPU, see below)
+    B, N, W = 160, 256, 1500.0         # (a batch large enough for one CTA per replicate to fill the GPU, see below)
     res = {}
-    for name, spread in (("crowded", 60.0), ("sparse", 420.0)):
+    for name, spread in (("crowded", 60.0), ("sparse", 700.0)):
         ang = rng.uniform(0, 2 * np.pi, (B, N)); rr = np.sqrt(rng.uniform(0, 1, (B, N))) * spread
-        x = (450 + rr * np.cos(ang)).astype(np.float32); y = (450 + rr * np.sin(ang)).astype(np.float32)
+        x = (750 + rr * np.cos(ang)).astype(np.float32); y = (750 + rr * np.sin(ang)).astype(np.float32)
         th = rng.uniform(0, 2 * np.pi, (B, N)).astype(np.float32); v = np.zeros_like(x)
         eng = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True)
         eng.set_params(); eng.set_state(x, y, th, v, 10.0)
