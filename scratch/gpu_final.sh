@@ -7,3 +7,10 @@ timeout 240 python bench.py --impl reference > gpurun_out/${T}_bench_ref.json 2>
 ABM_BENCH_SWARM=0 ABM_BENCH_OTHER_CONFIGS=0 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_launches.log 2>&1
 ABM_BENCH_SWARM=0 ABM_BENCH_OTHER_CONFIGS=0 timeout 250 ncu --set full --clock-control none --import-source on -k regex:vf_step_sym -s 3 -c 1 -f -o gpurun_out/${T}_prof_sym python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu.log 2>&1
 ncu -i gpurun_out/${T}_prof_sym.ncu-rep --page raw --csv > gpurun_out/${T}_prof_sym_raw.csv 2>/dev/null
+# the swarm's per-rank kernel: 8192 focal agents against the 65 536-record table (tile 0 of 8, emulated exchange)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:vf_step_warp -s 27 -c 1 -f -o gpurun_out/${T}_prof_warp python scratch/c5_tile_probe.py 8 > gpurun_out/${T}_ncu_warp.log 2>&1
+ncu -i gpurun_out/${T}_prof_warp.ncu-rep --page raw --csv > gpurun_out/${T}_prof_warp_raw.csv 2>/dev/null
+# configs[2]: the fused foraging step
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:base_step -s 25 -c 1 -f -o gpurun_out/${T}_prof_base python scratch/base_probe.py 30 > gpurun_out/${T}_ncu_base.log 2>&1
+ncu -i gpurun_out/${T}_prof_base.ncu-rep --page raw --csv > gpurun_out/${T}_prof_base_raw.csv 2>/dev/null
+python scratch/ncu_keys.py gpurun_out/${T}_prof_warp_raw.csv | head -12
