@@ -152,6 +152,7 @@ SYMBOLS = {
     "abm_base_set_params": (C.c_int, [_P, _P, C.c_int]),
     "abm_base_set_agent_geometry": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "abm_base_set_agent_radii": (C.c_int, [_P, _P, C.c_int]),
+    "abm_base_set_agent_resolution": (C.c_int, [_P, _P, C.c_int]),
     "abm_base_set_agents": (C.c_int, [_P, C.POINTER(BaseAgents), C.c_int, _P]),
     "abm_base_get_agents": (C.c_int, [_P, C.POINTER(BaseAgents), C.c_int, _P]),
     "abm_base_set_patches": (C.c_int, [_P, C.POINTER(BasePatches), C.c_int, _P]),

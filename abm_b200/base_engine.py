@@ -116,6 +116,17 @@ class BaseEngine:
             self._h, C.c_void_p(f0.ctypes.data), C.c_void_p(f1.ctypes.data), C.c_void_p(vr.ctypes.data),
             self.B * self.N), "abm_base_set_agent_geometry")
 
+    def set_agent_resolution(self, v_field_res=None):
+        """Per-agent field resolution, (B, N) or (N,) integers <= the engine's resolution (heterogeneous agents,
+        sims.py:507); None returns to the engine-wide one.  fields() keeps the engine's resolution as its last axis:
+        agent i's row holds its own v_field_res[i] bins, the rest is False."""
+        if v_field_res is None:
+            _lib.check(self._lib.abm_base_set_agent_resolution(self._h, None, 0), "abm_base_set_agent_resolution")
+            return
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(v_field_res, np.int32), (self.B, self.N)))
+        _lib.check(self._lib.abm_base_set_agent_resolution(self._h, C.c_void_p(r.ctypes.data), self.B * self.N),
+                   "abm_base_set_agent_resolution")
+
     def set_agent_radii(self, radius=None):
         """Per-agent radius, (B, N) or (N,) (heterogeneous agents, sims.py:502); None returns to the engine-wide one."""
         if radius is None:

@@ -64,6 +64,13 @@ __device__ __forceinline__ const BaseParams& base_params_of(const BaseKernelArgs
   return *reinterpret_cast<const BaseParams*>(a.params + (size_t)b * a.param_stride + (size_t)i * a.param_stride_agent);
 }
 
+// Field resolution of agent g (heterogeneous agents: each agent's own v_field_res, agent.py:58, 480-481; rows keep the
+// engine-wide stride of W words, the bins beyond the agent's resolution stay 0).
+__device__ __forceinline__ int base_res_of(const BaseKernelArgs& a, size_t g) { return a.agent_geo ? a.agent_geo[g].res : a.R; }
+__device__ __forceinline__ double base_lin_step_of(const BaseKernelArgs& a, size_t g) {
+  return a.agent_geo ? a.agent_geo[g].lin_step : a.lin_step;
+}
+
 // One WARP per replicate: lanes take the agents of a chunk of 32 in parallel (membership, bias, notify, teleport),
 // chunks and patches go in the reference's order, and the one truly sequential piece -- the depletion of a patch by
 // its exploiting agents in agent order (sims.py:824-836) -- is replayed by all lanes in lock step over the ballot of
@@ -224,7 +231,9 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
   uint32_t* row = wf.row;
   const int b = (int)(gw / a.N), i = (int)(gw - (long long)b * a.N);
   const size_t a0 = (size_t)b * a.N, gi = a0 + i;
-  const int R = a.R, W = a.W, N = a.N;
+  const int W = a.W, N = a.N;
+  int R = a.R;
+  double lin_step = a.lin_step;
   for (int w = lane; w < W + 1; w += 32) row[w] = 0u;
 
   const float xi_f = a.ag.snap_x[gi], yi_f = a.ag.snap_y[gi];
@@ -239,6 +248,7 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
   if (a.agent_geo) {                                                                // this agent's own FOV / range
     const BaseAgentGeo g = a.agent_geo[gi];
     fov0 = g.fov0; fov1 = g.fov1; vision_range = g.vision_range; mask_lo = g.mask_lo; mask_hi = g.mask_hi;
+    R = g.res; lin_step = g.lin_step;
   }
   const BaseFast bf = base_fast_consts(th_f, r, fov0, fov1, R);
 
@@ -279,7 +289,7 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
           rec = vis; o.d = n2;
         } else {                                                                    // inside a guard band: fp64
           double dist;
-          rec = base_interval_cold(xi_f, yi_f, r, th_f, xj_f, yj_f, fov0, fov1, R, a.lin_step, o.s, o.e, dist);
+          rec = base_interval_cold(xi_f, yi_f, r, th_f, xj_f, yj_f, fov0, fov1, R, lin_step, o.s, o.e, dist);
           o.d = dist;
           atomicAdd(&a.counters[2], 1ull);
         }
@@ -302,11 +312,10 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
   if (a.fields_out) {
     uint32_t* out = a.fields_out + gi * W;
     for (int ws = lane; ws < W; ws += 32) {
-      uint32_t word = flipped_word(row, 1, R, W, ws);
       const int lo = max(mask_lo - (ws << 5), 0), hi = min(mask_hi + 1 - (ws << 5), 32);
       uint32_t m = 0u;
       if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-      out[ws] = word & m;
+      out[ws] = m ? (flipped_word(row, 1, R, W, ws) & m) : 0u;   // (words beyond the agent's own resolution: 0)
     }
   }
 }
@@ -317,7 +326,7 @@ __device__ __forceinline__ void base_agent_field(const BaseKernelArgs& a, WarpFi
 __device__ __forceinline__ void base_agent_decide(const BaseKernelArgs& a, long long gw, int n_left, int n_right, unsigned step) {
   const int b = (int)(gw / a.N), i = (int)(gw - (long long)b * a.N);
   const size_t gi = (size_t)b * a.N + i;
-  const int R = a.R, h = R / 2;
+  const int R = base_res_of(a, gi), h = R / 2;
   const double xi = a.ag.snap_x[gi], yi = a.ag.snap_y[gi], r = base_radius_of(a, gi);   // own radius at the walls
   const BaseParams prm = base_params_of(a, b, i);
   const double mean_all = (double)(n_left + n_right) / (double)R;
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(256, 3) base_agent_kernel(const BaseKernelArgs
 // hit) have to stay in a1 order.  `collided_agents` is a set: the warps mark its members with plain stores.
 __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a, int b, unsigned char* smem_raw) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int N = a.N, R = a.R, W = a.W, h = R / 2;
+  const int N = a.N, W = a.W;
   const size_t per_warp = warp_field_bytes(N, W);
   WarpField wf = warp_field_at(smem_raw + per_warp * wib, N);
   int* ov = reinterpret_cast<int*>(smem_raw + per_warp * wpb);          // override_mode (entry a2: its warp's)
@@ -462,6 +471,8 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
     const int a2 = work[slot < n_front ? slot : N - 1 - (slot - n_front)];
     const bool expl2 = ov[a2] == OV_EXPLOIT;                               // (fixed during the phase)
     const double r = rad[a2];                                              // the hit agent is the focal agent of its LIDAR field
+    const int R = base_res_of(a, a0 + a2), h = R / 2;                      // ... at its own resolution
+    const double lin_step = base_lin_step_of(a, a0 + a2);
     for (int j0 = 0; j0 < N; j0 += 32) {
       const int jj = j0 + lane;
       const bool hit = jj < N && jj != a2 && hits(jj, a2);                 // rect.x = int(position) (agent.py:303-304)
@@ -501,7 +512,7 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
                   if (!base_interval_fast(xj - x2, yj - y2, bf, o.s, o.e, vis)) {
                     rec = vis; o.d = n2;
                   } else {                                                          // inside a guard band: fp64
-                    rec = base_interval_cold(x2, y2, r, th2, xj, yj, -ABM_PI_D, ABM_PI_D, R, a.lin_step, o.s, o.e, dist);
+                    rec = base_interval_cold(x2, y2, r, th2, xj, yj, -ABM_PI_D, ABM_PI_D, R, lin_step, o.s, o.e, dist);
                     o.d = dist;
                   }
                 }
@@ -576,6 +587,8 @@ struct BlkShared {
   BaseFast* bf;                     // [G] fast-path constants of the group's focal agents
   double2* fovd;                    // [G] (fov0, fov1) in float64 (fp64 fallback)
   int2* mask;                       // [G] stored bins kept by the FOV mask (mask_lo, mask_hi)
+  int* res;                         // [G] the focal agent's own field resolution (<= R)
+  double* lin;                      // [G] its linspace step
   float* vr2;                       // [G] vision range squared
   uint32_t* se;                     // [G][N] raw interval ends: (uint16)s | (uint16)e << 16
   double* d;                        // [G][N] centre distance, float64 with the reference's operation sequence (:526-528):
@@ -588,7 +601,7 @@ struct BlkShared {
 };
 size_t base_block_smem_bytes(int N, int W, int G) {
   size_t b = 6 * 4 * (size_t)N;                                        // x, y, th, ov, pid, rad
-  b = (b + 15) / 16 * 16 + sizeof(BaseFast) * G + 16 * G + 8 * G + 4 * G;   // bf, fovd, mask, vr2
+  b = (b + 15) / 16 * 16 + sizeof(BaseFast) * G + 16 * G + 8 * G + 8 * G + 4 * G + 4 * G;   // bf, fovd, lin, mask, vr2, res
   b = (b + 15) / 16 * 16 + (8 + 4 + 1 + 2) * (size_t)G * N + 16;        // d, se, cls, cues
   b = (b + 15) / 16 * 16 + 4 * (size_t)G * (W + 1) + 8 * (size_t)N + 16;
   return b + 64;
@@ -608,9 +621,11 @@ __device__ __forceinline__ BlkShared base_block_carve(unsigned char* p, int N, i
   s.ov = reinterpret_cast<int*>(s.th + N); s.pid = s.ov + N; s.rad = reinterpret_cast<float*>(s.pid + N);
   p = up(reinterpret_cast<unsigned char*>(s.rad + N));
   s.fovd = reinterpret_cast<double2*>(p); p += 16 * G;
+  s.lin = reinterpret_cast<double*>(p); p += 8 * G;
   s.bf = reinterpret_cast<BaseFast*>(p); p += sizeof(BaseFast) * G;
   s.mask = reinterpret_cast<int2*>(p); p += 8 * G;
   s.vr2 = reinterpret_cast<float*>(p); p += 4 * G;
+  s.res = reinterpret_cast<int*>(p); p += 4 * G;
   p = up(p);
   s.d = reinterpret_cast<double*>(p); p += 8 * (size_t)G * N;
   s.se = reinterpret_cast<uint32_t*>(p); p += 4 * (size_t)G * N;
@@ -625,7 +640,7 @@ __device__ __forceinline__ BlkShared base_block_carve(unsigned char* p, int N, i
 
 __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b, unsigned char* smem_raw, unsigned step,
                                                   const int G) {
-  const int N = a.N, R = a.R, W = a.W;
+  const int N = a.N, W = a.W;
   const int tid = threadIdx.x, T = blockDim.x;
   const size_t a0 = (size_t)b * N;
   BlkShared sh = base_block_carve(smem_raw, N, W, G);
@@ -635,7 +650,6 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
     sh.rad[i] = a.ag.radius ? a.ag.radius[a0 + i] : (float)a.radius;
     sh.halves[2 * i] = 0; sh.halves[2 * i + 1] = 0;
   }
-  const int h = R / 2;                                       // int(V_field_len / 2) (supcalc.py:86-88)
   for (int g0 = 0; g0 < N; g0 += G) {
     const int ng = min(G, N - g0);
     __syncthreads();                                         // staging done / previous group's rows and table are free
@@ -643,9 +657,14 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
     if (tid < ng) {
       const int i = g0 + tid;
       double fov0 = a.fov0, fov1 = a.fov1, vr = a.vision_range;
-      int mlo = a.mask_lo, mhi = a.mask_hi;
-      if (a.agent_geo) { const BaseAgentGeo q = a.agent_geo[a0 + i]; fov0 = q.fov0; fov1 = q.fov1; vr = q.vision_range; mlo = q.mask_lo; mhi = q.mask_hi; }
+      int mlo = a.mask_lo, mhi = a.mask_hi, R = a.R;
+      double lin = a.lin_step;
+      if (a.agent_geo) {
+        const BaseAgentGeo q = a.agent_geo[a0 + i];
+        fov0 = q.fov0; fov1 = q.fov1; vr = q.vision_range; mlo = q.mask_lo; mhi = q.mask_hi; R = q.res; lin = q.lin_step;
+      }
       sh.bf[tid] = base_fast_consts(sh.th[i], a.ag.radius ? (double)sh.rad[i] : a.radius, fov0, fov1, R);
+      sh.res[tid] = R; sh.lin[tid] = lin;
       sh.fovd[tid] = make_double2(fov0, fov1);
       sh.mask[tid] = make_int2(mlo, mhi);
       sh.vr2[tid] = (float)(vr * vr);
@@ -698,7 +717,7 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
             dist_ij = base_distance_exact(__dadd_rn((double)xi, ri), __dadd_rn((double)yi, ri), ri, xj, yj);
           if (base_interval_fast(dxf, dyf, sh.bf[gi], s_, e_, vis)) {                // inside a guard band: float64
             double dist;
-            vis = base_interval_cold(xi, yi, ri, sh.th[i], xj, yj, sh.fovd[gi].x, sh.fovd[gi].y, R, a.lin_step, s_, e_, dist);
+            vis = base_interval_cold(xi, yi, ri, sh.th[i], xj, yj, sh.fovd[gi].x, sh.fovd[gi].y, sh.res[gi], sh.lin[gi], s_, e_, dist);
             atomicAdd(&a.counters[2], 1ull);
           }
           if (!vis) cls = 0;
@@ -753,7 +772,7 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
           if (os <= sx && oe >= ex) { sx = 0; ex = 0; }                               // :438-440
         }
       }
-      base_draw(sh.rows + (size_t)gi * (W + 1), R, sx, ex);
+      base_draw(sh.rows + (size_t)gi * (W + 1), sh.res[gi], sx, ex);
     }
     __syncthreads();
     // ---- (focal, word): set bins of the stored field's halves (flip + FOV mask, agent.py:593-595; supcalc.py:86-91)
@@ -762,6 +781,7 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
       const int gi = it / W, w = it - gi * W, i = g0 + gi;
       const uint32_t* row = sh.rows + (size_t)gi * (W + 1);
       const int mlo = sh.mask[gi].x, mhi = sh.mask[gi].y;
+      const int R = sh.res[gi], h = R / 2;                   // int(V_field_len / 2) (supcalc.py:86-88)
       const int va = R - 1 - mhi, vb = R - mlo;              // kept bins in v coordinates [va, vb)
       const uint32_t word = row[w];
       if (word) {
@@ -777,11 +797,10 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
         if (nr) atomicAdd(&sh.halves[2 * i + 1], nr);
       }
       if (a.fields_out) {
-        uint32_t fw = flipped_word(row, 1, R, W, w);
         const int lo = max(mlo - (w << 5), 0), hi = min(mhi + 1 - (w << 5), 32);
         uint32_t m = 0u;
         if (hi > lo) m = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-        a.fields_out[(a0 + i) * W + w] = fw & m;
+        a.fields_out[(a0 + i) * W + w] = m ? (flipped_word(row, 1, R, W, w) & m) : 0u;   // (beyond the agent's resolution: 0)
       }
     }
   }

@@ -37,10 +37,13 @@ struct BasePatchPtrs {
 };
 
 // Per-agent field geometry (heterogeneous agents, sims.py:499-517: FOV and vision_range are constructor arguments of
-// every agent): FOV in radians, vision range, and the stored bins the FOV mask keeps (agent.py:594-595).
+// every agent): FOV in radians, vision range, the stored bins the FOV mask keeps (agent.py:594-595), and the agent's own
+// field resolution (v_field_res, agent.py:58; <= BaseKernelArgs::R, which is the row stride) with its linspace step.
 struct BaseAgentGeo {
   double fov0, fov1, vision_range;
+  double lin_step;
   int mask_lo, mask_hi;
+  int res, pad_;
 };
 
 struct BaseKernelArgs {

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <utility>
 #include <new>
 #include <string>
@@ -26,8 +27,10 @@ struct abm_base_engine {
   DevBuf<float> px, py, pradius, pleft, pquality;
   DevBuf<int32_t> pid;
   DevBuf<double> params;
-  DevBuf<abm::BaseAgentGeo> agent_geo;   // B*N once abm_base_set_agent_geometry was called
+  DevBuf<abm::BaseAgentGeo> agent_geo;   // B*N once abm_base_set_agent_geometry / _resolution was called
   bool has_agent_geo = false;
+  std::vector<double> h_fov0, h_fov1, h_vr;   // host copies of what the two calls set (either may be empty)
+  std::vector<int> h_res;
   DevBuf<double> regen_draws;            // abm_base_inject_regeneration
   int regen_tries = 0;
   DevBuf<float> agent_radius;            // B*N once abm_base_set_agent_radii was called
@@ -174,34 +177,59 @@ static int agents_xfer(abm_base_engine_t* e, const abm_base_agents_t* s, bool to
   return ABM_OK;
 }
 
-int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const double* fov1,
-                                const double* vision_range, int n) {
-  if (!e) return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: null engine");
-  if (n == 0) { e->has_agent_geo = false; return ABM_OK; }   // back to the engine-wide values
-  if (!fov0 || !fov1 || !vision_range) return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: null argument");
-  if ((size_t)n != e->n_agents_total)
-    return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: n must be n_replicates * n_agents (or 0)");
-  const int R = e->cfg.resolution;
-  std::vector<abm::BaseAgentGeo> geo((size_t)n);
-  std::map<std::pair<double, double>, std::pair<int, int>> masks;   // few distinct FOVs: one O(R) scan each
-  for (int i = 0; i < n; ++i) {
-    const std::pair<double, double> key(fov0[i], fov1[i]);
+// The per-agent geometry table from whatever abm_base_set_agent_geometry and abm_base_set_agent_resolution hold (the
+// other call's part falls back to the engine-wide values of the config).
+static int base_upload_geo(abm_base_engine_t* e) {
+  const size_t n = e->n_agents_total;
+  const bool has_fov = !e->h_fov0.empty(), has_res = !e->h_res.empty();
+  if (!has_fov && !has_res) { e->has_agent_geo = false; return ABM_OK; }   // back to the engine-wide values
+  std::vector<abm::BaseAgentGeo> geo(n);
+  std::map<std::tuple<double, double, int>, std::pair<int, int>> masks;   // few distinct (FOV, resolution): one scan each
+  for (size_t i = 0; i < n; ++i) {
+    const double f0 = has_fov ? e->h_fov0[i] : e->cfg.fov0, f1 = has_fov ? e->h_fov1[i] : e->cfg.fov1;
+    const int R = has_res ? e->h_res[i] : e->cfg.resolution;
+    const double lin = ABM_TWO_PI_D / (double)(R - 1);       // numpy.linspace step of the agent's own grid (agent.py:481)
+    const auto key = std::make_tuple(f0, f1, R);
     auto it = masks.find(key);
     if (it == masks.end()) {
       int lo = R, hi = -1;   // FOV mask in stored coordinates (agent.py:594-595) on the numpy linspace grid
       for (int k = 0; k < R; ++k) {
-        const double phi = (k == R - 1) ? ABM_PI_D : ((double)k * e->lin_step + (-ABM_PI_D));
-        if (!(phi < fov0[i]) && !(phi > fov1[i])) { if (k < lo) lo = k; if (k > hi) hi = k; }
+        const double phi = (k == R - 1) ? ABM_PI_D : ((double)k * lin + (-ABM_PI_D));
+        if (!(phi < f0) && !(phi > f1)) { if (k < lo) lo = k; if (k > hi) hi = k; }
       }
       it = masks.emplace(key, std::make_pair(lo, hi)).first;
     }
-    geo[i] = abm::BaseAgentGeo{fov0[i], fov1[i], vision_range[i], it->second.first, it->second.second};
+    geo[i] = abm::BaseAgentGeo{f0, f1, has_fov ? e->h_vr[i] : e->cfg.vision_range, lin, it->second.first, it->second.second, R, 0};
   }
   ABM_CUDA(cudaSetDevice(e->device));
-  if (!e->agent_geo.p) ABM_CUDA(e->agent_geo.alloc((size_t)n));
-  ABM_CUDA(cudaMemcpy(e->agent_geo.p, geo.data(), sizeof(abm::BaseAgentGeo) * (size_t)n, cudaMemcpyHostToDevice));
+  if (!e->agent_geo.p) ABM_CUDA(e->agent_geo.alloc(n));
+  ABM_CUDA(cudaMemcpy(e->agent_geo.p, geo.data(), sizeof(abm::BaseAgentGeo) * n, cudaMemcpyHostToDevice));
   e->has_agent_geo = true;
   return ABM_OK;
+}
+
+int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const double* fov1,
+                                const double* vision_range, int n) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: null engine");
+  if (n == 0) { e->h_fov0.clear(); e->h_fov1.clear(); e->h_vr.clear(); return base_upload_geo(e); }
+  if (!fov0 || !fov1 || !vision_range) return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: null argument");
+  if ((size_t)n != e->n_agents_total)
+    return fail(ABM_E_INVALID, "abm_base_set_agent_geometry: n must be n_replicates * n_agents (or 0)");
+  e->h_fov0.assign(fov0, fov0 + n); e->h_fov1.assign(fov1, fov1 + n); e->h_vr.assign(vision_range, vision_range + n);
+  return base_upload_geo(e);
+}
+
+int abm_base_set_agent_resolution(abm_base_engine_t* e, const int32_t* resolution, int n) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_set_agent_resolution: null engine");
+  if (n == 0) { e->h_res.clear(); return base_upload_geo(e); }
+  if (!resolution) return fail(ABM_E_INVALID, "abm_base_set_agent_resolution: null argument");
+  if ((size_t)n != e->n_agents_total)
+    return fail(ABM_E_INVALID, "abm_base_set_agent_resolution: n must be n_replicates * n_agents (or 0)");
+  for (int i = 0; i < n; ++i)
+    if (resolution[i] < 2 || resolution[i] > e->cfg.resolution)
+      return fail(ABM_E_INVALID, "abm_base_set_agent_resolution: every value must be in [2, the engine's resolution]");
+  e->h_res.assign(resolution, resolution + n);
+  return base_upload_geo(e);
 }
 
 int abm_base_set_agent_radii(abm_base_engine_t* e, const double* radius, int n) {

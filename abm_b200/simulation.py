@@ -269,9 +269,13 @@ class AgentView(_View):
         if name == "mode":
             return _MODE_NAMES[int(o._cache()["mode"][self._b, self.id])]
         if name == "radius":
-            return o.agent_radii
+            rl = getattr(o, "agent_radii_list", None)                # sims.py:502: the agent's own radius
+            return o.agent_radii if rl is None else float(rl[self.id])
+        if name == "v_field_res":
+            rl = getattr(o, "agent_res_list", None)                  # sims.py:507: the agent's own resolution
+            return o.engine.R if rl is None else int(rl[self.id])
         if name == "soc_v_field":
-            return o._fields()[self._b, self.id].astype(np.float64)
+            return o._fields()[self._b, self.id, :self.v_field_res].astype(np.float64)   # agent.py:73: its own length
         raise AttributeError(name)
 
     def get_mode(self):
@@ -320,9 +324,9 @@ class Simulation(_RunOutputs):
         if pooling_time != 0:
             raise NotImplementedError("POOLING_TIME != 0 is not supported (every reference experiment uses 0)")
         self.heterogen_agents = agent_behave_param_list is not None                # sims.py:170-173
-        agent_radii_list = None
+        agent_radii_list = agent_res_list = None
         if self.heterogen_agents:
-            agent_radius, v_field_res, agent_radii_list = self._check_behave_params(
+            agent_radius, v_field_res, agent_radii_list, agent_res_list = self._check_behave_params(
                 agent_behave_param_list, int(N), agent_radius, v_field_res,
                 (decision_params or DecisionParams()).Tau)
         self.agent_behave_param_list = agent_behave_param_list
@@ -365,7 +369,9 @@ class Simulation(_RunOutputs):
                 vision_range=np.array([float(bp["vision_range"]) for bp in agent_behave_param_list]))
             if agent_radii_list is not None:                                       # sims.py:502: the agent's own radius
                 self.engine.set_agent_radii(agent_radii_list)
-        self.agent_radii_list = agent_radii_list
+            if agent_res_list is not None:                                         # sims.py:507: its own v_field_res
+                self.engine.set_agent_resolution(agent_res_list)
+        self.agent_radii_list, self.agent_res_list = agent_radii_list, agent_res_list
         self.engine.set_params(**prm)
         self.agents, self.rescources = [], []
         self._a = self._p = self._f = None
@@ -376,15 +382,13 @@ class Simulation(_RunOutputs):
     @staticmethod
     def _check_behave_params(plist, N, agent_radius, v_field_res, tau):
         """agent_behave_param_list (sims.py:499-517, template: contrib/evolution.py:1-26): the decision / movement
-        entries, agent_consumption, agent_fov, vision_range and agent_radius may differ between agents; v_field_res,
-        Tau and pooling must be the same for all agents (they are engine-wide) and then replace the constructor's
-        values like the reference does.  Returns (engine-wide radius, resolution, per-agent radii or None)."""
+        entries, agent_consumption, agent_fov, vision_range, agent_radius and v_field_res may differ between agents
+        (the engine's resolution -- its row stride -- is then the largest); Tau and pooling must be the same for all
+        agents (they are engine-wide) and then replace the constructor's values like the reference does.
+        Returns (engine-wide radius, engine resolution, per-agent radii or None, per-agent resolutions or None)."""
         if len(plist) != N:
             raise ValueError("agent_behave_param_list must hold one dictionary per agent")
-        res = {float(bp.get("v_field_res", v_field_res)) for bp in plist}
-        if len(res) != 1:
-            raise NotImplementedError("agent_behave_param_list: 'v_field_res' must be the same for all agents "
-                                      "(a per-agent resolution is not supported, SURVEY f4)")
+        res = np.array([int(bp.get("v_field_res", v_field_res)) for bp in plist])
         if any(int(bp.get("Tau", tau)) != int(tau) for bp in plist):
             raise NotImplementedError("agent_behave_param_list: 'Tau' must equal decision_params.Tau for all agents")
         if any(float(bp.get("pooling_time", 0)) != 0 for bp in plist):
@@ -392,7 +396,8 @@ class Simulation(_RunOutputs):
         radii = np.array([float(bp.get("agent_radius", agent_radius)) for bp in plist])
         radius = float(radii[0])
         hetero = None if np.all(radii == radii[0]) else radii
-        return (int(radius) if radius.is_integer() else radius), int(res.pop()), hetero
+        return ((int(radius) if radius.is_integer() else radius), int(res.max()), hetero,
+                None if np.all(res == res[0]) else res)
 
     def create_agents(self):
         """sims.py:526-537: integer positions, heading ~ U(0, 2pi)."""

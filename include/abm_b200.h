@@ -337,9 +337,16 @@ int abm_base_set_params(abm_base_engine_t* e, const double* params, int n_sets);
 /* Per-agent field geometry of heterogeneous agents (sims.py:499-517: every Agent gets its own FOV and vision_range):
  * fov0 / fov1 in radians (the reference's (-agent_fov * pi, agent_fov * pi)) and vision_range, n = n_replicates *
  * n_agents values each, replicate-major, host pointers.  n = 0 returns to the engine-wide values of the config.
- * The radius: abm_base_set_agent_radii; the resolution stays per engine. */
+ * The radius: abm_base_set_agent_radii; the resolution: abm_base_set_agent_resolution. */
 int abm_base_set_agent_geometry(abm_base_engine_t* e, const double* fov0, const double* fov1,
                                 const double* vision_range, int n);
+/* Per-agent field resolution of heterogeneous agents (sims.py:507: Agent(v_field_res = behave_params["v_field_res"]);
+ * agent.py:58, 480-481, 543, 577-588: the agent's own linspace grid, projection size and wrap; supcalc.py:86-91 and
+ * agent.py:196-199: the means over ITS field length; sims.py:449-462: the collision LIDAR field of the hit agent):
+ * n = n_replicates * n_agents values in [2, cfg.resolution], replicate-major, host pointer; n = 0 returns to
+ * cfg.resolution for everybody.  cfg.resolution stays the row stride of abm_base_fields: agent i's row holds its
+ * resolution[i] stored bins, the bits beyond are 0. */
+int abm_base_set_agent_resolution(abm_base_engine_t* e, const int32_t* resolution, int n);
 /* Per-agent radius of heterogeneous agents (sims.py:502: Agent(radius = behave_params["agent_radius"])): n =
  * n_replicates * n_agents values, replicate-major, host pointer; n = 0 returns to the config's agent_radius.  As in the
  * reference the candidate test (agent.py:400), the patch membership (sims.py:45-56), the wall reflection

@@ -278,7 +278,8 @@ def make_base_agents(st, cfg, behave_params_list=None):
             rad = behave_params_list[i]["agent_radius"]
         a = agent_mod.Agent(
             id=i, radius=rad, position=(float(st["x"][i]), float(st["y"][i])), orientation=float(st["theta"][i]),
-            env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0), v_field_res=cfg.R,
+            env_size=(int(cfg.width), int(cfg.height)), color=(0, 0, 0),
+            v_field_res=cfg.R if behave_params_list is None else int(behave_params_list[i].get("v_field_res", cfg.R)),  # sims.py:507
             FOV=tuple(cfg.fov) if behave_params_list is None else                      # sims.py:506
             (-float(behave_params_list[i]["agent_fov"]) * np.pi, float(behave_params_list[i]["agent_fov"]) * np.pi),
             window_pad=int(cfg.window_pad), pooling_time=0, pooling_prob=0, consumption=cfg.agent_consumption,

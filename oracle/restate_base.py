@@ -225,7 +225,8 @@ def base_step_frozen(st, cfg: BaseConfig, dtheta_random, agents=None, agent_cfgs
     patch_id (N,) ints, collected, collected_before (N,), radius (scalar).
     ``agent_cfgs``: optional list of one BaseConfig per agent (heterogeneous agents, agent.py:83-108: the
     behave_params entries replace the decision parameters, max_exp_vel and exp_stop_ratio of that agent;
-    the geometry fields must equal ``cfg``'s)."""
+    FOV, vision range and the field resolution R may differ too (sims.py:499-517); ``fields`` rows are padded with
+    False up to ``cfg.R``, which must be the largest)."""
     N = len(st["x"])
     out = {k: np.array(st[k], copy=True) for k in ("x", "y", "theta", "vel", "w", "u", "override", "mode",
                                                    "collected_before")}
@@ -233,7 +234,7 @@ def base_step_frozen(st, cfg: BaseConfig, dtheta_random, agents=None, agent_cfgs
     out["fields"] = np.zeros((N, cfg.R), bool)
     for i in (range(N) if agents is None else agents):
         r = base_agent_update(i, st, cfg if agent_cfgs is None else agent_cfgs[i], dtheta_random[i])
-        out["fields"][i] = r["field"]
+        out["fields"][i, :len(r["field"])] = r["field"]
         for k in ("x", "y", "theta", "vel", "w", "u", "override", "mode", "collected_before", "I_priv"):
             out[k][i] = r[k]
     return out
@@ -345,8 +346,6 @@ def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool, agent_cfgs=None)
     # rect centres: int-truncated position + half the (integer) rect size (agent.py:303-304; pygame Rect)
     ix, iy = np.trunc(st["x"]) + np.trunc(ra), np.trunc(st["y"]) + np.trunc(ra)
     collided = []
-    R = cfg.R
-    h = int(R / 2)
     for a1 in range(N):
         partners = [a2 for a2 in range(N)                                         # radii + 2 each, sims.py:739-752
                     if a2 != a1 and (ix[a1] - ix[a2]) ** 2 + (iy[a1] - iy[a2]) ** 2 <= (ra[a1] + ra[a2] + 4) ** 2]
@@ -362,19 +361,22 @@ def base_collision_phase(st, cfg: BaseConfig, ghost_mode: bool, agent_cfgs=None)
                 st["override"][a2] = OV_COLLIDE
                 st["mode"][a2] = MODE_COLLIDE
             r = ra[a2]                                                            # the hit agent is the focal agent
+            c2 = cfg if agent_cfgs is None else agent_cfgs[a2]                    # ... with its own resolution / range
+            R = c2.R
+            h = int(R / 2)
             d = np.sqrt(((st["x"] + ra) - (st["x"][a2] + r)) ** 2 + ((st["y"] + ra) - (st["y"][a2] + r)) ** 2)
             vicinity = [j for j in range(N) if d[j] < 2 * r + 20 and j != a2]     # :446-447 (own centres)
             full = (-np.pi, np.pi)
-            src = base_source_data(a2, st["x"], st["y"], r, st["theta"], vicinity, [], cfg, fov=full)
+            src = base_source_data(a2, st["x"], st["y"], r, st["theta"], vicinity, [], c2, fov=full)
             if cfg.visual_exclusion:
                 src = base_occlude(src)
-            field = base_fill(src, cfg, fov=full)                                 # :449 (binary part)
+            field = base_fill(src, c2, fov=full)                                  # :449 (binary part)
             last = [j for j in vicinity if not (st["x"][j] == st["x"][a2] and st["y"][j] == st["y"][a2])]
             amp = 1.0
             if last:                      # leaked loop variable of projection_field (agent.py:526-528, :590): the distance
                 j = last[-1]              # with BOTH centres formed with the focal radius
                 dl = np.sqrt(((st["x"][j] + r) - (st["x"][a2] + r)) ** 2 + ((st["y"][j] + r) - (st["y"][a2] + r)) ** 2)
-                amp = 1 - dl / cfg.vision_range
+                amp = 1 - dl / c2.vision_range
             left = amp * field[0:h].sum() / h
             right = amp * field[h:].sum() / (R - h)
             D = np.sign(left - right)

@@ -67,7 +67,7 @@ def run_reference(cfg, st, dth):
             a.update(cp)
         finally:
             np.random.uniform = orig
-        fields[i] = a.soc_v_field > 0
+        fields[i, :len(a.soc_v_field)] = a.soc_v_field > 0     # (own v_field_res <= cfg.R: heterogeneous agents)
         vals = dict(x=a.position[0], y=a.position[1], theta=a.orientation, vel=a.velocity, w=a.w, u=a.u,
                     I_priv=a.I_priv, override=ov[a.overriding_mode], mode=md[a.mode],
                     collected_before=a.collected_r_before)

@@ -85,7 +85,8 @@ def load_base_hetero_cases(fixture="base_hetero_golden.npz"):
     parameters went through the reference's own constructor (agent.py:83-108).  ``agent_cfgs``: one
     BaseConfig per agent; ``agent_params``: dict name -> (N,) array.  With
     fixture="base_hetero_radius_golden.npz" (make_golden_hetero_radius.py, oracle-only) the state's radius is
-    the (N,) array of the agents' own radii."""
+    the (N,) array of the agents' own radii; with "base_hetero_res_golden.npz" (make_golden_hetero_res.py) every
+    agent's BaseConfig has its own R and the fields are padded with zeros up to cfg.R."""
     import dataclasses
     from oracle import restate_base as rb
     z = np.load(os.path.join(GOLDEN, fixture))
@@ -103,7 +104,9 @@ def load_base_hetero_cases(fixture="base_hetero_golden.npz"):
         agent_params = {k: tab[:, j] for j, k in enumerate(keys)}
         agent_cfgs = []
         for i in range(tab.shape[0]):
-            kw = {k: float(agent_params[k][i]) for k in keys if k not in ("agent_fov", "agent_radius")}
+            kw = {k: float(agent_params[k][i]) for k in keys if k not in ("agent_fov", "agent_radius", "v_field_res")}
+            if "v_field_res" in agent_params:                                                   # sims.py:507
+                kw["R"] = int(agent_params["v_field_res"][i])
             f = float(agent_params["agent_fov"][i])
             agent_cfgs.append(dataclasses.replace(cfg, fov=(-f * np.pi, f * np.pi), **kw))      # sims.py:506
         st = {k: z[p + "st_" + k] for k in BASE_STATE_KEYS}

@@ -591,6 +591,80 @@ def test_agent_phase_matches_reference_fixture_heterogeneous_radii(built_lib, ca
     eng.close()
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["one_cta_per_replicate", "warp_per_agent"])
+@pytest.mark.parametrize("case", load_base_hetero_cases("base_hetero_res_golden.npz"),
+                         ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_agent_phase_matches_reference_fixture_heterogeneous_resolutions(built_lib, case, fused, monkeypatch):
+    """v_field_res of agent_behave_param_list (sims.py:507) in the kernels (abm_base_set_agent_resolution): every agent's
+    own linspace grid, projected size, wrap-around and field means (agent.py:58, 480-481, 543, 577-588;
+    supcalc.py:86-91) -- against the fixture the unmodified reference's constructor path produced, in the fused
+    kernel and in the one-grid-per-phase kernels."""
+    if not fused:
+        monkeypatch.setenv("ABM_BASE_SEPARATE_PHASES", "1")
+    cfg, st = case["cfg"], case["st"]
+    N = len(case["dth"])
+    eng = _engine_for(cfg, 1, N)
+    geo = ("agent_fov", "vision_range", "v_field_res")
+    eng.set_params(exp_theta_min=cfg.exp_theta_min, exp_theta_max=cfg.exp_theta_max, reloc_theta_max=cfg.reloc_theta_max,
+                   **{k: v[None] for k, v in case["agent_params"].items() if k not in geo})
+    eng.set_agent_geometry(agent_fov=case["agent_params"]["agent_fov"][None],
+                           vision_range=case["agent_params"]["vision_range"][None])
+    res = case["agent_params"]["v_field_res"].astype(int)
+    eng.set_agent_resolution(res[None])
+    _upload(eng, st)
+    eng.step(1, inject_dtheta=case["dth"], phases=PHASE_AGENTS)
+    fields = eng.fields()[0]
+    assert np.array_equal(rs.pack_bits(fields), case["fields"])                   # bit-exact stored fields
+    assert all(not fields[i, r:].any() for i, r in enumerate(res))
+    _compare_agents(eng.get_agents(), case["out"])
+    eng.set_agent_resolution(None)                                                # back to one resolution: different fields
+    _upload(eng, st)
+    eng.step(1, inject_dtheta=case["dth"], phases=PHASE_AGENTS)
+    assert not np.array_equal(rs.pack_bits(eng.fields()[0]), case["fields"])
+    with pytest.raises(Exception):
+        eng.set_agent_resolution(np.full((1, N), cfg.R + 1))                      # beyond the row stride
+    eng.close()
+
+
+def test_collision_lidar_uses_the_hit_agents_own_resolution(built_lib):
+    """sims.py:449-462: the proximity field of the hit agent is ITS projection_field (own v_field_res): left / right
+    means and the frontal +-100 bins -- against the oracle with one BaseConfig per agent."""
+    import dataclasses
+    rng = np.random.default_rng(77)
+    B, N, W = 2, 40, 260.0
+    cfg = rb.BaseConfig(R=1200, width=W, height=W, visual_exclusion=True, teleport_exploit=True, exp_vel_max=2.0)
+    res = rng.choice([1200, 700, 333, 150], (B, N))
+    states = []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 0, 0, 1], N); st["mode"] = np.where(st["override"] == 1, 1, 0)
+        states.append(st)
+    eng = _engine_for(cfg, B, N, 0, collide_agents=True, ghost_mode=False, regenerate_patches=False)
+    eng.set_agent_resolution(res)
+    stacked = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    eng.set_agents(x=stacked["x"], y=stacked["y"], theta=stacked["theta"], vel=stacked["vel"], w=stacked["w"],
+                   u=stacked["u"], collected=stacked["collected"], collected_before=stacked["collected_before"],
+                   env_status=stacked["env_status"], override_mode=stacked["override"], mode=stacked["mode"],
+                   patch_id=stacked["patch_id"], novelty=stacked["novelty"])
+    eng.step(1, phases=4)                                                         # the collision phase alone
+    got = eng.get_agents()
+    n_coll, n_differs = 0, 0
+    for b in range(B):
+        def run(agent_cfgs):
+            st = {k: (np.array(v, dtype=float) if k in ("theta", "vel", "x", "y") else np.array(v)) for k, v in states[b].items()}
+            collided = rb.base_collision_phase(st, cfg, False, agent_cfgs=agent_cfgs)
+            return st, collided
+        st, collided = run([dataclasses.replace(cfg, R=int(r)) for r in res[b]])
+        st_same, _ = run(None)
+        n_coll += len(set(collided))
+        n_differs += int(np.sum(st["theta"] != st_same["theta"]) + np.sum(st["vel"] != st_same["vel"]))
+        np.testing.assert_allclose(got["theta"][b], st["theta"], rtol=RTOL, atol=1e-5)
+        np.testing.assert_allclose(got["vel"][b], st["vel"], rtol=RTOL, atol=1e-5)
+        assert np.array_equal(got["override_mode"][b], st["override"].astype(int))
+    assert n_coll > 6 and n_differs > 0          # ... and one shared resolution gives other turns / stops
+    eng.close()
+
+
 @pytest.mark.parametrize("ghost,vis_excl", [(True, False), (False, True)])
 def test_env_and_collision_phases_with_per_agent_radii(built_lib, ghost, vis_excl):
     """The agents' own radii in the patch membership / bias / teleport (sims.py:45-56, 544-552, 820-821) and in the

@@ -92,6 +92,28 @@ def test_simulation_facade_heterogeneous_agents(built_lib):
     assert np.allclose(v[explore], np.broadcast_to(vmax, v.shape)[explore], rtol=1e-6)   # own max_exp_vel
 
 
+def test_simulation_facade_per_agent_resolution_and_radius(built_lib):
+    """v_field_res and agent_radius of agent_behave_param_list (sims.py:502, 507): the engine's resolution is the
+    largest, every agent view has its own field length and radius."""
+    from abm_b200.simulation import Simulation
+    N = 9
+    plist = [_behave_template(v_field_res=[1200, 640, 333][i % 3], agent_radius=[10, 6, 14][i % 3], Eps_w=2.0,
+                              agent_fov=1.0, vision_range=2000) for i in range(N)]
+    sim = Simulation(N=N, T=60, v_field_res=320, width=300, height=300, N_resc=2, patch_radius=40,
+                     min_resc_perpatch=500, max_resc_perpatch=-1, min_resc_quality=0.25, max_resc_quality=-1,
+                     visual_exclusion=True, teleport_exploit=False, allow_border_patch_overlap=True,
+                     collide_agents=True, n_replicates=4, seed=5, agent_behave_param_list=plist)
+    assert sim.engine.R == 1200 and list(sim.agent_res_list[:3]) == [1200, 640, 333]
+    sim.start()
+    a = sim.engine.get_agents()
+    assert np.isfinite(a["x"]).all() and np.isfinite(a["w"]).all()
+    assert [len(ag.soc_v_field) for ag in sim.agents[:3]] == [1200, 640, 333]
+    assert [ag.radius for ag in sim.agents[:3]] == [10.0, 6.0, 14.0]
+    f = sim.engine.fields()
+    for i in range(N):
+        assert not f[:, i, plist[i]["v_field_res"]:].any()
+
+
 def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
     """the generated env files run as ONE replicate batch, and every replicate leaves what the reference's
     sequential run of its env file leaves on disk (metarunner.py:168-254, ifdb_params.py:34-40, ifdb.py:435-535,

@@ -84,15 +84,17 @@ def test_tunable_requires_values():
 
 
 def test_simulation_facade_rejects_per_agent_geometry():
-    """agent_behave_param_list (sims.py:499-517): per-agent decision parameters, FOV, vision range and radius are
-    supported, per-agent resolution / Tau are refused loudly, before any engine is created."""
+    """agent_behave_param_list (sims.py:499-517): per-agent decision parameters, FOV, vision range, radius and
+    resolution are supported, a per-agent Tau / pooling is refused loudly, before any engine is created."""
     from abm_b200.simulation import Simulation
     base = dict(S_wu=0, T_w=0.5, Eps_w=0, g_w=0.085, B_w=0, w_max=1, Tau=10, S_uw=0, T_u=0.5, Eps_u=3, g_u=0.085,
                 B_u=0, u_max=1, F_N=2, F_R=1, exp_vel_max=3, exp_stop_ratio=0.15, agent_radius=10, v_field_res=1200,
                 pooling_time=0, pooling_prob=0, agent_consumption=1, vision_range=2000, agent_fov=0.9)
     plist = [dict(base, v_field_res=1200 if i else 600) for i in range(4)]
-    with pytest.raises(NotImplementedError, match="v_field_res"):
-        Simulation(N=4, T=10, agent_behave_param_list=plist)
+    radius, res, radii, res_list = Simulation._check_behave_params(plist, 4, 10, 800, 10)
+    assert (radius, res, radii) == (10, 1200, None) and list(res_list) == [600, 1200, 1200, 1200]
+    with pytest.raises(NotImplementedError, match="POOLING"):
+        Simulation(N=4, T=10, agent_behave_param_list=[dict(base, pooling_time=3)] * 4)
     with pytest.raises(ValueError):
         Simulation(N=5, T=10, agent_behave_param_list=plist)
     with pytest.raises(NotImplementedError, match="Tau"):

@@ -1,6 +1,8 @@
 """CPU tests: the BASE oracle (oracle/restate_base.py) against SURVEY KAT-B1, against fixtures
 produced by executing the unmodified reference's Agent.update (tests/golden/base_golden.npz)
 and, when /root/reference is mounted, the reference's own notify / deplete / bias functions."""
+import dataclasses
+
 import numpy as np
 import pytest
 
@@ -77,6 +79,25 @@ def test_restatement_matches_reference_fixture_heterogeneous_radii(case):
         np.testing.assert_allclose(out[k], case["out"][k], rtol=1e-12, atol=1e-12, err_msg=k)
     # one shared radius does not reproduce it
     shared = rb.base_step_frozen(dict(case["st"], radius=10.0), case["cfg"], case["dth"], agent_cfgs=case["agent_cfgs"])
+    assert not np.array_equal(rs.pack_bits(shared["fields"]), case["fields"])
+
+
+@pytest.mark.parametrize("case", load_base_hetero_cases("base_hetero_res_golden.npz"),
+                         ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
+def test_restatement_matches_reference_fixture_heterogeneous_resolutions(case):
+    """v_field_res of agent_behave_param_list (sims.py:507): every agent's own linspace grid, projection size, wrap and
+    field means (agent.py:58, 480-481, 543, 577-588; supcalc.py:86-91), fields padded with zeros up to cfg.R."""
+    res = [c.R for c in case["agent_cfgs"]]
+    assert len(set(res)) > 2 and max(res) == case["cfg"].R
+    out = rb.base_step_frozen(case["st"], case["cfg"], case["dth"], agent_cfgs=case["agent_cfgs"])
+    assert np.array_equal(rs.pack_bits(out["fields"]), case["fields"])
+    for k in BASE_OUT_KEYS:
+        np.testing.assert_allclose(out[k], case["out"][k], rtol=1e-12, atol=1e-12, err_msg=k)
+    for i, r in enumerate(res):
+        assert not out["fields"][i, r:].any()
+    # one shared resolution does not reproduce it
+    same = [dataclasses.replace(c, R=case["cfg"].R) for c in case["agent_cfgs"]]
+    shared = rb.base_step_frozen(case["st"], case["cfg"], case["dth"], agent_cfgs=same)
     assert not np.array_equal(rs.pack_bits(shared["fields"]), case["fields"])
 
 
