@@ -87,6 +87,8 @@ void build_grid(int R, GridConsts& g) {
 
 }  // namespace
 
+constexpr int kMaxChunks = 16;
+
 struct abm_engine {
   abm_vf_config_t cfg;
   int device = 0;
@@ -146,6 +148,11 @@ struct abm_engine {
   int bbox_tile[2] = {0, 0};     // records per tile the boxes were computed for
   DevBuf<float> metrics;      // abm_vf_metrics staging (allocated on first use)
   DevBuf<float> tile_cull2;
+  // abm_vf_step_host: replicate chunks pipelined over two copy streams
+  int chunk_b0 = 0, chunk_nb = 0;          // replicates [b0, b0 + nb) of the step launches (nb == 0: all)
+  cudaStream_t io_stream[3] = {nullptr, nullptr, nullptr};  // host -> device, device -> host, second compute stream
+  cudaEvent_t io_in[kMaxChunks] = {}, io_step[kMaxChunks] = {}, io_out[kMaxChunks] = {}, io_fence = nullptr;
+  bool io_out_pending[kMaxChunks] = {};    // a device -> host copy of staging region c may still be running
 };
 
 namespace {
@@ -301,6 +308,16 @@ int abm_vf_create(const abm_vf_config_t* cfg, int device, abm_engine_t** out) {
 }
 
 int abm_destroy(abm_engine_t* e) {
+  if (e) {
+    cudaSetDevice(e->device);
+    for (int k = 0; k < 3; ++k) if (e->io_stream[k]) { cudaStreamSynchronize(e->io_stream[k]); cudaStreamDestroy(e->io_stream[k]); }
+    for (int c = 0; c < kMaxChunks; ++c) {
+      if (e->io_in[c]) cudaEventDestroy(e->io_in[c]);
+      if (e->io_step[c]) cudaEventDestroy(e->io_step[c]);
+      if (e->io_out[c]) cudaEventDestroy(e->io_out[c]);
+    }
+    if (e->io_fence) cudaEventDestroy(e->io_fence);
+  }
   if (!e) return ABM_OK;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
@@ -718,7 +735,20 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       }
     }
     e->host_synced = false;
-    if (use_sym) abm::launch_vf_step_sym(a, wide3, st);
+    if (e->chunk_nb > 0) {   // abm_vf_step_host: this call steps the replicates [b0, b0 + nb) only
+      if (!use_sym) return fail(ABM_E_STATE, "abm_vf_step: replicate chunks need the symmetric kernel");
+      abm::VFKernelArgs c = a;
+      const size_t o = (size_t)e->chunk_b0 * a.N;
+      c.B = e->chunk_nb;
+      c.rec_in += o; c.rec_out += o; c.theta += o; c.vel += o;
+      if (c.ov_alp0) c.ov_alp0 += o;
+      if (c.ov_bet0) c.ov_bet0 += o;
+      if (c.ov_v0) c.ov_v0 += o;
+      c.params += (size_t)e->chunk_b0 * a.param_stride;
+      if (c.fields_out) c.fields_out += o * a.W;
+      if (c.terms_out) c.terms_out += o * 6;
+      abm::launch_vf_step_sym(c, wide3, st);
+    } else if (use_sym) abm::launch_vf_step_sym(a, wide3, st);
     else if (use_warp) abm::launch_vf_step_warp(a, cull, uniform_r, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
     if (e->n_peers > 0 && !fused_close) { abm::launch_vf_publish(a, st); ++e->launches; }
@@ -735,6 +765,119 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     ++e->launches;
     ++e->steps_done;
   }
+  ABM_CUDA(cudaGetLastError());
+  return ABM_OK;
+}
+
+// Would abm_vf_step run the symmetric kernel (one CTA per replicate) on the whole batch?  Then replicate chunks can be
+// stepped independently.  Mirrors the kernel choice of abm_vf_step; needs the radii's min / max on the host.
+static bool vf_chunkable(const abm_engine* e) {
+  if (!e->radius_known || e->r_min != e->r_max) return false;
+  if (e->tile_count != e->cfg.n_agents || e->n_peers > 0 || getenv("ABM_VF_KERNEL")) return false;
+  if (e->sort_enabled && !e->perm_identity) return false;
+  const GridConsts& g = e->grid;
+  const int B = e->cfg.n_replicates, N = e->cfg.n_agents;
+  const double d_cull = (double)e->r_max * std::sqrt((double)g.cull_scale);
+  if (ABM_PI_D * d_cull * d_cull < 0.5 * (double)e->cfg.width * (double)e->cfg.height) return false;   // culling: warp kernel
+  abm::VFKernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.W = g.W; a.tile_begin = 0; a.tile_count = N;
+  if (!abm::vf_sym_applicable(a, true, false, e->smem_optin)) return false;
+  const int Np = (N + 63) / 64 * 64;
+  const size_t smem = abm::vf_sym_smem_bytes(Np, g.W, false);
+  const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
+  const double agents = (double)B * N, pairs = agents * (N - 1);
+  const double t_warp = 10.0 + 1.2e-3 * agents + 4.0e-6 * pairs;
+  const double t_cta = std::ceil((double)B / ((double)e->n_sms * resident)) * (45.0 + 0.05 * Np + 1.6e-4 * (double)Np * Np);
+  return !(t_warp < 0.9 * t_cta);
+}
+
+int abm_vf_step_host(abm_engine_t* e, const float* xytv_in, float* xytv_out, int n_steps, void* stream) {
+  if (!e || !xytv_in || !xytv_out) return fail(ABM_E_INVALID, "abm_vf_step_host: null argument");
+  if (!e->state_set)
+    return fail(ABM_E_STATE, "abm_vf_step_host: needs an earlier abm_set_state / abm_set_state_packed that passed the radii");
+  if (n_steps < 0) return fail(ABM_E_INVALID, "abm_vf_step_host: n_steps < 0");
+  ABM_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = e->cfg.n_replicates, N = e->cfg.n_agents;
+  // ---- chunks: about two waves of resident CTAs each, a small first one (its upload is exposed) and a small last one
+  //      (its download is).  Consecutive chunks step on two alternating streams, so the CTAs of chunk c + 1 fill the SMs
+  //      that the tail of chunk c leaves idle: the chunks need not be whole waves ----
+  int bounds[kMaxChunks + 1];
+  int n_chunks = 1;
+  bounds[0] = 0; bounds[1] = B;
+  if (!getenv("ABM_VF_HOST_ONE_CHUNK") && vf_chunkable(e)) {
+    const int Np = (N + 63) / 64 * 64;
+    const size_t smem = abm::vf_sym_smem_bytes(Np, e->grid.W, false);
+    const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
+    const int wave = e->n_sms * resident;
+    if (B >= 3 * wave) {
+      const int edge = std::max(1, wave / 2);
+      const int mid_total = B - 2 * edge;
+      const int n_mid = std::min(kMaxChunks - 2, std::max(1, (mid_total + wave) / (2 * wave)));
+      n_chunks = 0;
+      bounds[0] = 0;
+      bounds[++n_chunks] = edge;
+      for (int k = 1; k <= n_mid; ++k) bounds[++n_chunks] = edge + (int)((long long)mid_total * k / n_mid);
+      bounds[++n_chunks] = B;
+    }
+  }
+  if (n_chunks == 1) {   // nothing to overlap: the plain sequence on the caller's stream
+    int rc = abm_set_state_packed(e, xytv_in, nullptr, ABM_HOST_PINNED_ASYNC, stream);
+    if (!rc) rc = abm_vf_step(e, n_steps, stream);
+    if (!rc) rc = abm_get_state_packed(e, xytv_out, ABM_HOST_PINNED_ASYNC, stream);
+    return rc;
+  }
+  if (!e->io_stream[0]) {
+    for (int k = 0; k < 3; ++k) ABM_CUDA(cudaStreamCreateWithFlags(&e->io_stream[k], cudaStreamNonBlocking));
+    for (int c = 0; c < kMaxChunks; ++c) {
+      ABM_CUDA(cudaEventCreateWithFlags(&e->io_in[c], cudaEventDisableTiming));
+      ABM_CUDA(cudaEventCreateWithFlags(&e->io_step[c], cudaEventDisableTiming));
+      ABM_CUDA(cudaEventCreateWithFlags(&e->io_out[c], cudaEventDisableTiming));
+    }
+    ABM_CUDA(cudaEventCreateWithFlags(&e->io_fence, cudaEventDisableTiming));
+  }
+  if (!e->stage4.p) ABM_CUDA(e->stage4.alloc(e->n_total));
+  // the uploads may start once everything enqueued on the caller's stream so far has run (an earlier step / download
+  // may still use the staging array), and once the previous call's downloads have left it
+  ABM_CUDA(cudaEventRecord(e->io_fence, st));
+  ABM_CUDA(cudaStreamWaitEvent(e->io_stream[0], e->io_fence, 0));
+  ABM_CUDA(cudaStreamWaitEvent(e->io_stream[2], e->io_fence, 0));
+  for (int c = 0; c < kMaxChunks; ++c)
+    if (e->io_out_pending[c]) { ABM_CUDA(cudaStreamWaitEvent(e->io_stream[0], e->io_out[c], 0)); e->io_out_pending[c] = false; }
+  const int cur0 = e->cur;
+  const uint32_t steps0 = e->steps_done;
+  const int since0 = e->steps_since_sort;
+  const int wide0 = e->wide_steps_left;
+  const float4* in4 = reinterpret_cast<const float4*>(xytv_in);
+  float4* out4 = reinterpret_cast<float4*>(xytv_out);
+  int rc = ABM_OK;
+  for (int c = 0; c < n_chunks && !rc; ++c) {
+    const int b0 = bounds[c], nb = bounds[c + 1] - b0;
+    const size_t o = (size_t)b0 * N, n = (size_t)nb * N;
+    cudaStream_t cs = (c & 1) ? e->io_stream[2] : st;
+    ABM_CUDA(cudaMemcpyAsync(e->stage4.p + o, in4 + o, sizeof(float4) * n, cudaMemcpyHostToDevice, e->io_stream[0]));
+    ABM_CUDA(cudaEventRecord(e->io_in[c], e->io_stream[0]));
+    ABM_CUDA(cudaStreamWaitEvent(cs, e->io_in[c], 0));
+    abm::launch_pack_state4(e->stage4.p + o, e->radius_api.p + o, nullptr, N, e->grid.cull_scale, e->rec[cur0].p + o,
+                            e->theta.p + o, e->vel.p + o, nullptr, (long long)n, cs);
+    e->cur = cur0; e->steps_done = steps0; e->steps_since_sort = since0; e->wide_steps_left = wide0;
+    e->chunk_b0 = b0; e->chunk_nb = nb;
+    rc = abm_vf_step(e, n_steps, cs);
+    e->chunk_nb = 0; e->chunk_b0 = 0;
+    if (rc) break;
+    abm::launch_unpack_state4(e->rec[e->cur].p + o, e->theta.p + o, e->vel.p + o, nullptr, N, e->stage4.p + o, (long long)n, cs);
+    ABM_CUDA(cudaEventRecord(e->io_step[c], cs));
+    ABM_CUDA(cudaStreamWaitEvent(e->io_stream[1], e->io_step[c], 0));
+    ABM_CUDA(cudaMemcpyAsync(out4 + o, e->stage4.p + o, sizeof(float4) * n, cudaMemcpyDeviceToHost, e->io_stream[1]));
+    ABM_CUDA(cudaEventRecord(e->io_out[c], e->io_stream[1]));
+    e->io_out_pending[c] = true;
+  }
+  if (rc) return rc;
+  e->bbox_valid[0] = e->bbox_valid[1] = false;
+  e->host_synced = false;
+  // stream-ordered for the caller: work enqueued on `stream` after this call (and abm_synchronize) sees the downloads done
+  ABM_CUDA(cudaStreamWaitEvent(st, e->io_out[n_chunks - 1], 0));
   ABM_CUDA(cudaGetLastError());
   return ABM_OK;
 }

@@ -228,6 +228,19 @@ class VFEngine:
     def step(self, n_steps: int = 1):
         _lib.check(self._lib.abm_vf_step(self._h, int(n_steps), C.c_void_p(_current_stream())), "abm_vf_step")
 
+    def step_host(self, xytv_in, xytv_out, n_steps: int = 1):
+        """Upload the (B, N, 4) float32 state ``xytv_in``, run ``n_steps`` steps, download the new state into ``xytv_out``
+        -- one call (abm_vf_step_host) that does not block: both arrays must be PINNED host memory (e.g. the numpy view
+        of a ``torch.empty(..., pin_memory=True)``) and stay alive until ``synchronize()``.  Large batches go through in
+        replicate chunks whose copies overlap the other chunks' steps.  The radii are those of an earlier
+        ``set_state`` / ``set_state_packed``."""
+        total = 4 * self.B * self.N
+        for a in (xytv_in, xytv_out):
+            if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != total:
+                raise ValueError("step_host: arrays must be C-contiguous float32 of shape (B, N, 4)")
+        _lib.check(self._lib.abm_vf_step_host(self._h, C.c_void_p(xytv_in.ctypes.data), C.c_void_p(xytv_out.ctypes.data),
+                                              int(n_steps), C.c_void_p(_current_stream())), "abm_vf_step_host")
+
     def synchronize(self):
         _lib.check(self._lib.abm_synchronize(self._h, C.c_void_p(_current_stream())), "abm_synchronize")
 

@@ -539,47 +539,56 @@ def main():
         # region; the copy engines move two batches while the SMs step the third (ABM_HOST_PINNED_ASYNC calls).
         hr = torch.from_numpy(rad).pin_memory().numpy()
         NB = int(os.environ.get('ABM_E2E_BATCHES', '3'))
-        extra = [VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank) for _ in range(NB - 1)]
-        for e_ in extra:
-            e_.set_params(**PARAMS)
-        engs = [eng] + extra
-        streams = [torch.cuda.Stream() for _ in range(NB)]
+        e2e_api = os.environ.get('ABM_E2E_API', 'step_host')
         # ONE interleaved pinned buffer (x, y, theta, vel per agent) per direction and batch: one copy each way per step
         packed0 = np.ascontiguousarray(np.stack([x, y, th, v], axis=-1))
-        hosts = [[torch.from_numpy(packed0.copy()).pin_memory().numpy() for _ in range(2)] for _ in range(NB)]
-        e2e_steps = NB * max(2, min(args.steps, 60) // NB)            # batch-steps, round robin over the batches
-        cur = [0] * NB
 
-        def batch_step(k, first=False):
-            with torch.cuda.stream(streams[k]):
-                # H2D of the step's inputs; the radii are constants of the run, uploaded with the first call
-                engs[k].set_state_packed(hosts[k][cur[k]], hr if first else None, nonblocking=True)
-                engs[k].step(1)
-                engs[k].get_state_packed(hosts[k][cur[k] ^ 1], nonblocking=True)   # D2H of the step's result
-                cur[k] ^= 1
+        def e2e_arm(nb):
+            extra = [VFEngine(B, N, resolution=R, width=W, height=W, device=local_rank) for _ in range(nb - 1)]
+            for e_ in extra:
+                e_.set_params(**PARAMS)
+            engs = [eng] + extra
+            streams = [torch.cuda.Stream() for _ in range(nb)]
+            hosts = [[torch.from_numpy(packed0.copy()).pin_memory().numpy() for _ in range(2)] for _ in range(nb)]
+            n_steps = nb * max(2, min(args.steps, 60) // nb)            # batch-steps, round robin over the batches
+            cur = [0] * nb
 
-        torch.cuda.synchronize()
-        for k in range(NB):
-            batch_step(k, first=True); batch_step(k)
-        torch.cuda.synchronize()
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for k in range(NB):
-            streams[k].wait_event(e0)
-        t_host0 = time.perf_counter()
-        for it in range(e2e_steps):
-            batch_step(it % NB)
-        t_host_enqueue = time.perf_counter() - t_host0
-        for k in range(NB):
-            done = torch.cuda.Event(); done.record(streams[k]); torch.cuda.current_stream().wait_event(done)
-        e1.record()
-        barrier()
-        for j in range(NB):                                            # every batch came back whole
-            assert np.isfinite(hosts[j][cur[j]]).all()
-        for e_ in extra:
-            e_.close()
-        e2e_ms = e0.elapsed_time(e1)
+            def batch_step(k, first=False):
+                with torch.cuda.stream(streams[k]):
+                    # H2D of the step's inputs; the radii are constants of the run, uploaded with the first call
+                    if first or e2e_api != 'step_host':
+                        engs[k].set_state_packed(hosts[k][cur[k]], hr if first else None, nonblocking=True)
+                        engs[k].step(1)
+                        engs[k].get_state_packed(hosts[k][cur[k] ^ 1], nonblocking=True)   # D2H of the step's result
+                    else:   # the same three in one call; replicate chunks pipelined over the engine's copy streams
+                        engs[k].step_host(hosts[k][cur[k]], hosts[k][cur[k] ^ 1], 1)
+                    cur[k] ^= 1
+
+            torch.cuda.synchronize()
+            for k in range(nb):
+                batch_step(k, first=True); batch_step(k)
+            torch.cuda.synchronize()
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(nb):
+                streams[k].wait_event(e0)
+            t_host0 = time.perf_counter()
+            for it in range(n_steps):
+                batch_step(it % nb)
+            t_enq = time.perf_counter() - t_host0
+            for k in range(nb):
+                done = torch.cuda.Event(); done.record(streams[k]); torch.cuda.current_stream().wait_event(done)
+            e1.record()
+            barrier()
+            for j in range(nb):                                            # every batch came back whole
+                assert np.isfinite(hosts[j][cur[j]]).all()
+            for e_ in extra:
+                e_.close()
+            return e0.elapsed_time(e1), n_steps, t_enq
+
+        e2e1_ms, e2e1_steps, _ = e2e_arm(1)                              # one batch in flight (reported beside the headline)
+        e2e_ms, e2e_steps, t_host_enqueue = e2e_arm(NB) if NB > 1 else (e2e1_ms, e2e1_steps, _)
     clocks = sampler.summary()
     counters = eng.counters()
     timed_kernel = eng.last_kernel()
@@ -609,10 +618,10 @@ def main():
     if world == 1 and os.environ.get("ABM_BENCH_OTHER_CONFIGS", "1") != "0":
         others = other_configs_arm(VFEngine, local_rank, measured_peaks()[0])
 
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_ms, e2e1_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = (float(v) for v in t.tolist())
+    total_ms, e2e_ms, e2e1_ms = (float(v) for v in t.tolist())
     agents_total = B * N * world
     value = agents_total * args.steps / (total_ms * 1e-3)
     e2e_value = agents_total * e2e_steps / (e2e_ms * 1e-3)
@@ -638,9 +647,15 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * 4 * B * N),
                     "d2h_bytes_per_step": int(4 * 4 * B * N), "steps": e2e_steps,
                     "host_enqueue_s": t_host_enqueue, "device_s": e2e_ms * 1e-3,
-                    "api": "VFEngine.set_state_packed -> step -> get_state_packed (abm_set_state_packed / abm_vf_step / "
-                           "abm_get_state_packed, ABM_HOST_PINNED_ASYNC): one pinned (x, y, theta, vel) array per direction",
-                    "pipeline": "%d batches in flight (one engine, stream and pair of pinned buffers each): copies overlap the other batches' steps" % NB},
+                    "api": ("VFEngine.step_host (abm_vf_step_host: upload, step, download in one non-blocking call; replicate "
+                            "chunks of whole CTA waves, copies on the engine's two copy streams overlap the other chunks' steps)"
+                            if e2e_api == 'step_host' else
+                            "VFEngine.set_state_packed -> step -> get_state_packed (abm_set_state_packed / abm_vf_step / "
+                            "abm_get_state_packed, ABM_HOST_PINNED_ASYNC)") + ": one pinned (x, y, theta, vel) array per direction",
+                    "pipeline": "%d batches in flight (one engine, stream and pair of pinned buffers each): copies overlap the "
+                                "other batches' steps, and their CTAs fill each other's tail waves (which is why this can exceed "
+                                "`value`, measured on ONE batch with an L2 flush between steps)" % NB,
+                    "one_batch_in_flight": agents_total * e2e1_steps / (e2e1_ms * 1e-3)},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": ops_launch / avg_s / 1e12, "peak": peak_ops / 1e12,
                          "unit": "Tlaneop/s", "frac": ops_launch / avg_s / peak_ops,

@@ -145,6 +145,18 @@ int abm_get_state_packed(abm_engine_t* e, float* xytv, int on_device, void* stre
  * VFAgent.update (vf_agent.py:52-80) for every agent of every replicate. */
 int abm_vf_step(abm_engine_t* e, int n_steps, void* stream);
 
+/* The host-driven loop of the reference in ONE call: upload the state (xytv_in, as abm_set_state_packed with radius ==
+ * NULL: an earlier call passed the radii), n_steps steps, download the new state (xytv_out, as abm_get_state_packed).
+ * Both arrays must be PINNED host memory (ABM_HOST_PINNED_ASYNC semantics: the call does not block; xytv_in may be
+ * reused and xytv_out read after abm_synchronize(e, stream), or after any later work on `stream`).  When the batch runs
+ * the symmetric kernel (a CTA per replicate) and is at least three waves of CTAs, the replicates go through in chunks of
+ * whole waves: the upload of chunk c + 1 and the download of chunk c - 1 overlap the steps of chunk c on two copy
+ * streams of the engine, so that one batch in flight already hides the PCIe time (only the first chunk's upload and the
+ * last chunk's download are exposed).  Results are identical to the three separate calls.
+ * Replaces: the per-step read of agent.position / orientation / velocity around VFSimulation.step_sim
+ * (vf_sims.py:291-302) for a caller that keeps its agents on the host. */
+int abm_vf_step_host(abm_engine_t* e, const float* xytv_in, float* xytv_out, int n_steps, void* stream);
+
 /* Packed STORED fields of the last step, n_replicates*tile*abm_field_words(R) words
  * (needs ABM_VF_KEEP_FIELDS).  Replaces reading Agent.soc_v_field (vf_agent.py:209).
  * Row order: the caller's agent order for an engine that owns whole replicates.  A TILED engine (tile_count != 0)

@@ -624,6 +624,47 @@ def test_set_state_keeps_radii_when_omitted(built_lib):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("B,N,chunked", [(450, 1024, True), (40, 128, False), (1, 3000, False)],
+                         ids=["chunks_of_whole_waves", "one_chunk", "large_sparse_swarm"])
+def test_step_host_matches_the_three_calls(built_lib, B, N, chunked):
+    """abm_vf_step_host (upload, steps, download in one non-blocking call; the replicates of a large batch go through in
+    chunks whose copies overlap the other chunks' steps) against set_state_packed -> step -> get_state_packed: the same
+    bits out, the same fields and terms kept, repeated calls feeding the output back in."""
+    import torch
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(41)
+    W = {3000: 9000.0, 1024: 2880.0}.get(N, 700.0)
+    x, y, th, v = _random_scene(rng, B, N, W)
+    packed = np.ascontiguousarray(np.stack([x, y, th, v], axis=-1))
+    ea = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True, keep_terms=True)
+    eb = VFEngine(B, N, resolution=1200, width=W, height=W, keep_fields=True, keep_terms=True)
+    for e in (ea, eb):
+        e.set_params()
+        e.set_state_packed(packed, 10.0)           # the radii (and what the kernel choice needs of them)
+        e.step(1)
+    bufs = [torch.from_numpy(packed.copy()).pin_memory().numpy() for _ in range(2)]
+    ref = packed
+    for it in range(3):
+        n_steps = 1 + (it % 2)
+        ea.set_state_packed(ref)
+        ea.step(n_steps)
+        ref = ea.get_state_packed()
+        launches0 = eb.counters()["launches"]
+        eb.step_host(bufs[it % 2], bufs[(it + 1) % 2], n_steps)
+        eb.synchronize()
+        assert np.array_equal(bufs[(it + 1) % 2], ref), it
+        assert np.array_equal(eb.fields(), ea.fields()) and np.array_equal(eb.terms(), ea.terms())
+        n_launch = eb.counters()["launches"] - launches0
+        if chunked:
+            assert eb.last_kernel() == "abm::vf_step_sym_kernel" and n_launch > n_steps     # one launch per chunk and step
+        st = eb.get_state()
+        assert np.array_equal(st["x"], ref[..., 0]) and np.array_equal(st["vel"], ref[..., 3])
+    # (the state the engine keeps is the downloaded one: a plain step continues from it)
+    ea.step(1); eb.step(1)
+    assert np.array_equal(eb.get_state_packed(), ea.get_state_packed())
+    ea.close(); eb.close()
+
+
 @pytest.mark.parametrize("sorted_swarm", [False, True])
 def test_packed_state_matches_soa_state(built_lib, monkeypatch, sorted_swarm):
     """abm_set_state_packed / abm_get_state_packed (ONE interleaved (x, y, theta, vel) array per direction) against the
