@@ -130,6 +130,7 @@ SYMBOLS = {
     "abm_set_state_packed": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "abm_get_state_packed": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_vf_step_host": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "abm_vf_set_line_map": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P]),
     "abm_vf_step": (C.c_int, [_P, C.c_int, _P]),
     "abm_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_vf_get_terms": (C.c_int, [_P, _P, C.c_int, _P]),

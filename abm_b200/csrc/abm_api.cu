@@ -148,6 +148,10 @@ struct abm_engine {
   int bbox_tile[2] = {0, 0};     // records per tile the boxes were computed for
   DevBuf<float> metrics;      // abm_vf_metrics staging (allocated on first use)
   DevBuf<float> tile_cull2;
+  DevBuf<float> line_map;     // abm_vf_set_line_map
+  int lm_d0 = 0, lm_d1 = 0;
+  double lm_sr = 9.0, lm_sd = 20.0;
+  bool has_line_map = false;
   // abm_vf_step_host: replicate chunks pipelined over two copy streams
   int chunk_b0 = 0, chunk_nb = 0;          // replicates [b0, b0 + nb) of the step launches (nb == 0: all)
   cudaStream_t io_stream[3] = {nullptr, nullptr, nullptr};  // host -> device, device -> host, second compute stream
@@ -328,7 +332,7 @@ int abm_destroy(abm_engine_t* e) {
   e->lut.release(); e->fields.release(); e->terms.release(); e->counters.release();
   e->perm.release(); e->perm_tmp.release(); e->order.release(); e->vals_in.release(); e->offsets.release();
   e->keys_in.release(); e->keys_out.release(); e->sort_temp.release(); e->tile_bbox[0].release(); e->tile_bbox[1].release(); e->tile_cull2.release(); e->ticket.release(); e->metrics.release();
-  e->radius_minmax.release();
+  e->radius_minmax.release(); e->line_map.release();
   for (int p = 0; p < e->n_peers; ++p)
     for (int k = 0; k < 5; ++k)
       if (e->peer_maps[p][k]) cudaIpcCloseMemHandle(e->peer_maps[p][k]);
@@ -583,6 +587,8 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.lut = e->lut.p;
   a.fields_out = e->fields.p; a.terms_out = e->terms.p;
   a.counters = e->counters.p;
+  a.line_map = e->has_line_map ? e->line_map.p : nullptr;
+  a.lm_d0 = e->lm_d0; a.lm_d1 = e->lm_d1; a.lm_sr = e->lm_sr; a.lm_sd = e->lm_sd;
   if (!e->radius_known) {   // kernel variant selection needs min / max radius of the batch (once per set_state)
     unsigned mm[2];
     ABM_CUDA(cudaMemcpyAsync(mm, e->radius_minmax.p, sizeof(mm), cudaMemcpyDeviceToHost, st));
@@ -766,6 +772,26 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     ++e->steps_done;
   }
   ABM_CUDA(cudaGetLastError());
+  return ABM_OK;
+}
+
+int abm_vf_set_line_map(abm_engine_t* e, const float* map, int dim0, int dim1, double sensor_radius, double sensor_distance,
+                        int on_device, void* stream) {
+  if (!e) return fail(ABM_E_INVALID, "abm_vf_set_line_map: null engine");
+  if (!map) { e->has_line_map = false; return ABM_OK; }          // no lines: the flocking heading change again
+  if (dim0 <= 0 || dim1 <= 0) return fail(ABM_E_INVALID, "abm_vf_set_line_map: dimensions must be > 0");
+  ABM_CUDA(cudaSetDevice(e->device));
+  const size_t n = (size_t)dim0 * dim1;
+  if (!e->line_map.p || (size_t)e->lm_d0 * e->lm_d1 != n) {
+    ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));       // (a step still reading the old map)
+    e->line_map.release();
+    ABM_CUDA(e->line_map.alloc(n));
+  }
+  int rc = copy_in(e->line_map.p, map, sizeof(float) * n, on_device, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (on_device == 0) ABM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->lm_d0 = dim0; e->lm_d1 = dim1; e->lm_sr = sensor_radius; e->lm_sd = sensor_distance;
+  e->has_line_map = true;
   return ABM_OK;
 }
 

@@ -73,6 +73,10 @@ struct VFKernelArgs {
   // and the interval must fit three (symmetric kernel: h <= 32) or two (warp kernel: h <= 16) row words; also catches
   // NaN / inf (coincident centres) and the sign change of the truncated series at large q
   float sym_qs_max, sym_qs_max2, warp_qs_max;   // three-word / two-word fast path of the symmetric kernel, warp kernel
+  // line following (vf_supcalc.follow_lines_local): the rasterised line map [lm_d0][lm_d1] (first axis x) or nullptr
+  const float* line_map;
+  int lm_d0, lm_d1;
+  double lm_sr, lm_sd;            // sensor radius (VFAgent.sensor_size) and distance (vf_agent.py:30-31)
   uint32_t sym_tie32, sym_seam32; // guard bands of the binary-angle bin index, in 2^-32 bins / 2^-32 turns
   uint32_t opaque_zero;           // always 0: OR-ed into loop constants so that ptxas keeps them in registers
   int full_fov;                   // fov covers every bin: any interval with h >= 1 is visible

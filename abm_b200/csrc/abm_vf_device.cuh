@@ -661,30 +661,31 @@ __device__ __forceinline__ double limit_abs(double v, double lim) {   // vf_agen
   return (fabs(v) > lim) ? lim * sg : v;
 }
 
-// Agent.reflect_from_walls (agent.py:347-394): tests use the centre BEFORE any fix.
+// Agent.reflect_from_walls (agent.py:347-394): tests use the centre BEFORE any fix.  `turn`: pi/2 (the mirror-like rule
+// of the base class); a VFAgent that has lines to follow turns by pi instead (vf_agent.py:80-129).
 __device__ __forceinline__ void reflect_from_walls(double& x, double& y, double& th, double r,
-                                                   double width, double height, double pad) {
+                                                   double width, double height, double pad, double turn = ABM_PI_D / 2.0) {
   const double bx0 = pad, bx1 = pad + width, by0 = pad, by1 = pad + height;
   const double cx = x + r, cy = y + r;
   const double PI = ABM_PI_D, H = ABM_PI_D / 2.0, T3 = 3.0 * ABM_PI_D / 2.0, TWO = 2.0 * ABM_PI_D;
   if (cx < bx0) {
     x = bx0 - r;
-    if (H <= th && th < PI) th -= H; else if (PI <= th && th <= T3) th += H;
+    if (H <= th && th < PI) th -= turn; else if (PI <= th && th <= T3) th += turn;
     th = wrap_heading_once(th);
   }
   if (cx > bx1) {
     x = bx1 - r - 1.0;
-    if (T3 <= th && th < TWO) th -= H; else if (0.0 <= th && th <= H) th += H;
+    if (T3 <= th && th < TWO) th -= turn; else if (0.0 <= th && th <= H) th += turn;
     th = wrap_heading_once(th);
   }
   if (cy < by0) {
     y = by0 - r;
-    if (H <= th && th <= PI) th += H; else if (0.0 <= th && th < H) th -= H;
+    if (H <= th && th <= PI) th += turn; else if (0.0 <= th && th < H) th -= turn;
     th = wrap_heading_once(th);
   }
   if (cy > by1) {
     y = by1 - r - 1.0;
-    if (T3 <= th && th <= TWO) th += H; else if (PI <= th && th < T3) th -= H;
+    if (T3 <= th && th <= TWO) th += turn; else if (PI <= th && th < T3) th -= turn;
     th = wrap_heading_once(th);
   }
 }
@@ -711,6 +712,45 @@ __device__ __forceinline__ uint32_t flipped_word(const uint32_t* f, int stride, 
   const int nvalid = min(32, hi + 1);
   if (nvalid < 32) out &= (1u << nvalid) - 1u;
   return out;
+}
+
+// vf_supcalc.follow_lines_local (vf_supcalc.py:293-328): two sensors ahead-left / ahead-right of the agent read the mean of
+// the line map over a square window (numpy basic slices of int()-truncated bounds: negative bounds wrap, out-of-range
+// ones clip, an empty window gives nan and a heading change of 0); the agent steers towards the brighter sensor.
+// map: [d0][d1] as VFAgent.line_map (first axis x).  fp64 with the reference's operation order; the window sums run in
+// row order (numpy's pairwise order is not reproduced: 1e-16 relative).
+__device__ __forceinline__ void np_slice_bounds(int a, int b, int n, int& lo, int& hi) {
+  if (a < 0) a = max(a + n, 0);
+  if (b < 0) b = max(b + n, 0);
+  lo = min(a, n); hi = min(b, n);
+}
+__device__ __forceinline__ double vf_line_window_mean(const float* map, int d0, int d1, double s0, double s1, double sr) {
+  int a, b, c, d;
+  np_slice_bounds((int)(s1 - sr), (int)(s1 + sr), d0, a, b);      // :310 first axis: sensor_pos[1]
+  np_slice_bounds((int)(s0 - sr), (int)(s0 + sr), d1, c, d);      //      second axis: sensor_pos[0]
+  if (b <= a || d <= c) return __longlong_as_double(0x7ff8000000000000ll);   // empty slice: nan
+  double sum = 0.0;
+  int cnt = 0;
+  for (int i = a; i < b; ++i) {
+    const float* row = map + (size_t)i * d1;
+    for (int j = c; j < d; ++j) {
+      const float v = __ldg(row + j);
+      if (v == v) { sum += (double)v; ++cnt; }                    // nanmean
+    }
+  }
+  return cnt ? sum / (double)cnt : __longlong_as_double(0x7ff8000000000000ll);
+}
+__device__ __forceinline__ double vf_follow_lines(const VFKernelArgs& a, double x, double y, double r, double th, double vel) {
+  const double a34 = 3.0 * ABM_PI_D / 4.0, sd = a.lm_sd;
+  const double base0 = (y + r) - sd, base1 = (x + r) - sd;       // :295-302
+  const double s1_0 = base0 + (1.0 + sin(th + a34)) * sd, s1_1 = base1 + (1.0 - cos(th + a34)) * sd;
+  const double s2_0 = base0 + (1.0 + sin(th - a34)) * sd, s2_1 = base1 + (1.0 - cos(th - a34)) * sd;
+  const double m1 = vf_line_window_mean(a.line_map, a.lm_d0, a.lm_d1, s1_0, s1_1, a.lm_sr);
+  const double m2 = vf_line_window_mean(a.line_map, a.lm_d0, a.lm_d1, s2_0, s2_1, a.lm_sr);
+  if (m1 != m1 || m2 != m2) return 0.0;                          // :314-315
+  const double ori_change = (vel != 0.0) ? 0.5 * (m2 - m1) : 0.0;   // np.sign(agvel) truthy (:317-320)
+  if (m1 != m2) return ori_change;                               // :321-324
+  return (m1 != 0.0) ? 0.01 : 0.0;                               // :326-329
 }
 
 // Epilogue shared by the step kernels, K agents per thread: fold the row padding, edges + flocking integrals, heading /
@@ -748,6 +788,8 @@ __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, 
       ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
     }
     double dpsi = ft.dpsi, dvel = ft.dvel;
+    if (a.line_map)                                               // lines to follow replace the heading change (:273-276)
+      dpsi = vf_follow_lines(a, (double)me[j].x, (double)me[j].y, (double)me[j].z, (double)th[j], vel0);
     if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
     double nth = wrap_heading_once((double)th[j] + dpsi);         // :295-296
     double nv = vel0 + dvel;                                      // :298
@@ -756,7 +798,8 @@ __device__ __forceinline__ void vf_agent_epilogue(const VFKernelArgs& a, int b, 
     sincos(nth, &sn, &cn);
     double nx = (double)me[j].x + nv * cn;                        // :303-306
     double ny = (double)me[j].y - nv * sn;
-    if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me[j].z, a.width_d, a.height_d, a.pad_d);
+    if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me[j].z, a.width_d, a.height_d, a.pad_d,
+                                   a.line_map ? ABM_PI_D : ABM_PI_D / 2.0);       // vf_agent.py:80-129
     else teleport_torus(nx, ny, (double)me[j].z, a.width_d, a.height_d, a.pad_d);
 
     const float4 rec_new = make_float4((float)nx, (float)ny, me[j].z, me[j].w);

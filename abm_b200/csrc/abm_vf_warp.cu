@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
         ft.dvel = ft.dpsi = ft.a_blob = ft.a_edge = ft.b_blob = ft.b_edge = 0.0;
       }
       double dpsi = ft.dpsi, dvel = ft.dvel;
+      if (a.line_map)                                               // lines to follow replace the heading change (:273-276)
+        dpsi = vf_follow_lines(a, (double)me.x, (double)me.y, (double)me.z, (double)th, vel0);
       if (a.limit_movement) dpsi = limit_abs(dpsi, a.max_th);       // vf_agent.py:293-294
       double nth = wrap_heading_once((double)th + dpsi);            // :295-296
       double nv = vel0 + dvel;                                      // :298
@@ -339,7 +341,8 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
       sincos(nth, &sn, &cn);
       double nx = (double)me.x + nv * cn;                           // :303-306
       double ny = (double)me.y - nv * sn;
-      if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d);
+      if (!TORUS) reflect_from_walls(nx, ny, nth, (double)me.z, a.width_d, a.height_d, a.pad_d,
+                                     a.line_map ? ABM_PI_D : ABM_PI_D / 2.0);     // vf_agent.py:80-129
       else teleport_torus(nx, ny, (double)me.z, a.width_d, a.height_d, a.pad_d);
       const float4 rec_new = make_float4((float)nx, (float)ny, me.z, rep_in[i].w);
       rec_out_t[gi] = rec_new;

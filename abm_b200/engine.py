@@ -228,6 +228,20 @@ class VFEngine:
     def step(self, n_steps: int = 1):
         _lib.check(self._lib.abm_vf_step(self._h, int(n_steps), C.c_void_p(_current_stream())), "abm_vf_step")
 
+    def set_line_map(self, line_map=None, sensor_radius=9, sensor_distance=20):
+        """Lines to follow (vf_agent.py:273-276, vf_supcalc.follow_lines_local): ``line_map`` is the reference's
+        ``VFAgent.line_map``, shape (WIDTH + window_pad, HEIGHT + window_pad), values in [0, 1]; None switches line
+        following off.  Sensor defaults as VFAgent.sensor_size / sensor_distance (vf_agent.py:30-31)."""
+        if line_map is None:
+            _lib.check(self._lib.abm_vf_set_line_map(self._h, None, 0, 0, 0.0, 0.0, 0, None), "abm_vf_set_line_map")
+            return
+        m = np.ascontiguousarray(line_map, np.float32)
+        if m.ndim != 2:
+            raise ValueError("line_map must be two-dimensional")
+        _lib.check(self._lib.abm_vf_set_line_map(self._h, C.c_void_p(m.ctypes.data), m.shape[0], m.shape[1],
+                                                 float(sensor_radius), float(sensor_distance), 0,
+                                                 C.c_void_p(_current_stream())), "abm_vf_set_line_map")
+
     def step_host(self, xytv_in, xytv_out, n_steps: int = 1):
         """Upload the (B, N, 4) float32 state ``xytv_in``, run ``n_steps`` steps, download the new state into ``xytv_out``
         -- one call (abm_vf_step_host) that does not block: both arrays must be PINNED host memory (e.g. the numpy view

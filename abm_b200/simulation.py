@@ -203,6 +203,12 @@ class VFSimulation(_RunOutputs):
         """vf_sims.py:342-352."""
         self.create_agents()
 
+    def set_line_map(self, line_map=None, sensor_radius=9, sensor_distance=20):
+        """Lines for the agents to follow: what the reference's GUI leaves in every ``agent.line_map`` after lines were
+        drawn (vf_agent.py:246-260; shape (WIDTH + window_pad, HEIGHT + window_pad)); the agents then steer by
+        vf_supcalc.follow_lines_local instead of the flocking heading change (vf_agent.py:273-276).  None: no lines."""
+        self.engine.set_line_map(line_map, sensor_radius, sensor_distance)
+
     def step_sim(self):
         """vf_sims.py:291-340: one time step for every agent of every replicate."""
         self._sync_up()

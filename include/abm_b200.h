@@ -145,6 +145,16 @@ int abm_get_state_packed(abm_engine_t* e, float* xytv, int on_device, void* stre
  * VFAgent.update (vf_agent.py:52-80) for every agent of every replicate. */
 int abm_vf_step(abm_engine_t* e, int n_steps, void* stream);
 
+/* Line following: a VFAgent with lines to follow (`len(self.lines) != 0`, vf_agent.py:273-276) takes its
+ * heading change from vf_supcalc.follow_lines_local (vf_supcalc.py:293-328: two sensors read window means of
+ * `agent.line_map`) instead of the flocking integral -- the speed change stays the flocking one -- and turns back by pi
+ * at the walls instead of pi/2 (vf_agent.py:80-129).  map: dim0 x dim1 float32, row-major, first axis x -- the
+ * reference's `line_map` of shape (WIDTH + window_pad, HEIGHT + window_pad) (vf_agent.py:32), the same for every agent
+ * and replicate; sensor_radius / sensor_distance: VFAgent.sensor_size = 9 / sensor_distance = 20 (vf_agent.py:30-31).
+ * map == NULL: no lines again.  The six terms of abm_vf_get_terms stay the flocking ones. */
+int abm_vf_set_line_map(abm_engine_t* e, const float* map, int dim0, int dim1, double sensor_radius, double sensor_distance,
+                        int on_device, void* stream);
+
 /* The host-driven loop of the reference in ONE call: upload the state (xytv_in, as abm_set_state_packed with radius ==
  * NULL: an earlier call passed the radii), n_steps steps, download the new state (xytv_out, as abm_get_state_packed).
  * Both arrays must be PINNED host memory (ABM_HOST_PINNED_ASYNC semantics: the call does not block; xytv_in may be

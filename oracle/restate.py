@@ -270,9 +270,10 @@ def wrap_heading_once(theta: float) -> float:
     return theta
 
 
-def reflect_from_walls(x, y, theta, r, width, height, pad):
+def reflect_from_walls(x, y, theta, r, width, height, pad, turn=np.pi / 2):
     """Agent.reflect_from_walls (agent.py:347-394).  The x / y tests use the centre
-    BEFORE any fix; heading changes cascade through the four tests."""
+    BEFORE any fix; heading changes cascade through the four tests.  ``turn``: a VFAgent with lines
+    to follow turns back by pi instead of pi / 2 (vf_agent.py:80-129)."""
     bx0, bx1 = pad, pad + width
     by0, by1 = pad, pad + height
     cx, cy = x + r, y + r
@@ -280,30 +281,30 @@ def reflect_from_walls(x, y, theta, r, width, height, pad):
     if cx < bx0:
         x = bx0 - r
         if pi / 2 <= theta < pi:
-            theta -= pi / 2
+            theta -= turn
         elif pi <= theta <= 3 * pi / 2:
-            theta += pi / 2
+            theta += turn
         theta = wrap_heading_once(theta)
     if cx > bx1:
         x = bx1 - r - 1
         if 3 * pi / 2 <= theta < 2 * pi:
-            theta -= pi / 2
+            theta -= turn
         elif 0 <= theta <= pi / 2:
-            theta += pi / 2
+            theta += turn
         theta = wrap_heading_once(theta)
     if cy < by0:
         y = by0 - r
         if pi / 2 <= theta <= pi:
-            theta += pi / 2
+            theta += turn
         elif 0 <= theta < pi / 2:
-            theta -= pi / 2
+            theta -= turn
         theta = wrap_heading_once(theta)
     if cy > by1:
         y = by1 - r - 1
         if 3 * pi / 2 <= theta <= 2 * pi:
-            theta += pi / 2
+            theta += turn
         elif pi <= theta < 3 * pi / 2:
-            theta -= pi / 2
+            theta -= turn
         theta = wrap_heading_once(theta)
     return x, y, theta
 
@@ -334,7 +335,7 @@ def _limit(value, lim):
     return value
 
 
-def vf_move(x, y, theta, vel, r, dvel, dpsi, cfg: VFConfig):
+def vf_move(x, y, theta, vel, r, dvel, dpsi, cfg: VFConfig, lines=False):
     """VFAgent.update_agent_position (vf_agent.py:289-309) followed by the boundary
     rule of VFAgent.update (:71-74)."""
     if cfg.limit_movement:
@@ -346,17 +347,59 @@ def vf_move(x, y, theta, vel, r, dvel, dpsi, cfg: VFConfig):
     x = x + vel * np.cos(theta)
     y = y - vel * np.sin(theta)
     if cfg.boundary == "walls":
-        x, y, theta = reflect_from_walls(x, y, theta, r, cfg.width, cfg.height, cfg.window_pad)
+        x, y, theta = reflect_from_walls(x, y, theta, r, cfg.width, cfg.height, cfg.window_pad,
+                                         np.pi if lines else np.pi / 2)
     elif cfg.boundary == "infinite":
         x, y = teleport_torus(x, y, r, cfg.width, cfg.height, cfg.window_pad)
     return x, y, theta, vel
 
 
+def follow_lines_local(pos, radius, orientation, linemap, vel, sensor_radius=10, sensor_distance=5):
+    """vf_supcalc.follow_lines_local (vf_supcalc.py:293-328): two sensors ahead-left / ahead-right of the agent read the
+    mean of the line map in a square window; the heading change steers towards the brighter one.  The windows are numpy
+    basic slices of int()-truncated bounds (negative bounds wrap, out-of-range ones clip; an empty window -> nan -> 0)."""
+    a34 = 3 * np.pi / 4
+    s1 = [pos[1] + radius - sensor_distance + (1 + np.sin(orientation + a34)) * sensor_distance,       # :295-298
+          pos[0] + radius - sensor_distance + (1 - np.cos(orientation + a34)) * sensor_distance]
+    s2 = [pos[1] + radius - sensor_distance + (1 + np.sin(orientation - a34)) * sensor_distance,       # :299-302
+          pos[0] + radius - sensor_distance + (1 - np.cos(orientation - a34)) * sensor_distance]
+
+    def window_mean(s):
+        d0, d1 = linemap.shape
+        a, b = _slice_bounds(int(s[1] - sensor_radius), int(s[1] + sensor_radius), d0)                # :310-312
+        c, d = _slice_bounds(int(s[0] - sensor_radius), int(s[0] + sensor_radius), d1)
+        if b <= a or d <= c:
+            return np.nan
+        w = linemap[a:b, c:d]
+        ok = ~np.isnan(w)
+        return w[ok].sum() / ok.sum() if ok.any() else np.nan                                          # np.nanmean
+
+    m1, m2 = window_mean(s1), window_mean(s2)
+    if np.isnan(m1) or np.isnan(m2):                                                                   # :314-315
+        return 0.0
+    ori_change = 0.5 * (m2 - m1) if np.sign(vel) else 0.0                                              # :317-320
+    if m1 != m2:                                                                                       # :321-324
+        return ori_change
+    return 0.01 if m1 != 0 else 0.0                                                                    # :326-329
+
+
+def _slice_bounds(a: int, b: int, n: int):
+    """Effective [lo, hi) of the numpy basic slice [a:b] on an axis of length n."""
+    if a < 0:
+        a = max(a + n, 0)
+    if b < 0:
+        b = max(b + n, 0)
+    return min(a, n), min(b, n)
+
+
 def vf_step_frozen(px, py, theta, vel, r, cfg: VFConfig, alp0=None, bet0=None, v0=None,
-                   agents=None):
+                   agents=None, line_map=None, sensor_radius=9, sensor_distance=20):
     """One synchronous (Jacobi) step: every agent is updated from the SAME frozen
     snapshot -- the per-agent parity definition of SURVEY 8c (the reference itself
     updates agents sequentially in place, vf_sims.py:302; see vf_step_sequential).
+
+    ``line_map``: an agent with lines to follow (vf_agent.py:273-276; sensor defaults :30-31) takes its heading change
+    from follow_lines_local instead of the flocking integral (the speed change stays the flocking one).
 
     Returns dict(x, y, theta, vel, rows (N,R bool un-flipped), terms (N,6))."""
     px = np.asarray(px, np.float64); py = np.asarray(py, np.float64)
@@ -374,7 +417,11 @@ def vf_step_frozen(px, py, theta, vel, r, cfg: VFConfig, alp0=None, bet0=None, v
                         None if bet0 is None else bet0[i],
                         None if v0 is None else v0[i])
         terms[i] = t
-        nx[i], ny[i], nt[i], nv[i] = vf_move(px[i], py[i], theta[i], vel[i], rr[i], t[0], t[1], cfg)
+        dpsi = t[1]
+        if line_map is not None:
+            dpsi = follow_lines_local((px[i], py[i]), rr[i], theta[i], line_map, vel[i], sensor_radius, sensor_distance)
+        nx[i], ny[i], nt[i], nv[i] = vf_move(px[i], py[i], theta[i], vel[i], rr[i], t[0], dpsi, cfg,
+                                             lines=line_map is not None)
     return dict(x=nx, y=ny, theta=nt, vel=nv, rows=rows, terms=terms)
 
 

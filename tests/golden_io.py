@@ -23,6 +23,21 @@ def load_vf_cases():
     return cases
 
 
+def load_vf_lines_cases():
+    """tests/golden/vf_lines_golden.npz (make_golden_lines.py): VF agents with lines to follow -- the unmodified
+    reference's VFAgent.update with a non-empty ``lines`` and a synthetic ``line_map`` (vf_agent.py:273-276, 80-129)."""
+    z = np.load(os.path.join(GOLDEN, "vf_lines_golden.npz"))
+    cases = []
+    for c in range(int(z["n_cases"])):
+        p = f"c{c}_"
+        R, W, torus, fov, limit = z[p + "cfg"]
+        cases.append(dict(N=len(z[p + "x"]), R=int(R), W=float(W), boundary="infinite" if torus else "walls",
+                          fov_ratio=float(fov), limit=bool(limit), x=z[p + "x"], y=z[p + "y"], theta=z[p + "theta"],
+                          vel=z[p + "vel"], radius=z[p + "radius"], line_map=z[p + "line_map"], fields=z[p + "fields"],
+                          new=z[p + "new"]))
+    return cases
+
+
 def load_pf_cases():
     z = np.load(os.path.join(GOLDEN, "vf_golden.npz"))
     cases = []

@@ -131,3 +131,25 @@ def test_literal_port_matches_reference_fixture(case):
                                                     c["alp0"], c["bet0"], c["v0"])
         assert np.array_equal(rs.pack_bits(field > 0), c["fields"][i])
         np.testing.assert_allclose([nx, ny, th, v], c["new"][i], rtol=1e-14, atol=1e-12)
+
+
+def test_restatement_matches_reference_fixture_line_following():
+    """follow_lines_local (vf_supcalc.py:293-328) and the turn-back wall rule of an agent with lines (vf_agent.py:80-129,
+    273-276) against fixtures of the unmodified reference: every branch occurs (steering, standing agents, equal
+    non-zero sensors -> 0.01, both sensors dark -> 0, empty windows at the arena's edge -> 0)."""
+    from golden_io import load_vf_lines_cases
+    n_const = n_zero = n_steer = 0
+    for c in load_vf_lines_cases():
+        cfg = rs.VFConfig(R=c["R"], fov=(-c["fov_ratio"] * np.pi, c["fov_ratio"] * np.pi), boundary=c["boundary"],
+                          width=c["W"], height=c["W"], limit_movement=c["limit"])
+        lm = c["line_map"].astype(np.float64)
+        out = rs.vf_step_frozen(c["x"], c["y"], c["theta"], c["vel"], c["radius"], cfg, line_map=lm)
+        assert np.array_equal(rs.pack_bits(out["rows"][:, ::-1]), c["fields"])
+        got = np.stack([out["x"], out["y"], out["theta"], out["vel"]], axis=1)
+        np.testing.assert_allclose(got, c["new"], rtol=1e-12, atol=1e-12)
+        plain = rs.vf_step_frozen(c["x"], c["y"], c["theta"], c["vel"], c["radius"], cfg)
+        assert (np.abs(plain["theta"] - c["new"][:, 2]) > 1e-9).sum() > c["N"] // 2     # not the flocking heading
+        for i in range(c["N"]):
+            d = rs.follow_lines_local((c["x"][i], c["y"][i]), c["radius"][i], c["theta"][i], lm, c["vel"][i], 9, 20)
+            n_const += d == 0.01; n_zero += d == 0.0; n_steer += d not in (0.0, 0.01)
+    assert n_const >= 3 and n_zero >= 20 and n_steer >= 20

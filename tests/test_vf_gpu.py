@@ -10,7 +10,7 @@ fields are expected to match bit for bit, and the tests assert exactly that.
 import numpy as np
 import pytest
 
-from golden_io import load_pf_cases, load_vf_cases
+from golden_io import load_vf_lines_cases, load_pf_cases, load_vf_cases
 from oracle import restate as rs
 
 pytestmark = pytest.mark.gpu
@@ -75,6 +75,35 @@ def test_step_matches_reference_fixture(built_lib, monkeypatch, case, kernel):
     st = eng.get_state()
     got = np.stack([st["x"][0], st["y"][0], st["theta"][0], st["vel"][0]], axis=1)
     np.testing.assert_allclose(got, c["new"], rtol=RTOL, atol=1e-5)
+    eng.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("case", load_vf_lines_cases(), ids=lambda c: f"N{c['N']}_R{c['R']}_{c['boundary']}")
+def test_line_following_matches_reference_fixture(built_lib, monkeypatch, case, kernel):
+    """agents with lines to follow (vf_agent.py:273-276 -> vf_supcalc.follow_lines_local, :293-328; turn-back
+    wall rule vf_agent.py:80-129) through abm_vf_set_line_map, under every step kernel, against fixtures of the
+    unmodified reference; switching the map off again gives the flocking step."""
+    c = case
+    _force_kernel(monkeypatch, kernel)
+    fov = (-c["fov_ratio"] * np.pi, c["fov_ratio"] * np.pi)
+    eng = _engine(None, 1, c["N"], resolution=c["R"], fov=fov, boundary=c["boundary"], width=c["W"],
+                  height=c["W"], limit_movement=c["limit"])
+    eng.set_params()
+    eng.set_line_map(c["line_map"], sensor_radius=9, sensor_distance=20)
+    eng.set_state(c["x"], c["y"], c["theta"], c["vel"], c["radius"])
+    eng.step(1)
+    assert _ran_forced_kernel(eng, kernel)
+    assert np.array_equal(eng.fields_packed()[0], c["fields"])          # bit-exact stored fields
+    st = eng.get_state()
+    got = np.stack([st["x"][0], st["y"][0], st["theta"][0], st["vel"][0]], axis=1)
+    np.testing.assert_allclose(got, c["new"], rtol=RTOL, atol=1e-5)
+    eng.set_line_map(None)
+    eng.set_state(c["x"], c["y"], c["theta"], c["vel"], c["radius"])
+    eng.step(1)
+    cfg = rs.VFConfig(R=c["R"], fov=fov, boundary=c["boundary"], width=c["W"], height=c["W"], limit_movement=c["limit"])
+    plain = rs.vf_step_frozen(c["x"], c["y"], c["theta"], c["vel"], c["radius"], cfg)
+    np.testing.assert_allclose(eng.get_state()["theta"][0], plain["theta"], rtol=RTOL, atol=1e-5)
     eng.close()
 
 
