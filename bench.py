@@ -38,7 +38,7 @@ PAD = 30.0
 PARAMS = dict(GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, BET0=1.0, BET1=0.09)
 # dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch at the default workload, from the committed
 # `ncu --set full` captures (profiles/r1_*_ncu_summary.md); None for any other workload size or kernel
-NCU_DRAM_BYTES_PER_LAUNCH = {"abm::vf_step_kernel": 55.2e6, "abm::vf_step_sym_kernel": 26.1e6} \
+NCU_DRAM_BYTES_PER_LAUNCH = {"abm::vf_step_kernel": 55.2e6, "abm::vf_step_sym_kernel": 26.5e6} \
     if (N_AGENTS, N_REPLICATES) == (1024, 1024) else {}
 METRIC = "agent-steps/sec (visual field + flocking update)"
 UNIT = "agent-steps/s"
@@ -633,7 +633,8 @@ def main():
         vis = 0.5 * (vis0 + vis1)
         pairs = B * N * (N - 1)
         # OPS_PAIR = 6 * P_all + 42 * P_vis ; OPS_AGENT = 8 * ceil(R/32) + 12 * n_edges + 30
-        ops_launch = 6.0 * pairs + 42.0 * pairs * vis + B * N * (8 * ((R + 31) // 32) + 30)
+        n_edges = float(par.get("edges_per_agent", 0.0))              # measured on the parity step (workload's first step)
+        ops_launch = 6.0 * pairs + 42.0 * pairs * vis + B * N * (8 * ((R + 31) // 32) + 12.0 * n_edges + 30)
         avg_s = total_ms * 1e-3 / args.steps
         sm_clock = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
         peak_ops = sms * 128 * sm_clock
@@ -662,7 +663,7 @@ def main():
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(timed_kernel), "kernel": timed_kernel,
                          "kernel_launches_by_variant": kernel_stats,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, committed `ncu --set full` "
-                                           "capture under profiles/ (not measured in this run)",
+                                           "capture under profiles/r2_vf_step_sym_ncu_summary.md (not measured in this run)",
                          "algorithmic_ops_per_launch": ops_launch,
                          "visible_pair_fraction": vis, "peak_source": f"{sms} SMs x 128 lanes x "
                          f"{sm_clock / 1e6:.0f} MHz ({peak_kind} sm_max_mhz)",
