@@ -138,6 +138,8 @@ SYMBOLS = {
     "abm_vf_record_table": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
     "abm_vf_last_kernel": (C.c_char_p, [_P]),
     "abm_vf_kernel_stats": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "abm_vf_cluster_launches": (C.c_int, [_P, _P]),
+    "abm_vf_cluster_launches": (C.c_int, [_P, _P]),
     "abm_vf_ipc_export": (C.c_int, [_P, _P]),
     "abm_vf_ipc_attach": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "abm_vf_metrics": (C.c_int, [_P, _P, C.c_int, _P]),

@@ -133,6 +133,7 @@ struct abm_engine {
   bool slow_pending = false;
   unsigned long long slow_seen = 0, sym_launches = 0, slow_req_launch = 0, slow_seen_launch = 0;
   unsigned long long kstat[4] = {0, 0, 0, 0};   // launches: symmetric two-word / three-word, one-sided, warp
+  unsigned long long kstat_cluster = 0;         // multi-step launches whose grid was one thread-block cluster
   int wide_steps_left = 0;   // steps the symmetric kernel still runs with its three-word fast path (crowded scene)
   size_t smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   int n_sms = 148;
@@ -649,7 +650,10 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     a.n_peers = 0; a.step_no = e->steps_done; a.xflags = nullptr;
     a.tile_bbox = nullptr; a.tile_cull2 = nullptr; a.bbox_out = nullptr;
     a.step_ticket = e->ticket.p;
-    if (abm::launch_vf_step_warp_multi(a, uniform_r, n_steps, st)) {
+    bool launched = abm::launch_vf_step_warp_cluster(a, uniform_r, n_steps, st);   // one small replicate: one cluster
+    if (launched) ++e->kstat_cluster;
+    else { cudaGetLastError(); launched = abm::launch_vf_step_warp_multi(a, uniform_r, n_steps, st); }
+    if (launched) {
       ABM_CUDA(cudaMemsetAsync(e->ticket.p, 0, sizeof(uint32_t), st));
       e->cur ^= (n_steps & 1);
       e->steps_done += (uint32_t)n_steps; e->steps_since_sort += n_steps;
@@ -976,6 +980,12 @@ const char* abm_vf_last_kernel(abm_engine_t* e) { return e ? e->last_kernel : ""
 int abm_vf_kernel_stats(abm_engine_t* e, uint64_t stats[4]) {
   if (!e || !stats) return fail(ABM_E_INVALID, "abm_vf_kernel_stats: null argument");
   for (int k = 0; k < 4; ++k) stats[k] = e->kstat[k];
+  return ABM_OK;
+}
+
+int abm_vf_cluster_launches(abm_engine_t* e, uint64_t* out) {
+  if (!e || !out) return fail(ABM_E_INVALID, "abm_vf_cluster_launches: null argument");
+  *out = e->kstat_cluster;
   return ABM_OK;
 }
 

@@ -149,6 +149,7 @@ int vf_step_threads(int tile_count, int n_replicates, int n_sms);
 void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaStream_t stream);
 int vf_warp_focal_per_cta(long long focal_total, int n_sms);
 bool launch_vf_step_warp_multi(const VFKernelArgs& a, bool uniform_r, int n_steps, cudaStream_t stream);
+bool launch_vf_step_warp_cluster(const VFKernelArgs& a, bool uniform_r, int n_steps, cudaStream_t stream);
 struct VFPeerFlags { uint32_t* p[7]; };
 void launch_vf_publish(const VFKernelArgs& a, cudaStream_t stream);   // fused tile exchange: step done -> all ranks
 

@@ -143,10 +143,17 @@ __device__ __forceinline__ void warp_pair(const VFKernelArgs& a, const float4 f,
   asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wa + 4u), "r"(__funnelshift_l(mask, 0u, ps)));
 }
 
-// MULTI: n_steps time steps in ONE (cooperative) launch, a grid-wide barrier between steps -- for runs so small that a
-// step is shorter than a kernel launch (one run of 100 agents: BASELINE configs[1]); the record tables swap roles
-// every step.  Without peers, culling lists or re-sorting (abm_api.cu checks).
-template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R, bool MULTI>
+// MULTI: n_steps time steps in ONE launch, a barrier over all CTAs between steps -- for runs so small that a step is
+// shorter than a kernel launch (one run of 100 agents: BASELINE configs[1]); the record tables swap roles every step.
+// Without peers, culling lists or re-sorting (abm_api.cu checks).
+//   1: cooperative launch, the barrier is a ticket counter in global memory (an atomic + an acquire poll per step);
+//   2: the whole grid is ONE thread-block cluster (one replicate of at most 16 * 4 agents): the barrier is the hardware's
+//      barrier.cluster (release / acquire at cluster scope); CTAs beyond the last focal agent only take part in the
+//      barrier.  Measured (scratch/c2_cluster_probe.py, us per step, cluster / grid barrier): N = 16 5.9 / 6.5, N = 64
+//      8.3 / 8.7; with 8 focal agents per CTA (N = 100 in 13 CTAs) 10.1 / 9.2 -- the longer pair loop per CTA costs more
+//      than the barrier saves, so larger replicates keep mode 1.  Either way a step of a small run is a chain of
+//      dependent latencies (state loads from L2, the few fp64 pairs, the fp64 epilogue), not the barrier.
+template <bool TORUS, bool CULL, bool FULL_FOV, bool UNIFORM_R, int MULTI>
 __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const __grid_constant__ VFKernelArgs a, const int F,
                                                                        const int n_steps_arg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -162,9 +169,10 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x;                                // 256 or 512 threads
   const int per_rep = (a.tile_count + F - 1) / F;
-  const int b = blockIdx.x / per_rep;
-  const int li0 = (blockIdx.x - b * per_rep) * F;          // first focal agent of the CTA inside this engine's tile
-  const int nf = min(F, a.tile_count - li0);               // focal agents of this CTA
+  const bool idle = MULTI == 2 && (int)blockIdx.x >= per_rep * a.B;   // cluster padding: barrier only
+  const int b = idle ? 0 : blockIdx.x / per_rep;
+  const int li0 = idle ? 0 : (blockIdx.x - b * per_rep) * F;   // first focal agent of the CTA inside this engine's tile
+  const int nf = idle ? 0 : min(F, a.tile_count - li0);    // focal agents of this CTA
   const int R = a.R, W = a.W;
   const int row_words = W + 3;
   int* tile_list = sh.tile_list;
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
   const int tile_sh = 31 - __clz(tile_sz);
   const int n_tiles = (a.N + tile_sz - 1) / tile_sz;
   const bool use_list = CULL && a.tile_bbox != nullptr && n_tiles <= kMaxTileList;
-  int n_stage = n_tiles;
+  int n_stage = idle ? 0 : n_tiles;
   if (use_list) {
     const float4* bb = a.tile_bbox + (size_t)b * n_tiles;
     const float* c2 = a.tile_cull2 + (size_t)b * n_tiles;
@@ -364,7 +372,11 @@ __global__ void __launch_bounds__(kWarpMaxThreads, 2) vf_step_warp_kernel(const 
     }
   }
 
-  if (MULTI) {   // grid-wide barrier: every CTA's records of this step are in place before anybody reads them
+  if (MULTI == 2) {   // one cluster: every CTA's records of this step are in place before anybody reads them
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+    continue;
+  }
+  if (MULTI == 1) {   // grid-wide barrier
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -445,8 +457,8 @@ static void launch_warp_variant(const VFKernelArgs& a, int F, cudaStream_t strea
   const int per_rep = (a.tile_count + F - 1) / F;
   const size_t smem = vf_warp_smem_bytes(a.W, F);
   static SmemOptIn optin;
-  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R, false>, smem);
-  vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R, false>
+  if (smem > 48 * 1024) optin.ensure(vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R, 0>, smem);
+  vf_step_warp_kernel<TORUS, CULL, FULL_FOV, UNIFORM_R, 0>
       <<<(unsigned)((size_t)a.B * per_rep), warp_threads_choice(a, F), smem, stream>>>(a, F, 1);
 }
 template <bool TORUS, bool CULL>
@@ -471,7 +483,7 @@ void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaS
 // n_steps steps in one cooperative launch (no culling, no peers); false: the grid cannot be co-resident -- nothing launched
 template <bool TORUS, bool FULL_FOV, bool UNIFORM_R>
 static bool launch_warp_multi_variant(const VFKernelArgs& a, int F, int n_steps, cudaStream_t stream) {
-  auto kernel = vf_step_warp_kernel<TORUS, false, FULL_FOV, UNIFORM_R, true>;
+  auto kernel = vf_step_warp_kernel<TORUS, false, FULL_FOV, UNIFORM_R, 1>;
   const int per_rep = (a.tile_count + F - 1) / F;
   const unsigned grid = (unsigned)((size_t)a.B * per_rep);
   const size_t smem = vf_warp_smem_bytes(a.W, F);
@@ -486,6 +498,40 @@ static bool launch_warp_multi_variant(const VFKernelArgs& a, int F, int n_steps,
   return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kWarpThreads), params, smem, stream) ==
          cudaSuccess;
 }
+// n_steps steps of ONE small replicate in one launch whose grid is a single thread-block cluster (at most 16 CTAs of 4
+// focal agents); false: not applicable / the cluster cannot be scheduled -- nothing launched
+template <bool TORUS, bool FULL_FOV, bool UNIFORM_R>
+static bool launch_warp_cluster_variant(const VFKernelArgs& a, int F, int cluster, int n_steps, cudaStream_t stream) {
+  auto kernel = vf_step_warp_kernel<TORUS, false, FULL_FOV, UNIFORM_R, 2>;
+  const size_t smem = vf_warp_smem_bytes(a.W, F);
+  static SmemOptIn optin;
+  if (smem > 48 * 1024) optin.ensure(kernel, smem);
+  if (cluster > 8 &&
+      cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cluster); cfg.blockDim = dim3(kWarpThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a, F, n_steps) == cudaSuccess;
+}
+bool launch_vf_step_warp_cluster(const VFKernelArgs& a, bool uniform_r, int n_steps, cudaStream_t stream) {
+  constexpr int kClusterMaxFocal = 4;
+  if (a.B != 1 || a.tile_count != a.N || a.N > 16 * kClusterMaxFocal || getenv("ABM_VF_NO_CLUSTER")) return false;
+  int F = 1;
+  while (F < kClusterMaxFocal && (a.N + F - 1) / F > 16) F <<= 1;   // as many CTAs as a cluster can hold
+  const int ctas = (a.N + F - 1) / F;
+  const int cluster = ctas <= 1 ? 1 : (ctas <= 2 ? 2 : (ctas <= 4 ? 4 : (ctas <= 8 ? 8 : 16)));
+  if (a.boundary == 1) {
+    if (a.full_fov) return uniform_r ? launch_warp_cluster_variant<true, true, true>(a, F, cluster, n_steps, stream) : launch_warp_cluster_variant<true, true, false>(a, F, cluster, n_steps, stream);
+    return uniform_r ? launch_warp_cluster_variant<true, false, true>(a, F, cluster, n_steps, stream) : launch_warp_cluster_variant<true, false, false>(a, F, cluster, n_steps, stream);
+  }
+  if (a.full_fov) return uniform_r ? launch_warp_cluster_variant<false, true, true>(a, F, cluster, n_steps, stream) : launch_warp_cluster_variant<false, true, false>(a, F, cluster, n_steps, stream);
+  return uniform_r ? launch_warp_cluster_variant<false, false, true>(a, F, cluster, n_steps, stream) : launch_warp_cluster_variant<false, false, false>(a, F, cluster, n_steps, stream);
+}
+
 bool launch_vf_step_warp_multi(const VFKernelArgs& a, bool uniform_r, int n_steps, cudaStream_t stream) {
   const int F = warp_focal_choice(a);
   if (a.boundary == 1) {

@@ -347,6 +347,12 @@ class VFEngine:
         _lib.check(self._lib.abm_vf_kernel_stats(self._h, c), "abm_vf_kernel_stats")
         return dict(symmetric=int(c[0]), symmetric_wide=int(c[1]), onesided=int(c[2]), warp=int(c[3]))
 
+    def cluster_launches(self) -> int:
+        """Multi-step launches that ran as ONE thread-block cluster (hardware barrier between the steps)."""
+        v = C.c_uint64(0)
+        _lib.check(self._lib.abm_vf_cluster_launches(self._h, C.byref(v)), "abm_vf_cluster_launches")
+        return int(v.value)
+
     def last_kernel(self) -> str:
         """Name of the step kernel the last step() launched."""
         return (self._lib.abm_vf_last_kernel(self._h) or b"").decode()

@@ -222,6 +222,10 @@ const char* abm_vf_last_kernel(abm_engine_t* e);
  * (crowded scenes: chosen when more than 4 % of the pairs of a two-word step left its fast path), [2] one thread per
  * focal agent, [3] warp kernel (a multi-step cooperative launch counts once). */
 int abm_vf_kernel_stats(abm_engine_t* e, uint64_t stats[4]);
+/* Multi-step launches (abm_vf_step with n_steps > 1 on one small replicate) whose grid was ONE thread-block cluster: the
+ * steps of the launch are separated by the hardware cluster barrier instead of a grid-wide barrier in global memory
+ * (at most 16 CTAs x 4 focal agents = 64 agents; ABM_VF_NO_CLUSTER=1 disables it).  Diagnostic, like the stats above. */
+int abm_vf_cluster_launches(abm_engine_t* e, uint64_t* out);
 /* Statistics behind the automatic choice: unordered pairs that left the symmetric kernel's (two-word) fast path -- wide
  * intervals, guard-band hits -- summed over its launches so far, and the number of those launches. */
 int abm_vf_slow_entries(abm_engine_t* e, uint64_t* entries, uint64_t* sym_launches, void* stream);

@@ -795,11 +795,13 @@ def test_engines_on_two_devices_in_one_process(built_lib):
 
 
 @pytest.mark.parametrize("B,N,boundary,fovr,hetero", [(1, 100, "walls", 1.0, False), (3, 40, "infinite", 1.0, True),
-                                                      (2, 64, "walls", 0.5, False)])
+                                                      (2, 64, "walls", 0.5, False), (1, 64, "infinite", 1.0, True),
+                                                      (1, 23, "walls", 0.5, False), (1, 5, "walls", 1.0, False)])
 def test_small_runs_step_inside_one_launch(built_lib, monkeypatch, B, N, boundary, fovr, hetero):
     """A run so small that a step is shorter than a kernel launch (BASELINE configs[1]: one run of 100 agents) takes all
-    n_steps in ONE cooperative launch with a grid-wide barrier between steps: the same trajectory, bit for bit, as a
-    launch per step, and the last step's fields / terms are the ones kept."""
+    n_steps in ONE launch with a barrier over all CTAs between steps -- one replicate of at most 64 agents as ONE
+    thread-block cluster (hardware cluster barrier), otherwise a cooperative launch with a grid-wide barrier in global
+    memory: the same trajectory, bit for bit, as a launch per step, and the last step's fields / terms are the ones kept."""
     from abm_b200 import VFEngine
     rng = np.random.default_rng(40 + N)
     W = 900.0 if N == 100 else 400.0
@@ -818,6 +820,7 @@ def test_small_runs_step_inside_one_launch(built_lib, monkeypatch, B, N, boundar
         eng.step(37)
         assert eng.last_kernel() == "abm::vf_step_warp_kernel"
         assert eng.counters()["launches"] == (37 if per_step else 1)
+        assert eng.cluster_launches() == (1 if (B == 1 and N <= 64 and not per_step) else 0)
         eng.step(2)                                   # an even and an odd count: both table parities
         res[per_step] = (eng.get_state(), eng.fields_packed(), eng.terms())
         eng.close()
