@@ -192,6 +192,74 @@ def test_step_matches_oracle_random(built_lib, monkeypatch, B, N, R, W, boundary
     eng.close()
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("boundary", ["walls", "infinite"])
+def test_degenerate_geometry_matches_oracle(built_lib, monkeypatch, boundary, kernel):
+    """The corners of the pair geometry in one scene, against the oracle under every kernel: coincident agents (skipped,
+    vf_supcalc.py:57), overlapping discs (distance < radius: atan(r / d) near pi / 2, intervals hundreds of bins wide that
+    wrap around the ring), touching discs, agents dead ahead / dead astern / exactly abeam (bin ties and the +-pi seam),
+    agents on and beyond the walls, standing agents, headings of exactly 0 and 2 pi."""
+    _force_kernel(monkeypatch, kernel)
+    W, R, r = 300.0, 1200, 10.0
+    base = np.array([[150, 150], [150, 150], [150, 150],          # three coincident agents
+                     [150.5, 150], [153, 150], [150, 159.99], [160, 150], [170, 150],   # overlapping / touching / near
+                     [150, 100], [150, 200], [100, 150], [200, 150],                    # abeam / ahead / astern of agent 0
+                     [20, 20], [20, 150], [329, 329], [335, 150], [150, 15], [10, 340],  # at and beyond the walls
+                     [31, 31], [299, 299], [60, 240], [240, 60]], np.float32)
+    N = len(base)
+    rng = np.random.default_rng(5)
+    x = np.stack([base[:, 0], base[::-1, 0]]); y = np.stack([base[:, 1], base[::-1, 1]])
+    th = rng.uniform(0, 2 * np.pi, (2, N)).astype(np.float32)
+    th[0, :4] = [0.0, np.float32(2 * np.pi), np.float32(np.pi), np.float32(np.pi / 2)]
+    v = rng.uniform(0, 2.5, (2, N)).astype(np.float32)
+    v[:, ::5] = 0.0
+    eng = _engine(None, 2, N, resolution=R, boundary=boundary, width=W, height=W)
+    eng.set_params()
+    eng.set_state(x, y, th, v, r)
+    eng.step(1)
+    assert _ran_forced_kernel(eng, kernel)
+    fields, terms, st = eng.fields(), eng.terms(), eng.get_state()
+    cfg = rs.VFConfig(R=R, boundary=boundary, width=W, height=W)
+    widest = 0
+    for b in range(2):
+        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], r, cfg)
+        assert np.array_equal(fields[b], ref["rows"][:, ::-1]), "stored field mismatch"
+        np.testing.assert_allclose(terms[b], ref["terms"], rtol=RTOL, atol=1e-9)
+        _check_state(st, ref, b)
+        widest = max(widest, int(ref["rows"].sum(axis=1).max()))
+    assert widest > 600                                  # an overlapping neighbour fills more than half the ring
+    eng.close()
+
+
+def test_invalid_calls_fail_loudly(built_lib):
+    """Error behaviour of the boundary: wrong sizes, calls in the wrong order and impossible configurations raise
+    (ABM_E_* codes with a message from abm_last_error), nothing is computed on a fallback path."""
+    from abm_b200 import VFEngine, _lib
+    eng = VFEngine(2, 8, resolution=1200, width=300.0, height=300.0)
+    with pytest.raises(_lib.AbmError):
+        eng.step(1)                                      # no state yet
+    with pytest.raises(_lib.AbmError):
+        eng.get_state()
+    x = np.zeros((2, 8), np.float32)
+    with pytest.raises(Exception):
+        eng.set_state(x[:, :4], x, x, x, 10.0)           # wrong shape
+    eng.set_params()
+    eng.set_state(x + 100, x + 100, x, x, 10.0)
+    with pytest.raises(_lib.AbmError):
+        eng.step(-1)
+    with pytest.raises(Exception):
+        eng.set_line_map(np.zeros(5, np.float32))        # not two-dimensional
+    with pytest.raises(Exception):
+        eng.step_host(np.zeros((2, 8, 3), np.float32), np.zeros((2, 8, 4), np.float32))
+    eng.step(1)                                          # (all agents coincident: nothing visible, still a valid step)
+    assert np.isfinite(eng.get_state()["x"]).all()
+    eng.close()
+    with pytest.raises(Exception):
+        VFEngine(1, 8, resolution=1, width=300.0, height=300.0)      # a ring of one bin
+    with pytest.raises(Exception):
+        VFEngine(0, 8, resolution=1200, width=300.0, height=300.0)
+
+
 def test_per_replicate_parameter_sweep(built_lib):
     """One launch, one parameter set per replicate (the MetaProtocol sweep shape)."""
     rng = np.random.default_rng(5)
