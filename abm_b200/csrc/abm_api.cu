@@ -539,6 +539,7 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.fov_px0 = e->cfg.fov_px0; a.fov_px1 = e->cfg.fov_px1;
   a.boundary = e->cfg.boundary; a.limit_movement = e->cfg.limit_movement;
   a.phi_ok = g.phi_ok; a.flags = e->cfg.flags;
+  if (getenv("ABM_VF_DEBUG_SKIP_SLOW")) a.flags |= 1u << 30;   // timing probe only (WRONG results): the slow pairs are dropped
   const bool exact = (e->cfg.flags & ABM_VF_EXACT_FIXUP) != 0;   // false: no guard bands (hard cases still go to fp64)
   a.inv_step = g.inv_step; a.t_half = g.t_half(); a.k_bias = g.k_bias(); a.y_scale = g.y_scale;
   a.thr_k = g.thr_k(exact); a.thr_h0 = g.thr_h0(exact); a.thr_h1 = g.thr_h1(exact); a.ca_guard = g.ca_guard;

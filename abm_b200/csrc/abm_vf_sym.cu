@@ -160,6 +160,7 @@ static __device__ __noinline__ void sym_fp64_drain(const VFKernelArgs& a, const 
 
 template <bool TORUS, int RC>
 static __device__ __noinline__ void sym_slow_batch(const VFKernelArgs& a, const SymShared& sh, uint32_t ent) {
+  if (a.flags & (1u << 30)) return;   // timing probe (ABM_VF_DEBUG_SKIP_SLOW, results are wrong): what the slow pairs cost
   const uint32_t dirs = ent >> 20;
   const int warp = threadIdx.x >> 5;
   if (dirs) sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s + 8u * (uint32_t)(warp * sh.fq_cap),
