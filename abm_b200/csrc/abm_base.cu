@@ -571,14 +571,14 @@ __global__ void __launch_bounds__(512) base_collision_kernel(const BaseKernelArg
 }
 
 // ---------------------------------------------------------------------------------------
-// agent phase of one replicate by the whole CTA (N <= 64 agents, R <= 8192): the work is dealt to the THREADS by item,
+// agent phase of one replicate by the whole CTA (N <= 128 agents, R <= 8192): the work is dealt to the THREADS by item,
 // not to warps by focal agent -- (focal, object) pairs, then (focal, social cue) occlusion scans, then (focal, word)
 // popcounts -- so every lane has work whatever N is (a warp per focal agent runs 49 objects as two ragged passes of 32
 // lanes and spends most of its instructions on per-focal bookkeeping).  Focal agents go in groups of kBlkGroup (the pair
 // table of a group lives in shared memory).
 // ---------------------------------------------------------------------------------------
 constexpr int kBlkMaxGroup = 32;    // focal agents per group (the pair table of a group lives in shared memory)
-constexpr int kBlkMaxN = 64;        // objects per focal agent fit one 64-bit mask
+constexpr int kBlkMaxN = 128;       // objects per focal agent fit a 128-bit mask (the reference's figure experiments: N <= 100)
 
 struct BlkShared {
   float *x, *y, *th;                // [N] frozen snapshot positions, headings
@@ -738,8 +738,8 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
       int sx = fs, ex = fe_;
       if (a.visual_exclusion) {
         const double dc = sh.d[gi * N + jc];
-        unsigned long long rel = 0ull;                       // objects strictly closer than the cue that meet its raw interval
-        const unsigned char* cl = sh.cls + gi * N;
+        unsigned long long rel0 = 0ull, rel1 = 0ull;         // objects strictly closer than the cue that meet its raw interval
+        const unsigned char* cl = sh.cls + gi * N;           // (two words: N <= 128)
         const uint32_t* sep = sh.se + gi * N;
         const double* dp = sh.d + gi * N;
 #pragma unroll 2
@@ -747,24 +747,27 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
           const uint32_t so = sep[j];
           const int os = (int)(short)(so & 0xffffu), oe = (int)(short)(so >> 16);
           if ((cl[j] != 0) & (os <= fe_) & (oe >= fs) & (j != jc)) {
-            if (dp[j] < dc) rel |= 1ull << j;                // :430 strict, on the float64 values
+            if (dp[j] < dc) { if (j < 64) rel0 |= 1ull << j; else rel1 |= 1ull << (j - 64); }   // :430 strict, on the float64 values
           }
         }
-        while (rel) {                                        // usually none to three
+        while (rel0 | rel1) {                                // usually none to three
           int best = -1;
-          if ((rel & (rel - 1ull)) == 0ull) {
-            best = __ffsll((long long)rel) - 1;
+          if (__popcll(rel0) + __popcll(rel1) == 1) {
+            best = rel0 ? __ffsll((long long)rel0) - 1 : 63 + __ffsll((long long)rel1);
           } else {                                           // several: nearest first, ties in list order (stable sort, :424)
             double bd = 0.0; int bk = 0;
-            for (unsigned long long m = rel; m; m &= m - 1ull) {
-              const int j = __ffsll((long long)m) - 1;
-              const double dj = dp[j];
-              const int cj = cl[j];
-              const int kj = ((cj == 1) ? 0 : (cj == 2 ? 1 : 2)) * N + j;
-              if (best < 0 || dj < bd || (dj == bd && kj < bk)) { best = j; bd = dj; bk = kj; }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              for (unsigned long long m = half ? rel1 : rel0; m; m &= m - 1ull) {
+                const int j = 64 * half + __ffsll((long long)m) - 1;
+                const double dj = dp[j];
+                const int cj = cl[j];
+                const int kj = ((cj == 1) ? 0 : (cj == 2 ? 1 : 2)) * N + j;
+                if (best < 0 || dj < bd || (dj == bd && kj < bk)) { best = j; bd = dj; bk = kj; }
+              }
             }
           }
-          rel &= ~(1ull << best);
+          if (best < 64) rel0 &= ~(1ull << best); else rel1 &= ~(1ull << (best - 64));
           const uint32_t so = sep[best];
           const int os = (int)(short)(so & 0xffffu), oe = (int)(short)(so >> 16);
           if (sx <= os && os <= ex) ex = os;                                          // :432-433

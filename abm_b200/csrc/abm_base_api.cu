@@ -341,7 +341,20 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
     }
     a.inject_dtheta = src;
   }
-  const bool separate = getenv("ABM_BASE_SEPARATE_PHASES") != nullptr;   // measurement probes: the three-grid path
+  // One CTA per replicate (the fused kernel) or one grid per phase with a warp per focal agent?  A replicate's three
+  // phases are a chain of dependent latencies: the fused kernel wins when the OTHER replicates fill the SMs meanwhile
+  // (or when the run is so small that a step is shorter than three launches); a batch of few, larger replicates is faster
+  // with its agents spread over the whole GPU.  Measured crossovers on B200 (scratch/base_n100_probe.py, occlusion +
+  // collisions): N = 10 fused at any B (0.021 against 0.030 ms per step at B = 1), N = 25 a tie up to B = 148,
+  // N = 50 fused from B ~ 400 (B = 148: 0.154 against 0.103; B = 1024: 0.22 against 0.42), N = 100 from B ~ 600
+  // (B = 148: 0.49 against 0.22; B = 1024: 1.13 against 1.56).  ABM_BASE_FUSED=1|0 forces the choice.
+  bool separate = getenv("ABM_BASE_SEPARATE_PHASES") != nullptr;
+  {
+    const char* f = getenv("ABM_BASE_FUSED");
+    const long long B = c.n_replicates, N = c.n_agents;
+    if (f) separate = separate || atoi(f) == 0;
+    else if (!separate) separate = !(N <= 25 || B * 148 >= (long long)e->n_sms * (200 + 4 * N));
+  }
   const bool collide = (phases & ABM_BASE_PHASE_COLLISIONS) && c.collide_agents;
   // ONE launch for all n_steps (a CTA per replicate runs the phases in the reference's order, step after step: replicates
   // never interact) whenever the batch fills the GPU that way; otherwise one grid per phase and step

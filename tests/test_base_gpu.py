@@ -13,6 +13,15 @@ RTOL = 1e-5
 PHASE_ENV, PHASE_AGENTS = 1, 2
 
 
+@pytest.fixture(autouse=True, params=["one_cta_per_replicate", "grid_per_phase"])
+def step_path(request, monkeypatch):
+    """Every test of this module runs on BOTH step paths: the fused kernel (a CTA per replicate runs collisions,
+    environment and agent phase) and one grid per phase with a warp per focal agent.  The engine picks between them from
+    the batch shape (abm_base_api.cu); ABM_BASE_FUSED forces the choice."""
+    monkeypatch.setenv("ABM_BASE_FUSED", "1" if request.param == "one_cta_per_replicate" else "0")
+    return request.param
+
+
 def _engine_for(cfg, B, N, P=0, **kw):
     from abm_b200 import BaseEngine
     fovr = cfg.fov[1] / np.pi
@@ -163,7 +172,9 @@ def _random_state(rng, N, W, cfg):
 @pytest.mark.parametrize("B,N,R,W,vis_excl,fovr", [
     (4, 50, 1200, 500.0, True, 1.0),        # config 3 shape
     (3, 10, 1200, 900.0, False, 0.5),       # config 1 shape
-    (2, 100, 1200, 500.0, True, 1.0),
+    (2, 100, 1200, 500.0, True, 1.0),       # the reference's figure experiments (N = 100): two mask words in the fused kernel
+    (2, 65, 1200, 300.0, True, 1.0),        # one object beyond the first mask word, crowded
+    (1, 128, 1200, 350.0, True, 1.0),       # the largest replicate of the fused kernel, crowded
     (2, 37, 601, 300.0, True, 0.75),
     (1, 200, 1200, 400.0, True, 1.0),       # crowded: heavy occlusion
 ])
@@ -238,7 +249,7 @@ def test_env_phase_matches_oracle(built_lib):
     eng.close()
 
 
-def test_full_loop_runs_and_forages(built_lib):
+def test_full_loop_runs_and_forages(built_lib, step_path):
     """configs[0] shape (N=10, 3 patches, R=1200) for 300 steps with the engine's own RNG:
     sanity properties -- agents stay inside the arena, some resource gets collected, patches
     are regenerated, state stays finite, replicates with different seeds differ."""
@@ -262,7 +273,8 @@ def test_full_loop_runs_and_forages(built_lib):
     assert a["collected"].sum() > 0
     assert not np.array_equal(a["x"][0], a["x"][1])
     c = eng.counters()
-    assert c["steps"] == 300 and c["launches"] == 1 and c["regeneration_failed"] == 0   # ONE launch for all 300 steps
+    assert c["steps"] == 300 and c["regeneration_failed"] == 0
+    assert c["launches"] == (1 if step_path == "one_cta_per_replicate" else 600)         # ONE launch for all 300 steps
     eng.close()
 
 
@@ -381,7 +393,7 @@ def test_collision_phase_with_per_agent_max_exp_vel(built_lib):
     eng.close()
 
 
-def test_full_loop_with_collisions(built_lib):
+def test_full_loop_with_collisions(built_lib, step_path):
     """configs[2]-like shape (N=50, 3 patches, occlusion + collisions on) for 200 steps: stays finite,
     inside the arena, and agents end up less overlapped than without collision avoidance."""
     from abm_b200 import BaseEngine
@@ -404,7 +416,8 @@ def test_full_loop_with_collisions(built_lib):
         assert np.isfinite(a["x"]).all() and np.isfinite(a["theta"]).all()
         d = np.sqrt((a["x"][:, :, None] - a["x"][:, None, :]) ** 2 + (a["y"][:, :, None] - a["y"][:, None, :]) ** 2)
         overlaps[collide] = int(((d < 12.0).sum() - B * N) // 2)
-        assert eng.counters()["launches"] == 1                              # one launch for the whole run either way
+        if step_path == "one_cta_per_replicate":
+            assert eng.counters()["launches"] == 1                          # one launch for the whole run either way
         eng.close()
     print("deeply overlapping pairs without / with collision avoidance:", overlaps[False], overlaps[True])
     assert overlaps[True] <= overlaps[False]
@@ -462,12 +475,34 @@ def test_base_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
     eng.close()
 
 
-def test_fused_step_equals_separate_phases(built_lib, monkeypatch):
+def test_step_path_follows_the_batch_shape(built_lib, monkeypatch, step_path):
+    """Without ABM_BASE_FUSED the engine picks the step path from the batch shape: small replicates and batches that fill
+    the GPU with one CTA per replicate take the fused kernel, few larger replicates one grid per phase."""
+    if step_path != "one_cta_per_replicate":
+        pytest.skip("independent of the forced path")
+    from abm_b200 import BaseEngine
+    monkeypatch.delenv("ABM_BASE_FUSED", raising=False)
+    rng = np.random.default_rng(2)
+    for B, N, fused in [(1, 10, True), (40, 25, True), (8, 50, False), (2, 100, False), (700, 50, True)]:
+        eng = BaseEngine(B, N, 2, resolution=1200, width=500.0, height=500.0, visual_exclusion=True, seed=1)
+        eng.set_params(Eps_w=2.0, Eps_u=1.0)
+        eng.set_agents(x=rng.integers(20, 520, (B, N)), y=rng.integers(20, 520, (B, N)), theta=rng.uniform(0, 6, (B, N)))
+        eng.set_patches(x=rng.integers(60, 400, (B, 2)), y=rng.integers(60, 400, (B, 2)), radius=np.full((B, 2), 30.0),
+                        left=np.full((B, 2), 50.0), quality=np.full((B, 2), 0.25), id=np.tile(np.arange(2), (B, 1)))
+        eng.step(4)
+        n = eng.counters()["launches"]
+        assert n == ((1 if B <= 148 else 4) if fused else 8), (B, N, n)      # env + agents: two grids per step when not fused
+        eng.close()
+
+
+@pytest.mark.parametrize("N", [50, 100])
+def test_fused_step_equals_separate_phases(built_lib, monkeypatch, N):
     """The one-launch step (a CTA per replicate runs collisions, agent-patch interaction and Agent.update in the
     reference's order, sims.py:733-864) against one grid per phase: identical trajectories, bit for bit, over 150 steps
-    of a config-3-like sweep (occlusion, collisions, depletion and regeneration, one Eps_w per replicate)."""
+    of a config-3-like sweep (occlusion, collisions, depletion and regeneration, one Eps_w per replicate); N = 100: the
+    replicate size of the reference's figure experiments (objects in two mask words)."""
     from abm_b200 import BaseEngine
-    B, N, P, W = 24, 50, 3, 500.0
+    B, P, W = 24, 3, 500.0
     rng = np.random.default_rng(17)
     x0, y0 = rng.integers(20, 520, (B, N)), rng.integers(20, 520, (B, N))
     th0 = rng.uniform(0, 2 * np.pi, (B, N))
@@ -475,10 +510,7 @@ def test_fused_step_equals_separate_phases(built_lib, monkeypatch):
               left=np.full((B, P), 40.0), quality=np.full((B, P), 0.25), id=np.tile(np.arange(P), (B, 1)))
     res = {}
     for separate in (False, True):
-        if separate:
-            monkeypatch.setenv("ABM_BASE_SEPARATE_PHASES", "1")
-        else:
-            monkeypatch.delenv("ABM_BASE_SEPARATE_PHASES", raising=False)
+        monkeypatch.setenv("ABM_BASE_FUSED", "0" if separate else "1")
         eng = BaseEngine(B, N, P, resolution=1200, width=W, height=W, visual_exclusion=True, collide_agents=True,
                          ghost_mode=False, min_resc_perpatch=30, max_resc_perpatch=50, seed=5, keep_fields=True)
         eng.set_params(Eps_w=np.linspace(0, 5, B), Eps_u=1.0, F_N=0.5, F_R=0.5, exp_vel_max=3.0, exp_theta_min=-0.5,
@@ -591,16 +623,13 @@ def test_agent_phase_matches_reference_fixture_heterogeneous_radii(built_lib, ca
     eng.close()
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["one_cta_per_replicate", "warp_per_agent"])
 @pytest.mark.parametrize("case", load_base_hetero_cases("base_hetero_res_golden.npz"),
                          ids=lambda c: f"N{len(c['dth'])}_R{c['cfg'].R}")
-def test_agent_phase_matches_reference_fixture_heterogeneous_resolutions(built_lib, case, fused, monkeypatch):
+def test_agent_phase_matches_reference_fixture_heterogeneous_resolutions(built_lib, case):
     """v_field_res of agent_behave_param_list (sims.py:507) in the kernels (abm_base_set_agent_resolution): every agent's
     own linspace grid, projected size, wrap-around and field means (agent.py:58, 480-481, 543, 577-588;
     supcalc.py:86-91) -- against the fixture the unmodified reference's constructor path produced, in the fused
     kernel and in the one-grid-per-phase kernels."""
-    if not fused:
-        monkeypatch.setenv("ABM_BASE_SEPARATE_PHASES", "1")
     cfg, st = case["cfg"], case["st"]
     N = len(case["dth"])
     eng = _engine_for(cfg, 1, N)
