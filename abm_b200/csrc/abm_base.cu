@@ -638,6 +638,9 @@ __device__ __forceinline__ BlkShared base_block_carve(unsigned char* p, int N, i
   return s;
 }
 
+// MASK2: replicates of 65 .. 128 agents (two 64-bit words for the set of closer objects; a kernel of its own, so that the
+// usual sizes do not pay for the second word: 7 % of the configs[2] step)
+template <bool MASK2>
 __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b, unsigned char* smem_raw, unsigned step,
                                                   const int G) {
   const int N = a.N, W = a.W;
@@ -747,17 +750,17 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
           const uint32_t so = sep[j];
           const int os = (int)(short)(so & 0xffffu), oe = (int)(short)(so >> 16);
           if ((cl[j] != 0) & (os <= fe_) & (oe >= fs) & (j != jc)) {
-            if (dp[j] < dc) { if (j < 64) rel0 |= 1ull << j; else rel1 |= 1ull << (j - 64); }   // :430 strict, on the float64 values
+            if (dp[j] < dc) { if (!MASK2 || j < 64) rel0 |= 1ull << j; else rel1 |= 1ull << (j - 64); }   // :430 strict, on the float64 values
           }
         }
-        while (rel0 | rel1) {                                // usually none to three
+        while (MASK2 ? (rel0 | rel1) != 0ull : rel0 != 0ull) {   // usually none to three
           int best = -1;
-          if (__popcll(rel0) + __popcll(rel1) == 1) {
-            best = rel0 ? __ffsll((long long)rel0) - 1 : 63 + __ffsll((long long)rel1);
+          if (MASK2 ? (__popcll(rel0) + __popcll(rel1) == 1) : ((rel0 & (rel0 - 1ull)) == 0ull)) {
+            best = (!MASK2 || rel0) ? __ffsll((long long)rel0) - 1 : 63 + __ffsll((long long)rel1);
           } else {                                           // several: nearest first, ties in list order (stable sort, :424)
             double bd = 0.0; int bk = 0;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < (MASK2 ? 2 : 1); ++half) {
               for (unsigned long long m = half ? rel1 : rel0; m; m &= m - 1ull) {
                 const int j = 64 * half + __ffsll((long long)m) - 1;
                 const double dj = dp[j];
@@ -767,7 +770,7 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
               }
             }
           }
-          if (best < 64) rel0 &= ~(1ull << best); else rel1 &= ~(1ull << (best - 64));
+          if (!MASK2 || best < 64) rel0 &= ~(1ull << best); else rel1 &= ~(1ull << (best - 64));
           const uint32_t so = sep[best];
           const int os = (int)(short)(so & 0xffffu), oe = (int)(short)(so >> 16);
           if (sx <= os && os <= ex) ex = os;                                          // :432-433
@@ -822,6 +825,7 @@ size_t base_step_smem_bytes(int N, int W, int warps) {
   return warp_field_bytes(N, W) * warps + 8 * sizeof(int) * (size_t)N + 4 * sizeof(int) + 2 * sizeof(int) * (size_t)N;
 }
 
+template <bool MASK2>
 __global__ void __launch_bounds__(128, 7) base_step_kernel(const __grid_constant__ BaseKernelArgs a, unsigned phases, int collide, int n_steps,
                                                            int blk_group) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -849,7 +853,7 @@ __global__ void __launch_bounds__(128, 7) base_step_kernel(const __grid_constant
     __syncthreads();
     if (!(phases & 2u)) continue;
     // sims.py:861: Agent.update of every agent from the frozen snapshot
-    base_agents_block(a, b, smem_raw, step, blk_group);   // the whole CTA, work dealt by item
+    base_agents_block<MASK2>(a, b, smem_raw, step, blk_group);   // the whole CTA, work dealt by item
   }
 }
 
@@ -975,9 +979,14 @@ bool launch_base_step(const BaseKernelArgs& a, unsigned phases, bool collide, in
   const int blk_group = base_block_group(a.N, a.W, (size_t)(224 * 1024) / 7 - 1024);
   smem = std::max(smem, base_block_smem_bytes(a.N, a.W, blk_group));
   if (smem > (size_t)smem_max) return false;
-  static SmemOptIn optin;
-  optin.ensure(base_step_kernel, smem);
-  base_step_kernel<<<a.B, warps * 32, smem, stream>>>(a, phases, collide ? 1 : 0, n_steps, blk_group);
+  static SmemOptIn optin, optin2;
+  if (a.N > 64) {
+    optin2.ensure(base_step_kernel<true>, smem);
+    base_step_kernel<true><<<a.B, warps * 32, smem, stream>>>(a, phases, collide ? 1 : 0, n_steps, blk_group);
+  } else {
+    optin.ensure(base_step_kernel<false>, smem);
+    base_step_kernel<false><<<a.B, warps * 32, smem, stream>>>(a, phases, collide ? 1 : 0, n_steps, blk_group);
+  }
   return true;
 }
 
