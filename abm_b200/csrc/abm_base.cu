@@ -80,12 +80,43 @@ __device__ __forceinline__ double base_lin_step_of(const BaseKernelArgs& a, size
 __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int b, int lane, unsigned step) {
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * a.N, p0 = (size_t)b * a.P;
+  // The reference visits every patch (sims.py:790-858), but a patch with nobody on it is a no-op, and this loop is the one
+  // sequential piece of the step: with the 10 .. 100 patches of the reference's figure experiments most (patch, chunk)
+  // iterations find nobody.  The lanes keep their agents' centres in registers (fp32; replicates of up to 128 agents) and
+  // reject a whole patch with one compare per chunk and a vote -- conservatively (0.5 px of margin); a patch somebody may
+  // stand on goes through the exact float64 code below.  The copies follow the teleports.
+  constexpr int kStaged = 4;                    // chunks of 32 agents kept in registers
+  const bool staged = a.N <= 32 * kStaged;
+  float scx[kStaged], scy[kStaged];
+  if (staged) {
+#pragma unroll
+    for (int c = 0; c < kStaged; ++c) {
+      const int i = c * 32 + lane;
+      scx[c] = scy[c] = 3.0e18f;                // no agent: far from every patch
+      if (i < a.N) {
+        const float r = (float)base_radius_of(a, a0 + i);
+        scx[c] = a.ag.x[a0 + i] + r; scy[c] = a.ag.y[a0 + i] + r;
+      }
+    }
+  }
   for (int p = 0; p < a.P; ++p) {
     const double prad = a.pa.radius[p0 + p];
     const double pcx = (double)a.pa.x[p0 + p] + prad, pcy = (double)a.pa.y[p0 + p] + prad;
+    unsigned near_chunks = 0xffffffffu;         // chunks of 32 agents with somebody near the patch (warp-uniform)
+    if (staged) {
+      near_chunks = 0u;
+      const float fx = (float)pcx, fy = (float)pcy, reach = (float)prad + 0.5f, reach2 = reach * reach;
+#pragma unroll
+      for (int c = 0; c < kStaged; ++c) {
+        const float dx = scx[c] - fx, dy = scy[c] - fy;
+        if (__any_sync(0xffffffffu, dx * dx + dy * dy < reach2)) near_chunks |= 1u << c;
+      }
+      if (!near_chunks) continue;               // nobody can be a member: the iteration below would change nothing
+    }
     bool destroy = false;                       // warp-uniform
     double left = a.pa.left[p0 + p];            // warp-uniform running value (stored as float after every take)
     for (int c0 = 0; c0 < a.N; c0 += 32) {
+      if (staged && !((near_chunks >> (c0 >> 5)) & 1u)) continue;   // (the teleports of THIS patch go to its centre: already near)
       const int i = c0 + lane;
       const size_t g = a0 + (i < a.N ? i : 0);
       bool member = false;
@@ -124,6 +155,11 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
           if (a.teleport_exploit) {                                                   // :820-821
             a.ag.x[g] = (float)((double)a.pa.x[p0 + p] + prad - r);
             a.ag.y[g] = (float)((double)a.pa.y[p0 + p] + prad - r);
+            if (staged) {                                                             // the register copy follows
+#pragma unroll
+              for (int c = 0; c < kStaged; ++c)
+                if (c0 == 32 * c) { scx[c] = (float)pcx; scy[c] = (float)pcy; }
+            }
           }
           if (expl) {                                                                 // :824-828
             const float c = a.ag.collected[g];

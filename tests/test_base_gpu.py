@@ -249,6 +249,61 @@ def test_env_phase_matches_oracle(built_lib):
     eng.close()
 
 
+@pytest.mark.parametrize("teleport", [False, True])
+def test_env_phase_with_many_patches_matches_oracle(built_lib, teleport):
+    """The patch counts of the reference's figure experiments (N_RESOURCES up to 100): most patches have nobody on them
+    and are skipped by the kernels (a parallel pre-test, abm_base.cu) -- against the oracle, which visits every patch in
+    order like the reference (sims.py:790-858).  Some patches overlap, some contain another patch's centre (an agent
+    teleported to a patch centre lands inside the next patch), some are dead (radius 0), one replicate has no agent on
+    any patch."""
+    rng = np.random.default_rng(21)
+    B, N, P, W = 4, 70, 90, 500.0
+    cfg = rb.BaseConfig(R=320, width=W, height=W, agent_consumption=1.0, teleport_exploit=teleport)
+    from abm_b200 import BaseEngine
+    eng = BaseEngine(B, N, P, resolution=320, width=W, height=W, regenerate_patches=False, tau=cfg.Tau,
+                     teleport_exploit=teleport)
+    eng.set_params(agent_consumption=1.0)
+    states, patches = [], []
+    for b in range(B):
+        st = _random_state(rng, N, W, cfg)
+        st["override"] = rng.choice([0, 1], N); st["mode"] = st["override"].copy()
+        px, py = rng.uniform(20, 480, P), rng.uniform(20, 480, P)
+        pr = rng.choice([8.0, 15.0, 25.0], P)
+        px[1], py[1], pr[1] = px[0] + pr[0] - 20.0 + 3.0, py[0] + pr[0] - 20.0, 20.0   # centre of patch 0 inside patch 1
+        pr[5] = 0.0                                                                     # a killed patch
+        if b == 3:                                                                      # nobody anywhere near a patch
+            st["x"] = rng.integers(600, 700, N).astype(float); st["y"] = rng.integers(600, 700, N).astype(float)
+        else:                                                                           # a few agents right on patch 0
+            st["x"][:4] = px[0] + pr[0] - 10.0 + np.array([0.0, 1.0, -2.0, 3.0]); st["y"][:4] = py[0] + pr[0] - 10.0
+        states.append(st)
+        patches.append(dict(x=px, y=py, radius=pr, left=rng.choice([0.5, 3.0, 400.0], P),
+                            quality=rng.choice([0.25, 0.75, 1.0], P), id=np.arange(P)))
+    S = {k: np.stack([s[k] for s in states]) for k in states[0] if k != "radius"}
+    Pm = {k: np.stack([p_[k] for p_ in patches]) for k in patches[0]}
+    eng.set_agents(x=S["x"], y=S["y"], theta=S["theta"], vel=S["vel"], w=S["w"], u=S["u"], collected=S["collected"],
+                   collected_before=S["collected_before"], env_status=S["env_status"], override_mode=S["override"],
+                   mode=S["mode"], patch_id=S["patch_id"], novelty=S["novelty"])
+    eng.set_patches(**Pm)
+    eng.step(1, phases=PHASE_ENV)
+    got, gp = eng.get_agents(), eng.get_patches()
+    n_on, n_depleted = 0, 0
+    for b in range(B):
+        st = {k: (np.array(v, dtype=float) if k in ("x", "y", "theta", "collected", "collected_before") else np.array(v))
+              for k, v in states[b].items()}
+        pa = {k: np.array(v, dtype=float if k != "id" else int) for k, v in patches[b].items()}
+        depleted = rb.base_patch_phase(st, pa, cfg)
+        n_depleted += len(depleted); n_on += int((st["env_status"] == 1).sum())
+        for k in ("x", "y", "theta", "collected", "collected_before"):
+            np.testing.assert_allclose(got[k][b], st[k], rtol=RTOL, atol=1e-5, err_msg=k)
+        assert np.array_equal(got["env_status"][b], st["env_status"])
+        assert np.array_equal(got["patch_id"][b], st["patch_id"])
+        np.testing.assert_allclose(gp["left"][b], pa["left"], rtol=RTOL, atol=1e-6)
+        for p_ in depleted:
+            assert gp["radius"][b][p_] == 0.0
+    assert n_on > 20 and n_depleted > 0
+    eng.close()
+
+
 def test_full_loop_runs_and_forages(built_lib, step_path):
     """configs[0] shape (N=10, 3 patches, R=1200) for 300 steps with the engine's own RNG:
     sanity properties -- agents stay inside the arena, some resource gets collected, patches
