@@ -758,8 +758,8 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
       c.params += (size_t)e->chunk_b0 * a.param_stride;
       if (c.fields_out) c.fields_out += o * a.W;
       if (c.terms_out) c.terms_out += o * 6;
-      abm::launch_vf_step_sym(c, wide3, st);
-    } else if (use_sym) abm::launch_vf_step_sym(a, wide3, st);
+      abm::launch_vf_step_sym(c, wide3, uniform_r, st);
+    } else if (use_sym) abm::launch_vf_step_sym(a, wide3, uniform_r, st);
     else if (use_warp) abm::launch_vf_step_warp(a, cull, uniform_r, st);
     else abm::launch_vf_step(a, uniform_r, cull, st);
     if (e->n_peers > 0 && !fused_close) { abm::launch_vf_publish(a, st); ++e->launches; }

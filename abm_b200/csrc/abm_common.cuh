@@ -141,9 +141,9 @@ constexpr int kMaxTileList = 1024;   // tiles per replicate the culling list can
                                      // N <= 131072 at 128)
 size_t vf_step_smem_bytes(int threads, int W);
 // symmetric kernel (abm_vf_sym.cu): every unordered pair once, all rows of a replicate in one CTA
-size_t vf_sym_smem_bytes(int Np, int W, bool wide3);
+size_t vf_sym_smem_bytes(int Np, int W, bool wide3, bool het = false);
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit);
-void launch_vf_step_sym(const VFKernelArgs& a, bool wide3, cudaStream_t stream);
+void launch_vf_step_sym(const VFKernelArgs& a, bool wide3, bool uniform_r, cudaStream_t stream);
 int vf_step_threads(int tile_count, int n_replicates, int n_sms);
 // warp-per-focal-agent kernel (abm_vf_warp.cu): one large sparse swarm and its tiles
 void launch_vf_step_warp(const VFKernelArgs& a, bool cull, bool uniform_r, cudaStream_t stream);

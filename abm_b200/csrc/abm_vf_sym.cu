@@ -25,7 +25,7 @@
 // fp64 path (the reference's own operation sequence, abm_vf_device.cuh), also per warp and 32 at a time -- while the
 // other warps keep running their pair loops.
 //
-// Used when all radii are equal, no distance culling is wanted, the engine owns whole replicates, the rows fit in
+// Used when no distance culling is wanted (unequal radii: the HET variants, two half widths per pair), the engine owns whole replicates, the rows fit in
 // shared memory and the batch is large enough to fill the GPU with one CTA per replicate; otherwise vf_step_kernel
 // (abm_vf.cu) or vf_step_warp_kernel (abm_vf_warp.cu) runs (abm_api.cu).
 #include "abm_vf_device.cuh"
@@ -53,6 +53,7 @@ __device__ __forceinline__ void or_if(uint32_t& acc, bool p, uint32_t m) {
 
 struct SymShared {
   float4* ag;          // [Np] (x, y, heading constant, the same + half a turn); padding agents beyond N are far away
+  uint32_t rad_s;      // shared-space address of the radii [Np] (unequal radii: the HET variants), else 0
   uint32_t* rows;      // [W + 5][Np] padded rows (W + 2 words) + three scratch words (draws of slow directions land there)
   uint32_t* queue;     // [kSymQueueCap][2]  directions waiting for fp64 (focal << 16 | object, k << 16 | h), per warp
   uint32_t* warpq;     // [warps][kSymWarpQ] per-warp queue of pairs with directions off the fast path
@@ -102,28 +103,37 @@ __device__ __forceinline__ void sym_slow_dir(const VFKernelArgs& a, uint32_t row
   }
 }
 template <bool TORUS, int RC>
-static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_t ag_s, uint32_t rows_s, uint32_t queue_s,
+static __device__ __noinline__ void sym_slow_pair(const VFKernelArgs& a, uint32_t ag_s, uint32_t rad_s, uint32_t rows_s, uint32_t queue_s,
                                                   uint32_t qcount_s, int fq_cap, int Np, int i, int j, uint32_t dirs) {
   using K = PairK<RC>;
   if ((i >= a.N) | (j >= a.N)) return;                                // padding agents
   const float4 ia = lds_f4(ag_s + 16u * (uint32_t)i), ja = lds_f4(ag_s + 16u * (uint32_t)j);
   if ((ia.x == ja.x) & (ia.y == ja.y)) return;                        // vf_supcalc.py:57
-  float dx = ja.x - ia.x, dy = ja.y - ia.y;
+  // unequal radii: centre = position + own radius (vf_supcalc.py:42, 60-63), and i sees j under j's radius
+  const float ri = rad_s ? lds_f32(rad_s + 4u * (uint32_t)i) : a.sym_radius;
+  const float rj = rad_s ? lds_f32(rad_s + 4u * (uint32_t)j) : a.sym_radius;
+  const float dr = rj - ri;
+  float dx = (ja.x - ia.x) + dr, dy = (ja.y - ia.y) + dr;             // positions first (exact for close neighbours), then radii
   bool wrap_tie = false;
   if (TORUS) {
-    dx = torus_delta(ja.x, ia.x, a.width, a.half_w, wrap_tie);
-    dy = torus_delta(ja.y, ia.y, a.height, a.half_h, wrap_tie);
+    dx = torus_delta_r(ja.x, ia.x, dr, a.width, a.half_w, wrap_tie);
+    dy = torus_delta_r(ja.y, ia.y, dr, a.height, a.half_h, wrap_tie);
   }
   const float d2 = fmaf(dx, dx, dy * dy);
-  const float q = a.sym_radius * rsqrt_approx(d2);
-  const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
-  const float yr = y + kMagic;
-  const int h = __float_as_int(yr) - kMagicBits;
-  const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
+  const float rs = rsqrt_approx(d2);
   const uint32_t nb = sym_bearing_bits(dx, dy, kBearingA6);           // bearing of j seen from i
   const uint32_t stride_b = 4u * (uint32_t)Np;
-  if (dirs & 1u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
-  if (dirs & 2u) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
+#pragma unroll 1
+  for (int dir = 0; dir < 2; ++dir) {                                  // 0: i sees j (j's radius), 1: j sees i
+    if (!((dirs >> dir) & 1u)) continue;
+    const float q = (dir ? ri : rj) * rs;
+    const float y = fmaf(atan_unit(q), K::y_scale(a), -0.5f);
+    const float yr = y + kMagic;
+    const int h = __float_as_int(yr) - kMagicBits;
+    const bool flagged = !(q <= 1.0f) | (fmaf(y, a.nthr_h1, fabsf(y - (yr - kMagic))) > a.thr_h0) | wrap_tie;
+    if (dir == 0) sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, i, j, nb, __float_as_uint(ia.z), h, flagged);
+    else sym_slow_dir<RC>(a, rows_s, queue_s, qcount_s, fq_cap, stride_b, j, i, nb, __float_as_uint(ja.w), h, flagged);
+  }
 }
 
 // One entry of a warp's slow queue = one unordered pair with directions off the fast path: agent i | agent j << 10 |
@@ -163,7 +173,7 @@ static __device__ __noinline__ void sym_slow_batch(const VFKernelArgs& a, const 
   if (a.flags & (1u << 30)) return;   // timing probe (ABM_VF_DEBUG_SKIP_SLOW, results are wrong): what the slow pairs cost
   const uint32_t dirs = ent >> 20;
   const int warp = threadIdx.x >> 5;
-  if (dirs) sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rows_s, sh.queue_s + 8u * (uint32_t)(warp * sh.fq_cap),
+  if (dirs) sym_slow_pair<TORUS, RC>(a, sh.ag_s, sh.rad_s, sh.rows_s, sh.queue_s + 8u * (uint32_t)(warp * sh.fq_cap),
                                      sh.qcount_s + 8u + 4u * (uint32_t)warp, sh.fq_cap, sh.Np, (int)(ent & 1023u),
                                      (int)((ent >> 10) & 1023u), dirs);
   __syncwarp();
@@ -243,30 +253,21 @@ __device__ __forceinline__ void sym_push_round(const VFKernelArgs& a, const SymS
 // (already redirected to the scratch word when the direction is off the fast path), the 2h-ones mask.
 struct SymStep {
   int ps_i, ps_j;
-  uint32_t mask, mask_hi;   // 2h ones: bits 0..31 / 32..63
+  uint32_t mask, mask_hi;   // 2h ones: bits 0..31 / 32..63 (the lane's own direction; both when all radii are equal)
+  uint32_t mask_j, mask_hi_j;   // the partner's direction (unequal radii: its half width comes from the OTHER radius)
   bool slow_i, slow_j;
 };
 
 // Pure arithmetic (no shared-memory access): the compiler interleaves two of these.
 // BOTH: evaluate both directions; otherwise only the lane's own.
-template <bool TORUS, bool FULL_FOV, int RC, bool BOTH, bool WIDE3>
-__device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, float xi, float yi, uint32_t hc_i,
-                                            const SymConsts& c) {
-  using K = PairK<RC>;
-  SymStep r;
-  float dx = o.x - xi, dy = o.y - yi;
-  bool wrap_tie = false;
-  if (TORUS) {                                               // vf_supcalc.py:70-83
-    dx = torus_delta(o.x, xi, a.width, a.half_w, wrap_tie);
-    dy = torus_delta(o.y, yi, a.height, a.half_h, wrap_tie);
-  }
-  const float d2 = fmaf(dx, dx, dy * dy);
-  // ---- half width h = floor(atan(r/d) * R/2pi) (vf_supcalc.py:96-99, :114-117), shared by both directions.
-  //      Four-term series in q = r/d (truncation error 3e-6 bins at h = 32, q = 0.17, R = 1200); larger q -> slow path.
-  //      (With the fast path ending at h = 16 -- intervals of two words -- the pairs between 56 and 112 px, three
-  //      quarters of all wide ones, went through the out-of-line slow path: 29 % of the kernel's warp samples.) ----
-  const float rs = rsqrt_approx(d2);
-  const float qs = rs * c.rS;                                // q * R/2pi
+// One direction's half width: h = floor(atan(r / d) R / 2pi) from qs = (r R / 2pi) / d (vf_supcalc.py:96-99, :114-117).
+struct SymHalf { uint32_t hraw, mask, mask_hi; bool slow; };
+template <int RC, bool WIDE3>
+__device__ __forceinline__ SymHalf sym_half_width(const VFKernelArgs& a, float qs, const SymConsts& c) {
+  // Four-term series in q = r/d (truncation error 3e-6 bins at h = 32, q = 0.17, R = 1200); larger q -> slow path.
+  // (With the fast path ending at h = 16 -- intervals of two words -- the pairs between 56 and 112 px, three
+  // quarters of all wide ones, went through the out-of-line slow path: 29 % of the kernel's warp samples.)
+  SymHalf r;
   const float zs = qs * qs;
   float p;
   if (WIDE3) { p = fmaf(zs, c.c7s, c.c5s); p = fmaf(p, zs, c.c3s); }   // four terms: exact to the guard band up to q = 0.18
@@ -274,35 +275,77 @@ __device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, flo
   p = fmaf(p, zs, 1.0f);
   const float y = fmaf(qs, p, -0.5f);
   const float yr = y + kMagic;
-  const uint32_t hraw = __float_as_uint(yr);                 // h + kMagicBits
+  r.hraw = __float_as_uint(yr);                              // h + kMagicBits
   // (the limit is on qs, not on y: beyond q = 0.18 / 0.12 the truncated series is inexact, and the four-term one finally
   // changes sign; at R = 1200 the two-word limit h <= 16 is q < 0.087 and the three-term series only grows: the
   // benchmark's variant keeps its immediate compare)
   const bool too_wide = (!WIDE3 && RC == 1200) ? !(y < 16.5f) : !(qs < c.qs_max);   // also d2 == 0 (inf / NaN)
-  const bool slow_h = too_wide | (fabsf(y - (yr - kMagic)) > a.sym_thr_h) | wrap_tie;
-  const uint32_t w2 = 2u * hraw - 2u * (uint32_t)kMagicBits; // 2h
+  r.slow = too_wide | (fabsf(y - (yr - kMagic)) > a.sym_thr_h);
+  const uint32_t w2 = 2u * r.hraw - 2u * (uint32_t)kMagicBits; // 2h
   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask) : "r"(w2));                                      // min(2h, 32) ones
   r.mask_hi = 0u;
   if (WIDE3) asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r.mask_hi) : "r"((uint32_t)max((int)w2 - 32, 0)));   // the ones beyond 32
-  const int bh = 32 + kMagicBits - (int)hraw;                // ps = bin index + 32 - h
+  return r;
+}
+
+// Pure arithmetic (no shared-memory access): the compiler interleaves two of these.
+// BOTH: evaluate both directions; otherwise only the lane's own.
+// HET: unequal radii -- centres are positions + OWN radii (vf_supcalc.py:42, 60-63: distance and bearing are still shared by
+// the two directions, bit for bit: every term of the other direction's difference is the exact negative), but i sees j under
+// j's radius and j sees i under i's: two half widths.  rS_o / rS_me: the partner's / the lane's radius times R / 2pi,
+// dr: partner's radius - own.
+template <bool TORUS, bool FULL_FOV, int RC, bool BOTH, bool WIDE3, bool HET = false>
+__device__ __forceinline__ SymStep sym_eval(const VFKernelArgs& a, float4 o, float xi, float yi, uint32_t hc_i,
+                                            const SymConsts& c, float rS_o = 0.f, float rS_me = 0.f, float dr = 0.f) {
+  SymStep r;
+  float dx = o.x - xi, dy = o.y - yi;
+  if (HET) { dx += dr; dy += dr; }                           // positions first (exact for close neighbours), then radii
+  bool wrap_tie = false;
+  if (TORUS) {                                               // vf_supcalc.py:70-83
+    if (HET) {
+      dx = torus_delta_r(o.x, xi, dr, a.width, a.half_w, wrap_tie);
+      dy = torus_delta_r(o.y, yi, dr, a.height, a.half_h, wrap_tie);
+    } else {
+      dx = torus_delta(o.x, xi, a.width, a.half_w, wrap_tie);
+      dy = torus_delta(o.y, yi, a.height, a.half_h, wrap_tie);
+    }
+  }
+  if (HET) wrap_tie |= (o.x == xi) & (o.y == yi);            // coincident POSITIONS are skipped (vf_supcalc.py:57): slow path
+  const float d2 = fmaf(dx, dx, dy * dy);
+  // ---- half width(s): shared by both directions when all radii are equal ----
+  const float rs = rsqrt_approx(d2);
+  const SymHalf hi_ = sym_half_width<RC, WIDE3>(a, rs * (HET ? rS_o : c.rS), c);   // q * R/2pi
+  const bool slow_h = hi_.slow | wrap_tie;
+  r.mask = hi_.mask; r.mask_hi = hi_.mask_hi;
+  const int bh = 32 + kMagicBits - (int)hi_.hraw;            // ps = bin index + 32 - h
   // ---- bearing (shared), bin index of both directions ----
   const uint32_t nb = sym_bearing_bits(dx, dy, c.a6);
   r.slow_i = slow_h;
   const int ps_i = sym_side_k<RC, true>(a, nb, hc_i, bh, r.slow_i, c.half64);
   bool draw_i = !r.slow_i;
   if (!FULL_FOV) {
-    const int pe = ps_i + 2 * ((int)hraw - kMagicBits);
+    const int pe = ps_i + 2 * ((int)hi_.hraw - kMagicBits);
     draw_i &= ((unsigned)(ps_i - a.fov0p) < a.span) | ((unsigned)(pe - a.fov0p) < a.span);   // vf_supcalc.py:119
   }
   r.ps_i = draw_i ? ps_i : c.scratch_pos;
   r.slow_j = false;
   r.ps_j = c.scratch_pos;
+  r.mask_j = r.mask; r.mask_hi_j = r.mask_hi;
   if (BOTH) {
+    uint32_t hraw_j = hi_.hraw;
+    int bh_j = bh;
     r.slow_j = slow_h;
-    const int ps_j = sym_side_k<RC, true>(a, nb, __float_as_uint(o.w), bh, r.slow_j, c.half64);   // o.w: heading constant + half a turn
+    if (HET) {                                               // the partner sees this lane's agent under ITS radius
+      const SymHalf hj = sym_half_width<RC, WIDE3>(a, rs * rS_me, c);
+      r.slow_j = hj.slow | wrap_tie;
+      r.mask_j = hj.mask; r.mask_hi_j = hj.mask_hi;
+      hraw_j = hj.hraw;
+      bh_j = 32 + kMagicBits - (int)hj.hraw;
+    }
+    const int ps_j = sym_side_k<RC, true>(a, nb, __float_as_uint(o.w), bh_j, r.slow_j, c.half64);   // o.w: heading constant + half a turn
     bool draw_j = !r.slow_j;
     if (!FULL_FOV) {
-      const int pe = ps_j + 2 * ((int)hraw - kMagicBits);
+      const int pe = ps_j + 2 * ((int)hraw_j - kMagicBits);
       draw_j &= ((unsigned)(ps_j - a.fov0p) < a.span) | ((unsigned)(pe - a.fov0p) < a.span);
     }
     r.ps_j = draw_j ? ps_j : c.scratch_pos;
@@ -328,16 +371,18 @@ __device__ __forceinline__ void sym_red(uint32_t row, uint32_t stride_b, int ps,
   }
 }
 
-size_t vf_sym_smem_bytes(int Np, int W, bool wide3) {
+size_t vf_sym_smem_bytes(int Np, int W, bool wide3, bool het) {
   return sizeof(float4) * (size_t)Np + sizeof(uint32_t) * (size_t)(W + (wide3 ? 5 : 3)) * Np + 2 * sizeof(uint32_t) * kSymQueueCap +
-         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + 96;   // counters: 2 + one per warp (<= 16)
+         sizeof(uint32_t) * kSymWarpQ * (size_t)(Np / 64) + 96 +   // counters: 2 + one per warp (<= 16)
+         (het ? sizeof(float) * (size_t)Np + 128 : 0);            // the radii (128-byte aligned)
 }
 
 // NPC > 0: compile-time padded replicate size (row stride becomes an immediate), 0: the run-time argument.
 // WIDE3: the fast path takes intervals of up to 64 bins (three row words, four-term series) instead of 32 -- a few more
 // instructions on every pair, but in a crowded scene the pairs between 56 and 112 px stay out of the slow path (the
 // engine switches on the measured share of slow pairs, abm_api.cu).
-template <bool TORUS, bool FULL_FOV, int RC, int NPC, bool WIDE3>
+// HET: unequal radii (two half widths per pair, sym_eval); the radii live in shared memory next to the records.
+template <bool TORUS, bool FULL_FOV, int RC, int NPC, bool WIDE3, bool HET>
 __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_constant__ VFKernelArgs a, int Np_arg) {
   const int Np = NPC ? NPC : Np_arg;
   using K = PairK<RC>;
@@ -349,6 +394,9 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   sh.queue = sh.rows + (size_t)(a.W + kRowExtra) * Np;
   sh.warpq = sh.queue + 2 * kSymQueueCap;
   sh.qcount = reinterpret_cast<int*>(sh.warpq + kSymWarpQ * (Np / 64));
+  // [Np] (HET only), on a 128-byte boundary: the pair loop walks it with the same XOR as the rows
+  float* rad = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sh.qcount + 24) + 127) & ~uintptr_t(127));
+  sh.rad_s = HET ? smem_u32(rad) : 0u;
   sh.Np = Np; sh.N = a.N;
   sh.fq_cap = kSymQueueCap / (int)(blockDim.x >> 5);
   sh.rep_in = a.rec_in + (size_t)blockIdx.x * a.N; sh.th_in = a.theta + (size_t)blockIdx.x * a.N;
@@ -374,6 +422,7 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
       v = make_float4(-1.0e6f - 4096.0f * (float)(j - N), -1.0e6f, 0.f, 0.f);
     }
     sh.ag[j] = v;
+    if (HET) rad[j] = (j < N) ? rep_in[j].z : a.sym_radius;
   }
   for (int w = tid; w < (a.W + kRowExtra) * Np; w += T) sh.rows[w] = 0u;
   if (tid < 18) sh.qcount[tid] = 0;
@@ -404,15 +453,17 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
   //      evaluated once, and own / partner rows of a warp instruction still hit 32 different banks. ----
   {
     const float4 me0 = sh.ag[(2 * warp << 5) + lane], me1 = sh.ag[((2 * warp + 1) << 5) + lane];
+    const float r0 = HET ? rad[(2 * warp << 5) + lane] : 0.f, r1 = HET ? rad[((2 * warp + 1) << 5) + lane] : 0.f;
 #pragma unroll 1
     for (int s = 1; s < 32; ++s) {
       const int sel = (lane >> (31 - __clz(s))) & 1;
       const int i = ((2 * warp + sel) << 5) + lane, j = i ^ s;
       const float4 me = sel ? me1 : me0;
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3>(a, lds_f4(ag_s + 16u * (uint32_t)j), me.x, me.y,
-                                                            __float_as_uint(me.z), c);
+      const float rme = sel ? r1 : r0, rj = HET ? rad[j] : 0.f;
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3, HET>(a, lds_f4(ag_s + 16u * (uint32_t)j), me.x, me.y,
+                                                                 __float_as_uint(me.z), c, rj * S, rme * S, rj - rme);
       sym_red<WIDE3>(rows_s + 4u * (uint32_t)i, stride_b, A.ps_i, A.mask, A.mask_hi);
-      sym_red<WIDE3>(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask, A.mask_hi);
+      sym_red<WIDE3>(rows_s + 4u * (uint32_t)j, stride_b, A.ps_j, A.mask_j, A.mask_hi_j);
       sym_push<TORUS, RC>(a, sh, wq, wcount, lane, i, j, A.slow_i, A.slow_j, ws);
     }
   }
@@ -433,17 +484,20 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
     float4 oA = lds_f4(rec_j0), oB = lds_f4(rec_j0 ^ 16u);
     uint32_t fi = 0u, fj = 0u, tbit = 1u;                  // slow flags of the round (own / partner's direction), bit s = step s
     const uint32_t rec_j1 = rec_j0 ^ 16u, row_j1 = row_j0 ^ 4u;
+    const float rme = HET ? rad[i] : 0.f, rSme = rme * S;
+    const uint32_t rad_j0 = sh.rad_s + 4u * (uint32_t)j0;      // (the radii are 4-byte words like the rows: same XOR walk)
 #pragma unroll 1
     for (uint32_t o16 = 32u; o16 <= 512u; o16 += 32u) {       // o16 = 16 (s + 2), s = 0, 2, .. 30: ONE induction variable
       // prefetch the next two partner records (the last iteration reads block J ^ 1: harmless)
       const float4 nA = lds_f4(rec_j0 ^ o16), nB = lds_f4(rec_j1 ^ o16);
-      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3>(a, oA, me.x, me.y, __float_as_uint(me.z), c);
-      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3>(a, oB, me.x, me.y, __float_as_uint(me.z), c);
       const uint32_t o4 = (o16 >> 2) - 8u;                     // 4 s
+      const float rA = HET ? lds_f32(rad_j0 ^ o4) : 0.f, rB = HET ? lds_f32(rad_j0 ^ 4u ^ o4) : 0.f;
+      const SymStep A = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3, HET>(a, oA, me.x, me.y, __float_as_uint(me.z), c, rA * S, rSme, rA - rme);
+      const SymStep B = sym_eval<TORUS, FULL_FOV, RC, true, WIDE3, HET>(a, oB, me.x, me.y, __float_as_uint(me.z), c, rB * S, rSme, rB - rme);
       sym_red<WIDE3>(row_i, stride_b, A.ps_i, A.mask, A.mask_hi);
-      sym_red<WIDE3>(row_j0 ^ o4, stride_b, A.ps_j, A.mask, A.mask_hi);
+      sym_red<WIDE3>(row_j0 ^ o4, stride_b, A.ps_j, A.mask_j, A.mask_hi_j);
       sym_red<WIDE3>(row_i, stride_b, B.ps_i, B.mask, B.mask_hi);
-      sym_red<WIDE3>(row_j1 ^ o4, stride_b, B.ps_j, B.mask, B.mask_hi);
+      sym_red<WIDE3>(row_j1 ^ o4, stride_b, B.ps_j, B.mask_j, B.mask_hi_j);
       // ---- off the fast path (~1 % of the directions): remembered, pushed after the round ----
       or_if(fi, A.slow_i, tbit);
       or_if(fj, A.slow_j, tbit);
@@ -494,34 +548,38 @@ __global__ void __launch_bounds__(512, 1) vf_step_sym_kernel(const __grid_consta
 }
 
 bool vf_sym_applicable(const VFKernelArgs& a, bool uniform_r, bool cull, size_t smem_limit) {
-  if (!uniform_r || cull) return false;
+  if (cull) return false;
   if (a.tile_begin != 0 || a.tile_count != a.N) return false;
   const int Np = (a.N + 63) / 64 * 64;
   if (Np > 1024) return false;   // 16 warps at most; queue entries hold 16-bit agent indices
-  return vf_sym_smem_bytes(Np, a.W, true) <= smem_limit;
+  return vf_sym_smem_bytes(Np, a.W, true, !uniform_r) <= smem_limit;
 }
 
-template <bool TORUS, bool FULL_FOV, int RC, int NPC, bool WIDE3>
+template <bool TORUS, bool FULL_FOV, int RC, int NPC, bool WIDE3, bool HET>
 static void launch_sym_variant(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
   static SmemOptIn optin;   // per device (abm_common.cuh)
-  optin.ensure(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC, WIDE3>, smem);
-  vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC, WIDE3><<<a.B, threads, smem, stream>>>(a, Np);
+  optin.ensure(vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC, WIDE3, HET>, smem);
+  vf_step_sym_kernel<TORUS, FULL_FOV, RC, NPC, WIDE3, HET><<<a.B, threads, smem, stream>>>(a, Np);
 }
 
 template <bool TORUS, bool WIDE3>
-static void launch_sym_fov(const VFKernelArgs& a, int Np, int threads, size_t smem, cudaStream_t stream) {
-  if (a.full_fov && a.R == 1200 && Np == 1024) launch_sym_variant<TORUS, true, 1200, 1024, WIDE3>(a, Np, threads, smem, stream);
-  else if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200, 0, WIDE3>(a, Np, threads, smem, stream);
-  else if (a.full_fov) launch_sym_variant<TORUS, true, 0, 0, WIDE3>(a, Np, threads, smem, stream);
-  else launch_sym_variant<TORUS, false, 0, 0, WIDE3>(a, Np, threads, smem, stream);
+static void launch_sym_fov(const VFKernelArgs& a, int Np, int threads, size_t smem, bool het, cudaStream_t stream) {
+  if (het) {   // unequal radii: the generic instantiations only
+    if (a.full_fov) launch_sym_variant<TORUS, true, 0, 0, WIDE3, true>(a, Np, threads, smem, stream);
+    else launch_sym_variant<TORUS, false, 0, 0, WIDE3, true>(a, Np, threads, smem, stream);
+  } else if (a.full_fov && a.R == 1200 && Np == 1024) launch_sym_variant<TORUS, true, 1200, 1024, WIDE3, false>(a, Np, threads, smem, stream);
+  else if (a.full_fov && a.R == 1200) launch_sym_variant<TORUS, true, 1200, 0, WIDE3, false>(a, Np, threads, smem, stream);
+  else if (a.full_fov) launch_sym_variant<TORUS, true, 0, 0, WIDE3, false>(a, Np, threads, smem, stream);
+  else launch_sym_variant<TORUS, false, 0, 0, WIDE3, false>(a, Np, threads, smem, stream);
 }
 
-void launch_vf_step_sym(const VFKernelArgs& a, bool wide3, cudaStream_t stream) {
+void launch_vf_step_sym(const VFKernelArgs& a, bool wide3, bool uniform_r, cudaStream_t stream) {
   const int Np = (a.N + 63) / 64 * 64;
   const int threads = 32 * (Np / 64);
-  const size_t smem = vf_sym_smem_bytes(Np, a.W, wide3);
-  if (a.boundary == 1) { if (wide3) launch_sym_fov<true, true>(a, Np, threads, smem, stream); else launch_sym_fov<true, false>(a, Np, threads, smem, stream); }
-  else { if (wide3) launch_sym_fov<false, true>(a, Np, threads, smem, stream); else launch_sym_fov<false, false>(a, Np, threads, smem, stream); }
+  const bool het = !uniform_r;
+  const size_t smem = vf_sym_smem_bytes(Np, a.W, wide3, het);
+  if (a.boundary == 1) { if (wide3) launch_sym_fov<true, true>(a, Np, threads, smem, het, stream); else launch_sym_fov<true, false>(a, Np, threads, smem, het, stream); }
+  else { if (wide3) launch_sym_fov<false, true>(a, Np, threads, smem, het, stream); else launch_sym_fov<false, false>(a, Np, threads, smem, het, stream); }
 }
 
 }  // namespace abm

@@ -38,8 +38,8 @@ def _force_kernel(monkeypatch, kernel):
 
 
 def _ran_forced_kernel(eng, kernel):
-    """False when the forced kernel does not apply to the scene (the symmetric kernel needs equal radii and
-    N <= 1024) -- the caller skips; any other mismatch is a failure."""
+    """False when the forced kernel does not apply to the scene (the symmetric kernel needs N <= 1024) -- the caller
+    skips; any other mismatch is a failure."""
     if kernel == "auto":
         return True
     if eng.last_kernel() == KERNEL_NAMES[kernel]:
@@ -162,6 +162,9 @@ SCENES = [
     (1, 300, 1200, 1559.0, "walls", 1.0, 10.0),      # more than one CTA per replicate
     (4, 10, 320, 900.0, "walls", 1.0, 10.0),
     (1, 600, 1200, 400.0, "walls", 1.0, 10.0),       # crowded, > one record stage
+    (2, 90, 1200, 500.0, "walls", 1.0, 0.0),         # unequal radii (0: drawn per agent): two half widths per pair
+    (2, 130, 1200, 600.0, "infinite", 1.0, 0.0),     # ... on the torus, crowded
+    (1, 75, 2400, 450.0, "walls", 0.5, 0.0),         # ... limited FOV
 ]
 
 
@@ -171,17 +174,19 @@ def test_step_matches_oracle_random(built_lib, monkeypatch, B, N, R, W, boundary
     _force_kernel(monkeypatch, kernel)
     rng = np.random.default_rng(1234 + N + R)
     x, y, th, v = _random_scene(rng, B, N, W)
+    if radius == 0.0:                                                    # every agent its own radius
+        radius = rng.choice([4.0, 7.5, 10.0, 16.0], (B, N)).astype(np.float32)
     fov = (-fovr * np.pi, fovr * np.pi)
     eng = _engine(None, B, N, resolution=R, fov=fov, boundary=boundary, width=W, height=W)
     eng.set_params()
     eng.set_state(x, y, th, v, radius)
     eng.step(1)
-    assert _ran_forced_kernel(eng, kernel)                               # equal radii, N <= 1024: every kernel applies
+    assert _ran_forced_kernel(eng, kernel)                               # N <= 1024: every kernel applies
     fields, terms, st = eng.fields(), eng.terms(), eng.get_state()
     cfg = rs.VFConfig(R=R, fov=fov, boundary=boundary, width=W, height=W)
-    sample = range(N) if N <= 120 else sorted(rng.choice(N, 60, replace=False).tolist())
+    sample = range(N) if N <= 130 else sorted(rng.choice(N, 60, replace=False).tolist())
     for b in range(B):
-        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], radius, cfg, agents=sample)
+        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], radius if np.ndim(radius) == 0 else radius[b], cfg, agents=sample)
         idx = np.array(list(sample))
         assert np.array_equal(fields[b][idx], ref["rows"][idx][:, ::-1]), "stored field mismatch"
         np.testing.assert_allclose(terms[b][idx], ref["terms"][idx], rtol=RTOL, atol=1e-9)
@@ -444,7 +449,8 @@ def test_spatial_sort_is_invisible(built_lib, monkeypatch):
     (5, 40, 1200, "walls", 1.0),        # a single block pair
     (1, 700, 2400, "infinite", 0.75),   # large R
 ])
-def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, boundary, fov_ratio):
+@pytest.mark.parametrize("radii", ["equal", "unequal"])
+def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, boundary, fov_ratio, radii):
     """The three step kernels (every unordered pair once / one thread per focal agent / one warp per focal agent) are
     independent implementations of the same step; with the fp64 re-evaluation on, both must produce the exact
     fields, so they agree bit for bit -- fields, terms and new state -- also over several steps,
@@ -455,14 +461,16 @@ def test_symmetric_and_onesided_kernels_agree(built_lib, monkeypatch, B, N, R, b
     x, y, th, v = _random_scene(rng, B, N, W)
     x[0, 1], y[0, 1] = x[0, 0], y[0, 0]       # coincident pair (vf_supcalc.py:57)
     x[0, 3], y[0, 3] = x[0, 2] + 3.0, y[0, 2] # overlapping pair (d < r)
+    rad = 10.0 if radii == "equal" else rng.choice([5.0, 10.0, 12.5, 20.0], (B, N)).astype(np.float32)
     fov = (-fov_ratio * np.pi, fov_ratio * np.pi)
     res = {}
     for kern in ("onesided", "symmetric", "warp"):
         monkeypatch.setenv("ABM_VF_KERNEL", kern)
         eng = VFEngine(B, N, resolution=R, width=W, height=W, boundary=boundary, fov=fov, keep_fields=True,
                        keep_terms=True, spatial_sort=False)
-        eng.set_params(); eng.set_state(x, y, th, v, 10.0)
+        eng.set_params(); eng.set_state(x, y, th, v, rad)
         eng.step(1)
+        assert _ran_forced_kernel(eng, kern) or R == 2400     # (700 rows of 2400 bins do not fit the symmetric kernel's shared memory)
         f1, t1 = eng.fields_packed().copy(), eng.terms().copy()
         eng.step(3)
         res[kern] = (f1, t1, eng.fields_packed(), eng.terms(), eng.get_state(), eng.counters())
