@@ -166,6 +166,29 @@ constexpr double kWideThreshold = 0.04;   // share of the unordered pairs off th
 
 inline bool sym_ok_forced_off(const char* force) { return force && strcmp(force, "onesided") == 0; }
 
+// Small batches cannot fill the GPU with one CTA per replicate (or per tile of 256 focal agents): a warp per focal
+// agent spreads them over all SMs.  Cost models fitted to B200 measurements at R = 1200 (scratch/c2_probe.py), in
+// microseconds: warp kernel 10 + 1.2e-3 agents + 4.0e-6 ordered pairs; symmetric kernel 45 + 0.05 Np + 1.6e-4 Np^2
+// per wave of resident CTAs; one-sided kernel 45 + 0.2 N per wave.  E.g. one run of 100 agents: 12 us instead of 54
+// per step; 16 x 1024: 97 instead of 270; from 48 x 1024 or 256 x 256 upwards the symmetric kernel wins.
+bool vf_small_grid(const abm_engine* e, bool sym_ok) {
+  const int B = e->cfg.n_replicates, N = e->cfg.n_agents;
+  const double agents = (double)B * N, pairs = agents * (N - 1);
+  const double t_warp = 10.0 + 1.2e-3 * agents + 4.0e-6 * pairs;
+  double t_cta;
+  if (sym_ok) {
+    const int Np = (N + 63) / 64 * 64;
+    const size_t smem = abm::vf_sym_smem_bytes(Np, e->grid.W, false);
+    const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
+    const double waves = std::ceil((double)B / ((double)e->n_sms * resident));
+    t_cta = waves * (45.0 + 0.05 * Np + 1.6e-4 * (double)Np * Np);
+  } else {
+    const double ctas = (double)B * ((N + 255) / 256);
+    t_cta = std::ceil(ctas / (3.0 * e->n_sms)) * (45.0 + 0.2 * N);
+  }
+  return t_warp < 0.9 * t_cta;
+}
+
 int copy_in(void* dst, const void* src, size_t bytes, int on_device, cudaStream_t st) {
   ABM_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   return ABM_OK;
@@ -610,28 +633,8 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
   a.sym_radius = e->r_max;
   const bool sym_ok = !(force && (strcmp(force, "onesided") == 0 || strcmp(force, "warp") == 0)) &&
                       abm::vf_sym_applicable(a, uniform_r, cull, e->smem_optin);
-  // Small batches cannot fill the GPU with one CTA per replicate (or per tile of 256 focal agents): a warp per focal
-  // agent spreads them over all SMs.  Cost models fitted to B200 measurements at R = 1200 (scratch/c2_probe.py), in
-  // microseconds: warp kernel 10 + 1.2e-3 agents + 4.0e-6 ordered pairs; symmetric kernel 45 + 0.05 Np + 1.6e-4 Np^2
-  // per wave of resident CTAs; one-sided kernel 45 + 0.2 N per wave.  E.g. one run of 100 agents: 12 us instead of 54
-  // per step; 16 x 1024: 97 instead of 270; from 48 x 1024 or 256 x 256 upwards the symmetric kernel wins.
-  bool small_grid = false;
-  if (!force && e->tile_count == e->cfg.n_agents) {
-    const double agents = (double)a.B * a.N, pairs = agents * (a.N - 1);
-    const double t_warp = 10.0 + 1.2e-3 * agents + 4.0e-6 * pairs;
-    double t_cta;
-    if (sym_ok) {
-      const int Np = (a.N + 63) / 64 * 64;
-      const size_t smem = abm::vf_sym_smem_bytes(Np, a.W, false);
-      const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
-      const double waves = std::ceil((double)a.B / ((double)e->n_sms * resident));
-      t_cta = waves * (45.0 + 0.05 * Np + 1.6e-4 * (double)Np * Np);
-    } else {
-      const double ctas = (double)a.B * ((a.N + 255) / 256);
-      t_cta = std::ceil(ctas / (3.0 * e->n_sms)) * (45.0 + 0.2 * a.N);
-    }
-    small_grid = t_warp < 0.9 * t_cta;
-  }
+  // small batches: a warp per focal agent (vf_small_grid)
+  const bool small_grid = !force && e->tile_count == e->cfg.n_agents && vf_small_grid(e, sym_ok);
   const bool adaptive = sym_ok && !force && !small_grid;
   if (adaptive && !e->slow_host) {
     ABM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&e->slow_host), sizeof(unsigned long long)));
@@ -807,20 +810,14 @@ static bool vf_chunkable(const abm_engine* e) {
   if (e->tile_count != e->cfg.n_agents || e->n_peers > 0 || getenv("ABM_VF_KERNEL")) return false;
   if (e->sort_enabled && !e->perm_identity) return false;
   const GridConsts& g = e->grid;
-  const int B = e->cfg.n_replicates, N = e->cfg.n_agents;
+  const int N = e->cfg.n_agents;
   const double d_cull = (double)e->r_max * std::sqrt((double)g.cull_scale);
   if (ABM_PI_D * d_cull * d_cull < 0.5 * (double)e->cfg.width * (double)e->cfg.height) return false;   // culling: warp kernel
   abm::VFKernelArgs a;
   memset(&a, 0, sizeof(a));
   a.N = N; a.W = g.W; a.tile_begin = 0; a.tile_count = N;
   if (!abm::vf_sym_applicable(a, true, false, e->smem_optin)) return false;
-  const int Np = (N + 63) / 64 * 64;
-  const size_t smem = abm::vf_sym_smem_bytes(Np, g.W, false);
-  const int resident = std::max(1, std::min((int)(e->smem_optin / smem), 2048 / (32 * (Np / 64))));
-  const double agents = (double)B * N, pairs = agents * (N - 1);
-  const double t_warp = 10.0 + 1.2e-3 * agents + 4.0e-6 * pairs;
-  const double t_cta = std::ceil((double)B / ((double)e->n_sms * resident)) * (45.0 + 0.05 * Np + 1.6e-4 * (double)Np * Np);
-  return !(t_warp < 0.9 * t_cta);
+  return !vf_small_grid(e, true);
 }
 
 int abm_vf_step_host(abm_engine_t* e, const float* xytv_in, float* xytv_out, int n_steps, void* stream) {
