@@ -38,7 +38,7 @@ PAD = 30.0
 PARAMS = dict(GAM=0.1, V0=1.0, ALP0=1.0, ALP1=0.09, BET0=1.0, BET1=0.09)
 # dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch at the default workload, from the committed
 # `ncu --set full` captures (profiles/r1_*_ncu_summary.md); None for any other workload size or kernel
-NCU_DRAM_BYTES_PER_LAUNCH = {"abm::vf_step_kernel": 55.2e6, "abm::vf_step_sym_kernel": 26.5e6} \
+NCU_DRAM_BYTES_PER_LAUNCH = {"abm::vf_step_kernel": 55.2e6, "abm::vf_step_sym_kernel": 26.2e6} \
     if (N_AGENTS, N_REPLICATES) == (1024, 1024) else {}
 METRIC = "agent-steps/sec (visual field + flocking update)"
 UNIT = "agent-steps/s"
