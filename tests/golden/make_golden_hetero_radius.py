@@ -1,6 +1,6 @@
 """Generates tests/golden/base_hetero_radius_golden.npz: agents with their OWN radius (agent_radius entry of
-agent_behave_param_list, sims.py:502) on top of per-agent decision parameters.  ORACLE-ONLY fixture: the CUDA path
-refuses per-agent radii; this pins the restatement for the round that adds them.  The
+agent_behave_param_list, sims.py:502) on top of per-agent decision parameters; pins the restatement and the CUDA path
+(abm_base_set_agent_radii).  The
 UNMODIFIED reference's constructor takes the dictionaries, Agent.update runs from a frozen snapshot as in
 make_golden_base.py.  Build container only:
 

@@ -99,7 +99,7 @@ def load_base_hetero_cases(fixture="base_hetero_golden.npz"):
     """tests/golden/base_hetero_golden.npz (make_golden_hetero.py): heterogeneous agents, the per-agent
     parameters went through the reference's own constructor (agent.py:83-108).  ``agent_cfgs``: one
     BaseConfig per agent; ``agent_params``: dict name -> (N,) array.  With
-    fixture="base_hetero_radius_golden.npz" (make_golden_hetero_radius.py, oracle-only) the state's radius is
+    fixture="base_hetero_radius_golden.npz" (make_golden_hetero_radius.py) the state's radius is
     the (N,) array of the agents' own radii; with "base_hetero_res_golden.npz" (make_golden_hetero_res.py) every
     agent's BaseConfig has its own R and the fields are padded with zeros up to cfg.R."""
     import dataclasses

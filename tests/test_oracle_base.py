@@ -71,7 +71,7 @@ def test_restatement_matches_reference_fixture_heterogeneous_agents(case):
 def test_restatement_matches_reference_fixture_heterogeneous_radii(case):
     """agent_radius of agent_behave_param_list (sims.py:502): every agent's own radius in the candidate distance
     (supcalc.py:73-78) and in its wall reflection, the FOCAL radius for both centres and the projection size
-    (agent.py:504-509, 529).  Oracle-only: the CUDA path refuses per-agent radii."""
+    (agent.py:504-509, 529).  The same fixture pins the CUDA path (abm_base_set_agent_radii, tests/test_base_gpu.py)."""
     assert np.ndim(case["st"]["radius"]) == 1 and len(set(case["st"]["radius"])) > 1
     out = rb.base_step_frozen(case["st"], case["cfg"], case["dth"], agent_cfgs=case["agent_cfgs"])
     assert np.array_equal(rs.pack_bits(out["fields"]), case["fields"])
