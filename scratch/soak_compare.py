@@ -7,12 +7,14 @@ from abm_b200 import VFEngine
 B, N, T = int(sys.argv[1]), 1024, int(sys.argv[2])
 W = bench.arena_side(N)
 x, y, th, v = bench.synthetic_state(B, N)
+# "het" as third argument: every agent its own radius (the symmetric kernel's two-half-width variant)
+rad = np.random.default_rng(5).choice([5.0, 7.5, 10.0, 12.5, 16.0], (B, N)).astype(np.float32) if "het" in sys.argv[3:] else 10.0
 res = {}
 for k in ("symmetric", "onesided"):
     os.environ["ABM_VF_KERNEL"] = k
     for boundary in ("walls", "infinite"):
         eng = VFEngine(B, N, resolution=1200, width=W, height=W, boundary=boundary, keep_fields=True)
-        eng.set_params(**bench.PARAMS); eng.set_state(x, y, th, v, 10.0)
+        eng.set_params(**bench.PARAMS); eng.set_state(x, y, th, v, rad)
         eng.step(T); torch.cuda.synchronize()
         res[(k, boundary)] = (eng.get_state(), eng.fields_packed().copy(), eng.counters())
         eng.close()
