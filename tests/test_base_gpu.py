@@ -530,6 +530,63 @@ def test_base_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
     eng.close()
 
 
+@pytest.mark.parametrize("teleport,ghost", [(True, False), (False, True)])
+def test_full_step_in_lockstep_with_oracle(built_lib, teleport, ghost):
+    """The whole loop body (sims.py:733-864) as ONE engine step -- collisions, agent-patch interaction, Agent.update of
+    every agent from the snapshot the environment phase leaves -- against the oracle's three phases chained in the
+    reference's order, for 10 consecutive steps in lockstep (every step starts from the engine's own state, so nothing
+    drifts): what one phase hands to the next (turned headings and collide modes, teleports, notifications, the collided
+    set, depleted patches) is compared as well as the phases themselves."""
+    from abm_b200 import BaseEngine
+    rng = np.random.default_rng(31)
+    B, N, P, W = 2, 36, 3, 240.0
+    cfg = rb.BaseConfig(R=1200, width=W, height=W, visual_exclusion=True, teleport_exploit=teleport, Eps_w=2.0, Eps_u=1.0,
+                        exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5, reloc_theta_max=1.8, exp_stop_ratio=0.175,
+                        F_N=0.5, F_R=0.5, agent_consumption=1.0)
+    eng = _engine_for(cfg, B, N, P, collide_agents=True, ghost_mode=ghost, regenerate_patches=False)
+    x0, y0 = rng.integers(30, 250, (B, N)).astype(float), rng.integers(30, 250, (B, N)).astype(float)
+    x0[:, :6] = 40.0 + 32.0 - 10.0 + rng.integers(-12, 12, (B, 6)); y0[:, :6] = 50.0 + 32.0 - 10.0 + rng.integers(-12, 12, (B, 6))
+    x0[:, 6:10] = 150.0 + 22.0 + rng.integers(-10, 10, (B, 4)); y0[:, 6:10] = 150.0 + 22.0 + rng.integers(-10, 10, (B, 4))
+    on = np.arange(N) < 10                                              # the agents standing on patches 1 and 2 exploit them
+    u0 = np.where(on, 0.9, 0.0) * np.ones((B, 1))
+    ov0 = np.where(on, 1, 0) * np.ones((B, 1), int)
+    pid0 = np.where(np.arange(N) < 6, 1, np.where(on, 2, -1)) * np.ones((B, 1), int)
+    eng.set_agents(x=x0, y=y0, theta=rng.uniform(0, 2 * np.pi, (B, N)), u=u0, override_mode=ov0, mode=ov0,
+                   env_status=np.where(on, 1, -1) * np.ones((B, 1), int), patch_id=pid0)
+    eng.set_patches(x=np.tile([40.0, 150.0, 60.0], (B, 1)), y=np.tile([50.0, 150.0, 170.0], (B, 1)),
+                    radius=np.full((B, P), 32.0), left=np.tile([3.0, 400.0, 400.0], (B, 1)),
+                    quality=np.full((B, P), 0.5), id=np.tile(np.arange(1, P + 1), (B, 1)))
+    n_collided = n_exploit = n_depleted = 0
+    for step in range(10):
+        a0, p0 = eng.get_agents(), eng.get_patches()
+        dth = np.asarray(rng.uniform(-0.5, 0.5, (B, N)), np.float32)
+        eng.step(1, inject_dtheta=dth)
+        got, gp, fields = eng.get_agents(), eng.get_patches(), eng.fields()
+        for b in range(B):
+            st = dict(x=a0["x"][b].astype(float), y=a0["y"][b].astype(float), theta=a0["theta"][b].astype(float),
+                      vel=a0["vel"][b].astype(float), w=a0["w"][b].astype(float), u=a0["u"][b].astype(float),
+                      collected=a0["collected"][b].astype(float), collected_before=a0["collected_before"][b].astype(float),
+                      env_status=a0["env_status"][b].copy(), override=a0["override_mode"][b].copy(), mode=a0["mode"][b].copy(),
+                      patch_id=a0["patch_id"][b].copy(), radius=10.0,
+                      novelty=((a0["novelty"][b][:, None] >> np.arange(cfg.Tau)) & 1).astype(float))
+            pa = {k: np.array(p0[k][b], dtype=float if k != "id" else int) for k in p0}
+            collided = rb.base_collision_phase(st, cfg, ghost)                         # sims.py:736-783
+            depleted = rb.base_patch_phase(st, pa, cfg, collided=set(collided))       # :790-858
+            ref = rb.base_step_frozen(st, cfg, dth[b].astype(np.float64))             # :861
+            n_collided += len(set(collided)); n_depleted += len(depleted); n_exploit += int((st["override"] == 1).sum())
+            assert np.array_equal(fields[b], ref["fields"]), (step, b)
+            _compare_agents(got, ref, b)
+            np.testing.assert_allclose(got["collected"][b], st["collected"], rtol=RTOL, atol=1e-6)
+            assert np.array_equal(got["env_status"][b], st["env_status"]) and np.array_equal(got["patch_id"][b], st["patch_id"])
+            nov = ((got["novelty"][b][:, None] >> np.arange(cfg.Tau)) & 1).astype(float)
+            assert np.array_equal(nov, st["novelty"])
+            np.testing.assert_allclose(gp["left"][b], pa["left"], rtol=RTOL, atol=1e-6)
+            for p_ in depleted:
+                assert gp["radius"][b][p_] == 0.0
+    assert n_collided > 20 and n_exploit > 5 and n_depleted >= 1
+    eng.close()
+
+
 def test_step_path_follows_the_batch_shape(built_lib, monkeypatch, step_path):
     """Without ABM_BASE_FUSED the engine picks the step path from the batch shape: small replicates and batches that fill
     the GPU with one CTA per replicate take the fused kernel, few larger replicates one grid per phase."""
