@@ -76,15 +76,17 @@ class BaseEngine:
     def set_params(self, **kw):
         """Decision / movement parameters by name (_lib.BASE_PARAM_NAMES): scalars, length-B arrays (one set
         per replicate, e.g. a DEC_EPSW sweep) or (B, N) arrays (one set per agent: the heterogeneous agents of
-        agent.py:83-108 / sims.py:499-517)."""
-        defaults = dict(T_w=0.5, Eps_w=3, g_w=0.085, B_w=0, w_max=1, T_u=0.5, Eps_u=3, g_u=0.085, B_u=0, u_max=1,
-                        S_wu=0.25, S_uw=0.01, F_N=2, F_R=1, exp_vel_max=1, exp_theta_min=-0.3, exp_theta_max=0.3,
-                        reloc_theta_max=0.5, exp_stop_ratio=0.08, agent_consumption=1)
-        unknown = set(kw) - set(defaults)
+        agent.py:83-108 / sims.py:499-517).  Parameters not named keep the value of the previous call (initially the
+        reference's param-module defaults), like assigning single attributes of the reference's param modules."""
+        if not hasattr(self, "_param_values"):
+            self._param_values = dict(T_w=0.5, Eps_w=3, g_w=0.085, B_w=0, w_max=1, T_u=0.5, Eps_u=3, g_u=0.085, B_u=0,
+                                      u_max=1, S_wu=0.25, S_uw=0.01, F_N=2, F_R=1, exp_vel_max=1, exp_theta_min=-0.3,
+                                      exp_theta_max=0.3, reloc_theta_max=0.5, exp_stop_ratio=0.08, agent_consumption=1)
+        unknown = set(kw) - set(self._param_values)
         if unknown:
             raise TypeError(f"unknown parameter(s): {sorted(unknown)}")
-        defaults.update(kw)
-        vals = [np.asarray(defaults[n], np.float64) for n in _lib.BASE_PARAM_NAMES]
+        self._param_values.update(kw)
+        vals = [np.asarray(self._param_values[n], np.float64) for n in _lib.BASE_PARAM_NAMES]
         for v in vals:
             if v.shape not in ((), (1,), (self.B,), (self.B, self.N)):
                 raise ValueError("parameter arrays must have length 1 or n_replicates, or shape (n_replicates, n_agents)")

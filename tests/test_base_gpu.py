@@ -530,13 +530,15 @@ def test_base_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
     eng.close()
 
 
-@pytest.mark.parametrize("teleport,ghost", [(True, False), (False, True)])
-def test_full_step_in_lockstep_with_oracle(built_lib, teleport, ghost):
+@pytest.mark.parametrize("teleport,ghost,hetero", [(True, False, False), (False, True, False), (True, False, True)])
+def test_full_step_in_lockstep_with_oracle(built_lib, teleport, ghost, hetero):
     """The whole loop body (sims.py:733-864) as ONE engine step -- collisions, agent-patch interaction, Agent.update of
     every agent from the snapshot the environment phase leaves -- against the oracle's three phases chained in the
     reference's order, for 10 consecutive steps in lockstep (every step starts from the engine's own state, so nothing
     drifts): what one phase hands to the next (turned headings and collide modes, teleports, notifications, the collided
-    set, depleted patches) is compared as well as the phases themselves."""
+    set, depleted patches) is compared as well as the phases themselves.  hetero: every agent with its own radius, field
+    resolution, FOV, vision range, speed and consumption (agent_behave_param_list, sims.py:499-517)."""
+    import dataclasses
     from abm_b200 import BaseEngine
     rng = np.random.default_rng(31)
     B, N, P, W = 2, 36, 3, 240.0
@@ -544,6 +546,19 @@ def test_full_step_in_lockstep_with_oracle(built_lib, teleport, ghost):
                         exp_vel_max=3.0, exp_theta_min=-0.5, exp_theta_max=0.5, reloc_theta_max=1.8, exp_stop_ratio=0.175,
                         F_N=0.5, F_R=0.5, agent_consumption=1.0)
     eng = _engine_for(cfg, B, N, P, collide_agents=True, ghost_mode=ghost, regenerate_patches=False)
+    radii = np.full((B, N), 10.0)
+    acfgs = [None] * B
+    if hetero:
+        radii = rng.choice([6.0, 10.0, 13.0], (B, N)); res = rng.choice([1200, 800, 333], (B, N))
+        fov = rng.choice([1.0, 0.75, 0.5], (B, N)); vr = rng.choice([80.0, 200.0, 2000.0], (B, N))
+        vmax = np.asarray(rng.uniform(1, 4, (B, N)), np.float32).astype(np.float64); cons = rng.choice([0.25, 1.0, 2.0], (B, N))
+        names = ("T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u", "u_max", "S_wu", "S_uw", "F_N", "F_R",
+                 "exp_theta_min", "exp_theta_max", "reloc_theta_max", "exp_stop_ratio")
+        eng.set_params(exp_vel_max=vmax, agent_consumption=cons, **{k: getattr(cfg, k) for k in names})
+        eng.set_agent_radii(radii); eng.set_agent_resolution(res); eng.set_agent_geometry(agent_fov=fov, vision_range=vr)
+        acfgs = [[dataclasses.replace(cfg, R=int(res[b, i]), fov=(-fov[b, i] * np.pi, fov[b, i] * np.pi),
+                                      vision_range=float(vr[b, i]), exp_vel_max=float(vmax[b, i]),
+                                      agent_consumption=float(cons[b, i])) for i in range(N)] for b in range(B)]
     x0, y0 = rng.integers(30, 250, (B, N)).astype(float), rng.integers(30, 250, (B, N)).astype(float)
     x0[:, :6] = 40.0 + 32.0 - 10.0 + rng.integers(-12, 12, (B, 6)); y0[:, :6] = 50.0 + 32.0 - 10.0 + rng.integers(-12, 12, (B, 6))
     x0[:, 6:10] = 150.0 + 22.0 + rng.integers(-10, 10, (B, 4)); y0[:, 6:10] = 150.0 + 22.0 + rng.integers(-10, 10, (B, 4))
@@ -567,12 +582,12 @@ def test_full_step_in_lockstep_with_oracle(built_lib, teleport, ghost):
                       vel=a0["vel"][b].astype(float), w=a0["w"][b].astype(float), u=a0["u"][b].astype(float),
                       collected=a0["collected"][b].astype(float), collected_before=a0["collected_before"][b].astype(float),
                       env_status=a0["env_status"][b].copy(), override=a0["override_mode"][b].copy(), mode=a0["mode"][b].copy(),
-                      patch_id=a0["patch_id"][b].copy(), radius=10.0,
+                      patch_id=a0["patch_id"][b].copy(), radius=radii[b].copy() if hetero else 10.0,
                       novelty=((a0["novelty"][b][:, None] >> np.arange(cfg.Tau)) & 1).astype(float))
             pa = {k: np.array(p0[k][b], dtype=float if k != "id" else int) for k in p0}
-            collided = rb.base_collision_phase(st, cfg, ghost)                         # sims.py:736-783
-            depleted = rb.base_patch_phase(st, pa, cfg, collided=set(collided))       # :790-858
-            ref = rb.base_step_frozen(st, cfg, dth[b].astype(np.float64))             # :861
+            collided = rb.base_collision_phase(st, cfg, ghost, agent_cfgs=acfgs[b])    # sims.py:736-783
+            depleted = rb.base_patch_phase(st, pa, cfg, collided=set(collided), agent_cfgs=acfgs[b])   # :790-858
+            ref = rb.base_step_frozen(st, cfg, dth[b].astype(np.float64), agent_cfgs=acfgs[b])         # :861
             n_collided += len(set(collided)); n_depleted += len(depleted); n_exploit += int((st["override"] == 1).sum())
             assert np.array_equal(fields[b], ref["fields"]), (step, b)
             _compare_agents(got, ref, b)
