@@ -57,6 +57,92 @@ def test_simulation_facade_runs(built_lib):
     assert sim.rescources[0].radius == 30.0 and sim.rescources[0].resc_left <= 101
 
 
+@pytest.mark.parametrize("boundary,limit", [("walls", True), ("infinite", False)])
+def test_vfsimulation_kwargs_reach_the_kernels(built_lib, boundary, limit):
+    """VFSimulation's constructor kwargs and the vf_params values (vf_sims.py:31-68, vf_params.py:12-23), all away from their
+    defaults -- a non-square arena, a limited FOV (which rescales the resolution, vf_sims.py:41-44), boundary condition,
+    movement limits, every flocking parameter -- through the façade: four steps of `step_sim` in lockstep with the oracle
+    configured from the same kwargs."""
+    from abm_b200.simulation import VFSimulation
+    from abm_b200.params import VFParams
+    vp = VFParams(GAM=0.2, V0=1.5, ALP0=0.7, ALP1=0.05, BET0=1.4, BET1=0.12, BOUNDARY=boundary, LIMIT_MOVEMENT=limit,
+                  MAX_VEL=2.0, MAX_TH=0.05)
+    sim = VFSimulation(N=40, T=10, v_field_res=900, width=420, height=300, window_pad=30, agent_radius=7, agent_fov=0.75,
+                       vf_params=vp, n_replicates=3, seed=12)
+    sim.prepare_start()
+    R = int(900 * (1 / 0.75))
+    assert sim.v_field_res == R
+    cfg = rs.VFConfig(R=R, fov=(-0.75 * np.pi, 0.75 * np.pi), boundary=boundary, width=420, height=300, window_pad=30,
+                      GAM=0.2, V0=1.5, ALP0=0.7, ALP1=0.05, BET0=1.4, BET1=0.12, limit_movement=limit, max_vel=2.0, max_th=0.05)
+    for step in range(4):
+        before = [(ag.position.copy(), ag.orientation, ag.velocity) for b in range(3) for ag in sim.replicate_agents(b)]
+        sim.step_sim()
+        st = sim.engine.get_state()
+        fields = sim.engine.fields()
+        for b in range(3):
+            rows = before[b * 40:(b + 1) * 40]
+            x = np.array([r[0][0] for r in rows]); y = np.array([r[0][1] for r in rows])
+            th = np.array([r[1] for r in rows]); v = np.array([r[2] for r in rows])
+            ref = rs.vf_step_frozen(x, y, th, v, 7.0, cfg)
+            assert np.array_equal(fields[b], ref["rows"][:, ::-1]), (step, b)
+            for k in ("x", "y", "theta", "vel"):
+                np.testing.assert_allclose(st[k][b], ref[k], rtol=1e-5, atol=1e-5, err_msg=f"{k} step {step}")
+    assert sim.t == 4
+
+
+def test_simulation_kwargs_reach_the_kernels(built_lib):
+    """The reference's constructor kwargs (sims.py:60-68) and decision / movement parameters, all away from their defaults,
+    through `Simulation` into the engine: five steps of the façade's engine in lockstep with the oracle configured from the
+    SAME kwargs by the reference's rules (agent_fov as a fraction of pi, vision range, exclusion flags, teleport, ghost
+    mode, radius, resolution, consumption) -- a wrong or dropped kwarg shows as a field or state difference."""
+    from abm_b200.simulation import Simulation
+    from abm_b200.params import DecisionParams
+    from oracle import restate_base as rb
+    dp = DecisionParams(T_w=0.4, Eps_w=2.5, g_w=0.07, B_w=0.05, w_max=0.9, T_u=0.45, Eps_u=1.5, g_u=0.09, B_u=0.02,
+                        u_max=0.95, S_wu=0.2, S_uw=0.03, Tau=7, F_N=1.5, F_R=0.8, exp_vel_max=2.5, exp_theta_min=-0.4,
+                        exp_theta_max=0.2, reloc_theta_max=1.1, exp_stop_ratio=0.12)
+    kw = dict(N=24, T=100, v_field_res=900, width=260, height=220, window_pad=30, agent_radius=8, N_resc=3, patch_radius=28,
+              min_resc_perpatch=300, max_resc_perpatch=-1, min_resc_quality=0.4, max_resc_quality=-1,
+              regenerate_patches=False, agent_consumption=0.5, teleport_exploit=True, vision_range=140, agent_fov=0.6,
+              visual_exclusion=True, ghost_mode=False, patchwise_exclusion=False, collide_agents=True)
+    sim = Simulation(n_replicates=2, seed=9, decision_params=dp, **kw)
+    sim.create_agents(); sim.create_resources()
+    eng = sim.engine
+    cfg = rb.BaseConfig(R=900, fov=(-0.6 * np.pi, 0.6 * np.pi), width=260, height=220, window_pad=30, vision_range=140.0,
+                        visual_exclusion=True, patchwise_exclusion=False, teleport_exploit=True, agent_consumption=0.5,
+                        **{k: getattr(dp, k) for k in ("T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u",
+                                                       "u_max", "S_wu", "S_uw", "Tau", "F_N", "F_R", "exp_vel_max",
+                                                       "exp_theta_min", "exp_theta_max", "reloc_theta_max", "exp_stop_ratio")})
+    rng = np.random.default_rng(4)
+    a = eng.get_agents()
+    a["u"][:, :8] = 0.9                                   # some agents about to exploit (the run is only five steps long)
+    p = eng.get_patches()
+    a["x"][:, :8] = p["x"][:, :1] + 28 - 8 + rng.integers(-10, 10, (2, 8)); a["y"][:, :8] = p["y"][:, :1] + 28 - 8
+    eng.set_agents(x=a["x"], y=a["y"], theta=a["theta"], u=a["u"])
+    for step in range(5):
+        a0, p0 = eng.get_agents(), eng.get_patches()
+        dth = np.asarray(rng.uniform(-0.4, 0.2, (2, kw["N"])), np.float32)
+        eng.step(1, inject_dtheta=dth)
+        got, fields = eng.get_agents(), eng.fields()
+        for b in range(2):
+            st = dict(x=a0["x"][b].astype(float), y=a0["y"][b].astype(float), theta=a0["theta"][b].astype(float),
+                      vel=a0["vel"][b].astype(float), w=a0["w"][b].astype(float), u=a0["u"][b].astype(float),
+                      collected=a0["collected"][b].astype(float), collected_before=a0["collected_before"][b].astype(float),
+                      env_status=a0["env_status"][b].copy(), override=a0["override_mode"][b].copy(), mode=a0["mode"][b].copy(),
+                      patch_id=a0["patch_id"][b].copy(), radius=8.0,
+                      novelty=((a0["novelty"][b][:, None] >> np.arange(cfg.Tau)) & 1).astype(float))
+            pa = {k: np.array(p0[k][b], dtype=float if k != "id" else int) for k in p0}
+            collided = rb.base_collision_phase(st, cfg, False)
+            rb.base_patch_phase(st, pa, cfg, collided=set(collided))
+            ref = rb.base_step_frozen(st, cfg, dth[b].astype(np.float64))
+            assert np.array_equal(fields[b], ref["fields"]), (step, b)
+            for k, g in dict(x="x", y="y", theta="theta", vel="vel", w="w", u="u").items():
+                np.testing.assert_allclose(got[g][b], ref[k], rtol=1e-5, atol=1e-5, err_msg=f"{k} step {step}")
+            assert np.array_equal(got["mode"][b], np.asarray(ref["mode"]).astype(int))
+            np.testing.assert_allclose(got["collected"][b], st["collected"], rtol=1e-5, atol=1e-6)
+    assert got["collected"].sum() > 0                      # somebody exploited a patch at consumption 0.5 / quality 0.4
+
+
 def _behave_template(**over):
     """contrib/evolution.py:1-26."""
     d = dict(S_wu=0, T_w=0.5, Eps_w=0, g_w=0.085, B_w=0, w_max=1, Tau=10, S_uw=0, T_u=0.5, Eps_u=3, g_u=0.085, B_u=0,
