@@ -57,6 +57,30 @@ def test_simulation_facade_runs(built_lib):
     assert sim.rescources[0].radius == 30.0 and sim.rescources[0].resc_left <= 101
 
 
+def test_apps_start_from_the_references_own_env_file(built_lib, tmp_path):
+    """abm/app.py:16-70 and app_visual_flocking.py:40-108 mirrored: the reference's OWN root `.env` (copied unmodified to
+    oracle/_ref) -> kwargs -> Simulation / VFSimulation .start(), with only the run length, the InfluxDB switch and the
+    output folder overridden; the runs leave the reference's output layout."""
+    import glob
+    from oracle import ref_shim
+    env_file = os.path.join(ref_shim._reference_root(), ".env")
+    if not os.path.isfile(env_file):
+        pytest.skip("the reference's .env is not at hand")
+    from abm_b200 import app, app_visual_flocking, params
+    env = params.read_env(env_file)
+    over = dict(T=40, use_ifdb_logging=False, save_root_dir=str(tmp_path / "out"), n_replicates=2, seed=3)
+    vsim = app_visual_flocking.start(env_file=env_file, **over)                     # the file says APP_VERSION=VisualFlocking
+    fov = float(env["AGENT_FOV"])
+    assert vsim.t == 40 and vsim.N == int(env["N"]) and vsim.v_field_res == int(int(env["VISUAL_FIELD_RESOLUTION"]) / fov)
+    assert vsim.WIDTH == float(env["ENV_WIDTH"]) and np.isfinite(vsim.engine.get_state()["x"]).all()
+    bsim = app.start(env_file=env_file, **over)                                     # the foraging app reads the same file
+    assert bsim.t == 40 and bsim.N == int(env["N"]) and bsim.N_resc == int(env["N_RESOURCES"])
+    assert np.isfinite(bsim.engine.get_agents()["x"]).all()
+    if int(env.get("USE_RAM_LOGGING", "0")) and int(env.get("SAVE_CSV_FILES", "0")):
+        assert len(glob.glob(str(tmp_path / "out" / "*" / "ag_posx.zarr"))) + \
+               len(glob.glob(str(tmp_path / "out" / "*" / "*" / "ag_posx.zarr"))) >= 2
+
+
 @pytest.mark.parametrize("boundary,limit", [("walls", True), ("infinite", False)])
 def test_vfsimulation_kwargs_reach_the_kernels(built_lib, boundary, limit):
     """VFSimulation's constructor kwargs and the vf_params values (vf_sims.py:31-68, vf_params.py:12-23), all away from their
