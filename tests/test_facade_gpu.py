@@ -278,6 +278,39 @@ def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
     assert mp.run_protocols(project="VisualFlocking") == []      # env files are consumed
 
 
+def test_metaprotocol_foraging_sweep_groups_by_shape(built_lib, tmp_path):
+    """The foraging project through MetaProtocol (the reference's figure experiments are such sweeps): env files that
+    differ only in decision / movement parameters run as ONE batch with one parameter set per replicate; a parameter
+    that changes the batch's shape (N_RESOURCES) starts another batch.  Replicates with DEC_EPSU = 0 never build up the
+    exploitation drive, so only the others can collect; MOV_EXP_VEL_MAX is the speed of every exploring agent of its
+    replicate."""
+    from abm_b200 import metarunner as mr
+    env = dict(N="16", T="250", VISUAL_FIELD_RESOLUTION="320", ENV_WIDTH="300", ENV_HEIGHT="300", RADIUS_AGENT="10",
+               AGENT_FOV="1", VISION_RANGE="2000", RADIUS_RESOURCE="45", MIN_RESOURCE_PER_PATCH="400",
+               MAX_RESOURCE_PER_PATCH="401", MIN_RESOURCE_QUALITY="0.25", MAX_RESOURCE_QUALITY="0.25", VISUAL_EXCLUSION="1",
+               TELEPORT_TO_MIDDLE="0", PATCH_BORDER_OVERLAP="1", AGENT_AGENT_COLLISION="0", GHOST_WHILE_EXPLOIT="1",
+               AGENT_CONSUMPTION="1", REGENERATE_PATCHES="1", USE_RAM_LOGGING="0", DEC_EPSW="2")
+    mp = mr.MetaProtocol("forage", num_batches=1, default_envconf=env, root_dir=str(tmp_path))
+    mp.add_criterion(mr.Tunable("DEC_EPSU", values_override=[0, 3]))
+    mp.add_criterion(mr.Tunable("MOV_EXP_VEL_MAX", values_override=[1.5, 3]))
+    mp.add_criterion(mr.Tunable("N_RESOURCES", values_override=[2, 4]))
+    assert mp.generate_temp_env_files() == 8
+    res = mp.run_protocols(project="Base", seed=3)
+    assert len(res) == 2 and sorted(sim.N_resc for _, sim in res) == [2, 4]         # one batch per shape
+    for paths, sim in res:
+        assert len(paths) == 4 and sim.B == 4 and sim.t == 250
+        a = sim.engine.get_agents()
+        assert np.isfinite(a["x"]).all()
+        # the env files are consumed; the per-replicate parameters are in env_params
+        for b, e in enumerate(sim.env_params):
+            eps_u, vmax = float(e["DEC_EPSU"]), float(e["MOV_EXP_VEL_MAX"])
+            if eps_u == 0:
+                assert (a["collected"][b] == 0).all()
+            explore = a["mode"][b] == 0
+            assert np.allclose(np.abs(a["vel"][b][explore]), vmax, rtol=1e-6)
+        assert any(float(e["DEC_EPSU"]) > 0 and a["collected"][b].sum() > 0 for b, e in enumerate(sim.env_params))
+
+
 def test_simulation_writes_reference_output_folder(built_lib, tmp_path):
     """Simulation(use_ram_logging, save_csv_files, use_zarr) -> <root>/<SAVE_ROOT_DIR>/<timestamp>/ with the agent and
     resource arrays of ifdb.py:435-535 and env_params.json; saving without logging raises like sims.py:909-912."""
