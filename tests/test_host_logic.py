@@ -99,3 +99,81 @@ def test_simulation_facade_rejects_per_agent_geometry():
         Simulation(N=5, T=10, agent_behave_param_list=plist)
     with pytest.raises(NotImplementedError, match="Tau"):
         Simulation(N=4, T=10, agent_behave_param_list=[dict(base, Tau=5)] * 4)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/abm/metarunner"), reason="reference tree not mounted")
+@pytest.mark.parametrize("exp_file", ["figExp3BN50PatchyCollOcc.py", "VFExp4c.py"])
+def test_references_own_experiment_files_generate_the_same_env_files(tmp_path, monkeypatch, exp_file):
+    """Drop-in check of the sweep language: the reference's OWN experiment files (BASELINE configs[2] and configs[3] are
+    these two) are executed unchanged, once against the reference's metarunner (a temporary copy, so that nothing is
+    written into the reference tree; `abm.app` stubbed, `run_protocols` a no-op) and once against abm_b200.metarunner
+    under the same module name: the generated env files -- names, keys, values -- must be identical."""
+    import importlib.util
+    import shutil
+    import sys
+    import types
+    src = "/root/reference"
+    exp_path = os.path.join(src, "abm/data/metaprotocol/experiments", exp_file)
+    exp_name = "dropin_exp"
+    monkeypatch.setenv("EXPERIMENT_NAME", exp_name)
+    code = compile(open(exp_path).read(), exp_path, "exec")
+
+    def run_with(module, root):
+        saved = {k: sys.modules.get(k) for k in ("abm", "abm.app", "abm.metarunner", "abm.metarunner.metarunner")}
+        try:
+            pkg = types.ModuleType("abm"); pkg.__path__ = []
+            sys.modules["abm"] = pkg
+            sys.modules["abm.app"] = types.ModuleType("abm.app"); pkg.app = sys.modules["abm.app"]
+            sys.modules["abm.metarunner"] = types.ModuleType("abm.metarunner")
+            mod = module()
+            sys.modules["abm.metarunner.metarunner"] = mod
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                exec(code, {"__name__": "__exp__"})
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+        d = os.path.join(root, "abm/data/metaprotocol/temp", exp_name)
+        return {f: params.read_env(os.path.join(d, f)) for f in sorted(os.listdir(d))}
+
+    # ---- the reference's metarunner, from a temporary copy (root_abm_dir = three levels above the module file) ----
+    ref_root = tmp_path / "ref"
+    os.makedirs(ref_root / "abm/metarunner")
+    shutil.copyfile(os.path.join(src, "abm/metarunner/metarunner.py"), ref_root / "abm/metarunner/metarunner.py")
+    shutil.copyfile(os.path.join(src, ".env"), ref_root / f"{exp_name}.env")
+
+    def load_reference():
+        spec = importlib.util.spec_from_file_location("abm.metarunner.metarunner", ref_root / "abm/metarunner/metarunner.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.MetaProtocol.run_protocols = lambda self, *a, **k: None
+        return mod
+
+    want = run_with(load_reference, str(ref_root))
+
+    # ---- abm_b200.metarunner under the same name, same default .env, its own root ----
+    our_root = tmp_path / "ours"
+    os.makedirs(our_root)
+    shutil.copyfile(os.path.join(src, ".env"), our_root / f"{exp_name}.env")
+
+    def load_ours():
+        mod = types.ModuleType("abm.metarunner.metarunner")
+        for name in ("Tunable", "Constant", "TunedPairRestrain"):
+            setattr(mod, name, getattr(mr, name))
+
+        class MetaProtocol(mr.MetaProtocol):
+            def __init__(self, *a, **k):
+                super().__init__(*a, root_dir=str(our_root), **k)
+
+            def run_protocols(self, *a, **k):
+                return None
+        mod.MetaProtocol = MetaProtocol
+        return mod
+
+    got = run_with(load_ours, str(our_root))
+    assert list(got) == list(want) and len(want) >= 12
+    for f in want:
+        assert got[f] == want[f], f
