@@ -177,3 +177,46 @@ def test_references_own_experiment_files_generate_the_same_env_files(tmp_path, m
     assert list(got) == list(want) and len(want) >= 12
     for f in want:
         assert got[f] == want[f], f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/abm/metarunner"), reason="reference tree not mounted")
+@pytest.mark.parametrize("app_name", ["app", "app_visual_flocking"])
+def test_env_to_kwargs_equals_the_references_own_app(monkeypatch, app_name):
+    """`.env` -> constructor kwargs: the reference's own `start()` (abm/app.py:16-70, app_visual_flocking.py:40-108) is
+    run on its own root `.env` with the simulation class replaced by a recorder of its keyword arguments; every kwarg it
+    passes must equal what abm_b200.params.simulation_kwargs makes of the same file (types included)."""
+    import importlib
+    from oracle import ref_shim
+    import sys
+    import types
+    ref_shim.install()
+    monkeypatch.setenv("EXPERIMENT_NAME", "")
+    # the interactive playground classes the apps import at module level pull in GUI widget packages: not on this path
+    for name, attrs in (("abm.simulation.isims", ("PlaygroundSimulation",)),
+                        ("abm.projects.visual_flocking.vf_simulation.vf_isims", ("VFPlaygroundSimulation",)),
+                        ("abm.projects.visual_flocking.vf_contrib.vf_playgroundtool", ("setup_visflock_playground",)),
+                        ("abm.contrib.playgroundtool", ())):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for a_ in attrs:
+                setattr(m, a_, object)
+            monkeypatch.setitem(sys.modules, name, m)
+    mod = importlib.import_module(f"abm.{app_name}")
+    captured = {}
+
+    class Recorder:
+        def __init__(self, **kw):
+            captured.update(kw)
+
+        def start(self):
+            pass
+    cls_name = "Simulation" if app_name == "app" else "VFSimulation"
+    monkeypatch.setattr(mod, cls_name, Recorder)
+    mod.start(parallel=False, headless=False)
+    assert len(captured) > 30
+    ours = params.simulation_kwargs(params.read_env("/root/reference/.env"))
+    for k, v in captured.items():
+        if k in ("parallel", "agent_behave_param_list"):
+            continue
+        assert k in ours, f"the reference passes {k!r}, simulation_kwargs does not"
+        assert ours[k] == v and type(ours[k]) is type(v), (k, ours[k], v)
