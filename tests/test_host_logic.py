@@ -220,3 +220,26 @@ def test_env_to_kwargs_equals_the_references_own_app(monkeypatch, app_name):
             continue
         assert k in ours, f"the reference passes {k!r}, simulation_kwargs does not"
         assert ours[k] == v and type(ours[k]) is type(v), (k, ours[k], v)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/abm/metarunner"), reason="reference tree not mounted")
+def test_parameter_sets_equal_the_references_param_modules(monkeypatch):
+    """DecisionParams / VFParams .from_env against the reference's own parameter modules (contrib/decision_params.py,
+    movement_params.py, vf_contrib/vf_params.py), which read the same root `.env` at import: every value the hot path
+    uses must agree -- including the VF_GAMMA key quirk (the file sets VF_GAM, the module reads VF_GAMMA)."""
+    import importlib
+    from oracle import ref_shim
+    ref_shim.install()
+    monkeypatch.setenv("EXPERIMENT_NAME", "")
+    env = params.read_env("/root/reference/.env")
+    dp = params.DecisionParams.from_env(env)
+    dec = importlib.reload(importlib.import_module("abm.contrib.decision_params"))
+    mov = importlib.reload(importlib.import_module("abm.contrib.movement_params"))
+    for k in ("T_w", "Eps_w", "g_w", "B_w", "w_max", "T_u", "Eps_u", "g_u", "B_u", "u_max", "S_wu", "S_uw", "Tau", "F_N", "F_R"):
+        assert getattr(dp, k) == getattr(dec, k), k
+    for k in ("exp_vel_max", "exp_theta_min", "exp_theta_max", "reloc_theta_max", "exp_stop_ratio"):
+        assert getattr(dp, k) == getattr(mov, k), k
+    vp = params.VFParams.from_env(env)
+    vfp = importlib.reload(importlib.import_module("abm.projects.visual_flocking.vf_contrib.vf_params"))
+    for k in ("GAM", "V0", "ALP0", "ALP1", "ALP2", "BET0", "BET1", "BET2", "BOUNDARY", "LIMIT_MOVEMENT", "MAX_VEL", "MAX_TH"):
+        assert getattr(vp, k) == getattr(vfp, k), k
