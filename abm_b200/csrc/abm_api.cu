@@ -877,6 +877,7 @@ int abm_vf_step_host(abm_engine_t* e, const float* xytv_in, float* xytv_out, int
   const uint32_t steps0 = e->steps_done;
   const int since0 = e->steps_since_sort;
   const int wide0 = e->wide_steps_left;
+  int wide_after = 0;
   const float4* in4 = reinterpret_cast<const float4*>(xytv_in);
   float4* out4 = reinterpret_cast<float4*>(xytv_out);
   int rc = ABM_OK;
@@ -894,6 +895,7 @@ int abm_vf_step_host(abm_engine_t* e, const float* xytv_in, float* xytv_out, int
     rc = abm_vf_step(e, n_steps, cs);
     e->chunk_nb = 0; e->chunk_b0 = 0;
     if (rc) break;
+    wide_after = std::max(wide_after, e->wide_steps_left);   // (a chunk's call may have seen a crowded scene: keep that)
     abm::launch_unpack_state4(e->rec[e->cur].p + o, e->theta.p + o, e->vel.p + o, nullptr, N, e->stage4.p + o, (long long)n, cs);
     ABM_CUDA(cudaEventRecord(e->io_step[c], cs));
     ABM_CUDA(cudaStreamWaitEvent(e->io_stream[1], e->io_step[c], 0));
@@ -902,6 +904,7 @@ int abm_vf_step_host(abm_engine_t* e, const float* xytv_in, float* xytv_out, int
     e->io_out_pending[c] = true;
   }
   if (rc) return rc;
+  e->wide_steps_left = wide_after;
   e->bbox_valid[0] = e->bbox_valid[1] = false;
   e->host_synced = false;
   // stream-ordered for the caller: work enqueued on `stream` after this call (and abm_synchronize) sees the downloads done

@@ -770,6 +770,30 @@ def test_step_host_matches_the_three_calls(built_lib, B, N, chunked):
     ea.close(); eb.close()
 
 
+def test_step_host_adapts_to_crowding_like_step(built_lib):
+    """The crowded-scene detection (pairs off the fast path, counted by the kernel, read back without blocking) also works
+    when the steps come in through abm_vf_step_host's replicate chunks: after a few calls the three-word variant runs,
+    and the results stay those of the plain calls."""
+    import torch
+    from abm_b200 import VFEngine
+    rng = np.random.default_rng(43)
+    B, N, W = 450, 1024, 2880.0
+    x, y, th, v = _random_scene(rng, B, N, W, spread=(1200.0, 1700.0))       # 1024 agents in 500 x 500 px: crowded
+    packed = np.ascontiguousarray(np.stack([x, y, th, v], axis=-1))
+    ea = VFEngine(B, N, resolution=1200, width=W, height=W)
+    eb = VFEngine(B, N, resolution=1200, width=W, height=W)
+    for e in (ea, eb):
+        e.set_params(); e.set_state_packed(packed, 10.0); e.step(1)
+    bufs = [torch.from_numpy(packed.copy()).pin_memory().numpy() for _ in range(2)]
+    ref = packed
+    for it in range(8):
+        ea.set_state_packed(ref); ea.step(1); ref = ea.get_state_packed()
+        eb.step_host(bufs[it % 2], bufs[(it + 1) % 2], 1); eb.synchronize()
+        assert np.array_equal(bufs[(it + 1) % 2], ref), it
+    assert ea.kernel_stats()["symmetric_wide"] > 0 and eb.kernel_stats()["symmetric_wide"] > 0
+    ea.close(); eb.close()
+
+
 @pytest.mark.parametrize("sorted_swarm", [False, True])
 def test_packed_state_matches_soa_state(built_lib, monkeypatch, sorted_swarm):
     """abm_set_state_packed / abm_get_state_packed (ONE interleaved (x, y, theta, vel) array per direction) against the
