@@ -131,7 +131,8 @@ struct abm_engine {
   unsigned long long* slow_host = nullptr;   // pinned copy of counters[4]
   cudaEvent_t slow_event = nullptr;
   bool slow_pending = false;
-  unsigned long long slow_seen = 0, sym_launches = 0, slow_req_launch = 0, slow_seen_launch = 0;
+  unsigned long long slow_seen = 0, sym_launches = 0;
+  double sym_units = 0.0, slow_req_units = 0.0, slow_seen_units = 0.0;   // unordered pairs the symmetric launches evaluated (a launch may be a replicate chunk)
   unsigned long long kstat[4] = {0, 0, 0, 0};   // launches: symmetric two-word / three-word, one-sided, warp
   unsigned long long kstat_cluster = 0;         // multi-step launches whose grid was one thread-block cluster
   int wide_steps_left = 0;   // steps the symmetric kernel still runs with its three-word fast path (crowded scene)
@@ -676,12 +677,11 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     if (adaptive && e->slow_pending && cudaEventQuery(e->slow_event) == cudaSuccess) {
       e->slow_pending = false;
       const unsigned long long entries = *e->slow_host - e->slow_seen;      // of the symmetric launches since the last look
-      const unsigned long long n_launch = e->slow_req_launch - e->slow_seen_launch;
-      e->slow_seen = *e->slow_host; e->slow_seen_launch = e->slow_req_launch;
-      const double pairs = 0.5 * (double)a.B * (double)a.N * (double)(a.N - 1);   // unordered; one queue entry each
+      const double pairs = e->slow_req_units - e->slow_seen_units;              // unordered; one queue entry each
+      e->slow_seen = *e->slow_host; e->slow_seen_units = e->slow_req_units;
       // crowded scene (many intervals wider than 32 bins): the next 64 steps take the three-word fast path (measured on
       // discs of decreasing radius, scratch/dense_probe.py); then a two-word step looks again
-      if (n_launch && (double)entries > kWideThreshold * pairs * (double)n_launch) e->wide_steps_left = 64;
+      if (pairs > 0.0 && (double)entries > kWideThreshold * pairs) e->wide_steps_left = 64;
     }
     bool use_sym = sym_ok && !small_grid;
     bool wide3 = false;
@@ -768,9 +768,12 @@ int abm_vf_step(abm_engine_t* e, int n_steps, void* stream) {
     if (e->n_peers > 0 && !fused_close) { abm::launch_vf_publish(a, st); ++e->launches; }
     e->last_kernel = use_sym ? "abm::vf_step_sym_kernel" : (use_warp ? "abm::vf_step_warp_kernel" : "abm::vf_step_kernel");
     ++e->kstat[use_sym ? (wide3 ? 1 : 0) : (use_warp ? 3 : 2)];
-    if (use_sym) ++e->sym_launches;
+    if (use_sym) {
+      ++e->sym_launches;
+      e->sym_units += 0.5 * (double)(e->chunk_nb > 0 ? e->chunk_nb : a.B) * (double)a.N * (double)(a.N - 1);
+    }
     if (adaptive && use_sym && !wide3 && !e->slow_pending) {   // (the share of slow pairs is defined by the two-word path)
-      e->slow_req_launch = e->sym_launches;
+      e->slow_req_units = e->sym_units;
       ABM_CUDA(cudaMemcpyAsync(e->slow_host, e->counters.p + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       ABM_CUDA(cudaEventRecord(e->slow_event, st));
       e->slow_pending = true;
