@@ -265,6 +265,31 @@ def test_invalid_calls_fail_loudly(built_lib):
         VFEngine(0, 8, resolution=1200, width=300.0, height=300.0)
 
 
+@pytest.mark.parametrize("boundary,fovr", [("walls", 1.0), ("infinite", 1.0), ("walls", 0.6)])
+def test_three_word_variant_with_unequal_radii_matches_oracle(built_lib, monkeypatch, boundary, fovr):
+    """The symmetric kernel's three-word fast path (ABM_VF_SYM_WIDE=1, otherwise chosen in crowded scenes) together with
+    its unequal-radii variant, in a crowded scene where most intervals are wider than 32 bins: against the oracle."""
+    monkeypatch.setenv("ABM_VF_KERNEL", "symmetric")
+    monkeypatch.setenv("ABM_VF_SYM_WIDE", "1")
+    rng = np.random.default_rng(77)
+    B, N, W = 2, 120, 260.0
+    R = int(1200 / fovr)
+    x, y, th, v = _random_scene(rng, B, N, W)
+    rad = rng.choice([5.0, 9.0, 12.0, 18.0], (B, N)).astype(np.float32)
+    fov = (-fovr * np.pi, fovr * np.pi)
+    eng = _engine(None, B, N, resolution=R, fov=fov, boundary=boundary, width=W, height=W)
+    eng.set_params(); eng.set_state(x, y, th, v, rad); eng.step(1)
+    assert eng.last_kernel() == "abm::vf_step_sym_kernel" and eng.kernel_stats()["symmetric_wide"] == 1
+    fields, terms, st = eng.fields(), eng.terms(), eng.get_state()
+    cfg = rs.VFConfig(R=R, fov=fov, boundary=boundary, width=W, height=W)
+    for b in range(B):
+        ref = rs.vf_step_frozen(x[b], y[b], th[b], v[b], rad[b], cfg)
+        assert np.array_equal(fields[b], ref["rows"][:, ::-1]), "stored field mismatch"
+        np.testing.assert_allclose(terms[b], ref["terms"], rtol=RTOL, atol=1e-9)
+        _check_state(st, ref, b)
+    eng.close()
+
+
 def test_per_replicate_parameter_sweep(built_lib):
     """One launch, one parameter set per replicate (the MetaProtocol sweep shape)."""
     rng = np.random.default_rng(5)
