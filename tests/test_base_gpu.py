@@ -177,6 +177,9 @@ def _random_state(rng, N, W, cfg):
     (1, 128, 1200, 350.0, True, 1.0),       # the largest replicate of the fused kernel, crowded
     (2, 37, 601, 300.0, True, 0.75),
     (1, 200, 1200, 400.0, True, 1.0),       # crowded: heavy occlusion
+    (1, 20, 8192, 250.0, True, 1.0),        # the largest resolution of the fused kernel (16-bit packed interval ends)
+    (1, 20, 10000, 250.0, True, 0.8),       # beyond it: the per-phase kernels whatever the batch shape
+    (2, 12, 8, 200.0, True, 1.0),           # the smallest ring the engine accepts
 ])
 def test_agent_phase_matches_oracle_random(built_lib, B, N, R, W, vis_excl, fovr):
     rng = np.random.default_rng(100 + N + R)
