@@ -31,7 +31,8 @@ class _RunOutputs:
 
     def _init_outputs(self, use_ifdb_logging, use_ram_logging, save_csv_files, use_zarr, save_root_dir, root_dir,
                       env_params):
-        if use_ifdb_logging:
+        if use_ifdb_logging and not use_ram_logging:   # (sims.py:206-208: RAM logging switches InfluxDB logging off -- the
+            # reference's experiment files set both)
             raise NotImplementedError("InfluxDB logging is out of scope of abm_b200: use USE_RAM_LOGGING=1")
         self.save_in_ram, self.save_csv_files, self.use_zarr = bool(use_ram_logging), bool(save_csv_files), bool(use_zarr)
         if self.save_csv_files and not self.save_in_ram:                           # sims.py:909-912

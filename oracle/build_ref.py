@@ -43,6 +43,9 @@ FILES = [
     "abm/projects/cooperative_signaling/__init__.py",
     "abm/projects/cooperative_signaling/cs_agent/__init__.py",
     "abm/projects/cooperative_signaling/cs_agent/cs_supcalc.py",
+    # the experiment definitions of BASELINE configs[2] and configs[3] (run unchanged through abm_b200.compat by the tests)
+    "abm/data/metaprotocol/experiments/figExp3BN50PatchyCollOcc.py",
+    "abm/data/metaprotocol/experiments/VFExp4c.py",
 ]
 
 

@@ -59,8 +59,8 @@ def test_simulation_facade_runs(built_lib):
 
 def test_apps_start_from_the_references_own_env_file(built_lib, tmp_path):
     """abm/app.py:16-70 and app_visual_flocking.py:40-108 mirrored: the reference's OWN root `.env` (copied unmodified to
-    oracle/_ref) -> kwargs -> Simulation / VFSimulation .start(), with only the run length, the InfluxDB switch and the
-    output folder overridden; the runs leave the reference's output layout."""
+    oracle/_ref) -> kwargs -> Simulation / VFSimulation .start(), with only the run length and the output folder
+    overridden; the runs leave the reference's output layout."""
     import glob
     from oracle import ref_shim
     env_file = os.path.join(ref_shim._reference_root(), ".env")
@@ -68,7 +68,8 @@ def test_apps_start_from_the_references_own_env_file(built_lib, tmp_path):
         pytest.skip("the reference's .env is not at hand")
     from abm_b200 import app, app_visual_flocking, params
     env = params.read_env(env_file)
-    over = dict(T=40, use_ifdb_logging=False, save_root_dir=str(tmp_path / "out"), n_replicates=2, seed=3)
+    over = dict(T=40, save_root_dir=str(tmp_path / "out"), n_replicates=2, seed=3)   # (the file sets USE_IFDB_LOGGING=1 AND
+    # USE_RAM_LOGGING=1: RAM logging wins, sims.py:206-208)
     vsim = app_visual_flocking.start(env_file=env_file, **over)                     # the file says APP_VERSION=VisualFlocking
     fov = float(env["AGENT_FOV"])
     assert vsim.t == 40 and vsim.N == int(env["N"]) and vsim.v_field_res == int(int(env["VISUAL_FIELD_RESOLUTION"]) / fov)
@@ -382,3 +383,42 @@ def test_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
             assert np.array_equal(got, np.trunc(want) if trunc else want), name
         assert not read_zarr_v2(os.path.join(d, "ag_mode.zarr")).any()
     eng.close()
+
+
+@pytest.mark.parametrize("exp_file,project_dirs", [("VFExp4c.py", 363), ("figExp3BN50PatchyCollOcc.py", 70)])
+def test_references_experiment_files_run_unchanged_on_the_engine(built_lib, tmp_path, exp_file, project_dirs):
+    """The drop-in claim end to end: the reference's OWN experiment file (BASELINE configs[3] / configs[2]; an unmodified
+    copy under oracle/_ref) is executed in a fresh interpreter with `import abm_b200.compat` in front and nothing else
+    changed but the run length (T = 25000 -> 120): its imports, its criteria, `generate_temp_env_files()` and
+    `run_protocols()` all run on the B200 engine, and every run of the sweep leaves the reference's output folder."""
+    import glob
+    import shutil
+    import subprocess
+    import sys
+    import textwrap
+    from oracle import ref_shim
+    ref_root = ref_shim._reference_root()
+    exp_path = os.path.join(ref_root, "abm/data/metaprotocol/experiments", exp_file)
+    if not os.path.isfile(exp_path):
+        pytest.skip("the reference's experiment files are not at hand")
+    shutil.copyfile(os.path.join(ref_root, ".env"), tmp_path / "dropin.env")        # the default env, `<root>/<EXP>.env`
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {repo!r})
+        import abm_b200.compat
+        src = open({exp_path!r}).read()
+        assert src.count('Constant("T", 25000)') == 1
+        exec(compile(src.replace('Constant("T", 25000)', 'Constant("T", 120)'), {exp_path!r}, "exec"))
+        print("EXPERIMENT_DONE")
+    """)
+    env = dict(os.environ, EXPERIMENT_NAME="dropin")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert "EXPERIMENT_DONE" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    runs = glob.glob(str(tmp_path / "abm/data/simulation_data/dropin/batch_0/*"))
+    assert len(runs) == project_dirs
+    from abm_b200.recorder import read_zarr_v2
+    ori = read_zarr_v2(os.path.join(sorted(runs)[0], "ag_ori.zarr"))
+    assert ori.shape[1] == 120 and np.isfinite(ori).all()
+    assert os.path.isfile(os.path.join(sorted(runs)[-1], "env_params.json"))
+    assert glob.glob(str(tmp_path / "abm/data/metaprotocol/temp/dropin/*.env")) == []   # every protocol was consumed

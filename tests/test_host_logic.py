@@ -243,3 +243,40 @@ def test_parameter_sets_equal_the_references_param_modules(monkeypatch):
     vfp = importlib.reload(importlib.import_module("abm.projects.visual_flocking.vf_contrib.vf_params"))
     for k in ("GAM", "V0", "ALP0", "ALP1", "ALP2", "BET0", "BET1", "BET2", "BOUNDARY", "LIMIT_MOVEMENT", "MAX_VEL", "MAX_TH"):
         assert getattr(vp, k) == getattr(vfp, k), k
+
+
+def test_compat_module_resolves_the_references_import_paths(tmp_path):
+    """`import abm_b200.compat`: the reference's import lines work unchanged and resolve to this package's mirrors; a
+    module outside the hot path fails like a missing package.  In a fresh interpreter (sys.modules is process-wide)."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {root!r})
+        import abm_b200.compat
+        from abm.metarunner.metarunner import Tunable, Constant, MetaProtocol, TunedPairRestrain
+        from abm import app, app_visual_flocking
+        from abm.simulation.sims import Simulation
+        from abm.projects.visual_flocking.vf_simulation.vf_sims import VFSimulation
+        from abm.projects.visual_flocking.vf_agent import vf_supcalc
+        from abm.projects.cooperative_signaling.cs_agent import cs_supcalc
+        from abm.agent import supcalc
+        import abm_b200.metarunner, abm_b200.simulation, abm_b200.vf_supcalc
+        assert MetaProtocol is abm_b200.metarunner.MetaProtocol and Simulation is abm_b200.simulation.Simulation
+        assert VFSimulation is abm_b200.simulation.VFSimulation and vf_supcalc is abm_b200.vf_supcalc
+        assert callable(supcalc.projection_field) and callable(cs_supcalc.projection_field) and callable(app.start)
+        mp = MetaProtocol("e", default_envconf={{"N": "3"}}, root_dir={str(tmp_path)!r})
+        mp.add_criterion(Tunable("X", values_override=[1, 2])); mp.add_criterion(Constant("Y", 5))
+        assert mp.generate_temp_env_files() == 2
+        try:
+            import abm.replay.replay
+            raise SystemExit("a module outside the hot path must not resolve")
+        except ModuleNotFoundError:
+            pass
+        abm_b200.compat.install()                      # idempotent
+        print("COMPAT_OK")
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "COMPAT_OK" in out.stdout, out.stdout + out.stderr
