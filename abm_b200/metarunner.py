@@ -186,10 +186,14 @@ class MetaProtocol:
         temp_dir = os.path.join(self.root_dir, self.temp_dir)
         paths = sorted(glob.iglob(os.path.join(temp_dir, "*.env")))
         rep_keys = VF_REPLICATE_KEYS if project == "VisualFlocking" else BASE_REPLICATE_KEYS
+        # the foraging engine takes FOV and vision range per agent (abm_base_set_agent_geometry): per replicate as well
+        # (in the flocking project AGENT_FOV rescales the resolution, vf_sims.py:41-44: a different shape)
+        geo_keys = ("AGENT_FOV", "VISION_RANGE") if project == "Base" else ()
         groups = {}
         for p in paths:
             env = params.read_env(p)
-            shape = tuple(sorted((k, v) for k, v in env.items() if k not in rep_keys and k != "SAVE_ROOT_DIR"))
+            shape = tuple(sorted((k, v) for k, v in env.items()
+                                 if k not in rep_keys and k not in geo_keys and k != "SAVE_ROOT_DIR"))
             groups.setdefault(shape, []).append((p, env))
         self.results = []
         for g, members in enumerate(groups.values()):
@@ -209,6 +213,11 @@ class MetaProtocol:
                 base = dict(dp.engine_kwargs(), agent_consumption=kw["agent_consumption"])
                 per = {name: [float(e.get(k, base[name])) for e in envs] for k, name in rep_keys.items()}
                 sim.engine.set_params(**per)
+                fovs = np.array([float(e.get("AGENT_FOV", kw["agent_fov"])) for e in envs])
+                ranges = np.array([float(int(float(e.get("VISION_RANGE", kw["vision_range"])))) for e in envs])   # app.py:53
+                if (fovs != fovs[0]).any() or (ranges != ranges[0]).any():
+                    ones = np.ones((1, sim.N))
+                    sim.engine.set_agent_geometry(agent_fov=fovs[:, None] * ones, vision_range=ranges[:, None] * ones)
             else:
                 raise NotImplementedError(f"project {project!r} is out of scope of abm_b200")
             sim.start()

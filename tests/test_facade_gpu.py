@@ -312,6 +312,39 @@ def test_metaprotocol_foraging_sweep_groups_by_shape(built_lib, tmp_path):
         assert any(float(e["DEC_EPSU"]) > 0 and a["collected"][b].sum() > 0 for b, e in enumerate(sim.env_params))
 
 
+def test_metaprotocol_foraging_sweep_over_fov_is_one_batch(built_lib, tmp_path):
+    """A sweep over AGENT_FOV (the reference's figExp2A files sweep it from 0 to 1) and VISION_RANGE runs as ONE batch of
+    the foraging engine -- FOV and vision range are per-agent quantities there -- and every replicate sees through ITS
+    field of view: nothing at 0, only the front half of the ring at 0.5, everything at 1."""
+    from abm_b200 import metarunner as mr
+    env = dict(N="20", T="60", VISUAL_FIELD_RESOLUTION="400", ENV_WIDTH="250", ENV_HEIGHT="250", RADIUS_AGENT="10",
+               N_RESOURCES="2", RADIUS_RESOURCE="60", MIN_RESOURCE_PER_PATCH="4000", MAX_RESOURCE_PER_PATCH="4001",
+               MIN_RESOURCE_QUALITY="0.25", MAX_RESOURCE_QUALITY="0.25", VISUAL_EXCLUSION="0", TELEPORT_TO_MIDDLE="0",
+               PATCH_BORDER_OVERLAP="1", AGENT_AGENT_COLLISION="0", GHOST_WHILE_EXPLOIT="1", AGENT_CONSUMPTION="1",
+               REGENERATE_PATCHES="1", USE_RAM_LOGGING="0", DEC_EPSW="2", DEC_EPSU="3")
+    mp = mr.MetaProtocol("fov", num_batches=1, default_envconf=env, root_dir=str(tmp_path))
+    mp.add_criterion(mr.Tunable("AGENT_FOV", values_override=[0, 0.5, 1]))
+    mp.add_criterion(mr.Tunable("VISION_RANGE", values_override=[2000, 30]))
+    assert mp.generate_temp_env_files() == 6
+    res = mp.run_protocols(project="Base", seed=5)
+    assert len(res) == 1 and res[0][1].B == 6                     # ONE batch
+    sim = res[0][1]
+    seen = {}
+    for _ in range(40):                                           # the union of the fields over some more steps
+        sim.step_sim()
+        f = sim.engine.fields()
+        for b, e in enumerate(sim.env_params):
+            key = (float(e["AGENT_FOV"]), int(e["VISION_RANGE"]))
+            seen[key] = seen.get(key, 0) | f[b].any(axis=0)
+    R = 400
+    assert not seen[(0.0, 2000)].any() and not seen[(0.0, 30)].any()
+    half = seen[(0.5, 2000)]
+    assert half.any() and not half[:R // 4 - 1].any() and not half[3 * R // 4 + 2:].any()     # only the front half
+    full = seen[(1.0, 2000)]
+    assert full[:R // 4 - 1].any() and full[3 * R // 4 + 2:].any()
+    assert seen[(1.0, 30)].sum() < full.sum()                      # a 30-px vision range sees fewer exploiters
+
+
 def test_simulation_writes_reference_output_folder(built_lib, tmp_path):
     """Simulation(use_ram_logging, save_csv_files, use_zarr) -> <root>/<SAVE_ROOT_DIR>/<timestamp>/ with the agent and
     resource arrays of ifdb.py:435-535 and env_params.json; saving without logging raises like sims.py:909-912."""
