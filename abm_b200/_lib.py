@@ -163,6 +163,7 @@ SYMBOLS = {
     "abm_base_get_patches": (C.c_int, [_P, C.POINTER(BasePatches), C.c_int, _P]),
     "abm_base_step": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_uint32, _P]),
     "abm_base_inject_regeneration": (C.c_int, [_P, _P, C.c_int]),
+    "abm_base_set_regeneration_params": (C.c_int, [_P, _P, C.c_int]),
     "abm_base_get_fields": (C.c_int, [_P, _P, C.c_int, _P]),
     "abm_base_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "abm_base_metrics": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),

@@ -129,6 +129,20 @@ class BaseEngine:
         _lib.check(self._lib.abm_base_set_agent_resolution(self._h, C.c_void_p(r.ctypes.data), self.B * self.N),
                    "abm_base_set_agent_resolution")
 
+    def set_regeneration_params(self, patch_radius=None, min_resc_quality=None, max_resc_quality=None,
+                                min_resc_perpatch=None, max_resc_perpatch=None):
+        """One set of patch-regeneration parameters per replicate (scalars or length-B arrays; a sweep over the patch
+        parameters as one batch); without arguments: back to the constructor's values."""
+        vals = (patch_radius, min_resc_quality, max_resc_quality, min_resc_perpatch, max_resc_perpatch)
+        if all(v is None for v in vals):
+            _lib.check(self._lib.abm_base_set_regeneration_params(self._h, None, 0), "abm_base_set_regeneration_params")
+            return
+        if any(v is None for v in vals):
+            raise ValueError("set_regeneration_params: give all five parameters (or none)")
+        tab = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(v, np.float64), (self.B,)) for v in vals], axis=1))
+        _lib.check(self._lib.abm_base_set_regeneration_params(self._h, C.c_void_p(tab.ctypes.data), self.B),
+                   "abm_base_set_regeneration_params")
+
     def set_agent_radii(self, radius=None):
         """Per-agent radius, (B, N) or (N,) (heterogeneous agents, sims.py:502); None returns to the engine-wide one."""
         if radius is None:

@@ -187,7 +187,8 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
       if (lane == 0) {
         bool placed = false;
         for (unsigned t = 0; t < 10000u && !placed; ++t) {      // max_retries, sims.py:335
-          const double R_ = a.patch_radius;
+          const double* rt = a.regen_tab ? a.regen_tab + (size_t)b * 5 : nullptr;   // this replicate's own patch parameters
+          const double R_ = rt ? rt[0] : a.patch_radius;
           double nx, ny, q;
           int units;
           if (a.regen_draws) {                                  // injected draws (parity tests): try t of this slot
@@ -203,8 +204,10 @@ __device__ __forceinline__ void base_env_replicate(const BaseKernelArgs& a, int 
             const uint4 rn2 = philox4x32(make_uint4((uint32_t)b, (uint32_t)p, step, t), make_uint2((uint32_t)a.seed, 0x51554c54u));
             nx = floor(lox + floor(hix - lox) * u01(rn.x, rn.y));          // np.random.randint(lo, hi)
             ny = floor(loy + floor(hiy - loy) * u01(rn.z, rn.w));
-            units = a.min_units + (int)floor((double)(a.max_units - a.min_units) * u01(rn2.x, rn2.y));
-            q = a.min_quality + (a.max_quality - a.min_quality) * u01(rn2.z, rn2.w);
+            const int u_lo = rt ? (int)rt[3] : a.min_units, u_hi = rt ? (int)rt[4] : a.max_units;
+            const double q_lo = rt ? rt[1] : a.min_quality, q_hi = rt ? rt[2] : a.max_quality;
+            units = u_lo + (int)floor((double)(u_hi - u_lo) * u01(rn2.x, rn2.y));
+            q = q_lo + (q_hi - q_lo) * u01(rn2.z, rn2.w);
           }
           bool ok = true;
           for (int p2 = 0; p2 < a.P; ++p2) {                                          // proove_sprite: no patch-patch overlap

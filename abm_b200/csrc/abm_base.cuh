@@ -56,6 +56,9 @@ struct BaseKernelArgs {
   // patch regeneration (sims.py:332-374)
   double patch_radius, min_quality, max_quality;
   int min_units, max_units;
+  // nullable, B x 5 doubles (patch radius, min / max quality, min / max units): one set per replicate -- a sweep over the
+  // patch parameters as one batch (abm_base_set_regeneration_params)
+  const double* regen_tab;
   unsigned long long seed;
   unsigned step;               // time step index, part of the RNG counter
   BaseAgentPtrs ag;            // B*N, updated in place

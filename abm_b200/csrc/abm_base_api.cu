@@ -31,6 +31,8 @@ struct abm_base_engine {
   bool has_agent_geo = false;
   std::vector<double> h_fov0, h_fov1, h_vr;   // host copies of what the two calls set (either may be empty)
   std::vector<int> h_res;
+  DevBuf<double> regen_tab;              // B x 5 once abm_base_set_regeneration_params was called
+  bool has_regen_tab = false;
   DevBuf<double> regen_draws;            // abm_base_inject_regeneration
   int regen_tries = 0;
   DevBuf<float> agent_radius;            // B*N once abm_base_set_agent_radii was called
@@ -150,7 +152,7 @@ int abm_base_destroy(abm_base_engine_t* e) {
                            &e->pquality}) b->release();
   for (DevBuf<int32_t>* b : {&e->env_status, &e->override_mode, &e->mode, &e->patch_id, &e->snap_override, &e->pid,
                              &e->collided}) b->release();
-  e->novelty.release(); e->fields.release(); e->params.release(); e->agent_geo.release(); e->regen_draws.release(); e->agent_radius.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
+  e->novelty.release(); e->fields.release(); e->params.release(); e->agent_geo.release(); e->regen_tab.release(); e->regen_draws.release(); e->agent_radius.release(); e->counters.release(); e->mode_steps.release(); e->metrics.release();
   delete e;
   return ABM_OK;
 }
@@ -321,6 +323,7 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   a.width = c.width; a.height = c.height; a.pad = c.window_pad; a.vision_range = c.vision_range; a.radius = c.agent_radius;
   a.patch_radius = c.patch_radius; a.min_quality = c.min_quality; a.max_quality = c.max_quality;
   a.min_units = c.min_units; a.max_units = c.max_units; a.seed = c.seed;
+  a.regen_tab = e->has_regen_tab ? e->regen_tab.p : nullptr;
   a.ag = abm::BaseAgentPtrs{e->x.p, e->y.p, e->theta.p, e->vel.p, e->w.p, e->u.p, e->collected.p,
                             e->collected_before.p, e->i_priv.p, e->env_status.p, e->override_mode.p, e->mode.p,
                             e->patch_id.p, e->novelty.p, e->snap_x.p, e->snap_y.p, e->snap_override.p, e->collided.p,
@@ -390,6 +393,24 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
   }
   ABM_CUDA(cudaGetLastError());
   if (inject_dtheta && !inject_on_device) ABM_CUDA(cudaStreamSynchronize(st));
+  return ABM_OK;
+}
+
+int abm_base_set_regeneration_params(abm_base_engine_t* e, const double* table, int n) {
+  if (!e) return fail(ABM_E_INVALID, "abm_base_set_regeneration_params: null engine");
+  if (n == 0) { e->has_regen_tab = false; return ABM_OK; }      // back to the config's values
+  if (!table) return fail(ABM_E_INVALID, "abm_base_set_regeneration_params: null argument");
+  if (n != e->cfg.n_replicates)
+    return fail(ABM_E_INVALID, "abm_base_set_regeneration_params: n must be n_replicates (or 0)");
+  for (int b = 0; b < n; ++b) {
+    const double* t = table + (size_t)b * 5;
+    if (!(t[0] > 0.0) || t[2] < t[1] || t[4] < t[3])
+      return fail(ABM_E_INVALID, "abm_base_set_regeneration_params: radius > 0, max >= min expected");
+  }
+  ABM_CUDA(cudaSetDevice(e->device));
+  if (!e->regen_tab.p) ABM_CUDA(e->regen_tab.alloc((size_t)n * 5));
+  ABM_CUDA(cudaMemcpy(e->regen_tab.p, table, sizeof(double) * (size_t)n * 5, cudaMemcpyHostToDevice));
+  e->has_regen_tab = true;
   return ABM_OK;
 }
 

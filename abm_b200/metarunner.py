@@ -189,6 +189,10 @@ class MetaProtocol:
         # the foraging engine takes FOV and vision range per agent (abm_base_set_agent_geometry): per replicate as well
         # (in the flocking project AGENT_FOV rescales the resolution, vf_sims.py:41-44: a different shape)
         geo_keys = ("AGENT_FOV", "VISION_RANGE") if project == "Base" else ()
+        # ... and one set of patch parameters per replicate (abm_base_set_regeneration_params); N_RESOURCES stays a shape
+        patch_keys = ("RADIUS_RESOURCE", "MIN_RESOURCE_PER_PATCH", "MAX_RESOURCE_PER_PATCH", "MIN_RESOURCE_QUALITY",
+                      "MAX_RESOURCE_QUALITY") if project == "Base" else ()
+        geo_keys = geo_keys + patch_keys
         groups = {}
         for p in paths:
             env = params.read_env(p)
@@ -215,6 +219,11 @@ class MetaProtocol:
                 sim.engine.set_params(**per)
                 fovs = np.array([float(e.get("AGENT_FOV", kw["agent_fov"])) for e in envs])
                 ranges = np.array([float(int(float(e.get("VISION_RANGE", kw["vision_range"])))) for e in envs])   # app.py:53
+                pk = [params.simulation_kwargs(e) for e in envs]
+                patch = {k: np.array([float(q[k]) for q in pk]) for k in ("patch_radius", "min_resc_perpatch", "max_resc_perpatch",
+                                                                           "min_resc_quality", "max_resc_quality")}
+                if any((v != v[0]).any() for v in patch.values()):
+                    sim.set_replicate_patch_params(**patch)
                 if (fovs != fovs[0]).any() or (ranges != ranges[0]).any():
                     ones = np.ones((1, sim.N))
                     sim.engine.set_agent_geometry(agent_fov=fovs[:, None] * ones, vision_range=ranges[:, None] * ones)

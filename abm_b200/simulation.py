@@ -415,12 +415,28 @@ class Simulation(_RunOutputs):
         self.engine.set_agents(x=x, y=y, theta=th)
         self.agents = [AgentView(self, 0, i) for i in range(self.N)]
 
+    def set_replicate_patch_params(self, patch_radius, min_resc_perpatch, max_resc_perpatch, min_resc_quality,
+                                   max_resc_quality):
+        """One set of patch parameters per replicate (length-B arrays): a sweep over RADIUS_RESOURCE / the resource units /
+        the quality as ONE batch.  The rules for negative maxima are the constructor's (sims.py:176-179), per replicate."""
+        a = lambda v: np.broadcast_to(np.asarray(v, np.float64), (self.B,)).copy()
+        R, u0, u1, q0, q1 = a(patch_radius), a(min_resc_perpatch), a(max_resc_perpatch), a(min_resc_quality), a(max_resc_quality)
+        q1 = np.where(q1 < 0, q0, q1)
+        u1 = np.where(u1 < 0, u0 + 1, u1)
+        self._patch_params = dict(R=R, u0=u0, u1=u1, q0=q0, q1=q1)
+        self.engine.set_regeneration_params(patch_radius=R, min_resc_quality=q0, max_resc_quality=q1, min_resc_perpatch=u0,
+                                            max_resc_perpatch=u1)
+
     def create_resources(self):
         """sims.py:539-541 -> add_new_resource_patch (:332-374): rejection-sampled, no patch-patch overlap."""
-        P, R = self.N_resc, self.resc_radius
+        P = self.N_resc
+        pp = getattr(self, "_patch_params", None)
         pa = {k: np.zeros((self.B, P), np.float32) for k in ("x", "y", "radius", "left", "quality")}
         pa["id"] = np.tile(np.arange(1, P + 1, dtype=np.int32), (self.B, 1))
         for b in range(self.B):
+            R = self.resc_radius if pp is None else int(pp["R"][b]) if float(pp["R"][b]).is_integer() else float(pp["R"][b])
+            u0, u1 = (self.min_resc_units, self.max_resc_units) if pp is None else (int(pp["u0"][b]), int(pp["u1"][b]))
+            q0, q1 = (self.min_resc_quality, self.max_resc_quality) if pp is None else (float(pp["q0"][b]), float(pp["q1"][b]))
             for p in range(P):
                 for _retry in range(10000):
                     if self.allow_border_patch_overlap:
@@ -429,8 +445,8 @@ class Simulation(_RunOutputs):
                     else:
                         x = self._rng.randint(self.window_pad, self.WIDTH + self.window_pad - 2 * R)
                         y = self._rng.randint(self.window_pad, self.HEIGHT + self.window_pad - 2 * R)
-                    units = self._rng.randint(self.min_resc_units, self.max_resc_units)
-                    quality = self._rng.uniform(self.min_resc_quality, self.max_resc_quality)
+                    units = self._rng.randint(u0, u1)
+                    quality = self._rng.uniform(q0, q1)
                     d2 = (pa["x"][b, :p] - x) ** 2 + (pa["y"][b, :p] - y) ** 2
                     if not (d2 <= (2 * R) ** 2).any():
                         break

@@ -400,6 +400,11 @@ int abm_base_step(abm_base_engine_t* e, int n_steps, const float* inject_dtheta,
  * n_tries counts as failed (abm_base_get_counters [1]) and leaves the slot dead.  Applies to all following steps;
  * draws == NULL or n_tries <= 0 returns to the engine's counter-based RNG. */
 int abm_base_inject_regeneration(abm_base_engine_t* e, const double* draws, int n_tries);
+/* One set of patch-regeneration parameters per replicate (a MetaProtocol sweep over RADIUS_RESOURCE,
+ * MIN/MAX_RESOURCE_PER_PATCH, MIN/MAX_RESOURCE_QUALITY as ONE batch; add_new_resource_patch, sims.py:332-374, reads them
+ * from the simulation object): table = n_replicates x 5 doubles (patch radius, min quality, max quality, min units,
+ * max units), host pointer; n = 0 returns to the values of the config. */
+int abm_base_set_regeneration_params(abm_base_engine_t* e, const double* table, int n);
 
 /* Packed STORED fields (flipped + FOV-masked: Agent.soc_v_field, agent.py:593-597) of the last step. */
 int abm_base_get_fields(abm_base_engine_t* e, uint32_t* packed, int on_device, void* stream);

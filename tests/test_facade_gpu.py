@@ -345,6 +345,33 @@ def test_metaprotocol_foraging_sweep_over_fov_is_one_batch(built_lib, tmp_path):
     assert seen[(1.0, 30)].sum() < full.sum()                      # a 30-px vision range sees fewer exploiters
 
 
+def test_metaprotocol_foraging_sweep_over_patch_parameters_is_one_batch(built_lib, tmp_path):
+    """A sweep over the patch parameters (the reference's figExp3 file -- BASELINE configs[2] -- sweeps RADIUS_RESOURCE and
+    DEC_EPSW) runs as ONE batch: every replicate creates AND regenerates its patches with its own radius, units and
+    quality (add_new_resource_patch, sims.py:332-374, reads them from the simulation)."""
+    from abm_b200 import metarunner as mr
+    env = dict(N="16", T="400", VISUAL_FIELD_RESOLUTION="320", ENV_WIDTH="300", ENV_HEIGHT="300", RADIUS_AGENT="10",
+               AGENT_FOV="1", VISION_RANGE="2000", N_RESOURCES="3", MAX_RESOURCE_PER_PATCH="-1", MAX_RESOURCE_QUALITY="-1",
+               VISUAL_EXCLUSION="1", TELEPORT_TO_MIDDLE="0", PATCH_BORDER_OVERLAP="1", AGENT_AGENT_COLLISION="0",
+               GHOST_WHILE_EXPLOIT="1", AGENT_CONSUMPTION="1", REGENERATE_PATCHES="1", USE_RAM_LOGGING="0",
+               DEC_EPSW="2", DEC_EPSU="3", DEC_SWU="0", DEC_SUW="0")
+    mp = mr.MetaProtocol("patches", num_batches=1, default_envconf=env, root_dir=str(tmp_path))
+    mp.add_criterion(mr.Tunable("RADIUS_RESOURCE", values_override=[20, 45]))
+    mp.add_criterion(mr.Tunable("MIN_RESOURCE_PER_PATCH", values_override=[4, 60]))
+    mp.add_criterion(mr.Tunable("MIN_RESOURCE_QUALITY", values_override=[0.25, 1.0]))
+    assert mp.generate_temp_env_files() == 8
+    res = mp.run_protocols(project="Base", seed=11)
+    assert len(res) == 1 and res[0][1].B == 8
+    sim = res[0][1]
+    p, cnt = sim.engine.get_patches(), sim.engine.counters()
+    assert cnt["patches_regenerated"] > 0 and cnt["regeneration_failed"] == 0      # the 4-unit patches are eaten up
+    for b, e in enumerate(sim.env_params):
+        R, units, q = float(e["RADIUS_RESOURCE"]), int(e["MIN_RESOURCE_PER_PATCH"]), float(e["MIN_RESOURCE_QUALITY"])
+        assert (p["radius"][b] == R).all()                                          # created and re-created with ITS radius
+        assert (p["quality"][b] == np.float32(q)).all()                             # max < 0: the minimum is the value
+        assert (p["left"][b] <= units).all() and (p["left"][b] > 0).all()           # units in [min, min + 1)
+
+
 def test_simulation_writes_reference_output_folder(built_lib, tmp_path):
     """Simulation(use_ram_logging, save_csv_files, use_zarr) -> <root>/<SAVE_ROOT_DIR>/<timestamp>/ with the agent and
     resource arrays of ifdb.py:435-535 and env_params.json; saving without logging raises like sims.py:909-912."""
