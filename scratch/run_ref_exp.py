@@ -4,8 +4,10 @@ import sys, time
 sys.path.insert(0, '/root/repo')
 import abm_b200.compat
 path, T = sys.argv[1], int(sys.argv[2])
+import re
 src = open(path).read()
-assert src.count('Constant("T", 25000)') == 1
+src, n = re.subn(r'Constant\("T",\s*[0-9]+\)', f'Constant("T", {T})', src)
+assert n >= 1, "no Constant(\"T\", ...) in this file"
 t0 = time.time()
-exec(compile(src.replace('Constant("T", 25000)', f'Constant("T", {T})'), path, "exec"))
+exec(compile(src, path, "exec"))
 print("EXPERIMENT_DONE in %.1f s" % (time.time() - t0))
