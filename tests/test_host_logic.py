@@ -280,3 +280,72 @@ def test_compat_module_resolves_the_references_import_paths(tmp_path):
     """)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert "COMPAT_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/abm/metarunner"), reason="reference tree not mounted")
+@pytest.mark.parametrize("variant", ["batches_and_bools", "tuned_pair", "quadratic_pair", "no_experiment_name", "linspace"])
+def test_env_generation_equals_the_references_metarunner(tmp_path, monkeypatch, variant):
+    """The sweep language against the reference's own classes (a temporary copy of abm/metarunner/metarunner.py, `abm.app`
+    stubbed): the same criteria given to both MetaProtocols -- several batches, boolean values, a product restraint, a
+    quadratic restraint, no experiment name, a linspace Tunable -- generate the same env files (names, keys, values)."""
+    import importlib.util
+    import shutil
+    import sys
+    import types
+    exp_name = None if variant == "no_experiment_name" else "gen_exp"
+    monkeypatch.setenv("EXPERIMENT_NAME", exp_name or "")
+    ref_root = tmp_path / "ref"
+    os.makedirs(ref_root / "abm/metarunner")
+    shutil.copyfile("/root/reference/abm/metarunner/metarunner.py", ref_root / "abm/metarunner/metarunner.py")
+    shutil.copyfile("/root/reference/.env", ref_root / f"{exp_name or ''}.env")
+    our_root = tmp_path / "ours"
+    os.makedirs(our_root)
+    shutil.copyfile("/root/reference/.env", our_root / f"{exp_name or ''}.env")
+    saved = {k: sys.modules.get(k) for k in ("abm", "abm.app")}
+    try:
+        pkg = types.ModuleType("abm"); pkg.__path__ = []
+        sys.modules["abm"] = pkg
+        sys.modules["abm.app"] = types.ModuleType("abm.app"); pkg.app = sys.modules["abm.app"]
+        spec = importlib.util.spec_from_file_location("ref_metarunner_copy", ref_root / "abm/metarunner/metarunner.py")
+        ref = importlib.util.module_from_spec(spec)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+    def build(m, **kw):
+        mp = m.MetaProtocol(experiment_name=exp_name, num_batches=3 if variant == "batches_and_bools" else 1,
+                            parallel=exp_name is not None, description="d", headless=True, **kw)
+        if variant == "batches_and_bools":
+            mp.add_criterion(m.Tunable("VISUAL_EXCLUSION", values_override=[True, False]))
+            mp.add_criterion(m.Constant("N", 7))
+        elif variant == "tuned_pair":
+            mp.add_criterion(m.Tunable("N_RESOURCES", values_override=[1, 2, 3, 4, 6]))
+            mp.add_criterion(m.Tunable("MIN_RESOURCE_PER_PATCH", values_override=[100, 200, 300, 400, 600]))
+            mp.add_tuned_pair(m.TunedPairRestrain("N_RESOURCES", "MIN_RESOURCE_PER_PATCH", 1200))
+        elif variant == "quadratic_pair":
+            mp.add_criterion(m.Tunable("N_RESOURCES", values_override=[1, 4, 16]))
+            mp.add_criterion(m.Tunable("RADIUS_RESOURCE", values_override=[10.0, 20.0, 40.0]))
+            mp.add_quadratic_tuned_pair(m.TunedPairRestrain("N_RESOURCES", "RADIUS_RESOURCE", 1600))
+        elif variant == "linspace":
+            mp.add_criterion(m.Tunable("DEC_EPSW", 0, 5, 6))
+            mp.add_criterion(m.Tunable("DEC_EPSU", 0.5, 1.5, 3))
+        else:
+            mp.add_criterion(m.Tunable("DEC_EPSW", values_override=[0, 1]))
+        with contextlib.redirect_stdout(io.StringIO()):
+            mp.generate_temp_env_files()
+        return mp
+
+    build(ref)
+    build(mr, root_dir=str(our_root))
+    sub = os.path.join("abm/data/metaprotocol/temp", exp_name) if exp_name else "abm/data/metaprotocol/temp"
+    want = {f: params.read_env(os.path.join(ref_root, sub, f)) for f in sorted(os.listdir(os.path.join(ref_root, sub)))}
+    got = {f: params.read_env(os.path.join(our_root, sub, f)) for f in sorted(os.listdir(os.path.join(our_root, sub)))}
+    assert list(got) == list(want) and len(want) >= 2
+    for f in want:
+        assert got[f] == want[f], (f, {k: (got[f].get(k), want[f].get(k)) for k in set(got[f]) | set(want[f]) if got[f].get(k) != want[f].get(k)})
