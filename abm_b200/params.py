@@ -5,6 +5,7 @@ dataclasses built from one env dictionary instead of modules re-imported per age
 from __future__ import annotations
 
 import os
+import re
 from dataclasses import dataclass
 
 
@@ -19,8 +20,10 @@ def read_env(path: str) -> dict:
                 continue
             k, v = line.split("=", 1)
             v = v.strip()
-            if len(v) >= 2 and v[0] == v[-1] and v[0] in "\"'":
-                v = v[1:-1]
+            if v[:1] in ("\"", "'") and v.find(v[0], 1) > 0:     # quoted: up to the closing quote (a comment may follow)
+                v = v[1:v.find(v[0], 1)]
+            else:                                                # unquoted: an inline comment starts at whitespace + '#'
+                v = re.sub(r"\s+#.*", "", v).rstrip()
             out[k.strip()] = v
     return out
 

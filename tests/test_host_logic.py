@@ -349,3 +349,18 @@ def test_env_generation_equals_the_references_metarunner(tmp_path, monkeypatch, 
     assert list(got) == list(want) and len(want) >= 2
     for f in want:
         assert got[f] == want[f], (f, {k: (got[f].get(k), want[f].get(k)) for k in set(got[f]) | set(want[f]) if got[f].get(k) != want[f].get(k)})
+
+
+def test_read_env_equals_dotenv(tmp_path):
+    """params.read_env against python-dotenv's dotenv_values (what the reference reads its `.env` files with) on the
+    reference's own root `.env` (if at hand) and on a file with comments, blank lines, quotes, inline comments and `=`
+    inside values."""
+    dotenv = pytest.importorskip("dotenv")
+    tricky = tmp_path / "t.env"
+    tricky.write_text("\n".join(["# a comment", "", "N=10", 'NAME="quoted value"', "SINGLE='single'", "SPACED = 5", "WITH_EQ=a=b",
+                                 "INLINE=3 # trailing comment", "EMPTY=", "SAVE_ROOT_DIR=abm/data/simulation_data/x/batch_0", ""]))
+    paths = [str(tricky)]
+    if os.path.isfile("/root/reference/.env"):
+        paths.append("/root/reference/.env")
+    for p in paths:
+        assert params.read_env(p) == dict(dotenv.dotenv_values(p)), p
