@@ -52,6 +52,14 @@ def read_zarr_v2(path) -> np.ndarray:
     return out
 
 
+def agent_row(agent_id: int, n_agents: int) -> int:
+    """Row of the `ag_*.zarr` arrays that holds agent ``agent_id``.  The reference writes agent ``ag_id`` into row
+    ``ag_id - 1`` (ifdb.py:504-508) while its agents are numbered from 0 (sims.py:528, vf_sims.py:212): agent 0 ends up
+    in the LAST row (index -1), agent i in row i - 1.  The recorders here leave exactly that layout on disk (patches are
+    numbered from 1, sims.py:362, so patch p is row p - 1 = its slot)."""
+    return (agent_id - 1) % n_agents
+
+
 class VFRecorder:
     """Records a VFEngine's trajectory.  ``replicates``: which replicates to keep (default: all);
     ``every``: record every k-th call of `record()`; ``chunk``: steps per device ring / per zarr chunk."""
@@ -146,7 +154,7 @@ class VFRecorder:
                     blk[:, 0] = np.trunc(blk[:, 0]); blk[:, 1] = np.trunc(blk[:, 1])   # int(agent.position[.]), ifdb.py:83-84
                     for fi, name in enumerate(_FIELDS):
                         out = np.zeros((self.N, self.chunk), np.float64)
-                        out[:, :n] = blk[:, fi].T
+                        out[:, :n] = np.roll(blk[:, fi].T, -1, axis=0)        # row = agent id - 1 (see agent_row)
                         out.tofile(os.path.join(d, f"ag_{name}.zarr", f"0.{chunk_idx}"))
                     np.zeros((self.N, self.chunk), np.float64).tofile(os.path.join(d, "ag_mode.zarr", f"0.{chunk_idx}"))
             except Exception as exc:                                          # surfaced by close()
@@ -214,7 +222,10 @@ class BaseRecorder:
                 for n, steps in store.items():
                     if not steps:
                         continue
-                    arr = np.ascontiguousarray(np.stack([s[ri] for s in steps], axis=1))     # (num, T)
+                    arr = np.stack([s[ri] for s in steps], axis=1)                          # (num, T)
+                    if prefix == "ag":
+                        arr = np.roll(arr, -1, axis=0)                                      # row = agent id - 1 (agent_row)
+                    arr = np.ascontiguousarray(arr)
                     path = os.path.join(d, f"{prefix}_{n}.zarr")
                     os.makedirs(path, exist_ok=True)
                     arr.tofile(os.path.join(path, "0.0"))

@@ -527,6 +527,7 @@ def test_base_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
                              ("collr", "collected", False), ("explr", "patch_id", False)):
         got = read_zarr_v2(os.path.join(d, f"ag_{name}.zarr"))
         exp = np.stack([w[0][key][1].astype(np.float64) for w in want], axis=1)
+        exp = np.roll(exp, -1, axis=0)            # the reference's row order: agent id - 1, agent 0 in the last row (ifdb.py:504-508)
         assert got.shape == (N, T) and np.array_equal(got, np.trunc(exp) if trunc else exp), name
     got = read_zarr_v2(os.path.join(d, "res_left.zarr"))
     assert got.shape == (P, T) and np.array_equal(got, np.stack([w[1]["left"][1].astype(np.float64) for w in want], axis=1))

@@ -266,8 +266,9 @@ def test_metaprotocol_runs_sweep_as_one_batch(built_lib, tmp_path):
             ori = read_zarr_v2(os.path.join(d, "ag_ori.zarr"))
             posx = read_zarr_v2(os.path.join(d, "ag_posx.zarr"))
             assert ori.shape == (12, 20) and posx.shape == (12, 20)
-            assert np.array_equal(ori[:, -1], st["theta"][b].astype(np.float64))          # the replicate's own trajectory
-            assert np.array_equal(posx[:, -1], np.trunc(st["x"][b].astype(np.float64)))   # int(position), ifdb.py:83-84
+            # the replicate's own trajectory, in the reference's row order (agent id - 1: agent 0 in the last row)
+            assert np.array_equal(ori[:, -1], np.roll(st["theta"][b].astype(np.float64), -1))
+            assert np.array_equal(posx[:, -1], np.trunc(np.roll(st["x"][b].astype(np.float64), -1)))   # int(position), ifdb.py:83-84
             if float(saved["VF_ALP0"]) == 0 and float(saved["VF_BET0"]) == 0:
                 zero_gain.append(ori)
     # replicates with ALP0 = BET0 = 0 only relax their speed towards V0: their headings never change
@@ -394,7 +395,10 @@ def test_simulation_writes_reference_output_folder(built_lib, tmp_path):
         assert read_zarr_v2(os.path.join(d, name + ".zarr")).shape == (3, 15), name
     assert os.path.isfile(os.path.join(d, "env_params.json"))
     a = sim.engine.get_agents()
-    assert np.array_equal(read_zarr_v2(os.path.join(d, "ag_w.zarr"))[:, -1], a["w"][0].astype(np.float64))
+    from abm_b200.recorder import agent_row
+    w_rows = read_zarr_v2(os.path.join(d, "ag_w.zarr"))[:, -1]
+    assert np.array_equal(w_rows, np.roll(a["w"][0].astype(np.float64), -1))      # agent i in row i - 1, agent 0 in the last
+    assert agent_row(0, 10) == 9 and agent_row(3, 10) == 2 and w_rows[agent_row(3, 10)] == np.float64(a["w"][0][3])
 
 
 def test_tiled_swarm_matches_single_gpu_if_two_gpus(built_lib):
@@ -439,7 +443,7 @@ def test_recorder_writes_reference_zarr_layout(built_lib, tmp_path):
         assert json.load(open(os.path.join(d, "env_params.json")))["T"] == T
         for name, key, trunc in (("posx", "x", True), ("posy", "y", True), ("ori", "theta", False), ("vel", "vel", False)):
             got = read_zarr_v2(os.path.join(d, f"ag_{name}.zarr"))
-            want = np.stack([e[key][b].astype(np.float64) for e in expect], axis=1)
+            want = np.roll(np.stack([e[key][b].astype(np.float64) for e in expect], axis=1), -1, axis=0)   # row = agent id - 1
             assert np.array_equal(got, np.trunc(want) if trunc else want), name
         assert not read_zarr_v2(os.path.join(d, "ag_mode.zarr")).any()
     eng.close()
