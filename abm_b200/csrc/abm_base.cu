@@ -469,9 +469,15 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
   float* rad = py + N;                                                   // radii (own: heterogeneous agents)
   const uint32_t tau_mask = (a.Tau >= 32) ? 0xffffffffu : ((1u << a.Tau) - 1u);
   const size_t a0 = (size_t)b * N;
+  int* work = reinterpret_cast<int*>(rad + N);                           // [N] hit agents, then: front count, back count, next
+  // "exploits at the start of the phase" as its own read-only array: ov[] of a hit agent is written by ITS warp
+  // (-> collide, never to or from exploit) while other warps test their hitting agents for exploit -- the answer cannot
+  // change, but reading it from ov[] was a read/write hazard between warps (racecheck)
+  int* ex = work + N + 4;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     ov[i] = a.ag.override_mode[a0 + i]; md[i] = a.ag.mode[a0 + i]; th[i] = a.ag.theta[a0 + i]; col[i] = 0;
     px[i] = a.ag.x[a0 + i]; py[i] = a.ag.y[a0 + i]; rad[i] = (float)base_radius_of(a, a0 + i);
+    ex[i] = (ov[i] == OV_EXPLOIT) ? 1 : 0;
   }
   __syncthreads();
   // pygame's collide_circle (documented): circles of the sprites' radii (+2 each, sims.py:739-752) around the rect
@@ -487,7 +493,6 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
   // of fp64 latency, and with a fixed assignment the CTA waited at the final barrier for its unluckiest warp (more than
   // half of the kernel's warp time)
   // (agents hit by several others -- the long chains -- are listed from the front and taken first, the rest from the back)
-  int* work = reinterpret_cast<int*>(rad + N);                           // [N] hit agents, then: front count, back count, next
   if (threadIdx.x == 0) { work[N] = 0; work[N + 1] = 0; work[N + 2] = 0; }
   __syncthreads();
   for (int a2 = wib; a2 < N; a2 += wpb) {
@@ -508,7 +513,7 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= n_work) break;
     const int a2 = work[slot < n_front ? slot : N - 1 - (slot - n_front)];
-    const bool expl2 = ov[a2] == OV_EXPLOIT;                               // (fixed during the phase)
+    const bool expl2 = ex[a2] != 0;                                      // (fixed during the phase)
     const double r = rad[a2];                                              // the hit agent is the focal agent of its LIDAR field
     const int R = base_res_of(a, a0 + a2), h = R / 2;                      // ... at its own resolution
     const double lin_step = base_lin_step_of(a, a0 + a2);
@@ -519,7 +524,7 @@ __device__ __forceinline__ void base_collision_replicate(const BaseKernelArgs& a
       while (hitm) {                                                       // the agents a1 that hit a2, in group order
         const int a1 = j0 + __ffs(hitm) - 1;
         hitm &= hitm - 1;
-        const bool expl1 = ov[a1] == OV_EXPLOIT;
+        const bool expl1 = ex[a1] != 0;
         // ---- agent_agent_collision_proximity(a1, a2) (sims.py:421-468) ----
         bool do_coll = true;
         if (a.ghost_mode) do_coll = !expl2 && !expl1;
@@ -861,7 +866,8 @@ __device__ __forceinline__ void base_agents_block(const BaseKernelArgs& a, int b
 // grids one after the other (each with its own launch and its own tail).
 // ---------------------------------------------------------------------------------------
 size_t base_step_smem_bytes(int N, int W, int warps) {
-  return warp_field_bytes(N, W) * warps + 8 * sizeof(int) * (size_t)N + 4 * sizeof(int) + 2 * sizeof(int) * (size_t)N;
+  // the collision phase's layout (base_collision_replicate: the warps' fields, nine per-agent arrays, 4 counters) + N spare
+  return warp_field_bytes(N, W) * warps + 9 * sizeof(int) * (size_t)N + 4 * sizeof(int) + sizeof(int) * (size_t)N;
 }
 
 template <bool MASK2>
@@ -913,7 +919,7 @@ static int base_smem_optin() {
 
 void launch_base_collisions(const BaseKernelArgs& a, cudaStream_t stream) {
   const int smem_max = base_smem_optin();
-  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 8 * sizeof(int) * (size_t)a.N + 4 * sizeof(int);
+  const size_t per_warp = warp_field_bytes(a.N, a.W), shared = 9 * sizeof(int) * (size_t)a.N + 4 * sizeof(int);
   int warps = 16;
   while (warps > 1 && (warps / 2 >= a.N || per_warp * warps + shared > (size_t)smem_max)) warps >>= 1;
   const size_t smem = per_warp * warps + shared;
