@@ -67,3 +67,34 @@ def test_follow_lines_restatement_equals_the_reference_expression(x, y, ori, vel
         oc = 0.5 * (m2 - m1) if np.sign(vel) else 0
         want = oc if m1 != m2 else (0.01 if m1 != 0 else 0)
     assert abs(got - want) <= 1e-12
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.integers(1, 40), st.integers(1, 70), st.integers(1, 33), st.integers(0, 2**31 - 1))
+def test_zarr_v2_directories_round_trip_and_agent_rows(n_agents, T, chunk, seed):
+    """The recorders write zarr-format-2 directories without the zarr package: the minimal reader returns what the writer
+    laid out, chunk by chunk (ragged last chunk included); `agent_row` is the reference's row rule (agent id - 1, so agent
+    0 lands in the last row, ifdb.py:504-508) -- a bijection of the agents onto the rows."""
+    import json
+    import os
+    import tempfile
+    from abm_b200.recorder import _write_zarray, agent_row, read_zarr_v2
+    rng = np.random.default_rng(seed)
+    data = rng.normal(size=(n_agents, T))
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ag_ori.zarr")
+        os.makedirs(path)
+        _write_zarray(path, (n_agents, T), (n_agents, chunk))
+        for k in range(-(-T // chunk)):
+            blk = np.zeros((n_agents, chunk))
+            w = min(chunk, T - k * chunk)
+            blk[:, :w] = np.roll(data, -1, axis=0)[:, k * chunk:k * chunk + w]      # row = agent id - 1
+            blk.tofile(os.path.join(path, f"0.{k}"))
+        meta = json.load(open(os.path.join(path, ".zarray")))
+        assert meta["zarr_format"] == 2 and meta["shape"] == [n_agents, T] and meta["dtype"] == "<f8"
+        got = read_zarr_v2(path)
+    assert got.shape == (n_agents, T)
+    rows = [agent_row(i, n_agents) for i in range(n_agents)]
+    assert sorted(rows) == list(range(n_agents)) and rows[0] == n_agents - 1
+    for i in range(n_agents):
+        assert np.array_equal(got[rows[i]], data[i])
