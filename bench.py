@@ -625,6 +625,8 @@ def main():
             swarm = swarm_arm(VFEngine, local_rank, rank, world, dist)
         except Exception as exc:                                      # noqa: BLE001
             print(f"bench.py: swarm arm failed on rank {rank}: {exc!r}", file=sys.stderr, flush=True)
+            if world > 1:       # the other ranks may be inside the arm's exchange: fail fast rather than leave them waiting
+                raise
             swarm = {"error": repr(exc)}
     others = None
     if world == 1 and os.environ.get("ABM_BENCH_OTHER_CONFIGS", "1") != "0":
